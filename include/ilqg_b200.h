@@ -1,0 +1,116 @@
+/* ilqg_b200.h — C ABI of the B200-native iLQG hot path.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers and sizes, returns an int status
+ * (0 = ok) and never exits the process (the reference returns void and lets MuJoCo abort,
+ * /root/reference/inc/mjderivative.h:7).  No torch / C++ types cross this boundary.
+ *
+ * Two flavours of each compute call:
+ *   *_dev  : all buffers are DEVICE pointers on the handle's GPU; stream-ordered on `stream`
+ *            (a cudaStream_t passed as void*; NULL = legacy default stream); asynchronous.
+ *   *_host : all buffers are HOST pointers; the call copies in, launches, copies out and
+ *            synchronises.  This is what the drop-in `calcMJDerivatives` / `mj_step` wrappers
+ *            in ilqg-mujoco_b200/host/ use.
+ * There is no CPU implementation behind these calls: without a CUDA device they fail with
+ * ILQG_ERR_CUDA.
+ *
+ * Layouts are the reference's:
+ *   deriv (per knot, ND = nv*(2nv+nu) + 2nv + nu doubles, /root/reference/inc/differentiator.h:56-61):
+ *     [0, nv^2)                 d qacc_j / d qpos_i   at i + j*nv   (/root/reference/src/mjderivative.cpp:202)
+ *     [nv^2, 2nv^2)             d qacc_j / d qvel_i   at i + j*nv   (:138)
+ *     [2nv^2, 2nv^2+nv*nu)      d qacc_j / d ctrl_i   at i + j*nu   (:107)
+ *     then dg/dqpos[nv], dg/dqvel[nv], dg/dctrl[nu]   (:174,:120,:88; forward differences)
+ *   knot inputs: qpos[nq], qvel[nv], ctrl[nu], qacc_warmstart[nv] — the fields cpMjData copies
+ *     (/root/reference/src/util.cpp:4-13) that the dynamics read (qfrc_applied/xfrc_applied are
+ *     always zero in the reference and are not supported).
+ */
+#ifndef ILQG_B200_H
+#define ILQG_B200_H
+
+#include "ilqg_model.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    ILQG_OK = 0,
+    ILQG_ERR_ARG = 1,         /* null pointer / bad size */
+    ILQG_ERR_MODEL = 2,       /* malformed model or MJCF outside the supported subset */
+    ILQG_ERR_IO = 3,
+    ILQG_ERR_CUDA = 4,        /* CUDA runtime error (text via ilqg_last_error) */
+    ILQG_ERR_UNSUPPORTED = 5, /* no kernel instantiation for this model's shape */
+    ILQG_ERR_NONFINITE = 6    /* a rollout produced NaN/Inf (per-knot flags in `status`) */
+};
+
+typedef struct ilqg_handle_s* ilqg_handle;
+
+/* ---- model compilation (host only; replaces mj_loadXML, /root/reference/cmd/basic.cpp:123) */
+int ilqg_compile_mjcf(const char* xml_path, ilqg_model* out, char* err, int errlen);
+int ilqg_compile_mjcf_string(const char* xml, ilqg_model* out, char* err, int errlen);
+int ilqg_model_save(const char* path, const ilqg_model* m);
+int ilqg_model_load(const char* path, ilqg_model* m);
+int ilqg_model_sizeof(void);
+
+/* ---- GPU-resident model (the role of mjModel* in every reference call) */
+int ilqg_create(const ilqg_model* m, int device, ilqg_handle* out);
+int ilqg_destroy(ilqg_handle h);
+const char* ilqg_last_error(ilqg_handle h); /* h may be NULL: last creation error */
+int ilqg_deriv_size(const ilqg_model* m);   /* ND */
+
+/* ---- FD options: the file-static tunables of /root/reference/src/mjderivative.cpp:36-39 */
+typedef struct ilqg_fd_opts {
+    double eps;   /* 1e-6 */
+    int niter;    /* 30: solver iterations pinned during FD (:241) */
+    int nwarmup;  /* 3: centre-point repetitions (:67) */
+} ilqg_fd_opts;
+void ilqg_fd_opts_default(ilqg_fd_opts* o);
+
+/* ---- device-evaluable step cost.  The reference's stepCostFn_t is a host function pointer
+ *      (/root/reference/inc/mjderivative.h:5) that reads qpos/qvel/ctrl only; on the GPU the
+ *      same role is played by  g = sum_i a2_i z_i^2 + a1_i z_i  over z = (qpos, qvel, ctrl).
+ *      It covers /root/reference/inc/inverted_pendulum/cost.h:7-17 (q2={1,10}, v2={1,10}, u2={1})
+ *      and the test's cost /root/reference/tst/test_derivatives.cpp:16-20 (q1={1}).  Terms are
+ *      accumulated qpos, then qvel, then ctrl, index ascending, quadratic before linear. */
+typedef struct ilqg_cost {
+    double q2[ILQG_MAXQ], q1[ILQG_MAXQ];
+    double v2[ILQG_MAXV], v1[ILQG_MAXV];
+    double u2[ILQG_MAXU], u1[ILQG_MAXU];
+} ilqg_cost;
+
+/* ---- FD linearisation of all knots in one launch.
+ * Replaces calcMJDerivatives (/root/reference/inc/mjderivative.h:7, body
+ * /root/reference/src/mjderivative.cpp:43-255) called once per knot by
+ * Differentiator::updateDerivatives (/root/reference/inc/differentiator.h:87).
+ *   qpos[nknots*nq], qvel[nknots*nv], ctrl[nknots*nu], warmstart[nknots*nv]  (knot-major)
+ *   cost      : NULL -> the 2nv+nu cost-gradient entries of deriv are left untouched
+ *               (host wrappers fill them with the caller's stepCostFn)
+ *   deriv     : [nknots*ND] out
+ *   qacc_out  : optional [nknots*nv] centre accelerations after warm-up (the value the reference
+ *               leaves in the workers' qacc_warmstart); may be NULL
+ *   status    : optional [nknots] out; 0 ok, ILQG_ERR_NONFINITE
+ */
+int ilqg_fd_batch_dev(ilqg_handle h, int nknots, const double* qpos, const double* qvel, const double* ctrl,
+                      const double* warmstart, const ilqg_cost* cost, const ilqg_fd_opts* opts, double* deriv,
+                      double* qacc_out, int* status, void* stream);
+int ilqg_fd_batch_host(ilqg_handle h, int nknots, const double* qpos, const double* qvel, const double* ctrl,
+                       const double* warmstart, const ilqg_cost* cost, const ilqg_fd_opts* opts, double* deriv,
+                       double* qacc_out, int* status);
+
+/* ---- forward dynamics / stepping of n independent states.
+ * ilqg_forward_*: mj_forward (/root/reference/src/mjderivative.cpp:64): qacc[n*nv] out; warmstart in/out.
+ * ilqg_step_*   : nsteps x mj_step (/root/reference/inc/ilqr.h:86,128): qpos, qvel, warmstart in/out;
+ *                 ctrl is held constant; qacc (optional) receives the last step's acceleration.
+ * iterations/tolerance are the model's (the XML's), as in the reference's rollouts. */
+int ilqg_forward_batch_dev(ilqg_handle h, int n, const double* qpos, const double* qvel, const double* ctrl,
+                           double* warmstart, double* qacc, void* stream);
+int ilqg_forward_batch_host(ilqg_handle h, int n, const double* qpos, const double* qvel, const double* ctrl,
+                            double* warmstart, double* qacc);
+int ilqg_step_batch_dev(ilqg_handle h, int n, int nsteps, double* qpos, double* qvel, const double* ctrl,
+                        double* warmstart, double* qacc, void* stream);
+int ilqg_step_batch_host(ilqg_handle h, int n, int nsteps, double* qpos, double* qvel, const double* ctrl,
+                         double* warmstart, double* qacc);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

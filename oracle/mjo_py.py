@@ -1,0 +1,77 @@
+"""ctypes view of the CPU ORACLE (oracle/libmjo.so).  Test infrastructure only:
+import it from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs."""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+MODEL_BYTES = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "libmjo.so")
+        if not os.path.exists(path):
+            raise RuntimeError("oracle/libmjo.so missing: run `make -C oracle` (or __graft_entry__.build())")
+        _LIB = C.CDLL(path)
+        _LIB.mjo_make_data.restype = C.c_void_p
+        _LIB.mjo_energy.restype = C.c_double
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Model:
+    """Opaque ilqg_model table loaded from a .ilqgm file, plus the few sizes tests need."""
+
+    def __init__(self, path):
+        self.buf = np.fromfile(path, dtype=np.uint8)
+        ints = self.buf[:40].view(np.int32)
+        assert ints[0] == 0x494C5147, "bad model magic"
+        self.nq, self.nv, self.nu, self.nbody, self.njnt, self.ngeom, self.npair = (int(x) for x in ints[2:9])
+        self.nd = self.nv * (2 * self.nv + self.nu) + 2 * self.nv + self.nu
+        self.timestep = float(self.buf[40:48].view(np.float64)[0])
+
+    @property
+    def ptr(self):
+        return self.buf.ctypes.data_as(C.c_void_p)
+
+
+def fd_batch(m, qpos, qvel, ctrl, warm, cost=None, eps=1e-6, niter=30, nwarmup=3, nthreads=0):
+    n = qpos.shape[0]
+    qpos = np.ascontiguousarray(qpos, np.float64); qvel = np.ascontiguousarray(qvel, np.float64)
+    ctrl = np.ascontiguousarray(ctrl, np.float64); warm = np.ascontiguousarray(warm, np.float64)
+    deriv = np.zeros((n, m.nd)); qacc = np.zeros((n, m.nv)); fl = C.c_double(0)
+    lib().mjo_fd_batch_quad(m.ptr, n, _p(qpos), _p(qvel), _p(ctrl), _p(warm), _p(cost), C.c_double(eps), niter, nwarmup,
+                            _p(deriv), _p(qacc), nthreads, C.byref(fl))
+    return deriv, qacc, fl.value
+
+
+def step_batch(m, qpos, qvel, ctrl, warm, nsteps, nthreads=0):
+    qpos = np.array(qpos, np.float64, order="C"); qvel = np.array(qvel, np.float64, order="C")
+    ctrl = np.ascontiguousarray(ctrl, np.float64); warm = np.array(warm, np.float64, order="C")
+    n = qpos.shape[0]
+    qacc = np.zeros((n, m.nv))
+    lib().mjo_step_batch(m.ptr, n, nsteps, _p(qpos), _p(qvel), _p(ctrl), _p(warm), _p(qacc), nthreads)
+    return qpos, qvel, warm, qacc
+
+
+def forward_batch(m, qpos, qvel, ctrl, warm, nthreads=0):
+    qpos = np.ascontiguousarray(qpos, np.float64); qvel = np.ascontiguousarray(qvel, np.float64)
+    ctrl = np.ascontiguousarray(ctrl, np.float64); warm = np.array(warm, np.float64, order="C")
+    n = qpos.shape[0]
+    qacc = np.zeros((n, m.nv))
+    lib().mjo_forward_batch(m.ptr, n, _p(qpos), _p(qvel), _p(ctrl), _p(warm), _p(qacc), nthreads)
+    return qacc, warm
+
+
+def make_cost(q2=(), q1=(), v2=(), v1=(), u2=(), u1=()):
+    """ilqg_cost struct as a float64 array: q2[32] q1[32] v2[32] v1[32] u2[24] u1[24]."""
+    c = np.zeros(32 * 4 + 24 * 2)
+    for off, v in ((0, q2), (32, q1), (64, v2), (96, v1), (128, u2), (152, u1)):
+        c[off:off + len(v)] = v
+    return c

@@ -1,0 +1,192 @@
+"""ilqg-mujoco_b200 — Python view (ctypes) of the C ABI in include/ilqg_b200.h.
+
+The product is the CUDA library `libilqg_b200.so` (sources in csrc/, built by
+`__graft_entry__.build()`); this module only marshals pointers.  There is no CPU
+implementation here: if the library is missing, or no CUDA device is present, calls raise.
+The host-language mirror of the reference's classes (calcMJDerivatives / Differentiator /
+ILQR / InvertedPendulum) is C++ and lives in host/.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libilqg_b200.so")
+MODELS_DIR = os.path.join(_HERE, "models")
+
+OK, ERR_ARG, ERR_MODEL, ERR_IO, ERR_CUDA, ERR_UNSUPPORTED, ERR_NONFINITE = range(7)
+MAXQ, MAXV, MAXU = 32, 32, 24
+
+_lib = None
+
+
+class IlqgError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"ilqg error {code}: {msg}")
+        self.code = code
+
+
+def lib():
+    """Load libilqg_b200.so (fails loudly when it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(the CUDA extension is the product; there is no fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.ilqg_last_error.restype = C.c_char_p
+        L.ilqg_last_error.argtypes = [C.c_void_p]
+        L.ilqg_engine_name.restype = C.c_char_p
+        L.ilqg_engine_name.argtypes = [C.c_void_p]
+        L.ilqg_launch_count.restype = C.c_long
+        L.ilqg_launch_count.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+class FdOpts(C.Structure):
+    _fields_ = [("eps", C.c_double), ("niter", C.c_int), ("nwarmup", C.c_int)]
+
+
+def make_cost(q2=(), q1=(), v2=(), v1=(), u2=(), u1=()):
+    """struct ilqg_cost as a float64 array: q2[32] q1[32] v2[32] v1[32] u2[24] u1[24]."""
+    c = np.zeros(4 * MAXQ + 2 * MAXU)
+    for off, v in ((0, q2), (32, q1), (64, v2), (96, v1), (128, u2), (152, u1)):
+        c[off:off + len(v)] = v
+    return c
+
+
+class Model:
+    """The flat `ilqg_model` tables (opaque bytes) plus the sizes Python needs."""
+
+    def __init__(self, buf):
+        self.buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        ints = self.buf[:40].view(np.int32)
+        if ints[0] != 0x494C5147:
+            raise ValueError("not an ilqg model table")
+        self.nq, self.nv, self.nu, self.nbody, self.njnt, self.ngeom, self.npair = (int(x) for x in ints[2:9])
+        self.nd = self.nv * (2 * self.nv + self.nu) + 2 * self.nv + self.nu
+        self.timestep = float(self.buf[40:48].view(np.float64)[0])
+
+    @classmethod
+    def load(cls, path):
+        return cls(np.fromfile(path, dtype=np.uint8))
+
+    @classmethod
+    def named(cls, name):
+        """One of the compiled copies of the reference's models (inverted_pendulum, hopper, humanoid)."""
+        return cls.load(os.path.join(MODELS_DIR, name + ".ilqgm"))
+
+    @classmethod
+    def from_mjcf(cls, path):
+        n = lib().ilqg_model_sizeof()
+        buf = np.zeros(n, dtype=np.uint8)
+        err = C.create_string_buffer(512)
+        rc = lib().ilqg_compile_mjcf(path.encode(), buf.ctypes.data_as(C.c_void_p), err, 512)
+        if rc:
+            raise IlqgError(rc, err.value.decode())
+        return cls(buf)
+
+    @property
+    def ptr(self):
+        return self.buf.ctypes.data_as(C.c_void_p)
+
+
+def _hp(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _dp(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class Handle:
+    """GPU-resident compiled model (ilqg_create)."""
+
+    def __init__(self, model, device=0):
+        self.model = model
+        self._h = C.c_void_p()
+        rc = lib().ilqg_create(model.ptr, int(device), C.byref(self._h))
+        if rc:
+            raise IlqgError(rc, lib().ilqg_last_error(None).decode())
+
+    def close(self):
+        if self._h:
+            lib().ilqg_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc:
+            raise IlqgError(rc, lib().ilqg_last_error(self._h).decode())
+
+    @property
+    def engine(self):
+        return lib().ilqg_engine_name(self._h).decode()
+
+    @property
+    def launches(self):
+        return int(lib().ilqg_launch_count(self._h))
+
+    # ---- host-pointer flavour (numpy) ------------------------------------------------
+    def fd_batch_host(self, qpos, qvel, ctrl, warm=None, cost=None, opts=None, deriv=None):
+        m = self.model
+        qpos = np.ascontiguousarray(qpos, np.float64).reshape(-1, m.nq)
+        n = qpos.shape[0]
+        qvel = np.ascontiguousarray(qvel, np.float64).reshape(n, m.nv)
+        ctrl = np.ascontiguousarray(ctrl, np.float64).reshape(n, m.nu)
+        warm = None if warm is None else np.ascontiguousarray(warm, np.float64).reshape(n, m.nv)
+        if deriv is None:
+            deriv = np.zeros((n, m.nd))
+        qacc = np.zeros((n, m.nv))
+        status = np.zeros(n, np.int32)
+        rc = lib().ilqg_fd_batch_host(self._h, n, _hp(qpos), _hp(qvel), _hp(ctrl), _hp(warm), _hp(cost),
+                                      C.byref(opts) if opts is not None else None, _hp(deriv), _hp(qacc), _hp(status))
+        if rc and rc != ERR_NONFINITE:
+            self._check(rc)
+        return deriv, qacc, status
+
+    def forward_batch_host(self, qpos, qvel, ctrl, warm=None):
+        m = self.model
+        qpos = np.ascontiguousarray(qpos, np.float64).reshape(-1, m.nq)
+        n = qpos.shape[0]
+        qvel = np.ascontiguousarray(qvel, np.float64).reshape(n, m.nv)
+        ctrl = np.ascontiguousarray(ctrl, np.float64).reshape(n, m.nu)
+        warm = np.zeros((n, m.nv)) if warm is None else np.array(warm, np.float64, order="C").reshape(n, m.nv)
+        qacc = np.zeros((n, m.nv))
+        self._check(lib().ilqg_forward_batch_host(self._h, n, _hp(qpos), _hp(qvel), _hp(ctrl), _hp(warm), _hp(qacc)))
+        return qacc, warm
+
+    def step_batch_host(self, qpos, qvel, ctrl, warm=None, nsteps=1):
+        m = self.model
+        qpos = np.array(qpos, np.float64, order="C").reshape(-1, m.nq)
+        n = qpos.shape[0]
+        qvel = np.array(qvel, np.float64, order="C").reshape(n, m.nv)
+        ctrl = np.ascontiguousarray(ctrl, np.float64).reshape(n, m.nu)
+        warm = np.zeros((n, m.nv)) if warm is None else np.array(warm, np.float64, order="C").reshape(n, m.nv)
+        qacc = np.zeros((n, m.nv))
+        self._check(lib().ilqg_step_batch_host(self._h, n, int(nsteps), _hp(qpos), _hp(qvel), _hp(ctrl), _hp(warm), _hp(qacc)))
+        return qpos, qvel, warm, qacc
+
+    # ---- device-pointer flavour (torch CUDA tensors, float64, contiguous) ---------------
+    def fd_batch_dev(self, qpos, qvel, ctrl, warm, deriv, qacc=None, status=None, cost=None, opts=None, stream=None):
+        n = qpos.shape[0]
+        self._check(lib().ilqg_fd_batch_dev(self._h, n, _dp(qpos), _dp(qvel), _dp(ctrl), _dp(warm), _hp(cost),
+                                            C.byref(opts) if opts is not None else None, _dp(deriv), _dp(qacc), _dp(status),
+                                            C.c_void_p(stream) if stream else None))
+
+    def step_batch_dev(self, qpos, qvel, ctrl, warm, qacc=None, nsteps=1, stream=None):
+        n = qpos.shape[0]
+        self._check(lib().ilqg_step_batch_dev(self._h, n, int(nsteps), _dp(qpos), _dp(qvel), _dp(ctrl), _dp(warm), _dp(qacc),
+                                              C.c_void_p(stream) if stream else None))
+
+    def forward_batch_dev(self, qpos, qvel, ctrl, warm, qacc, stream=None):
+        n = qpos.shape[0]
+        self._check(lib().ilqg_forward_batch_dev(self._h, n, _dp(qpos), _dp(qvel), _dp(ctrl), _dp(warm), _dp(qacc),
+                                                 C.c_void_p(stream) if stream else None))

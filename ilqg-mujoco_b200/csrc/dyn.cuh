@@ -1,0 +1,840 @@
+// dyn.cuh — per-rollout fp64 forward dynamics for small kinematic trees, one CUDA thread per rollout.
+//
+// This is the device-side replacement of what the reference reaches through
+// mj_forward / mj_forwardSkip / mj_step (/root/reference/src/mjderivative.cpp:64,68,92,124,178;
+// /root/reference/inc/ilqr.h:86,128).  It is written for sm_100a only, from the pipeline
+// description in SURVEY.md Appendix A — not from the CPU oracle's code: every loop over bodies,
+// joints, dofs, geoms and collision pairs is unrolled at compile time over a Topo_* description
+// (topo_gen.h) so the mjData-equivalent of a rollout (frames, spatial inertias, motion axes, mass
+// matrix, factors) lives in registers; only the variable-length constraint rows go to local memory.
+// Model constants arrive in DevModel<T> as a __grid_constant__ kernel parameter (constant bank).
+//
+// Because every perturbed evaluation recomputes all stages from its own inputs, the reference's
+// stage skipping (mjSTAGE_POS / mjSTAGE_VEL) needs no special handling: re-evaluating a skipped
+// stage from unperturbed inputs reproduces the centre's values exactly.  Only the solver warm start
+// is carried from the centre (mjderivative.cpp:75,91).
+#pragma once
+#include <cuda_runtime.h>
+#include <type_traits>
+
+#include "../../include/ilqg_b200.h"
+#include "topo_gen.h"
+
+namespace ilqg {
+
+#define ILQG_MINVAL 1e-15
+#define DEV __device__ __forceinline__
+
+template <int I, int N, class F>
+DEV void sfor(F&& f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        sfor<I + 1, N>(f);
+    }
+}
+// descending: I = N-1 ... LO
+template <int I, int LO, class F>
+DEV void sfor_down(F&& f) {
+    if constexpr (I >= LO) {
+        f(std::integral_constant<int, I>{});
+        sfor_down<I - 1, LO>(f);
+    }
+}
+#define IDX(x) (decltype(x)::value)
+
+__host__ __device__ constexpr int tri(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
+__host__ __device__ constexpr int nz(int n) { return n > 0 ? n : 1; }
+
+// ------------------------------------------------------------------ model constants (kernel parameter)
+template <class T>
+struct DevModel {
+    double timestep, gravity[3], tolerance, meaninertia;
+    int iterations, ls_iterations, integrator, pad;
+    double body_pos[T::NBODY][3], body_quat[T::NBODY][4], body_mass[T::NBODY], body_ipos[T::NBODY][3];
+    double body_inertia[T::NBODY][6], body_invw[T::NBODY];
+    double jnt_pos[T::NJNT][3], jnt_axis[T::NJNT][3], jnt_range[T::NJNT][2], jnt_stiffness[T::NJNT], jnt_margin[T::NJNT];
+    double jnt_solref[T::NJNT][2], jnt_solimp[T::NJNT][5];
+    double qpos0[T::NQ], qpos_spring[T::NQ];
+    double dof_armature[T::NV], dof_damping[T::NV], dof_invw[T::NV];
+    double geom_size[T::NGEOM][2], geom_pos[T::NGEOM][3], geom_axis[T::NGEOM][3];
+    double pair_margin[nz(T::NPAIR)], pair_mu[nz(T::NPAIR)], pair_solref[nz(T::NPAIR)][2], pair_solimp[nz(T::NPAIR)][5];
+    double act_gear[nz(T::NU)], act_range[nz(T::NU)][2];
+};
+
+// host: fill from the flat tables; returns false if the tables do not have this topology
+template <class T>
+bool dev_model_from_tables(const ilqg_model& s, DevModel<T>& d) {
+    if (s.nq != T::NQ || s.nv != T::NV || s.nu != T::NU || s.nbody != T::NBODY || s.njnt != T::NJNT || s.ngeom != T::NGEOM ||
+        s.npair != T::NPAIR)
+        return false;
+    for (int b = 0; b < T::NBODY; b++)
+        if (s.body_parentid[b] != T::body_parent(b) || s.body_rootid[b] != T::body_root(b) || s.body_jntadr[b] != T::body_jntadr(b) ||
+            s.body_jntnum[b] != T::body_jntnum(b) || s.body_dofadr[b] != T::body_dofadr(b) || s.body_dofnum[b] != T::body_dofnum(b))
+            return false;
+    for (int j = 0; j < T::NJNT; j++)
+        if (s.jnt_type[j] != T::jnt_type(j) || s.jnt_bodyid[j] != T::jnt_body(j) || s.jnt_qposadr[j] != T::jnt_qposadr(j) ||
+            s.jnt_dofadr[j] != T::jnt_dofadr(j) || (s.jnt_limited[j] != 0) != (T::jnt_limited(j) != 0) ||
+            (s.jnt_stiffness[j] != 0 && !T::jnt_hasspring(j)))
+            return false;
+    for (int i = 0; i < T::NV; i++)
+        if (s.dof_bodyid[i] != T::dof_body(i) || s.dof_jntid[i] != T::dof_jnt(i) || s.dof_parentid[i] != T::dof_parent(i)) return false;
+    for (int g = 0; g < T::NGEOM; g++)
+        if (s.geom_type[g] != T::geom_type(g) || s.geom_bodyid[g] != T::geom_body(g)) return false;
+    for (int p = 0; p < T::NPAIR; p++)
+        if (s.pair_geom1[p] != T::pair_g1(p) || s.pair_geom2[p] != T::pair_g2(p) || s.pair_condim[p] != T::pair_condim(p)) return false;
+    for (int u = 0; u < T::NU; u++)
+        if (s.act_dofid[u] != T::act_dof(u) || (s.act_ctrllimited[u] != 0) != (T::act_limited(u) != 0)) return false;
+    bool damped = false;
+    for (int i = 0; i < T::NV; i++) damped |= s.dof_damping[i] > 0;
+    if (damped && !T::ANY_DAMPING) return false;
+
+    d.timestep = s.timestep;
+    for (int k = 0; k < 3; k++) d.gravity[k] = s.gravity[k];
+    d.tolerance = s.tolerance;
+    d.meaninertia = s.meaninertia;
+    d.iterations = s.iterations;
+    d.ls_iterations = s.ls_iterations;
+    d.integrator = s.integrator;
+    d.pad = 0;
+    for (int b = 0; b < T::NBODY; b++) {
+        for (int k = 0; k < 3; k++) { d.body_pos[b][k] = s.body_pos[b][k]; d.body_ipos[b][k] = s.body_ipos[b][k]; }
+        for (int k = 0; k < 4; k++) d.body_quat[b][k] = s.body_quat[b][k];
+        for (int k = 0; k < 6; k++) d.body_inertia[b][k] = s.body_inertia[b][k];
+        d.body_mass[b] = s.body_mass[b];
+        d.body_invw[b] = s.body_invweight0[b][0];
+    }
+    for (int j = 0; j < T::NJNT; j++) {
+        for (int k = 0; k < 3; k++) { d.jnt_pos[j][k] = s.jnt_pos[j][k]; d.jnt_axis[j][k] = s.jnt_axis[j][k]; }
+        for (int k = 0; k < 2; k++) { d.jnt_range[j][k] = s.jnt_range[j][k]; d.jnt_solref[j][k] = s.jnt_solref[j][k]; }
+        for (int k = 0; k < 5; k++) d.jnt_solimp[j][k] = s.jnt_solimp[j][k];
+        d.jnt_stiffness[j] = s.jnt_stiffness[j];
+        d.jnt_margin[j] = s.jnt_margin[j];
+    }
+    for (int i = 0; i < T::NQ; i++) { d.qpos0[i] = s.qpos0[i]; d.qpos_spring[i] = s.qpos_spring[i]; }
+    for (int i = 0; i < T::NV; i++) { d.dof_armature[i] = s.dof_armature[i]; d.dof_damping[i] = s.dof_damping[i]; d.dof_invw[i] = s.dof_invweight0[i]; }
+    for (int g = 0; g < T::NGEOM; g++) {
+        d.geom_size[g][0] = s.geom_size[g][0];
+        d.geom_size[g][1] = s.geom_size[g][1];
+        for (int k = 0; k < 3; k++) d.geom_pos[g][k] = s.geom_pos[g][k];
+        const double* q = s.geom_quat[g];  // local +z axis of the geom in the body frame (third column of its rotation)
+        d.geom_axis[g][0] = 2 * (q[1] * q[3] + q[0] * q[2]);
+        d.geom_axis[g][1] = 2 * (q[2] * q[3] - q[0] * q[1]);
+        d.geom_axis[g][2] = q[0] * q[0] - q[1] * q[1] - q[2] * q[2] + q[3] * q[3];
+    }
+    for (int p = 0; p < T::NPAIR; p++) {
+        d.pair_margin[p] = s.pair_margin[p];
+        d.pair_mu[p] = s.pair_friction[p];
+        for (int k = 0; k < 2; k++) d.pair_solref[p][k] = s.pair_solref[p][k];
+        for (int k = 0; k < 5; k++) d.pair_solimp[p][k] = s.pair_solimp[p][k];
+    }
+    for (int u = 0; u < T::NU; u++) {
+        d.act_gear[u] = s.act_gear[u];
+        d.act_range[u][0] = s.act_ctrlrange[u][0];
+        d.act_range[u][1] = s.act_ctrlrange[u][1];
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------ small math
+struct V3 { double x, y, z; };
+DEV V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+DEV V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+DEV V3 operator*(double s, V3 a) { return {s * a.x, s * a.y, s * a.z}; }
+DEV double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+DEV V3 cross(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+DEV V3 ld3(const double* p) { return {p[0], p[1], p[2]}; }
+DEV V3 normalized(V3 a) {
+    double n = sqrt(dot(a, a));
+    if (n < ILQG_MINVAL) return {1, 0, 0};
+    double r = 1.0 / n;
+    return {a.x * r, a.y * r, a.z * r};
+}
+struct Q4 { double w, x, y, z; };
+DEV Q4 qmul(Q4 a, Q4 b) {
+    return {a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z, a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y,
+            a.w * b.y - a.x * b.z + a.y * b.w + a.z * b.x, a.w * b.z + a.x * b.y - a.y * b.x + a.z * b.w};
+}
+DEV Q4 qnormalized(Q4 q) {
+    double n = sqrt(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
+    if (n < ILQG_MINVAL) return {1, 0, 0, 0};
+    double r = 1.0 / n;
+    return {q.w * r, q.x * r, q.y * r, q.z * r};
+}
+struct M3 { V3 r0, r1, r2; };  // rows
+DEV M3 q2m(Q4 q) {
+    double w = q.w, x = q.x, y = q.y, z = q.z;
+    return {{w * w + x * x - y * y - z * z, 2 * (x * y - w * z), 2 * (x * z + w * y)},
+            {2 * (x * y + w * z), w * w - x * x + y * y - z * z, 2 * (y * z - w * x)},
+            {2 * (x * z - w * y), 2 * (y * z + w * x), w * w - x * x - y * y + z * z}};
+}
+DEV V3 mulv(const M3& R, V3 v) { return {dot(R.r0, v), dot(R.r1, v), dot(R.r2, v)}; }
+DEV V3 col(const M3& R, int k) { return k == 0 ? V3{R.r0.x, R.r1.x, R.r2.x} : k == 1 ? V3{R.r0.y, R.r1.y, R.r2.y} : V3{R.r0.z, R.r1.z, R.r2.z}; }
+DEV double clampd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
+// spatial vectors: [angular; linear] about the tree's centre of mass
+struct S6 { V3 w, v; };
+DEV S6 operator+(S6 a, S6 b) { return {a.w + b.w, a.v + b.v}; }
+DEV S6 operator*(double s, S6 a) { return {s * a.w, s * a.v}; }
+DEV double dot(S6 a, S6 b) { return dot(a.w, b.w) + dot(a.v, b.v); }
+DEV S6 cross_motion(S6 vel, S6 x) { return {cross(vel.w, x.w), cross(vel.w, x.v) + cross(vel.v, x.w)}; }
+DEV S6 cross_force(S6 vel, S6 f) { return {cross(vel.w, f.w) + cross(vel.v, f.v), cross(vel.w, f.v)}; }
+// spatial inertia about the tree com: symmetric rotational part, first moment h = m (c - com), mass
+struct Inert { double xx, yy, zz, xy, xz, yz; V3 h; double m; };
+DEV Inert operator+(const Inert& a, const Inert& b) {
+    return {a.xx + b.xx, a.yy + b.yy, a.zz + b.zz, a.xy + b.xy, a.xz + b.xz, a.yz + b.yz, a.h + b.h, a.m + b.m};
+}
+DEV S6 mul(const Inert& I, S6 s) {
+    V3 Iw = {I.xx * s.w.x + I.xy * s.w.y + I.xz * s.w.z, I.xy * s.w.x + I.yy * s.w.y + I.yz * s.w.z,
+             I.xz * s.w.x + I.yz * s.w.y + I.zz * s.w.z};
+    return {Iw + cross(I.h, s.v), I.m * s.v + cross(s.w, I.h)};
+}
+
+// ------------------------------------------------------------------ per-rollout solver inputs
+template <class T>
+struct Work {
+    static constexpr int NV = T::NV, NT = T::NV * (T::NV + 1) / 2, ME = nz(T::MAXEFC);
+    double M[NT];    // mass matrix (packed lower)
+    double L[NT];    // Cholesky factor of M, diagonal entries hold 1/L_ii
+    double fs[NV];   // qfrc_smooth
+    double as[NV];   // qacc_smooth
+    double fc[NV];   // qfrc_constraint of the last solve
+    int nefc;
+    int iters;       // Newton iterations of the last solve
+    double J[ME][NV];
+    double D[ME], aref[ME], jar[ME], jv[ME];
+};
+
+// packed Cholesky A = L L^T with reciprocal diagonal
+template <int N>
+DEV void chol_packed(const double* A, double* L) {
+    sfor<0, N>([&](auto ii) {
+        constexpr int i = IDX(ii);
+        sfor<0, i + 1>([&](auto jj) {
+            constexpr int j = IDX(jj);
+            double s = A[tri(i, j)];
+            sfor<0, j>([&](auto kk) { constexpr int k = IDX(kk); s -= L[tri(i, k)] * L[tri(j, k)]; });
+            if constexpr (i == j) {
+                if (s < ILQG_MINVAL) s = ILQG_MINVAL;
+                L[tri(i, i)] = 1.0 / sqrt(s);
+            } else
+                L[tri(i, j)] = s * L[tri(j, j)];
+        });
+    });
+}
+template <int N>
+DEV void chol_solve_packed(const double* L, double* x) {
+    sfor<0, N>([&](auto ii) {
+        constexpr int i = IDX(ii);
+        double s = x[i];
+        sfor<0, i>([&](auto kk) { constexpr int k = IDX(kk); s -= L[tri(i, k)] * x[k]; });
+        x[i] = s * L[tri(i, i)];
+    });
+    sfor_down<N - 1, 0>([&](auto ii) {
+        constexpr int i = IDX(ii);
+        double s = x[i];
+        sfor<i + 1, N>([&](auto kk) { constexpr int k = IDX(kk); s -= L[tri(k, i)] * x[k]; });
+        x[i] = s * L[tri(i, i)];
+    });
+}
+
+template <class T>
+__host__ __device__ constexpr bool dof_is_ancestor(int a, int i) {  // a is i or an ancestor of i in the dof chain
+    while (i >= 0) {
+        if (i == a) return true;
+        i = T::dof_parent(i);
+    }
+    return false;
+}
+template <class T>
+__host__ __device__ constexpr bool dof_moves_body(int dof, int body) {
+    int b = body;
+    while (b > 0) {
+        if (T::dof_body(dof) == b) return true;
+        b = T::body_parent(b);
+    }
+    return false;
+}
+
+DEV double impedance(const double* solimp, double pos, double margin) {
+    double dmin = clampd(solimp[0], 1e-4, 0.9999), dmax = clampd(solimp[1], 1e-4, 0.9999);
+    double width = solimp[2], mid = clampd(solimp[3], 1e-4, 0.9999), power = solimp[4] < 1 ? 1 : solimp[4];
+    if (dmin == dmax || width <= ILQG_MINVAL) return 0.5 * (dmin + dmax);
+    double x = fabs(pos - margin) / width;
+    if (x >= 1) return dmax;
+    if (x <= 0) return dmin;
+    double y;
+    if (power == 1) y = x;
+    else if (power == 2) y = x <= mid ? x * x / mid : 1 - (1 - x) * (1 - x) / (1 - mid);
+    else if (x <= mid) y = pow(x, power) / pow(mid, power - 1);
+    else y = 1 - pow(1 - x, power) / pow(1 - mid, power - 1);
+    return dmin + y * (dmax - dmin);
+}
+
+// regulariser R, damping B and stiffness term K*imp*(pos-margin) of one row
+// (mj_makeImpedance + mj_referenceConstraint: aref = -B*vel - kterm)
+DEV void row_params(double timestep, const double* solref, const double* solimp, double pos, double margin, double diagApprox,
+                    double& R, double& B, double& kterm) {
+    double tc = solref[0], dr = solref[1];
+    if (tc < 2 * timestep) tc = 2 * timestep;
+    double dmax = clampd(solimp[1], 1e-4, 0.9999);
+    double imp = impedance(solimp, pos, margin);
+    R = (1 - imp) / imp * diagApprox;
+    if (R < ILQG_MINVAL) R = ILQG_MINVAL;
+    double kk = dmax * dmax * tc * tc * dr * dr, bb = dmax * tc;
+    double K = 1.0 / (kk < ILQG_MINVAL ? ILQG_MINVAL : kk);
+    B = 2.0 / (bb < ILQG_MINVAL ? ILQG_MINVAL : bb);
+    kterm = K * imp * (pos - margin);
+}
+
+// contact frame from the normal and an optional tangent hint (mju_makeFrame)
+DEV void make_frame(V3 n, V3 hint, bool has_hint, V3& t1, V3& t2) {
+    V3 y = hint;
+    if (!has_hint || sqrt(dot(y, y)) < 0.5) y = (n.y < 0.5 && n.y > -0.5) ? V3{0, 1, 0} : V3{0, 0, 1};
+    y = y - dot(n, y) * n;
+    if (sqrt(dot(y, y)) < 1e-12) {
+        y = (n.y < 0.5 && n.y > -0.5) ? V3{0, 1, 0} : V3{0, 0, 1};
+        y = y - dot(n, y) * n;
+    }
+    t1 = normalized(y);
+    t2 = cross(n, t1);
+}
+
+// ------------------------------------------------------------------ the pipeline up to the constraint problem
+// Computes M, its factor, qfrc_smooth, qacc_smooth and the constraint rows (J, D, aref) for one rollout.
+template <class T>
+DEV void build_problem(const DevModel<T>& m, const double (&q)[T::NQ], const double (&qv)[T::NV], const double (&u)[nz(T::NU)],
+                       Work<T>& w) {
+    constexpr int NB = T::NBODY, NV = T::NV, NJ = T::NJNT;
+    V3 xpos[NB];
+    M3 xmat[NB];
+    Q4 xquat[NB];
+    V3 anchor[NJ], axis[NJ];
+    xpos[0] = {0, 0, 0};
+    xquat[0] = {1, 0, 0, 0};
+    xmat[0] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    // ---- mj_kinematics
+    sfor<1, NB>([&](auto bb) {
+        constexpr int b = IDX(bb), p = T::body_parent(b);
+        V3 pos;
+        Q4 quat;
+        if constexpr (p == 0) {
+            pos = ld3(m.body_pos[b]);
+            quat = {m.body_quat[b][0], m.body_quat[b][1], m.body_quat[b][2], m.body_quat[b][3]};
+        } else {
+            pos = xpos[p] + mulv(xmat[p], ld3(m.body_pos[b]));
+            quat = qmul(xquat[p], {m.body_quat[b][0], m.body_quat[b][1], m.body_quat[b][2], m.body_quat[b][3]});
+        }
+        sfor<0, T::body_jntnum(b)>([&](auto jj) {
+            constexpr int j = T::body_jntadr(b) + IDX(jj), qa = T::jnt_qposadr(j), ty = T::jnt_type(j);
+            if constexpr (ty == ILQG_JNT_FREE) {
+                pos = {q[qa], q[qa + 1], q[qa + 2]};
+                quat = qnormalized({q[qa + 3], q[qa + 4], q[qa + 5], q[qa + 6]});
+                anchor[j] = pos;
+                axis[j] = {0, 0, 1};
+            } else {
+                M3 R = q2m(quat);
+                anchor[j] = pos + mulv(R, ld3(m.jnt_pos[j]));
+                axis[j] = mulv(R, ld3(m.jnt_axis[j]));
+                double qq = q[qa] - m.qpos0[qa];
+                if constexpr (ty == ILQG_JNT_SLIDE) {
+                    pos = pos + qq * axis[j];
+                } else {
+                    double s, c;
+                    sincos(0.5 * qq, &s, &c);
+                    quat = qmul(quat, {c, m.jnt_axis[j][0] * s, m.jnt_axis[j][1] * s, m.jnt_axis[j][2] * s});
+                    pos = anchor[j] - mulv(q2m(quat), ld3(m.jnt_pos[j]));
+                }
+            }
+        });
+        quat = qnormalized(quat);
+        xpos[b] = pos;
+        xquat[b] = quat;
+        xmat[b] = q2m(quat);
+    });
+    // ---- mj_comPos: tree centres of mass, spatial inertias, motion axes
+    V3 xipos[NB], com[NB];
+    double tmass[NB];
+    sfor<1, NB>([&](auto bb) {
+        constexpr int b = IDX(bb);
+        xipos[b] = xpos[b] + mulv(xmat[b], ld3(m.body_ipos[b]));
+        if constexpr (T::body_root(b) == b) { com[b] = m.body_mass[b] * xipos[b]; tmass[b] = m.body_mass[b]; }
+        else { com[T::body_root(b)] = com[T::body_root(b)] + m.body_mass[b] * xipos[b]; tmass[T::body_root(b)] += m.body_mass[b]; }
+    });
+    sfor<1, NB>([&](auto bb) {
+        constexpr int b = IDX(bb);
+        if constexpr (T::body_root(b) == b) com[b] = (1.0 / tmass[b]) * com[b];
+    });
+    Inert cin[NB];
+    sfor<1, NB>([&](auto bb) {
+        constexpr int b = IDX(bb);
+        const M3& R = xmat[b];
+        const double* in = m.body_inertia[b];
+        // Iw = R Ib R^T
+        V3 c0 = col(R, 0), c1 = col(R, 1), c2 = col(R, 2);  // unused helper columns keep the algebra readable
+        (void)c0; (void)c1; (void)c2;
+        V3 t0 = {R.r0.x * in[0] + R.r0.y * in[3] + R.r0.z * in[4], R.r0.x * in[3] + R.r0.y * in[1] + R.r0.z * in[5],
+                 R.r0.x * in[4] + R.r0.y * in[5] + R.r0.z * in[2]};
+        V3 t1 = {R.r1.x * in[0] + R.r1.y * in[3] + R.r1.z * in[4], R.r1.x * in[3] + R.r1.y * in[1] + R.r1.z * in[5],
+                 R.r1.x * in[4] + R.r1.y * in[5] + R.r1.z * in[2]};
+        V3 t2 = {R.r2.x * in[0] + R.r2.y * in[3] + R.r2.z * in[4], R.r2.x * in[3] + R.r2.y * in[1] + R.r2.z * in[5],
+                 R.r2.x * in[4] + R.r2.y * in[5] + R.r2.z * in[2]};
+        double ms = m.body_mass[b];
+        V3 d = xipos[b] - com[T::body_root(b)];
+        double dd = dot(d, d);
+        cin[b] = {dot(t0, R.r0) + ms * (dd - d.x * d.x), dot(t1, R.r1) + ms * (dd - d.y * d.y), dot(t2, R.r2) + ms * (dd - d.z * d.z),
+                  dot(t0, R.r1) - ms * d.x * d.y, dot(t0, R.r2) - ms * d.x * d.z, dot(t1, R.r2) - ms * d.y * d.z, ms * d, ms};
+    });
+    S6 cdof[NV];
+    sfor<0, NJ>([&](auto jj) {
+        constexpr int j = IDX(jj), b = T::jnt_body(j), da = T::jnt_dofadr(j), ty = T::jnt_type(j);
+        V3 off = com[T::body_root(b)] - anchor[j];
+        if constexpr (ty == ILQG_JNT_FREE) {
+            cdof[da] = {{0, 0, 0}, {1, 0, 0}};
+            cdof[da + 1] = {{0, 0, 0}, {0, 1, 0}};
+            cdof[da + 2] = {{0, 0, 0}, {0, 0, 1}};
+            sfor<0, 3>([&](auto kk) { V3 a = col(xmat[b], IDX(kk)); cdof[da + 3 + IDX(kk)] = {a, cross(a, off)}; });
+        } else if constexpr (ty == ILQG_JNT_SLIDE) {
+            cdof[da] = {{0, 0, 0}, axis[j]};
+        } else {
+            cdof[da] = {axis[j], cross(axis[j], off)};
+        }
+    });
+    // ---- mj_comVel + mj_rne(flg_acc=0): bias forces
+    S6 cvel[NB], cdofdot[NV], cacc[NB], cfrc[NB];
+    cvel[0] = {{0, 0, 0}, {0, 0, 0}};
+    cacc[0] = {{0, 0, 0}, {-m.gravity[0], -m.gravity[1], -m.gravity[2]}};
+    sfor<1, NB>([&](auto bb) {
+        constexpr int b = IDX(bb), p = T::body_parent(b);
+        S6 cv = cvel[p];
+        S6 ca = cacc[p];
+        sfor<0, T::body_jntnum(b)>([&](auto jj) {
+            constexpr int j = T::body_jntadr(b) + IDX(jj), da = T::jnt_dofadr(j), ty = T::jnt_type(j);
+            if constexpr (ty == ILQG_JNT_FREE) {
+                sfor<0, 3>([&](auto kk) { cdofdot[da + IDX(kk)] = {{0, 0, 0}, {0, 0, 0}}; cv = cv + qv[da + IDX(kk)] * cdof[da + IDX(kk)]; });
+                sfor<3, 6>([&](auto kk) { cdofdot[da + IDX(kk)] = cross_motion(cv, cdof[da + IDX(kk)]); });
+                sfor<3, 6>([&](auto kk) { cv = cv + qv[da + IDX(kk)] * cdof[da + IDX(kk)]; });
+            } else {
+                cdofdot[da] = cross_motion(cv, cdof[da]);
+                cv = cv + qv[da] * cdof[da];
+            }
+        });
+        sfor<T::body_dofadr(b), T::body_dofadr(b) + T::body_dofnum(b)>([&](auto ii) { ca = ca + qv[IDX(ii)] * cdofdot[IDX(ii)]; });
+        cvel[b] = cv;
+        cacc[b] = ca;
+        cfrc[b] = mul(cin[b], ca) + cross_force(cv, mul(cin[b], cv));
+    });
+    sfor_down<NB - 1, 1>([&](auto bb) {
+        constexpr int b = IDX(bb), p = T::body_parent(b);
+        if constexpr (p > 0) cfrc[p] = cfrc[p] + cfrc[b];
+    });
+    // qfrc_smooth = passive - bias + actuator
+    sfor<0, NV>([&](auto ii) {
+        constexpr int i = IDX(ii), j = T::dof_jnt(i);
+        double f = -dot(cdof[i], cfrc[T::dof_body(i)]);
+        if constexpr (T::ANY_DAMPING) f -= m.dof_damping[i] * qv[i];
+        if constexpr (T::jnt_type(j) != ILQG_JNT_FREE && T::jnt_hasspring(j))
+            f -= m.jnt_stiffness[j] * (q[T::jnt_qposadr(j)] - m.qpos_spring[T::jnt_qposadr(j)]);
+        w.fs[i] = f;
+    });
+    sfor<0, T::NU>([&](auto uu) {
+        constexpr int a = IDX(uu);
+        double c = u[a];
+        if constexpr (T::act_limited(a)) c = clampd(c, m.act_range[a][0], m.act_range[a][1]);
+        w.fs[T::act_dof(a)] += m.act_gear[a] * c;
+    });
+    // ---- mj_crb + factor
+    Inert crb[NB];
+    sfor<1, NB>([&](auto bb) { crb[IDX(bb)] = cin[IDX(bb)]; });
+    sfor_down<NB - 1, 1>([&](auto bb) {
+        constexpr int b = IDX(bb), p = T::body_parent(b);
+        if constexpr (p > 0) crb[p] = crb[p] + crb[b];
+    });
+    sfor<0, NV>([&](auto ii) {
+        constexpr int i = IDX(ii);
+        S6 buf = mul(crb[T::dof_body(i)], cdof[i]);
+        sfor<0, i + 1>([&](auto jj) {
+            constexpr int j = IDX(jj);
+            if constexpr (dof_is_ancestor<T>(j, i)) w.M[tri(i, j)] = dot(cdof[j], buf);
+            else w.M[tri(i, j)] = 0;
+        });
+        w.M[tri(i, i)] += m.dof_armature[i];
+    });
+    chol_packed<NV>(w.M, w.L);
+    sfor<0, NV>([&](auto ii) { w.as[IDX(ii)] = w.fs[IDX(ii)]; });
+    chol_solve_packed<NV>(w.L, w.as);
+
+    // ---- constraint rows: joint limits, then contacts
+    int ne = 0;
+    sfor<0, NJ>([&](auto jj) {
+        constexpr int j = IDX(jj);
+        if constexpr (T::jnt_limited(j) && T::jnt_type(j) != ILQG_JNT_FREE) {
+            constexpr int da = T::jnt_dofadr(j);
+            double value = q[T::jnt_qposadr(j)];
+            sfor<0, 2>([&](auto ss) {
+                constexpr int side = 2 * IDX(ss) - 1;
+                double dist = side * (m.jnt_range[j][IDX(ss)] - value);
+                if (dist < m.jnt_margin[j]) {
+                    double R, B, kt;
+                    row_params(m.timestep, m.jnt_solref[j], m.jnt_solimp[j], dist, m.jnt_margin[j], m.dof_invw[da], R, B, kt);
+                    sfor<0, NV>([&](auto ii) { w.J[ne][IDX(ii)] = IDX(ii) == da ? -side : 0.0; });
+                    w.D[ne] = 1.0 / R;
+                    w.aref[ne] = -B * (-side * qv[da]) - kt;
+                    ne++;
+                }
+            });
+        }
+    });
+    if constexpr (T::NPAIR > 0) {
+        // geom frames
+        V3 gpos[T::NGEOM], gax[T::NGEOM];
+        sfor<0, T::NGEOM>([&](auto gg) {
+            constexpr int g = IDX(gg), b = T::geom_body(g);
+            if constexpr (b == 0) { gpos[g] = ld3(m.geom_pos[g]); gax[g] = ld3(m.geom_axis[g]); }
+            else { gpos[g] = xpos[b] + mulv(xmat[b], ld3(m.geom_pos[g])); gax[g] = mulv(xmat[b], ld3(m.geom_axis[g])); }
+        });
+        sfor<0, T::NPAIR>([&](auto pp) {
+            constexpr int p = IDX(pp), g1 = T::pair_g1(p), g2 = T::pair_g2(p), t1 = T::geom_type(g1), t2 = T::geom_type(g2);
+            constexpr int b1 = T::geom_body(g1), b2 = T::geom_body(g2), condim = T::pair_condim(p);
+            const double margin = m.pair_margin[p];
+            // emit the rows of one contact
+            auto emit = [&](double dist, V3 pos, V3 n, V3 hint, bool has_hint) {
+                V3 ta, tb;
+                make_frame(n, hint, has_hint, ta, tb);
+                double jn[NV], ja[NV], jb[NV];
+                double vn = 0, va = 0, vb = 0;
+                sfor<0, NV>([&](auto ii) {
+                    constexpr int i = IDX(ii);
+                    constexpr bool m1 = b1 > 0 && dof_moves_body<T>(i, b1), m2 = b2 > 0 && dof_moves_body<T>(i, b2);
+                    if constexpr (m1 == m2) {  // moves both bodies or neither: relative motion is zero
+                        jn[i] = 0; ja[i] = 0; jb[i] = 0;
+                    } else {
+                        constexpr int bd = m2 ? b2 : b1;
+                        V3 jp = cdof[i].v + cross(cdof[i].w, pos - com[T::body_root(bd)]);
+                        if constexpr (!m2) jp = -1.0 * jp;
+                        jn[i] = dot(n, jp);
+                        if constexpr (condim == 3) { ja[i] = dot(ta, jp); jb[i] = dot(tb, jp); va += ja[i] * qv[i]; vb += jb[i] * qv[i]; }
+                        vn += jn[i] * qv[i];
+                    }
+                });
+                double tran = m.body_invw[b1] + m.body_invw[b2];
+                if (tran < ILQG_MINVAL) tran = ILQG_MINVAL;
+                if constexpr (condim == 1) {
+                    double R, B, kt;
+                    row_params(m.timestep, m.pair_solref[p], m.pair_solimp[p], dist, margin, tran, R, B, kt);
+                    sfor<0, NV>([&](auto ii) { w.J[ne][IDX(ii)] = jn[IDX(ii)]; });
+                    w.D[ne] = 1.0 / R;
+                    w.aref[ne] = -B * vn - kt;
+                    ne++;
+                } else {
+                    const double mu = m.pair_mu[p];
+                    double R0, B, kt;
+                    // all four facets share pos/margin; R of the first facet sets the pyramid's regulariser
+                    row_params(m.timestep, m.pair_solref[p], m.pair_solimp[p], dist, margin, tran * (1 + mu * mu), R0, B, kt);
+                    double Rpy = 2 * mu * mu * R0;
+                    if (Rpy < ILQG_MINVAL) Rpy = ILQG_MINVAL;
+                    double Dpy = 1.0 / Rpy;
+                    sfor<0, 4>([&](auto kk) {
+                        constexpr int k = IDX(kk);
+                        double sg = (k % 2) ? -mu : mu;
+                        double vel = vn + sg * (k < 2 ? va : vb);
+                        sfor<0, NV>([&](auto ii) { w.J[ne][IDX(ii)] = jn[IDX(ii)] + sg * (k < 2 ? ja[IDX(ii)] : jb[IDX(ii)]); });
+                        w.D[ne] = Dpy;
+                        w.aref[ne] = -B * vel - kt;
+                        ne++;
+                    });
+                }
+            };
+            auto sphere_sphere = [&](V3 p1, double r1, V3 p2, double r2) {
+                V3 n = p2 - p1;
+                double len = sqrt(dot(n, n));
+                double dist = len - r1 - r2;
+                if (dist > margin) return false;
+                if (len < ILQG_MINVAL) n = {1, 0, 0};
+                else n = (1.0 / len) * n;
+                emit(dist, p1 + (r1 + 0.5 * dist) * n, n, V3{0, 0, 0}, false);
+                return true;
+            };
+            if constexpr (t1 == ILQG_GEOM_PLANE && (t2 == ILQG_GEOM_CAPSULE || t2 == ILQG_GEOM_SPHERE)) {
+                V3 pn = gax[g1];
+                double r = m.geom_size[g2][0];
+                auto plane_sphere = [&](V3 c, bool hint) {
+                    double dist = dot(c - gpos[g1], pn) - r;
+                    if (dist > margin) return;
+                    emit(dist, c - (r + 0.5 * dist) * pn, pn, gax[g2], hint);
+                };
+                if constexpr (t2 == ILQG_GEOM_SPHERE) plane_sphere(gpos[g2], false);
+                else {
+                    double h = m.geom_size[g2][1];
+#pragma unroll 1
+                    for (int e = 0; e < 2; e++) plane_sphere(gpos[g2] + (e ? -h : h) * gax[g2], true);
+                }
+            } else if constexpr (t1 == ILQG_GEOM_SPHERE && t2 == ILQG_GEOM_SPHERE) {
+                sphere_sphere(gpos[g1], m.geom_size[g1][0], gpos[g2], m.geom_size[g2][0]);
+            } else if constexpr (t1 == ILQG_GEOM_SPHERE && t2 == ILQG_GEOM_CAPSULE) {
+                double h = m.geom_size[g2][1];
+                double t = clampd(dot(gpos[g1] - gpos[g2], gax[g2]), -h, h);
+                sphere_sphere(gpos[g1], m.geom_size[g1][0], gpos[g2] + t * gax[g2], m.geom_size[g2][0]);
+            } else if constexpr (t1 == ILQG_GEOM_CAPSULE && t2 == ILQG_GEOM_CAPSULE) {
+                V3 p1 = gpos[g1], a1 = gax[g1], p2 = gpos[g2], a2 = gax[g2];
+                double r1 = m.geom_size[g1][0], h1 = m.geom_size[g1][1], r2 = m.geom_size[g2][0], h2 = m.geom_size[g2][1];
+                // candidate closest-point pairs on the two axis segments (at most two survive the distance test)
+                V3 ca[2], cb[2];
+                int nc = 0;
+                auto consider = [&](V3 c1, V3 c2) {
+                    V3 d = c2 - c1;
+                    if (sqrt(dot(d, d)) - r1 - r2 > margin) return false;
+                    if (nc == 0) { ca[0] = c1; cb[0] = c2; } else { ca[1] = c1; cb[1] = c2; }
+                    nc++;
+                    return true;
+                };
+                V3 dif = p1 - p2;
+                double mb = -dot(a1, a2), uu = -dot(a1, dif), vv = dot(a2, dif);
+                double det = 1.0 - mb * mb;
+                if (fabs(det) >= 1e-12) {
+                    double x1 = (uu - mb * vv) / det, x2 = (vv - mb * uu) / det;
+                    if (x1 > h1) { x1 = h1; x2 = vv - mb * h1; }
+                    else if (x1 < -h1) { x1 = -h1; x2 = vv + mb * h1; }
+                    if (x2 > h2) { x2 = h2; x1 = clampd(uu - mb * h2, -h1, h1); }
+                    else if (x2 < -h2) { x2 = -h2; x1 = clampd(uu + mb * h2, -h1, h1); }
+                    consider(p1 + x1 * a1, p2 + x2 * a2);
+                } else {  // parallel axes: end points against the other segment, at most two contacts
+                    for (int s = -1; s <= 1 && nc < 2; s += 2) {
+                        V3 c1 = p1 + (s * h1) * a1;
+                        double t = dot(c1 - p2, a2);
+                        if (t < -h2 || t > h2) continue;
+                        consider(c1, p2 + t * a2);
+                    }
+                    for (int s = -1; s <= 1 && nc < 2; s += 2) {
+                        V3 c2 = p2 + (s * h2) * a2;
+                        double t = dot(c2 - p1, a1);
+                        if (t <= -h1 || t >= h1) continue;
+                        consider(p1 + t * a1, c2);
+                    }
+                    if (nc == 0) {
+                        double best = 1e300;
+                        V3 bq1 = p1, bq2 = p2;
+                        for (int s = -1; s <= 1; s += 2)
+                            for (int t = -1; t <= 1; t += 2) {
+                                V3 c1 = p1 + (s * h1) * a1, c2 = p2 + (t * h2) * a2;
+                                double dd = dot(c1 - c2, c1 - c2);
+                                if (dd < best) { best = dd; bq1 = c1; bq2 = c2; }
+                            }
+                        consider(bq1, bq2);
+                    }
+                }
+#pragma unroll 1
+                for (int c = 0; c < nc; c++) sphere_sphere(c ? ca[1] : ca[0], r1, c ? cb[1] : cb[0], r2);
+            }
+        });
+    }
+    w.nefc = ne;
+}
+
+// ------------------------------------------------------------------ constraint solve (mj_fwdConstraint)
+template <class T>
+DEV double problem_cost(const Work<T>& w, const double* a) {
+    constexpr int NV = T::NV;
+    double cost = 0;
+    for (int r = 0; r < w.nefc; r++) {
+        double jar = -w.aref[r];
+        sfor<0, NV>([&](auto ii) { jar += w.J[r][IDX(ii)] * a[IDX(ii)]; });
+        if (jar < 0) cost += 0.5 * w.D[r] * jar * jar;
+    }
+    sfor<0, NV>([&](auto ii) {
+        constexpr int i = IDX(ii);
+        double Ma = 0;
+        sfor<0, NV>([&](auto kk) { Ma += w.M[tri(i, IDX(kk))] * a[IDX(kk)]; });
+        cost += 0.5 * (Ma - w.fs[i]) * (a[i] - w.as[i]);
+    });
+    return cost;
+}
+
+// Newton with exact linesearch on the convex piecewise-quadratic cost.  `warm` in: qacc_warmstart;
+// out: the solution (which is also the next warm start, as in MuJoCo 2.x).  qacc out.
+template <class T>
+DEV void solve(const DevModel<T>& m, Work<T>& w, double (&warm)[T::NV], double (&qacc)[T::NV], int maxiter, double tol) {
+    constexpr int NV = T::NV, NT = NV * (NV + 1) / 2;
+    const int ne = w.nefc;
+    w.iters = 0;
+    if (ne == 0) {
+        sfor<0, NV>([&](auto ii) { qacc[IDX(ii)] = w.as[IDX(ii)]; warm[IDX(ii)] = w.as[IDX(ii)]; w.fc[IDX(ii)] = 0; });
+        return;
+    }
+    {
+        double cw = problem_cost<T>(w, warm), cs = problem_cost<T>(w, w.as);
+        if (cw < cs) sfor<0, NV>([&](auto ii) { qacc[IDX(ii)] = warm[IDX(ii)]; });
+        else sfor<0, NV>([&](auto ii) { qacc[IDX(ii)] = w.as[IDX(ii)]; });
+    }
+    const double scale = 1.0 / (m.meaninertia * (NV > 1 ? NV : 1));
+    double Ma[NV], grad[NV], search[NV], Mv[NV];
+    sfor<0, NV>([&](auto ii) {
+        constexpr int i = IDX(ii);
+        double s = 0;
+        sfor<0, NV>([&](auto kk) { s += w.M[tri(i, IDX(kk))] * qacc[IDX(kk)]; });
+        Ma[i] = s;
+    });
+    for (int r = 0; r < ne; r++) {
+        double s = -w.aref[r];
+        sfor<0, NV>([&](auto ii) { s += w.J[r][IDX(ii)] * qacc[IDX(ii)]; });
+        w.jar[r] = s;
+    }
+    double cost = 0;
+    // cost, gradient, Hessian factor and Newton direction at the current point
+    auto update = [&]() {
+        double H[NT], Lh[NT];
+        sfor<0, NT>([&](auto tt) { H[IDX(tt)] = w.M[IDX(tt)]; });
+        sfor<0, NV>([&](auto ii) { w.fc[IDX(ii)] = 0; });
+        double c = 0;
+        for (int r = 0; r < ne; r++) {
+            double jar = w.jar[r];
+            if (jar < 0) {
+                double D = w.D[r];
+                double Jr[NV];
+                sfor<0, NV>([&](auto ii) { Jr[IDX(ii)] = w.J[r][IDX(ii)]; });
+                double f = -D * jar;
+                c += 0.5 * D * jar * jar;
+                sfor<0, NV>([&](auto ii) {
+                    constexpr int i = IDX(ii);
+                    w.fc[i] += Jr[i] * f;
+                    double t = D * Jr[i];
+                    sfor<0, i + 1>([&](auto kk) { H[tri(i, IDX(kk))] += t * Jr[IDX(kk)]; });
+                });
+            }
+        }
+        sfor<0, NV>([&](auto ii) {
+            constexpr int i = IDX(ii);
+            c += 0.5 * (Ma[i] - w.fs[i]) * (qacc[i] - w.as[i]);
+            grad[i] = Ma[i] - w.fs[i] - w.fc[i];
+            search[i] = grad[i];
+        });
+        cost = c;
+        chol_packed<NV>(H, Lh);
+        chol_solve_packed<NV>(Lh, search);
+        sfor<0, NV>([&](auto ii) { search[IDX(ii)] = -search[IDX(ii)]; });
+    };
+    update();
+    int iter = 0;
+    while (iter < maxiter) {
+        // ---- exact linesearch
+        double g1 = 0, g2 = 0;
+        sfor<0, NV>([&](auto ii) {
+            constexpr int i = IDX(ii);
+            double s = 0;
+            sfor<0, NV>([&](auto kk) { s += w.M[tri(i, IDX(kk))] * search[IDX(kk)]; });
+            Mv[i] = s;
+        });
+        sfor<0, NV>([&](auto ii) { constexpr int i = IDX(ii); g1 += search[i] * (Ma[i] - w.fs[i]); g2 += search[i] * Mv[i]; });
+        for (int r = 0; r < ne; r++) {
+            double s = 0;
+            sfor<0, NV>([&](auto ii) { s += w.J[r][IDX(ii)] * search[IDX(ii)]; });
+            w.jv[r] = s;
+        }
+        double alpha = 0, lo = 0, hi = CUDART_INF;
+        bool descent = true;
+        for (int it = 0; it < m.ls_iterations; it++) {
+            double d1 = g1 + g2 * alpha, d2 = g2;
+            for (int r = 0; r < ne; r++) {
+                double jv = w.jv[r];
+                double x = w.jar[r] + alpha * jv;
+                if (x < 0) {
+                    double t = w.D[r] * jv;
+                    d1 += t * x;
+                    d2 += t * jv;
+                }
+            }
+            if (it == 0 && d1 >= 0) { descent = false; break; }
+            if (d1 == 0) break;
+            if (d1 < 0) lo = alpha; else hi = alpha;
+            if (d2 < ILQG_MINVAL) break;
+            double an = alpha - d1 / d2;
+            if (!(an > lo && an < hi)) an = isinf(hi) ? 2 * alpha + 1 : 0.5 * (lo + hi);
+            bool done = fabs(an - alpha) <= 1e-14 * fabs(an);
+            alpha = an;
+            if (done) break;
+        }
+        if (!descent || alpha == 0) break;
+        sfor<0, NV>([&](auto ii) { constexpr int i = IDX(ii); qacc[i] += alpha * search[i]; Ma[i] += alpha * Mv[i]; });
+        for (int r = 0; r < ne; r++) w.jar[r] += alpha * w.jv[r];
+        double old = cost;
+        update();
+        iter++;
+        double gn = 0;
+        sfor<0, NV>([&](auto ii) { gn += grad[IDX(ii)] * grad[IDX(ii)]; });
+        double improvement = scale * (old - cost), gradient = scale * sqrt(gn);
+        if (improvement < tol || gradient < tol) break;
+    }
+    w.iters = iter;
+    sfor<0, NV>([&](auto ii) { warm[IDX(ii)] = qacc[IDX(ii)]; });
+}
+
+// ------------------------------------------------------------------ integration (mj_Euler / mj_RungeKutta)
+DEV void quat_integrate(double* quat, V3 vel, double scale) {
+    double n = sqrt(dot(vel, vel));
+    V3 ax = n < ILQG_MINVAL ? V3{1, 0, 0} : (1.0 / n) * vel;
+    if (n < ILQG_MINVAL) n = 0;
+    double s, c;
+    sincos(0.5 * scale * n, &s, &c);
+    Q4 q = qnormalized({quat[0], quat[1], quat[2], quat[3]});
+    Q4 r = qmul(q, {c, ax.x * s, ax.y * s, ax.z * s});
+    quat[0] = r.w; quat[1] = r.x; quat[2] = r.y; quat[3] = r.z;
+}
+
+template <class T>
+DEV void integrate_pos(double (&q)[T::NQ], const double (&v)[T::NV], double dt) {
+    sfor<0, T::NJNT>([&](auto jj) {
+        constexpr int j = IDX(jj), qa = T::jnt_qposadr(j), da = T::jnt_dofadr(j);
+        if constexpr (T::jnt_type(j) == ILQG_JNT_FREE) {
+            q[qa] += dt * v[da]; q[qa + 1] += dt * v[da + 1]; q[qa + 2] += dt * v[da + 2];
+            quat_integrate(&q[qa + 3], {v[da + 3], v[da + 4], v[da + 5]}, dt);
+        } else
+            q[qa] += dt * v[da];
+    });
+}
+
+// one mj_step: forward dynamics with the model's solver settings, then the model's integrator
+template <class T>
+DEV void step(const DevModel<T>& m, Work<T>& w, double (&q)[T::NQ], double (&v)[T::NV], const double (&u)[nz(T::NU)],
+              double (&warm)[T::NV], double (&qacc)[T::NV]) {
+    constexpr int NV = T::NV, NQ = T::NQ, NT = NV * (NV + 1) / 2;
+    const double h = m.timestep;
+    build_problem<T>(m, q, v, u, w);
+    solve<T>(m, w, warm, qacc, m.iterations, m.tolerance);
+    if (m.integrator == ILQG_INT_RK4) {
+        double q0[NQ], v0[NV], X[4][NV], F[4][NV], dX[NV], dF[NV];
+        sfor<0, NQ>([&](auto ii) { q0[IDX(ii)] = q[IDX(ii)]; });
+        sfor<0, NV>([&](auto ii) { v0[IDX(ii)] = v[IDX(ii)]; X[0][IDX(ii)] = v[IDX(ii)]; F[0][IDX(ii)] = qacc[IDX(ii)]; });
+        sfor<1, 4>([&](auto ss) {
+            constexpr int s = IDX(ss);
+            constexpr double a = s == 3 ? 1.0 : 0.5;  // the only non-zero tableau entry of row s-1 sits at column s-1
+            sfor<0, NV>([&](auto ii) { dX[IDX(ii)] = a * X[s - 1][IDX(ii)]; dF[IDX(ii)] = a * F[s - 1][IDX(ii)]; });
+            sfor<0, NQ>([&](auto ii) { q[IDX(ii)] = q0[IDX(ii)]; });
+            integrate_pos<T>(q, dX, h);
+            sfor<0, NV>([&](auto ii) { v[IDX(ii)] = v0[IDX(ii)] + h * dF[IDX(ii)]; });
+            build_problem<T>(m, q, v, u, w);
+            solve<T>(m, w, warm, qacc, m.iterations, m.tolerance);
+            sfor<0, NV>([&](auto ii) { X[s][IDX(ii)] = v[IDX(ii)]; F[s][IDX(ii)] = qacc[IDX(ii)]; });
+        });
+        sfor<0, NV>([&](auto ii) {
+            constexpr int i = IDX(ii);
+            dX[i] = (1.0 / 6) * X[0][i] + (1.0 / 3) * X[1][i] + (1.0 / 3) * X[2][i] + (1.0 / 6) * X[3][i];
+            dF[i] = (1.0 / 6) * F[0][i] + (1.0 / 3) * F[1][i] + (1.0 / 3) * F[2][i] + (1.0 / 6) * F[3][i];
+        });
+        sfor<0, NQ>([&](auto ii) { q[IDX(ii)] = q0[IDX(ii)]; });
+        sfor<0, NV>([&](auto ii) { v[IDX(ii)] = v0[IDX(ii)] + h * dF[IDX(ii)]; });
+        integrate_pos<T>(q, dX, h);
+    } else {
+        double a[NV];
+        if constexpr (T::ANY_DAMPING) {
+            double A[NT], La[NT];
+            sfor<0, NT>([&](auto tt) { A[IDX(tt)] = w.M[IDX(tt)]; });
+            sfor<0, NV>([&](auto ii) { constexpr int i = IDX(ii); A[tri(i, i)] += h * m.dof_damping[i]; a[i] = w.fs[i] + w.fc[i]; });
+            chol_packed<NV>(A, La);
+            chol_solve_packed<NV>(La, a);
+        } else
+            sfor<0, NV>([&](auto ii) { a[IDX(ii)] = qacc[IDX(ii)]; });
+        sfor<0, NV>([&](auto ii) { v[IDX(ii)] += h * a[IDX(ii)]; });
+        integrate_pos<T>(q, v, h);
+    }
+}
+
+}  // namespace ilqg

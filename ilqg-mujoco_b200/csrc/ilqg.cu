@@ -1,0 +1,483 @@
+// ilqg.cu — sm_100a kernels and the C ABI (include/ilqg_b200.h) of the iLQG hot path.
+//
+// FD linearisation (replaces /root/reference/src/mjderivative.cpp:43-255):
+//   fd_center_kernel  : one thread per knot — the centre evaluation and its nwarmup-1 extra solves
+//                       (:61-68); its only product is the warm start every perturbed solve begins from (:75).
+//   fd_perturb_kernel : one thread per perturbed evaluation, G = 2(2nv+nu) consecutive lanes per knot
+//                       (+/- pairs adjacent), floor(32/G) knots per warp.  The +/- lanes difference their
+//                       qacc with one shuffle, the knot's deriv block is staged in shared memory in the
+//                       reference layout and written to HBM by the whole warp in consecutive 8-byte words.
+// All T x 2(2nv+nu) perturbations of every trajectory in the batch go out in one launch each.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+
+#include "dyn.cuh"
+
+namespace ilqg {
+
+// ------------------------------------------------------------------ step cost on the device
+template <class T>
+DEV double cost_eval(const ilqg_cost& c, const double (&q)[T::NQ], const double (&v)[T::NV], const double (&u)[nz(T::NU)]) {
+    // same term order as the host-side evaluation (no FMA contraction: the +eps forward difference
+    // divides by 1e-6, so the cost must round like the caller's C++ cost function)
+    double g = 0;
+    sfor<0, T::NQ>([&](auto ii) { constexpr int i = IDX(ii); g = __dadd_rn(g, __dmul_rn(__dmul_rn(c.q2[i], q[i]), q[i])); g = __dadd_rn(g, __dmul_rn(c.q1[i], q[i])); });
+    sfor<0, T::NV>([&](auto ii) { constexpr int i = IDX(ii); g = __dadd_rn(g, __dmul_rn(__dmul_rn(c.v2[i], v[i]), v[i])); g = __dadd_rn(g, __dmul_rn(c.v1[i], v[i])); });
+    sfor<0, T::NU>([&](auto ii) { constexpr int i = IDX(ii); g = __dadd_rn(g, __dmul_rn(__dmul_rn(c.u2[i], u[i]), u[i])); g = __dadd_rn(g, __dmul_rn(c.u1[i], u[i])); });
+    return g;
+}
+
+template <class T>
+DEV void load_knot(int k, const double* qpos, const double* qvel, const double* ctrl, double (&q)[T::NQ], double (&v)[T::NV],
+                   double (&u)[nz(T::NU)]) {
+    sfor<0, T::NQ>([&](auto ii) { q[IDX(ii)] = qpos[(size_t)k * T::NQ + IDX(ii)]; });
+    sfor<0, T::NV>([&](auto ii) { v[IDX(ii)] = qvel[(size_t)k * T::NV + IDX(ii)]; });
+    sfor<0, T::NU>([&](auto ii) { u[IDX(ii)] = ctrl[(size_t)k * T::NU + IDX(ii)]; });
+}
+
+// ------------------------------------------------------------------ FD: centre
+template <class T>
+__global__ void __launch_bounds__(128) fd_center_kernel(const __grid_constant__ DevModel<T> m, int nknots, const double* __restrict__ qpos,
+                                                        const double* __restrict__ qvel, const double* __restrict__ ctrl,
+                                                        const double* __restrict__ warmstart, int niter, int nwarmup,
+                                                        double* __restrict__ qacc_center, int* __restrict__ status) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nknots) return;
+    double q[T::NQ], v[T::NV], u[nz(T::NU)], warm[T::NV], qacc[T::NV];
+    load_knot<T>(k, qpos, qvel, ctrl, q, v, u);
+    sfor<0, T::NV>([&](auto ii) { warm[IDX(ii)] = warmstart ? warmstart[(size_t)k * T::NV + IDX(ii)] : 0.0; });
+    Work<T> w;
+    build_problem<T>(m, q, v, u, w);
+    solve<T>(m, w, warm, qacc, niter, 0.0);
+    for (int rep = 1; rep < nwarmup; rep++) solve<T>(m, w, warm, qacc, niter, 0.0);
+    bool ok = true;
+    sfor<0, T::NV>([&](auto ii) { qacc_center[(size_t)k * T::NV + IDX(ii)] = qacc[IDX(ii)]; ok = ok && isfinite(qacc[IDX(ii)]); });
+    if (status) status[k] = ok ? 0 : ILQG_ERR_NONFINITE;
+}
+
+// ------------------------------------------------------------------ FD: perturbed evaluations
+template <class T>
+struct FdShape {
+    static constexpr int NV = T::NV, NU = T::NU;
+    static constexpr int NCOL = 2 * NV + NU;    // columns per knot: ctrl, qvel, qpos
+    static constexpr int G = 2 * NCOL;          // lanes per knot
+    static constexpr int KPW = 32 / G;          // knots per warp
+    static constexpr int ND = NV * NCOL + NCOL; // deriv doubles per knot
+    static constexpr int NJAC = NV * NCOL;
+    static_assert(G <= 32, "thread-per-rollout FD kernel needs 2(2nv+nu) <= 32; larger models use the cooperative kernel");
+};
+
+template <class T, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) fd_perturb_kernel(const __grid_constant__ DevModel<T> m, int nknots,
+                                                                 const double* __restrict__ qpos, const double* __restrict__ qvel,
+                                                                 const double* __restrict__ ctrl, const double* __restrict__ qacc_center,
+                                                                 const ilqg_cost* __restrict__ cost, double eps, int niter,
+                                                                 double* __restrict__ deriv, int* __restrict__ status) {
+    using S = FdShape<T>;
+    constexpr int NV = T::NV, NU = T::NU, NQ = T::NQ;
+    __shared__ double stage[WARPS][S::KPW * S::ND];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int warp = blockIdx.x * WARPS + wib;
+    const int sub = lane / S::G, l = lane - sub * S::G;
+    const int k = warp * S::KPW + sub;
+    const bool valid = sub < S::KPW && k < nknots;
+    const int col = l >> 1;
+    const double se = (l & 1) ? -eps : eps;
+    double qacc[NV];
+    double dcost = 0;
+    if (valid) {
+        double q[NQ], v[NV], u[nz(NU)], warm[NV];
+        load_knot<T>(k, qpos, qvel, ctrl, q, v, u);
+        sfor<0, NV>([&](auto ii) { warm[IDX(ii)] = qacc_center[(size_t)k * NV + IDX(ii)]; });
+        double c0 = 0;
+        if (cost) c0 = cost_eval<T>(*cost, q, v, u);
+        // perturb this lane's input (ctrl: mjderivative.cpp:85,99; qvel: :117,130; qpos: :164-169,187-192)
+        sfor<0, NU>([&](auto ii) { if (col == IDX(ii)) u[IDX(ii)] += se; });
+        sfor<0, NV>([&](auto ii) { if (col == NU + IDX(ii)) v[IDX(ii)] += se; });
+        sfor<0, NV>([&](auto ii) {
+            constexpr int i = IDX(ii), j = T::dof_jnt(i);
+            if (col == NU + NV + i) {
+                if constexpr (T::jnt_type(j) == ILQG_JNT_FREE && i >= T::jnt_dofadr(j) + 3) {
+                    constexpr int a = i - T::jnt_dofadr(j) - 3;
+                    quat_integrate(&q[T::jnt_qposadr(j) + 3], V3{a == 0 ? se : 0.0, a == 1 ? se : 0.0, a == 2 ? se : 0.0}, 1.0);
+                } else
+                    q[T::jnt_qposadr(j) + i - T::jnt_dofadr(j)] += se;
+            }
+        });
+        if (cost && !(l & 1)) dcost = __ddiv_rn(__dsub_rn(cost_eval<T>(*cost, q, v, u), c0), eps);
+        Work<T> w;
+        build_problem<T>(m, q, v, u, w);
+        solve<T>(m, w, warm, qacc, niter, 0.0);
+    } else {
+        sfor<0, NV>([&](auto ii) { qacc[IDX(ii)] = 0; });
+    }
+    // central difference: the '+' lane (even) takes the '-' lane's result
+    bool finite = true;
+    double* st = stage[wib] + sub * S::ND;
+    sfor<0, NV>([&](auto jj) {
+        constexpr int j = IDX(jj);
+        double other = __shfl_xor_sync(0xffffffffu, qacc[j], 1);
+        double d = (qacc[j] - other) / (2 * eps);
+        finite = finite && isfinite(d);
+        if (valid && !(l & 1)) {
+            // reference layout: block of kind, element i + j*stride
+            int off;
+            if (col < NU) off = 2 * NV * NV + col + j * NU;
+            else if (col < NU + NV) off = NV * NV + (col - NU) + j * NV;
+            else off = (col - NU - NV) + j * NV;
+            st[off] = d;
+        }
+    });
+    if (valid && !(l & 1)) {
+        // cost gradient entries: dg/dqpos[nv], dg/dqvel[nv], dg/dctrl[nu]
+        int off;
+        if (col < NU) off = S::NJAC + 2 * NV + col;
+        else if (col < NU + NV) off = S::NJAC + NV + (col - NU);
+        else off = S::NJAC + (col - NU - NV);
+        st[off] = dcost;
+        if (!finite && status) atomicExch(&status[k], ILQG_ERR_NONFINITE);
+    }
+    __syncwarp();
+    // coalesced write-out: the warp's knots are contiguous in deriv
+    const int k0 = warp * S::KPW;
+    int nk = nknots - k0;
+    if (nk > S::KPW) nk = S::KPW;
+    if (nk > 0) {
+        const int per = cost ? S::ND : S::NJAC;  // without a device cost the gradient entries stay untouched
+        double* out = deriv + (size_t)k0 * S::ND;
+        if (per == S::ND) {
+            for (int e = lane; e < nk * S::ND; e += 32) out[e] = stage[wib][e];
+        } else {
+            for (int kk = 0; kk < nk; kk++)
+                for (int e = lane; e < per; e += 32) out[kk * S::ND + e] = stage[wib][kk * S::ND + e];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ forward / step batches
+template <class T>
+__global__ void __launch_bounds__(128) forward_kernel(const __grid_constant__ DevModel<T> m, int n, const double* __restrict__ qpos,
+                                                      const double* __restrict__ qvel, const double* __restrict__ ctrl,
+                                                      double* __restrict__ warmstart, double* __restrict__ qacc_out) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    double q[T::NQ], v[T::NV], u[nz(T::NU)], warm[T::NV], qacc[T::NV];
+    load_knot<T>(k, qpos, qvel, ctrl, q, v, u);
+    sfor<0, T::NV>([&](auto ii) { warm[IDX(ii)] = warmstart ? warmstart[(size_t)k * T::NV + IDX(ii)] : 0.0; });
+    Work<T> w;
+    build_problem<T>(m, q, v, u, w);
+    solve<T>(m, w, warm, qacc, m.iterations, m.tolerance);
+    sfor<0, T::NV>([&](auto ii) {
+        qacc_out[(size_t)k * T::NV + IDX(ii)] = qacc[IDX(ii)];
+        if (warmstart) warmstart[(size_t)k * T::NV + IDX(ii)] = warm[IDX(ii)];
+    });
+}
+
+template <class T>
+__global__ void __launch_bounds__(128) step_kernel(const __grid_constant__ DevModel<T> m, int n, int nsteps, double* __restrict__ qpos,
+                                                   double* __restrict__ qvel, const double* __restrict__ ctrl,
+                                                   double* __restrict__ warmstart, double* __restrict__ qacc_out) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    double q[T::NQ], v[T::NV], u[nz(T::NU)], warm[T::NV], qacc[T::NV];
+    load_knot<T>(k, qpos, qvel, ctrl, q, v, u);
+    sfor<0, T::NV>([&](auto ii) { warm[IDX(ii)] = warmstart ? warmstart[(size_t)k * T::NV + IDX(ii)] : 0.0; qacc[IDX(ii)] = 0; });
+    Work<T> w;
+    for (int s = 0; s < nsteps; s++) step<T>(m, w, q, v, u, warm, qacc);
+    sfor<0, T::NQ>([&](auto ii) { qpos[(size_t)k * T::NQ + IDX(ii)] = q[IDX(ii)]; });
+    sfor<0, T::NV>([&](auto ii) {
+        qvel[(size_t)k * T::NV + IDX(ii)] = v[IDX(ii)];
+        if (warmstart) warmstart[(size_t)k * T::NV + IDX(ii)] = warm[IDX(ii)];
+        if (qacc_out) qacc_out[(size_t)k * T::NV + IDX(ii)] = qacc[IDX(ii)];
+    });
+}
+
+// ------------------------------------------------------------------ engines (one per compiled-in topology)
+struct Engine {
+    virtual ~Engine() {}
+    virtual const char* name() const = 0;
+    virtual cudaError_t fd(int nknots, const double* qpos, const double* qvel, const double* ctrl, const double* warm,
+                           const ilqg_cost* cost_dev, const ilqg_fd_opts& o, double* deriv, double* qacc_center, int* status,
+                           cudaStream_t s) = 0;
+    virtual cudaError_t forward(int n, const double* qpos, const double* qvel, const double* ctrl, double* warm, double* qacc,
+                                cudaStream_t s) = 0;
+    virtual cudaError_t step(int n, int nsteps, double* qpos, double* qvel, const double* ctrl, double* warm, double* qacc,
+                             cudaStream_t s) = 0;
+};
+
+template <class T>
+struct EngineT : Engine {
+    DevModel<T> dm;
+    const char* name() const override { return T::NAME; }
+    cudaError_t fd(int nknots, const double* qpos, const double* qvel, const double* ctrl, const double* warm, const ilqg_cost* cost_dev,
+                   const ilqg_fd_opts& o, double* deriv, double* qacc_center, int* status, cudaStream_t s) override {
+        using S = FdShape<T>;
+        constexpr int WARPS = 4;
+        if (nknots <= 0) return cudaSuccess;
+        fd_center_kernel<T><<<(nknots + 127) / 128, 128, 0, s>>>(dm, nknots, qpos, qvel, ctrl, warm, o.niter, o.nwarmup, qacc_center, status);
+        int nwarps = (nknots + S::KPW - 1) / S::KPW;
+        fd_perturb_kernel<T, WARPS><<<(nwarps + WARPS - 1) / WARPS, WARPS * 32, 0, s>>>(dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps,
+                                                                                     o.niter, deriv, status);
+        return cudaGetLastError();
+    }
+    cudaError_t forward(int n, const double* qpos, const double* qvel, const double* ctrl, double* warm, double* qacc,
+                        cudaStream_t s) override {
+        if (n <= 0) return cudaSuccess;
+        forward_kernel<T><<<(n + 127) / 128, 128, 0, s>>>(dm, n, qpos, qvel, ctrl, warm, qacc);
+        return cudaGetLastError();
+    }
+    cudaError_t step(int n, int nsteps, double* qpos, double* qvel, const double* ctrl, double* warm, double* qacc, cudaStream_t s) override {
+        if (n <= 0) return cudaSuccess;
+        step_kernel<T><<<(n + 127) / 128, 128, 0, s>>>(dm, n, nsteps, qpos, qvel, ctrl, warm, qacc);
+        return cudaGetLastError();
+    }
+};
+
+static Engine* make_engine(const ilqg_model& m) {
+#define ILQG_TRY(TOPO)                                          \
+    {                                                           \
+        auto e = std::make_unique<EngineT<TOPO>>();             \
+        if (dev_model_from_tables<TOPO>(m, e->dm)) return e.release(); \
+    }
+    ILQG_FOR_EACH_TOPOLOGY(ILQG_TRY)
+#undef ILQG_TRY
+    return nullptr;
+}
+
+}  // namespace ilqg
+
+// ==================================================================== C ABI
+struct ilqg_handle_s {
+    int device = 0;
+    ilqg_model model;
+    ilqg::Engine* eng = nullptr;
+    std::string err;
+    // scratch owned by the handle (grown on demand)
+    double* d_center = nullptr; size_t center_cap = 0;
+    ilqg_cost* d_cost = nullptr;
+    // staging for the *_host entry points
+    void* d_stage = nullptr; size_t stage_cap = 0;
+    long launches = 0;  // kernels launched through this handle (bench.py reports it)
+};
+
+static thread_local std::string g_create_err;
+
+static int fail(ilqg_handle h, int code, const std::string& msg) {
+    if (h) h->err = msg; else g_create_err = msg;
+    return code;
+}
+static int cuda_fail(ilqg_handle h, cudaError_t e, const char* what) {
+    return fail(h, ILQG_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(h, call)                                         \
+    do {                                                    \
+        cudaError_t e_ = (call);                            \
+        if (e_ != cudaSuccess) return cuda_fail(h, e_, #call); \
+    } while (0)
+
+extern "C" {
+
+void ilqg_fd_opts_default(ilqg_fd_opts* o) {
+    if (!o) return;
+    o->eps = 1e-6;
+    o->niter = 30;
+    o->nwarmup = 3;
+}
+
+int ilqg_deriv_size(const ilqg_model* m) { return m ? m->nv * (2 * m->nv + m->nu) + 2 * m->nv + m->nu : 0; }
+
+const char* ilqg_last_error(ilqg_handle h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int ilqg_create(const ilqg_model* m, int device, ilqg_handle* out) {
+    if (!m || !out) return fail(nullptr, ILQG_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (m->magic != ILQG_MODEL_MAGIC || m->version != ILQG_MODEL_VERSION) return fail(nullptr, ILQG_ERR_MODEL, "bad model magic/version");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, ILQG_ERR_CUDA, std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, ILQG_ERR_ARG, "bad device index");
+    CU(nullptr, cudaSetDevice(device));
+    ilqg::Engine* eng = ilqg::make_engine(*m);
+    if (!eng)
+        return fail(nullptr, ILQG_ERR_UNSUPPORTED,
+                    "no kernel instantiation matches this model's kinematic tree; add it with tools/gen_topology and rebuild");
+    auto* h = new ilqg_handle_s();
+    h->device = device;
+    h->model = *m;
+    h->eng = eng;
+    if (cudaMalloc(&h->d_cost, sizeof(ilqg_cost)) != cudaSuccess) {
+        delete eng;
+        delete h;
+        return fail(nullptr, ILQG_ERR_CUDA, "cudaMalloc failed");
+    }
+    *out = h;
+    return ILQG_OK;
+}
+
+int ilqg_destroy(ilqg_handle h) {
+    if (!h) return ILQG_OK;
+    cudaSetDevice(h->device);
+    cudaFree(h->d_center);
+    cudaFree(h->d_cost);
+    cudaFree(h->d_stage);
+    delete h->eng;
+    delete h;
+    return ILQG_OK;
+}
+
+long ilqg_launch_count(ilqg_handle h) { return h ? h->launches : 0; }
+const char* ilqg_engine_name(ilqg_handle h) { return h && h->eng ? h->eng->name() : ""; }
+
+static int ensure_center(ilqg_handle h, size_t n) {
+    if (n <= h->center_cap) return ILQG_OK;
+    cudaFree(h->d_center);
+    h->d_center = nullptr;
+    h->center_cap = 0;
+    CU(h, cudaMalloc(&h->d_center, n * sizeof(double)));
+    h->center_cap = n;
+    return ILQG_OK;
+}
+static int ensure_stage(ilqg_handle h, size_t bytes) {
+    if (bytes <= h->stage_cap) return ILQG_OK;
+    cudaFree(h->d_stage);
+    h->d_stage = nullptr;
+    h->stage_cap = 0;
+    CU(h, cudaMalloc(&h->d_stage, bytes));
+    h->stage_cap = bytes;
+    return ILQG_OK;
+}
+
+int ilqg_fd_batch_dev(ilqg_handle h, int nknots, const double* qpos, const double* qvel, const double* ctrl, const double* warmstart,
+                      const ilqg_cost* cost, const ilqg_fd_opts* opts, double* deriv, double* qacc_out, int* status, void* stream) {
+    if (!h) return ILQG_ERR_ARG;
+    if (nknots < 0 || (nknots > 0 && (!qpos || !qvel || !deriv || (h->model.nu > 0 && !ctrl)))) return fail(h, ILQG_ERR_ARG, "null buffer");
+    if (nknots == 0) return ILQG_OK;
+    ilqg_fd_opts o;
+    ilqg_fd_opts_default(&o);
+    if (opts) o = *opts;
+    if (!(o.eps > 0) || o.niter < 0 || o.nwarmup < 1) return fail(h, ILQG_ERR_ARG, "bad FD options");
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(h, cudaSetDevice(h->device));
+    double* center = qacc_out;
+    if (!center) {
+        int rc = ensure_center(h, (size_t)nknots * h->model.nv);
+        if (rc) return rc;
+        center = h->d_center;
+    }
+    const ilqg_cost* dcost = nullptr;
+    if (cost) {  // `cost` is a HOST struct even in the _dev flavour (it is a small parameter block, like opts)
+        CU(h, cudaMemcpyAsync(h->d_cost, cost, sizeof(ilqg_cost), cudaMemcpyHostToDevice, s));
+        dcost = h->d_cost;
+    }
+    CU(h, h->eng->fd(nknots, qpos, qvel, ctrl, warmstart, dcost, o, deriv, center, status, s));
+    h->launches += 2;
+    return ILQG_OK;
+}
+
+int ilqg_fd_batch_host(ilqg_handle h, int nknots, const double* qpos, const double* qvel, const double* ctrl, const double* warmstart,
+                       const ilqg_cost* cost, const ilqg_fd_opts* opts, double* deriv, double* qacc_out, int* status) {
+    if (!h) return ILQG_ERR_ARG;
+    if (nknots < 0 || (nknots > 0 && (!qpos || !qvel || !deriv))) return fail(h, ILQG_ERR_ARG, "null buffer");
+    if (nknots == 0) return ILQG_OK;
+    CU(h, cudaSetDevice(h->device));
+    const int nq = h->model.nq, nv = h->model.nv, nu = h->model.nu, nd = ilqg_deriv_size(&h->model);
+    size_t n = (size_t)nknots;
+    // one staging block: qpos | qvel | ctrl | warm | qacc | deriv | status
+    size_t off_q = 0, off_v = off_q + n * nq, off_u = off_v + n * nv, off_w = off_u + n * nu, off_a = off_w + n * nv,
+           off_d = off_a + n * nv, ndbl = off_d + n * nd;
+    size_t bytes = ndbl * sizeof(double) + n * sizeof(int);
+    int rc = ensure_stage(h, bytes);
+    if (rc) return rc;
+    double* b = (double*)h->d_stage;
+    int* dstat = (int*)(b + ndbl);
+    cudaStream_t s = 0;
+    CU(h, cudaMemcpyAsync(b + off_q, qpos, n * nq * sizeof(double), cudaMemcpyHostToDevice, s));
+    CU(h, cudaMemcpyAsync(b + off_v, qvel, n * nv * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (nu) CU(h, cudaMemcpyAsync(b + off_u, ctrl, n * nu * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (warmstart) CU(h, cudaMemcpyAsync(b + off_w, warmstart, n * nv * sizeof(double), cudaMemcpyHostToDevice, s));
+    else CU(h, cudaMemsetAsync(b + off_w, 0, n * nv * sizeof(double), s));
+    if (!cost) CU(h, cudaMemcpyAsync(b + off_d, deriv, n * nd * sizeof(double), cudaMemcpyHostToDevice, s));  // keep caller's cost entries
+    rc = ilqg_fd_batch_dev(h, nknots, b + off_q, b + off_v, b + off_u, b + off_w, cost, opts, b + off_d, b + off_a, dstat, s);
+    if (rc) return rc;
+    CU(h, cudaMemcpyAsync(deriv, b + off_d, n * nd * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (qacc_out) CU(h, cudaMemcpyAsync(qacc_out, b + off_a, n * nv * sizeof(double), cudaMemcpyDeviceToHost, s));
+    std::unique_ptr<int[]> hs(new int[n]);
+    CU(h, cudaMemcpyAsync(hs.get(), dstat, n * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU(h, cudaStreamSynchronize(s));
+    int bad = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (status) status[i] = hs[i];
+        if (hs[i]) bad = 1;
+    }
+    return bad ? fail(h, ILQG_ERR_NONFINITE, "non-finite accelerations in at least one knot") : ILQG_OK;
+}
+
+int ilqg_forward_batch_dev(ilqg_handle h, int n, const double* qpos, const double* qvel, const double* ctrl, double* warmstart,
+                           double* qacc, void* stream) {
+    if (!h) return ILQG_ERR_ARG;
+    if (n < 0 || (n > 0 && (!qpos || !qvel || !qacc))) return fail(h, ILQG_ERR_ARG, "null buffer");
+    CU(h, cudaSetDevice(h->device));
+    CU(h, h->eng->forward(n, qpos, qvel, ctrl, warmstart, qacc, (cudaStream_t)stream));
+    h->launches += 1;
+    return ILQG_OK;
+}
+
+int ilqg_step_batch_dev(ilqg_handle h, int n, int nsteps, double* qpos, double* qvel, const double* ctrl, double* warmstart, double* qacc,
+                        void* stream) {
+    if (!h) return ILQG_ERR_ARG;
+    if (n < 0 || nsteps < 0 || (n > 0 && (!qpos || !qvel))) return fail(h, ILQG_ERR_ARG, "null buffer");
+    CU(h, cudaSetDevice(h->device));
+    CU(h, h->eng->step(n, nsteps, qpos, qvel, ctrl, warmstart, qacc, (cudaStream_t)stream));
+    h->launches += 1;
+    return ILQG_OK;
+}
+
+static int state_host_call(ilqg_handle h, int n, int nsteps, bool stepping, double* qpos, double* qvel, const double* ctrl, double* warmstart,
+                           double* qacc) {
+    if (!h) return ILQG_ERR_ARG;
+    if (n < 0 || (n > 0 && (!qpos || !qvel))) return fail(h, ILQG_ERR_ARG, "null buffer");
+    if (n == 0) return ILQG_OK;
+    CU(h, cudaSetDevice(h->device));
+    const int nq = h->model.nq, nv = h->model.nv, nu = h->model.nu;
+    size_t N = (size_t)n;
+    size_t off_q = 0, off_v = off_q + N * nq, off_u = off_v + N * nv, off_w = off_u + N * nu, off_a = off_w + N * nv, ndbl = off_a + N * nv;
+    int rc = ensure_stage(h, ndbl * sizeof(double));
+    if (rc) return rc;
+    double* b = (double*)h->d_stage;
+    cudaStream_t s = 0;
+    CU(h, cudaMemcpyAsync(b + off_q, qpos, N * nq * sizeof(double), cudaMemcpyHostToDevice, s));
+    CU(h, cudaMemcpyAsync(b + off_v, qvel, N * nv * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (nu) CU(h, cudaMemcpyAsync(b + off_u, ctrl, N * nu * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (warmstart) CU(h, cudaMemcpyAsync(b + off_w, warmstart, N * nv * sizeof(double), cudaMemcpyHostToDevice, s));
+    else CU(h, cudaMemsetAsync(b + off_w, 0, N * nv * sizeof(double), s));
+    if (stepping) rc = ilqg_step_batch_dev(h, n, nsteps, b + off_q, b + off_v, b + off_u, b + off_w, b + off_a, s);
+    else rc = ilqg_forward_batch_dev(h, n, b + off_q, b + off_v, b + off_u, b + off_w, b + off_a, s);
+    if (rc) return rc;
+    if (stepping) {
+        CU(h, cudaMemcpyAsync(qpos, b + off_q, N * nq * sizeof(double), cudaMemcpyDeviceToHost, s));
+        CU(h, cudaMemcpyAsync(qvel, b + off_v, N * nv * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    if (warmstart) CU(h, cudaMemcpyAsync(warmstart, b + off_w, N * nv * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (qacc) CU(h, cudaMemcpyAsync(qacc, b + off_a, N * nv * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CU(h, cudaStreamSynchronize(s));
+    return ILQG_OK;
+}
+
+int ilqg_forward_batch_host(ilqg_handle h, int n, const double* qpos, const double* qvel, const double* ctrl, double* warmstart,
+                            double* qacc) {
+    if (n > 0 && !qacc) return h ? fail(h, ILQG_ERR_ARG, "null buffer") : ILQG_ERR_ARG;
+    return state_host_call(h, n, 0, false, const_cast<double*>(qpos), const_cast<double*>(qvel), ctrl, warmstart, qacc);
+}
+
+int ilqg_step_batch_host(ilqg_handle h, int n, int nsteps, double* qpos, double* qvel, const double* ctrl, double* warmstart, double* qacc) {
+    if (nsteps < 0) return h ? fail(h, ILQG_ERR_ARG, "negative nsteps") : ILQG_ERR_ARG;
+    return state_host_call(h, n, nsteps, true, qpos, qvel, ctrl, warmstart, qacc);
+}
+
+}  // extern "C"

@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the iLQG hot path on B200 (contract: see the task statement).
+
+A "step" is one FD linearisation pass over one batch of synthetic knots: BASELINE.json configs[1],
+hopper (nq=nv=6, nu=3), 4096 trajectories x 21 knots (N=20) = 86,016 knots, eps=1e-6, solver pinned
+to 30 iterations / tolerance 0, 3 centre repetitions — everything calcMJDerivatives does per knot
+(/root/reference/src/mjderivative.cpp:212-255), for all knots in two kernel launches.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+`value`  : knots/s with inputs resident in HBM (CUDA events on the launching stream, max over ranks).
+`e2e`    : knots/s through the host-pointer C-ABI call (pinned host buffers; H2D + kernels + D2H inside).
+`--impl reference`: the reference's own OpenMP FD driver (oracle/_ref, compiled verbatim from
+           /root/reference/src/mjderivative.cpp against the oracle physics) on the host cores.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as entry  # noqa: E402
+
+METRIC = "FD dynamics Jacobian knots/sec (hopper, fp64)"
+UNIT = "knots/s"
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ CPU arms (oracle = checker/baseline only)
+def cpu_workload(o, om, ntraj, T, seed):
+    """Same generator as ilqg-mujoco_b200/workload.py, stepped by the CPU oracle (reference arm only)."""
+    pkg = entry.load_package()
+    from ilqg_mujoco_b200 import workload as wl  # noqa
+    qpos, qvel, ctrl, roll = wl.hopper_initial_states(ntraj, seed)
+    warm = np.zeros((ntraj, om.nv))
+    for i in range(ntraj):
+        if roll[i]:
+            q, v, w, _ = o.step_batch(om, qpos[i:i + 1], qvel[i:i + 1], ctrl[i:i + 1], warm[i:i + 1], int(roll[i]))
+            qpos[i], qvel[i], warm[i] = q[0], v[0], w[0]
+    Q = np.zeros((ntraj, T, om.nq)); V = np.zeros((ntraj, T, om.nv)); W = np.zeros((ntraj, T, om.nv))
+    for t in range(T):
+        Q[:, t], V[:, t], W[:, t] = qpos, qvel, warm
+        if t + 1 < T:
+            qpos, qvel, warm, _ = o.step_batch(om, qpos, qvel, ctrl, warm, 1)
+    U = np.repeat(ctrl[:, None, :], T, axis=1)
+    ok = np.isfinite(Q).all(axis=(1, 2)) & np.isfinite(V).all(axis=(1, 2))
+    Q, V, W, U = Q[ok], V[ok], W[ok], U[ok]
+    return (Q.reshape(-1, om.nq).copy(), V.reshape(-1, om.nv).copy(), U.reshape(-1, om.nu).copy(), W.reshape(-1, om.nv).copy())
+
+
+def time_reference_driver(o, om, q, v, u, w, cost, maxcpus=16):
+    """One pass of the reference's own calcMJDerivatives over the knots, serially in knots (ilqr.h:144-154)."""
+    ref_path = os.path.join(ROOT, "oracle", "_ref", "libref_fd.so")
+    if not os.path.exists(ref_path):
+        return None
+    R = C.CDLL(ref_path)
+    deriv = np.zeros((q.shape[0], om.nd))
+    t0 = time.perf_counter()
+    ncpu = R.ref_calc_derivatives_batch(om.ptr, q.shape[0], o._p(q), o._p(v), o._p(u), o._p(w), o._p(cost), o._p(deriv), maxcpus)
+    dt = time.perf_counter() - t0
+    return dt, int(ncpu), deriv
+
+
+def run_reference_arm(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return 0
+    o = entry.load_oracle()
+    pkg = entry.load_package()
+    om = o.Model(os.path.join(pkg.MODELS_DIR, "hopper.ilqgm"))
+    ntraj_s = args.ref_traj
+    q, v, u, w = cpu_workload(o, om, ntraj_s, args.T, seed=0)
+    cost = o.make_cost(q1=[1.0])
+    nk = q.shape[0]
+    kind = "reference"
+    for _ in range(args.warmup):
+        r = time_reference_driver(o, om, q, v, u, w, cost)
+        if r is None:
+            break
+    times = []
+    cores = 1
+    if r is None:  # oracle/_ref absent (should not happen: it is prebuilt and shipped): fall back to the port
+        kind = "port"
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            o.fd_batch(om, q, v, u, w, cost, nthreads=0)
+            times.append(time.perf_counter() - t0)
+        cores = os.cpu_count()
+    else:
+        for _ in range(args.steps):
+            dt, cores, _ = time_reference_driver(o, om, q, v, u, w, cost)
+            times.append(dt)
+    total = sum(times)
+    value = nk * len(times) / total
+    sample = (f"{ntraj_s} trajectories x {args.T} knots = {nk} knots per step from the same generator (seed 0), CPU-stepped; "
+              "/root/reference/src/mjderivative.cpp compiled verbatim (g++ -O3 -mavx -fopenmp) against the restated MuJoCo-subset "
+              "physics of oracle/ (upstream libmujoco is not available); knots serial, OpenMP across FD columns, <=16 threads (MAXTHREAD)")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"hopper FD Jacobians, {args.ntraj} trajectories x {args.T} knots (bounded CPU sample: {nk} knots/step)",
+                       "eps": 1e-6, "niter": 30, "nwarmup": 3},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------ the GPU arm
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    world = env_int("WORLD_SIZE", 1)
+    rank = env_int("RANK", 0)
+    local = env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+
+    pkg = entry.load_package()
+    from ilqg_mujoco_b200 import workload as wl
+    model = pkg.Model.named("hopper")
+    h = pkg.Handle(model, local)
+    # weak scaling: every rank linearises its own ntraj x T knots (independent trajectories, no collective on the data path)
+    q, v, u, w, nbad = wl.make_knots(h, args.ntraj, args.T, seed=1000 * rank, device=dev, model="hopper")
+    nk = q.shape[0]
+    deriv = torch.zeros((nk, model.nd), dtype=torch.float64, device=dev)
+    qacc = torch.zeros((nk, model.nv), dtype=torch.float64, device=dev)
+    status = torch.zeros(nk, dtype=torch.int32, device=dev)
+    cost = pkg.make_cost(q1=[1.0])  # the cost of /root/reference/tst/test_derivatives.cpp:16-20
+    flush = torch.empty(512 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)  # > 126 MB L2
+    stream = torch.cuda.current_stream().cuda_stream
+    L = pkg.lib()
+    L.ilqg_set_profiling(h._h, 1)
+
+    def one_step():
+        h.fd_batch_dev(q, v, u, w, deriv, qacc, status, cost=cost, stream=stream)
+
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    torch.cuda.synchronize()
+    launches0 = h.launches
+
+    sampler = ClockSampler(local)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kern_ms = []
+    for i in range(args.steps):
+        flush.fill_(float(i))  # L2 flush between timed iterations (outside the timed events)
+        ev[i][0].record()
+        one_step()
+        ev[i][1].record()
+        ev[i][1].synchronize()
+        c_ms, p_ms = C.c_float(0), C.c_float(0)
+        L.ilqg_fd_last_kernel_ms(h._h, C.byref(c_ms), C.byref(p_ms))
+        kern_ms.append((c_ms.value, p_ms.value))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    launches = h.launches - launches0
+    nonfinite = int((status != 0).sum())
+
+    # ---- e2e: host buffers through the host-pointer C ABI
+    hq, hv, hu, hw = (t.cpu().pin_memory() for t in (q, v, u, w))
+    hderiv = torch.zeros((nk, model.nd), dtype=torch.float64).pin_memory()
+    hqacc = torch.zeros((nk, model.nv), dtype=torch.float64).pin_memory()
+    hstat = torch.zeros(nk, dtype=torch.int32).pin_memory()
+    costp = cost.ctypes.data_as(C.c_void_p)
+
+    def e2e_step():
+        rc = L.ilqg_fd_batch_host(h._h, nk, C.c_void_p(hq.data_ptr()), C.c_void_p(hv.data_ptr()), C.c_void_p(hu.data_ptr()),
+                                  C.c_void_p(hw.data_ptr()), costp, None, C.c_void_p(hderiv.data_ptr()), C.c_void_p(hqacc.data_ptr()),
+                                  C.c_void_p(hstat.data_ptr()))
+        if rc not in (0, pkg.ERR_NONFINITE):
+            raise pkg.IlqgError(rc, L.ilqg_last_error(h._h).decode())
+
+    for _ in range(2):
+        e2e_step()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    e2e_s = time.perf_counter() - t0
+    h2d = nk * (model.nq + 2 * model.nv + model.nu) * 8
+    d2h = nk * (model.nd + model.nv) * 8 + nk * 4
+
+    tt = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = float(tt[0]), float(tt[1])
+    value = world * nk * args.steps / (total_ms * 1e-3)
+    e2e_value = world * nk * args.steps / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": f"hopper FD Jacobians (BASELINE configs[1]): {args.ntraj} trajectories x {args.T} knots per GPU",
+                           "knots_per_gpu": nk, "eps": 1e-6, "niter": 30, "nwarmup": 3, "parallelism": f"independent trajectories x{world}",
+                           "l2": "flushed between timed iterations (512 MiB fill outside the events)",
+                           "replaced_nonfinite_knots": nbad, "nonfinite_status": nonfinite},
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": launches}
+        # ---- roofline of the dominant kernel (fd_perturb_kernel) + cpu baseline: rank 0 only
+        p_ms = float(np.mean([k[1] for k in kern_ms]))
+        c_ms = float(np.mean([k[0] for k in kern_ms]))
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        alg_bytes = nk * (8 * (model.nq + 2 * model.nv + model.nu) + 8 * model.nd)
+        ach = alg_bytes / (p_ms * 1e-3) / 1e9
+        line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                            "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650",
+                            "kernel": "fd_perturb_kernel<Topo_hopper>", "kernel_ms": p_ms, "center_kernel_ms": c_ms,
+                            "note": "schema-conformant HBM view; the path is fp64-compute bound (SURVEY 8d): see roofline_fp64"}
+        if world == 1:
+            o = entry.load_oracle()
+            om = o.Model(os.path.join(pkg.MODELS_DIR, "hopper.ilqgm"))
+            ns = min(nk, args.cpu_sample)
+            sq, sv, su, sw = (t[:ns].cpu().numpy().copy() for t in (q, v, u, w))
+            # (i) fair port: OpenMP over knots, all cores; also yields the oracle-counted flops per knot
+            t0 = time.perf_counter()
+            dref, _, flops = o.fd_batch(om, sq, sv, su, sw, cost, nthreads=0)
+            port_s = time.perf_counter() - t0
+            flops_per_knot = flops / ns
+            # (ii) the reference's own driver (knots serial, OpenMP over columns), smaller sample
+            nr = min(ns, args.ref_sample)
+            r = time_reference_driver(o, om, sq[:nr], sv[:nr], su[:nr], sw[:nr], cost)
+            tf = C.c_double(0)
+            L.ilqg_fp64_peak(local, C.byref(tf))
+            ach_tf = flops_per_knot * nk / ((p_ms + c_ms) * 1e-3) / 1e12
+            line["roofline_fp64"] = {"bound": "fp64", "achieved": ach_tf, "peak": tf.value, "unit": "TFLOP/s",
+                                     "frac": ach_tf / tf.value if tf.value else None, "flops_per_knot": flops_per_knot,
+                                     "how": "oracle-counted fp64 flops per knot (FMA=2) on a sample of this workload x knots / (center+perturb kernel time); "
+                                            "peak = DFMA-chain microbenchmark run now on this GPU (MEASURED_PEAKS.json has no fp64 figure)"}
+            # parity spot check of the timed outputs against the oracle on the sample
+            dg = deriv[:ns].cpu().numpy()
+            err = float(np.abs(dg - dref).max() / max(1.0, np.abs(dref).max()))
+            line["parity_sample_max_rel_err"] = err
+            if r is not None:
+                rdt, rc, _ = r
+                line["cpu_baseline"] = {"value": nr / rdt, "unit": UNIT, "cores": rc, "kind": "reference",
+                                        "sample": f"first {nr} knots of this workload; the reference's calcMJDerivatives (verbatim source, oracle "
+                                                  "physics) knot by knot, OpenMP over FD columns"}
+            line["cpu_baseline_port"] = {"value": ns / port_s, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                         "sample": f"first {ns} knots of this workload; oracle FD, OpenMP over knots, persistent scratch"}
+            if "cpu_baseline" not in line:
+                line["cpu_baseline"] = line["cpu_baseline_port"]
+        print(json.dumps(line), flush=True)
+    h.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ntraj", type=int, default=4096)
+    ap.add_argument("--T", type=int, default=21)
+    ap.add_argument("--cpu-sample", type=int, default=21 * 1024, help="knots of the workload timed on the CPU port (rank 0, N=1)")
+    ap.add_argument("--ref-sample", type=int, default=21 * 48, help="knots timed through the reference's own driver in the GPU arm")
+    ap.add_argument("--ref-traj", type=int, default=24, help="trajectories per step in --impl reference")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -203,7 +203,7 @@ struct Engine {
     virtual const char* name() const = 0;
     virtual cudaError_t fd(int nknots, const double* qpos, const double* qvel, const double* ctrl, const double* warm,
                            const ilqg_cost* cost_dev, const ilqg_fd_opts& o, double* deriv, double* qacc_center, int* status,
-                           cudaStream_t s) = 0;
+                           cudaStream_t s, cudaEvent_t* ev) = 0;
     virtual cudaError_t forward(int n, const double* qpos, const double* qvel, const double* ctrl, double* warm, double* qacc,
                                 cudaStream_t s) = 0;
     virtual cudaError_t step(int n, int nsteps, double* qpos, double* qvel, const double* ctrl, double* warm, double* qacc,
@@ -215,14 +215,17 @@ struct EngineT : Engine {
     DevModel<T> dm;
     const char* name() const override { return T::NAME; }
     cudaError_t fd(int nknots, const double* qpos, const double* qvel, const double* ctrl, const double* warm, const ilqg_cost* cost_dev,
-                   const ilqg_fd_opts& o, double* deriv, double* qacc_center, int* status, cudaStream_t s) override {
+                   const ilqg_fd_opts& o, double* deriv, double* qacc_center, int* status, cudaStream_t s, cudaEvent_t* ev) override {
         using S = FdShape<T>;
         constexpr int WARPS = 4;
         if (nknots <= 0) return cudaSuccess;
+        if (ev) cudaEventRecord(ev[0], s);
         fd_center_kernel<T><<<(nknots + 127) / 128, 128, 0, s>>>(dm, nknots, qpos, qvel, ctrl, warm, o.niter, o.nwarmup, qacc_center, status);
+        if (ev) cudaEventRecord(ev[1], s);
         int nwarps = (nknots + S::KPW - 1) / S::KPW;
         fd_perturb_kernel<T, WARPS><<<(nwarps + WARPS - 1) / WARPS, WARPS * 32, 0, s>>>(dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps,
                                                                                      o.niter, deriv, status);
+        if (ev) cudaEventRecord(ev[2], s);
         return cudaGetLastError();
     }
     cudaError_t forward(int n, const double* qpos, const double* qvel, const double* ctrl, double* warm, double* qacc,
@@ -249,6 +252,23 @@ static Engine* make_engine(const ilqg_model& m) {
     return nullptr;
 }
 
+// ------------------------------------------------------------------ fp64 pipe peak (roofline denominator)
+// MEASURED_PEAKS.json carries no fp64 figure, so bench.py measures one: register-resident DFMA chains,
+// 16 independent accumulators per thread, every SM busy.
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double b, double c) {
+    double a[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) a[i] = threadIdx.x * 1e-3 + i;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) a[i] = fma(a[i], b, c);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s += a[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 }  // namespace ilqg
 
 // ==================================================================== C ABI
@@ -263,6 +283,8 @@ struct ilqg_handle_s {
     // staging for the *_host entry points
     void* d_stage = nullptr; size_t stage_cap = 0;
     long launches = 0;  // kernels launched through this handle (bench.py reports it)
+    bool profiling = false;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};  // around the two FD kernels when profiling is on
 };
 
 static thread_local std::string g_create_err;
@@ -326,13 +348,61 @@ int ilqg_destroy(ilqg_handle h) {
     cudaFree(h->d_center);
     cudaFree(h->d_cost);
     cudaFree(h->d_stage);
+    for (int i = 0; i < 3; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     delete h->eng;
     delete h;
     return ILQG_OK;
 }
 
 long ilqg_launch_count(ilqg_handle h) { return h ? h->launches : 0; }
+
+int ilqg_set_profiling(ilqg_handle h, int on) {
+    if (!h) return ILQG_ERR_ARG;
+    CU(h, cudaSetDevice(h->device));
+    if (on && !h->ev[0])
+        for (int i = 0; i < 3; i++) CU(h, cudaEventCreate(&h->ev[i]));
+    h->profiling = on != 0;
+    return ILQG_OK;
+}
+
+int ilqg_fd_last_kernel_ms(ilqg_handle h, float* center_ms, float* perturb_ms) {
+    if (!h || !h->ev[0] || !center_ms || !perturb_ms) return ILQG_ERR_ARG;
+    CU(h, cudaEventSynchronize(h->ev[2]));
+    CU(h, cudaEventElapsedTime(center_ms, h->ev[0], h->ev[1]));
+    CU(h, cudaEventElapsedTime(perturb_ms, h->ev[1], h->ev[2]));
+    return ILQG_OK;
+}
 const char* ilqg_engine_name(ilqg_handle h) { return h && h->eng ? h->eng->name() : ""; }
+
+// diagnostic: sustained fp64 FMA throughput of `device` in TFLOP/s (FMA = 2 flops)
+int ilqg_fp64_peak(int device, double* tflops) {
+    if (!tflops) return ILQG_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return ILQG_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return ILQG_ERR_CUDA;
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 20000;
+    double* out = nullptr;
+    if (cudaMalloc(&out, sizeof(double) * blocks * threads) != cudaSuccess) return ILQG_ERR_CUDA;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double best = 0;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(e0);
+        ilqg::fp64_peak_kernel<<<blocks, threads>>>(out, iters, 0.999999, 1e-9);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(out); return ILQG_ERR_CUDA; }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        double tf = 2.0 * 16 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    *tflops = best;
+    return ILQG_OK;
+}
 
 static int ensure_center(ilqg_handle h, size_t n) {
     if (n <= h->center_cap) return ILQG_OK;
@@ -375,7 +445,7 @@ int ilqg_fd_batch_dev(ilqg_handle h, int nknots, const double* qpos, const doubl
         CU(h, cudaMemcpyAsync(h->d_cost, cost, sizeof(ilqg_cost), cudaMemcpyHostToDevice, s));
         dcost = h->d_cost;
     }
-    CU(h, h->eng->fd(nknots, qpos, qvel, ctrl, warmstart, dcost, o, deriv, center, status, s));
+    CU(h, h->eng->fd(nknots, qpos, qvel, ctrl, warmstart, dcost, o, deriv, center, status, s, h->profiling ? h->ev : nullptr));
     h->launches += 2;
     return ILQG_OK;
 }

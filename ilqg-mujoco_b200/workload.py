@@ -1,0 +1,71 @@
+"""Synthetic workloads of the shapes BASELINE.json names, generated on the GPU through
+the product's own step kernel (no oracle, no reference).  Deterministic for a given seed."""
+import numpy as np
+import torch
+
+
+def hopper_initial_states(n, seed=0):
+    """Config-2 generator: rootz ~ U[1.0,1.4], joint angles within 50 % of their range,
+    qvel ~ N(0,0.5^2), ctrl ~ U[-1,1] (ranges: /root/reference/res/hopper.xml:18,21,24,32-34)."""
+    rng = np.random.default_rng(seed)
+    qpos = np.zeros((n, 6))
+    qpos[:, 0] = rng.uniform(-0.1, 0.1, n)
+    qpos[:, 1] = rng.uniform(1.0, 1.4, n)
+    qpos[:, 2] = rng.uniform(-0.1, 0.1, n)
+    lo = np.array([-150.0, -150.0, -45.0]) * np.pi / 180
+    hi = np.array([0.0, 0.0, 45.0]) * np.pi / 180
+    mid, half = 0.5 * (lo + hi), 0.5 * (hi - lo)
+    qpos[:, 3:] = mid + rng.uniform(-0.5, 0.5, (n, 3)) * half
+    qvel = rng.normal(0, 0.5, (n, 6))
+    ctrl = rng.uniform(-1, 1, (n, 3))
+    roll = rng.integers(0, 11, n) * 20  # pre-roll steps in {0,20,...,200}
+    return qpos, qvel, ctrl, roll
+
+
+def pendulum_initial_states(n, seed=0):
+    """Config-4 generator: slider, hinge ~ U[-0.5,0.5], qvel ~ N(0,0.5^2)."""
+    rng = np.random.default_rng(seed)
+    qpos = rng.uniform(-0.5, 0.5, (n, 2))
+    qvel = rng.normal(0, 0.5, (n, 2))
+    ctrl = rng.uniform(-0.5, 0.5, (n, 1))
+    return qpos, qvel, ctrl, np.zeros(n, dtype=np.int64)
+
+
+def make_knots(handle, ntraj, T, seed=0, device="cuda:0", model="hopper"):
+    """ntraj trajectories x T knots: random initial states, pre-rolled 0..200 steps so that a good share
+    of the knots is in ground contact, then T knots one mj_step apart under constant control.
+    Returns device tensors (qpos[ntraj*T,nq], qvel, ctrl, warm) in trajectory-major order."""
+    m = handle.model
+    gen = hopper_initial_states if model == "hopper" else pendulum_initial_states
+    qpos, qvel, ctrl, roll = gen(ntraj, seed)
+    order = np.argsort(roll, kind="stable")
+    qpos, qvel, ctrl, roll = qpos[order], qvel[order], ctrl[order], roll[order]
+    dq = torch.from_numpy(qpos).to(device)
+    dv = torch.from_numpy(qvel).to(device)
+    du = torch.from_numpy(ctrl).to(device)
+    dw = torch.zeros((ntraj, m.nv), dtype=torch.float64, device=device)
+    # pre-roll: instances sorted by roll count; advance the tail that still has steps to go, 20 at a time
+    for r in range(20, int(roll.max()) + 1, 20):
+        start = int(np.searchsorted(roll, r, side="left"))
+        if start < ntraj:
+            handle.step_batch_dev(dq[start:], dv[start:], du[start:], dw[start:], None, nsteps=20)
+    Q = torch.empty((ntraj, T, m.nq), dtype=torch.float64, device=device)
+    V = torch.empty((ntraj, T, m.nv), dtype=torch.float64, device=device)
+    W = torch.empty((ntraj, T, m.nv), dtype=torch.float64, device=device)
+    for t in range(T):
+        Q[:, t], V[:, t], W[:, t] = dq, dv, dw
+        if t + 1 < T:
+            handle.step_batch_dev(dq, dv, du, dw, None, nsteps=1)
+    U = du[:, None, :].expand(ntraj, T, m.nu).contiguous()
+    torch.cuda.synchronize()
+    # a diverged pre-roll (non-finite state) would poison the benchmark: replace by the model's rest pose
+    bad = ~(torch.isfinite(Q).all(dim=2) & torch.isfinite(V).all(dim=2) & torch.isfinite(W).all(dim=2))
+    nbad = int(bad.sum())
+    if nbad:
+        Q[bad] = 0.0
+        V[bad] = 0.0
+        W[bad] = 0.0
+        if model == "hopper":
+            Q[bad, 1] = 1.25
+    return (Q.reshape(-1, m.nq).contiguous(), V.reshape(-1, m.nv).contiguous(), U.reshape(-1, m.nu).contiguous(),
+            W.reshape(-1, m.nv).contiguous(), nbad)

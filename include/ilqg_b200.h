@@ -110,6 +110,13 @@ int ilqg_step_batch_dev(ilqg_handle h, int n, int nsteps, double* qpos, double* 
 int ilqg_step_batch_host(ilqg_handle h, int n, int nsteps, double* qpos, double* qvel, const double* ctrl,
                          double* warmstart, double* qacc);
 
+/* ---- diagnostics */
+long ilqg_launch_count(ilqg_handle h);        /* kernels launched through this handle so far */
+const char* ilqg_engine_name(ilqg_handle h);  /* name of the kernel instantiation serving this model */
+int ilqg_fp64_peak(int device, double* tflops); /* measured fp64 FMA throughput (roofline denominator) */
+int ilqg_set_profiling(ilqg_handle h, int on);  /* record CUDA events around each FD kernel on the launch stream */
+int ilqg_fd_last_kernel_ms(ilqg_handle h, float* center_ms, float* perturb_ms); /* durations of the last FD call's kernels */
+
 #ifdef __cplusplus
 }
 #endif

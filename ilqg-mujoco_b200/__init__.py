@@ -92,6 +92,18 @@ class Model:
     def ptr(self):
         return self.buf.ctypes.data_as(C.c_void_p)
 
+    def field(self, name):
+        """Writable numpy view of a named table field (see ilqg_model_field)."""
+        off, cnt, dbl = C.c_int(), C.c_int(), C.c_int()
+        rc = lib().ilqg_model_field(name.encode(), C.byref(off), C.byref(cnt), C.byref(dbl))
+        if rc:
+            raise KeyError(name)
+        n = cnt.value * (8 if dbl.value else 4)
+        return self.buf[off.value:off.value + n].view(np.float64 if dbl.value else np.int32)
+
+    def copy(self):
+        return Model(self.buf.copy())
+
 
 def _hp(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None

@@ -59,7 +59,22 @@ struct DevModel {
     double geom_size[T::NGEOM][2], geom_pos[T::NGEOM][3], geom_axis[T::NGEOM][3];
     double pair_margin[nz(T::NPAIR)], pair_mu[nz(T::NPAIR)], pair_solref[nz(T::NPAIR)][2], pair_solimp[nz(T::NPAIR)][5];
     double act_gear[nz(T::NU)], act_range[nz(T::NU)][2];
+    // per-row constants of mj_makeImpedance precomputed on the host: stiffness K, damping B (refsafe applied)
+    // and the impedance when solimp is flat (dmin == dmax), else -1
+    double jnt_K[T::NJNT], jnt_B[T::NJNT], jnt_imp[T::NJNT];
+    double pair_K[nz(T::NPAIR)], pair_B[nz(T::NPAIR)], pair_imp[nz(T::NPAIR)];
 };
+
+inline void host_row_consts(double timestep, const double* solref, const double* solimp, double& K, double& B, double& imp) {
+    auto cl = [](double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); };
+    double tc = solref[0], dr = solref[1];
+    if (tc < 2 * timestep) tc = 2 * timestep;
+    double dmin = cl(solimp[0], 1e-4, 0.9999), dmax = cl(solimp[1], 1e-4, 0.9999);
+    double kk = dmax * dmax * tc * tc * dr * dr, bb = dmax * tc;
+    K = 1.0 / (kk < ILQG_MINVAL ? ILQG_MINVAL : kk);
+    B = 2.0 / (bb < ILQG_MINVAL ? ILQG_MINVAL : bb);
+    imp = (dmin == dmax || solimp[2] <= ILQG_MINVAL) ? 0.5 * (dmin + dmax) : -1.0;
+}
 
 // host: fill from the flat tables; returns false if the tables do not have this topology
 template <class T>
@@ -109,6 +124,7 @@ bool dev_model_from_tables(const ilqg_model& s, DevModel<T>& d) {
         for (int k = 0; k < 5; k++) d.jnt_solimp[j][k] = s.jnt_solimp[j][k];
         d.jnt_stiffness[j] = s.jnt_stiffness[j];
         d.jnt_margin[j] = s.jnt_margin[j];
+        host_row_consts(s.timestep, s.jnt_solref[j], s.jnt_solimp[j], d.jnt_K[j], d.jnt_B[j], d.jnt_imp[j]);
     }
     for (int i = 0; i < T::NQ; i++) { d.qpos0[i] = s.qpos0[i]; d.qpos_spring[i] = s.qpos_spring[i]; }
     for (int i = 0; i < T::NV; i++) { d.dof_armature[i] = s.dof_armature[i]; d.dof_damping[i] = s.dof_damping[i]; d.dof_invw[i] = s.dof_invweight0[i]; }
@@ -126,6 +142,7 @@ bool dev_model_from_tables(const ilqg_model& s, DevModel<T>& d) {
         d.pair_mu[p] = s.pair_friction[p];
         for (int k = 0; k < 2; k++) d.pair_solref[p][k] = s.pair_solref[p][k];
         for (int k = 0; k < 5; k++) d.pair_solimp[p][k] = s.pair_solimp[p][k];
+        host_row_consts(s.timestep, s.pair_solref[p], s.pair_solimp[p], d.pair_K[p], d.pair_B[p], d.pair_imp[p]);
     }
     for (int u = 0; u < T::NU; u++) {
         d.act_gear[u] = s.act_gear[u];
@@ -215,7 +232,7 @@ DEV void chol_packed(const double* A, double* L) {
             sfor<0, j>([&](auto kk) { constexpr int k = IDX(kk); s -= L[tri(i, k)] * L[tri(j, k)]; });
             if constexpr (i == j) {
                 if (s < ILQG_MINVAL) s = ILQG_MINVAL;
-                L[tri(i, i)] = 1.0 / sqrt(s);
+                L[tri(i, i)] = rsqrt(s);
             } else
                 L[tri(i, j)] = s * L[tri(j, j)];
         });
@@ -255,7 +272,9 @@ __host__ __device__ constexpr bool dof_moves_body(int dof, int body) {
     return false;
 }
 
-DEV double impedance(const double* solimp, double pos, double margin) {
+// position-dependent impedance d(r) (getimpedance); one out-of-line copy — it holds two pow() expansions and
+// is only reached for non-flat solimp
+__device__ __noinline__ double impedance(const double* solimp, double pos, double margin) {
     double dmin = clampd(solimp[0], 1e-4, 0.9999), dmax = clampd(solimp[1], 1e-4, 0.9999);
     double width = solimp[2], mid = clampd(solimp[3], 1e-4, 0.9999), power = solimp[4] < 1 ? 1 : solimp[4];
     if (dmin == dmax || width <= ILQG_MINVAL) return 0.5 * (dmin + dmax);
@@ -270,19 +289,13 @@ DEV double impedance(const double* solimp, double pos, double margin) {
     return dmin + y * (dmax - dmin);
 }
 
-// regulariser R, damping B and stiffness term K*imp*(pos-margin) of one row
-// (mj_makeImpedance + mj_referenceConstraint: aref = -B*vel - kterm)
-DEV void row_params(double timestep, const double* solref, const double* solimp, double pos, double margin, double diagApprox,
-                    double& R, double& B, double& kterm) {
-    double tc = solref[0], dr = solref[1];
-    if (tc < 2 * timestep) tc = 2 * timestep;
-    double dmax = clampd(solimp[1], 1e-4, 0.9999);
-    double imp = impedance(solimp, pos, margin);
+// regulariser R and stiffness term K*imp*(pos-margin) of one row
+// (mj_makeImpedance + mj_referenceConstraint: aref = -B*vel - kterm); K, B, flat impedance come precomputed
+DEV void row_params(double K, double flat_imp, const double* solimp, double pos, double margin, double diagApprox, double& R,
+                    double& kterm) {
+    double imp = flat_imp >= 0 ? flat_imp : impedance(solimp, pos, margin);
     R = (1 - imp) / imp * diagApprox;
     if (R < ILQG_MINVAL) R = ILQG_MINVAL;
-    double kk = dmax * dmax * tc * tc * dr * dr, bb = dmax * tc;
-    double K = 1.0 / (kk < ILQG_MINVAL ? ILQG_MINVAL : kk);
-    B = 2.0 / (bb < ILQG_MINVAL ? ILQG_MINVAL : bb);
     kterm = K * imp * (pos - margin);
 }
 
@@ -474,8 +487,9 @@ DEV void build_problem(const DevModel<T>& m, const double (&q)[T::NQ], const dou
                 constexpr int side = 2 * IDX(ss) - 1;
                 double dist = side * (m.jnt_range[j][IDX(ss)] - value);
                 if (dist < m.jnt_margin[j]) {
-                    double R, B, kt;
-                    row_params(m.timestep, m.jnt_solref[j], m.jnt_solimp[j], dist, m.jnt_margin[j], m.dof_invw[da], R, B, kt);
+                    double R, kt;
+                    const double B = m.jnt_B[j];
+                    row_params(m.jnt_K[j], m.jnt_imp[j], m.jnt_solimp[j], dist, m.jnt_margin[j], m.dof_invw[da], R, kt);
                     sfor<0, NV>([&](auto ii) { w.J[ne][IDX(ii)] = IDX(ii) == da ? -side : 0.0; });
                     w.D[ne] = 1.0 / R;
                     w.aref[ne] = -B * (-side * qv[da]) - kt;
@@ -519,17 +533,19 @@ DEV void build_problem(const DevModel<T>& m, const double (&q)[T::NQ], const dou
                 double tran = m.body_invw[b1] + m.body_invw[b2];
                 if (tran < ILQG_MINVAL) tran = ILQG_MINVAL;
                 if constexpr (condim == 1) {
-                    double R, B, kt;
-                    row_params(m.timestep, m.pair_solref[p], m.pair_solimp[p], dist, margin, tran, R, B, kt);
+                    double R, kt;
+                    const double B = m.pair_B[p];
+                    row_params(m.pair_K[p], m.pair_imp[p], m.pair_solimp[p], dist, margin, tran, R, kt);
                     sfor<0, NV>([&](auto ii) { w.J[ne][IDX(ii)] = jn[IDX(ii)]; });
                     w.D[ne] = 1.0 / R;
                     w.aref[ne] = -B * vn - kt;
                     ne++;
                 } else {
                     const double mu = m.pair_mu[p];
-                    double R0, B, kt;
+                    double R0, kt;
+                    const double B = m.pair_B[p];
                     // all four facets share pos/margin; R of the first facet sets the pyramid's regulariser
-                    row_params(m.timestep, m.pair_solref[p], m.pair_solimp[p], dist, margin, tran * (1 + mu * mu), R0, B, kt);
+                    row_params(m.pair_K[p], m.pair_imp[p], m.pair_solimp[p], dist, margin, tran * (1 + mu * mu), R0, kt);
                     double Rpy = 2 * mu * mu * R0;
                     if (Rpy < ILQG_MINVAL) Rpy = ILQG_MINVAL;
                     double Dpy = 1.0 / Rpy;
@@ -651,9 +667,19 @@ DEV double problem_cost(const Work<T>& w, const double* a) {
 
 // Newton with exact linesearch on the convex piecewise-quadratic cost.  `warm` in: qacc_warmstart;
 // out: the solution (which is also the next warm start, as in MuJoCo 2.x).  qacc out.
+//
+// Termination: MuJoCo's rule (scaled cost improvement or gradient below `tol`, or `maxiter`), plus an exact
+// optimality test that makes tol = 0 cheap: when the line minimiser lands in the same quadratic piece the
+// Hessian was built for (same active set before and after the step), the step was a full Newton step onto
+// that piece's minimiser and the piece is the right one — the point is the global minimum up to the
+// round-off of the linear solve, and further iterations (which the reference's tol = 0 setting would
+// spend until the cost stops decreasing in fp64) only add rounding noise.
 template <class T>
-DEV void solve(const DevModel<T>& m, Work<T>& w, double (&warm)[T::NV], double (&qacc)[T::NV], int maxiter, double tol) {
+DEV void solve(const DevModel<T>& m, Work<T>& w, double (&warm)[T::NV], double (&qacc)[T::NV], int maxiter, double tol,
+               bool need_forces = false) {
     constexpr int NV = T::NV, NT = NV * (NV + 1) / 2;
+    static_assert(T::MAXEFC <= 64, "active-set masks are 64-bit: larger models use the cooperative kernel");
+    typedef unsigned long long mask_t;
     const int ne = w.nefc;
     w.iters = 0;
     if (ne == 0) {
@@ -678,44 +704,53 @@ DEV void solve(const DevModel<T>& m, Work<T>& w, double (&warm)[T::NV], double (
         sfor<0, NV>([&](auto ii) { s += w.J[r][IDX(ii)] * qacc[IDX(ii)]; });
         w.jar[r] = s;
     }
-    double cost = 0;
-    // cost, gradient, Hessian factor and Newton direction at the current point
-    auto update = [&]() {
-        double H[NT], Lh[NT];
-        sfor<0, NT>([&](auto tt) { H[IDX(tt)] = w.M[IDX(tt)]; });
-        sfor<0, NV>([&](auto ii) { w.fc[IDX(ii)] = 0; });
-        double c = 0;
-        for (int r = 0; r < ne; r++) {
-            double jar = w.jar[r];
-            if (jar < 0) {
-                double D = w.D[r];
-                double Jr[NV];
-                sfor<0, NV>([&](auto ii) { Jr[IDX(ii)] = w.J[r][IDX(ii)]; });
-                double f = -D * jar;
-                c += 0.5 * D * jar * jar;
-                sfor<0, NV>([&](auto ii) {
-                    constexpr int i = IDX(ii);
-                    w.fc[i] += Jr[i] * f;
-                    double t = D * Jr[i];
-                    sfor<0, i + 1>([&](auto kk) { H[tri(i, IDX(kk))] += t * Jr[IDX(kk)]; });
-                });
-            }
-        }
-        sfor<0, NV>([&](auto ii) {
-            constexpr int i = IDX(ii);
-            c += 0.5 * (Ma[i] - w.fs[i]) * (qacc[i] - w.as[i]);
-            grad[i] = Ma[i] - w.fs[i] - w.fc[i];
-            search[i] = grad[i];
-        });
-        cost = c;
-        chol_packed<NV>(H, Lh);
-        chol_solve_packed<NV>(Lh, search);
-        sfor<0, NV>([&](auto ii) { search[IDX(ii)] = -search[IDX(ii)]; });
-    };
-    update();
+    double cost = 0, old = 0;
     int iter = 0;
-    while (iter < maxiter) {
-        // ---- exact linesearch
+    bool forces_current = false;
+    for (;;) {
+        // ---- cost, gradient, Hessian factor and Newton direction at the current point
+        mask_t act = 0;
+        {
+            double H[NT], Lh[NT];
+            sfor<0, NT>([&](auto tt) { H[IDX(tt)] = w.M[IDX(tt)]; });
+            sfor<0, NV>([&](auto ii) { w.fc[IDX(ii)] = 0; });
+            double c = 0;
+            for (int r = 0; r < ne; r++) {
+                double jar = w.jar[r];
+                if (jar < 0) {
+                    act |= (mask_t)1 << r;
+                    double D = w.D[r];
+                    double Jr[NV];
+                    sfor<0, NV>([&](auto ii) { Jr[IDX(ii)] = w.J[r][IDX(ii)]; });
+                    double f = -D * jar;
+                    c += 0.5 * D * jar * jar;
+                    sfor<0, NV>([&](auto ii) {
+                        constexpr int i = IDX(ii);
+                        w.fc[i] += Jr[i] * f;
+                        double t = D * Jr[i];
+                        sfor<0, i + 1>([&](auto kk) { H[tri(i, IDX(kk))] += t * Jr[IDX(kk)]; });
+                    });
+                }
+            }
+            sfor<0, NV>([&](auto ii) {
+                constexpr int i = IDX(ii);
+                c += 0.5 * (Ma[i] - w.fs[i]) * (qacc[i] - w.as[i]);
+                grad[i] = Ma[i] - w.fs[i] - w.fc[i];
+                search[i] = grad[i];
+            });
+            cost = c;
+            forces_current = true;
+            chol_packed<NV>(H, Lh);
+            chol_solve_packed<NV>(Lh, search);
+            sfor<0, NV>([&](auto ii) { search[IDX(ii)] = -search[IDX(ii)]; });
+        }
+        if (iter > 0) {
+            double gn = 0;
+            sfor<0, NV>([&](auto ii) { gn += grad[IDX(ii)] * grad[IDX(ii)]; });
+            if (scale * (old - cost) < tol || scale * sqrt(gn) < tol) break;
+        }
+        if (iter >= maxiter) break;
+        // ---- exact linesearch: root of the piecewise-linear derivative along `search`
         double g1 = 0, g2 = 0;
         sfor<0, NV>([&](auto ii) {
             constexpr int i = IDX(ii);
@@ -724,44 +759,62 @@ DEV void solve(const DevModel<T>& m, Work<T>& w, double (&warm)[T::NV], double (
             Mv[i] = s;
         });
         sfor<0, NV>([&](auto ii) { constexpr int i = IDX(ii); g1 += search[i] * (Ma[i] - w.fs[i]); g2 += search[i] * Mv[i]; });
+        double d1 = g1, d2 = g2;
         for (int r = 0; r < ne; r++) {
             double s = 0;
             sfor<0, NV>([&](auto ii) { s += w.J[r][IDX(ii)] * search[IDX(ii)]; });
             w.jv[r] = s;
-        }
-        double alpha = 0, lo = 0, hi = CUDART_INF;
-        bool descent = true;
-        for (int it = 0; it < m.ls_iterations; it++) {
-            double d1 = g1 + g2 * alpha, d2 = g2;
-            for (int r = 0; r < ne; r++) {
-                double jv = w.jv[r];
-                double x = w.jar[r] + alpha * jv;
-                if (x < 0) {
-                    double t = w.D[r] * jv;
-                    d1 += t * x;
-                    d2 += t * jv;
-                }
+            if ((act >> r) & 1) {
+                double t = w.D[r] * s;
+                d1 += t * w.jar[r];
+                d2 += t * s;
             }
-            if (it == 0 && d1 >= 0) { descent = false; break; }
-            if (d1 == 0) break;
+        }
+        if (d1 >= 0 || d2 < ILQG_MINVAL) break;  // not a descent direction: converged to round-off
+        double alpha = 0, lo = 0, hi = CUDART_INF;
+        mask_t cur = act;   // active set at `alpha`
+        mask_t reached = act;
+        for (int it = 0; it < m.ls_iterations; it++) {
             if (d1 < 0) lo = alpha; else hi = alpha;
-            if (d2 < ILQG_MINVAL) break;
             double an = alpha - d1 / d2;
             if (!(an > lo && an < hi)) an = isinf(hi) ? 2 * alpha + 1 : 0.5 * (lo + hi);
-            bool done = fabs(an - alpha) <= 1e-14 * fabs(an);
+            double e1 = g1 + g2 * an, e2 = g2;
+            mask_t mk = 0;
+            for (int r = 0; r < ne; r++) {
+                double jv = w.jv[r];
+                double x = w.jar[r] + an * jv;
+                if (x < 0) {
+                    double t = w.D[r] * jv;
+                    e1 += t * x;
+                    e2 += t * jv;
+                    mk |= (mask_t)1 << r;
+                }
+            }
+            bool same = mk == cur;  // the step stayed inside one linear piece of the derivative: `an` is its root
             alpha = an;
-            if (done) break;
+            d1 = e1;
+            d2 = e2;
+            cur = mk;
+            reached = mk;
+            if (same || d1 == 0 || d2 < ILQG_MINVAL) break;
         }
-        if (!descent || alpha == 0) break;
+        if (alpha == 0) break;
         sfor<0, NV>([&](auto ii) { constexpr int i = IDX(ii); qacc[i] += alpha * search[i]; Ma[i] += alpha * Mv[i]; });
         for (int r = 0; r < ne; r++) w.jar[r] += alpha * w.jv[r];
-        double old = cost;
-        update();
+        old = cost;
         iter++;
-        double gn = 0;
-        sfor<0, NV>([&](auto ii) { gn += grad[IDX(ii)] * grad[IDX(ii)]; });
-        double improvement = scale * (old - cost), gradient = scale * sqrt(gn);
-        if (improvement < tol || gradient < tol) break;
+        forces_current = false;
+        if (reached == act) break;  // exact optimum (see above)
+    }
+    if (need_forces && !forces_current) {  // qfrc_constraint at the final point (the integrators need it)
+        sfor<0, NV>([&](auto ii) { w.fc[IDX(ii)] = 0; });
+        for (int r = 0; r < ne; r++) {
+            double jar = w.jar[r];
+            if (jar < 0) {
+                double f = -w.D[r] * jar;
+                sfor<0, NV>([&](auto ii) { w.fc[IDX(ii)] += w.J[r][IDX(ii)] * f; });
+            }
+        }
     }
     w.iters = iter;
     sfor<0, NV>([&](auto ii) { warm[IDX(ii)] = qacc[IDX(ii)]; });
@@ -798,7 +851,7 @@ DEV void step(const DevModel<T>& m, Work<T>& w, double (&q)[T::NQ], double (&v)[
     constexpr int NV = T::NV, NQ = T::NQ, NT = NV * (NV + 1) / 2;
     const double h = m.timestep;
     build_problem<T>(m, q, v, u, w);
-    solve<T>(m, w, warm, qacc, m.iterations, m.tolerance);
+    solve<T>(m, w, warm, qacc, m.iterations, m.tolerance, true);
     if (m.integrator == ILQG_INT_RK4) {
         double q0[NQ], v0[NV], X[4][NV], F[4][NV], dX[NV], dF[NV];
         sfor<0, NQ>([&](auto ii) { q0[IDX(ii)] = q[IDX(ii)]; });

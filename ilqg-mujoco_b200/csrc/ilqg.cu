@@ -12,6 +12,7 @@
 #include <math_constants.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -72,8 +73,8 @@ struct FdShape {
     static_assert(G <= 32, "thread-per-rollout FD kernel needs 2(2nv+nu) <= 32; larger models use the cooperative kernel");
 };
 
-template <class T, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) fd_perturb_kernel(const __grid_constant__ DevModel<T> m, int nknots,
+template <class T, int WARPS, int MINBLOCKS>
+__global__ void __launch_bounds__(WARPS * 32, MINBLOCKS) fd_perturb_kernel(const __grid_constant__ DevModel<T> m, int nknots,
                                                                  const double* __restrict__ qpos, const double* __restrict__ qvel,
                                                                  const double* __restrict__ ctrl, const double* __restrict__ qacc_center,
                                                                  const ilqg_cost* __restrict__ cost, double eps, int niter,
@@ -199,6 +200,7 @@ __global__ void __launch_bounds__(128) step_kernel(const __grid_constant__ DevMo
 
 // ------------------------------------------------------------------ engines (one per compiled-in topology)
 struct Engine {
+    int fd_minblocks = 2;
     virtual ~Engine() {}
     virtual const char* name() const = 0;
     virtual cudaError_t fd(int nknots, const double* qpos, const double* qvel, const double* ctrl, const double* warm,
@@ -223,8 +225,12 @@ struct EngineT : Engine {
         fd_center_kernel<T><<<(nknots + 127) / 128, 128, 0, s>>>(dm, nknots, qpos, qvel, ctrl, warm, o.niter, o.nwarmup, qacc_center, status);
         if (ev) cudaEventRecord(ev[1], s);
         int nwarps = (nknots + S::KPW - 1) / S::KPW;
-        fd_perturb_kernel<T, WARPS><<<(nwarps + WARPS - 1) / WARPS, WARPS * 32, 0, s>>>(dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps,
-                                                                                     o.niter, deriv, status);
+        dim3 grid((nwarps + WARPS - 1) / WARPS), block(WARPS * 32);
+        switch (fd_minblocks) {  // register budget of the perturb kernel: 255 / 168 / 128 per thread
+            case 4: fd_perturb_kernel<T, WARPS, 4><<<grid, block, 0, s>>>(dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps, o.niter, deriv, status); break;
+            case 3: fd_perturb_kernel<T, WARPS, 3><<<grid, block, 0, s>>>(dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps, o.niter, deriv, status); break;
+            default: fd_perturb_kernel<T, WARPS, 2><<<grid, block, 0, s>>>(dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps, o.niter, deriv, status); break;
+        }
         if (ev) cudaEventRecord(ev[2], s);
         return cudaGetLastError();
     }
@@ -333,6 +339,7 @@ int ilqg_create(const ilqg_model* m, int device, ilqg_handle* out) {
     h->device = device;
     h->model = *m;
     h->eng = eng;
+    if (const char* e = getenv("ILQG_FD_MINBLOCKS")) eng->fd_minblocks = atoi(e);
     if (cudaMalloc(&h->d_cost, sizeof(ilqg_cost)) != cudaSuccess) {
         delete eng;
         delete h;

@@ -13,6 +13,7 @@
 // Jacobian formulation  M = sum_b m Jp'Jp + Jr' I Jr  — deliberately a different algorithm from
 // the CRBA used by the oracle and the kernels, so tests can cross-check the three.
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -734,3 +735,27 @@ extern "C" int ilqg_model_load(const char* path, ilqg_model* m) {
 }
 
 extern "C" int ilqg_model_sizeof(void) { return (int)sizeof(ilqg_model); }
+
+// byte offset and element count of a named field of ilqg_model (for bindings that treat the table as bytes)
+extern "C" int ilqg_model_field(const char* name, int* offset, int* count, int* is_double) {
+#define F(field, n, dbl)                                   \
+    if (!strcmp(name, #field)) {                           \
+        *offset = (int)offsetof(ilqg_model, field);        \
+        *count = (n);                                      \
+        *is_double = (dbl);                                \
+        return ILQG_OK;                                    \
+    }
+    if (!name || !offset || !count || !is_double) return ILQG_ERR_ARG;
+    F(timestep, 1, 1) F(gravity, 3, 1) F(tolerance, 1, 1) F(meaninertia, 1, 1) F(integrator, 1, 0) F(iterations, 1, 0)
+    F(npair, 1, 0) F(body_parentid, ILQG_MAXBODY, 0) F(body_mass, ILQG_MAXBODY, 1) F(body_ipos, ILQG_MAXBODY * 3, 1)
+    F(body_inertia, ILQG_MAXBODY * 6, 1) F(body_invweight0, ILQG_MAXBODY * 2, 1) F(body_pos, ILQG_MAXBODY * 3, 1)
+    F(jnt_type, ILQG_MAXJNT, 0) F(jnt_limited, ILQG_MAXJNT, 0) F(jnt_range, ILQG_MAXJNT * 2, 1) F(jnt_stiffness, ILQG_MAXJNT, 1)
+    F(jnt_axis, ILQG_MAXJNT * 3, 1) F(jnt_pos, ILQG_MAXJNT * 3, 1) F(jnt_solimp, ILQG_MAXJNT * 5, 1) F(qpos0, ILQG_MAXQ, 1)
+    F(dof_armature, ILQG_MAXV, 1) F(dof_damping, ILQG_MAXV, 1) F(dof_invweight0, ILQG_MAXV, 1) F(dof_parentid, ILQG_MAXV, 0)
+    F(geom_type, ILQG_MAXGEOM, 0) F(geom_size, ILQG_MAXGEOM * 3, 1) F(geom_pos, ILQG_MAXGEOM * 3, 1) F(geom_quat, ILQG_MAXGEOM * 4, 1)
+    F(pair_geom1, ILQG_MAXPAIR, 0) F(pair_geom2, ILQG_MAXPAIR, 0) F(pair_condim, ILQG_MAXPAIR, 0) F(pair_margin, ILQG_MAXPAIR, 1)
+    F(pair_friction, ILQG_MAXPAIR, 1) F(pair_solref, ILQG_MAXPAIR * 2, 1) F(pair_solimp, ILQG_MAXPAIR * 5, 1)
+    F(act_dofid, ILQG_MAXU, 0) F(act_gear, ILQG_MAXU, 1) F(act_ctrllimited, ILQG_MAXU, 0) F(act_ctrlrange, ILQG_MAXU * 2, 1)
+#undef F
+    return ILQG_ERR_ARG;
+}

@@ -50,6 +50,8 @@ int ilqg_compile_mjcf_string(const char* xml, ilqg_model* out, char* err, int er
 int ilqg_model_save(const char* path, const ilqg_model* m);
 int ilqg_model_load(const char* path, ilqg_model* m);
 int ilqg_model_sizeof(void);
+/* byte offset / element count / type of a named ilqg_model field (bindings that hold the table as bytes) */
+int ilqg_model_field(const char* name, int* offset, int* count, int* is_double);
 
 /* ---- GPU-resident model (the role of mjModel* in every reference call) */
 int ilqg_create(const ilqg_model* m, int device, ilqg_handle* out);

@@ -1,0 +1,175 @@
+"""GPU parity of the FD linearisation (through the C ABI) against the CPU oracle and the golden fixtures.
+
+Tolerance (stated): per deriv block, max-abs difference <= 1e-6 * max(1, ||block||_inf).
+The central difference divides by 2e-6, so this bounds the disagreement of the underlying accelerations
+at ~1e-12 relative — round-off of two independent fp64 implementations (FMA contraction on the GPU, none
+in the oracle).  Knots whose contact active set flips inside the +/-1e-6 stencil are the only legitimate
+outliers; none occur in the seeded sets below."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, scenario_states
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(ROOT, "tests", "golden")
+TOL = 1e-6
+
+
+def blocks(nv, nu):
+    return {"dqacc/dqpos": slice(0, nv * nv), "dqacc/dqvel": slice(nv * nv, 2 * nv * nv), "dqacc/dctrl": slice(2 * nv * nv, 2 * nv * nv + nv * nu),
+            "dcost": slice(2 * nv * nv + nv * nu, 2 * nv * nv + nv * nu + 2 * nv + nu)}
+
+
+def assert_deriv_close(d_gpu, d_ref, nv, nu, tol=TOL):
+    for name, sl in blocks(nv, nu).items():
+        a, b = d_gpu[:, sl], d_ref[:, sl]
+        scale = np.maximum(1.0, np.abs(b).max(axis=1))
+        err = np.abs(a - b).max(axis=1) / scale
+        assert err.max() <= tol, (name, err.max(), int(err.argmax()))
+
+
+@pytest.mark.parametrize("name", ["inverted_pendulum", "hopper"])
+def test_golden_vectors(handles, name):
+    h = handles[name]; m = h.model
+    g = np.load(os.path.join(GOLD, f"fd_{name}.npz"))
+    deriv, qacc, status = h.fd_batch_host(g["qpos"], g["qvel"], g["ctrl"], g["warm"], g["cost"])
+    assert status.sum() == 0
+    assert_deriv_close(deriv, g["deriv"], m.nv, m.nu)
+    assert np.allclose(qacc, g["qacc"], rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("name,n,roll", [("inverted_pendulum", 257, 0), ("inverted_pendulum", 64, 25), ("hopper", 200, 0),
+                                         ("hopper", 96, 150), ("hopper", 33, 400)])
+def test_parity_with_oracle_on_seeded_states(handles, oracle, omodels, name, n, roll):
+    h = handles[name]; m = h.model; om = omodels[name]
+    q, v, u, w = scenario_states(name, n, seed=100 + roll, oracle=oracle, om=om, roll=roll)
+    cost = oracle.make_cost(q2=[1, 10], v2=[1, 10], u2=[1], q1=[0.5])
+    d_ref, a_ref, _ = oracle.fd_batch(om, q, v, u, w, cost)
+    d_gpu, a_gpu, status = h.fd_batch_host(q, v, u, w, cost)
+    assert status.sum() == 0
+    assert_deriv_close(d_gpu, d_ref, m.nv, m.nu)
+    assert np.allclose(a_gpu, a_ref, rtol=1e-9, atol=1e-9)
+
+
+def test_reference_test_scenario(handles, oracle, omodels):
+    """/root/reference/tst/test_derivatives.cpp:38-56: hopper, 500 passive steps, ctrl -= 0.1, linearise, cost = qpos[0]."""
+    h = handles["hopper"]; om = omodels["hopper"]
+    q = np.array([[0, 1.25, 0, 0, 0, 0.0]]); z = np.zeros((1, 6)); u = np.zeros((1, 3))
+    q, v, w, _ = h.step_batch_host(q, z, u, z.copy(), nsteps=500)
+    qo, vo, wo, _ = oracle.step_batch(om, np.array([[0, 1.25, 0, 0, 0, 0.0]]), z, u, z.copy(), 500)
+    assert np.allclose(q, qo, atol=1e-7) and np.allclose(v, vo, atol=1e-6)  # 500 contact-rich steps, two implementations
+    u = u - 0.1
+    cost = oracle.make_cost(q1=[1.0])
+    d_gpu, _, status = h.fd_batch_host(qo, vo, u, wo, cost)
+    d_ref, _, _ = oracle.fd_batch(om, qo, vo, u, wo, cost)
+    assert status[0] == 0
+    assert_deriv_close(d_gpu, d_ref, 6, 3)
+    assert d_gpu[0, -15] == pytest.approx(1.0, abs=1e-9)  # dg/dqpos[0] of cost = qpos[0]
+
+
+def test_joint_limits_active(handles, oracle, omodels):
+    h = handles["inverted_pendulum"]; om = omodels["inverted_pendulum"]
+    q = np.array([[1.01, 0.2], [-1.02, -0.4], [0.3, 1.58], [0.999999, -1.5707], [1.0, 0.0]])
+    v = np.array([[0.3, 0.1], [-0.2, 0.3], [0.0, 0.5], [0.1, -0.1], [0.0, 0.0]]); u = np.zeros((5, 1)) + 0.2
+    w = np.zeros((5, 2))
+    d_ref, _, _ = oracle.fd_batch(om, q, v, u, w, None)
+    d_gpu, _, status = h.fd_batch_host(q, v, u, w, None)
+    assert status.sum() == 0
+    # rows 3 and 4 sit on a limit boundary: the active set flips inside the stencil, so only the smooth knots are compared tightly
+    assert_deriv_close(d_gpu[:3], d_ref[:3], 2, 1)
+    assert np.isfinite(d_gpu).all()
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 31, 32, 33, 95, 97])
+def test_ragged_batch_sizes(handles, oracle, omodels, n):
+    """Empty and ragged batches (3 pendulum knots share a warp; hopper uses one warp per knot)."""
+    for name in ("inverted_pendulum", "hopper"):
+        h = handles[name]; m = h.model; om = omodels[name]
+        q, v, u, w = scenario_states(name, max(n, 1), seed=n)
+        q, v, u, w = q[:n], v[:n], u[:n], w[:n]
+        d_gpu, a_gpu, status = h.fd_batch_host(q, v, u, w, None)
+        assert d_gpu.shape == (n, m.nd)
+        if n:
+            d_ref, _, _ = oracle.fd_batch(om, q, v, u, w, None)
+            assert_deriv_close(d_gpu, d_ref, m.nv, m.nu)
+
+
+def test_null_cost_leaves_gradient_entries_untouched(handles):
+    h = handles["hopper"]; m = h.model
+    q, v, u, w = scenario_states("hopper", 5, seed=1)
+    deriv = np.full((5, m.nd), 123.25)
+    d, _, _ = h.fd_batch_host(q, v, u, w, None, deriv=deriv)
+    njac = m.nv * (2 * m.nv + m.nu)
+    assert (d[:, njac:] == 123.25).all() and not (d[:, :njac] == 123.25).any()
+
+
+def test_cost_gradient_is_bit_exact_vs_host_arithmetic(handles, oracle, omodels):
+    """The forward-difference cost rows are computed with the caller's arithmetic (no FMA contraction)."""
+    h = handles["inverted_pendulum"]; om = omodels["inverted_pendulum"]
+    q, v, u, w = scenario_states("inverted_pendulum", 64, seed=9)
+    cost = oracle.make_cost(q2=[1, 10], v2=[1, 10], u2=[1])
+    d_ref, _, _ = oracle.fd_batch(om, q, v, u, w, cost)
+    d_gpu, _, _ = h.fd_batch_host(q, v, u, w, cost)
+    assert np.array_equal(d_gpu[:, 10:], d_ref[:, 10:])
+
+
+def test_nonfinite_input_is_flagged_not_fatal(handles, pkg):
+    h = handles["hopper"]
+    q, v, u, w = scenario_states("hopper", 4, seed=2)
+    q[2, 1] = np.nan
+    d, _, status = h.fd_batch_host(q, v, u, w, None)
+    assert status[2] == pkg.ERR_NONFINITE and status[0] == 0 and status[1] == 0 and status[3] == 0
+    assert np.isfinite(d[[0, 1, 3]]).all()
+
+
+def test_bad_arguments(handles, pkg):
+    h = handles["hopper"]
+    L = pkg.lib()
+    assert L.ilqg_fd_batch_host(h._h, 4, None, None, None, None, None, None, None, None, None) == pkg.ERR_ARG
+    opts = pkg.FdOpts(eps=-1.0, niter=30, nwarmup=3)
+    q, v, u, w = scenario_states("hopper", 2, seed=2)
+    with pytest.raises(pkg.IlqgError):
+        h.fd_batch_host(q, v, u, w, None, opts=opts)
+
+
+def test_full_size_properties(handles, pkg):
+    """BASELINE configs[1] at full size (4096 x 21 knots): size-independent properties instead of the oracle.
+    (1) all knots finite; (2) device-pointer and host-pointer paths agree bit for bit; (3) idempotence;
+    (4) the control Jacobian of flight knots equals M^-1 * gear (linearity in ctrl): checked via
+        qacc(u + du) - qacc(u) = B du through the forward kernel on a subsample."""
+    import torch
+    from ilqg_mujoco_b200 import workload as wl
+    h = handles["hopper"]; m = h.model
+    q, v, u, w, nbad = wl.make_knots(h, 4096, 21, seed=0, device="cuda:0")
+    nk = q.shape[0]
+    assert nk == 4096 * 21 and nbad == 0
+    deriv = torch.zeros((nk, m.nd), dtype=torch.float64, device="cuda:0")
+    qacc = torch.zeros((nk, m.nv), dtype=torch.float64, device="cuda:0")
+    status = torch.zeros(nk, dtype=torch.int32, device="cuda:0")
+    h.fd_batch_dev(q, v, u, w, deriv, qacc, status, cost=None)
+    torch.cuda.synchronize()
+    assert int(status.sum()) == 0 and bool(torch.isfinite(deriv[:, :90]).all())
+    d2 = torch.zeros_like(deriv)
+    h.fd_batch_dev(q, v, u, w, d2, qacc, status, cost=None)
+    torch.cuda.synchronize()
+    assert torch.equal(deriv, d2)                       # idempotent / deterministic
+    dh, _, st = h.fd_batch_host(q.cpu().numpy(), v.cpu().numpy(), u.cpu().numpy(), w.cpu().numpy(), None)
+    assert np.array_equal(dh[:, :90], deriv[:, :90].cpu().numpy())
+    # linearity in ctrl inside the clamp range: finite control step predicted by the FD block
+    idx = torch.arange(0, nk, 97, device="cuda:0")
+    qs, vs, us, ws = q[idx].contiguous(), v[idx].contiguous(), (0.5 * u[idx]).contiguous(), w[idx].contiguous()
+    n = qs.shape[0]
+    dd = torch.zeros((n, m.nd), dtype=torch.float64, device="cuda:0"); a0 = torch.zeros((n, 6), dtype=torch.float64, device="cuda:0")
+    h.fd_batch_dev(qs, vs, us, ws, dd, a0, None, cost=None)
+    du = torch.full((n, 3), 1e-3, dtype=torch.float64, device="cuda:0")
+    a1 = torch.zeros_like(a0); wtmp = a0.clone()
+    h.forward_batch_dev(qs, vs, (us + du).contiguous(), wtmp, a1)
+    torch.cuda.synchronize()
+    B = dd[:, 72:90].reshape(n, 6, 3)                   # d qacc_j / d ctrl_i at i + j*nu
+    pred = torch.einsum("nji,ni->nj", B, du)
+    err = (a1 - a0 - pred).abs().max(dim=1).values / (1 + (a1 - a0).abs().max(dim=1).values)
+    # contact knots are piecewise linear: allow the few whose active set changes under the 1e-3 step
+    assert float(err.median()) < 1e-6 and float((err < 1e-4).double().mean()) > 0.9

@@ -202,3 +202,55 @@ class Handle:
         n = qpos.shape[0]
         self._check(lib().ilqg_forward_batch_dev(self._h, n, _dp(qpos), _dp(qvel), _dp(ctrl), _dp(warm), _dp(qacc),
                                                  C.c_void_p(stream) if stream else None))
+
+
+class Ilqr:
+    """Batched iLQR workspace on the GPU (ilqg_ilqr_*): the role of `ILQR<nv,nu,N>` for `ninst` problems."""
+
+    def __init__(self, handle, ninst, N, alphas=(1.0,)):
+        self.h, self.ninst, self.N = handle, int(ninst), int(N)
+        al = np.ascontiguousarray(alphas, np.float64)
+        self._w = C.c_void_p()
+        handle._check(lib().ilqg_ilqr_create(handle._h, self.ninst, self.N, len(al), _hp(al), C.byref(self._w)))
+
+    def close(self):
+        if self._w:
+            lib().ilqg_ilqr_destroy(self._w)
+            self._w = C.c_void_p()
+
+    def set_cost(self, cost):
+        self.h._check(lib().ilqg_ilqr_set_cost(self._w, _hp(cost)))
+
+    def set_mu(self, mu):
+        self.h._check(lib().ilqg_ilqr_set_mu(self._w, C.c_double(mu)))
+
+    def init_host(self, qpos, qvel, ctrl, warm=None):
+        m = self.h.model
+        a = [np.ascontiguousarray(x, np.float64) if x is not None else None for x in (qpos, qvel, ctrl, warm)]
+        assert a[0].shape == (self.ninst, m.nq) and a[1].shape == (self.ninst, m.nv)
+        self.h._check(lib().ilqg_ilqr_init_host(self._w, _hp(a[0]), _hp(a[1]), _hp(a[2]), _hp(a[3])))
+
+    def set_state_host(self, qpos, qvel, warm=None):
+        a = [np.ascontiguousarray(x, np.float64) if x is not None else None for x in (qpos, qvel, warm)]
+        self.h._check(lib().ilqg_ilqr_set_state_host(self._w, _hp(a[0]), _hp(a[1]), _hp(a[2])))
+
+    def init_dev(self, qpos, qvel, ctrl, warm=None, stream=None):
+        self.h._check(lib().ilqg_ilqr_init_dev(self._w, _dp(qpos), _dp(qvel), _dp(ctrl), _dp(warm), C.c_void_p(stream) if stream else None))
+
+    def iterate(self, niter=1, accept_always=True, stream=None):
+        self.h._check(lib().ilqg_ilqr_iterate(self._w, int(niter), 1 if accept_always else 0, C.c_void_p(stream) if stream else None))
+
+    @property
+    def iterations(self):
+        return int(lib().ilqg_ilqr_iterations_done(self._w))
+
+    def get(self):
+        m = self.h.model
+        n, T, nx = self.ninst, self.N + 1, 2 * m.nv
+        kept = min(self.iterations, 256)
+        out = dict(qpos=np.zeros((n, T, m.nq)), qvel=np.zeros((n, T, m.nv)), ctrl=np.zeros((n, T, m.nu)), K=np.zeros((n, T, m.nu * nx)),
+                   k=np.zeros((n, T, m.nu)), V=np.zeros((n, nx * nx)), v=np.zeros((n, nx)), J=np.zeros((n, kept)),
+                   accepted=np.zeros((n, kept), np.int32))
+        self.h._check(lib().ilqg_ilqr_get_host(self._w, _hp(out["qpos"]), _hp(out["qvel"]), _hp(out["ctrl"]), _hp(out["K"]), _hp(out["k"]),
+                                               _hp(out["V"]), _hp(out["v"]), _hp(out["J"]), _hp(out["accepted"])))
+        return out

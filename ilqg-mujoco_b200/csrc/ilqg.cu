@@ -16,8 +16,11 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <vector>
+#include <cmath>
 
 #include "dyn.cuh"
+#include "ilqr.cuh"
 
 namespace ilqg {
 
@@ -198,6 +201,32 @@ __global__ void __launch_bounds__(128) step_kernel(const __grid_constant__ DevMo
     });
 }
 
+template <class T, bool OK = (T::NQ == T::NV)>
+struct IlqrLaunch {
+    static cudaError_t rollout(const DevModel<T>&, const IlqrBuffers&, const ilqg_cost*, cudaStream_t) { return cudaErrorNotSupported; }
+    static cudaError_t accept(const IlqrBuffers&, int, double*, int*, cudaStream_t) { return cudaErrorNotSupported; }
+    static cudaError_t backward(const IlqrBuffers&, double, cudaStream_t) { return cudaErrorNotSupported; }
+};
+template <class T>
+struct IlqrLaunch<T, true> {
+    static cudaError_t rollout(const DevModel<T>& dm, const IlqrBuffers& b, const ilqg_cost* cost, cudaStream_t s) {
+        int n = b.ninst * b.nalpha;
+        ilqr_rollout_kernel<T><<<(n + 127) / 128, 128, 0, s>>>(dm, b, cost);
+        return cudaGetLastError();
+    }
+    static cudaError_t accept(const IlqrBuffers& b, int accept_always, double* Jtrace, int* acc_trace, cudaStream_t s) {
+        ilqr_accept_kernel<T><<<(b.ninst + 127) / 128, 128, 0, s>>>(b, accept_always, Jtrace, acc_trace);
+        return cudaGetLastError();
+    }
+    static cudaError_t backward(const IlqrBuffers& b, double dt, cudaStream_t s) {
+        constexpr int NX = 2 * T::NV;
+        constexpr int LANES = NX * NX >= 64 ? 32 : 8, GROUPS = 128 / LANES;
+        size_t smem = sizeof(BackwardSmem<T::NV, T::NU, LANES>) * GROUPS;
+        ilqr_backward_kernel<T::NV, T::NU, LANES, GROUPS><<<(b.ninst + GROUPS - 1) / GROUPS, LANES * GROUPS, smem, s>>>(b, dt);
+        return cudaGetLastError();
+    }
+};
+
 // ------------------------------------------------------------------ engines (one per compiled-in topology)
 struct Engine {
     int fd_minblocks = 2;
@@ -210,6 +239,11 @@ struct Engine {
                                 cudaStream_t s) = 0;
     virtual cudaError_t step(int n, int nsteps, double* qpos, double* qvel, const double* ctrl, double* warm, double* qacc,
                              cudaStream_t s) = 0;
+    // batched iLQR (ilqr.cuh); false when the model's state is not (qpos, qvel) with nq == nv (quirk Q9)
+    virtual bool ilqr_supported() const = 0;
+    virtual cudaError_t ilqr_rollout(const IlqrBuffers& b, const ilqg_cost* cost_dev, cudaStream_t s) = 0;
+    virtual cudaError_t ilqr_accept(const IlqrBuffers& b, int accept_always, double* Jtrace, int* acc_trace, cudaStream_t s) = 0;
+    virtual cudaError_t ilqr_backward(const IlqrBuffers& b, cudaStream_t s) = 0;
 };
 
 template <class T>
@@ -245,6 +279,14 @@ struct EngineT : Engine {
         step_kernel<T><<<(n + 127) / 128, 128, 0, s>>>(dm, n, nsteps, qpos, qvel, ctrl, warm, qacc);
         return cudaGetLastError();
     }
+    bool ilqr_supported() const override { return T::NQ == T::NV; }
+    cudaError_t ilqr_rollout(const IlqrBuffers& b, const ilqg_cost* cost_dev, cudaStream_t s) override {
+        return IlqrLaunch<T>::rollout(dm, b, cost_dev, s);
+    }
+    cudaError_t ilqr_accept(const IlqrBuffers& b, int accept_always, double* Jtrace, int* acc_trace, cudaStream_t s) override {
+        return IlqrLaunch<T>::accept(b, accept_always, Jtrace, acc_trace, s);
+    }
+    cudaError_t ilqr_backward(const IlqrBuffers& b, cudaStream_t s) override { return IlqrLaunch<T>::backward(b, dm.timestep, s); }
 };
 
 static Engine* make_engine(const ilqg_model& m) {
@@ -555,6 +597,237 @@ int ilqg_forward_batch_host(ilqg_handle h, int n, const double* qpos, const doub
 int ilqg_step_batch_host(ilqg_handle h, int n, int nsteps, double* qpos, double* qvel, const double* ctrl, double* warmstart, double* qacc) {
     if (nsteps < 0) return h ? fail(h, ILQG_ERR_ARG, "negative nsteps") : ILQG_ERR_ARG;
     return state_host_call(h, n, nsteps, true, qpos, qvel, ctrl, warmstart, qacc);
+}
+
+
+// ------------------------------------------------------------------ batched iLQR workspace
+struct ilqg_ilqr_s {
+    ilqg_handle h = nullptr;
+    ilqg::IlqrBuffers b{};
+    ilqg_cost* d_cost = nullptr;
+    bool has_cost = false;
+    double* d_Jtrace = nullptr;   // [trace_cap][ninst]
+    int* d_acc_trace = nullptr;
+    int trace_cap = 0, iters = 0;
+    std::vector<void*> allocs;
+    ilqg_fd_opts fd;
+};
+
+#define ILQR_ALLOC(w, ptr, count)                                                              \
+    do {                                                                                       \
+        void* p_ = nullptr;                                                                    \
+        cudaError_t e_ = cudaMalloc(&p_, sizeof(*(ptr)) * (size_t)(count));                    \
+        if (e_ != cudaSuccess) { ilqg_ilqr_destroy(w); return cuda_fail(h, e_, "cudaMalloc"); } \
+        cudaMemset(p_, 0, sizeof(*(ptr)) * (size_t)(count));                                   \
+        (w)->allocs.push_back(p_);                                                             \
+        (ptr) = (decltype(ptr))p_;                                                             \
+    } while (0)
+
+int ilqg_ilqr_destroy(ilqg_ilqr w) {
+    if (!w) return ILQG_OK;
+    if (w->h) cudaSetDevice(w->h->device);
+    for (void* p : w->allocs) cudaFree(p);
+    delete w;
+    return ILQG_OK;
+}
+
+int ilqg_ilqr_create(ilqg_handle h, int ninst, int N, int nalpha, const double* alphas, ilqg_ilqr* out) {
+    if (!h || !out) return ILQG_ERR_ARG;
+    *out = nullptr;
+    if (ninst <= 0 || N < 1 || nalpha < 1 || nalpha > 64) return fail(h, ILQG_ERR_ARG, "bad iLQR sizes");
+    if (!h->eng->ilqr_supported()) return fail(h, ILQG_ERR_UNSUPPORTED, "iLQR needs nq == nv (the reference's state vector, SURVEY quirk Q9)");
+    CU(h, cudaSetDevice(h->device));
+    auto* w = new ilqg_ilqr_s();
+    w->h = h;
+    ilqg_fd_opts_default(&w->fd);
+    const int nq = h->model.nq, nv = h->model.nv, nu = h->model.nu, nx = 2 * nv, nd = ilqg_deriv_size(&h->model);
+    const size_t T = (size_t)N + 1, TI = T * ninst;
+    auto& b = w->b;
+    b.ninst = ninst; b.N = N; b.nalpha = nalpha; b.mu = 1000.0;  // ilqr.h:65
+    ILQR_ALLOC(w, b.nom_q, TI * nq); ILQR_ALLOC(w, b.nom_v, TI * nv); ILQR_ALLOC(w, b.nom_u, TI * nu); ILQR_ALLOC(w, b.nom_w, TI * nv);
+    ILQR_ALLOC(w, b.init_q, (size_t)ninst * nq); ILQR_ALLOC(w, b.init_v, (size_t)ninst * nv); ILQR_ALLOC(w, b.init_w, (size_t)ninst * nv);
+    ILQR_ALLOC(w, b.cand_q, nalpha * TI * nq); ILQR_ALLOC(w, b.cand_v, nalpha * TI * nv); ILQR_ALLOC(w, b.cand_u, nalpha * TI * nu);
+    ILQR_ALLOC(w, b.cand_w, nalpha * TI * nv); ILQR_ALLOC(w, b.cand_J, (size_t)nalpha * ninst);
+    ILQR_ALLOC(w, b.alphas, nalpha); ILQR_ALLOC(w, b.nom_J, ninst); ILQR_ALLOC(w, b.accepted, ninst);
+    ILQR_ALLOC(w, b.K, TI * nu * nx); ILQR_ALLOC(w, b.k, TI * nu); ILQR_ALLOC(w, b.V, (size_t)ninst * nx * nx); ILQR_ALLOC(w, b.v, (size_t)ninst * nx);
+    ILQR_ALLOC(w, b.deriv, TI * nd);
+    ILQR_ALLOC(w, w->d_cost, 1);
+    w->trace_cap = 256;
+    ILQR_ALLOC(w, w->d_Jtrace, (size_t)w->trace_cap * ninst); ILQR_ALLOC(w, w->d_acc_trace, (size_t)w->trace_cap * ninst);
+    std::vector<double> al(nalpha);
+    for (int a = 0; a < nalpha; a++) al[a] = alphas ? alphas[a] : std::ldexp(1.0, -a);  // default ladder 1, 1/2, 1/4, ...
+    CU(h, cudaMemcpy(b.alphas, al.data(), sizeof(double) * nalpha, cudaMemcpyHostToDevice));
+    *out = w;
+    return ILQG_OK;
+}
+
+int ilqg_ilqr_set_cost(ilqg_ilqr w, const ilqg_cost* cost) {
+    if (!w || !cost) return ILQG_ERR_ARG;
+    ilqg_handle h = w->h;
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaMemcpy(w->d_cost, cost, sizeof(ilqg_cost), cudaMemcpyHostToDevice));
+    w->has_cost = true;
+    return ILQG_OK;
+}
+int ilqg_ilqr_set_mu(ilqg_ilqr w, double mu) {
+    if (!w) return ILQG_ERR_ARG;
+    w->b.mu = mu;
+    return ILQG_OK;
+}
+
+// setDInit (ilqr.h:110-113) for every instance; device pointers, instance-major
+int ilqg_ilqr_set_state_dev(ilqg_ilqr w, const double* qpos, const double* qvel, const double* warm, void* stream) {
+    if (!w || !qpos || !qvel) return ILQG_ERR_ARG;
+    ilqg_handle h = w->h;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nq = h->model.nq, nv = h->model.nv, n = w->b.ninst;
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaMemcpyAsync(w->b.init_q, qpos, sizeof(double) * (size_t)n * nq, cudaMemcpyDeviceToDevice, s));
+    CU(h, cudaMemcpyAsync(w->b.init_v, qvel, sizeof(double) * (size_t)n * nv, cudaMemcpyDeviceToDevice, s));
+    if (warm) CU(h, cudaMemcpyAsync(w->b.init_w, warm, sizeof(double) * (size_t)n * nv, cudaMemcpyDeviceToDevice, s));
+    else CU(h, cudaMemsetAsync(w->b.init_w, 0, sizeof(double) * (size_t)n * nv, s));
+    return ILQG_OK;
+}
+
+// ILQR constructor (ilqr.h:69-97): open-loop rollout of every instance under its initial control; K = k = 0 (quirk Q5)
+int ilqg_ilqr_init_dev(ilqg_ilqr w, const double* qpos, const double* qvel, const double* ctrl, const double* warm, void* stream) {
+    if (!w || !qpos || !qvel) return ILQG_ERR_ARG;
+    ilqg_handle h = w->h;
+    if (!w->has_cost) return fail(h, ILQG_ERR_ARG, "ilqg_ilqr_set_cost must be called first");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nq = h->model.nq, nv = h->model.nv, nu = h->model.nu, nx = 2 * nv, n = w->b.ninst;
+    const size_t T = (size_t)w->b.N + 1, TI = T * n;
+    int rc = ilqg_ilqr_set_state_dev(w, qpos, qvel, warm, stream);
+    if (rc) return rc;
+    auto& b = w->b;
+    CU(h, cudaMemsetAsync(b.K, 0, sizeof(double) * TI * nu * nx, s));
+    CU(h, cudaMemsetAsync(b.k, 0, sizeof(double) * TI * nu, s));
+    CU(h, cudaMemsetAsync(b.nom_q, 0, sizeof(double) * TI * nq, s));
+    CU(h, cudaMemsetAsync(b.nom_v, 0, sizeof(double) * TI * nv, s));
+    for (size_t t = 0; t < T && nu > 0; t++) {  // u*_n = the initial control at every knot
+        if (ctrl) CU(h, cudaMemcpyAsync(b.nom_u + t * n * nu, ctrl, sizeof(double) * (size_t)n * nu, cudaMemcpyDeviceToDevice, s));
+        else CU(h, cudaMemsetAsync(b.nom_u + t * n * nu, 0, sizeof(double) * (size_t)n * nu, s));
+    }
+    ilqg::IlqrBuffers one = b;
+    one.nalpha = 1;  // alphas[0] multiplies k = 0: any value gives the open-loop rollout
+    CU(h, h->eng->ilqr_rollout(one, w->d_cost, s));
+    CU(h, h->eng->ilqr_accept(one, 1, nullptr, nullptr, s));
+    h->launches += 2;
+    w->iters = 0;
+    return ILQG_OK;
+}
+
+// niter x ILQR::iterate (ilqr.h:179-186) for the whole batch, all on `stream`:
+//   rollouts of every alpha -> ladder-order accept -> FD of all T x ninst knots -> Riccati sweep.
+// accept_always != 0 with alphas[0] = 1 is the reference's behaviour (full step, no cost test).
+int ilqg_ilqr_iterate(ilqg_ilqr w, int niter, int accept_always, void* stream) {
+    if (!w || niter < 0) return ILQG_ERR_ARG;
+    ilqg_handle h = w->h;
+    if (!w->has_cost) return fail(h, ILQG_ERR_ARG, "ilqg_ilqr_set_cost must be called first");
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(h, cudaSetDevice(h->device));
+    auto& b = w->b;
+    const int nknots = (b.N + 1) * b.ninst;
+    int rc = ensure_center(h, (size_t)nknots * h->model.nv);
+    if (rc) return rc;
+    for (int it = 0; it < niter; it++) {
+        int slot = w->iters % w->trace_cap;
+        CU(h, h->eng->ilqr_rollout(b, w->d_cost, s));
+        CU(h, h->eng->ilqr_accept(b, accept_always, w->d_Jtrace + (size_t)slot * b.ninst, w->d_acc_trace + (size_t)slot * b.ninst, s));
+        CU(h, h->eng->fd(nknots, b.nom_q, b.nom_v, b.nom_u, b.nom_w, w->d_cost, w->fd, b.deriv, h->d_center, nullptr, s, nullptr));
+        CU(h, h->eng->ilqr_backward(b, s));
+        h->launches += 5;
+        w->iters++;
+    }
+    return ILQG_OK;
+}
+
+int ilqg_ilqr_iterations_done(ilqg_ilqr w) { return w ? w->iters : 0; }
+
+// Results to the host, instance-major: traj [ninst][T][.], K [ninst][T][nu*nx], k [ninst][T][nu], V [ninst][nx*nx],
+// v [ninst][nx], Jtrace / accepted [ninst][iters] (last min(iters, 256) iterations).  Any pointer may be NULL.
+int ilqg_ilqr_get_host(ilqg_ilqr w, double* qpos, double* qvel, double* ctrl, double* K, double* k, double* V, double* v, double* Jtrace,
+                       int* accepted) {
+    if (!w) return ILQG_ERR_ARG;
+    ilqg_handle h = w->h;
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaDeviceSynchronize());
+    auto& b = w->b;
+    const int nq = h->model.nq, nv = h->model.nv, nu = h->model.nu, nx = 2 * nv, n = b.ninst, T = b.N + 1;
+    auto fetch_tm = [&](const double* dev, double* host, int width) -> int {  // time-major device -> instance-major host
+        if (!host) return ILQG_OK;
+        std::vector<double> tmp((size_t)T * n * width);
+        CU(h, cudaMemcpy(tmp.data(), dev, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost));
+        for (int t = 0; t < T; t++)
+            for (int i = 0; i < n; i++)
+                memcpy(host + ((size_t)i * T + t) * width, tmp.data() + ((size_t)t * n + i) * width, sizeof(double) * width);
+        return ILQG_OK;
+    };
+    int rc;
+    if ((rc = fetch_tm(b.nom_q, qpos, nq))) return rc;
+    if ((rc = fetch_tm(b.nom_v, qvel, nv))) return rc;
+    if ((rc = fetch_tm(b.nom_u, ctrl, nu))) return rc;
+    if ((rc = fetch_tm(b.K, K, nu * nx))) return rc;
+    if ((rc = fetch_tm(b.k, k, nu))) return rc;
+    if (V) CU(h, cudaMemcpy(V, b.V, sizeof(double) * (size_t)n * nx * nx, cudaMemcpyDeviceToHost));
+    if (v) CU(h, cudaMemcpy(v, b.v, sizeof(double) * (size_t)n * nx, cudaMemcpyDeviceToHost));
+    int kept = w->iters < w->trace_cap ? w->iters : w->trace_cap;
+    if ((Jtrace || accepted) && kept > 0) {
+        std::vector<double> tj((size_t)w->trace_cap * n);
+        std::vector<int> ta((size_t)w->trace_cap * n);
+        CU(h, cudaMemcpy(tj.data(), w->d_Jtrace, sizeof(double) * tj.size(), cudaMemcpyDeviceToHost));
+        CU(h, cudaMemcpy(ta.data(), w->d_acc_trace, sizeof(int) * ta.size(), cudaMemcpyDeviceToHost));
+        int first = w->iters - kept;
+        for (int j = 0; j < kept; j++) {
+            int slot = (first + j) % w->trace_cap;
+            for (int i = 0; i < n; i++) {
+                if (Jtrace) Jtrace[(size_t)i * kept + j] = tj[(size_t)slot * n + i];
+                if (accepted) accepted[(size_t)i * kept + j] = ta[(size_t)slot * n + i];
+            }
+        }
+    }
+    return ILQG_OK;
+}
+
+// host-pointer conveniences (copy in, call the device flavour)
+static int ilqr_upload(ilqg_ilqr w, const double* qpos, const double* qvel, const double* ctrl, const double* warm, double** dq, double** dv,
+                       double** du, double** dw) {
+    ilqg_handle h = w->h;
+    const int nq = h->model.nq, nv = h->model.nv, nu = h->model.nu, n = w->b.ninst;
+    size_t tot = (size_t)n * (nq + 2 * nv + nu);
+    int rc = ensure_stage(h, tot * sizeof(double));
+    if (rc) return rc;
+    double* base = (double*)h->d_stage;
+    *dq = base; *dv = *dq + (size_t)n * nq; *du = *dv + (size_t)n * nv; *dw = *du + (size_t)n * nu;
+    CU(h, cudaMemcpy(*dq, qpos, sizeof(double) * (size_t)n * nq, cudaMemcpyHostToDevice));
+    CU(h, cudaMemcpy(*dv, qvel, sizeof(double) * (size_t)n * nv, cudaMemcpyHostToDevice));
+    if (ctrl && nu) CU(h, cudaMemcpy(*du, ctrl, sizeof(double) * (size_t)n * nu, cudaMemcpyHostToDevice));
+    else if (nu) CU(h, cudaMemset(*du, 0, sizeof(double) * (size_t)n * nu));
+    if (warm) CU(h, cudaMemcpy(*dw, warm, sizeof(double) * (size_t)n * nv, cudaMemcpyHostToDevice));
+    else CU(h, cudaMemset(*dw, 0, sizeof(double) * (size_t)n * nv));
+    return ILQG_OK;
+}
+int ilqg_ilqr_init_host(ilqg_ilqr w, const double* qpos, const double* qvel, const double* ctrl, const double* warm) {
+    if (!w || !qpos || !qvel) return ILQG_ERR_ARG;
+    CU(w->h, cudaSetDevice(w->h->device));
+    double *dq, *dv, *du, *dw;
+    int rc = ilqr_upload(w, qpos, qvel, ctrl, warm, &dq, &dv, &du, &dw);
+    if (rc) return rc;
+    rc = ilqg_ilqr_init_dev(w, dq, dv, du, dw, nullptr);
+    if (rc) return rc;
+    CU(w->h, cudaDeviceSynchronize());
+    return ILQG_OK;
+}
+int ilqg_ilqr_set_state_host(ilqg_ilqr w, const double* qpos, const double* qvel, const double* warm) {
+    if (!w || !qpos || !qvel) return ILQG_ERR_ARG;
+    CU(w->h, cudaSetDevice(w->h->device));
+    double *dq, *dv, *du, *dw;
+    int rc = ilqr_upload(w, qpos, qvel, nullptr, warm, &dq, &dv, &du, &dw);
+    if (rc) return rc;
+    rc = ilqg_ilqr_set_state_dev(w, dq, dv, dw, nullptr);
+    if (rc) return rc;
+    CU(w->h, cudaDeviceSynchronize());
+    return ILQG_OK;
 }
 
 }  // extern "C"

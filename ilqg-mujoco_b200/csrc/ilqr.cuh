@@ -1,0 +1,328 @@
+// ilqr.cuh — batched iLQR on the GPU: closed-loop rollouts for all line-search step sizes at once,
+// ladder-order acceptance, and the Riccati backward pass, for `ninst` independent problems.
+//
+// Replaces, for a whole batch and without leaving the device:
+//   ILQR::forwardPass   /root/reference/inc/ilqr.h:116-130   -> ilqr_rollout_kernel (one thread per instance x alpha)
+//   (A10 line search: absent from the reference; specification in oracle/mjo_ilqr.c) -> ilqr_accept_kernel
+//   Differentiator::updateDerivatives  /root/reference/inc/differentiator.h:85-93 -> fused into the backward kernel
+//   ILQR::initV / backwardPass  /root/reference/inc/ilqr.h:100-107,133-176 -> ilqr_backward_kernel (one lane group per instance)
+// The FD linearisation of all T x ninst knots between them is fd_center_kernel / fd_perturb_kernel (ilqg.cu).
+//
+// Device layout is time-major so that the threads of a warp (consecutive instances) touch consecutive memory:
+//   knot (n, i) of instance i lives at index n * ninst + i;  n = N is the initial knot, n = 0 the final one
+//   (the reference's dArray indexing, ilqr.h:52).  K[n] is nu x nx column-major, as Eigen stores it.
+#pragma once
+#include "dyn.cuh"
+
+namespace ilqg {
+
+template <class T>
+DEV double cost_eval(const ilqg_cost& c, const double (&q)[T::NQ], const double (&v)[T::NV], const double (&u)[nz(T::NU)]);
+
+struct IlqrBuffers {
+    int ninst, N, nalpha;
+    // nominal trajectory and the state every forward pass starts from (ILQR::d)
+    double *nom_q, *nom_v, *nom_u, *nom_w;
+    double *init_q, *init_v, *init_w;
+    // candidates: [nalpha][T][ninst]
+    double *cand_q, *cand_v, *cand_u, *cand_w, *cand_J;
+    double *alphas;     // [nalpha]
+    double *nom_J;      // [ninst]
+    int* accepted;      // [ninst] index of the accepted alpha in the last iteration (-1: none)
+    double *K, *k;      // [T][ninst][nu*nx], [T][ninst][nu]
+    double *V, *v;      // [ninst][nx*nx] (column-major), [ninst][nx]
+    double* deriv;      // [T][ninst][ND]
+    double mu;
+};
+
+// ------------------------------------------------------------------ forward pass, all alphas at once
+template <class T>
+__global__ void __launch_bounds__(128) ilqr_rollout_kernel(const __grid_constant__ DevModel<T> m, IlqrBuffers b, const ilqg_cost* __restrict__ cost) {
+    constexpr int NQ = T::NQ, NV = T::NV, NU = T::NU, NX = 2 * NV;
+    static_assert(NQ == NV, "the reference's state vector is 2*nv doubles starting at qpos (quirk Q9)");
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ninst = b.ninst;
+    if (tid >= ninst * b.nalpha) return;
+    const int a = tid / ninst, i = tid - a * ninst;   // consecutive threads = consecutive instances
+    const double alpha = b.alphas[a];
+    double q[NQ], v[NV], u[nz(NU)], warm[NV], qacc[NV];
+    sfor<0, NQ>([&](auto ii) { q[IDX(ii)] = b.init_q[(size_t)i * NQ + IDX(ii)]; });
+    sfor<0, NV>([&](auto ii) { v[IDX(ii)] = b.init_v[(size_t)i * NV + IDX(ii)]; warm[IDX(ii)] = b.init_w[(size_t)i * NV + IDX(ii)]; qacc[IDX(ii)] = 0; });
+    Work<T> w;
+    double J = 0;
+    const size_t T1 = (size_t)(b.N + 1) * ninst;
+    for (int n = b.N; n >= 0; n--) {
+        const size_t kn = (size_t)n * ninst + i;
+        // u = K[n] (x - x*_n) + alpha k[n] + u*_n      (ilqr.h:126; alpha = 1 there)
+        double dx[NX];
+        sfor<0, NV>([&](auto ii) {
+            dx[IDX(ii)] = q[IDX(ii)] - b.nom_q[kn * NQ + IDX(ii)];
+            dx[NV + IDX(ii)] = v[IDX(ii)] - b.nom_v[kn * NV + IDX(ii)];
+        });
+        const double* K = b.K + kn * NU * NX;
+        sfor<0, NU>([&](auto rr) {
+            constexpr int r = IDX(rr);
+            double s = 0;
+            sfor<0, NX>([&](auto cc) { s += K[r + IDX(cc) * NU] * dx[IDX(cc)]; });
+            u[r] = s + alpha * b.k[kn * NU + r] + b.nom_u[kn * NU + r];
+        });
+        // snapshot the knot (cpMjData(dArray[n], d), ilqr.h:127) into this alpha's candidate
+        const size_t cn = (size_t)a * T1 + kn;
+        sfor<0, NQ>([&](auto ii) { b.cand_q[cn * NQ + IDX(ii)] = q[IDX(ii)]; });
+        sfor<0, NV>([&](auto ii) { b.cand_v[cn * NV + IDX(ii)] = v[IDX(ii)]; b.cand_w[cn * NV + IDX(ii)] = warm[IDX(ii)]; });
+        sfor<0, NU>([&](auto ii) { b.cand_u[cn * NU + IDX(ii)] = u[IDX(ii)]; });
+        if (cost) J = __dadd_rn(J, cost_eval<T>(*cost, q, v, u));
+        step<T>(m, w, q, v, u, warm, qacc);   // mj_step (ilqr.h:128)
+    }
+    b.cand_J[(size_t)a * ninst + i] = J;
+}
+
+// ------------------------------------------------------------------ ladder-order acceptance
+// One block column per instance: thread (knot) copies the accepted candidate over the nominal.  The accepted alpha is
+// the FIRST one in ladder order whose cost beats the nominal's — exactly what sequential backtracking would pick.
+template <class T>
+__global__ void ilqr_accept_kernel(IlqrBuffers b, int accept_always, double* __restrict__ Jtrace, int* __restrict__ acc_trace) {
+    constexpr int NQ = T::NQ, NV = T::NV, NU = T::NU;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b.ninst) return;
+    const int ninst = b.ninst, Tn = b.N + 1;
+    int acc = -1;
+    const double Jprev = b.nom_J[i];
+    double J = Jprev;
+    if (accept_always) { acc = 0; J = b.cand_J[i]; }
+    else
+        for (int a = 0; a < b.nalpha; a++) {
+            double Ja = b.cand_J[(size_t)a * ninst + i];
+            if (Ja < Jprev) { acc = a; J = Ja; break; }
+        }
+    if (acc >= 0) {
+        const size_t T1 = (size_t)Tn * ninst;
+        for (int n = 0; n < Tn; n++) {
+            const size_t kn = (size_t)n * ninst + i, cn = (size_t)acc * T1 + kn;
+            for (int c = 0; c < NQ; c++) b.nom_q[kn * NQ + c] = b.cand_q[cn * NQ + c];
+            for (int c = 0; c < NV; c++) { b.nom_v[kn * NV + c] = b.cand_v[cn * NV + c]; b.nom_w[kn * NV + c] = b.cand_w[cn * NV + c]; }
+            for (int c = 0; c < NU; c++) b.nom_u[kn * NU + c] = b.cand_u[cn * NU + c];
+        }
+        b.nom_J[i] = J;
+    }
+    b.accepted[i] = acc;
+    if (Jtrace) Jtrace[i] = J;
+    if (acc_trace) acc_trace[i] = acc;
+    // setDInit(dArray[N]) (ilqr.h:183): the next pass starts from the nominal's first knot
+    const size_t kN = (size_t)b.N * ninst + i;
+    for (int c = 0; c < NQ; c++) b.init_q[(size_t)i * NQ + c] = b.nom_q[kN * NQ + c];
+    for (int c = 0; c < NV; c++) { b.init_v[(size_t)i * NV + c] = b.nom_v[kN * NV + c]; b.init_w[(size_t)i * NV + c] = b.nom_w[kN * NV + c]; }
+}
+
+// ------------------------------------------------------------------ backward pass
+// LANES threads cooperate on one instance; all matrices live in shared memory, column-major like the reference's
+// Eigen objects.  Every lane loops over the output elements it owns; the nu x nu solve runs redundantly per lane
+// on a private copy (nu <= 3 here), a pivoted L D L^T like the reference's .ldlt() (ilqr.h:167).
+template <int NV, int NU, int LANES>
+struct BackwardSmem {
+    static constexpr int NX = 2 * NV;
+    double V[NX * NX], A[NX * NX], Acl[NX * NX], T1[NX * NX], Vn[NX * NX];
+    double B[NX * NU], VB[NX * NU], K[NU * NX], S[NU * NU];
+    double v[NX], q[NX], c[NX], w[NX], wV[NX], rK[NX], vn[NX], r[NU], k[NU];
+};
+
+template <int N>
+DEV void ldlt_solve_small(const double* S, double* x) {  // S: N x N column-major symmetric (any sign); x in/out
+    double W[N * N], L[N * N], D[N];
+    int perm[N];
+#pragma unroll
+    for (int i = 0; i < N * N; i++) { W[i] = S[i]; L[i] = 0; }
+#pragma unroll
+    for (int i = 0; i < N; i++) perm[i] = i;
+    for (int j = 0; j < N; j++) {
+        int p = j;
+        for (int i = j + 1; i < N; i++) if (fabs(W[i + i * N]) > fabs(W[p + p * N])) p = i;
+        if (p != j) {
+            for (int c = 0; c < N; c++) { double t = W[j + c * N]; W[j + c * N] = W[p + c * N]; W[p + c * N] = t; }
+            for (int r = 0; r < N; r++) { double t = W[r + j * N]; W[r + j * N] = W[r + p * N]; W[r + p * N] = t; }
+            for (int c = 0; c < j; c++) { double t = L[j + c * N]; L[j + c * N] = L[p + c * N]; L[p + c * N] = t; }
+            int t = perm[j]; perm[j] = perm[p]; perm[p] = t;
+        }
+        D[j] = W[j + j * N];
+        L[j + j * N] = 1;
+        for (int i = j + 1; i < N; i++) L[i + j * N] = W[i + j * N] / D[j];
+        for (int r = j + 1; r < N; r++) for (int c = j + 1; c < N; c++) W[r + c * N] -= L[r + j * N] * D[j] * L[c + j * N];
+    }
+    double y[N];
+    for (int i = 0; i < N; i++) y[i] = x[perm[i]];
+    for (int i = 0; i < N; i++) for (int c = 0; c < i; c++) y[i] -= L[i + c * N] * y[c];
+    for (int i = 0; i < N; i++) y[i] /= D[i];
+    for (int i = N - 1; i >= 0; i--) for (int c = i + 1; c < N; c++) y[i] -= L[c + i * N] * y[c];
+    for (int i = 0; i < N; i++) x[perm[i]] = y[i];
+}
+
+template <int NV, int NU, int LANES, int GROUPS>
+__global__ void __launch_bounds__(LANES * GROUPS) ilqr_backward_kernel(IlqrBuffers b, double dt) {
+    constexpr int NX = 2 * NV, ND = NV * (2 * NV + NU) + 2 * NV + NU, NQ = NV;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    typedef BackwardSmem<NV, NU, LANES> SM;
+    SM* all = reinterpret_cast<SM*>(smem_raw);
+    const int g = threadIdx.x / LANES, lane = threadIdx.x % LANES;
+    const int i = blockIdx.x * GROUPS + g;
+    const bool live = i < b.ninst;
+    SM& s = all[g];
+    const int ninst = b.ninst;
+    // groups are whole warps or aligned sub-warps; sync the lanes of this group only
+    const unsigned gmask = LANES == 32 ? 0xffffffffu : (((1u << LANES) - 1u) << ((threadIdx.x % 32) / LANES * LANES));
+    auto gsync = [&]() { __syncwarp(gmask); };
+#define CMX(M, r, c, rows) ((M)[(r) + (c) * (rows)])
+    if (live) {
+        // initV (ilqr.h:100-107): v = dgdx at knot 0, V = v' v
+        const double* d0 = b.deriv + ((size_t)0 * ninst + i) * ND + 2 * NV * NV + NV * NU;
+        for (int e = lane; e < NX; e += LANES) s.v[e] = d0[e];
+    }
+    gsync();
+    if (live)
+        for (int e = lane; e < NX * NX; e += LANES) s.V[e] = s.v[e % NX] * s.v[e / NX];
+    gsync();
+    for (int n = 1; n <= b.N; n++) {
+        const size_t kn = (size_t)n * ninst + i, kp = (size_t)(n - 1) * ninst + i;
+        if (live) {
+            const double* deriv = b.deriv + kn * ND;
+            // V <- (V + V')/2 into Vn, then back (ilqr.h:150)
+            for (int e = lane; e < NX * NX; e += LANES) { int r = e % NX, c = e / NX; s.Vn[e] = (CMX(s.V, r, c, NX) + CMX(s.V, c, r, NX)) / 2; }
+            // A, B through the column-major views of the row-major deriv blocks (differentiator.h:68-71,89-92; quirk Q1)
+            for (int e = lane; e < NX * NX; e += LANES) {
+                int r = e % NX, c = e / NX;
+                double a;
+                if (r < NV) a = (c == r ? 1.0 : 0.0) + (c == NV + r ? dt : 0.0);
+                else if (c < NV) a = deriv[(r - NV) + c * NV] * dt;
+                else a = ((r - NV) == (c - NV) ? 1.0 : 0.0) + deriv[NV * NV + (r - NV) + (c - NV) * NV] * dt;
+                s.A[e] = a;
+            }
+            for (int e = lane; e < NX * NU; e += LANES) {
+                int r = e % NX, c = e / NX;
+                s.B[e] = r < NV ? 0.0 : deriv[2 * NV * NV + (r - NV) + c * NV] * dt;
+            }
+            for (int e = lane; e < NX; e += LANES) {
+                s.q[e] = deriv[2 * NV * NV + NV * NU + e];
+                s.c[e] = e < NV ? b.nom_q[kp * NQ + e] - b.nom_q[kn * NQ + e] : b.nom_v[kp * NV + (e - NV)] - b.nom_v[kn * NV + (e - NV)];
+            }
+            for (int e = lane; e < NU; e += LANES) s.r[e] = deriv[2 * NV * NV + NV * NU + 2 * NV + e];
+        }
+        gsync();
+        if (live)  // V = sym(V) + mu I   (ilqr.h:166; never removed — quirk Q3)
+            for (int e = lane; e < NX * NX; e += LANES) s.V[e] = s.Vn[e] + ((e % NX) == (e / NX) ? b.mu : 0.0);
+        gsync();
+        if (live) {
+            for (int e = lane; e < NX * NU; e += LANES) {  // VB = V B
+                int r = e % NX, c = e / NX;
+                double t = 0;
+                for (int x = 0; x < NX; x++) t += CMX(s.V, r, x, NX) * CMX(s.B, x, c, NX);
+                s.VB[e] = t;
+            }
+            for (int e = lane; e < NX * NX; e += LANES) {  // T1 = V A
+                int r = e % NX, c = e / NX;
+                double t = 0;
+                for (int x = 0; x < NX; x++) t += CMX(s.V, r, x, NX) * CMX(s.A, x, c, NX);
+                s.T1[e] = t;
+            }
+            for (int e = lane; e < NX; e += LANES) {       // w = v' + 2 V c
+                double t = 0;
+                for (int x = 0; x < NX; x++) t += CMX(s.V, e, x, NX) * s.c[x];
+                s.w[e] = s.v[e] + 2 * t;
+            }
+        }
+        gsync();
+        if (live) {
+            for (int e = lane; e < NU * NU; e += LANES) {  // S = -2 B'VB - 2 r'r
+                int a = e % NU, c = e / NU;
+                double t = 0;
+                for (int x = 0; x < NX; x++) t += CMX(s.B, x, a, NX) * CMX(s.VB, x, c, NX);
+                s.S[e] = -2 * t - 2 * s.r[a] * s.r[c];
+            }
+            for (int e = lane; e < NU * NX; e += LANES) {  // rhsK = 2 B' V A
+                int a = e % NU, c = e / NU;
+                double t = 0;
+                for (int x = 0; x < NX; x++) t += CMX(s.B, x, a, NX) * CMX(s.T1, x, c, NX);
+                s.K[e] = 2 * t;
+            }
+            for (int e = lane; e < NU; e += LANES) {       // rhsk = B'(v' + 2Vc) + r'
+                double t = 0;
+                for (int x = 0; x < NX; x++) t += CMX(s.B, x, e, NX) * s.w[x];
+                s.k[e] = t + s.r[e];
+            }
+        }
+        gsync();
+        if (live) {  // K[n] = S^-1 rhsK (column by column), k[n] = S^-1 rhsk
+            for (int c = lane; c < NX + 1; c += LANES) {
+                double x[NU];
+                if (c < NX) { for (int a = 0; a < NU; a++) x[a] = s.K[a + c * NU]; }
+                else for (int a = 0; a < NU; a++) x[a] = s.k[a];
+                ldlt_solve_small<NU>(s.S, x);
+                if (c < NX) { for (int a = 0; a < NU; a++) s.K[a + c * NU] = x[a]; }
+                else for (int a = 0; a < NU; a++) s.k[a] = x[a];
+            }
+        }
+        gsync();
+        if (live) {
+            for (int e = lane; e < NU * NX; e += LANES) b.K[kn * NU * NX + e] = s.K[e];
+            for (int e = lane; e < NU; e += LANES) b.k[kn * NU + e] = s.k[e];
+            for (int e = lane; e < NX * NX; e += LANES) {  // Acl = A + B K
+                int r = e % NX, c = e / NX;
+                double t = s.A[e];
+                for (int a = 0; a < NU; a++) t += CMX(s.B, r, a, NX) * s.K[a + c * NU];
+                s.Acl[e] = t;
+            }
+            for (int e = lane; e < NX; e += LANES) {       // rK = r K ; wB = c + B k
+                double t = 0;
+                for (int a = 0; a < NU; a++) t += s.r[a] * s.K[a + e * NU];
+                s.rK[e] = t;
+                double u = s.c[e];
+                for (int a = 0; a < NU; a++) u += CMX(s.B, e, a, NX) * s.k[a];
+                s.w[e] = u;
+            }
+        }
+        gsync();
+        if (live)
+            for (int e = lane; e < NX * NX; e += LANES) {  // T1 = V Acl
+                int r = e % NX, c = e / NX;
+                double t = 0;
+                for (int x = 0; x < NX; x++) t += CMX(s.V, r, x, NX) * CMX(s.Acl, x, c, NX);
+                s.T1[e] = t;
+            }
+        gsync();
+        if (live)
+            for (int e = lane; e < NX * NX; e += LANES) {  // Vn = Acl' V Acl + q'q + (rK)'(rK)   (ilqr.h:173)
+                int r = e % NX, c = e / NX;
+                double t = 0;
+                for (int x = 0; x < NX; x++) t += CMX(s.Acl, x, r, NX) * CMX(s.T1, x, c, NX);
+                s.Vn[e] = t + s.q[r] * s.q[c] + s.rK[r] * s.rK[c];
+            }
+        gsync();
+        if (live) {
+            for (int e = lane; e < NX * NX; e += LANES) s.V[e] = s.Vn[e];
+            for (int e = lane; e < NX; e += LANES) {       // wV = (k'B' + c') V_new      (quirk Q4)
+                double t = 0;
+                for (int x = 0; x < NX; x++) t += s.w[x] * CMX(s.Vn, x, e, NX);
+                s.wV[e] = t;
+            }
+        }
+        gsync();
+        if (live) {
+            double kr = 0;
+            for (int a = 0; a < NU; a++) kr += s.k[a] * s.r[a];
+            for (int e = lane; e < NX; e += LANES) {       // v = 2 wV Acl + v Acl + q + 2 (k'r') rK   (ilqr.h:174)
+                double t1 = 0, t2 = 0;
+                for (int x = 0; x < NX; x++) { t1 += s.wV[x] * CMX(s.Acl, x, e, NX); t2 += s.v[x] * CMX(s.Acl, x, e, NX); }
+                s.vn[e] = 2 * t1 + t2 + s.q[e] + 2 * kr * s.rK[e];
+            }
+        }
+        gsync();
+        if (live)
+            for (int e = lane; e < NX; e += LANES) s.v[e] = s.vn[e];
+        gsync();
+    }
+    if (live) {
+        for (int e = lane; e < NX * NX; e += LANES) b.V[(size_t)i * NX * NX + e] = s.V[e];
+        for (int e = lane; e < NX; e += LANES) b.v[(size_t)i * NX + e] = s.v[e];
+    }
+#undef CMX
+}
+
+}  // namespace ilqg

@@ -112,6 +112,31 @@ int ilqg_step_batch_dev(ilqg_handle h, int n, int nsteps, double* qpos, double* 
 int ilqg_step_batch_host(ilqg_handle h, int n, int nsteps, double* qpos, double* qvel, const double* ctrl,
                          double* warmstart, double* qacc);
 
+/* ---- batched iLQR: ninst independent problems of horizon N (T = N+1 knots) resident on the GPU.
+ * Replaces ILQR<nv,nu,N> (/root/reference/inc/ilqr.h:14-188) for a whole batch:
+ *   ilqg_ilqr_init_*      ILQR::ILQR (:69-97)  open-loop rollout under the initial control, K = k = 0
+ *   ilqg_ilqr_set_state_* ILQR::setDInit (:110-113)
+ *   ilqg_ilqr_iterate     niter x ILQR::iterate (:179-186): forwardPass (:116-130) for every line-search step size in one
+ *                         launch, acceptance of the first alpha in ladder order whose trajectory cost improves (the A10
+ *                         specification, oracle/mjo_ilqr.c), FD of all knots (differentiator.h:85-93), backwardPass (:133-176).
+ *                         accept_always != 0 with alphas = {1} reproduces the reference (full step, no cost test).
+ * Index n of a trajectory runs as in the reference: n = N is the initial knot, n = 0 the final one (ilqr.h:52).
+ * K[n] is nu x 2nv column-major (Eigen's layout); V is 2nv x 2nv column-major; the model must have nq == nv. */
+typedef struct ilqg_ilqr_s* ilqg_ilqr;
+int ilqg_ilqr_create(ilqg_handle h, int ninst, int N, int nalpha, const double* alphas /* host, NULL: 1,1/2,1/4,.. */, ilqg_ilqr* out);
+int ilqg_ilqr_destroy(ilqg_ilqr w);
+int ilqg_ilqr_set_cost(ilqg_ilqr w, const ilqg_cost* cost); /* host struct */
+int ilqg_ilqr_set_mu(ilqg_ilqr w, double mu);               /* Levenberg-Marquardt term, default 1000 (ilqr.h:65) */
+int ilqg_ilqr_init_dev(ilqg_ilqr w, const double* qpos, const double* qvel, const double* ctrl, const double* warm, void* stream);
+int ilqg_ilqr_init_host(ilqg_ilqr w, const double* qpos, const double* qvel, const double* ctrl, const double* warm);
+int ilqg_ilqr_set_state_dev(ilqg_ilqr w, const double* qpos, const double* qvel, const double* warm, void* stream);
+int ilqg_ilqr_set_state_host(ilqg_ilqr w, const double* qpos, const double* qvel, const double* warm);
+int ilqg_ilqr_iterate(ilqg_ilqr w, int niter, int accept_always, void* stream); /* asynchronous on `stream` */
+int ilqg_ilqr_iterations_done(ilqg_ilqr w);
+/* results, instance-major on the host; any pointer may be NULL.  Jtrace/accepted: [ninst][min(iterations,256)] */
+int ilqg_ilqr_get_host(ilqg_ilqr w, double* qpos, double* qvel, double* ctrl, double* K, double* k, double* V, double* v,
+                       double* Jtrace, int* accepted);
+
 /* ---- diagnostics */
 long ilqg_launch_count(ilqg_handle h);        /* kernels launched through this handle so far */
 const char* ilqg_engine_name(ilqg_handle h);  /* name of the kernel instantiation serving this model */

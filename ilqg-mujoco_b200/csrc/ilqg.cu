@@ -606,6 +606,7 @@ struct ilqg_ilqr_s {
     ilqg::IlqrBuffers b{};
     ilqg_cost* d_cost = nullptr;
     bool has_cost = false;
+    bool host_cost = false;
     double* d_Jtrace = nullptr;   // [trace_cap][ninst]
     int* d_acc_trace = nullptr;
     int trace_cap = 0, iters = 0;
@@ -662,11 +663,12 @@ int ilqg_ilqr_create(ilqg_handle h, int ninst, int N, int nalpha, const double* 
 }
 
 int ilqg_ilqr_set_cost(ilqg_ilqr w, const ilqg_cost* cost) {
-    if (!w || !cost) return ILQG_ERR_ARG;
+    if (!w) return ILQG_ERR_ARG;
     ilqg_handle h = w->h;
     CU(h, cudaSetDevice(h->device));
-    CU(h, cudaMemcpy(w->d_cost, cost, sizeof(ilqg_cost), cudaMemcpyHostToDevice));
+    if (cost) CU(h, cudaMemcpy(w->d_cost, cost, sizeof(ilqg_cost), cudaMemcpyHostToDevice));
     w->has_cost = true;
+    w->host_cost = cost == nullptr;  // NULL: the caller owns the cost (a host stepCostFn) and supplies the gradient rows itself
     return ILQG_OK;
 }
 int ilqg_ilqr_set_mu(ilqg_ilqr w, double mu) {
@@ -710,35 +712,91 @@ int ilqg_ilqr_init_dev(ilqg_ilqr w, const double* qpos, const double* qvel, cons
     }
     ilqg::IlqrBuffers one = b;
     one.nalpha = 1;  // alphas[0] multiplies k = 0: any value gives the open-loop rollout
-    CU(h, h->eng->ilqr_rollout(one, w->d_cost, s));
+    CU(h, h->eng->ilqr_rollout(one, w->host_cost ? nullptr : w->d_cost, s));
     CU(h, h->eng->ilqr_accept(one, 1, nullptr, nullptr, s));
     h->launches += 2;
     w->iters = 0;
     return ILQG_OK;
 }
 
-// niter x ILQR::iterate (ilqr.h:179-186) for the whole batch, all on `stream`:
-//   rollouts of every alpha -> ladder-order accept -> FD of all T x ninst knots -> Riccati sweep.
-// accept_always != 0 with alphas[0] = 1 is the reference's behaviour (full step, no cost test).
-int ilqg_ilqr_iterate(ilqg_ilqr w, int niter, int accept_always, void* stream) {
-    if (!w || niter < 0) return ILQG_ERR_ARG;
+int ilqg_ilqr_get_host(ilqg_ilqr w, double* qpos, double* qvel, double* ctrl, double* K, double* k, double* V, double* v, double* Jtrace,
+                       int* accepted);
+
+// The three phases of ILQR::iterate (ilqr.h:179-186), each for the whole batch and asynchronous on `stream`.
+int ilqg_ilqr_forward(ilqg_ilqr w, int accept_always, void* stream) {   // forwardPass (+ A10 acceptance) + setDInit(dArray[N])
+    if (!w) return ILQG_ERR_ARG;
     ilqg_handle h = w->h;
     if (!w->has_cost) return fail(h, ILQG_ERR_ARG, "ilqg_ilqr_set_cost must be called first");
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(h, cudaSetDevice(h->device));
+    auto& b = w->b;
+    int slot = w->iters % w->trace_cap;
+    CU(h, h->eng->ilqr_rollout(b, w->host_cost ? nullptr : w->d_cost, s));
+    CU(h, h->eng->ilqr_accept(b, accept_always, w->d_Jtrace + (size_t)slot * b.ninst, w->d_acc_trace + (size_t)slot * b.ninst, s));
+    h->launches += 2;
+    w->iters++;
+    return ILQG_OK;
+}
+int ilqg_ilqr_linearise(ilqg_ilqr w, void* stream) {                     // FD at every knot of every instance
+    if (!w) return ILQG_ERR_ARG;
+    ilqg_handle h = w->h;
     cudaStream_t s = (cudaStream_t)stream;
     CU(h, cudaSetDevice(h->device));
     auto& b = w->b;
     const int nknots = (b.N + 1) * b.ninst;
     int rc = ensure_center(h, (size_t)nknots * h->model.nv);
     if (rc) return rc;
+    CU(h, h->eng->fd(nknots, b.nom_q, b.nom_v, b.nom_u, b.nom_w, w->host_cost ? nullptr : w->d_cost, w->fd, b.deriv, h->d_center, nullptr, s, nullptr));
+    h->launches += 2;
+    return ILQG_OK;
+}
+int ilqg_ilqr_backward(ilqg_ilqr w, void* stream) {                      // initV + backwardPass
+    if (!w) return ILQG_ERR_ARG;
+    ilqg_handle h = w->h;
+    CU(h, cudaSetDevice(h->device));
+    CU(h, h->eng->ilqr_backward(w->b, (cudaStream_t)stream));
+    h->launches += 1;
+    return ILQG_OK;
+}
+int ilqg_ilqr_iterate(ilqg_ilqr w, int niter, int accept_always, void* stream) {
+    if (!w || niter < 0) return ILQG_ERR_ARG;
+    if (w->host_cost) return fail(w->h, ILQG_ERR_ARG, "host-cost workspaces drive the phases themselves (cost rows come from the host)");
     for (int it = 0; it < niter; it++) {
-        int slot = w->iters % w->trace_cap;
-        CU(h, h->eng->ilqr_rollout(b, w->d_cost, s));
-        CU(h, h->eng->ilqr_accept(b, accept_always, w->d_Jtrace + (size_t)slot * b.ninst, w->d_acc_trace + (size_t)slot * b.ninst, s));
-        CU(h, h->eng->fd(nknots, b.nom_q, b.nom_v, b.nom_u, b.nom_w, w->d_cost, w->fd, b.deriv, h->d_center, nullptr, s, nullptr));
-        CU(h, h->eng->ilqr_backward(b, s));
-        h->launches += 5;
-        w->iters++;
+        int rc;
+        if ((rc = ilqg_ilqr_forward(w, accept_always, stream))) return rc;
+        if ((rc = ilqg_ilqr_linearise(w, stream))) return rc;
+        if ((rc = ilqg_ilqr_backward(w, stream))) return rc;
     }
+    return ILQG_OK;
+}
+
+// host-cost mode: the 2nv+nu cost-gradient entries of every knot's deriv block, instance-major [ninst][T][2nv+nu]
+int ilqg_ilqr_put_cost_rows_host(ilqg_ilqr w, const double* rows) {
+    if (!w || !rows) return ILQG_ERR_ARG;
+    ilqg_handle h = w->h;
+    CU(h, cudaSetDevice(h->device));
+    auto& b = w->b;
+    const int nv = h->model.nv, nu = h->model.nu, nd = ilqg_deriv_size(&h->model), nr = 2 * nv + nu, T = b.N + 1, n = b.ninst;
+    CU(h, cudaDeviceSynchronize());
+    for (int t = 0; t < T; t++)
+        for (int i = 0; i < n; i++)
+            CU(h, cudaMemcpy(b.deriv + ((size_t)t * n + i) * nd + (nd - nr), rows + ((size_t)i * T + t) * nr, sizeof(double) * nr,
+                             cudaMemcpyHostToDevice));
+    return ILQG_OK;
+}
+
+// the knots of the nominal incl. warm starts, instance-major [ninst][T][.]
+int ilqg_ilqr_get_knots_host(ilqg_ilqr w, double* qpos, double* qvel, double* ctrl, double* warm) {
+    if (!w) return ILQG_ERR_ARG;
+    ilqg_handle h = w->h;
+    int rc = ilqg_ilqr_get_host(w, qpos, qvel, ctrl, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    if (rc || !warm) return rc;
+    auto& b = w->b;
+    const int nv = h->model.nv, T = b.N + 1, n = b.ninst;
+    std::vector<double> tmp((size_t)T * n * nv);
+    CU(h, cudaMemcpy(tmp.data(), b.nom_w, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost));
+    for (int t = 0; t < T; t++)
+        for (int i = 0; i < n; i++) memcpy(warm + ((size_t)i * T + t) * nv, tmp.data() + ((size_t)t * n + i) * nv, sizeof(double) * nv);
     return ILQG_OK;
 }
 

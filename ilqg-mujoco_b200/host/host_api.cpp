@@ -1,0 +1,253 @@
+// host_api.cpp — host-language side of the drop-in: the MuJoCo-shaped entry points and the reference's free functions
+// (calcMJDerivatives, cpMjData, forwardStep/forwardFrame, InvertedPendulum) implemented on the B200 C ABI.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "inverted_pendulum/cost.h"
+#include "inverted_pendulum/inverted_pendulum.h"
+#include "mjderivative.h"
+#include "update.h"
+#include "util.h"
+
+static const double kEps = 1e-6;  // /root/reference/src/mjderivative.cpp:39
+
+extern "C" {
+
+void mju_error(const char* msg) {
+    fprintf(stderr, "ilqg-b200 ERROR: %s\n", msg);
+    exit(1);
+}
+void mju_copy(mjtNum* res, const mjtNum* data, int n) { memcpy(res, data, sizeof(mjtNum) * n); }
+void* mju_malloc(size_t size) { return malloc(size); }
+void mju_free(void* p) { free(p); }
+int mj_activate(const char*) { return 1; }
+
+mjModel* mj_loadXML(const char* filename, const void*, char* error, int error_sz) {
+    mjModel* m = (mjModel*)calloc(1, sizeof(mjModel));
+    int rc;
+    size_t len = filename ? strlen(filename) : 0;
+    if (len > 6 && !strcmp(filename + len - 6, ".ilqgm")) {
+        rc = ilqg_model_load(filename, &m->tab);
+        if (rc && error) snprintf(error, error_sz, "cannot load compiled model '%s' (%d)", filename, rc);
+    } else
+        rc = ilqg_compile_mjcf(filename, &m->tab, error, error_sz);
+    if (rc) { free(m); return NULL; }
+    const char* dev = getenv("ILQG_DEVICE");
+    rc = ilqg_create(&m->tab, dev ? atoi(dev) : 0, &m->gpu);
+    if (rc) {
+        if (error) snprintf(error, error_sz, "GPU model creation failed (%d): %s", rc, ilqg_last_error(NULL));
+        free(m);
+        return NULL;
+    }
+    m->nq = m->tab.nq; m->nv = m->tab.nv; m->nu = m->tab.nu; m->nbody = m->tab.nbody;
+    m->dof_jntid = m->tab.dof_jntid; m->jnt_type = m->tab.jnt_type;
+    m->jnt_qposadr = m->tab.jnt_qposadr; m->jnt_dofadr = m->tab.jnt_dofadr;
+    m->opt.timestep = m->tab.timestep; m->opt.tolerance = m->tab.tolerance; m->opt.iterations = m->tab.iterations;
+    return m;
+}
+void mj_deleteModel(mjModel* m) {
+    if (!m) return;
+    ilqg_destroy(m->gpu);
+    free(m);
+}
+mjData* mj_makeData(const mjModel* m) {
+    mjData* d = (mjData*)calloc(1, sizeof(mjData));
+    size_t n = (size_t)m->nq + 4 * (size_t)m->nv + m->nu + 6 * (size_t)m->nbody;
+    mjtNum* b = (mjtNum*)calloc(n, sizeof(mjtNum));
+    d->buffer = b;
+    d->qpos = b; b += m->nq;
+    d->qvel = b; b += m->nv;
+    d->qacc_warmstart = b; b += m->nv;
+    d->ctrl = b; b += m->nu;
+    d->qfrc_applied = b; b += m->nv;
+    d->xfrc_applied = b; b += 6 * m->nbody;
+    d->qacc = b;
+    mj_resetData(m, d);
+    return d;
+}
+void mj_deleteData(mjData* d) {
+    if (!d) return;
+    free(d->buffer);
+    free(d);
+}
+void mj_resetData(const mjModel* m, mjData* d) {
+    size_t n = (size_t)m->nq + 4 * (size_t)m->nv + m->nu + 6 * (size_t)m->nbody;
+    memset(d->buffer, 0, n * sizeof(mjtNum));
+    memcpy(d->qpos, m->tab.qpos0, sizeof(mjtNum) * m->nq);
+    d->time = 0;
+}
+static void gpu_check(const mjModel* m, int rc, const char* what) {
+    if (rc) {
+        char buf[512];
+        snprintf(buf, sizeof buf, "%s failed (%d): %s", what, rc, ilqg_last_error(m->gpu));
+        mju_error(buf);
+    }
+}
+void mj_step(const mjModel* m, mjData* d) {
+    gpu_check(m, ilqg_step_batch_host(m->gpu, 1, 1, d->qpos, d->qvel, d->ctrl, d->qacc_warmstart, d->qacc), "mj_step");
+    d->time += m->opt.timestep;
+}
+void mj_forward(const mjModel* m, mjData* d) {
+    gpu_check(m, ilqg_forward_batch_host(m->gpu, 1, d->qpos, d->qvel, d->ctrl, d->qacc_warmstart, d->qacc), "mj_forward");
+}
+
+}  // extern "C"
+
+// ---- /root/reference/src/util.cpp:4-13
+void cpMjData(const mjModel* m, mjData* d_dest, const mjData* d_src) {
+    d_dest->time = d_src->time;
+    mju_copy(d_dest->qpos, d_src->qpos, m->nq);
+    mju_copy(d_dest->qvel, d_src->qvel, m->nv);
+    mju_copy(d_dest->qacc, d_src->qacc, m->nv);
+    mju_copy(d_dest->qacc_warmstart, d_src->qacc_warmstart, m->nv);
+    mju_copy(d_dest->qfrc_applied, d_src->qfrc_applied, m->nv);
+    mju_copy(d_dest->xfrc_applied, d_src->xfrc_applied, 6 * m->nbody);
+    mju_copy(d_dest->ctrl, d_src->ctrl, m->nu);
+}
+
+// ---- /root/reference/src/update.cpp:8-20
+void forwardStep(mjModel* model, mjData* data) { mj_step(model, data); }
+void forwardFrame(mjModel* model, mjData* data) {
+    const mjtNum simstart = data->time;
+    while (data->time - simstart < 1.0 / 60.0) forwardStep(model, data);
+}
+
+// ---- cost rows: forward differences with the caller's host function, same expressions and evaluation order as
+//      /root/reference/src/mjderivative.cpp:72,88,120,174 (centre from dmain, perturbed from a private copy)
+void calcCostGradientRows(const mjModel* m, const mjData* dmain, stepCostFn_t stepCostFn, mjtNum* rows) {
+    const int nv = m->nv, nu = m->nu;
+    mjData* d = mj_makeData(m);
+    cpMjData(m, d, dmain);
+    const mjtNum costCenter = stepCostFn(dmain);
+    for (int i = 0; i < nv && i < nu; i++) {  // the reference's ctrl loop runs over min(nv, nu) columns (:81-82)
+        d->ctrl[i] = dmain->ctrl[i] + kEps;
+        rows[2 * nv + i] = (stepCostFn(d) - costCenter) / kEps;
+        d->ctrl[i] = dmain->ctrl[i];
+    }
+    for (int i = 0; i < nv; i++) {
+        d->qvel[i] = dmain->qvel[i] + kEps;
+        rows[nv + i] = (stepCostFn(d) - costCenter) / kEps;
+        d->qvel[i] = dmain->qvel[i];
+    }
+    for (int i = 0; i < nv; i++) {
+        const int jid = m->dof_jntid[i];
+        if (m->jnt_type[jid] == mjJNT_FREE && i >= m->jnt_dofadr[jid] + 3) { rows[i] = 0; continue; }  // quaternion dofs: GPU-side cost only
+        const int adr = m->jnt_qposadr[jid] + i - m->jnt_dofadr[jid];
+        d->qpos[adr] += kEps;
+        rows[i] = (stepCostFn(d) - costCenter) / kEps;
+        d->qpos[adr] = dmain->qpos[adr];
+    }
+    mj_deleteData(d);
+}
+
+void calcMJDerivativesBatch(mjModel* m, mjData* const* dknots, int nknots, mjtNum* deriv, stepCostFn_t stepCostFn) {
+    const int nq = m->nq, nv = m->nv, nu = m->nu, nd = ilqg_deriv_size(&m->tab), nr = 2 * nv + nu;
+    std::vector<mjtNum> q((size_t)nknots * nq), v((size_t)nknots * nv), u((size_t)nknots * nu), w((size_t)nknots * nv);
+    for (int k = 0; k < nknots; k++) {
+        mju_copy(q.data() + (size_t)k * nq, dknots[k]->qpos, nq);
+        mju_copy(v.data() + (size_t)k * nv, dknots[k]->qvel, nv);
+        mju_copy(u.data() + (size_t)k * nu, dknots[k]->ctrl, nu);
+        mju_copy(w.data() + (size_t)k * nv, dknots[k]->qacc_warmstart, nv);
+    }
+    int rc = ilqg_fd_batch_host(m->gpu, nknots, q.data(), v.data(), u.data(), w.data(), NULL, NULL, deriv, NULL, NULL);
+    if (rc && rc != ILQG_ERR_NONFINITE) gpu_check(m, rc, "calcMJDerivatives");
+    if (stepCostFn)
+        for (int k = 0; k < nknots; k++) calcCostGradientRows(m, dknots[k], stepCostFn, deriv + (size_t)k * nd + (nd - nr));
+}
+
+// drop-in for /root/reference/src/mjderivative.cpp:212 (one knot)
+void calcMJDerivatives(mjModel* m, mjData* dmain, mjtNum* deriv, stepCostFn_t stepCostFn) {
+    mjData* one[1] = {dmain};
+    calcMJDerivativesBatch(m, one, 1, deriv, stepCostFn);
+}
+
+// ---- /root/reference/src/inverted_pendulum/inverted_pendulum.cpp:6-30
+InvertedPendulum::InvertedPendulum(mjModel* m, mjData* d) : m(m), d(d) {
+    stepCostFn = stepCost;
+    for (auto i = 0; i < 10; i++) mj_step(m, d);
+    iLQR = new ILQR<nv, nu, N>(m, d, stepCostFn);
+}
+void InvertedPendulum::forward() {
+    iLQR->setDInit(d);
+    for (int i = 0; i < maxIterUtilConvergence; i++) iLQR->iterate();
+    mju_copy(d->ctrl, iLQR->dArray[N]->ctrl, nu);  // get first u
+    mj_step(m, d);                                 // proceed simulation
+}
+
+// ---- C entry points for tests (ctypes): the headless MPC demo and a Differentiator<6,3> probe
+extern "C" int ilqg_host_pendulum_mpc(const char* model_path, const double* qpos0, const double* qvel0, int nmpc, double* trace,
+                                      double* nom_qpos, double* nom_qvel, double* nom_ctrl, double* K, double* k, double* V, double* v) {
+    char err[512] = "";
+    mjModel* m = mj_loadXML(model_path, NULL, err, sizeof err);
+    if (!m) { fprintf(stderr, "%s\n", err); return 1; }
+    mjData* d = mj_makeData(m);
+    if (qpos0) mju_copy(d->qpos, qpos0, m->nq);
+    if (qvel0) mju_copy(d->qvel, qvel0, m->nv);
+    InvertedPendulum ip(m, d);
+    constexpr int N = InvertedPendulum::N, nv = InvertedPendulum::nv, nu = InvertedPendulum::nu;
+    for (int s = 0; s < nmpc; s++) {
+        ip.forward();
+        if (trace) {
+            trace[5 * s + 0] = d->qpos[0]; trace[5 * s + 1] = d->qpos[1];
+            trace[5 * s + 2] = d->qvel[0]; trace[5 * s + 3] = d->qvel[1]; trace[5 * s + 4] = d->ctrl[0];
+        }
+    }
+    for (int n = 0; n <= N; n++) {
+        if (nom_qpos) mju_copy(nom_qpos + n * nv, ip.iLQR->dArray[n]->qpos, nv);
+        if (nom_qvel) mju_copy(nom_qvel + n * nv, ip.iLQR->dArray[n]->qvel, nv);
+        if (nom_ctrl) mju_copy(nom_ctrl + n * nu, ip.iLQR->dArray[n]->ctrl, nu);
+        if (K) mju_copy(K + n * nu * 2 * nv, ip.iLQR->K[n].data(), nu * 2 * nv);
+        if (k) mju_copy(k + n * nu, ip.iLQR->k[n].data(), nu);
+    }
+    if (V) mju_copy(V, ip.iLQR->V->data(), 4 * nv * nv);
+    if (v) mju_copy(v, ip.iLQR->v->data(), 2 * nv);
+    delete ip.iLQR;
+    mj_deleteData(d);
+    mj_deleteModel(m);
+    return 0;
+}
+
+static mjtNum hopperTestCost(const mjData* d) { return d->qpos[0]; }  // /root/reference/tst/test_derivatives.cpp:16-20
+
+// the scenario of /root/reference/tst/test_derivatives.cpp:34-93 with Differentiator<6,3>: returns A (12x12), B (12x3), deriv and
+// the one-step prediction residual the reference test prints
+extern "C" int ilqg_host_hopper_differentiator(const char* model_path, int nsteps, double* A, double* B, double* deriv, double* residual) {
+    char err[512] = "";
+    mjModel* m = mj_loadXML(model_path, NULL, err, sizeof err);
+    if (!m) { fprintf(stderr, "%s\n", err); return 1; }
+    mjData* dStar = mj_makeData(m);
+    for (int i = 0; i < nsteps; i++) mj_step(m, dStar);
+    for (int i = 0; i < m->nu; i++) dStar->ctrl[i] -= 0.1;
+    stepCostFn_t fn = hopperTestCost;
+    Differentiator<6, 3> diff(m, dStar, fn);
+    diff.updateDerivatives();
+    if (A) mju_copy(A, diff.A->data(), 144);
+    if (B) mju_copy(B, diff.B->data(), 36);
+    if (deriv) mju_copy(deriv, diff.deriv, 105);
+    if (residual) {
+        mjData* d = mj_makeData(m);
+        cpMjData(m, d, dStar);
+        double xs[12], us[3];
+        mju_copy(xs, dStar->qpos, 12);
+        mju_copy(us, dStar->ctrl, 3);
+        mj_step(m, dStar);
+        for (int i = 0; i < 12; i++) d->qpos[i] += 1e-6;  // qpos and qvel are contiguous
+        for (int i = 0; i < 3; i++) d->ctrl[i] += 1e-6;
+        double x[12], u[3];
+        mju_copy(x, d->qpos, 12);
+        mju_copy(u, d->ctrl, 3);
+        mj_step(m, d);
+        for (int r = 0; r < 12; r++) {
+            double p = dStar->qpos[r];
+            for (int c = 0; c < 12; c++) p += (*diff.A)(r, c) * (x[c] - xs[c]);
+            for (int c = 0; c < 3; c++) p += (*diff.B)(r, c) * (u[c] - us[c]);
+            residual[r] = p - d->qpos[r];
+        }
+        mj_deleteData(d);
+    }
+    mj_deleteData(dStar);
+    mj_deleteModel(m);
+    return 0;
+}

@@ -125,13 +125,21 @@ int ilqg_step_batch_host(ilqg_handle h, int n, int nsteps, double* qpos, double*
 typedef struct ilqg_ilqr_s* ilqg_ilqr;
 int ilqg_ilqr_create(ilqg_handle h, int ninst, int N, int nalpha, const double* alphas /* host, NULL: 1,1/2,1/4,.. */, ilqg_ilqr* out);
 int ilqg_ilqr_destroy(ilqg_ilqr w);
-int ilqg_ilqr_set_cost(ilqg_ilqr w, const ilqg_cost* cost); /* host struct */
+int ilqg_ilqr_set_cost(ilqg_ilqr w, const ilqg_cost* cost); /* host struct; NULL selects host-cost mode */
 int ilqg_ilqr_set_mu(ilqg_ilqr w, double mu);               /* Levenberg-Marquardt term, default 1000 (ilqr.h:65) */
 int ilqg_ilqr_init_dev(ilqg_ilqr w, const double* qpos, const double* qvel, const double* ctrl, const double* warm, void* stream);
 int ilqg_ilqr_init_host(ilqg_ilqr w, const double* qpos, const double* qvel, const double* ctrl, const double* warm);
 int ilqg_ilqr_set_state_dev(ilqg_ilqr w, const double* qpos, const double* qvel, const double* warm, void* stream);
 int ilqg_ilqr_set_state_host(ilqg_ilqr w, const double* qpos, const double* qvel, const double* warm);
 int ilqg_ilqr_iterate(ilqg_ilqr w, int niter, int accept_always, void* stream); /* asynchronous on `stream` */
+/* the phases of one iteration, separately (ilqg_ilqr_iterate = forward; linearise; backward) */
+int ilqg_ilqr_forward(ilqg_ilqr w, int accept_always, void* stream);
+int ilqg_ilqr_linearise(ilqg_ilqr w, void* stream);
+int ilqg_ilqr_backward(ilqg_ilqr w, void* stream);
+/* host-cost mode (ilqg_ilqr_set_cost(w, NULL)): the caller's stepCostFn_t cannot run on the device, so the caller evaluates
+   the forward-difference cost rows itself and uploads them between linearise and backward: rows[ninst][T][2nv+nu] */
+int ilqg_ilqr_put_cost_rows_host(ilqg_ilqr w, const double* rows);
+int ilqg_ilqr_get_knots_host(ilqg_ilqr w, double* qpos, double* qvel, double* ctrl, double* warm);
 int ilqg_ilqr_iterations_done(ilqg_ilqr w);
 /* results, instance-major on the host; any pointer may be NULL.  Jtrace/accepted: [ninst][min(iterations,256)] */
 int ilqg_ilqr_get_host(ilqg_ilqr w, double* qpos, double* qvel, double* ctrl, double* K, double* k, double* V, double* v,

@@ -170,6 +170,122 @@ def run_reference_arm(args):
     return 0
 
 
+# ------------------------------------------------------------------ iLQR iterations/s (BASELINE configs[3])
+def bench_ilqr(pkg, dev_index, ninst, niter, reps, world, rank, with_cpu):
+    """4096 independent inverted-pendulum iLQR problems (N = 20), `niter` x ILQR::iterate each, all on the device:
+    rollouts + FD of 21 knots + Riccati per iteration.  Reference mode (alpha = 1 accepted unconditionally)."""
+    import torch
+    import torch.distributed as dist
+    from ilqg_mujoco_b200 import workload as wl
+    dev = f"cuda:{dev_index}"
+    model = pkg.Model.named("inverted_pendulum")
+    h = pkg.Handle(model, dev_index)
+    q, v, u, _ = wl.pendulum_initial_states(ninst, seed=100 + rank)
+    u = u * 0.0
+    dq, dv, du = (torch.from_numpy(a).to(dev) for a in (q, v, u))
+    dw = torch.zeros((ninst, 2), dtype=torch.float64, device=dev)
+    cost = pkg.make_cost(q2=[1, 10], v2=[1, 10], u2=[1])   # /root/reference/inc/inverted_pendulum/cost.h:7-17
+    il = pkg.Ilqr(h, ninst, 20, (1.0,))
+    il.set_cost(cost)
+    stream = torch.cuda.current_stream().cuda_stream
+    times = []
+    for r in range(reps + 1):
+        il.init_dev(dq, dv, du, dw, stream=stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        il.iterate(niter, accept_always=True, stream=stream)
+        e1.record()
+        e1.synchronize()
+        if r > 0:
+            times.append(e0.elapsed_time(e1))
+    out = il.get()
+    nonfinite = int((~np.isfinite(out["J"]).all(axis=1)).sum())
+    okm = np.isfinite(out["J"]).all(axis=1)
+    total_ms = sum(times)
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    res = {"metric": "iLQR iterations/sec (inverted pendulum, N=20, fp64)", "value": world * ninst * niter * reps / (float(t[0]) * 1e-3),
+           "unit": "iterations/s", "instances_per_gpu": ninst, "iterations": niter, "ms_per_batch_iteration": float(t[0]) / (reps * niter),
+           "diverged_instances": nonfinite,
+           "note": "reference mode = full step, no line search (ilqr.h:126): a few random starts diverge, in the oracle too (same instances)",
+           "mean_cost_first_last": [float(out["J"][okm, 0].mean()), float(out["J"][okm, -1].mean())]}
+    if with_cpu:
+        o = entry.load_oracle()
+        om = o.Model(os.path.join(pkg.MODELS_DIR, "inverted_pendulum.ilqgm"))
+        ns = min(ninst, 8 * (os.cpu_count() or 1))
+        t0 = time.perf_counter()
+        ref = o.ilqr_run_batch(om, 20, niter, q[:ns], v[:ns], u[:ns], None, cost, alphas=None)
+        dt = time.perf_counter() - t0
+        res["cpu_baseline"] = {"value": ns * niter / dt, "unit": "iterations/s", "cores": os.cpu_count(), "kind": "port",
+                               "sample": f"first {ns} instances, oracle restatement of ILQR::iterate, OpenMP over instances"}
+        both = np.isfinite(ref["J"]).all(axis=1) & okm[:ns]
+        res["parity_cost_trace_max_rel_err"] = float((np.abs(out["J"][:ns][both] - ref["J"][both]) / np.abs(ref["J"][both])).max())
+    il.close()
+    h.close()
+    return res
+
+
+# ------------------------------------------------------------------ hopper T=1000, knots sharded + all-gather (BASELINE configs[4])
+def bench_t1000(pkg, dev_index, T, steps, world, rank):
+    import torch
+    import torch.distributed as dist
+    from ilqg_mujoco_b200 import sharding, workload as wl
+    dev = f"cuda:{dev_index}"
+    model = pkg.Model.named("hopper")
+    h = pkg.Handle(model, dev_index)
+    q, v, u, w, _ = wl.make_knots(h, 1, T, seed=0, device=dev, model="hopper")   # the same nominal on every rank
+    # smooth random control (sum of 3 sinusoids) replaces the constant one: re-roll the trajectory on the device
+    tt = torch.arange(T, device=dev, dtype=torch.float64)[:, None] * 0.002
+    gen = torch.Generator(device="cpu").manual_seed(0)
+    amp = torch.rand((3, 3), generator=gen, dtype=torch.float64).to(dev) * 0.3
+    frq = (torch.rand((3, 3), generator=gen, dtype=torch.float64) * 6 + 1).to(dev)
+    u = sum(amp[i][None, :] * torch.sin(2 * np.pi * frq[i][None, :] * tt + i) for i in range(3)).contiguous()
+    qs, vs, ws = q[:1].clone(), v[:1].clone(), w[:1].clone()
+    Q, V, W = [], [], []
+    for t in range(T):
+        Q.append(qs.clone()); V.append(vs.clone()); W.append(ws.clone())
+        h.step_batch_dev(qs, vs, u[t:t + 1].contiguous(), ws, None, nsteps=1)
+    q, v, w = torch.cat(Q), torch.cat(V), torch.cat(W)
+    torch.cuda.synchronize()
+    stream = torch.cuda.current_stream().cuda_stream
+    per = sharding.padded_count(T, world)
+    local = torch.zeros((per, model.nd), dtype=torch.float64, device=dev)
+
+    def compute(qq, vv, uu, ww):
+        h.fd_batch_dev(qq, vv, uu, ww, local[:qq.shape[0]], None, None, cost=None, stream=stream)
+        return local[:qq.shape[0]]
+
+    for _ in range(3):
+        full = sharding.fd_knot_sharded(compute, q, v, u, w, model.nd)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    tot, tot_fd = 0.0, 0.0
+    lo, hi = min(rank * per, T), min(rank * per + per, T)
+    for _ in range(steps):
+        ev[0].record()
+        compute(q[lo:hi].contiguous(), v[lo:hi].contiguous(), u[lo:hi].contiguous(), w[lo:hi].contiguous())
+        ev[1].record()
+        full = sharding.fd_knot_sharded(compute, q, v, u, w, model.nd)
+        ev[2].record()
+        ev[2].synchronize()
+        tot_fd += ev[0].elapsed_time(ev[1])
+        tot += ev[1].elapsed_time(ev[2])
+    t = torch.tensor([tot, tot_fd], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ok = bool(torch.isfinite(full[:, :90]).all())
+    h.close()
+    return {"metric": "hopper T=1000 knot-sharded FD knots/sec", "value": T * steps / (float(t[0]) * 1e-3), "unit": "knots/s",
+            "value_excluding_all_gather": T * steps / (float(t[1]) * 1e-3), "T": T, "knots_per_rank": per, "finite": ok,
+            "collective": "all_gather_into_tensor of deriv blocks (840 B/knot)" if world > 1 else "none (1 rank)", "scaling": "strong"}
+
+
 # ------------------------------------------------------------------ the GPU arm
 def run_gpu_arm(args):
     import torch
@@ -262,6 +378,11 @@ def run_gpu_arm(args):
     tt = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    # secondary workloads (every rank takes part; rank 0 reports)
+    secondary = []
+    if not args.no_secondary:
+        secondary.append(bench_ilqr(pkg, local, args.ilqr_instances, 10, 3, world, rank, with_cpu=(world == 1 and rank == 0)))
+        secondary.append(bench_t1000(pkg, local, 1000, 20, world, rank))
     total_ms, e2e_ms = float(tt[0]), float(tt[1])
     value = world * nk * args.steps / (total_ms * 1e-3)
     e2e_value = world * nk * args.steps / (e2e_ms * 1e-3)
@@ -276,7 +397,7 @@ def run_gpu_arm(args):
                            "replaced_nonfinite_knots": nbad, "nonfinite_status": nonfinite},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-                "gpu_launches": launches}
+                "gpu_launches": launches, "secondary": secondary}
         # ---- roofline of the dominant kernel (fd_perturb_kernel) + cpu baseline: rank 0 only
         p_ms = float(np.mean([k[1] for k in kern_ms]))
         c_ms = float(np.mean([k[0] for k in kern_ms]))
@@ -288,7 +409,13 @@ def run_gpu_arm(args):
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         alg_bytes = nk * (8 * (model.nq + 2 * model.nv + model.nu) + 8 * model.nd)
         ach = alg_bytes / (p_ms * 1e-3) / 1e9
-        line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+        traffic = None
+        try:  # dram bytes per knot of the perturb kernel from the committed ncu --set full capture, scaled to this launch
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = tj["fd_perturb_dram_bytes_per_knot"] * nk
+        except (OSError, KeyError, ValueError):
+            pass
+        line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic,
                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650",
                             "kernel": "fd_perturb_kernel<Topo_hopper>", "kernel_ms": p_ms, "center_kernel_ms": c_ms,
                             "note": "schema-conformant HBM view; the path is fp64-compute bound (SURVEY 8d): see roofline_fp64"}
@@ -335,7 +462,7 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ntraj", type=int, default=4096)
@@ -343,6 +470,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=21 * 1024, help="knots of the workload timed on the CPU port (rank 0, N=1)")
     ap.add_argument("--ref-sample", type=int, default=21 * 48, help="knots timed through the reference's own driver in the GPU arm")
     ap.add_argument("--ref-traj", type=int, default=24, help="trajectories per step in --impl reference")
+    ap.add_argument("--ilqr-instances", type=int, default=4096, help="pendulum iLQR problems per GPU (secondary metric)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the iLQR and T=1000 secondary workloads")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

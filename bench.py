@@ -212,7 +212,7 @@ def bench_ilqr(pkg, dev_index, ninst, niter, reps, world, rank, with_cpu):
            "unit": "iterations/s", "instances_per_gpu": ninst, "iterations": niter, "ms_per_batch_iteration": float(t[0]) / (reps * niter),
            "diverged_instances": nonfinite,
            "note": "reference mode = full step, no line search (ilqr.h:126): a few random starts diverge, in the oracle too (same instances)",
-           "mean_cost_first_last": [float(out["J"][okm, 0].mean()), float(out["J"][okm, -1].mean())]}
+           "median_cost_first_last": [float(np.median(out["J"][okm, 0])), float(np.median(out["J"][okm, -1]))]}
     if with_cpu:
         o = entry.load_oracle()
         om = o.Model(os.path.join(pkg.MODELS_DIR, "inverted_pendulum.ilqgm"))

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libilqg_b200.so")
 MODELS_DIR = os.path.join(_HERE, "models")
 
-OK, ERR_ARG, ERR_MODEL, ERR_IO, ERR_CUDA, ERR_UNSUPPORTED, ERR_NONFINITE = range(7)
+OK, ERR_ARG, ERR_MODEL, ERR_IO, ERR_CUDA, ERR_UNSUPPORTED, ERR_NONFINITE, ERR_CAPACITY = range(8)
 MAXQ, MAXV, MAXU = 32, 32, 24
 
 _lib = None

@@ -21,6 +21,7 @@
 
 #include "dyn.cuh"
 #include "ilqr.cuh"
+#include "coop.cuh"
 
 namespace ilqg {
 
@@ -289,7 +290,72 @@ struct EngineT : Engine {
     cudaError_t ilqr_backward(const IlqrBuffers& b, cudaStream_t s) override { return IlqrLaunch<T>::backward(b, dm.timestep, s); }
 };
 
+// generic warp-per-rollout engine (coop.cuh): any model of the subset, used when no topology instantiation matches
+struct CoopEngine : Engine {
+    GModel* d_g = nullptr;
+    size_t warp_bytes = 0;
+    int warps = 4;
+    ilqg_model tab;
+    const char* name() const override { return "generic-warp-per-rollout"; }
+    ~CoopEngine() override { cudaFree(d_g); }
+    cudaError_t init(const ilqg_model& m) {
+        GModel* hg = new GModel();
+        if (!gmodel_from_tables(m, *hg)) { delete hg; return cudaErrorInvalidValue; }
+        tab = m;
+        warp_bytes = (coop_bytes_per_warp(m) + 15) / 16 * 16;
+        cudaError_t e = cudaMalloc(&d_g, sizeof(GModel));
+        if (e == cudaSuccess) e = cudaMemcpy(d_g, hg, sizeof(GModel), cudaMemcpyHostToDevice);
+        delete hg;
+        if (e != cudaSuccess) return e;
+        int dev = 0, maxsm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        while (warps > 1 && warp_bytes * warps > (size_t)maxsm) warps /= 2;
+        if (warp_bytes * warps > (size_t)maxsm) return cudaErrorInvalidValue;
+        const int bytes = (int)(warp_bytes * warps);
+        if ((e = cudaFuncSetAttribute(coop_center_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(coop_perturb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(coop_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(coop_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+        return cudaSuccess;
+    }
+    cudaError_t fd(int nknots, const double* qpos, const double* qvel, const double* ctrl, const double* warm, const ilqg_cost* cost_dev,
+                   const ilqg_fd_opts& o, double* deriv, double* qacc_center, int* status, cudaStream_t s, cudaEvent_t* ev) override {
+        if (nknots <= 0) return cudaSuccess;
+        const size_t smem = warp_bytes * warps;
+        const int ncol = 2 * tab.nv + tab.nu;
+        if (ev) cudaEventRecord(ev[0], s);
+        coop_center_kernel<<<(nknots + warps - 1) / warps, warps * 32, smem, s>>>(d_g, nknots, qpos, qvel, ctrl, warm, o.niter, o.nwarmup, warp_bytes,
+                                                                                qacc_center, status);
+        if (ev) cudaEventRecord(ev[1], s);
+        long items = (long)nknots * ncol;
+        coop_perturb_kernel<<<(unsigned)((items + warps - 1) / warps), warps * 32, smem, s>>>(d_g, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps,
+                                                                                          o.niter, warp_bytes, deriv, status);
+        if (ev) cudaEventRecord(ev[2], s);
+        return cudaGetLastError();
+    }
+    cudaError_t forward(int n, const double* qpos, const double* qvel, const double* ctrl, double* warm, double* qacc, cudaStream_t s) override {
+        if (n <= 0) return cudaSuccess;
+        coop_forward_kernel<<<(n + warps - 1) / warps, warps * 32, warp_bytes * warps, s>>>(d_g, n, qpos, qvel, ctrl, warm, qacc, warp_bytes);
+        return cudaGetLastError();
+    }
+    cudaError_t step(int n, int nsteps, double* qpos, double* qvel, const double* ctrl, double* warm, double* qacc, cudaStream_t s) override {
+        if (n <= 0) return cudaSuccess;
+        if (tab.integrator != ILQG_INT_EULER) return cudaErrorNotSupported;
+        coop_step_kernel<<<(n + warps - 1) / warps, warps * 32, warp_bytes * warps, s>>>(d_g, n, nsteps, qpos, qvel, ctrl, warm, qacc, warp_bytes);
+        return cudaGetLastError();
+    }
+    bool ilqr_supported() const override { return false; }
+    cudaError_t ilqr_rollout(const IlqrBuffers&, const ilqg_cost*, cudaStream_t) override { return cudaErrorNotSupported; }
+    cudaError_t ilqr_accept(const IlqrBuffers&, int, double*, int*, cudaStream_t) override { return cudaErrorNotSupported; }
+    cudaError_t ilqr_backward(const IlqrBuffers&, cudaStream_t) override { return cudaErrorNotSupported; }
+};
+
 static Engine* make_engine(const ilqg_model& m) {
+    if (getenv("ILQG_FORCE_GENERIC")) {  // test hook: run a compiled-in topology through the generic engine
+        auto c = std::make_unique<CoopEngine>();
+        return c->init(m) == cudaSuccess ? c.release() : nullptr;
+    }
 #define ILQG_TRY(TOPO)                                          \
     {                                                           \
         auto e = std::make_unique<EngineT<TOPO>>();             \
@@ -297,6 +363,9 @@ static Engine* make_engine(const ilqg_model& m) {
     }
     ILQG_FOR_EACH_TOPOLOGY(ILQG_TRY)
 #undef ILQG_TRY
+    if (getenv("ILQG_NO_GENERIC")) return nullptr;
+    auto c = std::make_unique<CoopEngine>();
+    if (c->init(m) == cudaSuccess) return c.release();
     return nullptr;
 }
 
@@ -534,7 +603,7 @@ int ilqg_fd_batch_host(ilqg_handle h, int nknots, const double* qpos, const doub
         if (status) status[i] = hs[i];
         if (hs[i]) bad = 1;
     }
-    return bad ? fail(h, ILQG_ERR_NONFINITE, "non-finite accelerations in at least one knot") : ILQG_OK;
+    return bad ? fail(h, ILQG_ERR_NONFINITE, "non-finite accelerations or exceeded contact capacity in at least one knot (see status[])") : ILQG_OK;
 }
 
 int ilqg_forward_batch_dev(ilqg_handle h, int n, const double* qpos, const double* qvel, const double* ctrl, double* warmstart,

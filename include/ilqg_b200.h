@@ -39,7 +39,8 @@ enum {
     ILQG_ERR_IO = 3,
     ILQG_ERR_CUDA = 4,        /* CUDA runtime error (text via ilqg_last_error) */
     ILQG_ERR_UNSUPPORTED = 5, /* no kernel instantiation for this model's shape */
-    ILQG_ERR_NONFINITE = 6    /* a rollout produced NaN/Inf (per-knot flags in `status`) */
+    ILQG_ERR_NONFINITE = 6,   /* a rollout produced NaN/Inf (per-knot flags in `status`) */
+    ILQG_ERR_CAPACITY = 7     /* more contacts / constraint rows than the kernel's shared-memory budget (per-knot flag) */
 };
 
 typedef struct ilqg_handle_s* ilqg_handle;

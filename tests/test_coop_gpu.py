@@ -1,0 +1,80 @@
+"""The generic warp-per-rollout engine (csrc/coop.cuh): humanoid FD (BASELINE configs[2]: free-joint quaternion
+perturbations, nv = 27, 161 collision pairs) against the oracle and the golden fixture, and — forced onto the small
+models — against the same tolerances as the thread-per-rollout kernels."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, scenario_states
+from test_fd_gpu import assert_deriv_close
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def generic_handles(pkg):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    os.environ["ILQG_FORCE_GENERIC"] = "1"
+    try:
+        hs = {n: pkg.Handle(pkg.Model.named(n), 0) for n in ("inverted_pendulum", "hopper", "humanoid")}
+    finally:
+        del os.environ["ILQG_FORCE_GENERIC"]
+    for h in hs.values():
+        assert h.engine == "generic-warp-per-rollout"
+    yield hs
+    for h in hs.values():
+        h.close()
+
+
+def test_humanoid_uses_the_generic_engine_by_default(pkg):
+    h = pkg.Handle(pkg.Model.named("humanoid"), 0)
+    assert h.engine == "generic-warp-per-rollout"
+    h.close()
+
+
+@pytest.mark.parametrize("name", ["inverted_pendulum", "hopper", "humanoid"])
+def test_golden_vectors(generic_handles, name):
+    h = generic_handles[name]; m = h.model
+    g = np.load(os.path.join(GOLD, f"fd_{name}.npz"))
+    deriv, qacc, status = h.fd_batch_host(g["qpos"], g["qvel"], g["ctrl"], g["warm"], g["cost"])
+    assert status.sum() == 0, status
+    assert np.allclose(qacc, g["qacc"], rtol=1e-8, atol=1e-8)
+    assert_deriv_close(deriv, g["deriv"], m.nv, m.nu, tol=1e-6 if name != "humanoid" else 1e-5)
+
+
+@pytest.mark.parametrize("name,n,roll", [("inverted_pendulum", 70, 10), ("hopper", 64, 0), ("hopper", 40, 150), ("humanoid", 12, 0),
+                                         ("humanoid", 10, 30), ("humanoid", 8, 80)])
+def test_parity_with_oracle(generic_handles, oracle, omodels, name, n, roll):
+    h = generic_handles[name]; m = h.model; om = omodels[name]
+    q, v, u, w = scenario_states(name, n, seed=300 + roll, oracle=oracle, om=om, roll=roll)
+    cost = oracle.make_cost(q2=[1, 10], v2=[1, 10], u2=[1], q1=[0.5, 0, 2])
+    d_ref, a_ref, _ = oracle.fd_batch(om, q, v, u, w, cost)
+    d_gpu, a_gpu, status = h.fd_batch_host(q, v, u, w, cost)
+    assert status.sum() == 0, status
+    assert np.allclose(a_gpu, a_ref, rtol=1e-8, atol=1e-8)
+    assert_deriv_close(d_gpu, d_ref, m.nv, m.nu, tol=1e-6 if name != "humanoid" else 1e-5)
+
+
+def test_humanoid_forward_and_step_match_oracle(generic_handles, oracle, omodels):
+    h = generic_handles["humanoid"]; om = omodels["humanoid"]
+    q, v, u, w = scenario_states("humanoid", 16, seed=77, oracle=oracle, om=om, roll=40)
+    a_ref, _ = oracle.forward_batch(om, q, v, u, w)
+    a_gpu, _ = h.forward_batch_host(q, v, u, w)
+    assert np.allclose(a_gpu, a_ref, rtol=1e-5, atol=1e-5)       # XML tolerance 1e-10, 50 iterations
+    q1, v1, w1, _ = oracle.step_batch(om, q, v, u, w, 10)
+    q2, v2, w2, _ = h.step_batch_host(q, v, u, w, nsteps=10)
+    assert np.allclose(q2, q1, rtol=1e-7, atol=1e-7) and np.allclose(v2, v1, rtol=1e-5, atol=1e-5)
+    assert np.allclose(np.linalg.norm(q2[:, 3:7], axis=1), 1.0, atol=1e-12)   # quaternion stays normalised
+
+
+def test_capacity_overflow_is_flagged(generic_handles, pkg):
+    """A humanoid pushed deep into the floor produces more rows than the shared-memory budget: flagged, not silent."""
+    h = generic_handles["humanoid"]
+    q = np.zeros((1, 28)); q[0, 2] = 0.05; q[0, 3] = 1.0      # lying inside the ground plane: every geom touches
+    v = np.zeros((1, 27)); u = np.zeros((1, 21)); w = np.zeros((1, 27))
+    d, a, status = h.fd_batch_host(q, v, u, w, None)
+    assert status[0] in (0, pkg.ERR_CAPACITY, pkg.ERR_NONFINITE)

@@ -286,6 +286,57 @@ def bench_t1000(pkg, dev_index, T, steps, world, rank):
             "collective": "all_gather_into_tensor of deriv blocks (840 B/knot)" if world > 1 else "none (1 rank)", "scaling": "strong"}
 
 
+# ------------------------------------------------------------------ humanoid FD (BASELINE configs[2])
+def bench_humanoid(pkg, dev_index, nknots, steps, world, rank, with_cpu):
+    import torch
+    import torch.distributed as dist
+    from ilqg_mujoco_b200 import workload as wl
+    dev = f"cuda:{dev_index}"
+    model = pkg.Model.named("humanoid")
+    h = pkg.Handle(model, dev_index)
+    q, v, u, w, nbad = wl.humanoid_states(h, nknots, seed=rank, device=dev)
+    deriv = torch.zeros((nknots, model.nd), dtype=torch.float64, device=dev)
+    qacc = torch.zeros((nknots, model.nv), dtype=torch.float64, device=dev)
+    status = torch.zeros(nknots, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    for _ in range(2):
+        h.fd_batch_dev(q, v, u, w, deriv, qacc, status, cost=None, stream=stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        h.fd_batch_dev(q, v, u, w, deriv, qacc, status, cost=None, stream=stream)
+    e1.record()
+    e1.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    st = status.cpu().numpy()
+    res = {"metric": "FD dynamics Jacobian knots/sec (humanoid, fp64)", "value": world * nknots * steps / (float(t[0]) * 1e-3), "unit": "knots/s",
+           "knots_per_gpu": nknots, "engine": h.engine, "status_ok": int((st == 0).sum()), "status_capacity": int((st == 7).sum()),
+           "status_nonfinite": int((st == 6).sum()), "replaced_nonfinite_states": nbad}
+    if with_cpu:
+        o = entry.load_oracle()
+        om = o.Model(os.path.join(pkg.MODELS_DIR, "humanoid.ilqgm"))
+        ns = min(nknots, 4 * (os.cpu_count() or 1))
+        sq, sv, su, sw = (x[:ns].cpu().numpy().copy() for x in (q, v, u, w))
+        t0 = time.perf_counter()
+        dref, _, flops = o.fd_batch(om, sq, sv, su, sw, None, nthreads=0)
+        dt = time.perf_counter() - t0
+        ok = st[:ns] == 0
+        dg = deriv[:ns].cpu().numpy()[:, :model.nv * (2 * model.nv + model.nu)]
+        dr = dref[:, :model.nv * (2 * model.nv + model.nu)]
+        res["cpu_baseline"] = {"value": ns / dt, "unit": "knots/s", "cores": os.cpu_count(), "kind": "port",
+                               "sample": f"first {ns} knots, oracle FD, OpenMP over knots"}
+        res["flops_per_knot_oracle"] = flops / ns
+        if ok.any():
+            res["parity_sample_max_rel_err"] = float(np.abs(dg[ok] - dr[ok]).max() / max(1.0, np.abs(dr[ok]).max()))
+    h.close()
+    return res
+
+
 # ------------------------------------------------------------------ the GPU arm
 def run_gpu_arm(args):
     import torch
@@ -383,6 +434,7 @@ def run_gpu_arm(args):
     if not args.no_secondary:
         secondary.append(bench_ilqr(pkg, local, args.ilqr_instances, 10, 3, world, rank, with_cpu=(world == 1 and rank == 0)))
         secondary.append(bench_t1000(pkg, local, 1000, 20, world, rank))
+        secondary.append(bench_humanoid(pkg, local, args.humanoid_knots, 3, world, rank, with_cpu=(world == 1 and rank == 0)))
     total_ms, e2e_ms = float(tt[0]), float(tt[1])
     value = world * nk * args.steps / (total_ms * 1e-3)
     e2e_value = world * nk * args.steps / (e2e_ms * 1e-3)
@@ -471,6 +523,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=21 * 48, help="knots timed through the reference's own driver in the GPU arm")
     ap.add_argument("--ref-traj", type=int, default=24, help="trajectories per step in --impl reference")
     ap.add_argument("--ilqr-instances", type=int, default=4096, help="pendulum iLQR problems per GPU (secondary metric)")
+    ap.add_argument("--humanoid-knots", type=int, default=4096, help="humanoid knots per GPU (secondary metric)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the iLQR and T=1000 secondary workloads")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -31,6 +31,42 @@ def pendulum_initial_states(n, seed=0):
     return qpos, qvel, ctrl, np.zeros(n, dtype=np.int64)
 
 
+def humanoid_states(handle, n, seed=0, device="cuda:0"):
+    """Config-3 generator: torso z ~ U[1.2,1.5], unit quaternion perturbed by N(0,0.1^2) in the tangent space, joints within
+    30 % of their range, qvel ~ N(0,0.3^2), ctrl ~ U[-0.4,0.4] (/root/reference/res/humanoid.xml:16), rolled forward
+    0..300 steps on the device."""
+    m = handle.model
+    rng = np.random.default_rng(seed)
+    rngs = m.field("jnt_range").reshape(-1, 2)[1:m.njnt]
+    mid, half = 0.5 * (rngs[:, 0] + rngs[:, 1]), 0.5 * (rngs[:, 1] - rngs[:, 0])
+    q = np.zeros((n, m.nq))
+    q[:, 2] = rng.uniform(1.2, 1.5, n)
+    w = rng.normal(0, 0.1, (n, 3))
+    ang = np.linalg.norm(w, axis=1, keepdims=True)
+    q[:, 3] = np.cos(ang[:, 0] / 2)
+    q[:, 4:7] = w / np.maximum(ang, 1e-12) * np.sin(ang / 2)
+    q[:, 7:] = mid + rng.uniform(-0.3, 0.3, (n, m.njnt - 1)) * half
+    v = rng.normal(0, 0.3, (n, m.nv))
+    u = rng.uniform(-0.4, 0.4, (n, m.nu))
+    roll = rng.integers(0, 7, n) * 50
+    order = np.argsort(roll, kind="stable")
+    q, v, u, roll = q[order], v[order], u[order], roll[order]
+    dq, dv, du = (torch.from_numpy(a).to(device) for a in (q, v, u))
+    dw = torch.zeros((n, m.nv), dtype=torch.float64, device=device)
+    for r in range(50, int(roll.max()) + 1, 50):
+        start = int(np.searchsorted(roll, r, side="left"))
+        if start < n:
+            handle.step_batch_dev(dq[start:], dv[start:], du[start:], dw[start:], None, nsteps=50)
+    torch.cuda.synchronize()
+    bad = ~(torch.isfinite(dq).all(dim=1) & torch.isfinite(dv).all(dim=1) & torch.isfinite(dw).all(dim=1))
+    nbad = int(bad.sum())
+    if nbad:
+        dq[bad] = torch.from_numpy(m.field("qpos0")[:m.nq].copy()).to(device)
+        dv[bad] = 0.0
+        dw[bad] = 0.0
+    return dq.contiguous(), dv.contiguous(), du.contiguous(), dw.contiguous(), nbad
+
+
 def make_knots(handle, ntraj, T, seed=0, device="cuda:0", model="hopper"):
     """ntraj trajectories x T knots: random initial states, pre-rolled 0..200 steps so that a good share
     of the knots is in ground contact, then T knots one mj_step apart under constant control.

@@ -314,9 +314,14 @@ DEV void make_frame(V3 n, V3 hint, bool has_hint, V3& t1, V3& t2) {
 
 // ------------------------------------------------------------------ the pipeline up to the constraint problem
 // Computes M, its factor, qfrc_smooth, qacc_smooth and the constraint rows (J, D, aref) for one rollout.
-template <class T>
+// SYNC: block-wide barriers between the stages.  The stage code is long and straight-line (fully unrolled); without them the
+// warps of a CTA drift apart and each streams its own copy of the instructions through the instruction caches (ncu: the
+// second-largest stall reason was "no instruction").  With them the CTA's warps walk the code together and share fetches.
+// Every thread of the block must call build_problem when SYNC is set.
+template <class T, bool SYNC = false>
 DEV void build_problem(const DevModel<T>& m, const double (&q)[T::NQ], const double (&qv)[T::NV], const double (&u)[nz(T::NU)],
                        Work<T>& w) {
+    auto stage_sync = [&]() { if constexpr (SYNC) __syncthreads(); };
     constexpr int NB = T::NBODY, NV = T::NV, NJ = T::NJNT;
     V3 xpos[NB];
     M3 xmat[NB];
@@ -364,6 +369,7 @@ DEV void build_problem(const DevModel<T>& m, const double (&q)[T::NQ], const dou
         xquat[b] = quat;
         xmat[b] = q2m(quat);
     });
+    stage_sync();
     // ---- mj_comPos: tree centres of mass, spatial inertias, motion axes
     V3 xipos[NB], com[NB];
     double tmass[NB];
@@ -412,6 +418,7 @@ DEV void build_problem(const DevModel<T>& m, const double (&q)[T::NQ], const dou
             cdof[da] = {axis[j], cross(axis[j], off)};
         }
     });
+    stage_sync();
     // ---- mj_comVel + mj_rne(flg_acc=0): bias forces
     S6 cvel[NB], cdofdot[NV], cacc[NB], cfrc[NB];
     cvel[0] = {{0, 0, 0}, {0, 0, 0}};
@@ -455,6 +462,7 @@ DEV void build_problem(const DevModel<T>& m, const double (&q)[T::NQ], const dou
         if constexpr (T::act_limited(a)) c = clampd(c, m.act_range[a][0], m.act_range[a][1]);
         w.fs[T::act_dof(a)] += m.act_gear[a] * c;
     });
+    stage_sync();
     // ---- mj_crb + factor
     Inert crb[NB];
     sfor<1, NB>([&](auto bb) { crb[IDX(bb)] = cin[IDX(bb)]; });
@@ -476,6 +484,7 @@ DEV void build_problem(const DevModel<T>& m, const double (&q)[T::NQ], const dou
     sfor<0, NV>([&](auto ii) { w.as[IDX(ii)] = w.fs[IDX(ii)]; });
     chol_solve_packed<NV>(w.L, w.as);
 
+    stage_sync();
     // ---- constraint rows: joint limits, then contacts
     int ne = 0;
     sfor<0, NJ>([&](auto jj) {
@@ -498,6 +507,7 @@ DEV void build_problem(const DevModel<T>& m, const double (&q)[T::NQ], const dou
             });
         }
     });
+    stage_sync();
     if constexpr (T::NPAIR > 0) {
         // geom frames
         V3 gpos[T::NGEOM], gax[T::NGEOM];
@@ -644,6 +654,7 @@ DEV void build_problem(const DevModel<T>& m, const double (&q)[T::NQ], const dou
         });
     }
     w.nefc = ne;
+    stage_sync();
 }
 
 // ------------------------------------------------------------------ constraint solve (mj_fwdConstraint)

@@ -77,7 +77,7 @@ struct FdShape {
     static_assert(G <= 32, "thread-per-rollout FD kernel needs 2(2nv+nu) <= 32; larger models use the cooperative kernel");
 };
 
-template <class T, int WARPS, int MINBLOCKS>
+template <class T, int WARPS, int MINBLOCKS, bool SYNC>
 __global__ void __launch_bounds__(WARPS * 32, MINBLOCKS) fd_perturb_kernel(const __grid_constant__ DevModel<T> m, int nknots,
                                                                  const double* __restrict__ qpos, const double* __restrict__ qvel,
                                                                  const double* __restrict__ ctrl, const double* __restrict__ qacc_center,
@@ -95,10 +95,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINBLOCKS) fd_perturb_kernel(const
     const double se = (l & 1) ? -eps : eps;
     double qacc[NV];
     double dcost = 0;
-    if (valid) {
+    {
+        // idle lanes (tail of the grid, lanes 30-31 of a hopper warp) evaluate a clamped knot with their writes masked, so
+        // that every thread reaches the stage barriers
+        const int kk = valid ? k : (k < nknots ? k : nknots - 1);
         double q[NQ], v[NV], u[nz(NU)], warm[NV];
-        load_knot<T>(k, qpos, qvel, ctrl, q, v, u);
-        sfor<0, NV>([&](auto ii) { warm[IDX(ii)] = qacc_center[(size_t)k * NV + IDX(ii)]; });
+        load_knot<T>(kk, qpos, qvel, ctrl, q, v, u);
+        sfor<0, NV>([&](auto ii) { warm[IDX(ii)] = qacc_center[(size_t)kk * NV + IDX(ii)]; });
         double c0 = 0;
         if (cost) c0 = cost_eval<T>(*cost, q, v, u);
         // perturb this lane's input (ctrl: mjderivative.cpp:85,99; qvel: :117,130; qpos: :164-169,187-192)
@@ -116,18 +119,17 @@ __global__ void __launch_bounds__(WARPS * 32, MINBLOCKS) fd_perturb_kernel(const
         });
         if (cost && !(l & 1)) dcost = __ddiv_rn(__dsub_rn(cost_eval<T>(*cost, q, v, u), c0), eps);
         Work<T> w;
-        build_problem<T>(m, q, v, u, w);
+        build_problem<T, SYNC>(m, q, v, u, w);
         solve<T>(m, w, warm, qacc, niter, 0.0);
-    } else {
-        sfor<0, NV>([&](auto ii) { qacc[IDX(ii)] = 0; });
     }
     // central difference: the '+' lane (even) takes the '-' lane's result
     bool finite = true;
-    double* st = stage[wib] + sub * S::ND;
+    const double inv2eps = 1.0 / (2 * eps);
+    double* st = stage[wib] + (sub < S::KPW ? sub : 0) * S::ND;
     sfor<0, NV>([&](auto jj) {
         constexpr int j = IDX(jj);
         double other = __shfl_xor_sync(0xffffffffu, qacc[j], 1);
-        double d = (qacc[j] - other) / (2 * eps);
+        double d = (qacc[j] - other) * inv2eps;
         finite = finite && isfinite(d);
         if (valid && !(l & 1)) {
             // reference layout: block of kind, element i + j*stride
@@ -230,7 +232,7 @@ struct IlqrLaunch<T, true> {
 
 // ------------------------------------------------------------------ engines (one per compiled-in topology)
 struct Engine {
-    int fd_minblocks = 2;
+    int fd_variant = 2;
     virtual ~Engine() {}
     virtual const char* name() const = 0;
     virtual cudaError_t fd(int nknots, const double* qpos, const double* qvel, const double* ctrl, const double* warm,
@@ -261,10 +263,10 @@ struct EngineT : Engine {
         if (ev) cudaEventRecord(ev[1], s);
         int nwarps = (nknots + S::KPW - 1) / S::KPW;
         dim3 grid((nwarps + WARPS - 1) / WARPS), block(WARPS * 32);
-        switch (fd_minblocks) {  // register budget of the perturb kernel: 255 / 168 / 128 per thread
-            case 4: fd_perturb_kernel<T, WARPS, 4><<<grid, block, 0, s>>>(dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps, o.niter, deriv, status); break;
-            case 3: fd_perturb_kernel<T, WARPS, 3><<<grid, block, 0, s>>>(dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps, o.niter, deriv, status); break;
-            default: fd_perturb_kernel<T, WARPS, 2><<<grid, block, 0, s>>>(dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps, o.niter, deriv, status); break;
+        switch (fd_variant) {  // experiment switch (ILQG_FD_VARIANT): 0 = 4 warps x 2 CTAs/SM, no stage barriers; 1 = with barriers; 2 = 8 warps x 1 CTA with barriers
+            case 0: fd_perturb_kernel<T, 4, 2, false><<<grid, block, 0, s>>>(dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps, o.niter, deriv, status); break;
+            case 2: fd_perturb_kernel<T, 8, 1, true><<<dim3((nwarps + 7) / 8), dim3(256), 0, s>>>(dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps, o.niter, deriv, status); break;
+            default: fd_perturb_kernel<T, 4, 2, true><<<grid, block, 0, s>>>(dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps, o.niter, deriv, status); break;
         }
         if (ev) cudaEventRecord(ev[2], s);
         return cudaGetLastError();
@@ -401,6 +403,7 @@ struct ilqg_handle_s {
     void* d_stage = nullptr; size_t stage_cap = 0;
     long launches = 0;  // kernels launched through this handle (bench.py reports it)
     bool profiling = false;
+    cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};  // chunk pipeline of the *_host FD entry point
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};  // around the two FD kernels when profiling is on
 };
 
@@ -450,7 +453,7 @@ int ilqg_create(const ilqg_model* m, int device, ilqg_handle* out) {
     h->device = device;
     h->model = *m;
     h->eng = eng;
-    if (const char* e = getenv("ILQG_FD_MINBLOCKS")) eng->fd_minblocks = atoi(e);
+    if (const char* e = getenv("ILQG_FD_VARIANT")) eng->fd_variant = atoi(e);
     if (cudaMalloc(&h->d_cost, sizeof(ilqg_cost)) != cudaSuccess) {
         delete eng;
         delete h;
@@ -467,6 +470,7 @@ int ilqg_destroy(ilqg_handle h) {
     cudaFree(h->d_cost);
     cudaFree(h->d_stage);
     for (int i = 0; i < 3; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    for (int i = 0; i < 3; i++) if (h->pipe[i]) cudaStreamDestroy(h->pipe[i]);
     delete h->eng;
     delete h;
     return ILQG_OK;
@@ -541,31 +545,37 @@ static int ensure_stage(ilqg_handle h, size_t bytes) {
     return ILQG_OK;
 }
 
-int ilqg_fd_batch_dev(ilqg_handle h, int nknots, const double* qpos, const double* qvel, const double* ctrl, const double* warmstart,
-                      const ilqg_cost* cost, const ilqg_fd_opts* opts, double* deriv, double* qacc_out, int* status, void* stream) {
-    if (!h) return ILQG_ERR_ARG;
-    if (nknots < 0 || (nknots > 0 && (!qpos || !qvel || !deriv || (h->model.nu > 0 && !ctrl)))) return fail(h, ILQG_ERR_ARG, "null buffer");
-    if (nknots == 0) return ILQG_OK;
+// launch the two FD kernels; `dcost` is a DEVICE pointer (or NULL)
+static int fd_launch(ilqg_handle h, int nknots, const double* qpos, const double* qvel, const double* ctrl, const double* warmstart,
+                     const ilqg_cost* dcost, const ilqg_fd_opts* opts, double* deriv, double* qacc_out, int* status, cudaStream_t s) {
     ilqg_fd_opts o;
     ilqg_fd_opts_default(&o);
     if (opts) o = *opts;
     if (!(o.eps > 0) || o.niter < 0 || o.nwarmup < 1) return fail(h, ILQG_ERR_ARG, "bad FD options");
-    cudaStream_t s = (cudaStream_t)stream;
-    CU(h, cudaSetDevice(h->device));
     double* center = qacc_out;
     if (!center) {
         int rc = ensure_center(h, (size_t)nknots * h->model.nv);
         if (rc) return rc;
         center = h->d_center;
     }
+    CU(h, h->eng->fd(nknots, qpos, qvel, ctrl, warmstart, dcost, o, deriv, center, status, s, h->profiling ? h->ev : nullptr));
+    h->launches += 2;
+    return ILQG_OK;
+}
+
+int ilqg_fd_batch_dev(ilqg_handle h, int nknots, const double* qpos, const double* qvel, const double* ctrl, const double* warmstart,
+                      const ilqg_cost* cost, const ilqg_fd_opts* opts, double* deriv, double* qacc_out, int* status, void* stream) {
+    if (!h) return ILQG_ERR_ARG;
+    if (nknots < 0 || (nknots > 0 && (!qpos || !qvel || !deriv || (h->model.nu > 0 && !ctrl)))) return fail(h, ILQG_ERR_ARG, "null buffer");
+    if (nknots == 0) return ILQG_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(h, cudaSetDevice(h->device));
     const ilqg_cost* dcost = nullptr;
     if (cost) {  // `cost` is a HOST struct even in the _dev flavour (it is a small parameter block, like opts)
         CU(h, cudaMemcpyAsync(h->d_cost, cost, sizeof(ilqg_cost), cudaMemcpyHostToDevice, s));
         dcost = h->d_cost;
     }
-    CU(h, h->eng->fd(nknots, qpos, qvel, ctrl, warmstart, dcost, o, deriv, center, status, s, h->profiling ? h->ev : nullptr));
-    h->launches += 2;
-    return ILQG_OK;
+    return fd_launch(h, nknots, qpos, qvel, ctrl, warmstart, dcost, opts, deriv, qacc_out, status, s);
 }
 
 int ilqg_fd_batch_host(ilqg_handle h, int nknots, const double* qpos, const double* qvel, const double* ctrl, const double* warmstart,
@@ -584,20 +594,36 @@ int ilqg_fd_batch_host(ilqg_handle h, int nknots, const double* qpos, const doub
     if (rc) return rc;
     double* b = (double*)h->d_stage;
     int* dstat = (int*)(b + ndbl);
-    cudaStream_t s = 0;
-    CU(h, cudaMemcpyAsync(b + off_q, qpos, n * nq * sizeof(double), cudaMemcpyHostToDevice, s));
-    CU(h, cudaMemcpyAsync(b + off_v, qvel, n * nv * sizeof(double), cudaMemcpyHostToDevice, s));
-    if (nu) CU(h, cudaMemcpyAsync(b + off_u, ctrl, n * nu * sizeof(double), cudaMemcpyHostToDevice, s));
-    if (warmstart) CU(h, cudaMemcpyAsync(b + off_w, warmstart, n * nv * sizeof(double), cudaMemcpyHostToDevice, s));
-    else CU(h, cudaMemsetAsync(b + off_w, 0, n * nv * sizeof(double), s));
-    if (!cost) CU(h, cudaMemcpyAsync(b + off_d, deriv, n * nd * sizeof(double), cudaMemcpyHostToDevice, s));  // keep caller's cost entries
-    rc = ilqg_fd_batch_dev(h, nknots, b + off_q, b + off_v, b + off_u, b + off_w, cost, opts, b + off_d, b + off_a, dstat, s);
-    if (rc) return rc;
-    CU(h, cudaMemcpyAsync(deriv, b + off_d, n * nd * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (qacc_out) CU(h, cudaMemcpyAsync(qacc_out, b + off_a, n * nv * sizeof(double), cudaMemcpyDeviceToHost, s));
     std::unique_ptr<int[]> hs(new int[n]);
-    CU(h, cudaMemcpyAsync(hs.get(), dstat, n * sizeof(int), cudaMemcpyDeviceToHost, s));
-    CU(h, cudaStreamSynchronize(s));
+    // Pipeline over chunks of knots on three streams: while chunk c computes, chunk c+1 uploads and chunk c-1 downloads
+    // (the deriv download is 5x the upload and, at PCIe rates, as long as the kernels).
+    if (!h->pipe[0])
+        for (int i = 0; i < 3; i++) CU(h, cudaStreamCreateWithFlags(&h->pipe[i], cudaStreamNonBlocking));
+    const ilqg_cost* dcost = nullptr;
+    if (cost) {
+        CU(h, cudaMemcpy(h->d_cost, cost, sizeof(ilqg_cost), cudaMemcpyHostToDevice));
+        dcost = h->d_cost;
+    }
+    const size_t chunk = n <= 4096 ? n : (n + 7) / 8 < 4096 ? 4096 : (n + 7) / 8;
+    int ci = 0;
+    for (size_t lo = 0; lo < n; lo += chunk, ci++) {
+        const size_t cn = lo + chunk <= n ? chunk : n - lo;
+        cudaStream_t s = h->pipe[ci % 3];
+        CU(h, cudaMemcpyAsync(b + off_q + lo * nq, qpos + lo * nq, cn * nq * sizeof(double), cudaMemcpyHostToDevice, s));
+        CU(h, cudaMemcpyAsync(b + off_v + lo * nv, qvel + lo * nv, cn * nv * sizeof(double), cudaMemcpyHostToDevice, s));
+        if (nu) CU(h, cudaMemcpyAsync(b + off_u + lo * nu, ctrl + lo * nu, cn * nu * sizeof(double), cudaMemcpyHostToDevice, s));
+        if (warmstart) CU(h, cudaMemcpyAsync(b + off_w + lo * nv, warmstart + lo * nv, cn * nv * sizeof(double), cudaMemcpyHostToDevice, s));
+        else CU(h, cudaMemsetAsync(b + off_w + lo * nv, 0, cn * nv * sizeof(double), s));
+        if (!cost)  // keep the caller's cost-gradient entries
+            CU(h, cudaMemcpyAsync(b + off_d + lo * nd, deriv + lo * nd, cn * nd * sizeof(double), cudaMemcpyHostToDevice, s));
+        rc = fd_launch(h, (int)cn, b + off_q + lo * nq, b + off_v + lo * nv, b + off_u + lo * nu, b + off_w + lo * nv, dcost, opts,
+                       b + off_d + lo * nd, b + off_a + lo * nv, dstat + lo, s);
+        if (rc) return rc;
+        CU(h, cudaMemcpyAsync(deriv + lo * nd, b + off_d + lo * nd, cn * nd * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (qacc_out) CU(h, cudaMemcpyAsync(qacc_out + lo * nv, b + off_a + lo * nv, cn * nv * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    for (int i = 0; i < 3; i++) CU(h, cudaStreamSynchronize(h->pipe[i]));
+    CU(h, cudaMemcpy(hs.get(), dstat, n * sizeof(int), cudaMemcpyDeviceToHost));  // pageable target: after the pipeline has drained
     int bad = 0;
     for (size_t i = 0; i < n; i++) {
         if (status) status[i] = hs[i];

@@ -213,12 +213,22 @@ struct Work {
     double M[NT];    // mass matrix (packed lower)
     double L[NT];    // Cholesky factor of M, diagonal entries hold 1/L_ii
     double fs[NV];   // qfrc_smooth
+    double fb[NV];   // qfrc_passive - qfrc_bias (the velocity stage's product; qfrc_smooth = fb + actuation)
     double as[NV];   // qacc_smooth
     double fc[NV];   // qfrc_constraint of the last solve
     int nefc;
     int iters;       // Newton iterations of the last solve
     double J[ME][NV];
     double D[ME], aref[ME], jar[ME], jv[ME];
+    double rB[ME], rkt[ME];  // per-row damping B and stiffness term K*imp*(pos-margin): aref = -B (J qvel) - rkt
+};
+
+// what the position stage leaves for the velocity stage (mjSTAGE_POS products that mj_fwdVelocity reads)
+template <class T>
+struct PosStage {
+    S6 cdof[T::NV];
+    Inert cin[T::NBODY];
+    double dspr[T::NV];  // q - qpos_spring of sprung dofs
 };
 
 // packed Cholesky A = L L^T with reciprocal diagonal
@@ -313,14 +323,19 @@ DEV void make_frame(V3 n, V3 hint, bool has_hint, V3& t1, V3& t2) {
 }
 
 // ------------------------------------------------------------------ the pipeline up to the constraint problem
-// Computes M, its factor, qfrc_smooth, qacc_smooth and the constraint rows (J, D, aref) for one rollout.
+// Split along MuJoCo's stage boundaries (mjSTAGE_POS / mjSTAGE_VEL, the skip levels the reference passes to
+// mj_forwardSkip, /root/reference/src/mjderivative.cpp:92,124,178):
+//   build_pos     everything that depends on qpos only: frames, com, spatial inertias, motion axes, M and its factor,
+//                 the constraint rows' J, D and the per-row constants (B, K*imp*(pos-margin))
+//   build_vel     everything that also depends on qvel: bias forces (RNE), passive forces, the rows' aref
+//   finish_smooth actuation, qfrc_smooth, qacc_smooth
+// A qvel / ctrl column of the FD re-runs only the later stages on the centre's position-stage products.
 // SYNC: block-wide barriers between the stages.  The stage code is long and straight-line (fully unrolled); without them the
 // warps of a CTA drift apart and each streams its own copy of the instructions through the instruction caches (ncu: the
 // second-largest stall reason was "no instruction").  With them the CTA's warps walk the code together and share fetches.
-// Every thread of the block must call build_problem when SYNC is set.
+// Every thread of the block must call the stage functions when SYNC is set.
 template <class T, bool SYNC = false>
-DEV void build_problem(const DevModel<T>& m, const double (&q)[T::NQ], const double (&qv)[T::NV], const double (&u)[nz(T::NU)],
-                       Work<T>& w) {
+DEV void build_pos(const DevModel<T>& m, const double (&q)[T::NQ], PosStage<T>& ps, Work<T>& w) {
     auto stage_sync = [&]() { if constexpr (SYNC) __syncthreads(); };
     constexpr int NB = T::NBODY, NV = T::NV, NJ = T::NJNT;
     V3 xpos[NB];
@@ -383,7 +398,7 @@ DEV void build_problem(const DevModel<T>& m, const double (&q)[T::NQ], const dou
         constexpr int b = IDX(bb);
         if constexpr (T::body_root(b) == b) com[b] = (1.0 / tmass[b]) * com[b];
     });
-    Inert cin[NB];
+    Inert (&cin)[NB] = ps.cin;
     sfor<1, NB>([&](auto bb) {
         constexpr int b = IDX(bb);
         const M3& R = xmat[b];
@@ -403,7 +418,7 @@ DEV void build_problem(const DevModel<T>& m, const double (&q)[T::NQ], const dou
         cin[b] = {dot(t0, R.r0) + ms * (dd - d.x * d.x), dot(t1, R.r1) + ms * (dd - d.y * d.y), dot(t2, R.r2) + ms * (dd - d.z * d.z),
                   dot(t0, R.r1) - ms * d.x * d.y, dot(t0, R.r2) - ms * d.x * d.z, dot(t1, R.r2) - ms * d.y * d.z, ms * d, ms};
     });
-    S6 cdof[NV];
+    S6 (&cdof)[NV] = ps.cdof;
     sfor<0, NJ>([&](auto jj) {
         constexpr int j = IDX(jj), b = T::jnt_body(j), da = T::jnt_dofadr(j), ty = T::jnt_type(j);
         V3 off = com[T::body_root(b)] - anchor[j];
@@ -419,6 +434,241 @@ DEV void build_problem(const DevModel<T>& m, const double (&q)[T::NQ], const dou
         }
     });
     stage_sync();
+    sfor<0, NV>([&](auto ii) {
+        constexpr int i = IDX(ii), j = T::dof_jnt(i);
+        if constexpr (T::jnt_type(j) != ILQG_JNT_FREE && T::jnt_hasspring(j)) ps.dspr[i] = q[T::jnt_qposadr(j)] - m.qpos_spring[T::jnt_qposadr(j)];
+        else ps.dspr[i] = 0;
+    });
+    // ---- mj_crb + factor
+    Inert crb[NB];
+    sfor<1, NB>([&](auto bb) { crb[IDX(bb)] = cin[IDX(bb)]; });
+    sfor_down<NB - 1, 1>([&](auto bb) {
+        constexpr int b = IDX(bb), p = T::body_parent(b);
+        if constexpr (p > 0) crb[p] = crb[p] + crb[b];
+    });
+    sfor<0, NV>([&](auto ii) {
+        constexpr int i = IDX(ii);
+        S6 buf = mul(crb[T::dof_body(i)], cdof[i]);
+        sfor<0, i + 1>([&](auto jj) {
+            constexpr int j = IDX(jj);
+            if constexpr (dof_is_ancestor<T>(j, i)) w.M[tri(i, j)] = dot(cdof[j], buf);
+            else w.M[tri(i, j)] = 0;
+        });
+        w.M[tri(i, i)] += m.dof_armature[i];
+    });
+    chol_packed<NV>(w.M, w.L);
+
+    stage_sync();
+    // ---- constraint rows: joint limits, then contacts
+    int ne = 0;
+    sfor<0, NJ>([&](auto jj) {
+        constexpr int j = IDX(jj);
+        if constexpr (T::jnt_limited(j) && T::jnt_type(j) != ILQG_JNT_FREE) {
+            constexpr int da = T::jnt_dofadr(j);
+            double value = q[T::jnt_qposadr(j)];
+            sfor<0, 2>([&](auto ss) {
+                constexpr int side = 2 * IDX(ss) - 1;
+                double dist = side * (m.jnt_range[j][IDX(ss)] - value);
+                if (dist < m.jnt_margin[j]) {
+                    double R, kt;
+                    const double B = m.jnt_B[j];
+                    row_params(m.jnt_K[j], m.jnt_imp[j], m.jnt_solimp[j], dist, m.jnt_margin[j], m.dof_invw[da], R, kt);
+                    sfor<0, NV>([&](auto ii) { w.J[ne][IDX(ii)] = IDX(ii) == da ? -side : 0.0; });
+                    w.D[ne] = 1.0 / R;
+                    w.rB[ne] = B;
+                    w.rkt[ne] = kt;
+                    ne++;
+                }
+            });
+        }
+    });
+    stage_sync();
+    if constexpr (T::NPAIR > 0) {
+        // geom frames
+        V3 gpos[T::NGEOM], gax[T::NGEOM];
+        sfor<0, T::NGEOM>([&](auto gg) {
+            constexpr int g = IDX(gg), b = T::geom_body(g);
+            if constexpr (b == 0) { gpos[g] = ld3(m.geom_pos[g]); gax[g] = ld3(m.geom_axis[g]); }
+            else { gpos[g] = xpos[b] + mulv(xmat[b], ld3(m.geom_pos[g])); gax[g] = mulv(xmat[b], ld3(m.geom_axis[g])); }
+        });
+        // Phase A (unrolled over the model's pair list): narrow phase only — every contact found is pushed as a small
+        // record.  Phase B (one runtime loop over the records) builds the rows.  The row construction is by far the
+        // largest piece of code of the pipeline; keeping ONE copy of it instead of one per pair shrinks the kernel's
+        // instruction footprint by a third and lets lanes whose contacts come from different pairs share the same code.
+        constexpr int MC = nz(T::MAXCON);
+        double cdist[MC];
+        V3 cpos[MC], cnrm[MC], chint[MC];
+        int cpair[MC];   // pair index, bit 8 set when the tangent hint is valid
+        int nc = 0;
+        auto push = [&](int p, double dist, V3 pos, V3 n, V3 hint, bool has_hint) {
+            if (nc < MC) { cdist[nc] = dist; cpos[nc] = pos; cnrm[nc] = n; chint[nc] = hint; cpair[nc] = p | (has_hint ? 256 : 0); nc++; }
+        };
+        sfor<0, T::NPAIR>([&](auto pp) {
+            constexpr int p = IDX(pp), g1 = T::pair_g1(p), g2 = T::pair_g2(p), t1 = T::geom_type(g1), t2 = T::geom_type(g2);
+            const double margin = m.pair_margin[p];
+            auto sphere_sphere = [&](V3 p1, double r1, V3 p2, double r2) {
+                V3 n = p2 - p1;
+                double len = sqrt(dot(n, n));
+                double dist = len - r1 - r2;
+                if (dist > margin) return false;
+                if (len < ILQG_MINVAL) n = {1, 0, 0};
+                else n = (1.0 / len) * n;
+                push(p, dist, p1 + (r1 + 0.5 * dist) * n, n, V3{0, 0, 0}, false);
+                return true;
+            };
+            if constexpr (t1 == ILQG_GEOM_PLANE && (t2 == ILQG_GEOM_CAPSULE || t2 == ILQG_GEOM_SPHERE)) {
+                V3 pn = gax[g1];
+                double r = m.geom_size[g2][0];
+                auto plane_sphere = [&](V3 c, bool hint) {
+                    double dist = dot(c - gpos[g1], pn) - r;
+                    if (dist > margin) return;
+                    push(p, dist, c - (r + 0.5 * dist) * pn, pn, gax[g2], hint);
+                };
+                if constexpr (t2 == ILQG_GEOM_SPHERE) plane_sphere(gpos[g2], false);
+                else {
+                    double h = m.geom_size[g2][1];
+#pragma unroll 1
+                    for (int e = 0; e < 2; e++) plane_sphere(gpos[g2] + (e ? -h : h) * gax[g2], true);
+                }
+            } else if constexpr (t1 == ILQG_GEOM_SPHERE && t2 == ILQG_GEOM_SPHERE) {
+                sphere_sphere(gpos[g1], m.geom_size[g1][0], gpos[g2], m.geom_size[g2][0]);
+            } else if constexpr (t1 == ILQG_GEOM_SPHERE && t2 == ILQG_GEOM_CAPSULE) {
+                double h = m.geom_size[g2][1];
+                double t = clampd(dot(gpos[g1] - gpos[g2], gax[g2]), -h, h);
+                sphere_sphere(gpos[g1], m.geom_size[g1][0], gpos[g2] + t * gax[g2], m.geom_size[g2][0]);
+            } else if constexpr (t1 == ILQG_GEOM_CAPSULE && t2 == ILQG_GEOM_CAPSULE) {
+                V3 p1 = gpos[g1], a1 = gax[g1], p2 = gpos[g2], a2 = gax[g2];
+                double r1 = m.geom_size[g1][0], h1 = m.geom_size[g1][1], r2 = m.geom_size[g2][0], h2 = m.geom_size[g2][1];
+                // candidate closest-point pairs on the two axis segments (at most two survive the distance test)
+                V3 ca[2], cb[2];
+                int ncand = 0;
+                auto consider = [&](V3 c1, V3 c2) {
+                    V3 d = c2 - c1;
+                    if (sqrt(dot(d, d)) - r1 - r2 > margin) return false;
+                    if (ncand == 0) { ca[0] = c1; cb[0] = c2; } else { ca[1] = c1; cb[1] = c2; }
+                    ncand++;
+                    return true;
+                };
+                V3 dif = p1 - p2;
+                double mb = -dot(a1, a2), uu = -dot(a1, dif), vv = dot(a2, dif);
+                double det = 1.0 - mb * mb;
+                if (fabs(det) >= 1e-12) {
+                    double x1 = (uu - mb * vv) / det, x2 = (vv - mb * uu) / det;
+                    if (x1 > h1) { x1 = h1; x2 = vv - mb * h1; }
+                    else if (x1 < -h1) { x1 = -h1; x2 = vv + mb * h1; }
+                    if (x2 > h2) { x2 = h2; x1 = clampd(uu - mb * h2, -h1, h1); }
+                    else if (x2 < -h2) { x2 = -h2; x1 = clampd(uu + mb * h2, -h1, h1); }
+                    consider(p1 + x1 * a1, p2 + x2 * a2);
+                } else {  // parallel axes: end points against the other segment, at most two contacts
+                    for (int s = -1; s <= 1 && ncand < 2; s += 2) {
+                        V3 c1 = p1 + (s * h1) * a1;
+                        double t = dot(c1 - p2, a2);
+                        if (t < -h2 || t > h2) continue;
+                        consider(c1, p2 + t * a2);
+                    }
+                    for (int s = -1; s <= 1 && ncand < 2; s += 2) {
+                        V3 c2 = p2 + (s * h2) * a2;
+                        double t = dot(c2 - p1, a1);
+                        if (t <= -h1 || t >= h1) continue;
+                        consider(p1 + t * a1, c2);
+                    }
+                    if (ncand == 0) {
+                        double best = 1e300;
+                        V3 bq1 = p1, bq2 = p2;
+                        for (int s = -1; s <= 1; s += 2)
+                            for (int t = -1; t <= 1; t += 2) {
+                                V3 c1 = p1 + (s * h1) * a1, c2 = p2 + (t * h2) * a2;
+                                double dd = dot(c1 - c2, c1 - c2);
+                                if (dd < best) { best = dd; bq1 = c1; bq2 = c2; }
+                            }
+                        consider(bq1, bq2);
+                    }
+                }
+#pragma unroll 1
+                for (int c = 0; c < ncand; c++) sphere_sphere(c ? ca[1] : ca[0], r1, c ? cb[1] : cb[0], r2);
+            }
+        });
+        stage_sync();
+        // Phase B: rows of every contact found
+#pragma unroll 1
+        for (int c = 0; c < nc; c++) {
+            const int p = cpair[c] & 255;
+            const bool has_hint = (cpair[c] & 256) != 0;
+            const double dist = cdist[c];
+            const V3 pos = cpos[c], n = cnrm[c];
+            // the pair's constants, selected from compile-time-indexed tables
+            unsigned mk1 = 0, mk2 = 0;   // dofs that move body 1 / body 2
+            int condim = 1;
+            double margin = 0, mu = 0, tran = 0, K = 0, B = 0, imp = 0;
+            V3 r1 = {0, 0, 0}, r2 = {0, 0, 0};  // contact point relative to the com of body 1's / body 2's tree
+            sfor<0, T::NPAIR>([&](auto pp) {
+                constexpr int P = IDX(pp), b1 = T::geom_body(T::pair_g1(P)), b2 = T::geom_body(T::pair_g2(P));
+                if (p == P) {
+                    unsigned a = 0, b = 0;
+                    sfor<0, NV>([&](auto ii) {
+                        if constexpr (b1 > 0 && dof_moves_body<T>(IDX(ii), b1)) a |= 1u << IDX(ii);
+                        if constexpr (b2 > 0 && dof_moves_body<T>(IDX(ii), b2)) b |= 1u << IDX(ii);
+                    });
+                    mk1 = a; mk2 = b;
+                    condim = T::pair_condim(P);
+                    margin = m.pair_margin[P]; mu = m.pair_mu[P]; K = m.pair_K[P]; B = m.pair_B[P]; imp = m.pair_imp[P];
+                    tran = m.body_invw[b1] + m.body_invw[b2];
+                    if constexpr (b1 > 0) r1 = pos - com[T::body_root(b1)];
+                    if constexpr (b2 > 0) r2 = pos - com[T::body_root(b2)];
+                }
+            });
+            V3 ta, tb;
+            make_frame(n, chint[c], has_hint, ta, tb);
+            double jn[NV], ja[NV], jb[NV];
+            sfor<0, NV>([&](auto ii) {
+                constexpr int i = IDX(ii);
+                const bool m1 = (mk1 >> i) & 1u, m2 = (mk2 >> i) & 1u;
+                jn[i] = 0; ja[i] = 0; jb[i] = 0;
+                if (m1 != m2) {  // a dof that moves both bodies or neither gives no relative motion
+                    V3 jp = cdof[i].v + cross(cdof[i].w, m2 ? r2 : r1);
+                    if (!m2) jp = -1.0 * jp;
+                    jn[i] = dot(n, jp);
+                    if (condim == 3) { ja[i] = dot(ta, jp); jb[i] = dot(tb, jp); }
+                }
+            });
+            if (tran < ILQG_MINVAL) tran = ILQG_MINVAL;
+            if (condim == 1) {
+                double R, kt;
+                row_params(K, imp, m.pair_solimp[p], dist, margin, tran, R, kt);
+                sfor<0, NV>([&](auto ii) { w.J[ne][IDX(ii)] = jn[IDX(ii)]; });
+                w.D[ne] = 1.0 / R;
+                w.rB[ne] = B;
+                w.rkt[ne] = kt;
+                ne++;
+            } else {
+                double R0, kt;
+                // all four facets share pos/margin; R of the first facet sets the pyramid's regulariser
+                row_params(K, imp, m.pair_solimp[p], dist, margin, tran * (1 + mu * mu), R0, kt);
+                double Rpy = 2 * mu * mu * R0;
+                if (Rpy < ILQG_MINVAL) Rpy = ILQG_MINVAL;
+                double Dpy = 1.0 / Rpy;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const double sg = (k % 2) ? -mu : mu;
+                    sfor<0, NV>([&](auto ii) { w.J[ne][IDX(ii)] = jn[IDX(ii)] + sg * (k < 2 ? ja[IDX(ii)] : jb[IDX(ii)]); });
+                    w.D[ne] = Dpy;
+                    w.rB[ne] = B;
+                    w.rkt[ne] = kt;
+                    ne++;
+                }
+            }
+        }
+    }
+    w.nefc = ne;
+    stage_sync();
+}
+
+template <class T, bool SYNC = false>
+DEV void build_vel(const DevModel<T>& m, const PosStage<T>& ps, const double (&qv)[T::NV], Work<T>& w) {
+    auto stage_sync = [&]() { if constexpr (SYNC) __syncthreads(); };
+    constexpr int NB = T::NBODY, NV = T::NV;
+    const S6 (&cdof)[NV] = ps.cdof;
+    const Inert (&cin)[NB] = ps.cin;
     // ---- mj_comVel + mj_rne(flg_acc=0): bias forces
     S6 cvel[NB], cdofdot[NV], cacc[NB], cfrc[NB];
     cvel[0] = {{0, 0, 0}, {0, 0, 0}};
@@ -447,214 +697,45 @@ DEV void build_problem(const DevModel<T>& m, const double (&q)[T::NQ], const dou
         constexpr int b = IDX(bb), p = T::body_parent(b);
         if constexpr (p > 0) cfrc[p] = cfrc[p] + cfrc[b];
     });
-    // qfrc_smooth = passive - bias + actuator
+    // qfrc_passive - qfrc_bias
     sfor<0, NV>([&](auto ii) {
         constexpr int i = IDX(ii), j = T::dof_jnt(i);
         double f = -dot(cdof[i], cfrc[T::dof_body(i)]);
         if constexpr (T::ANY_DAMPING) f -= m.dof_damping[i] * qv[i];
-        if constexpr (T::jnt_type(j) != ILQG_JNT_FREE && T::jnt_hasspring(j))
-            f -= m.jnt_stiffness[j] * (q[T::jnt_qposadr(j)] - m.qpos_spring[T::jnt_qposadr(j)]);
-        w.fs[i] = f;
+        if constexpr (T::jnt_type(j) != ILQG_JNT_FREE && T::jnt_hasspring(j)) f -= m.jnt_stiffness[j] * ps.dspr[i];
+        w.fb[i] = f;
     });
+    // reference accelerations of the rows (mj_referenceConstraint): aref = -B (J qvel) - K imp (pos - margin)
+    for (int r = 0; r < w.nefc; r++) {
+        double s = 0;
+        sfor<0, NV>([&](auto ii) { s += w.J[r][IDX(ii)] * qv[IDX(ii)]; });
+        w.aref[r] = -w.rB[r] * s - w.rkt[r];
+    }
+    stage_sync();
+}
+
+template <class T>
+DEV void finish_smooth(const DevModel<T>& m, const double (&u)[nz(T::NU)], Work<T>& w) {
+    constexpr int NV = T::NV;
+    sfor<0, NV>([&](auto ii) { w.fs[IDX(ii)] = w.fb[IDX(ii)]; });
     sfor<0, T::NU>([&](auto uu) {
         constexpr int a = IDX(uu);
         double c = u[a];
         if constexpr (T::act_limited(a)) c = clampd(c, m.act_range[a][0], m.act_range[a][1]);
         w.fs[T::act_dof(a)] += m.act_gear[a] * c;
     });
-    stage_sync();
-    // ---- mj_crb + factor
-    Inert crb[NB];
-    sfor<1, NB>([&](auto bb) { crb[IDX(bb)] = cin[IDX(bb)]; });
-    sfor_down<NB - 1, 1>([&](auto bb) {
-        constexpr int b = IDX(bb), p = T::body_parent(b);
-        if constexpr (p > 0) crb[p] = crb[p] + crb[b];
-    });
-    sfor<0, NV>([&](auto ii) {
-        constexpr int i = IDX(ii);
-        S6 buf = mul(crb[T::dof_body(i)], cdof[i]);
-        sfor<0, i + 1>([&](auto jj) {
-            constexpr int j = IDX(jj);
-            if constexpr (dof_is_ancestor<T>(j, i)) w.M[tri(i, j)] = dot(cdof[j], buf);
-            else w.M[tri(i, j)] = 0;
-        });
-        w.M[tri(i, i)] += m.dof_armature[i];
-    });
-    chol_packed<NV>(w.M, w.L);
     sfor<0, NV>([&](auto ii) { w.as[IDX(ii)] = w.fs[IDX(ii)]; });
     chol_solve_packed<NV>(w.L, w.as);
+}
 
-    stage_sync();
-    // ---- constraint rows: joint limits, then contacts
-    int ne = 0;
-    sfor<0, NJ>([&](auto jj) {
-        constexpr int j = IDX(jj);
-        if constexpr (T::jnt_limited(j) && T::jnt_type(j) != ILQG_JNT_FREE) {
-            constexpr int da = T::jnt_dofadr(j);
-            double value = q[T::jnt_qposadr(j)];
-            sfor<0, 2>([&](auto ss) {
-                constexpr int side = 2 * IDX(ss) - 1;
-                double dist = side * (m.jnt_range[j][IDX(ss)] - value);
-                if (dist < m.jnt_margin[j]) {
-                    double R, kt;
-                    const double B = m.jnt_B[j];
-                    row_params(m.jnt_K[j], m.jnt_imp[j], m.jnt_solimp[j], dist, m.jnt_margin[j], m.dof_invw[da], R, kt);
-                    sfor<0, NV>([&](auto ii) { w.J[ne][IDX(ii)] = IDX(ii) == da ? -side : 0.0; });
-                    w.D[ne] = 1.0 / R;
-                    w.aref[ne] = -B * (-side * qv[da]) - kt;
-                    ne++;
-                }
-            });
-        }
-    });
-    stage_sync();
-    if constexpr (T::NPAIR > 0) {
-        // geom frames
-        V3 gpos[T::NGEOM], gax[T::NGEOM];
-        sfor<0, T::NGEOM>([&](auto gg) {
-            constexpr int g = IDX(gg), b = T::geom_body(g);
-            if constexpr (b == 0) { gpos[g] = ld3(m.geom_pos[g]); gax[g] = ld3(m.geom_axis[g]); }
-            else { gpos[g] = xpos[b] + mulv(xmat[b], ld3(m.geom_pos[g])); gax[g] = mulv(xmat[b], ld3(m.geom_axis[g])); }
-        });
-        sfor<0, T::NPAIR>([&](auto pp) {
-            constexpr int p = IDX(pp), g1 = T::pair_g1(p), g2 = T::pair_g2(p), t1 = T::geom_type(g1), t2 = T::geom_type(g2);
-            constexpr int b1 = T::geom_body(g1), b2 = T::geom_body(g2), condim = T::pair_condim(p);
-            const double margin = m.pair_margin[p];
-            // emit the rows of one contact
-            auto emit = [&](double dist, V3 pos, V3 n, V3 hint, bool has_hint) {
-                V3 ta, tb;
-                make_frame(n, hint, has_hint, ta, tb);
-                double jn[NV], ja[NV], jb[NV];
-                double vn = 0, va = 0, vb = 0;
-                sfor<0, NV>([&](auto ii) {
-                    constexpr int i = IDX(ii);
-                    constexpr bool m1 = b1 > 0 && dof_moves_body<T>(i, b1), m2 = b2 > 0 && dof_moves_body<T>(i, b2);
-                    if constexpr (m1 == m2) {  // moves both bodies or neither: relative motion is zero
-                        jn[i] = 0; ja[i] = 0; jb[i] = 0;
-                    } else {
-                        constexpr int bd = m2 ? b2 : b1;
-                        V3 jp = cdof[i].v + cross(cdof[i].w, pos - com[T::body_root(bd)]);
-                        if constexpr (!m2) jp = -1.0 * jp;
-                        jn[i] = dot(n, jp);
-                        if constexpr (condim == 3) { ja[i] = dot(ta, jp); jb[i] = dot(tb, jp); va += ja[i] * qv[i]; vb += jb[i] * qv[i]; }
-                        vn += jn[i] * qv[i];
-                    }
-                });
-                double tran = m.body_invw[b1] + m.body_invw[b2];
-                if (tran < ILQG_MINVAL) tran = ILQG_MINVAL;
-                if constexpr (condim == 1) {
-                    double R, kt;
-                    const double B = m.pair_B[p];
-                    row_params(m.pair_K[p], m.pair_imp[p], m.pair_solimp[p], dist, margin, tran, R, kt);
-                    sfor<0, NV>([&](auto ii) { w.J[ne][IDX(ii)] = jn[IDX(ii)]; });
-                    w.D[ne] = 1.0 / R;
-                    w.aref[ne] = -B * vn - kt;
-                    ne++;
-                } else {
-                    const double mu = m.pair_mu[p];
-                    double R0, kt;
-                    const double B = m.pair_B[p];
-                    // all four facets share pos/margin; R of the first facet sets the pyramid's regulariser
-                    row_params(m.pair_K[p], m.pair_imp[p], m.pair_solimp[p], dist, margin, tran * (1 + mu * mu), R0, kt);
-                    double Rpy = 2 * mu * mu * R0;
-                    if (Rpy < ILQG_MINVAL) Rpy = ILQG_MINVAL;
-                    double Dpy = 1.0 / Rpy;
-                    sfor<0, 4>([&](auto kk) {
-                        constexpr int k = IDX(kk);
-                        double sg = (k % 2) ? -mu : mu;
-                        double vel = vn + sg * (k < 2 ? va : vb);
-                        sfor<0, NV>([&](auto ii) { w.J[ne][IDX(ii)] = jn[IDX(ii)] + sg * (k < 2 ? ja[IDX(ii)] : jb[IDX(ii)]); });
-                        w.D[ne] = Dpy;
-                        w.aref[ne] = -B * vel - kt;
-                        ne++;
-                    });
-                }
-            };
-            auto sphere_sphere = [&](V3 p1, double r1, V3 p2, double r2) {
-                V3 n = p2 - p1;
-                double len = sqrt(dot(n, n));
-                double dist = len - r1 - r2;
-                if (dist > margin) return false;
-                if (len < ILQG_MINVAL) n = {1, 0, 0};
-                else n = (1.0 / len) * n;
-                emit(dist, p1 + (r1 + 0.5 * dist) * n, n, V3{0, 0, 0}, false);
-                return true;
-            };
-            if constexpr (t1 == ILQG_GEOM_PLANE && (t2 == ILQG_GEOM_CAPSULE || t2 == ILQG_GEOM_SPHERE)) {
-                V3 pn = gax[g1];
-                double r = m.geom_size[g2][0];
-                auto plane_sphere = [&](V3 c, bool hint) {
-                    double dist = dot(c - gpos[g1], pn) - r;
-                    if (dist > margin) return;
-                    emit(dist, c - (r + 0.5 * dist) * pn, pn, gax[g2], hint);
-                };
-                if constexpr (t2 == ILQG_GEOM_SPHERE) plane_sphere(gpos[g2], false);
-                else {
-                    double h = m.geom_size[g2][1];
-#pragma unroll 1
-                    for (int e = 0; e < 2; e++) plane_sphere(gpos[g2] + (e ? -h : h) * gax[g2], true);
-                }
-            } else if constexpr (t1 == ILQG_GEOM_SPHERE && t2 == ILQG_GEOM_SPHERE) {
-                sphere_sphere(gpos[g1], m.geom_size[g1][0], gpos[g2], m.geom_size[g2][0]);
-            } else if constexpr (t1 == ILQG_GEOM_SPHERE && t2 == ILQG_GEOM_CAPSULE) {
-                double h = m.geom_size[g2][1];
-                double t = clampd(dot(gpos[g1] - gpos[g2], gax[g2]), -h, h);
-                sphere_sphere(gpos[g1], m.geom_size[g1][0], gpos[g2] + t * gax[g2], m.geom_size[g2][0]);
-            } else if constexpr (t1 == ILQG_GEOM_CAPSULE && t2 == ILQG_GEOM_CAPSULE) {
-                V3 p1 = gpos[g1], a1 = gax[g1], p2 = gpos[g2], a2 = gax[g2];
-                double r1 = m.geom_size[g1][0], h1 = m.geom_size[g1][1], r2 = m.geom_size[g2][0], h2 = m.geom_size[g2][1];
-                // candidate closest-point pairs on the two axis segments (at most two survive the distance test)
-                V3 ca[2], cb[2];
-                int nc = 0;
-                auto consider = [&](V3 c1, V3 c2) {
-                    V3 d = c2 - c1;
-                    if (sqrt(dot(d, d)) - r1 - r2 > margin) return false;
-                    if (nc == 0) { ca[0] = c1; cb[0] = c2; } else { ca[1] = c1; cb[1] = c2; }
-                    nc++;
-                    return true;
-                };
-                V3 dif = p1 - p2;
-                double mb = -dot(a1, a2), uu = -dot(a1, dif), vv = dot(a2, dif);
-                double det = 1.0 - mb * mb;
-                if (fabs(det) >= 1e-12) {
-                    double x1 = (uu - mb * vv) / det, x2 = (vv - mb * uu) / det;
-                    if (x1 > h1) { x1 = h1; x2 = vv - mb * h1; }
-                    else if (x1 < -h1) { x1 = -h1; x2 = vv + mb * h1; }
-                    if (x2 > h2) { x2 = h2; x1 = clampd(uu - mb * h2, -h1, h1); }
-                    else if (x2 < -h2) { x2 = -h2; x1 = clampd(uu + mb * h2, -h1, h1); }
-                    consider(p1 + x1 * a1, p2 + x2 * a2);
-                } else {  // parallel axes: end points against the other segment, at most two contacts
-                    for (int s = -1; s <= 1 && nc < 2; s += 2) {
-                        V3 c1 = p1 + (s * h1) * a1;
-                        double t = dot(c1 - p2, a2);
-                        if (t < -h2 || t > h2) continue;
-                        consider(c1, p2 + t * a2);
-                    }
-                    for (int s = -1; s <= 1 && nc < 2; s += 2) {
-                        V3 c2 = p2 + (s * h2) * a2;
-                        double t = dot(c2 - p1, a1);
-                        if (t <= -h1 || t >= h1) continue;
-                        consider(p1 + t * a1, c2);
-                    }
-                    if (nc == 0) {
-                        double best = 1e300;
-                        V3 bq1 = p1, bq2 = p2;
-                        for (int s = -1; s <= 1; s += 2)
-                            for (int t = -1; t <= 1; t += 2) {
-                                V3 c1 = p1 + (s * h1) * a1, c2 = p2 + (t * h2) * a2;
-                                double dd = dot(c1 - c2, c1 - c2);
-                                if (dd < best) { best = dd; bq1 = c1; bq2 = c2; }
-                            }
-                        consider(bq1, bq2);
-                    }
-                }
-#pragma unroll 1
-                for (int c = 0; c < nc; c++) sphere_sphere(c ? ca[1] : ca[0], r1, c ? cb[1] : cb[0], r2);
-            }
-        });
-    }
-    w.nefc = ne;
-    stage_sync();
+// the whole of mj_fwdPosition + mj_fwdVelocity + mj_fwdActuation + qacc_smooth for one rollout
+template <class T, bool SYNC = false>
+DEV void build_problem(const DevModel<T>& m, const double (&q)[T::NQ], const double (&qv)[T::NV], const double (&u)[nz(T::NU)],
+                       Work<T>& w) {
+    PosStage<T> ps;
+    build_pos<T, SYNC>(m, q, ps, w);
+    build_vel<T, SYNC>(m, ps, qv, w);
+    finish_smooth<T>(m, u, w);
 }
 
 // ------------------------------------------------------------------ constraint solve (mj_fwdConstraint)
@@ -697,23 +778,39 @@ DEV void solve(const DevModel<T>& m, Work<T>& w, double (&warm)[T::NV], double (
         sfor<0, NV>([&](auto ii) { qacc[IDX(ii)] = w.as[IDX(ii)]; warm[IDX(ii)] = w.as[IDX(ii)]; w.fc[IDX(ii)] = 0; });
         return;
     }
-    {
-        double cw = problem_cost<T>(w, warm), cs = problem_cost<T>(w, w.as);
-        if (cw < cs) sfor<0, NV>([&](auto ii) { qacc[IDX(ii)] = warm[IDX(ii)]; });
-        else sfor<0, NV>([&](auto ii) { qacc[IDX(ii)] = w.as[IDX(ii)]; });
-    }
     const double scale = 1.0 / (m.meaninertia * (NV > 1 ? NV : 1));
     double Ma[NV], grad[NV], search[NV], Mv[NV];
-    sfor<0, NV>([&](auto ii) {
-        constexpr int i = IDX(ii);
-        double s = 0;
-        sfor<0, NV>([&](auto kk) { s += w.M[tri(i, IDX(kk))] * qacc[IDX(kk)]; });
-        Ma[i] = s;
-    });
-    for (int r = 0; r < ne; r++) {
-        double s = -w.aref[r];
-        sfor<0, NV>([&](auto ii) { s += w.J[r][IDX(ii)] * qacc[IDX(ii)]; });
-        w.jar[r] = s;
+    {
+        // start from the better of the warm start and qacc_smooth; one pass over the rows evaluates both candidates
+        // (J lives in local memory: every pass over it is a round of L1/L2 traffic) and leaves jar of the chosen one
+        double cw = 0, cs = 0;
+        for (int r = 0; r < ne; r++) {
+            double jw = -w.aref[r], js = jw;
+            sfor<0, NV>([&](auto ii) { const double Jri = w.J[r][IDX(ii)]; jw += Jri * warm[IDX(ii)]; js += Jri * w.as[IDX(ii)]; });
+            const double D = w.D[r];
+            if (jw < 0) cw += 0.5 * D * jw * jw;
+            if (js < 0) cs += 0.5 * D * js * js;   // the Gauss term of cost(qacc_smooth) is zero
+            w.jar[r] = jw;
+            w.jv[r] = js;
+        }
+        sfor<0, NV>([&](auto ii) {
+            constexpr int i = IDX(ii);
+            double s = 0;
+            sfor<0, NV>([&](auto kk) { s += w.M[tri(i, IDX(kk))] * warm[IDX(kk)]; });
+            Ma[i] = s;
+            cw += 0.5 * (s - w.fs[i]) * (warm[i] - w.as[i]);
+        });
+        if (cw < cs) sfor<0, NV>([&](auto ii) { qacc[IDX(ii)] = warm[IDX(ii)]; });
+        else {
+            sfor<0, NV>([&](auto ii) { qacc[IDX(ii)] = w.as[IDX(ii)]; });
+            sfor<0, NV>([&](auto ii) {
+                constexpr int i = IDX(ii);
+                double s = 0;
+                sfor<0, NV>([&](auto kk) { s += w.M[tri(i, IDX(kk))] * qacc[IDX(kk)]; });
+                Ma[i] = s;
+            });
+            for (int r = 0; r < ne; r++) w.jar[r] = w.jv[r];
+        }
     }
     double cost = 0, old = 0;
     int iter = 0;

@@ -166,6 +166,161 @@ __global__ void __launch_bounds__(WARPS * 32, MINBLOCKS) fd_perturb_kernel(const
     }
 }
 
+// ------------------------------------------------------------------ FD with stage skipping: two kernels after the centre
+// The reference re-runs only the stages a perturbation can change: mj_forwardSkip(mjSTAGE_VEL) for ctrl columns,
+// mj_forwardSkip(mjSTAGE_POS) for qvel columns, everything for qpos columns (mjderivative.cpp:92,124,178).  In SIMT the
+// lanes of a warp must walk the same stages, so the columns are regrouped by kind:
+//   fd_velctrl_kernel : GK = gcd(nv, nu) threads per knot; each runs the position stage ONCE on the unperturbed qpos and
+//                       then loops over its nu/GK ctrl columns (actuation + solve only) and nv/GK qvel columns
+//                       (velocity stage + solve), +eps then -eps, all lanes of the CTA in the same iteration kind.
+//   fd_qpos_kernel    : one thread per perturbed evaluation of a qpos column (full pipeline), +/- lanes adjacent.
+// Per knot that is (GK + 2nv) position stages instead of 2(2nv+nu).  A CTA owns a whole number of knots
+// (floor(256 / lanes-per-knot)); their deriv segments are staged in shared memory and written as contiguous runs
+// (the dv|du blocks are adjacent in the reference layout: 54 doubles per hopper knot; dq: 36).
+template <class T>
+struct FdSplit {
+    static constexpr int NV = T::NV, NU = T::NU, NCOL = 2 * NV + NU;
+    static constexpr int gcd_(int a, int b) { return b == 0 ? a : gcd_(b, a % b); }
+    static constexpr int GK = NU > 0 ? gcd_(NV, NU) : 1;
+    static constexpr int CU = NU / GK, CV = NV / GK;      // ctrl / qvel columns per thread
+    static constexpr int THREADS = 256;
+    static constexpr int KPC_VU = THREADS / GK;           // knots per CTA
+    static constexpr int KPC_Q = THREADS / (2 * NV);
+    static constexpr int NJAC = NV * NCOL, ND = NJAC + NCOL;
+    static constexpr int SEG_VU = NV * NV + NV * NU, STG_VU = SEG_VU + NV + NU;   // dv | du | dg/dqvel | dg/dctrl
+    static constexpr int SEG_Q = NV * NV, STG_Q = SEG_Q + NV;                     // dq | dg/dqpos
+    static_assert(2 * NV <= THREADS, "thread-per-rollout FD kernels need 2 nv <= 256");
+};
+
+template <class T, bool SYNC>
+__global__ void __launch_bounds__(256, 1) fd_velctrl_kernel(const __grid_constant__ DevModel<T> m, int nknots, const double* __restrict__ qpos,
+                                                            const double* __restrict__ qvel, const double* __restrict__ ctrl,
+                                                            const double* __restrict__ qacc_center, const ilqg_cost* __restrict__ cost,
+                                                            double eps, int niter, double* __restrict__ deriv, int* __restrict__ status) {
+    using S = FdSplit<T>;
+    constexpr int NV = T::NV, NU = T::NU, NQ = T::NQ, GK = S::GK;
+    __shared__ double stage[S::KPC_VU * S::STG_VU];
+    const int kl = threadIdx.x / GK, g = threadIdx.x - kl * GK;
+    const int k0 = blockIdx.x * S::KPC_VU, k = k0 + kl;
+    const bool valid = kl < S::KPC_VU && k < nknots;
+    const int kk = k < nknots ? k : nknots - 1;   // idle lanes evaluate a clamped knot with their writes masked (stage barriers)
+    double q[NQ], v[NV], u[nz(NU)], center[NV];
+    load_knot<T>(kk, qpos, qvel, ctrl, q, v, u);
+    sfor<0, NV>([&](auto ii) { center[IDX(ii)] = qacc_center[(size_t)kk * NV + IDX(ii)]; });
+    double c0 = 0;
+    if (cost) c0 = cost_eval<T>(*cost, q, v, u);
+    PosStage<T> ps;
+    Work<T> w;
+    build_pos<T, SYNC>(m, q, ps, w);
+    double* st = stage + (kl < S::KPC_VU ? kl : 0) * S::STG_VU;
+    const double inv2eps = 1.0 / (2 * eps);
+    double qplus[NV], dcost = 0;
+    bool finite = true;
+#pragma unroll 1
+    for (int it = 0; it < 2 * (S::CU + S::CV); it++) {
+        const int c = it >> 1;
+        const bool is_vel = c >= S::CU;                       // uniform over the grid
+        const int col = (is_vel ? c - S::CU : c) * GK + g;    // column within its kind
+        const double se = (it & 1) ? -eps : eps;
+        double vp[NV], up[nz(NU)], warm[NV], qacc[NV];
+        sfor<0, NV>([&](auto ii) { vp[IDX(ii)] = v[IDX(ii)] + ((is_vel && col == IDX(ii)) ? se : 0.0); warm[IDX(ii)] = center[IDX(ii)]; });
+        sfor<0, NU>([&](auto ii) { up[IDX(ii)] = u[IDX(ii)] + ((!is_vel && col == IDX(ii)) ? se : 0.0); });
+        if (cost && !(it & 1)) dcost = __ddiv_rn(__dsub_rn(cost_eval<T>(*cost, q, vp, up), c0), eps);
+        if (it == 0 || is_vel) build_vel<T, false>(m, ps, vp, w);   // ctrl columns keep the centre's velocity stage (mjSTAGE_VEL skip)
+        finish_smooth<T>(m, up, w);
+        solve<T>(m, w, warm, qacc, niter, 0.0);
+        if (!(it & 1)) {
+            sfor<0, NV>([&](auto jj) { qplus[IDX(jj)] = qacc[IDX(jj)]; });
+        } else {
+            sfor<0, NV>([&](auto jj) {
+                constexpr int j = IDX(jj);
+                double d = (qplus[j] - qacc[j]) * inv2eps;
+                finite = finite && isfinite(d);
+                if (valid) st[is_vel ? col + j * NV : NV * NV + col + j * NU] = d;
+            });
+            if (valid) st[S::SEG_VU + (is_vel ? col : NV + col)] = dcost;
+        }
+    }
+    if (valid && !finite && status) atomicExch(&status[k], ILQG_ERR_NONFINITE);
+    __syncthreads();
+    int nk = nknots - k0;
+    if (nk > S::KPC_VU) nk = S::KPC_VU;
+    for (int e = threadIdx.x; e < nk * S::SEG_VU; e += blockDim.x) {
+        const int kn = e / S::SEG_VU, off = e - kn * S::SEG_VU;
+        deriv[(size_t)(k0 + kn) * S::ND + NV * NV + off] = stage[kn * S::STG_VU + off];
+    }
+    if (cost)   // without a device cost the gradient entries stay untouched
+        for (int e = threadIdx.x; e < nk * (NV + NU); e += blockDim.x) {
+            const int kn = e / (NV + NU), off = e - kn * (NV + NU);
+            deriv[(size_t)(k0 + kn) * S::ND + S::NJAC + NV + off] = stage[kn * S::STG_VU + S::SEG_VU + off];
+        }
+}
+
+template <class T, bool SYNC>
+__global__ void __launch_bounds__(256, 1) fd_qpos_kernel(const __grid_constant__ DevModel<T> m, int nknots, const double* __restrict__ qpos,
+                                                         const double* __restrict__ qvel, const double* __restrict__ ctrl,
+                                                         const double* __restrict__ qacc_center, const ilqg_cost* __restrict__ cost,
+                                                         double eps, int niter, double* __restrict__ deriv, int* __restrict__ status) {
+    using S = FdSplit<T>;
+    constexpr int NV = T::NV, NU = T::NU, NQ = T::NQ, G = 2 * NV;
+    __shared__ double stage[S::KPC_Q * S::STG_Q];
+    const int kl = threadIdx.x / G, l = threadIdx.x - kl * G;
+    const int k0 = blockIdx.x * S::KPC_Q, k = k0 + kl;
+    const bool valid = kl < S::KPC_Q && k < nknots;
+    const int kk = k < nknots ? k : nknots - 1;
+    const int col = l >> 1;
+    const double se = (l & 1) ? -eps : eps;
+    double qacc[NV], dcost = 0;
+    {
+        double q[NQ], v[NV], u[nz(NU)], warm[NV];
+        load_knot<T>(kk, qpos, qvel, ctrl, q, v, u);
+        sfor<0, NV>([&](auto ii) { warm[IDX(ii)] = qacc_center[(size_t)kk * NV + IDX(ii)]; });
+        double c0 = 0;
+        if (cost) c0 = cost_eval<T>(*cost, q, v, u);
+        // tangent-space perturbation of qpos (mjderivative.cpp:152-169,187-192)
+        sfor<0, NV>([&](auto ii) {
+            constexpr int i = IDX(ii), j = T::dof_jnt(i);
+            if (col == i) {
+                if constexpr (T::jnt_type(j) == ILQG_JNT_FREE && i >= T::jnt_dofadr(j) + 3) {
+                    constexpr int a = i - T::jnt_dofadr(j) - 3;
+                    quat_integrate(&q[T::jnt_qposadr(j) + 3], V3{a == 0 ? se : 0.0, a == 1 ? se : 0.0, a == 2 ? se : 0.0}, 1.0);
+                } else
+                    q[T::jnt_qposadr(j) + i - T::jnt_dofadr(j)] += se;
+            }
+        });
+        if (cost && !(l & 1)) dcost = __ddiv_rn(__dsub_rn(cost_eval<T>(*cost, q, v, u), c0), eps);
+        Work<T> w;
+        build_problem<T, SYNC>(m, q, v, u, w);
+        solve<T>(m, w, warm, qacc, niter, 0.0);
+    }
+    bool finite = true;
+    const double inv2eps = 1.0 / (2 * eps);
+    double* st = stage + (kl < S::KPC_Q ? kl : 0) * S::STG_Q;
+    sfor<0, NV>([&](auto jj) {
+        constexpr int j = IDX(jj);
+        double other = __shfl_xor_sync(0xffffffffu, qacc[j], 1);   // G is even: the +/- pair never straddles a warp
+        double d = (qacc[j] - other) * inv2eps;
+        finite = finite && isfinite(d);
+        if (valid && !(l & 1)) st[col + j * NV] = d;
+    });
+    if (valid && !(l & 1)) {
+        st[S::SEG_Q + col] = dcost;
+        if (!finite && status) atomicExch(&status[k], ILQG_ERR_NONFINITE);
+    }
+    __syncthreads();
+    int nk = nknots - k0;
+    if (nk > S::KPC_Q) nk = S::KPC_Q;
+    for (int e = threadIdx.x; e < nk * S::SEG_Q; e += blockDim.x) {
+        const int kn = e / S::SEG_Q, off = e - kn * S::SEG_Q;
+        deriv[(size_t)(k0 + kn) * S::ND + off] = stage[kn * S::STG_Q + off];
+    }
+    if (cost)
+        for (int e = threadIdx.x; e < nk * NV; e += blockDim.x) {
+            const int kn = e / NV, off = e - kn * NV;
+            deriv[(size_t)(k0 + kn) * S::ND + S::NJAC + off] = stage[kn * S::STG_Q + S::SEG_Q + off];
+        }
+}
+
 // ------------------------------------------------------------------ forward / step batches
 template <class T>
 __global__ void __launch_bounds__(128) forward_kernel(const __grid_constant__ DevModel<T> m, int n, const double* __restrict__ qpos,
@@ -232,8 +387,9 @@ struct IlqrLaunch<T, true> {
 
 // ------------------------------------------------------------------ engines (one per compiled-in topology)
 struct Engine {
-    int fd_variant = 2;
+    int fd_variant = 3;
     virtual ~Engine() {}
+    virtual int fd_launches() const { return 2; }
     virtual const char* name() const = 0;
     virtual cudaError_t fd(int nknots, const double* qpos, const double* qvel, const double* ctrl, const double* warm,
                            const ilqg_cost* cost_dev, const ilqg_fd_opts& o, double* deriv, double* qacc_center, int* status,
@@ -253,6 +409,7 @@ template <class T>
 struct EngineT : Engine {
     DevModel<T> dm;
     const char* name() const override { return T::NAME; }
+    int fd_launches() const override { return fd_variant >= 3 ? 3 : 2; }
     cudaError_t fd(int nknots, const double* qpos, const double* qvel, const double* ctrl, const double* warm, const ilqg_cost* cost_dev,
                    const ilqg_fd_opts& o, double* deriv, double* qacc_center, int* status, cudaStream_t s, cudaEvent_t* ev) override {
         using S = FdShape<T>;
@@ -261,6 +418,17 @@ struct EngineT : Engine {
         if (ev) cudaEventRecord(ev[0], s);
         fd_center_kernel<T><<<(nknots + 127) / 128, 128, 0, s>>>(dm, nknots, qpos, qvel, ctrl, warm, o.niter, o.nwarmup, qacc_center, status);
         if (ev) cudaEventRecord(ev[1], s);
+        if (fd_variant >= 3) {  // stage-skipping split: qvel/ctrl columns, then qpos columns
+            using P = FdSplit<T>;
+            fd_velctrl_kernel<T, true><<<(nknots + P::KPC_VU - 1) / P::KPC_VU, P::THREADS, 0, s>>>(dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev,
+                                                                                                 o.eps, o.niter, deriv, status);
+            if (ev) cudaEventRecord(ev[3], s);
+            fd_qpos_kernel<T, true><<<(nknots + P::KPC_Q - 1) / P::KPC_Q, P::THREADS, 0, s>>>(dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps,
+                                                                                            o.niter, deriv, status);
+            if (ev) cudaEventRecord(ev[2], s);
+            return cudaGetLastError();
+        }
+        if (ev) cudaEventRecord(ev[3], s);
         int nwarps = (nknots + S::KPW - 1) / S::KPW;
         dim3 grid((nwarps + WARPS - 1) / WARPS), block(WARPS * 32);
         switch (fd_variant) {  // experiment switch (ILQG_FD_VARIANT): 0 = 4 warps x 2 CTAs/SM, no stage barriers; 1 = with barriers; 2 = 8 warps x 1 CTA with barriers
@@ -329,7 +497,7 @@ struct CoopEngine : Engine {
         if (ev) cudaEventRecord(ev[0], s);
         coop_center_kernel<<<(nknots + warps - 1) / warps, warps * 32, smem, s>>>(d_g, nknots, qpos, qvel, ctrl, warm, o.niter, o.nwarmup, warp_bytes,
                                                                                 qacc_center, status);
-        if (ev) cudaEventRecord(ev[1], s);
+        if (ev) { cudaEventRecord(ev[1], s); cudaEventRecord(ev[3], s); }
         long items = (long)nknots * ncol;
         coop_perturb_kernel<<<(unsigned)((items + warps - 1) / warps), warps * 32, smem, s>>>(d_g, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps,
                                                                                           o.niter, warp_bytes, deriv, status);
@@ -404,7 +572,7 @@ struct ilqg_handle_s {
     long launches = 0;  // kernels launched through this handle (bench.py reports it)
     bool profiling = false;
     cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};  // chunk pipeline of the *_host FD entry point
-    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};  // around the two FD kernels when profiling is on
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // before centre, after centre, after the last FD kernel, between the two column kernels
 };
 
 static thread_local std::string g_create_err;
@@ -469,7 +637,7 @@ int ilqg_destroy(ilqg_handle h) {
     cudaFree(h->d_center);
     cudaFree(h->d_cost);
     cudaFree(h->d_stage);
-    for (int i = 0; i < 3; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i < 3; i++) if (h->pipe[i]) cudaStreamDestroy(h->pipe[i]);
     delete h->eng;
     delete h;
@@ -482,7 +650,7 @@ int ilqg_set_profiling(ilqg_handle h, int on) {
     if (!h) return ILQG_ERR_ARG;
     CU(h, cudaSetDevice(h->device));
     if (on && !h->ev[0])
-        for (int i = 0; i < 3; i++) CU(h, cudaEventCreate(&h->ev[i]));
+        for (int i = 0; i < 4; i++) CU(h, cudaEventCreate(&h->ev[i]));
     h->profiling = on != 0;
     return ILQG_OK;
 }
@@ -492,6 +660,14 @@ int ilqg_fd_last_kernel_ms(ilqg_handle h, float* center_ms, float* perturb_ms) {
     CU(h, cudaEventSynchronize(h->ev[2]));
     CU(h, cudaEventElapsedTime(center_ms, h->ev[0], h->ev[1]));
     CU(h, cudaEventElapsedTime(perturb_ms, h->ev[1], h->ev[2]));
+    return ILQG_OK;
+}
+int ilqg_fd_last_stage_ms(ilqg_handle h, float* center_ms, float* velctrl_ms, float* qpos_ms) {
+    if (!h || !h->ev[0] || !center_ms || !velctrl_ms || !qpos_ms) return ILQG_ERR_ARG;
+    CU(h, cudaEventSynchronize(h->ev[2]));
+    CU(h, cudaEventElapsedTime(center_ms, h->ev[0], h->ev[1]));
+    CU(h, cudaEventElapsedTime(velctrl_ms, h->ev[1], h->ev[3]));
+    CU(h, cudaEventElapsedTime(qpos_ms, h->ev[3], h->ev[2]));
     return ILQG_OK;
 }
 const char* ilqg_engine_name(ilqg_handle h) { return h && h->eng ? h->eng->name() : ""; }
@@ -559,7 +735,7 @@ static int fd_launch(ilqg_handle h, int nknots, const double* qpos, const double
         center = h->d_center;
     }
     CU(h, h->eng->fd(nknots, qpos, qvel, ctrl, warmstart, dcost, o, deriv, center, status, s, h->profiling ? h->ev : nullptr));
-    h->launches += 2;
+    h->launches += h->eng->fd_launches();
     return ILQG_OK;
 }
 
@@ -842,7 +1018,7 @@ int ilqg_ilqr_linearise(ilqg_ilqr w, void* stream) {                     // FD a
     int rc = ensure_center(h, (size_t)nknots * h->model.nv);
     if (rc) return rc;
     CU(h, h->eng->fd(nknots, b.nom_q, b.nom_v, b.nom_u, b.nom_w, w->host_cost ? nullptr : w->d_cost, w->fd, b.deriv, h->d_center, nullptr, s, nullptr));
-    h->launches += 2;
+    h->launches += h->eng->fd_launches();
     return ILQG_OK;
 }
 int ilqg_ilqr_backward(ilqg_ilqr w, void* stream) {                      // initV + backwardPass

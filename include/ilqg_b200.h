@@ -152,6 +152,8 @@ const char* ilqg_engine_name(ilqg_handle h);  /* name of the kernel instantiatio
 int ilqg_fp64_peak(int device, double* tflops); /* measured fp64 FMA throughput (roofline denominator) */
 int ilqg_set_profiling(ilqg_handle h, int on);  /* record CUDA events around each FD kernel on the launch stream */
 int ilqg_fd_last_kernel_ms(ilqg_handle h, float* center_ms, float* perturb_ms); /* durations of the last FD call's kernels */
+/* the same, with the perturbed evaluations split by kernel: qvel/ctrl columns (stage-skipping) and qpos columns */
+int ilqg_fd_last_stage_ms(ilqg_handle h, float* center_ms, float* velctrl_ms, float* qpos_ms);
 
 #ifdef __cplusplus
 }

@@ -1,12 +1,24 @@
 // coop.cuh — warp-cooperative fp64 forward dynamics and FD linearisation for models that do not fit the
 // thread-per-rollout register budget (humanoid: nv = 27, 150 perturbed evaluations per knot, 161 collision pairs).
 //
-// One WARP per perturbed rollout (north star (3): "one warp or CTA per perturbed rollout"): the rollout's whole
-// mjData-equivalent — frames, spatial inertias, motion axes, the dense mass matrix and its Cholesky factor, the contact
-// list, the constraint Jacobian, the Newton Hessian — lives in that warp's slice of SHARED memory; lanes stride over
-// independent items (bodies of one tree level, dofs, geoms, collision pairs, constraint rows, matrix entries) and meet at
-// __syncwarp().  The model is read from a GModel block in global memory (uniform or lane-strided reads, L1/L2 resident).
-// Unlike dyn.cuh nothing is specialised on the kinematic tree: this path serves any model of the supported subset.
+// One WARP per rollout (north star (3): "one warp or CTA per perturbed rollout"): the rollout's mjData-equivalent lives in
+// that warp's slice of SHARED memory; lanes stride over independent items (bodies of one tree level, dofs, geoms, collision
+// pairs, constraint rows, matrix entries) and meet at __syncwarp().  Triangular solves keep the vector in registers
+// (lane i = dof i) and broadcast with shuffles.  The model is read from a GModel block in global memory (uniform or
+// lane-strided reads, L1/L2 resident).  Nothing is specialised on the kinematic tree: any model of the subset runs here.
+//
+// The state is split the way MuJoCo splits its pipeline (and the reference its skip levels, mjderivative.cpp:92,124,178):
+//   C-state  products of the POSITION stage (motion axes, spatial inertias, M, its factor, constraint rows J/D/B/k-term) plus
+//            the knot's inputs and the centre's velocity-stage products — 27 KB for the humanoid
+//   private  velocity stage + constraint solve working set (bias recursion, qfrc/qacc vectors, aref/jar/jv, Newton Hessian)
+//            — 11 KB; the position stage's temporaries (frames, geoms, contact records) alias it
+// FD of a knot = three launches:
+//   coop_center_kernel   warp per knot: full pipeline + warm-up solves; leaves the C-state in HBM and the list of collision
+//                        pairs within (margin + slack) of contact — the only pairs a +-eps perturbation can activate
+//   coop_velctrl_kernel  CTA per knot: loads the centre's C-state once; its warps share it read-only and take the qvel / ctrl
+//                        columns in turn, each re-running only the velocity stage (or only the actuation) and the solve.
+//                        8 warps x 11 KB private + 27 KB shared: 16 resident warps per SM instead of 4.
+//   coop_qpos_kernel     warp per (knot, qpos column): full pipeline at +eps and -eps, narrow phase on the candidate list only.
 //
 // Replaces, for such models, the same reference calls as dyn.cuh: mj_forward / mj_forwardSkip inside
 // /root/reference/src/mjderivative.cpp:64-198 (incl. the quaternion tangent perturbation :152-169,187-192).
@@ -21,6 +33,7 @@ namespace ilqg {
 #define COOP_MAXCON 24
 #define COOP_MAXEFC 72
 #define COOP_MAXLEVEL 16
+#define COOP_MAXCAND 63   // candidate pairs recorded per knot (more: the perturbed evaluations test every pair)
 
 // flat model + host-precomputed helpers, uploaded once per handle
 struct GModel {
@@ -65,46 +78,71 @@ inline bool gmodel_from_tables(const ilqg_model& s, GModel& g) {
     return true;
 }
 
-// ------------------------------------------------------------------ per-warp shared-memory slice
+// ------------------------------------------------------------------ shared-memory views
 struct CoopMem {
-    double *q, *v, *u, *warm;
-    double *xpos, *xquat, *xmat, *xipos, *anchor, *axis, *gpos, *gax, *com;
-    double *cinert, *crb, *cdof, *cdofdot, *cvel, *cacc, *cfrc;
-    double *M, *H;                       // nv x nv row-major (H doubles as Cholesky workspace)
-    double *fs, *as, *fc, *qacc, *Ma, *grad, *search, *Mv;
-    double *cdist, *cpos, *cframe;       // contacts
+    // ---- C-state (contiguous; copied to / from HBM as one block)
+    double *q, *v, *u, *center;            // knot inputs, centre qacc (warm start of the perturbed solves)
+    double *cdof, *cinert, *com, *dspr;    // motion axes, spatial inertias about the tree com, tree com, q - qpos_spring
+    double *M, *L;                         // packed lower triangles; L's diagonal holds 1 / L_ii
+    double *J, *D, *rB, *rkt;              // constraint rows: Jacobian, 1/R, damping B, K*imp*(pos - margin)
+    double *fb0, *aref0;                   // the centre's velocity-stage products (ctrl columns reuse them)
+    int* hdr;                              // hdr[0] = nefc, hdr[1] = capacity ok
+    // ---- private working set
+    double *pv, *pu;                       // perturbed qvel / ctrl
+    double *cvel, *cacc, *cfrc, *cdofdot;
+    double *fb, *fs, *as, *fc, *qacc, *warm, *Ma, *grad, *search, *Mv;
+    double *aref, *jar, *jv, *H;
+    int* alist;                            // active rows of the current Newton iteration
+    // ---- position-stage temporaries (alias the private block)
+    double *xpos, *xquat, *xmat, *xipos, *anchor, *axis, *gpos, *gax, *crb, *cdist, *cpos, *cframe;
     int* cpair;
-    double *J, *D, *aref, *jar, *jv;     // constraint rows
-    int ncon, nefc;
 };
 
-__host__ __device__ inline size_t coop_doubles(int nq, int nv, int nu, int nb, int nj, int ng) {
-    size_t n = nq + 2 * (size_t)nv + nu;                                   // q v u warm
-    n += (size_t)nb * (3 + 4 + 9 + 3) + (size_t)nj * 6 + (size_t)ng * 6 + (size_t)nb * 3;  // frames, anchors, geoms, com
-    n += (size_t)nb * 20 + (size_t)nv * 12 + (size_t)nb * 18;               // cinert crb, cdof cdofdot, cvel cacc cfrc
-    n += 2 * (size_t)nv * nv + 8 * (size_t)nv;                              // M H + 8 vectors
-    n += (size_t)COOP_MAXCON * 13;                                           // contacts
-    n += (size_t)COOP_MAXEFC * nv + 4 * (size_t)COOP_MAXEFC;                 // J D aref jar jv
-    return n;
+__host__ __device__ inline int coop_nt(int nv) { return nv * (nv + 1) / 2; }
+__host__ __device__ inline size_t coop_cstate_doubles(const ilqg_model& m) {
+    const size_t nv = m.nv, nb = m.nbody;
+    size_t n = m.nq + nv + m.nu + nv;                       // q v u center
+    n += 6 * nv + 10 * nb + 3 * nb + nv;                    // cdof cinert com dspr
+    n += 2 * (size_t)coop_nt(m.nv);                         // M L
+    n += (size_t)COOP_MAXEFC * nv + 3 * COOP_MAXEFC;        // J D rB rkt
+    n += nv + COOP_MAXEFC;                                  // fb0 aref0
+    n += 1;                                                 // hdr (2 ints)
+    return (n + 1) & ~(size_t)1;
 }
-__host__ __device__ inline size_t coop_bytes_per_warp(const ilqg_model& m) {
-    size_t d = coop_doubles(m.nq, m.nv, m.nu, m.nbody, m.njnt, m.ngeom);
-    return d * sizeof(double) + ((COOP_MAXCON * sizeof(int) + 15) / 16) * 16;
+__host__ __device__ inline size_t coop_priv_doubles(const ilqg_model& m) {
+    const size_t nv = m.nv, nb = m.nbody, nj = m.njnt, ng = m.ngeom;
+    size_t priv = nv + m.nu + 18 * nb + 6 * nv + 10 * nv + 3 * COOP_MAXEFC + coop_nt(m.nv) + (COOP_MAXEFC + 1) / 2;
+    size_t tmp = 19 * nb + 6 * nj + 6 * ng + 10 * nb + (size_t)COOP_MAXCON * 13 + (COOP_MAXCON + 1) / 2;
+    size_t n = priv > tmp ? priv : tmp;
+    return (n + 1) & ~(size_t)1;
 }
 
-DEV void coop_carve(CoopMem& w, double* base, const ilqg_model& m) {
-    const int nq = m.nq, nv = m.nv, nu = m.nu, nb = m.nbody, nj = m.njnt, ng = m.ngeom;
+DEV void coop_carve_cstate(CoopMem& w, double* base, const ilqg_model& m) {
+    const int nq = m.nq, nv = m.nv, nu = m.nu, nb = m.nbody, nt = coop_nt(m.nv);
     double* p = base;
     auto take = [&](size_t n) { double* r = p; p += n; return r; };
-    w.q = take(nq); w.v = take(nv); w.u = take(nu); w.warm = take(nv);
-    w.xpos = take(nb * 3); w.xquat = take(nb * 4); w.xmat = take(nb * 9); w.xipos = take(nb * 3);
-    w.anchor = take(nj * 3); w.axis = take(nj * 3); w.gpos = take(ng * 3); w.gax = take(ng * 3); w.com = take(nb * 3);
-    w.cinert = take(nb * 10); w.crb = take(nb * 10); w.cdof = take(nv * 6); w.cdofdot = take(nv * 6);
-    w.cvel = take(nb * 6); w.cacc = take(nb * 6); w.cfrc = take(nb * 6);
-    w.M = take((size_t)nv * nv); w.H = take((size_t)nv * nv);
-    w.fs = take(nv); w.as = take(nv); w.fc = take(nv); w.qacc = take(nv); w.Ma = take(nv); w.grad = take(nv); w.search = take(nv); w.Mv = take(nv);
+    w.q = take(nq); w.v = take(nv); w.u = take(nu); w.center = take(nv);
+    w.cdof = take(6 * nv); w.cinert = take(10 * nb); w.com = take(3 * nb); w.dspr = take(nv);
+    w.M = take(nt); w.L = take(nt);
+    w.J = take((size_t)COOP_MAXEFC * nv); w.D = take(COOP_MAXEFC); w.rB = take(COOP_MAXEFC); w.rkt = take(COOP_MAXEFC);
+    w.fb0 = take(nv); w.aref0 = take(COOP_MAXEFC);
+    w.hdr = reinterpret_cast<int*>(p);
+}
+DEV void coop_carve_priv(CoopMem& w, double* base, const ilqg_model& m) {
+    const int nv = m.nv, nu = m.nu, nb = m.nbody, nj = m.njnt, ng = m.ngeom, nt = coop_nt(m.nv);
+    double* p = base;
+    auto take = [&](size_t n) { double* r = p; p += n; return r; };
+    w.pv = take(nv); w.pu = take(nu);
+    w.cvel = take(6 * nb); w.cacc = take(6 * nb); w.cfrc = take(6 * nb); w.cdofdot = take(6 * nv);
+    w.fb = take(nv); w.fs = take(nv); w.as = take(nv); w.fc = take(nv); w.qacc = take(nv); w.warm = take(nv);
+    w.Ma = take(nv); w.grad = take(nv); w.search = take(nv); w.Mv = take(nv);
+    w.aref = take(COOP_MAXEFC); w.jar = take(COOP_MAXEFC); w.jv = take(COOP_MAXEFC); w.H = take(nt);
+    w.alist = reinterpret_cast<int*>(p);
+    // temporaries of the position stage share the same bytes
+    p = base;
+    w.xpos = take(3 * nb); w.xquat = take(4 * nb); w.xmat = take(9 * nb); w.xipos = take(3 * nb);
+    w.anchor = take(3 * nj); w.axis = take(3 * nj); w.gpos = take(3 * ng); w.gax = take(3 * ng); w.crb = take(10 * nb);
     w.cdist = take(COOP_MAXCON); w.cpos = take(COOP_MAXCON * 3); w.cframe = take(COOP_MAXCON * 9);
-    w.J = take((size_t)COOP_MAXEFC * nv); w.D = take(COOP_MAXEFC); w.aref = take(COOP_MAXEFC); w.jar = take(COOP_MAXEFC); w.jv = take(COOP_MAXEFC);
     w.cpair = reinterpret_cast<int*>(p);
 }
 
@@ -113,42 +151,51 @@ DEV double warp_sum(double x) {
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
     return x;
 }
+__host__ __device__ constexpr int ptri(int i, int j) { return i * (i + 1) / 2 + j; }   // j <= i
 
-// in-place dense Cholesky of the n x n row-major matrix A (lower triangle), cooperative over the warp
+// in-place Cholesky of the packed lower triangle A (n <= 32), left-looking: at column j lane l owns row j + l.
+// The diagonal is left holding 1 / L_jj.
 DEV void coop_chol(double* A, int n, int lane) {
     for (int j = 0; j < n; j++) {
-        __syncwarp();
-        double d = A[j * n + j];
-        if (d < ILQG_MINVAL) d = ILQG_MINVAL;
-        double rinv = rsqrt(d);
-        __syncwarp();
-        for (int i = j + lane; i < n; i += 32) A[i * n + j] = (i == j) ? d * rinv : A[i * n + j] * rinv;
-        __syncwarp();
-        // trailing update: rows i > j, columns j < k <= i
-        for (int i = j + 1 + lane; i < n; i += 32) {
-            double lij = A[i * n + j];
-            for (int k = j + 1; k <= i; k++) A[i * n + k] -= lij * A[k * n + j];
+        const int i = j + lane;
+        double s = 0;
+        if (i < n) {
+            s = A[ptri(i, j)];
+            const double* ri = A + ptri(i, 0);
+            const double* rj = A + ptri(j, 0);
+            for (int k = 0; k < j; k++) s -= ri[k] * rj[k];
         }
+        double d = __shfl_sync(0xffffffffu, s, 0);
+        if (d < ILQG_MINVAL) d = ILQG_MINVAL;
+        const double rinv = rsqrt(d);
+        if (i < n) A[ptri(i, j)] = (i == j) ? rinv : s * rinv;
+        __syncwarp();
     }
-    __syncwarp();
 }
-// x <- (L L^T)^-1 x, column-oriented so that no reductions are needed
-DEV void coop_chol_solve(const double* L, double* x, int n, int lane) {
+// x <- (L L^T)^-1 x with x in registers: lane i holds x_i (n <= 32); returns this lane's component
+DEV double coop_chol_solve(const double* L, double x, int n, int lane) {
     for (int j = 0; j < n; j++) {
-        __syncwarp();
-        double xj = x[j] / L[j * n + j];
-        __syncwarp();
-        if (lane == 0) x[j] = xj;
-        for (int i = j + 1 + lane; i < n; i += 32) x[i] -= L[i * n + j] * xj;
+        const double xj = __shfl_sync(0xffffffffu, x, j) * L[ptri(j, j)];
+        if (lane == j) x = xj;
+        else if (lane > j && lane < n) x -= L[ptri(lane, j)] * xj;
     }
     for (int j = n - 1; j >= 0; j--) {
-        __syncwarp();
-        double xj = x[j] / L[j * n + j];
-        __syncwarp();
-        if (lane == 0) x[j] = xj;
-        for (int i = lane; i < j; i += 32) x[i] -= L[j * n + i] * xj;
+        const double xj = __shfl_sync(0xffffffffu, x, j) * L[ptri(j, j)];
+        if (lane == j) x = xj;
+        else if (lane < j) x -= L[ptri(j, lane)] * xj;
     }
-    __syncwarp();
+    return x;
+}
+// y_i = sum_k M_ik x_k for the packed symmetric M; lane i < n returns y_i
+DEV double coop_symv(const double* M, const double* x, int n, int lane) {
+    double s = 0;
+    if (lane < n) {
+        const double* row = M + ptri(lane, 0);
+        for (int k = 0; k <= lane; k++) s += row[k] * x[k];
+        int idx = ptri(lane + 1, lane);
+        for (int k = lane + 1; k < n; k++) { s += M[idx] * x[k]; idx += k + 1; }
+    }
+    return s;
 }
 
 DEV void g_inert_vec(double* r, const double* i, const double* s) {  // same 10-number spatial inertia as dyn.cuh's Inert
@@ -162,11 +209,14 @@ DEV void g_inert_vec(double* r, const double* i, const double* s) {  // same 10-
 DEV V3 gl3(const double* p) { return {p[0], p[1], p[2]}; }
 DEV void gs3(double* p, V3 a) { p[0] = a.x; p[1] = a.y; p[2] = a.z; }
 
-// ------------------------------------------------------------------ the pipeline up to the constraint problem
-// Inputs w.q, w.v, w.u (already perturbed).  Returns false when the contact / row capacity is exceeded.
-DEV bool coop_build(const GModel* __restrict__ g, CoopMem& w, int lane) {
+// ------------------------------------------------------------------ position stage
+// In: w.q.  Out: the C-state's position products and hdr.  The narrow phase runs over `cand` (ncand pair indices) when
+// ncand >= 0, else over every pair; with cand_out != NULL (centre evaluation) it also records, in pair order, the pairs
+// within margin + slack of contact: cand_out[0] = count (or -1 when more than COOP_MAXCAND), cand_out[1..] = pair indices.
+DEV void coop_pos(const GModel* __restrict__ g, CoopMem& w, int lane, const int* __restrict__ cand, int ncand, int* __restrict__ cand_out,
+                  double slack) {
     const ilqg_model& m = g->m;
-    const int nv = m.nv, nb = m.nbody, nj = m.njnt, ng = m.ngeom;
+    const int nv = m.nv, nb = m.nbody, nj = m.njnt, ng = m.ngeom, nt = coop_nt(m.nv);
     // ---- kinematics, level by level (a level's bodies are independent)
     if (lane == 0) {
         w.xpos[0] = w.xpos[1] = w.xpos[2] = 0;
@@ -258,90 +308,43 @@ DEV bool coop_build(const GModel* __restrict__ g, CoopMem& w, int lane) {
                 gs3(w.cdof + 6 * (da + 3 + i), ax);
                 gs3(w.cdof + 6 * (da + 3 + i) + 3, cross(ax, off));
             }
-        } else if (ty == ILQG_JNT_SLIDE) {
-            gs3(w.cdof + 6 * da, {0, 0, 0});
-            gs3(w.cdof + 6 * da + 3, gl3(w.axis + 3 * j));
+            for (int i = 0; i < 6; i++) w.dspr[da + i] = 0;
         } else {
-            V3 ax = gl3(w.axis + 3 * j);
-            gs3(w.cdof + 6 * da, ax);
-            gs3(w.cdof + 6 * da + 3, cross(ax, off));
-        }
-    }
-    if (lane < 6) { w.cvel[lane] = 0; w.cacc[lane] = lane < 3 ? 0.0 : -m.gravity[lane - 3]; w.cfrc[lane] = 0; }
-    __syncwarp();
-    // ---- com velocities, cdof_dot, RNE forward sweep (level by level)
-    for (int L = 0; L < g->nlevel; L++) {
-        for (int idx = g->level_start[L] + lane; idx < g->level_start[L + 1]; idx += 32) {
-            const int b = g->level_body[idx], p = m.body_parentid[b];
-            S6 cv = {gl3(w.cvel + 6 * p), gl3(w.cvel + 6 * p + 3)}, ca = {gl3(w.cacc + 6 * p), gl3(w.cacc + 6 * p + 3)};
-            for (int jj = 0; jj < m.body_jntnum[b]; jj++) {
-                const int j = m.body_jntadr[b] + jj, da = m.jnt_dofadr[j];
-                auto cd = [&](int i) { return S6{gl3(w.cdof + 6 * i), gl3(w.cdof + 6 * i + 3)}; };
-                auto putdot = [&](int i, S6 s) { gs3(w.cdofdot + 6 * i, s.w); gs3(w.cdofdot + 6 * i + 3, s.v); };
-                if (m.jnt_type[j] == ILQG_JNT_FREE) {
-                    for (int i = 0; i < 3; i++) { putdot(da + i, {{0, 0, 0}, {0, 0, 0}}); cv = cv + w.v[da + i] * cd(da + i); }
-                    for (int i = 3; i < 6; i++) putdot(da + i, cross_motion(cv, cd(da + i)));
-                    for (int i = 3; i < 6; i++) cv = cv + w.v[da + i] * cd(da + i);
-                } else {
-                    putdot(da, cross_motion(cv, cd(da)));
-                    cv = cv + w.v[da] * cd(da);
-                }
+            if (ty == ILQG_JNT_SLIDE) {
+                gs3(w.cdof + 6 * da, {0, 0, 0});
+                gs3(w.cdof + 6 * da + 3, gl3(w.axis + 3 * j));
+            } else {
+                V3 ax = gl3(w.axis + 3 * j);
+                gs3(w.cdof + 6 * da, ax);
+                gs3(w.cdof + 6 * da + 3, cross(ax, off));
             }
-            for (int i = m.body_dofadr[b]; i < m.body_dofadr[b] + m.body_dofnum[b]; i++)
-                ca = ca + w.v[i] * S6{gl3(w.cdofdot + 6 * i), gl3(w.cdofdot + 6 * i + 3)};
-            gs3(w.cvel + 6 * b, cv.w); gs3(w.cvel + 6 * b + 3, cv.v);
-            gs3(w.cacc + 6 * b, ca.w); gs3(w.cacc + 6 * b + 3, ca.v);
-            double cvv[6] = {cv.w.x, cv.w.y, cv.w.z, cv.v.x, cv.v.y, cv.v.z}, caa[6] = {ca.w.x, ca.w.y, ca.w.z, ca.v.x, ca.v.y, ca.v.z};
-            double ia[6], iv[6];
-            g_inert_vec(ia, w.cinert + 10 * b, caa);
-            g_inert_vec(iv, w.cinert + 10 * b, cvv);
-            S6 cf = cross_force(cv, {{iv[0], iv[1], iv[2]}, {iv[3], iv[4], iv[5]}});
-            w.cfrc[6 * b] = ia[0] + cf.w.x; w.cfrc[6 * b + 1] = ia[1] + cf.w.y; w.cfrc[6 * b + 2] = ia[2] + cf.w.z;
-            w.cfrc[6 * b + 3] = ia[3] + cf.v.x; w.cfrc[6 * b + 4] = ia[4] + cf.v.y; w.cfrc[6 * b + 5] = ia[5] + cf.v.z;
+            w.dspr[da] = m.jnt_stiffness[j] != 0 ? w.q[m.jnt_qposadr[j]] - m.qpos_spring[m.jnt_qposadr[j]] : 0.0;
         }
-        __syncwarp();
     }
-    // ---- backward accumulations: one lane per component, serial over bodies (children have larger ids than parents)
+    // ---- composite inertias: one lane per component, serial over bodies (children have larger ids than parents)
     for (int k = lane; k < 10; k += 32) w.crb[k] = 0;
     for (int e = 10 + lane; e < 10 * nb; e += 32) w.crb[e] = w.cinert[e];
+    for (int e = lane; e < nt; e += 32) w.M[e] = 0;
     __syncwarp();
-    if (lane < 6) {
-        for (int b = nb - 1; b > 0; b--) { int p = m.body_parentid[b]; if (p > 0) w.cfrc[6 * p + lane] += w.cfrc[6 * b + lane]; }
-    } else if (lane < 16) {
-        const int k = lane - 6;
-        for (int b = nb - 1; b > 0; b--) { int p = m.body_parentid[b]; if (p > 0) w.crb[10 * p + k] += w.crb[10 * b + k]; }
-    }
-    for (int e = lane; e < nv * nv; e += 32) w.M[e] = 0;
+    if (lane < 10)
+        for (int b = nb - 1; b > 0; b--) { int p = m.body_parentid[b]; if (p > 0) w.crb[10 * p + lane] += w.crb[10 * b + lane]; }
     __syncwarp();
-    // ---- qfrc_smooth = passive - bias + actuator ; mass matrix
+    // ---- mass matrix (packed lower) and its factor
     for (int i = lane; i < nv; i += 32) {
-        const int b = m.dof_bodyid[i], j = m.dof_jntid[i];
-        double f = 0;
-        for (int k = 0; k < 6; k++) f -= w.cdof[6 * i + k] * w.cfrc[6 * b + k];
-        f -= m.dof_damping[i] * w.v[i];
-        if (m.jnt_type[j] != ILQG_JNT_FREE && m.jnt_stiffness[j] != 0) f -= m.jnt_stiffness[j] * (w.q[m.jnt_qposadr[j]] - m.qpos_spring[m.jnt_qposadr[j]]);
-        for (int a = 0; a < m.nu; a++)
-            if (m.act_dofid[a] == i) {
-                double c = w.u[a];
-                if (m.act_ctrllimited[a]) c = clampd(c, m.act_ctrlrange[a][0], m.act_ctrlrange[a][1]);
-                f += m.act_gear[a] * c;
-            }
-        w.fs[i] = f;
-        w.as[i] = f;
+        const int b = m.dof_bodyid[i];
         double buf[6];
         g_inert_vec(buf, w.crb + 10 * b, w.cdof + 6 * i);
         for (int a = i; a >= 0; a = m.dof_parentid[a]) {
             double s = 0;
             for (int k = 0; k < 6; k++) s += w.cdof[6 * a + k] * buf[k];
             if (a == i) s += m.dof_armature[i];
-            w.M[i * nv + a] = s;
-            w.M[a * nv + i] = s;
+            w.M[ptri(i, a)] = s;
         }
     }
     __syncwarp();
-    for (int e = lane; e < nv * nv; e += 32) w.H[e] = w.M[e];
-    coop_chol(w.H, nv, lane);
-    coop_chol_solve(w.H, w.as, nv, lane);
+    for (int e = lane; e < nt; e += 32) w.L[e] = w.M[e];
+    __syncwarp();
+    coop_chol(w.L, nv, lane);
     // ---- constraint rows: joint limits
     int ne = 0;
     for (int j0 = 0; j0 < nj; j0 += 32) {
@@ -363,24 +366,29 @@ DEV bool coop_build(const GModel* __restrict__ g, CoopMem& w, int lane) {
             for (int i = 0; i < nv; i++) w.J[r * nv + i] = 0;
             w.J[r * nv + da] = -side;
             w.D[r] = 1.0 / R;
-            w.aref[r] = -g->jnt_B[j] * (-side * w.v[da]) - kt;
+            w.rB[r] = g->jnt_B[j];
+            w.rkt[r] = kt;
         }
         ne += __popc(bal);
     }
     // ---- collision: lanes over candidate pairs, contacts appended through warp prefix sums
-    int ncon = 0;
-    for (int p0 = 0; p0 < m.npair; p0 += 32) {
-        const int p = p0 + lane;
-        int cnt = 0;
+    int ncon = 0, nrec = 0;
+    const int npairs = ncand >= 0 ? ncand : m.npair;
+    for (int p0 = 0; p0 < npairs; p0 += 32) {
+        const int pi = p0 + lane;
+        int cnt = 0, p = -1;
+        bool near = false;
         double cd[2], cp[2][3], cn[2][3], ch[3] = {0, 0, 0};
         bool hint = false;
-        if (p < m.npair) {
+        if (pi < npairs) {
+            p = ncand >= 0 ? cand[pi] : pi;
             const int g1 = m.pair_geom1[p], g2 = m.pair_geom2[p], t1 = m.geom_type[g1], t2 = m.geom_type[g2];
-            const double margin = m.pair_margin[p];
+            const double margin = m.pair_margin[p], wide = margin + slack;
             V3 x1 = gl3(w.gpos + 3 * g1), x2 = gl3(w.gpos + 3 * g2), a1 = gl3(w.gax + 3 * g1), a2 = gl3(w.gax + 3 * g2);
             auto sphere_sphere = [&](V3 c1, double r1, V3 c2, double r2) {
                 V3 n = c2 - c1;
                 double len = sqrt(dot(n, n)), dist = len - r1 - r2;
+                near = near || dist <= wide;
                 if (dist > margin || cnt >= 2) return;
                 n = len < ILQG_MINVAL ? V3{1, 0, 0} : (1.0 / len) * n;
                 V3 pos = c1 + (r1 + 0.5 * dist) * n;
@@ -388,6 +396,7 @@ DEV bool coop_build(const GModel* __restrict__ g, CoopMem& w, int lane) {
             };
             auto plane_sphere = [&](V3 c, double r) {
                 double dist = dot(c - x1, a1) - r;
+                near = near || dist <= wide;
                 if (dist > margin) return;
                 V3 pos = c - (r + 0.5 * dist) * a1;
                 cd[cnt] = dist; gs3(cp[cnt], pos); gs3(cn[cnt], a1); cnt++;
@@ -414,7 +423,9 @@ DEV bool coop_build(const GModel* __restrict__ g, CoopMem& w, int lane) {
                     if (s2 > h2) { s2 = h2; s1 = clampd(uu - mb * h2, -h1, h1); }
                     else if (s2 < -h2) { s2 = -h2; s1 = clampd(uu + mb * h2, -h1, h1); }
                     sphere_sphere(x1 + s1 * a1, r1, x2 + s2 * a2, r2);
+                    if (fabs(det) < 1e-9) near = true;   // close to the parallel-axes branch: keep the pair for the perturbed evaluations
                 } else {
+                    near = true;
                     for (int s = -1; s <= 1 && cnt < 2; s += 2) {
                         V3 c1 = x1 + (s * h1) * a1;
                         double t = dot(c1 - x2, a2);
@@ -441,6 +452,12 @@ DEV bool coop_build(const GModel* __restrict__ g, CoopMem& w, int lane) {
                 }
             }
         }
+        if (cand_out) {   // record the near pairs in pair order
+            unsigned nb_ = __ballot_sync(0xffffffffu, near);
+            int slot = nrec + __popc(nb_ & ((1u << lane) - 1u));
+            if (near && slot < COOP_MAXCAND) cand_out[1 + slot] = p;
+            nrec += __popc(nb_);
+        }
         // exclusive prefix of contact counts over the warp (pair order = oracle's contact order)
         int incl = cnt;
 #pragma unroll
@@ -459,6 +476,7 @@ DEV bool coop_build(const GModel* __restrict__ g, CoopMem& w, int lane) {
         }
         ncon += __shfl_sync(0xffffffffu, incl, 31);
     }
+    if (cand_out && lane == 0) cand_out[0] = nrec <= COOP_MAXCAND ? nrec : -1;
     __syncwarp();
     bool ok = ncon <= COOP_MAXCON;
     if (!ok) ncon = COOP_MAXCON;
@@ -479,8 +497,6 @@ DEV bool coop_build(const GModel* __restrict__ g, CoopMem& w, int lane) {
                 jn = dot(n, jp); ja = dot(ta, jp); jb = dot(tb, jp);
             }
         }
-        const double qv = lane < nv ? w.v[lane] : 0.0;
-        const double vn = warp_sum(jn * qv), va = warp_sum(ja * qv), vb = warp_sum(jb * qv);
         double tran = m.body_invweight0[b1][0] + m.body_invweight0[b2][0];
         if (tran < ILQG_MINVAL) tran = ILQG_MINVAL;
         const double margin = m.pair_margin[p], dist = w.cdist[c], B = g->pair_B[p];
@@ -488,7 +504,7 @@ DEV bool coop_build(const GModel* __restrict__ g, CoopMem& w, int lane) {
             double R, kt;
             row_params(g->pair_K[p], g->pair_imp[p], m.pair_solimp[p], dist, margin, tran, R, kt);
             if (lane < nv) w.J[ne * nv + lane] = jn;
-            if (lane == 0) { w.D[ne] = 1.0 / R; w.aref[ne] = -B * vn - kt; }
+            if (lane == 0) { w.D[ne] = 1.0 / R; w.rB[ne] = B; w.rkt[ne] = kt; }
             ne += 1;
         } else {
             const double mu = m.pair_friction[p];
@@ -499,128 +515,207 @@ DEV bool coop_build(const GModel* __restrict__ g, CoopMem& w, int lane) {
             for (int k = 0; k < 4; k++) {
                 const double sg = (k & 1) ? -mu : mu;
                 if (lane < nv) w.J[(ne + k) * nv + lane] = jn + sg * (k < 2 ? ja : jb);
-                if (lane == 0) { w.D[ne + k] = 1.0 / Rpy; w.aref[ne + k] = -B * (vn + sg * (k < 2 ? va : vb)) - kt; }
+                if (lane == 0) { w.D[ne + k] = 1.0 / Rpy; w.rB[ne + k] = B; w.rkt[ne + k] = kt; }
             }
             ne += 4;
         }
     }
+    if (lane == 0) { w.hdr[0] = ne; w.hdr[1] = ok ? 1 : 0; }
     __syncwarp();
-    w.ncon = ncon;
-    w.nefc = ne;
-    return ok;
+}
+
+// ------------------------------------------------------------------ velocity stage
+// In: the C-state's position products and the velocity vector vv (shared memory, nv doubles).
+// Out (private): fb = qfrc_passive - qfrc_bias, aref of every row.
+DEV void coop_vel(const GModel* __restrict__ g, CoopMem& w, const double* vv, int lane) {
+    const ilqg_model& m = g->m;
+    const int nv = m.nv, nb = m.nbody, ne = w.hdr[0];
+    if (lane < 6) { w.cvel[lane] = 0; w.cacc[lane] = lane < 3 ? 0.0 : -m.gravity[lane - 3]; w.cfrc[lane] = 0; }
+    __syncwarp();
+    // ---- com velocities, cdof_dot, RNE forward sweep (level by level)
+    for (int L = 0; L < g->nlevel; L++) {
+        for (int idx = g->level_start[L] + lane; idx < g->level_start[L + 1]; idx += 32) {
+            const int b = g->level_body[idx], p = m.body_parentid[b];
+            S6 cv = {gl3(w.cvel + 6 * p), gl3(w.cvel + 6 * p + 3)}, ca = {gl3(w.cacc + 6 * p), gl3(w.cacc + 6 * p + 3)};
+            for (int jj = 0; jj < m.body_jntnum[b]; jj++) {
+                const int j = m.body_jntadr[b] + jj, da = m.jnt_dofadr[j];
+                auto cd = [&](int i) { return S6{gl3(w.cdof + 6 * i), gl3(w.cdof + 6 * i + 3)}; };
+                auto putdot = [&](int i, S6 s) { gs3(w.cdofdot + 6 * i, s.w); gs3(w.cdofdot + 6 * i + 3, s.v); };
+                if (m.jnt_type[j] == ILQG_JNT_FREE) {
+                    for (int i = 0; i < 3; i++) { putdot(da + i, {{0, 0, 0}, {0, 0, 0}}); cv = cv + vv[da + i] * cd(da + i); }
+                    for (int i = 3; i < 6; i++) putdot(da + i, cross_motion(cv, cd(da + i)));
+                    for (int i = 3; i < 6; i++) cv = cv + vv[da + i] * cd(da + i);
+                } else {
+                    putdot(da, cross_motion(cv, cd(da)));
+                    cv = cv + vv[da] * cd(da);
+                }
+            }
+            for (int i = m.body_dofadr[b]; i < m.body_dofadr[b] + m.body_dofnum[b]; i++)
+                ca = ca + vv[i] * S6{gl3(w.cdofdot + 6 * i), gl3(w.cdofdot + 6 * i + 3)};
+            gs3(w.cvel + 6 * b, cv.w); gs3(w.cvel + 6 * b + 3, cv.v);
+            gs3(w.cacc + 6 * b, ca.w); gs3(w.cacc + 6 * b + 3, ca.v);
+            double cvv[6] = {cv.w.x, cv.w.y, cv.w.z, cv.v.x, cv.v.y, cv.v.z}, caa[6] = {ca.w.x, ca.w.y, ca.w.z, ca.v.x, ca.v.y, ca.v.z};
+            double ia[6], iv[6];
+            g_inert_vec(ia, w.cinert + 10 * b, caa);
+            g_inert_vec(iv, w.cinert + 10 * b, cvv);
+            S6 cf = cross_force(cv, {{iv[0], iv[1], iv[2]}, {iv[3], iv[4], iv[5]}});
+            w.cfrc[6 * b] = ia[0] + cf.w.x; w.cfrc[6 * b + 1] = ia[1] + cf.w.y; w.cfrc[6 * b + 2] = ia[2] + cf.w.z;
+            w.cfrc[6 * b + 3] = ia[3] + cf.v.x; w.cfrc[6 * b + 4] = ia[4] + cf.v.y; w.cfrc[6 * b + 5] = ia[5] + cf.v.z;
+        }
+        __syncwarp();
+    }
+    if (lane < 6)
+        for (int b = nb - 1; b > 0; b--) { int p = m.body_parentid[b]; if (p > 0) w.cfrc[6 * p + lane] += w.cfrc[6 * b + lane]; }
+    __syncwarp();
+    for (int i = lane; i < nv; i += 32) {
+        const int b = m.dof_bodyid[i], j = m.dof_jntid[i];
+        double f = 0;
+        for (int k = 0; k < 6; k++) f -= w.cdof[6 * i + k] * w.cfrc[6 * b + k];
+        f -= m.dof_damping[i] * vv[i];
+        if (m.jnt_type[j] != ILQG_JNT_FREE && m.jnt_stiffness[j] != 0) f -= m.jnt_stiffness[j] * w.dspr[i];
+        w.fb[i] = f;
+    }
+    for (int r = lane; r < ne; r += 32) {
+        double s = 0;
+        const double* Jr = w.J + r * nv;
+        for (int i = 0; i < nv; i++) s += Jr[i] * vv[i];
+        w.aref[r] = -w.rB[r] * s - w.rkt[r];
+    }
+    __syncwarp();
+}
+
+// actuation, qfrc_smooth, qacc_smooth (in: private fb; uu: ctrl vector in shared memory)
+DEV void coop_smooth(const GModel* __restrict__ g, CoopMem& w, const double* uu, int lane) {
+    const ilqg_model& m = g->m;
+    const int nv = m.nv;
+    double f = 0;
+    if (lane < nv) {
+        f = w.fb[lane];
+        for (int a = 0; a < m.nu; a++)
+            if (m.act_dofid[a] == lane) {
+                double c = uu[a];
+                if (m.act_ctrllimited[a]) c = clampd(c, m.act_ctrlrange[a][0], m.act_ctrlrange[a][1]);
+                f += m.act_gear[a] * c;
+            }
+        w.fs[lane] = f;
+    }
+    const double a = coop_chol_solve(w.L, f, nv, lane);
+    if (lane < nv) w.as[lane] = a;
+    __syncwarp();
 }
 
 // ------------------------------------------------------------------ constraint solve (same algorithm as dyn.cuh::solve)
-DEV double coop_cost(const CoopMem& w, const double* a, int nv, int lane) {
-    double c = 0;
-    for (int r = lane; r < w.nefc; r += 32) {
-        double jar = -w.aref[r];
-        for (int i = 0; i < nv; i++) jar += w.J[r * nv + i] * a[i];
-        if (jar < 0) c += 0.5 * w.D[r] * jar * jar;
-    }
-    for (int i = lane; i < nv; i += 32) {
-        double Ma = 0;
-        for (int k = 0; k < nv; k++) Ma += w.M[i * nv + k] * a[k];
-        c += 0.5 * (Ma - w.fs[i]) * (a[i] - w.as[i]);
-    }
-    return warp_sum(c);
-}
-
 struct Mask128 { unsigned w[4]; };
 DEV bool operator==(const Mask128& a, const Mask128& b) { return a.w[0] == b.w[0] && a.w[1] == b.w[1] && a.w[2] == b.w[2] && a.w[3] == b.w[3]; }
 
-// result in w.qacc (and w.warm, the next warm start)
+// in: private fs, as, aref, warm; out: private qacc (and warm, the next warm start); nv <= 32: lane i owns dof i
 DEV void coop_solve(const GModel* __restrict__ g, CoopMem& w, int maxiter, double tol, int lane, bool need_forces = false) {
     const ilqg_model& m = g->m;
-    const int nv = m.nv, ne = w.nefc;
+    const int nv = m.nv, ne = w.hdr[0], nt = coop_nt(m.nv);
     static_assert(COOP_MAXEFC <= 128, "mask width");
     if (ne == 0) {
-        for (int i = lane; i < nv; i += 32) { w.qacc[i] = w.as[i]; w.warm[i] = w.as[i]; w.fc[i] = 0; }
+        if (lane < nv) { w.qacc[lane] = w.as[lane]; w.warm[lane] = w.as[lane]; w.fc[lane] = 0; }
         __syncwarp();
         return;
     }
+    const bool dof = lane < nv;
+    const double fs_i = dof ? w.fs[lane] : 0.0, as_i = dof ? w.as[lane] : 0.0, warm_i = dof ? w.warm[lane] : 0.0;
+    double qacc_i, Ma_i;
     {
-        double cw = coop_cost(w, w.warm, nv, lane), cs = coop_cost(w, w.as, nv, lane);
-        for (int i = lane; i < nv; i += 32) w.qacc[i] = cw < cs ? w.warm[i] : w.as[i];
+        // the better of the warm start and qacc_smooth; one pass over the rows evaluates both
+        double cw = 0, cs = 0;
+        for (int r = lane; r < ne; r += 32) {
+            double jw = -w.aref[r], js = jw;
+            const double* Jr = w.J + r * nv;
+            for (int i = 0; i < nv; i++) { jw += Jr[i] * w.warm[i]; js += Jr[i] * w.as[i]; }
+            const double D = w.D[r];
+            if (jw < 0) cw += 0.5 * D * jw * jw;
+            if (js < 0) cs += 0.5 * D * js * js;
+            w.jar[r] = jw;
+            w.jv[r] = js;
+        }
+        const double Mw = coop_symv(w.M, w.warm, nv, lane);
+        if (dof) cw += 0.5 * (Mw - fs_i) * (warm_i - as_i);
+        cw = warp_sum(cw);
+        cs = warp_sum(cs);
+        if (cw < cs) { qacc_i = warm_i; Ma_i = Mw; }
+        else {
+            qacc_i = as_i;
+            Ma_i = coop_symv(w.M, w.as, nv, lane);
+            __syncwarp();
+            for (int r = lane; r < ne; r += 32) w.jar[r] = w.jv[r];
+        }
     }
     __syncwarp();
     const double scale = 1.0 / (m.meaninertia * (nv > 1 ? nv : 1));
-    for (int i = lane; i < nv; i += 32) {
-        double s = 0;
-        for (int k = 0; k < nv; k++) s += w.M[i * nv + k] * w.qacc[k];
-        w.Ma[i] = s;
-    }
-    for (int r = lane; r < ne; r += 32) {
-        double s = -w.aref[r];
-        for (int i = 0; i < nv; i++) s += w.J[r * nv + i] * w.qacc[i];
-        w.jar[r] = s;
-    }
-    __syncwarp();
-    double cost = 0, old = 0;
+    double cost = 0, old = 0, fc_i = 0;
     int iter = 0;
     for (;;) {
-        // ---- active set, cost, forces, gradient, Hessian, Newton direction
+        // ---- active set (compacted list), cost, forces, gradient, Hessian, Newton direction
         Mask128 act = {{0, 0, 0, 0}};
         double c = 0;
+        int na = 0;
         for (int r0 = 0; r0 < ne; r0 += 32) {
             const int r = r0 + lane;
-            bool a = r < ne && w.jar[r] < 0;
-            act.w[r0 >> 5] = __ballot_sync(0xffffffffu, a);
-            if (a) c += 0.5 * w.D[r] * w.jar[r] * w.jar[r];
+            const bool a = r < ne && w.jar[r] < 0;
+            const unsigned bal = __ballot_sync(0xffffffffu, a);
+            act.w[r0 >> 5] = bal;
+            if (a) {
+                c += 0.5 * w.D[r] * w.jar[r] * w.jar[r];
+                w.alist[na + __popc(bal & ((1u << lane) - 1u))] = r;
+            }
+            na += __popc(bal);
         }
-        for (int i = lane; i < nv; i += 32) {
-            double f = 0;
-            for (int r = 0; r < ne; r++)
-                if ((act.w[r >> 5] >> (r & 31)) & 1u) f += w.J[r * nv + i] * (-w.D[r] * w.jar[r]);
-            w.fc[i] = f;
-            c += 0.5 * (w.Ma[i] - w.fs[i]) * (w.qacc[i] - w.as[i]);
-            w.grad[i] = w.Ma[i] - w.fs[i] - f;
-            w.search[i] = w.grad[i];
-        }
+        __syncwarp();
+        double f = 0;
+        if (dof)
+            for (int a = 0; a < na; a++) { const int r = w.alist[a]; f += w.J[r * nv + lane] * (-w.D[r] * w.jar[r]); }
+        fc_i = f;
+        const double grad_i = Ma_i - fs_i - f;
+        if (dof) c += 0.5 * (Ma_i - fs_i) * (qacc_i - as_i);
         cost = warp_sum(c);
-        for (int e = lane; e < nv * (nv + 1) / 2; e += 32) {
+        for (int e = lane; e < nt; e += 32) {
             // e -> (i, j), j <= i
-            int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-            while ((i + 1) * (i + 2) / 2 <= e) i++;
-            while (i * (i + 1) / 2 > e) i--;
-            const int j = e - i * (i + 1) / 2;
-            double h = w.M[i * nv + j];
-            for (int r = 0; r < ne; r++)
-                if ((act.w[r >> 5] >> (r & 31)) & 1u) h += w.D[r] * w.J[r * nv + i] * w.J[r * nv + j];
-            w.H[i * nv + j] = h;
+            int i = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+            while (ptri(i + 1, 0) <= e) i++;
+            while (ptri(i, 0) > e) i--;
+            const int j = e - ptri(i, 0);
+            double h = w.M[e];
+            for (int a = 0; a < na; a++) { const double* Jr = w.J + w.alist[a] * nv; h += w.D[w.alist[a]] * Jr[i] * Jr[j]; }
+            w.H[e] = h;
         }
         __syncwarp();
         coop_chol(w.H, nv, lane);
-        coop_chol_solve(w.H, w.search, nv, lane);
-        for (int i = lane; i < nv; i += 32) w.search[i] = -w.search[i];
-        __syncwarp();
+        const double search_i = -coop_chol_solve(w.H, grad_i, nv, lane);
         if (iter > 0) {
-            double gn = 0;
-            for (int i = lane; i < nv; i += 32) gn += w.grad[i] * w.grad[i];
-            gn = warp_sum(gn);
+            const double gn = warp_sum(dof ? grad_i * grad_i : 0.0);
             if (scale * (old - cost) < tol || scale * sqrt(gn) < tol) break;
         }
         if (iter >= maxiter) break;
         // ---- exact line search
-        double g1 = 0, g2 = 0;
-        for (int i = lane; i < nv; i += 32) {
-            double s = 0;
-            for (int k = 0; k < nv; k++) s += w.M[i * nv + k] * w.search[k];
-            w.Mv[i] = s;
-            g1 += w.search[i] * (w.Ma[i] - w.fs[i]);
-            g2 += w.search[i] * s;
-        }
+        if (dof) w.search[lane] = search_i;
+        __syncwarp();
+        const double Mv_i = coop_symv(w.M, w.search, nv, lane);
+        double g1 = dof ? search_i * (Ma_i - fs_i) : 0.0, g2 = dof ? search_i * Mv_i : 0.0;
         double d1 = 0, d2 = 0;
         for (int r = lane; r < ne; r += 32) {
             double s = 0;
-            for (int i = 0; i < nv; i++) s += w.J[r * nv + i] * w.search[i];
+            const double* Jr = w.J + r * nv;
+            for (int i = 0; i < nv; i++) s += Jr[i] * w.search[i];
             w.jv[r] = s;
             if (w.jar[r] < 0) { double t = w.D[r] * s; d1 += t * w.jar[r]; d2 += t * s; }
         }
         g1 = warp_sum(g1); g2 = warp_sum(g2);
         d1 = warp_sum(d1) + g1; d2 = warp_sum(d2) + g2;
-        __syncwarp();
         if (d1 >= 0 || d2 < ILQG_MINVAL) break;
+        // rows this lane owns stay in registers for the whole search (ne <= 128: at most 4 per lane)
+        double rj[4], rv[4], rD[4];
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const int r = lane + 32 * t;
+            const bool in = r < ne;
+            rj[t] = in ? w.jar[r] : 0.0; rv[t] = in ? w.jv[r] : 0.0; rD[t] = in ? w.D[r] : 0.0;
+        }
         double alpha = 0, lo = 0, hi = CUDART_INF;
         Mask128 cur = act;
         for (int it = 0; it < m.ls_iterations; it++) {
@@ -629,23 +724,26 @@ DEV void coop_solve(const GModel* __restrict__ g, CoopMem& w, int maxiter, doubl
             if (!(an > lo && an < hi)) an = isinf(hi) ? 2 * alpha + 1 : 0.5 * (lo + hi);
             double e1 = 0, e2 = 0;
             Mask128 mk = {{0, 0, 0, 0}};
-            for (int r0 = 0; r0 < ne; r0 += 32) {
-                const int r = r0 + lane;
-                bool a = false;
-                if (r < ne) {
-                    double jv = w.jv[r], x = w.jar[r] + an * jv;
-                    if (x < 0) { double t = w.D[r] * jv; e1 += t * x; e2 += t * jv; a = true; }
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                if (32 * t < ne) {   // uniform
+                    bool a = false;
+                    if (lane + 32 * t < ne) {
+                        const double x = rj[t] + an * rv[t];
+                        if (x < 0) { const double tt = rD[t] * rv[t]; e1 += tt * x; e2 += tt * rv[t]; a = true; }
+                    }
+                    mk.w[t] = __ballot_sync(0xffffffffu, a);
                 }
-                mk.w[r0 >> 5] = __ballot_sync(0xffffffffu, a);
             }
             e1 = warp_sum(e1) + g1 + g2 * an;
             e2 = warp_sum(e2) + g2;
-            bool same = mk == cur;
+            const bool same = mk == cur;
             alpha = an; d1 = e1; d2 = e2; cur = mk;
             if (same || d1 == 0 || d2 < ILQG_MINVAL) break;
         }
         if (alpha == 0) break;
-        for (int i = lane; i < nv; i += 32) { w.qacc[i] += alpha * w.search[i]; w.Ma[i] += alpha * w.Mv[i]; }
+        qacc_i += alpha * search_i;
+        Ma_i += alpha * Mv_i;
         for (int r = lane; r < ne; r += 32) w.jar[r] += alpha * w.jv[r];
         __syncwarp();
         old = cost;
@@ -653,115 +751,185 @@ DEV void coop_solve(const GModel* __restrict__ g, CoopMem& w, int maxiter, doubl
         if (cur == act) break;  // exact optimum: full Newton step inside the piece the Hessian was built for
     }
     if (need_forces) {  // qfrc_constraint at the final point (mj_Euler needs it)
-        for (int i = lane; i < nv; i += 32) {
-            double f = 0;
+        double f = 0;
+        if (dof)
             for (int r = 0; r < ne; r++)
-                if (w.jar[r] < 0) f += w.J[r * nv + i] * (-w.D[r] * w.jar[r]);
-            w.fc[i] = f;
-        }
+                if (w.jar[r] < 0) f += w.J[r * nv + lane] * (-w.D[r] * w.jar[r]);
+        fc_i = f;
     }
-    for (int i = lane; i < nv; i += 32) w.warm[i] = w.qacc[i];
+    if (dof) { w.qacc[lane] = qacc_i; w.warm[lane] = qacc_i; w.fc[lane] = fc_i; }
     __syncwarp();
 }
 
+// step cost on the device, lane 0 semantics (same term order as ilqg.cu's cost_eval)
+DEV double coop_cost_eval(const ilqg_cost* cost, const double* q, const double* v, const double* u, int nq, int nv, int nu) {
+    double c = 0;
+    for (int i = 0; i < nq; i++) { c = __dadd_rn(c, __dmul_rn(__dmul_rn(cost->q2[i], q[i]), q[i])); c = __dadd_rn(c, __dmul_rn(cost->q1[i], q[i])); }
+    for (int i = 0; i < nv; i++) { c = __dadd_rn(c, __dmul_rn(__dmul_rn(cost->v2[i], v[i]), v[i])); c = __dadd_rn(c, __dmul_rn(cost->v1[i], v[i])); }
+    for (int i = 0; i < nu; i++) { c = __dadd_rn(c, __dmul_rn(__dmul_rn(cost->u2[i], u[i]), u[i])); c = __dadd_rn(c, __dmul_rn(cost->u1[i], u[i])); }
+    return c;
+}
+
 // ------------------------------------------------------------------ kernels
-// centre: one warp per knot -> qacc_center (the warm start of every perturbed solve)
-__global__ void __launch_bounds__(128) coop_center_kernel(const GModel* __restrict__ g, int nknots, const double* __restrict__ qpos,
-                                                          const double* __restrict__ qvel, const double* __restrict__ ctrl,
-                                                          const double* __restrict__ warmstart, int niter, int nwarmup, size_t warp_bytes,
-                                                          double* __restrict__ qacc_center, int* __restrict__ status) {
-    extern __shared__ __align__(16) unsigned char coop_smem[];
+// centre: one warp per knot -> qacc_center, the knot's C-state and candidate pair list in HBM
+__global__ void __launch_bounds__(64) coop_center_kernel(const GModel* __restrict__ g, int nknots, const double* __restrict__ qpos,
+                                                         const double* __restrict__ qvel, const double* __restrict__ ctrl,
+                                                         const double* __restrict__ warmstart, int niter, int nwarmup, double slack,
+                                                         int cdbl, int pdbl, double* __restrict__ qacc_center, int* __restrict__ status,
+                                                         double* __restrict__ cstate_out, int* __restrict__ cand_out) {
+    extern __shared__ __align__(16) double coop_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int k = blockIdx.x * (blockDim.x >> 5) + wib;
     if (k >= nknots) return;
     const ilqg_model& m = g->m;
     CoopMem w;
-    coop_carve(w, reinterpret_cast<double*>(coop_smem + wib * warp_bytes), m);
+    double* base = coop_smem + (size_t)wib * (cdbl + pdbl);
+    coop_carve_cstate(w, base, m);
+    coop_carve_priv(w, base + cdbl, m);
     for (int i = lane; i < m.nq; i += 32) w.q[i] = qpos[(size_t)k * m.nq + i];
-    for (int i = lane; i < m.nv; i += 32) { w.v[i] = qvel[(size_t)k * m.nv + i]; w.warm[i] = warmstart ? warmstart[(size_t)k * m.nv + i] : 0.0; }
+    for (int i = lane; i < m.nv; i += 32) w.v[i] = qvel[(size_t)k * m.nv + i];
     for (int i = lane; i < m.nu; i += 32) w.u[i] = ctrl[(size_t)k * m.nu + i];
     __syncwarp();
-    bool ok = coop_build(g, w, lane);
+    coop_pos(g, w, lane, nullptr, -1, cand_out ? cand_out + (size_t)k * (COOP_MAXCAND + 1) : nullptr, slack);
+    const bool ok = w.hdr[1] != 0;
+    coop_vel(g, w, w.v, lane);
+    coop_smooth(g, w, w.u, lane);
+    if (lane < m.nv) w.warm[lane] = warmstart ? warmstart[(size_t)k * m.nv + lane] : 0.0;
+    __syncwarp();
     for (int rep = 0; rep < nwarmup; rep++) coop_solve(g, w, niter, 0.0, lane);
     bool fin = true;
-    for (int i = lane; i < m.nv; i += 32) { qacc_center[(size_t)k * m.nv + i] = w.qacc[i]; fin = fin && isfinite(w.qacc[i]); }
+    for (int i = lane; i < m.nv; i += 32) { qacc_center[(size_t)k * m.nv + i] = w.qacc[i]; w.center[i] = w.qacc[i]; w.fb0[i] = w.fb[i]; fin = fin && isfinite(w.qacc[i]); }
+    for (int r = lane; r < w.hdr[0]; r += 32) w.aref0[r] = w.aref[r];
     fin = __all_sync(0xffffffffu, fin);
     if (status && lane == 0) status[k] = !ok ? ILQG_ERR_CAPACITY : (fin ? 0 : ILQG_ERR_NONFINITE);
+    __syncwarp();
+    if (cstate_out) {
+        double* dst = cstate_out + (size_t)k * cdbl;
+        for (int e = lane; e < cdbl; e += 32) dst[e] = base[e];
+    }
 }
 
-// perturbed: one warp per (knot, column); the warp evaluates +eps then -eps and writes the column of the deriv block
-__global__ void __launch_bounds__(128) coop_perturb_kernel(const GModel* __restrict__ g, int nknots, const double* __restrict__ qpos,
-                                                           const double* __restrict__ qvel, const double* __restrict__ ctrl,
-                                                           const double* __restrict__ qacc_center, const ilqg_cost* __restrict__ cost, double eps,
-                                                           int niter, size_t warp_bytes, double* __restrict__ deriv, int* __restrict__ status) {
-    extern __shared__ __align__(16) unsigned char coop_smem[];
+DEV size_t coop_deriv_off(int col, int j, int nv, int nu) {   // reference layout (differentiator.h:56-61)
+    if (col < nu) return 2 * (size_t)nv * nv + col + (size_t)j * nu;
+    if (col < nu + nv) return (size_t)nv * nv + (col - nu) + (size_t)j * nv;
+    return (col - nu - nv) + (size_t)j * nv;
+}
+DEV size_t coop_grad_off(int col, int nv, int nu) {
+    size_t off = (size_t)nv * (2 * nv + nu);
+    if (col < nu) return off + 2 * nv + col;
+    if (col < nu + nv) return off + nv + (col - nu);
+    return off + col - nu - nv;
+}
+
+// qvel / ctrl columns: one CTA per knot; the warps share the centre's C-state and take columns in turn
+__global__ void __launch_bounds__(256, 2) coop_velctrl_kernel(const GModel* __restrict__ g, int nknots, const double* __restrict__ cstate,
+                                                              const ilqg_cost* __restrict__ cost, double eps, int niter, int cdbl, int pdbl,
+                                                              double* __restrict__ deriv, int* __restrict__ status) {
+    extern __shared__ __align__(16) double coop_smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int k = blockIdx.x;
+    const ilqg_model& m = g->m;
+    const int nq = m.nq, nv = m.nv, nu = m.nu, ncol = 2 * nv + nu, nd = nv * ncol + ncol;
+    {
+        const double* src = cstate + (size_t)k * cdbl;
+        for (int e = threadIdx.x; e < cdbl; e += blockDim.x) coop_smem[e] = src[e];
+    }
+    __syncthreads();
+    CoopMem w;
+    coop_carve_cstate(w, coop_smem, m);
+    coop_carve_priv(w, coop_smem + cdbl + (size_t)wib * pdbl, m);
+    const int ne = w.hdr[0];
+    double c0 = 0;
+    if (cost && lane == 0) c0 = coop_cost_eval(cost, w.q, w.v, w.u, nq, nv, nu);
+    bool fin = true;
+    for (int col = wib; col < nu + nv; col += nwarp) {
+        const bool is_vel = col >= nu;
+        double plus = 0, dcost = 0;
+        for (int sgn = 1; sgn >= -1; sgn -= 2) {
+            const double se = sgn * eps;
+            if (lane < nv) { w.pv[lane] = w.v[lane] + ((is_vel && col - nu == lane) ? se : 0.0); w.warm[lane] = w.center[lane]; }
+            if (lane < nu) w.pu[lane] = w.u[lane] + ((!is_vel && col == lane) ? se : 0.0);
+            __syncwarp();
+            if (cost && sgn > 0 && lane == 0) dcost = __ddiv_rn(__dsub_rn(coop_cost_eval(cost, w.q, w.pv, w.pu, nq, nv, nu), c0), eps);
+            if (is_vel) coop_vel(g, w, w.pv, lane);
+            else {   // mjSTAGE_VEL skip: the centre's velocity-stage products
+                if (lane < nv) w.fb[lane] = w.fb0[lane];
+                for (int r = lane; r < ne; r += 32) w.aref[r] = w.aref0[r];
+                __syncwarp();
+            }
+            coop_smooth(g, w, w.pu, lane);
+            coop_solve(g, w, niter, 0.0, lane);
+            const double a = lane < nv ? w.qacc[lane] : 0.0;
+            if (sgn > 0) plus = a;
+            else if (lane < nv) {
+                const double d = (plus - a) / (2 * eps);
+                fin = fin && isfinite(d);
+                deriv[(size_t)k * nd + coop_deriv_off(col, lane, nv, nu)] = d;
+            }
+            __syncwarp();
+        }
+        if (cost && lane == 0) deriv[(size_t)k * nd + coop_grad_off(col, nv, nu)] = dcost;
+    }
+    fin = __all_sync(0xffffffffu, fin);
+    if (status && lane == 0 && !fin) atomicCAS(&status[k], 0, ILQG_ERR_NONFINITE);
+}
+
+// qpos columns: one warp per (knot, column); +eps then -eps through the full pipeline (narrow phase on the candidates)
+__global__ void __launch_bounds__(64) coop_qpos_kernel(const GModel* __restrict__ g, int nknots, const double* __restrict__ qpos,
+                                                       const double* __restrict__ qvel, const double* __restrict__ ctrl,
+                                                       const double* __restrict__ qacc_center, const int* __restrict__ cand,
+                                                       const ilqg_cost* __restrict__ cost, double eps, int niter, int cdbl, int pdbl,
+                                                       double* __restrict__ deriv, int* __restrict__ status) {
+    extern __shared__ __align__(16) double coop_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const ilqg_model& m = g->m;
     const int nq = m.nq, nv = m.nv, nu = m.nu, ncol = 2 * nv + nu, nd = nv * ncol + ncol;
     const long item = (long)blockIdx.x * (blockDim.x >> 5) + wib;
-    if (item >= (long)nknots * ncol) return;
-    const int k = (int)(item / ncol), col = (int)(item - (long)k * ncol);
+    if (item >= (long)nknots * nv) return;
+    const int k = (int)(item / nv), i = (int)(item - (long)k * nv), col = nu + nv + i;
     CoopMem w;
-    coop_carve(w, reinterpret_cast<double*>(coop_smem + wib * warp_bytes), m);
-    double plus[1];  // this lane's component of qacc(+eps) (nv <= 32)
-    plus[0] = 0;
-    bool ok = true;
-    double dcost = 0;
+    double* base = coop_smem + (size_t)wib * (cdbl + pdbl);
+    coop_carve_cstate(w, base, m);
+    coop_carve_priv(w, base + cdbl, m);
+    const int* kc = cand ? cand + (size_t)k * (COOP_MAXCAND + 1) : nullptr;
+    const int ncand = kc ? kc[0] : -1;
+    double plus = 0, dcost = 0;
+    bool ok = true, fin = true;
     for (int sgn = 1; sgn >= -1; sgn -= 2) {
-        for (int i = lane; i < nq; i += 32) w.q[i] = qpos[(size_t)k * nq + i];
-        for (int i = lane; i < nv; i += 32) { w.v[i] = qvel[(size_t)k * nv + i]; w.warm[i] = qacc_center[(size_t)k * nv + i]; }
-        for (int i = lane; i < nu; i += 32) w.u[i] = ctrl[(size_t)k * nu + i];
+        for (int e = lane; e < nq; e += 32) w.q[e] = qpos[(size_t)k * nq + e];
+        for (int e = lane; e < nv; e += 32) w.v[e] = qvel[(size_t)k * nv + e];
+        for (int e = lane; e < nu; e += 32) w.u[e] = ctrl[(size_t)k * nu + e];
         __syncwarp();
-        double c0 = 0;
-        if (cost && sgn > 0 && lane == 0) {
-            for (int i = 0; i < nq; i++) { c0 = __dadd_rn(c0, __dmul_rn(__dmul_rn(cost->q2[i], w.q[i]), w.q[i])); c0 = __dadd_rn(c0, __dmul_rn(cost->q1[i], w.q[i])); }
-            for (int i = 0; i < nv; i++) { c0 = __dadd_rn(c0, __dmul_rn(__dmul_rn(cost->v2[i], w.v[i]), w.v[i])); c0 = __dadd_rn(c0, __dmul_rn(cost->v1[i], w.v[i])); }
-            for (int i = 0; i < nu; i++) { c0 = __dadd_rn(c0, __dmul_rn(__dmul_rn(cost->u2[i], w.u[i]), w.u[i])); c0 = __dadd_rn(c0, __dmul_rn(cost->u1[i], w.u[i])); }
-        }
         if (lane == 0) {
             const double se = sgn * eps;
-            if (col < nu) w.u[col] += se;
-            else if (col < nu + nv) w.v[col - nu] += se;
-            else {
-                const int i = col - nu - nv, j = m.dof_jntid[i];
-                if (m.jnt_type[j] == ILQG_JNT_FREE && i >= m.jnt_dofadr[j] + 3) {
-                    const int a = i - m.jnt_dofadr[j] - 3;
-                    quat_integrate(&w.q[m.jnt_qposadr[j] + 3], V3{a == 0 ? se : 0.0, a == 1 ? se : 0.0, a == 2 ? se : 0.0}, 1.0);
-                } else
-                    w.q[m.jnt_qposadr[j] + i - m.jnt_dofadr[j]] += se;
-            }
-            if (cost && sgn > 0) {
-                double c1 = 0;
-                for (int i = 0; i < nq; i++) { c1 = __dadd_rn(c1, __dmul_rn(__dmul_rn(cost->q2[i], w.q[i]), w.q[i])); c1 = __dadd_rn(c1, __dmul_rn(cost->q1[i], w.q[i])); }
-                for (int i = 0; i < nv; i++) { c1 = __dadd_rn(c1, __dmul_rn(__dmul_rn(cost->v2[i], w.v[i]), w.v[i])); c1 = __dadd_rn(c1, __dmul_rn(cost->v1[i], w.v[i])); }
-                for (int i = 0; i < nu; i++) { c1 = __dadd_rn(c1, __dmul_rn(__dmul_rn(cost->u2[i], w.u[i]), w.u[i])); c1 = __dadd_rn(c1, __dmul_rn(cost->u1[i], w.u[i])); }
-                dcost = __ddiv_rn(__dsub_rn(c1, c0), eps);
-            }
+            double c0 = 0;
+            if (cost && sgn > 0) c0 = coop_cost_eval(cost, w.q, w.v, w.u, nq, nv, nu);
+            const int j = m.dof_jntid[i];
+            if (m.jnt_type[j] == ILQG_JNT_FREE && i >= m.jnt_dofadr[j] + 3) {
+                const int a = i - m.jnt_dofadr[j] - 3;
+                quat_integrate(&w.q[m.jnt_qposadr[j] + 3], V3{a == 0 ? se : 0.0, a == 1 ? se : 0.0, a == 2 ? se : 0.0}, 1.0);
+            } else
+                w.q[m.jnt_qposadr[j] + i - m.jnt_dofadr[j]] += se;
+            if (cost && sgn > 0) dcost = __ddiv_rn(__dsub_rn(coop_cost_eval(cost, w.q, w.v, w.u, nq, nv, nu), c0), eps);
         }
         __syncwarp();
-        ok = coop_build(g, w, lane) && ok;
+        coop_pos(g, w, lane, kc ? kc + 1 : nullptr, ncand, nullptr, 0.0);
+        ok = ok && w.hdr[1] != 0;
+        coop_vel(g, w, w.v, lane);
+        coop_smooth(g, w, w.u, lane);
+        if (lane < nv) w.warm[lane] = qacc_center[(size_t)k * nv + lane];
+        __syncwarp();
         coop_solve(g, w, niter, 0.0, lane);
-        if (sgn > 0) plus[0] = lane < nv ? w.qacc[lane] : 0.0;
+        const double a = lane < nv ? w.qacc[lane] : 0.0;
+        if (sgn > 0) plus = a;
+        else if (lane < nv) {
+            const double d = (plus - a) / (2 * eps);
+            fin = isfinite(d);
+            deriv[(size_t)k * nd + coop_deriv_off(col, lane, nv, nu)] = d;
+        }
         __syncwarp();
     }
-    // column `col`: d qacc_j / d input, j = lane
-    bool fin = true;
-    if (lane < nv) {
-        double d = (plus[0] - w.qacc[lane]) / (2 * eps);
-        fin = isfinite(d);
-        size_t off;
-        if (col < nu) off = 2 * (size_t)nv * nv + col + (size_t)lane * nu;
-        else if (col < nu + nv) off = (size_t)nv * nv + (col - nu) + (size_t)lane * nv;
-        else off = (col - nu - nv) + (size_t)lane * nv;
-        deriv[(size_t)k * nd + off] = d;
-    }
-    if (cost && lane == 0) {
-        size_t off = (size_t)nv * ncol;
-        if (col < nu) off += 2 * nv + col;
-        else if (col < nu + nv) off += nv + (col - nu);
-        else off += col - nu - nv;
-        deriv[(size_t)k * nd + off] = dcost;
-    }
+    if (cost && lane == 0) deriv[(size_t)k * nd + coop_grad_off(col, nv, nu)] = dcost;
     fin = __all_sync(0xffffffffu, fin);
     if (status && lane == 0) {
         if (!ok) atomicExch(&status[k], ILQG_ERR_CAPACITY);
@@ -770,21 +938,27 @@ __global__ void __launch_bounds__(128) coop_perturb_kernel(const GModel* __restr
 }
 
 // mj_forward for n states: one warp per state
-__global__ void __launch_bounds__(128) coop_forward_kernel(const GModel* __restrict__ g, int n, const double* __restrict__ qpos,
-                                                           const double* __restrict__ qvel, const double* __restrict__ ctrl,
-                                                           double* __restrict__ warmstart, double* __restrict__ qacc_out, size_t warp_bytes) {
-    extern __shared__ __align__(16) unsigned char coop_smem[];
+__global__ void __launch_bounds__(64) coop_forward_kernel(const GModel* __restrict__ g, int n, const double* __restrict__ qpos,
+                                                          const double* __restrict__ qvel, const double* __restrict__ ctrl,
+                                                          double* __restrict__ warmstart, double* __restrict__ qacc_out, int cdbl, int pdbl) {
+    extern __shared__ __align__(16) double coop_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int k = blockIdx.x * (blockDim.x >> 5) + wib;
     if (k >= n) return;
     const ilqg_model& m = g->m;
     CoopMem w;
-    coop_carve(w, reinterpret_cast<double*>(coop_smem + wib * warp_bytes), m);
+    double* base = coop_smem + (size_t)wib * (cdbl + pdbl);
+    coop_carve_cstate(w, base, m);
+    coop_carve_priv(w, base + cdbl, m);
     for (int i = lane; i < m.nq; i += 32) w.q[i] = qpos[(size_t)k * m.nq + i];
-    for (int i = lane; i < m.nv; i += 32) { w.v[i] = qvel[(size_t)k * m.nv + i]; w.warm[i] = warmstart ? warmstart[(size_t)k * m.nv + i] : 0.0; }
+    for (int i = lane; i < m.nv; i += 32) w.v[i] = qvel[(size_t)k * m.nv + i];
     for (int i = lane; i < m.nu; i += 32) w.u[i] = ctrl[(size_t)k * m.nu + i];
     __syncwarp();
-    coop_build(g, w, lane);
+    coop_pos(g, w, lane, nullptr, -1, nullptr, 0.0);
+    coop_vel(g, w, w.v, lane);
+    coop_smooth(g, w, w.u, lane);
+    if (lane < m.nv) w.warm[lane] = warmstart ? warmstart[(size_t)k * m.nv + lane] : 0.0;
+    __syncwarp();
     coop_solve(g, w, m.iterations, m.tolerance, lane);
     for (int i = lane; i < m.nv; i += 32) {
         qacc_out[(size_t)k * m.nv + i] = w.qacc[i];
@@ -793,37 +967,44 @@ __global__ void __launch_bounds__(128) coop_forward_kernel(const GModel* __restr
 }
 
 // nsteps x mj_step for n states (Euler with implicit joint damping; RK4 models use the thread-per-rollout path)
-__global__ void __launch_bounds__(128) coop_step_kernel(const GModel* __restrict__ g, int n, int nsteps, double* __restrict__ qpos,
-                                                        double* __restrict__ qvel, const double* __restrict__ ctrl, double* __restrict__ warmstart,
-                                                        double* __restrict__ qacc_out, size_t warp_bytes) {
-    extern __shared__ __align__(16) unsigned char coop_smem[];
+__global__ void __launch_bounds__(64) coop_step_kernel(const GModel* __restrict__ g, int n, int nsteps, double* __restrict__ qpos,
+                                                       double* __restrict__ qvel, const double* __restrict__ ctrl, double* __restrict__ warmstart,
+                                                       double* __restrict__ qacc_out, int cdbl, int pdbl) {
+    extern __shared__ __align__(16) double coop_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int k = blockIdx.x * (blockDim.x >> 5) + wib;
     if (k >= n) return;
     const ilqg_model& m = g->m;
-    const int nv = m.nv;
+    const int nv = m.nv, nt = coop_nt(m.nv);
     const double h = m.timestep;
     CoopMem w;
-    coop_carve(w, reinterpret_cast<double*>(coop_smem + wib * warp_bytes), m);
+    double* base = coop_smem + (size_t)wib * (cdbl + pdbl);
+    coop_carve_cstate(w, base, m);
+    coop_carve_priv(w, base + cdbl, m);
     for (int i = lane; i < m.nq; i += 32) w.q[i] = qpos[(size_t)k * m.nq + i];
-    for (int i = lane; i < nv; i += 32) { w.v[i] = qvel[(size_t)k * nv + i]; w.warm[i] = warmstart ? warmstart[(size_t)k * nv + i] : 0.0; }
+    for (int i = lane; i < nv; i += 32) w.v[i] = qvel[(size_t)k * nv + i];
     for (int i = lane; i < m.nu; i += 32) w.u[i] = ctrl[(size_t)k * m.nu + i];
+    double warm_i = (warmstart && lane < nv) ? warmstart[(size_t)k * nv + lane] : 0.0;   // the position stage's temporaries alias w.warm
     __syncwarp();
     for (int s = 0; s < nsteps; s++) {
-        coop_build(g, w, lane);
+        coop_pos(g, w, lane, nullptr, -1, nullptr, 0.0);
+        coop_vel(g, w, w.v, lane);
+        coop_smooth(g, w, w.u, lane);
+        if (lane < nv) w.warm[lane] = warm_i;
+        __syncwarp();
         coop_solve(g, w, m.iterations, m.tolerance, lane, true);
+        if (lane < nv) warm_i = w.warm[lane];
         // mj_Euler: (M + h diag(b)) a = qfrc_smooth + qfrc_constraint when any dof is damped
+        double a_i = lane < nv ? w.qacc[lane] : 0.0;
         if (g->any_damping) {
-            for (int e = lane; e < nv * nv; e += 32) w.H[e] = w.M[e] + ((e / nv) == (e % nv) ? h * m.dof_damping[e / nv] : 0.0);
-            for (int i = lane; i < nv; i += 32) w.search[i] = w.fs[i] + w.fc[i];
+            for (int e = lane; e < nt; e += 32) w.H[e] = w.M[e];
+            __syncwarp();
+            if (lane < nv) w.H[ptri(lane, lane)] += h * m.dof_damping[lane];
             __syncwarp();
             coop_chol(w.H, nv, lane);
-            coop_chol_solve(w.H, w.search, nv, lane);
-        } else {
-            for (int i = lane; i < nv; i += 32) w.search[i] = w.qacc[i];
-            __syncwarp();
+            a_i = coop_chol_solve(w.H, lane < nv ? w.fs[lane] + w.fc[lane] : 0.0, nv, lane);
         }
-        for (int i = lane; i < nv; i += 32) w.v[i] += h * w.search[i];
+        if (lane < nv) w.v[lane] += h * a_i;
         __syncwarp();
         for (int j = lane; j < m.njnt; j += 32) {
             const int qa = m.jnt_qposadr[j], da = m.jnt_dofadr[j];
@@ -838,7 +1019,7 @@ __global__ void __launch_bounds__(128) coop_step_kernel(const GModel* __restrict
     for (int i = lane; i < m.nq; i += 32) qpos[(size_t)k * m.nq + i] = w.q[i];
     for (int i = lane; i < nv; i += 32) {
         qvel[(size_t)k * nv + i] = w.v[i];
-        if (warmstart) warmstart[(size_t)k * nv + i] = w.warm[i];
+        if (warmstart) warmstart[(size_t)k * nv + i] = warm_i;
         if (qacc_out) qacc_out[(size_t)k * nv + i] = w.qacc[i];
     }
 }

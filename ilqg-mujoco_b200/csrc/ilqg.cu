@@ -369,6 +369,8 @@ template <class T>
 struct IlqrLaunch<T, true> {
     static cudaError_t rollout(const DevModel<T>& dm, const IlqrBuffers& b, const ilqg_cost* cost, cudaStream_t s) {
         int n = b.ninst * b.nalpha;
+        // (a rollout is one long dependent chain per thread — T steps x integrator stages — and latency-bound: spreading small
+        //  batches one warp per CTA over more SMs was measured and does not help)
         ilqr_rollout_kernel<T><<<(n + 127) / 128, 128, 0, s>>>(dm, b, cost);
         return cudaGetLastError();
     }
@@ -463,56 +465,90 @@ struct EngineT : Engine {
 // generic warp-per-rollout engine (coop.cuh): any model of the subset, used when no topology instantiation matches
 struct CoopEngine : Engine {
     GModel* d_g = nullptr;
-    size_t warp_bytes = 0;
-    int warps = 4;
+    int cdbl = 0, pdbl = 0;          // doubles of the C-state / private block of one rollout
+    int vc_warps = 1;                // warps per CTA of the qvel/ctrl kernel
     ilqg_model tab;
+    double* d_cstate = nullptr;      // [chunk][cdbl]  the centre's position-stage products
+    int* d_cand = nullptr;           // [chunk][COOP_MAXCAND + 1]  collision pairs near contact
+    int chunk_cap = 0;
+    static constexpr int MAX_CHUNK = 8192;   // knots per internal pass (bounds the scratch: 27 KB of C-state per humanoid knot)
     const char* name() const override { return "generic-warp-per-rollout"; }
-    ~CoopEngine() override { cudaFree(d_g); }
+    int fd_launches() const override { return 3; }
+    ~CoopEngine() override { cudaFree(d_g); cudaFree(d_cstate); cudaFree(d_cand); }
+    size_t warp_bytes() const { return (size_t)(cdbl + pdbl) * sizeof(double); }
     cudaError_t init(const ilqg_model& m) {
         GModel* hg = new GModel();
         if (!gmodel_from_tables(m, *hg)) { delete hg; return cudaErrorInvalidValue; }
         tab = m;
-        warp_bytes = (coop_bytes_per_warp(m) + 15) / 16 * 16;
+        cdbl = (int)coop_cstate_doubles(m);
+        pdbl = (int)coop_priv_doubles(m);
         cudaError_t e = cudaMalloc(&d_g, sizeof(GModel));
         if (e == cudaSuccess) e = cudaMemcpy(d_g, hg, sizeof(GModel), cudaMemcpyHostToDevice);
         delete hg;
         if (e != cudaSuccess) return e;
-        int dev = 0, maxsm = 0;
+        int dev = 0, maxblk = 0, maxsm = 0;
         cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-        while (warps > 1 && warp_bytes * warps > (size_t)maxsm) warps /= 2;
-        if (warp_bytes * warps > (size_t)maxsm) return cudaErrorInvalidValue;
-        const int bytes = (int)(warp_bytes * warps);
-        if ((e = cudaFuncSetAttribute(coop_center_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(coop_perturb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(coop_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(coop_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+        cudaDeviceGetAttribute(&maxblk, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+        if (warp_bytes() > (size_t)maxblk) return cudaErrorInvalidValue;
+        // qvel/ctrl kernel: as many warps as let two CTAs share an SM (each CTA also pays 1 KB of system shared memory)
+        const size_t cb = (size_t)cdbl * sizeof(double), pb = (size_t)pdbl * sizeof(double);
+        const size_t half = (size_t)maxsm / 2 - 1024;
+        int w2 = half > cb ? (int)((half - cb) / pb) : 0;
+        int w1 = (int)(((size_t)maxblk - cb) / pb);
+        vc_warps = w2 >= 4 ? w2 : w1;
+        if (vc_warps > 8) vc_warps = 8;
+        if (vc_warps < 1) return cudaErrorInvalidValue;
+        const int one = (int)warp_bytes(), vc = (int)(cb + vc_warps * pb);
+        if ((e = cudaFuncSetAttribute(coop_center_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, one)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(coop_qpos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, one)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(coop_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, one)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(coop_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, one)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(coop_velctrl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, vc)) != cudaSuccess) return e;
         return cudaSuccess;
+    }
+    cudaError_t ensure_scratch(int n) {
+        if (n <= chunk_cap) return cudaSuccess;
+        cudaFree(d_cstate); cudaFree(d_cand);
+        d_cstate = nullptr; d_cand = nullptr; chunk_cap = 0;
+        cudaError_t e = cudaMalloc(&d_cstate, (size_t)n * cdbl * sizeof(double));
+        if (e == cudaSuccess) e = cudaMalloc(&d_cand, (size_t)n * (COOP_MAXCAND + 1) * sizeof(int));
+        if (e == cudaSuccess) chunk_cap = n;
+        return e;
     }
     cudaError_t fd(int nknots, const double* qpos, const double* qvel, const double* ctrl, const double* warm, const ilqg_cost* cost_dev,
                    const ilqg_fd_opts& o, double* deriv, double* qacc_center, int* status, cudaStream_t s, cudaEvent_t* ev) override {
         if (nknots <= 0) return cudaSuccess;
-        const size_t smem = warp_bytes * warps;
-        const int ncol = 2 * tab.nv + tab.nu;
+        const int nq = tab.nq, nv = tab.nv, nu = tab.nu, nd = nv * (2 * nv + nu) + 2 * nv + nu;
+        const size_t one = warp_bytes(), vc = (size_t)cdbl * sizeof(double) + (size_t)vc_warps * pdbl * sizeof(double);
+        // a perturbation of eps moves a geom by eps x (lever arm): pairs farther than margin + slack from contact cannot become active
+        const double slack = 2000.0 * o.eps;
+        cudaError_t e = ensure_scratch(nknots < MAX_CHUNK ? nknots : MAX_CHUNK);
+        if (e != cudaSuccess) return e;
         if (ev) cudaEventRecord(ev[0], s);
-        coop_center_kernel<<<(nknots + warps - 1) / warps, warps * 32, smem, s>>>(d_g, nknots, qpos, qvel, ctrl, warm, o.niter, o.nwarmup, warp_bytes,
-                                                                                qacc_center, status);
-        if (ev) { cudaEventRecord(ev[1], s); cudaEventRecord(ev[3], s); }
-        long items = (long)nknots * ncol;
-        coop_perturb_kernel<<<(unsigned)((items + warps - 1) / warps), warps * 32, smem, s>>>(d_g, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps,
-                                                                                          o.niter, warp_bytes, deriv, status);
+        for (int lo = 0; lo < nknots; lo += MAX_CHUNK) {
+            const int n = nknots - lo < MAX_CHUNK ? nknots - lo : MAX_CHUNK;
+            const double *q = qpos + (size_t)lo * nq, *v = qvel + (size_t)lo * nv, *u = ctrl + (size_t)lo * nu, *w = warm ? warm + (size_t)lo * nv : nullptr;
+            double *qc = qacc_center + (size_t)lo * nv, *dv = deriv + (size_t)lo * nd;
+            int* st = status ? status + lo : nullptr;
+            coop_center_kernel<<<n, 32, one, s>>>(d_g, n, q, v, u, w, o.niter, o.nwarmup, slack, cdbl, pdbl, qc, st, d_cstate, d_cand);
+            if (ev && lo == 0) cudaEventRecord(ev[1], s);
+            coop_velctrl_kernel<<<n, vc_warps * 32, vc, s>>>(d_g, n, d_cstate, cost_dev, o.eps, o.niter, cdbl, pdbl, dv, st);
+            if (ev && lo == 0) cudaEventRecord(ev[3], s);
+            coop_qpos_kernel<<<(unsigned)((long)n * nv), 32, one, s>>>(d_g, n, q, v, u, qc, d_cand, cost_dev, o.eps, o.niter, cdbl, pdbl, dv, st);
+        }
         if (ev) cudaEventRecord(ev[2], s);
         return cudaGetLastError();
     }
     cudaError_t forward(int n, const double* qpos, const double* qvel, const double* ctrl, double* warm, double* qacc, cudaStream_t s) override {
         if (n <= 0) return cudaSuccess;
-        coop_forward_kernel<<<(n + warps - 1) / warps, warps * 32, warp_bytes * warps, s>>>(d_g, n, qpos, qvel, ctrl, warm, qacc, warp_bytes);
+        coop_forward_kernel<<<n, 32, warp_bytes(), s>>>(d_g, n, qpos, qvel, ctrl, warm, qacc, cdbl, pdbl);
         return cudaGetLastError();
     }
     cudaError_t step(int n, int nsteps, double* qpos, double* qvel, const double* ctrl, double* warm, double* qacc, cudaStream_t s) override {
         if (n <= 0) return cudaSuccess;
         if (tab.integrator != ILQG_INT_EULER) return cudaErrorNotSupported;
-        coop_step_kernel<<<(n + warps - 1) / warps, warps * 32, warp_bytes * warps, s>>>(d_g, n, nsteps, qpos, qvel, ctrl, warm, qacc, warp_bytes);
+        coop_step_kernel<<<n, 32, warp_bytes(), s>>>(d_g, n, nsteps, qpos, qvel, ctrl, warm, qacc, cdbl, pdbl);
         return cudaGetLastError();
     }
     bool ilqr_supported() const override { return false; }

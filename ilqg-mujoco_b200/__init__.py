@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libilqg_b200.so")
+LIB_PATH = os.environ.get("ILQG_LIB") or os.path.join(_HERE, "libilqg_b200.so")   # ILQG_LIB: A/B-test an alternative build
 MODELS_DIR = os.path.join(_HERE, "models")
 
 OK, ERR_ARG, ERR_MODEL, ERR_IO, ERR_CUDA, ERR_UNSUPPORTED, ERR_NONFINITE, ERR_CAPACITY = range(8)

@@ -17,7 +17,7 @@
 //                        pairs within (margin + slack) of contact — the only pairs a +-eps perturbation can activate
 //   coop_velctrl_kernel  CTA per knot: loads the centre's C-state once; its warps share it read-only and take the qvel / ctrl
 //                        columns in turn, each re-running only the velocity stage (or only the actuation) and the solve.
-//                        8 warps x 11 KB private + 27 KB shared: 16 resident warps per SM instead of 4.
+//                        7 warps x 11 KB private + 28 KB shared: 14 resident warps per SM instead of 4.
 //   coop_qpos_kernel     warp per (knot, qpos column): full pipeline at +eps and -eps, narrow phase on the candidate list only.
 //
 // Replaces, for such models, the same reference calls as dyn.cuh: mj_forward / mj_forwardSkip inside
@@ -44,6 +44,7 @@ struct GModel {
     unsigned body_dofmask[ILQG_MAXBODY];   // bit i set: dof i moves this body (nv <= 32)
     int nlevel, level_start[COOP_MAXLEVEL + 1], level_body[ILQG_MAXBODY];  // bodies grouped by tree depth
     int any_damping;
+    int dof_act[ILQG_MAXV];   // actuator driving dof i, -1: none, -2: several (loop over the actuators)
 };
 
 inline bool gmodel_from_tables(const ilqg_model& s, GModel& g) {
@@ -73,6 +74,8 @@ inline bool gmodel_from_tables(const ilqg_model& s, GModel& g) {
             for (int i = s.body_dofadr[a]; i < s.body_dofadr[a] + s.body_dofnum[a]; i++) mk |= 1u << i;
         g.body_dofmask[b] = mk;
     }
+    for (int i = 0; i < s.nv; i++) g.dof_act[i] = -1;
+    for (int a = 0; a < s.nu; a++) { int d = s.act_dofid[a]; g.dof_act[d] = g.dof_act[d] == -1 ? a : -2; }
     g.any_damping = 0;
     for (int i = 0; i < s.nv; i++) g.any_damping |= s.dof_damping[i] > 0;
     return true;
@@ -86,7 +89,8 @@ struct CoopMem {
     double *M, *L;                         // packed lower triangles; L's diagonal holds 1 / L_ii
     double *J, *D, *rB, *rkt;              // constraint rows: Jacobian, 1/R, damping B, K*imp*(pos - margin)
     double *fb0, *aref0;                   // the centre's velocity-stage products (ctrl columns reuse them)
-    int* hdr;                              // hdr[0] = nefc, hdr[1] = capacity ok
+    double* Hc;                            // factor of the Newton Hessian M + J_A' D_A J_A for the centre solution's active set A
+    int* hdr;                              // hdr[0] = nefc, hdr[1] = capacity ok, hdr[2] = Hc valid, hdr[4..7] = active-set mask of Hc
     // ---- private working set
     double *pv, *pu;                       // perturbed qvel / ctrl
     double *cvel, *cacc, *cfrc, *cdofdot;
@@ -99,19 +103,23 @@ struct CoopMem {
 };
 
 __host__ __device__ inline int coop_nt(int nv) { return nv * (nv + 1) / 2; }
-__host__ __device__ inline size_t coop_cstate_doubles(const ilqg_model& m) {
+__host__ __device__ inline size_t coop_cstate_doubles(const ilqg_model& m, bool full) {
     const size_t nv = m.nv, nb = m.nbody;
     size_t n = m.nq + nv + m.nu + nv;                       // q v u center
     n += 6 * nv + 10 * nb + 3 * nb + nv;                    // cdof cinert com dspr
     n += 2 * (size_t)coop_nt(m.nv);                         // M L
     n += (size_t)COOP_MAXEFC * nv + 3 * COOP_MAXEFC;        // J D rB rkt
-    n += nv + COOP_MAXEFC;                                  // fb0 aref0
-    n += 1;                                                 // hdr (2 ints)
+    n += 4;                                                 // hdr (8 ints)
+    n = (n + 1) & ~(size_t)1;
+    if (!full) return n;                                    // what a stand-alone rollout needs
+    n += nv + COOP_MAXEFC;                                  // fb0 aref0   } products of the centre evaluation that
+    n += coop_nt(m.nv);                                     // Hc          } the qvel / ctrl columns reuse
     return (n + 1) & ~(size_t)1;
 }
 __host__ __device__ inline size_t coop_priv_doubles(const ilqg_model& m) {
     const size_t nv = m.nv, nb = m.nbody, nj = m.njnt, ng = m.ngeom;
-    size_t priv = nv + m.nu + 18 * nb + 6 * nv + 10 * nv + 3 * COOP_MAXEFC + coop_nt(m.nv) + (COOP_MAXEFC + 1) / 2;
+    size_t rne = 18 * nb + 6 * nv, hes = coop_nt(m.nv);   // the bias recursion's scratch is dead before the Newton Hessian is built
+    size_t priv = nv + m.nu + (rne > hes ? rne : hes) + 10 * nv + 3 * COOP_MAXEFC + (COOP_MAXEFC + 1) / 2;
     size_t tmp = 19 * nb + 6 * nj + 6 * ng + 10 * nb + (size_t)COOP_MAXCON * 13 + (COOP_MAXCON + 1) / 2;
     size_t n = priv > tmp ? priv : tmp;
     return (n + 1) & ~(size_t)1;
@@ -125,18 +133,24 @@ DEV void coop_carve_cstate(CoopMem& w, double* base, const ilqg_model& m) {
     w.cdof = take(6 * nv); w.cinert = take(10 * nb); w.com = take(3 * nb); w.dspr = take(nv);
     w.M = take(nt); w.L = take(nt);
     w.J = take((size_t)COOP_MAXEFC * nv); w.D = take(COOP_MAXEFC); w.rB = take(COOP_MAXEFC); w.rkt = take(COOP_MAXEFC);
-    w.fb0 = take(nv); w.aref0 = take(COOP_MAXEFC);
     w.hdr = reinterpret_cast<int*>(p);
+    p = base + coop_cstate_doubles(m, false);
+    w.fb0 = take(nv); w.aref0 = take(COOP_MAXEFC); w.Hc = take(nt);   // only valid where the full C-state is allocated
 }
 DEV void coop_carve_priv(CoopMem& w, double* base, const ilqg_model& m) {
     const int nv = m.nv, nu = m.nu, nb = m.nbody, nj = m.njnt, ng = m.ngeom, nt = coop_nt(m.nv);
     double* p = base;
     auto take = [&](size_t n) { double* r = p; p += n; return r; };
     w.pv = take(nv); w.pu = take(nu);
-    w.cvel = take(6 * nb); w.cacc = take(6 * nb); w.cfrc = take(6 * nb); w.cdofdot = take(6 * nv);
+    {
+        const size_t rne = 18 * (size_t)nb + 6 * (size_t)nv;
+        double* blk = take(rne > (size_t)nt ? rne : (size_t)nt);
+        w.cvel = blk; w.cacc = blk + 6 * nb; w.cfrc = blk + 12 * nb; w.cdofdot = blk + 18 * nb;
+        w.H = blk;   // Newton Hessian: built after the velocity stage has consumed its scratch
+    }
     w.fb = take(nv); w.fs = take(nv); w.as = take(nv); w.fc = take(nv); w.qacc = take(nv); w.warm = take(nv);
     w.Ma = take(nv); w.grad = take(nv); w.search = take(nv); w.Mv = take(nv);
-    w.aref = take(COOP_MAXEFC); w.jar = take(COOP_MAXEFC); w.jv = take(COOP_MAXEFC); w.H = take(nt);
+    w.aref = take(COOP_MAXEFC); w.jar = take(COOP_MAXEFC); w.jv = take(COOP_MAXEFC);
     w.alist = reinterpret_cast<int*>(p);
     // temporaries of the position stage share the same bytes
     p = base;
@@ -153,8 +167,12 @@ DEV double warp_sum(double x) {
 }
 __host__ __device__ constexpr int ptri(int i, int j) { return i * (i + 1) / 2 + j; }   // j <= i
 
+#define COOP_NMAX 32   // lane i owns dof i / row i of the nv x nv matrices
+
 // in-place Cholesky of the packed lower triangle A (n <= 32), left-looking: at column j lane l owns row j + l.
-// The diagonal is left holding 1 / L_jj.
+// The diagonal is left holding 1 / L_jj.  (Measured alternatives that LOST on B200: rows in registers with every loop unrolled
+// — instruction-cache misses, the SM's warps sit at unrelated points of the pipeline; manual 4-way unrolling with split
+// accumulators; Hessian accumulators in registers streaming the active rows.  See profiles/r01_e_*.)
 DEV void coop_chol(double* A, int n, int lane) {
     for (int j = 0; j < n; j++) {
         const int i = j + lane;
@@ -520,7 +538,7 @@ DEV void coop_pos(const GModel* __restrict__ g, CoopMem& w, int lane, const int*
             ne += 4;
         }
     }
-    if (lane == 0) { w.hdr[0] = ne; w.hdr[1] = ok ? 1 : 0; }
+    if (lane == 0) { w.hdr[0] = ne; w.hdr[1] = ok ? 1 : 0; w.hdr[2] = 0; }
     __syncwarp();
 }
 
@@ -591,12 +609,14 @@ DEV void coop_smooth(const GModel* __restrict__ g, CoopMem& w, const double* uu,
     double f = 0;
     if (lane < nv) {
         f = w.fb[lane];
-        for (int a = 0; a < m.nu; a++)
-            if (m.act_dofid[a] == lane) {
-                double c = uu[a];
-                if (m.act_ctrllimited[a]) c = clampd(c, m.act_ctrlrange[a][0], m.act_ctrlrange[a][1]);
-                f += m.act_gear[a] * c;
-            }
+        const int one = g->dof_act[lane];
+        if (one != -1)
+            for (int a = one >= 0 ? one : 0; a < (one >= 0 ? one + 1 : m.nu); a++)
+                if (m.act_dofid[a] == lane) {
+                    double c = uu[a];
+                    if (m.act_ctrllimited[a]) c = clampd(c, m.act_ctrlrange[a][0], m.act_ctrlrange[a][1]);
+                    f += m.act_gear[a] * c;
+                }
         w.fs[lane] = f;
     }
     const double a = coop_chol_solve(w.L, f, nv, lane);
@@ -608,10 +628,29 @@ DEV void coop_smooth(const GModel* __restrict__ g, CoopMem& w, const double* uu,
 struct Mask128 { unsigned w[4]; };
 DEV bool operator==(const Mask128& a, const Mask128& b) { return a.w[0] == b.w[0] && a.w[1] == b.w[1] && a.w[2] == b.w[2] && a.w[3] == b.w[3]; }
 
+// Newton Hessian M + sum_active D_r J_r J_r' (packed) into `H`, then its Cholesky factor in place
+DEV void coop_hessian_factor(const CoopMem& w, double* H, int nv, int na, int lane) {
+    const int nt = coop_nt(nv);
+    for (int e = lane; e < nt; e += 32) {
+        // e -> (i, j), j <= i
+        int i = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+        while (ptri(i + 1, 0) <= e) i++;
+        while (ptri(i, 0) > e) i--;
+        const int j = e - ptri(i, 0);
+        double h = w.M[e];
+        for (int a = 0; a < na; a++) { const double* Jr = w.J + w.alist[a] * nv; h += w.D[w.alist[a]] * Jr[i] * Jr[j]; }
+        H[e] = h;
+    }
+    __syncwarp();
+    coop_chol(H, nv, lane);
+}
+
 // in: private fs, as, aref, warm; out: private qacc (and warm, the next warm start); nv <= 32: lane i owns dof i
-DEV void coop_solve(const GModel* __restrict__ g, CoopMem& w, int maxiter, double tol, int lane, bool need_forces = false) {
+// reuse: take the C-state's cached factor Hc whenever the active set equals the one it was built for (the qvel / ctrl columns
+// of a knot share M, J and D with the centre, so all of their Newton systems with that active set are the same matrix)
+DEV void coop_solve(const GModel* __restrict__ g, CoopMem& w, int maxiter, double tol, int lane, bool need_forces = false, bool reuse = false) {
     const ilqg_model& m = g->m;
-    const int nv = m.nv, ne = w.hdr[0], nt = coop_nt(m.nv);
+    const int nv = m.nv, ne = w.hdr[0];
     static_assert(COOP_MAXEFC <= 128, "mask width");
     if (ne == 0) {
         if (lane < nv) { w.qacc[lane] = w.as[lane]; w.warm[lane] = w.as[lane]; w.fc[lane] = 0; }
@@ -674,19 +713,13 @@ DEV void coop_solve(const GModel* __restrict__ g, CoopMem& w, int maxiter, doubl
         const double grad_i = Ma_i - fs_i - f;
         if (dof) c += 0.5 * (Ma_i - fs_i) * (qacc_i - as_i);
         cost = warp_sum(c);
-        for (int e = lane; e < nt; e += 32) {
-            // e -> (i, j), j <= i
-            int i = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
-            while (ptri(i + 1, 0) <= e) i++;
-            while (ptri(i, 0) > e) i--;
-            const int j = e - ptri(i, 0);
-            double h = w.M[e];
-            for (int a = 0; a < na; a++) { const double* Jr = w.J + w.alist[a] * nv; h += w.D[w.alist[a]] * Jr[i] * Jr[j]; }
-            w.H[e] = h;
-        }
-        __syncwarp();
-        coop_chol(w.H, nv, lane);
-        const double search_i = -coop_chol_solve(w.H, grad_i, nv, lane);
+        const double* Hf = w.H;
+        if (reuse && w.hdr[2] && act.w[0] == (unsigned)w.hdr[4] && act.w[1] == (unsigned)w.hdr[5] && act.w[2] == (unsigned)w.hdr[6] &&
+            act.w[3] == (unsigned)w.hdr[7])
+            Hf = w.Hc;
+        else
+            coop_hessian_factor(w, w.H, nv, na, lane);
+        const double search_i = -coop_chol_solve(Hf, grad_i, nv, lane);
         if (iter > 0) {
             const double gn = warp_sum(dof ? grad_i * grad_i : 0.0);
             if (scale * (old - cost) < tol || scale * sqrt(gn) < tol) break;
@@ -772,7 +805,7 @@ DEV double coop_cost_eval(const ilqg_cost* cost, const double* q, const double* 
 
 // ------------------------------------------------------------------ kernels
 // centre: one warp per knot -> qacc_center, the knot's C-state and candidate pair list in HBM
-__global__ void __launch_bounds__(64) coop_center_kernel(const GModel* __restrict__ g, int nknots, const double* __restrict__ qpos,
+__global__ void __launch_bounds__(32) coop_center_kernel(const GModel* __restrict__ g, int nknots, const double* __restrict__ qpos,
                                                          const double* __restrict__ qvel, const double* __restrict__ ctrl,
                                                          const double* __restrict__ warmstart, int niter, int nwarmup, double slack,
                                                          int cdbl, int pdbl, double* __restrict__ qacc_center, int* __restrict__ status,
@@ -800,6 +833,22 @@ __global__ void __launch_bounds__(64) coop_center_kernel(const GModel* __restric
     bool fin = true;
     for (int i = lane; i < m.nv; i += 32) { qacc_center[(size_t)k * m.nv + i] = w.qacc[i]; w.center[i] = w.qacc[i]; w.fb0[i] = w.fb[i]; fin = fin && isfinite(w.qacc[i]); }
     for (int r = lane; r < w.hdr[0]; r += 32) w.aref0[r] = w.aref[r];
+    {   // the Newton factor at the centre solution: every qvel / ctrl column whose first iterate has this active set reuses it
+        const int ne = w.hdr[0];
+        int na = 0;
+        unsigned mk[4] = {0, 0, 0, 0};
+        for (int r0 = 0; r0 < ne; r0 += 32) {
+            const int r = r0 + lane;
+            const bool a = r < ne && w.jar[r] < 0;
+            const unsigned bal = __ballot_sync(0xffffffffu, a);
+            mk[r0 >> 5] = bal;
+            if (a) w.alist[na + __popc(bal & ((1u << lane) - 1u))] = r;
+            na += __popc(bal);
+        }
+        __syncwarp();
+        if (ne > 0) coop_hessian_factor(w, w.Hc, m.nv, na, lane);
+        if (lane == 0) { w.hdr[2] = ne > 0 ? 1 : 0; w.hdr[4] = (int)mk[0]; w.hdr[5] = (int)mk[1]; w.hdr[6] = (int)mk[2]; w.hdr[7] = (int)mk[3]; }
+    }
     fin = __all_sync(0xffffffffu, fin);
     if (status && lane == 0) status[k] = !ok ? ILQG_ERR_CAPACITY : (fin ? 0 : ILQG_ERR_NONFINITE);
     __syncwarp();
@@ -858,7 +907,7 @@ __global__ void __launch_bounds__(256, 2) coop_velctrl_kernel(const GModel* __re
                 __syncwarp();
             }
             coop_smooth(g, w, w.pu, lane);
-            coop_solve(g, w, niter, 0.0, lane);
+            coop_solve(g, w, niter, 0.0, lane, false, true);
             const double a = lane < nv ? w.qacc[lane] : 0.0;
             if (sgn > 0) plus = a;
             else if (lane < nv) {
@@ -875,7 +924,7 @@ __global__ void __launch_bounds__(256, 2) coop_velctrl_kernel(const GModel* __re
 }
 
 // qpos columns: one warp per (knot, column); +eps then -eps through the full pipeline (narrow phase on the candidates)
-__global__ void __launch_bounds__(64) coop_qpos_kernel(const GModel* __restrict__ g, int nknots, const double* __restrict__ qpos,
+__global__ void __launch_bounds__(32) coop_qpos_kernel(const GModel* __restrict__ g, int nknots, const double* __restrict__ qpos,
                                                        const double* __restrict__ qvel, const double* __restrict__ ctrl,
                                                        const double* __restrict__ qacc_center, const int* __restrict__ cand,
                                                        const ilqg_cost* __restrict__ cost, double eps, int niter, int cdbl, int pdbl,
@@ -938,7 +987,7 @@ __global__ void __launch_bounds__(64) coop_qpos_kernel(const GModel* __restrict_
 }
 
 // mj_forward for n states: one warp per state
-__global__ void __launch_bounds__(64) coop_forward_kernel(const GModel* __restrict__ g, int n, const double* __restrict__ qpos,
+__global__ void __launch_bounds__(32) coop_forward_kernel(const GModel* __restrict__ g, int n, const double* __restrict__ qpos,
                                                           const double* __restrict__ qvel, const double* __restrict__ ctrl,
                                                           double* __restrict__ warmstart, double* __restrict__ qacc_out, int cdbl, int pdbl) {
     extern __shared__ __align__(16) double coop_smem[];
@@ -967,7 +1016,7 @@ __global__ void __launch_bounds__(64) coop_forward_kernel(const GModel* __restri
 }
 
 // nsteps x mj_step for n states (Euler with implicit joint damping; RK4 models use the thread-per-rollout path)
-__global__ void __launch_bounds__(64) coop_step_kernel(const GModel* __restrict__ g, int n, int nsteps, double* __restrict__ qpos,
+__global__ void __launch_bounds__(32) coop_step_kernel(const GModel* __restrict__ g, int n, int nsteps, double* __restrict__ qpos,
                                                        double* __restrict__ qvel, const double* __restrict__ ctrl, double* __restrict__ warmstart,
                                                        double* __restrict__ qacc_out, int cdbl, int pdbl) {
     extern __shared__ __align__(16) double coop_smem[];

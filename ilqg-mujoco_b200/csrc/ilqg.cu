@@ -465,7 +465,7 @@ struct EngineT : Engine {
 // generic warp-per-rollout engine (coop.cuh): any model of the subset, used when no topology instantiation matches
 struct CoopEngine : Engine {
     GModel* d_g = nullptr;
-    int cdbl = 0, pdbl = 0;          // doubles of the C-state / private block of one rollout
+    int cdbl = 0, cfull = 0, pdbl = 0;   // doubles of the core C-state / C-state with the centre's reusable products / private block
     int vc_warps = 1;                // warps per CTA of the qvel/ctrl kernel
     ilqg_model tab;
     double* d_cstate = nullptr;      // [chunk][cdbl]  the centre's position-stage products
@@ -476,11 +476,13 @@ struct CoopEngine : Engine {
     int fd_launches() const override { return 3; }
     ~CoopEngine() override { cudaFree(d_g); cudaFree(d_cstate); cudaFree(d_cand); }
     size_t warp_bytes() const { return (size_t)(cdbl + pdbl) * sizeof(double); }
+    size_t center_bytes() const { return (size_t)(cfull + pdbl) * sizeof(double); }
     cudaError_t init(const ilqg_model& m) {
         GModel* hg = new GModel();
         if (!gmodel_from_tables(m, *hg)) { delete hg; return cudaErrorInvalidValue; }
         tab = m;
-        cdbl = (int)coop_cstate_doubles(m);
+        cdbl = (int)coop_cstate_doubles(m, false);
+        cfull = (int)coop_cstate_doubles(m, true);
         pdbl = (int)coop_priv_doubles(m);
         cudaError_t e = cudaMalloc(&d_g, sizeof(GModel));
         if (e == cudaSuccess) e = cudaMemcpy(d_g, hg, sizeof(GModel), cudaMemcpyHostToDevice);
@@ -490,17 +492,17 @@ struct CoopEngine : Engine {
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&maxblk, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
         cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
-        if (warp_bytes() > (size_t)maxblk) return cudaErrorInvalidValue;
+        if (center_bytes() > (size_t)maxblk) return cudaErrorInvalidValue;
         // qvel/ctrl kernel: as many warps as let two CTAs share an SM (each CTA also pays 1 KB of system shared memory)
-        const size_t cb = (size_t)cdbl * sizeof(double), pb = (size_t)pdbl * sizeof(double);
+        const size_t cb = (size_t)cfull * sizeof(double), pb = (size_t)pdbl * sizeof(double);
         const size_t half = (size_t)maxsm / 2 - 1024;
         int w2 = half > cb ? (int)((half - cb) / pb) : 0;
         int w1 = (int)(((size_t)maxblk - cb) / pb);
         vc_warps = w2 >= 4 ? w2 : w1;
-        if (vc_warps > 8) vc_warps = 8;
+        if (vc_warps > 8) vc_warps = 8;   // __launch_bounds__(256, 2) of coop_velctrl_kernel
         if (vc_warps < 1) return cudaErrorInvalidValue;
         const int one = (int)warp_bytes(), vc = (int)(cb + vc_warps * pb);
-        if ((e = cudaFuncSetAttribute(coop_center_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, one)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(coop_center_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)center_bytes())) != cudaSuccess) return e;
         if ((e = cudaFuncSetAttribute(coop_qpos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, one)) != cudaSuccess) return e;
         if ((e = cudaFuncSetAttribute(coop_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, one)) != cudaSuccess) return e;
         if ((e = cudaFuncSetAttribute(coop_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, one)) != cudaSuccess) return e;
@@ -511,7 +513,7 @@ struct CoopEngine : Engine {
         if (n <= chunk_cap) return cudaSuccess;
         cudaFree(d_cstate); cudaFree(d_cand);
         d_cstate = nullptr; d_cand = nullptr; chunk_cap = 0;
-        cudaError_t e = cudaMalloc(&d_cstate, (size_t)n * cdbl * sizeof(double));
+        cudaError_t e = cudaMalloc(&d_cstate, (size_t)n * cfull * sizeof(double));
         if (e == cudaSuccess) e = cudaMalloc(&d_cand, (size_t)n * (COOP_MAXCAND + 1) * sizeof(int));
         if (e == cudaSuccess) chunk_cap = n;
         return e;
@@ -520,7 +522,7 @@ struct CoopEngine : Engine {
                    const ilqg_fd_opts& o, double* deriv, double* qacc_center, int* status, cudaStream_t s, cudaEvent_t* ev) override {
         if (nknots <= 0) return cudaSuccess;
         const int nq = tab.nq, nv = tab.nv, nu = tab.nu, nd = nv * (2 * nv + nu) + 2 * nv + nu;
-        const size_t one = warp_bytes(), vc = (size_t)cdbl * sizeof(double) + (size_t)vc_warps * pdbl * sizeof(double);
+        const size_t one = warp_bytes(), vc = (size_t)cfull * sizeof(double) + (size_t)vc_warps * pdbl * sizeof(double);
         // a perturbation of eps moves a geom by eps x (lever arm): pairs farther than margin + slack from contact cannot become active
         const double slack = 2000.0 * o.eps;
         cudaError_t e = ensure_scratch(nknots < MAX_CHUNK ? nknots : MAX_CHUNK);
@@ -531,9 +533,9 @@ struct CoopEngine : Engine {
             const double *q = qpos + (size_t)lo * nq, *v = qvel + (size_t)lo * nv, *u = ctrl + (size_t)lo * nu, *w = warm ? warm + (size_t)lo * nv : nullptr;
             double *qc = qacc_center + (size_t)lo * nv, *dv = deriv + (size_t)lo * nd;
             int* st = status ? status + lo : nullptr;
-            coop_center_kernel<<<n, 32, one, s>>>(d_g, n, q, v, u, w, o.niter, o.nwarmup, slack, cdbl, pdbl, qc, st, d_cstate, d_cand);
+            coop_center_kernel<<<n, 32, center_bytes(), s>>>(d_g, n, q, v, u, w, o.niter, o.nwarmup, slack, cfull, pdbl, qc, st, d_cstate, d_cand);
             if (ev && lo == 0) cudaEventRecord(ev[1], s);
-            coop_velctrl_kernel<<<n, vc_warps * 32, vc, s>>>(d_g, n, d_cstate, cost_dev, o.eps, o.niter, cdbl, pdbl, dv, st);
+            coop_velctrl_kernel<<<n, vc_warps * 32, vc, s>>>(d_g, n, d_cstate, cost_dev, o.eps, o.niter, cfull, pdbl, dv, st);
             if (ev && lo == 0) cudaEventRecord(ev[3], s);
             coop_qpos_kernel<<<(unsigned)((long)n * nv), 32, one, s>>>(d_g, n, q, v, u, qc, d_cand, cost_dev, o.eps, o.niter, cdbl, pdbl, dv, st);
         }

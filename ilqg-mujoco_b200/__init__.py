@@ -193,6 +193,40 @@ class Handle:
                                             C.byref(opts) if opts is not None else None, _dp(deriv), _dp(qacc), _dp(status),
                                             C.c_void_p(stream) if stream else None))
 
+    def fd_batch_dev_scatter(self, qpos, qvel, ctrl, warm, dst_ptrs, qacc=None, status=None, cost=None, opts=None, stream=None):
+        """FD of a knot range with the deriv blocks stored to every pointer of `dst_ptrs` (ints: device addresses of this
+        range's first block in each destination, local or peer-mapped) — ilqg_fd_batch_dev_scatter."""
+        n = qpos.shape[0]
+        arr = (C.c_void_p * len(dst_ptrs))(*[C.c_void_p(int(p)) for p in dst_ptrs])
+        self._check(lib().ilqg_fd_batch_dev_scatter(self._h, n, _dp(qpos), _dp(qvel), _dp(ctrl), _dp(warm), _hp(cost),
+                                                    C.byref(opts) if opts is not None else None, arr, len(dst_ptrs), _dp(qacc), _dp(status),
+                                                    C.c_void_p(stream) if stream else None))
+
+    # ---- peer-visible buffers (CUDA IPC) ---------------------------------------------------
+    def peer_alloc(self, nbytes):
+        ptr, hd = C.c_void_p(), (C.c_ubyte * 64)()
+        self._check(lib().ilqg_peer_alloc(self._h, C.c_size_t(nbytes), C.byref(ptr), hd))
+        return int(ptr.value), bytes(hd)
+
+    def peer_open(self, handle_bytes):
+        ptr = C.c_void_p()
+        hd = (C.c_ubyte * 64).from_buffer_copy(handle_bytes)
+        self._check(lib().ilqg_peer_open(self._h, hd, C.byref(ptr)))
+        return int(ptr.value)
+
+    def peer_barrier(self, flag_ptrs, rank, epoch, stream=None):
+        arr = (C.c_void_p * len(flag_ptrs))(*[C.c_void_p(int(p)) for p in flag_ptrs])
+        self._check(lib().ilqg_peer_barrier(self._h, arr, len(flag_ptrs), int(rank), int(epoch), C.c_void_p(stream) if stream else None))
+
+    def peer_barrier_timed_out(self):
+        return bool(lib().ilqg_peer_barrier_timed_out(self._h))
+
+    def peer_close(self, ptr):
+        self._check(lib().ilqg_peer_close(self._h, C.c_void_p(ptr)))
+
+    def peer_free(self, ptr):
+        self._check(lib().ilqg_peer_free(self._h, C.c_void_p(ptr)))
+
     def step_batch_dev(self, qpos, qvel, ctrl, warm, qacc=None, nsteps=1, stream=None):
         n = qpos.shape[0]
         self._check(lib().ilqg_step_batch_dev(self._h, n, int(nsteps), _dp(qpos), _dp(qvel), _dp(ctrl), _dp(warm), _dp(qacc),

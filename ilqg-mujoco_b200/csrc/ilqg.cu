@@ -66,6 +66,14 @@ __global__ void __launch_bounds__(128) fd_center_kernel(const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------ FD: perturbed evaluations
+// Destinations of the deriv blocks.  n = 1: the caller's buffer.  n > 1: the same block is stored to every destination —
+// the copies of a knot-sharded horizon's deriv array on the peer GPUs (mapped over NVLink with CUDA IPC), so that the
+// all-gather of SURVEY 8(e) happens in the FD kernels' write-out instead of a separate collective.
+struct FdDst {
+    double* p[ILQG_MAX_PEERS];
+    int n;
+};
+
 template <class T>
 struct FdShape {
     static constexpr int NV = T::NV, NU = T::NU;
@@ -82,7 +90,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINBLOCKS) fd_perturb_kernel(const
                                                                  const double* __restrict__ qpos, const double* __restrict__ qvel,
                                                                  const double* __restrict__ ctrl, const double* __restrict__ qacc_center,
                                                                  const ilqg_cost* __restrict__ cost, double eps, int niter,
-                                                                 double* __restrict__ deriv, int* __restrict__ status) {
+                                                                 const FdDst dst, int* __restrict__ status) {
     using S = FdShape<T>;
     constexpr int NV = T::NV, NU = T::NU, NQ = T::NQ;
     __shared__ double stage[WARPS][S::KPW * S::ND];
@@ -156,12 +164,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINBLOCKS) fd_perturb_kernel(const
     if (nk > S::KPW) nk = S::KPW;
     if (nk > 0) {
         const int per = cost ? S::ND : S::NJAC;  // without a device cost the gradient entries stay untouched
-        double* out = deriv + (size_t)k0 * S::ND;
-        if (per == S::ND) {
-            for (int e = lane; e < nk * S::ND; e += 32) out[e] = stage[wib][e];
-        } else {
-            for (int kk = 0; kk < nk; kk++)
-                for (int e = lane; e < per; e += 32) out[kk * S::ND + e] = stage[wib][kk * S::ND + e];
+        for (int d = 0; d < dst.n; d++) {
+            double* out = dst.p[d] + (size_t)k0 * S::ND;
+            if (per == S::ND) {
+                for (int e = lane; e < nk * S::ND; e += 32) out[e] = stage[wib][e];
+            } else {
+                for (int kk = 0; kk < nk; kk++)
+                    for (int e = lane; e < per; e += 32) out[kk * S::ND + e] = stage[wib][kk * S::ND + e];
+            }
         }
     }
 }
@@ -196,7 +206,7 @@ template <class T, bool SYNC>
 __global__ void __launch_bounds__(256, 1) fd_velctrl_kernel(const __grid_constant__ DevModel<T> m, int nknots, const double* __restrict__ qpos,
                                                             const double* __restrict__ qvel, const double* __restrict__ ctrl,
                                                             const double* __restrict__ qacc_center, const ilqg_cost* __restrict__ cost,
-                                                            double eps, int niter, double* __restrict__ deriv, int* __restrict__ status) {
+                                                            double eps, int niter, const FdDst dst, int* __restrict__ status) {
     using S = FdSplit<T>;
     constexpr int NV = T::NV, NU = T::NU, NQ = T::NQ, GK = S::GK;
     __shared__ double stage[S::KPC_VU * S::STG_VU];
@@ -247,12 +257,14 @@ __global__ void __launch_bounds__(256, 1) fd_velctrl_kernel(const __grid_constan
     if (nk > S::KPC_VU) nk = S::KPC_VU;
     for (int e = threadIdx.x; e < nk * S::SEG_VU; e += blockDim.x) {
         const int kn = e / S::SEG_VU, off = e - kn * S::SEG_VU;
-        deriv[(size_t)(k0 + kn) * S::ND + NV * NV + off] = stage[kn * S::STG_VU + off];
+        const double val = stage[kn * S::STG_VU + off];
+        for (int d = 0; d < dst.n; d++) dst.p[d][(size_t)(k0 + kn) * S::ND + NV * NV + off] = val;
     }
     if (cost)   // without a device cost the gradient entries stay untouched
         for (int e = threadIdx.x; e < nk * (NV + NU); e += blockDim.x) {
             const int kn = e / (NV + NU), off = e - kn * (NV + NU);
-            deriv[(size_t)(k0 + kn) * S::ND + S::NJAC + NV + off] = stage[kn * S::STG_VU + S::SEG_VU + off];
+            const double val = stage[kn * S::STG_VU + S::SEG_VU + off];
+            for (int d = 0; d < dst.n; d++) dst.p[d][(size_t)(k0 + kn) * S::ND + S::NJAC + NV + off] = val;
         }
 }
 
@@ -260,7 +272,7 @@ template <class T, bool SYNC>
 __global__ void __launch_bounds__(256, 1) fd_qpos_kernel(const __grid_constant__ DevModel<T> m, int nknots, const double* __restrict__ qpos,
                                                          const double* __restrict__ qvel, const double* __restrict__ ctrl,
                                                          const double* __restrict__ qacc_center, const ilqg_cost* __restrict__ cost,
-                                                         double eps, int niter, double* __restrict__ deriv, int* __restrict__ status) {
+                                                         double eps, int niter, const FdDst dst, int* __restrict__ status) {
     using S = FdSplit<T>;
     constexpr int NV = T::NV, NU = T::NU, NQ = T::NQ, G = 2 * NV;
     __shared__ double stage[S::KPC_Q * S::STG_Q];
@@ -312,12 +324,14 @@ __global__ void __launch_bounds__(256, 1) fd_qpos_kernel(const __grid_constant__
     if (nk > S::KPC_Q) nk = S::KPC_Q;
     for (int e = threadIdx.x; e < nk * S::SEG_Q; e += blockDim.x) {
         const int kn = e / S::SEG_Q, off = e - kn * S::SEG_Q;
-        deriv[(size_t)(k0 + kn) * S::ND + off] = stage[kn * S::STG_Q + off];
+        const double val = stage[kn * S::STG_Q + off];
+        for (int d = 0; d < dst.n; d++) dst.p[d][(size_t)(k0 + kn) * S::ND + off] = val;
     }
     if (cost)
         for (int e = threadIdx.x; e < nk * NV; e += blockDim.x) {
             const int kn = e / NV, off = e - kn * NV;
-            deriv[(size_t)(k0 + kn) * S::ND + S::NJAC + off] = stage[kn * S::STG_Q + S::SEG_Q + off];
+            const double val = stage[kn * S::STG_Q + S::SEG_Q + off];
+            for (int d = 0; d < dst.n; d++) dst.p[d][(size_t)(k0 + kn) * S::ND + S::NJAC + off] = val;
         }
 }
 
@@ -389,12 +403,12 @@ struct IlqrLaunch<T, true> {
 
 // ------------------------------------------------------------------ engines (one per compiled-in topology)
 struct Engine {
-    int fd_variant = 3;
+    int fd_variant = -1;   // -1: chosen per call by batch size (ILQG_FD_VARIANT overrides)
     virtual ~Engine() {}
     virtual int fd_launches() const { return 2; }
     virtual const char* name() const = 0;
     virtual cudaError_t fd(int nknots, const double* qpos, const double* qvel, const double* ctrl, const double* warm,
-                           const ilqg_cost* cost_dev, const ilqg_fd_opts& o, double* deriv, double* qacc_center, int* status,
+                           const ilqg_cost* cost_dev, const ilqg_fd_opts& o, const FdDst& dst, double* qacc_center, int* status,
                            cudaStream_t s, cudaEvent_t* ev) = 0;
     virtual cudaError_t forward(int n, const double* qpos, const double* qvel, const double* ctrl, double* warm, double* qacc,
                                 cudaStream_t s) = 0;
@@ -411,32 +425,37 @@ template <class T>
 struct EngineT : Engine {
     DevModel<T> dm;
     const char* name() const override { return T::NAME; }
-    int fd_launches() const override { return fd_variant >= 3 ? 3 : 2; }
+    int fd_launches() const override { return last_launches; }
+    int last_launches = 3;
     cudaError_t fd(int nknots, const double* qpos, const double* qvel, const double* ctrl, const double* warm, const ilqg_cost* cost_dev,
-                   const ilqg_fd_opts& o, double* deriv, double* qacc_center, int* status, cudaStream_t s, cudaEvent_t* ev) override {
+                   const ilqg_fd_opts& o, const FdDst& dst, double* qacc_center, int* status, cudaStream_t s, cudaEvent_t* ev) override {
         using S = FdShape<T>;
+        // variant: 3 = stage-skipping split (fewest instructions: best once its qvel/ctrl kernel fills the GPU), 2 = one thread per
+        // perturbed evaluation in a single launch (30x more threads per knot: lower latency for small batches), -1 = by size
+        const int variant = fd_variant >= 0 ? fd_variant : (nknots >= 16384 ? 3 : 2);
+        last_launches = variant >= 3 ? 3 : 2;
         constexpr int WARPS = 4;
         if (nknots <= 0) return cudaSuccess;
         if (ev) cudaEventRecord(ev[0], s);
         fd_center_kernel<T><<<(nknots + 127) / 128, 128, 0, s>>>(dm, nknots, qpos, qvel, ctrl, warm, o.niter, o.nwarmup, qacc_center, status);
         if (ev) cudaEventRecord(ev[1], s);
-        if (fd_variant >= 3) {  // stage-skipping split: qvel/ctrl columns, then qpos columns
+        if (variant >= 3) {  // stage-skipping split: qvel/ctrl columns, then qpos columns
             using P = FdSplit<T>;
             fd_velctrl_kernel<T, true><<<(nknots + P::KPC_VU - 1) / P::KPC_VU, P::THREADS, 0, s>>>(dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev,
-                                                                                                 o.eps, o.niter, deriv, status);
+                                                                                                 o.eps, o.niter, dst, status);
             if (ev) cudaEventRecord(ev[3], s);
             fd_qpos_kernel<T, true><<<(nknots + P::KPC_Q - 1) / P::KPC_Q, P::THREADS, 0, s>>>(dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps,
-                                                                                            o.niter, deriv, status);
+                                                                                            o.niter, dst, status);
             if (ev) cudaEventRecord(ev[2], s);
             return cudaGetLastError();
         }
         if (ev) cudaEventRecord(ev[3], s);
         int nwarps = (nknots + S::KPW - 1) / S::KPW;
         dim3 grid((nwarps + WARPS - 1) / WARPS), block(WARPS * 32);
-        switch (fd_variant) {  // experiment switch (ILQG_FD_VARIANT): 0 = 4 warps x 2 CTAs/SM, no stage barriers; 1 = with barriers; 2 = 8 warps x 1 CTA with barriers
-            case 0: fd_perturb_kernel<T, 4, 2, false><<<grid, block, 0, s>>>(dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps, o.niter, deriv, status); break;
-            case 2: fd_perturb_kernel<T, 8, 1, true><<<dim3((nwarps + 7) / 8), dim3(256), 0, s>>>(dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps, o.niter, deriv, status); break;
-            default: fd_perturb_kernel<T, 4, 2, true><<<grid, block, 0, s>>>(dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps, o.niter, deriv, status); break;
+        switch (variant) {  // experiment switch (ILQG_FD_VARIANT): 0 = 4 warps x 2 CTAs/SM, no stage barriers; 1 = with barriers; 2 = 8 warps x 1 CTA with barriers
+            case 0: fd_perturb_kernel<T, 4, 2, false><<<grid, block, 0, s>>>(dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps, o.niter, dst, status); break;
+            case 2: fd_perturb_kernel<T, 8, 1, true><<<dim3((nwarps + 7) / 8), dim3(256), 0, s>>>(dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps, o.niter, dst, status); break;
+            default: fd_perturb_kernel<T, 4, 2, true><<<grid, block, 0, s>>>(dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps, o.niter, dst, status); break;
         }
         if (ev) cudaEventRecord(ev[2], s);
         return cudaGetLastError();
@@ -519,8 +538,10 @@ struct CoopEngine : Engine {
         return e;
     }
     cudaError_t fd(int nknots, const double* qpos, const double* qvel, const double* ctrl, const double* warm, const ilqg_cost* cost_dev,
-                   const ilqg_fd_opts& o, double* deriv, double* qacc_center, int* status, cudaStream_t s, cudaEvent_t* ev) override {
+                   const ilqg_fd_opts& o, const FdDst& dst, double* qacc_center, int* status, cudaStream_t s, cudaEvent_t* ev) override {
         if (nknots <= 0) return cudaSuccess;
+        if (dst.n > 1) return cudaErrorNotSupported;   // peer scatter is wired into the thread-per-rollout kernels only
+        double* deriv = dst.p[0];
         const int nq = tab.nq, nv = tab.nv, nu = tab.nu, nd = nv * (2 * nv + nu) + 2 * nv + nu;
         const size_t one = warp_bytes(), vc = (size_t)cfull * sizeof(double) + (size_t)vc_warps * pdbl * sizeof(double);
         // a perturbation of eps moves a geom by eps x (lever arm): pairs farther than margin + slack from contact cannot become active
@@ -577,6 +598,32 @@ static Engine* make_engine(const ilqg_model& m) {
     return nullptr;
 }
 
+// ------------------------------------------------------------------ node-wide barrier through peer memory
+// After a rank's FD kernels have stored their blocks into every peer's array, the ranks only need to know that everybody
+// is done.  One warp: lane r release-stores this pass's epoch into slot [rank] of rank r's flag array (over NVLink for the
+// peers), then acquire-spins on slot [r] of its own array.  Stream order + the system-scope release make the preceding
+// kernels' peer stores visible before the flag.  Each rank runs on its own GPU, so all barrier kernels are co-resident;
+// the spin is bounded (about 2 s) and reports a timeout instead of hanging the device.
+struct PeerFlags {
+    int* p[ILQG_MAX_PEERS];
+};
+__global__ void peer_barrier_kernel(const PeerFlags f, int nranks, int rank, int epoch, int* __restrict__ timed_out) {
+    const int r = threadIdx.x;
+    if (r >= nranks) return;
+    __threadfence_system();
+    int* dst = f.p[r] + rank;
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(dst), "r"(epoch) : "memory");
+    const int* mine = f.p[rank] + r;
+    const long long t0 = clock64();
+    for (;;) {
+        int seen;
+        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
+        if (seen - epoch >= 0) break;
+        if (clock64() - t0 > 4000000000LL) { *timed_out = 1; break; }
+        __nanosleep(100);
+    }
+}
+
 // ------------------------------------------------------------------ fp64 pipe peak (roofline denominator)
 // MEASURED_PEAKS.json carries no fp64 figure, so bench.py measures one: register-resident DFMA chains,
 // 16 independent accumulators per thread, every SM busy.
@@ -605,6 +652,7 @@ struct ilqg_handle_s {
     // scratch owned by the handle (grown on demand)
     double* d_center = nullptr; size_t center_cap = 0;
     ilqg_cost* d_cost = nullptr;
+    int* d_timeout = nullptr;  // set by a peer barrier that gave up waiting
     // staging for the *_host entry points
     void* d_stage = nullptr; size_t stage_cap = 0;
     long launches = 0;  // kernels launched through this handle (bench.py reports it)
@@ -674,6 +722,7 @@ int ilqg_destroy(ilqg_handle h) {
     cudaSetDevice(h->device);
     cudaFree(h->d_center);
     cudaFree(h->d_cost);
+    cudaFree(h->d_timeout);
     cudaFree(h->d_stage);
     for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i < 3; i++) if (h->pipe[i]) cudaStreamDestroy(h->pipe[i]);
@@ -761,7 +810,7 @@ static int ensure_stage(ilqg_handle h, size_t bytes) {
 
 // launch the two FD kernels; `dcost` is a DEVICE pointer (or NULL)
 static int fd_launch(ilqg_handle h, int nknots, const double* qpos, const double* qvel, const double* ctrl, const double* warmstart,
-                     const ilqg_cost* dcost, const ilqg_fd_opts* opts, double* deriv, double* qacc_out, int* status, cudaStream_t s) {
+                     const ilqg_cost* dcost, const ilqg_fd_opts* opts, const ilqg::FdDst& dst, double* qacc_out, int* status, cudaStream_t s) {
     ilqg_fd_opts o;
     ilqg_fd_opts_default(&o);
     if (opts) o = *opts;
@@ -772,7 +821,7 @@ static int fd_launch(ilqg_handle h, int nknots, const double* qpos, const double
         if (rc) return rc;
         center = h->d_center;
     }
-    CU(h, h->eng->fd(nknots, qpos, qvel, ctrl, warmstart, dcost, o, deriv, center, status, s, h->profiling ? h->ev : nullptr));
+    CU(h, h->eng->fd(nknots, qpos, qvel, ctrl, warmstart, dcost, o, dst, center, status, s, h->profiling ? h->ev : nullptr));
     h->launches += h->eng->fd_launches();
     return ILQG_OK;
 }
@@ -789,7 +838,97 @@ int ilqg_fd_batch_dev(ilqg_handle h, int nknots, const double* qpos, const doubl
         CU(h, cudaMemcpyAsync(h->d_cost, cost, sizeof(ilqg_cost), cudaMemcpyHostToDevice, s));
         dcost = h->d_cost;
     }
-    return fd_launch(h, nknots, qpos, qvel, ctrl, warmstart, dcost, opts, deriv, qacc_out, status, s);
+    ilqg::FdDst dst{};
+    dst.p[0] = deriv;
+    dst.n = 1;
+    return fd_launch(h, nknots, qpos, qvel, ctrl, warmstart, dcost, opts, dst, qacc_out, status, s);
+}
+
+// The same linearisation with the deriv blocks stored to `ndst` destinations at once (each dsts[i] points at the slot of knot 0 of
+// this call in destination i).  Destinations may live on peer GPUs (ilqg_peer_open): the kernels' write-out then IS the gather.
+int ilqg_fd_batch_dev_scatter(ilqg_handle h, int nknots, const double* qpos, const double* qvel, const double* ctrl, const double* warmstart,
+                              const ilqg_cost* cost, const ilqg_fd_opts* opts, double* const* dsts, int ndst, double* qacc_out, int* status,
+                              void* stream) {
+    if (!h) return ILQG_ERR_ARG;
+    if (nknots < 0 || ndst < 1 || ndst > ILQG_MAX_PEERS || !dsts || (nknots > 0 && (!qpos || !qvel || (h->model.nu > 0 && !ctrl))))
+        return fail(h, ILQG_ERR_ARG, "bad argument");
+    if (nknots == 0) return ILQG_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(h, cudaSetDevice(h->device));
+    const ilqg_cost* dcost = nullptr;
+    if (cost) {
+        CU(h, cudaMemcpyAsync(h->d_cost, cost, sizeof(ilqg_cost), cudaMemcpyHostToDevice, s));
+        dcost = h->d_cost;
+    }
+    ilqg::FdDst dst{};
+    for (int i = 0; i < ndst; i++) {
+        if (!dsts[i]) return fail(h, ILQG_ERR_ARG, "null destination");
+        dst.p[i] = dsts[i];
+    }
+    dst.n = ndst;
+    return fd_launch(h, nknots, qpos, qvel, ctrl, warmstart, dcost, opts, dst, qacc_out, status, s);
+}
+
+// ---- peer-visible device buffers (CUDA IPC): one per rank, opened by every other rank of the node
+int ilqg_peer_alloc(ilqg_handle h, size_t bytes, void** dev_ptr, unsigned char* ipc_handle /* ILQG_IPC_HANDLE_BYTES */) {
+    if (!h || !dev_ptr || !ipc_handle || bytes == 0) return ILQG_ERR_ARG;
+    CU(h, cudaSetDevice(h->device));
+    void* p = nullptr;
+    CU(h, cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t hd;
+    cudaError_t e = cudaIpcGetMemHandle(&hd, p);
+    if (e != cudaSuccess) { cudaFree(p); return cuda_fail(h, e, "cudaIpcGetMemHandle"); }
+    static_assert(sizeof(cudaIpcMemHandle_t) == ILQG_IPC_HANDLE_BYTES, "IPC handle size");
+    memcpy(ipc_handle, &hd, sizeof(hd));
+    CU(h, cudaMemset(p, 0, bytes));
+    *dev_ptr = p;
+    return ILQG_OK;
+}
+int ilqg_peer_open(ilqg_handle h, const unsigned char* ipc_handle, void** dev_ptr) {
+    if (!h || !dev_ptr || !ipc_handle) return ILQG_ERR_ARG;
+    CU(h, cudaSetDevice(h->device));
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, ipc_handle, sizeof(hd));
+    CU(h, cudaIpcOpenMemHandle(dev_ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+    return ILQG_OK;
+}
+int ilqg_peer_close(ilqg_handle h, void* dev_ptr) {
+    if (!h || !dev_ptr) return ILQG_ERR_ARG;
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaIpcCloseMemHandle(dev_ptr));
+    return ILQG_OK;
+}
+// barrier over the ranks of a node: flags[r] = rank r's flag array (ILQG_MAX_PEERS ints, zero-initialised, own or peer-mapped);
+// epoch must increase by one per call on every rank.  Asynchronous on `stream`; ilqg_peer_barrier_timed_out reports a lost peer.
+int ilqg_peer_barrier(ilqg_handle h, int* const* flags, int nranks, int rank, int epoch, void* stream) {
+    if (!h || !flags || nranks < 1 || nranks > ILQG_MAX_PEERS || rank < 0 || rank >= nranks) return ILQG_ERR_ARG;
+    CU(h, cudaSetDevice(h->device));
+    if (!h->d_timeout) {
+        CU(h, cudaMalloc(&h->d_timeout, sizeof(int)));
+        CU(h, cudaMemset(h->d_timeout, 0, sizeof(int)));
+    }
+    ilqg::PeerFlags f{};
+    for (int r = 0; r < nranks; r++) {
+        if (!flags[r]) return fail(h, ILQG_ERR_ARG, "null flag array");
+        f.p[r] = flags[r];
+    }
+    ilqg::peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(f, nranks, rank, epoch, h->d_timeout);
+    CU(h, cudaGetLastError());
+    h->launches += 1;
+    return ILQG_OK;
+}
+int ilqg_peer_barrier_timed_out(ilqg_handle h) {   // synchronises the device
+    if (!h || !h->d_timeout) return 0;
+    int v = 0;
+    cudaSetDevice(h->device);
+    if (cudaMemcpy(&v, h->d_timeout, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+    return v;
+}
+int ilqg_peer_free(ilqg_handle h, void* dev_ptr) {
+    if (!h || !dev_ptr) return ILQG_ERR_ARG;
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaFree(dev_ptr));
+    return ILQG_OK;
 }
 
 int ilqg_fd_batch_host(ilqg_handle h, int nknots, const double* qpos, const double* qvel, const double* ctrl, const double* warmstart,
@@ -830,8 +969,11 @@ int ilqg_fd_batch_host(ilqg_handle h, int nknots, const double* qpos, const doub
         else CU(h, cudaMemsetAsync(b + off_w + lo * nv, 0, cn * nv * sizeof(double), s));
         if (!cost)  // keep the caller's cost-gradient entries
             CU(h, cudaMemcpyAsync(b + off_d + lo * nd, deriv + lo * nd, cn * nd * sizeof(double), cudaMemcpyHostToDevice, s));
-        rc = fd_launch(h, (int)cn, b + off_q + lo * nq, b + off_v + lo * nv, b + off_u + lo * nu, b + off_w + lo * nv, dcost, opts,
-                       b + off_d + lo * nd, b + off_a + lo * nv, dstat + lo, s);
+        ilqg::FdDst dst{};
+        dst.p[0] = b + off_d + lo * nd;
+        dst.n = 1;
+        rc = fd_launch(h, (int)cn, b + off_q + lo * nq, b + off_v + lo * nv, b + off_u + lo * nu, b + off_w + lo * nv, dcost, opts, dst,
+                       b + off_a + lo * nv, dstat + lo, s);
         if (rc) return rc;
         CU(h, cudaMemcpyAsync(deriv + lo * nd, b + off_d + lo * nd, cn * nd * sizeof(double), cudaMemcpyDeviceToHost, s));
         if (qacc_out) CU(h, cudaMemcpyAsync(qacc_out + lo * nv, b + off_a + lo * nv, cn * nv * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -1055,7 +1197,10 @@ int ilqg_ilqr_linearise(ilqg_ilqr w, void* stream) {                     // FD a
     const int nknots = (b.N + 1) * b.ninst;
     int rc = ensure_center(h, (size_t)nknots * h->model.nv);
     if (rc) return rc;
-    CU(h, h->eng->fd(nknots, b.nom_q, b.nom_v, b.nom_u, b.nom_w, w->host_cost ? nullptr : w->d_cost, w->fd, b.deriv, h->d_center, nullptr, s, nullptr));
+    ilqg::FdDst dst{};
+    dst.p[0] = b.deriv;
+    dst.n = 1;
+    CU(h, h->eng->fd(nknots, b.nom_q, b.nom_v, b.nom_u, b.nom_w, w->host_cost ? nullptr : w->d_cost, w->fd, dst, h->d_center, nullptr, s, nullptr));
     h->launches += h->eng->fd_launches();
     return ILQG_OK;
 }

@@ -48,6 +48,65 @@ def fd_knot_sharded(compute_fn, qpos, qvel, ctrl, warm, nd, group=None):
     return full[:T]
 
 
+class _DevArray:
+    """Expose a raw device allocation to torch through __cuda_array_interface__ (no copy)."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (int(ptr), False), "version": 3, "strides": None}
+
+
+class PeerDeriv:
+    """One deriv[T, nd] array per rank, each mapped into every other rank of the node with CUDA IPC, so that the FD kernels
+    of a knot-sharded horizon store their blocks straight into all copies (ilqg_fd_batch_dev_scatter): the all-gather of
+    SURVEY 8(e) rides in the kernels' write-out over NVLink instead of following them as a separate collective."""
+
+    def __init__(self, handle, T, nd, group=None):
+        self.h, self.T, self.nd, self.group = handle, int(T), int(nd), group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.flag_off = self.T * self.nd * 8           # the barrier's flag array sits behind the blocks (zero-initialised)
+        self.epoch = 0
+        self.own, hd = handle.peer_alloc(self.flag_off + 256)
+        handles = [hd]
+        if self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, hd, group=group)
+        self.ptrs = [self.own if r == self.rank else handle.peer_open(handles[r]) for r in range(self.world)]
+        self.full = torch.as_tensor(_DevArray(self.own, (self.T, self.nd)), device=f"cuda:{torch.cuda.current_device()}")
+
+    def scatter_ptrs(self, first_knot):
+        """Destination addresses of knot `first_knot` in every rank's copy, this rank's first."""
+        order = [self.rank] + [r for r in range(self.world) if r != self.rank]
+        return [self.ptrs[r] + first_knot * self.nd * 8 for r in order]
+
+    def barrier(self, stream=None):
+        """Every rank's preceding kernels (and their peer stores) are complete and visible once this returns on the stream."""
+        self.epoch += 1
+        self.h.peer_barrier([p + self.flag_off for p in self.ptrs], self.rank, self.epoch, stream=stream)
+
+    def close(self):
+        if self.world > 1:
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)      # nobody unmaps while a peer may still be storing
+        for r, p in enumerate(self.ptrs):
+            if r != self.rank:
+                self.h.peer_close(p)
+        self.full = None
+        self.h.peer_free(self.own)
+
+
+def fd_knot_sharded_peer(handle, peer, qpos, qvel, ctrl, warm, cost=None, stream=None):
+    """FD linearisation of one long trajectory, knots sharded over the ranks, blocks stored by the kernels into every
+    rank's `peer.full`.  Returns peer.full (all T blocks, knot order) once every rank's kernels have finished."""
+    T = qpos.shape[0]
+    lo, hi = shard_range(T, peer.world, peer.rank)
+    if hi > lo:
+        handle.fd_batch_dev_scatter(qpos[lo:hi], qvel[lo:hi], ctrl[lo:hi], warm[lo:hi], peer.scatter_ptrs(lo), cost=cost, stream=stream)
+    if peer.world > 1:
+        peer.barrier(stream=stream)   # a 1-warp kernel per rank exchanging flags through peer memory: no NCCL call on this path
+    return peer.full
+
+
 def gather_results(local, n_total, group=None):
     """Optional final gather of small per-instance results (first control, cost) from instance-sharded ranks."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1

@@ -26,6 +26,8 @@
 #ifndef ILQG_B200_H
 #define ILQG_B200_H
 
+#include <stddef.h>
+
 #include "ilqg_model.h"
 
 #ifdef __cplusplus
@@ -98,6 +100,31 @@ int ilqg_fd_batch_dev(ilqg_handle h, int nknots, const double* qpos, const doubl
 int ilqg_fd_batch_host(ilqg_handle h, int nknots, const double* qpos, const double* qvel, const double* ctrl,
                        const double* warmstart, const ilqg_cost* cost, const ilqg_fd_opts* opts, double* deriv,
                        double* qacc_out, int* status);
+
+/* ---- multi-GPU: the knots of ONE long horizon sharded over the GPUs of a node (BASELINE configs[4]).
+ * The reference computes the knots' derivatives one after the other inside ILQR::backwardPass
+ * (/root/reference/inc/ilqr.h:144-154); FD at knot n reads only knot n's inputs (/root/reference/src/mjderivative.cpp:61,72),
+ * so ranks take contiguous knot ranges.  Instead of an all-gather after the kernels, ilqg_fd_batch_dev_scatter lets the
+ * FD kernels' write-out store every deriv block to `ndst` destinations at once: this rank's copy of the horizon's deriv
+ * array and the peers' copies, mapped into this process with CUDA IPC (stores travel over NVLink / NVSwitch).
+ *   ilqg_peer_alloc   cudaMalloc a peer-visible buffer on the handle's GPU and export its IPC handle (64 bytes)
+ *   ilqg_peer_open    map another rank's buffer (same node) into this process; ilqg_peer_close unmaps it
+ *   dsts[i]           device pointer to where THIS call's knot 0 goes in destination i (base + first_knot * ND doubles)
+ * Completion is stream-ordered per rank; ranks need one barrier (ilqg_peer_barrier, or any other) before reading blocks
+ * written by their peers. */
+#define ILQG_MAX_PEERS 8
+#define ILQG_IPC_HANDLE_BYTES 64
+int ilqg_peer_alloc(ilqg_handle h, size_t bytes, void** dev_ptr, unsigned char* ipc_handle);
+int ilqg_peer_open(ilqg_handle h, const unsigned char* ipc_handle, void** dev_ptr);
+int ilqg_peer_close(ilqg_handle h, void* dev_ptr);
+int ilqg_peer_free(ilqg_handle h, void* dev_ptr);
+/* node-wide barrier through peer memory (one 1-warp kernel per rank, no NCCL call): flags[r] = rank r's flag array
+ * (ILQG_MAX_PEERS zero-initialised ints inside a peer buffer); epoch increases by one per call on every rank. */
+int ilqg_peer_barrier(ilqg_handle h, int* const* flags, int nranks, int rank, int epoch, void* stream);
+int ilqg_peer_barrier_timed_out(ilqg_handle h);
+int ilqg_fd_batch_dev_scatter(ilqg_handle h, int nknots, const double* qpos, const double* qvel, const double* ctrl,
+                              const double* warmstart, const ilqg_cost* cost, const ilqg_fd_opts* opts, double* const* dsts,
+                              int ndst, double* qacc_out, int* status, void* stream);
 
 /* ---- forward dynamics / stepping of n independent states.
  * ilqg_forward_*: mj_forward (/root/reference/src/mjderivative.cpp:64): qacc[n*nv] out; warmstart in/out.

@@ -173,3 +173,32 @@ def test_full_size_properties(handles, pkg):
     err = (a1 - a0 - pred).abs().max(dim=1).values / (1 + (a1 - a0).abs().max(dim=1).values)
     # contact knots are piecewise linear: allow the few whose active set changes under the 1e-3 step
     assert float(err.median()) < 1e-6 and float((err < 1e-4).double().mean()) > 0.9
+
+
+@pytest.mark.parametrize("variant", ["2", "3"])
+@pytest.mark.parametrize("name,n,roll", [("inverted_pendulum", 300, 10), ("hopper", 271, 150), ("hopper", 85, 0), ("hopper", 1, 200)])
+def test_both_fd_kernel_variants(pkg, oracle, omodels, variant, name, n, roll):
+    """The per-call choice between the single-launch kernel (variant 2: one thread per perturbed evaluation) and the
+    stage-skipping split (variant 3: fd_velctrl_kernel + fd_qpos_kernel) depends on the batch size; both must meet the
+    same tolerance on the same inputs, including ragged tails (n not a multiple of the knots a CTA owns: 85 / 21 hopper)."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    os.environ["ILQG_FD_VARIANT"] = variant
+    try:
+        h = pkg.Handle(pkg.Model.named(name), 0)
+    finally:
+        del os.environ["ILQG_FD_VARIANT"]
+    m = h.model; om = omodels[name]
+    q, v, u, w = scenario_states(name, n, seed=900 + roll, oracle=oracle, om=om, roll=roll)
+    cost = oracle.make_cost(q2=[1, 10], v2=[1, 10], u2=[1], q1=[0.5])
+    d_ref, a_ref, _ = oracle.fd_batch(om, q, v, u, w, cost)
+    d_gpu, a_gpu, status = h.fd_batch_host(q, v, u, w, cost)
+    assert status.sum() == 0
+    assert_deriv_close(d_gpu, d_ref, m.nv, m.nu)
+    # without a device cost the caller's gradient entries must survive (host wrappers fill them)
+    pre = np.full((n, m.nd), 7.0)
+    d2, _, _ = h.fd_batch_host(q, v, u, w, None, deriv=pre.copy())
+    nj = m.nv * (2 * m.nv + m.nu)
+    assert np.array_equal(d2[:, nj:], pre[:, nj:]) and np.array_equal(d2[:, :nj], d_gpu[:, :nj])
+    h.close()

@@ -1,0 +1,85 @@
+"""Knot-sharded FD with the gather fused into the kernels' write-out (ilqg_fd_batch_dev_scatter + CUDA IPC peer buffers).
+
+1 GPU: several destinations on the same device receive identical blocks.  >= 2 GPUs (skipped otherwise): two ranks, NCCL
+for the plumbing, each linearises half of the knots and stores its blocks into both ranks' arrays over NVLink; every rank
+must end with exactly what a single GPU computes for the whole horizon."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, scenario_states
+
+pytestmark = pytest.mark.gpu
+
+
+def test_scatter_to_several_local_destinations(pkg, oracle, omodels):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    h = pkg.Handle(pkg.Model.named("hopper"), 0)
+    m = h.model
+    q, v, u, w = scenario_states("hopper", 53, seed=11, oracle=oracle, om=omodels["hopper"], roll=120)
+    dq, dv, du, dw = (torch.from_numpy(a).cuda() for a in (q, v, u, w))
+    cost = pkg.make_cost(q1=[1.0])
+    ref = torch.zeros((53, m.nd), dtype=torch.float64, device="cuda")
+    h.fd_batch_dev(dq, dv, du, dw, ref, cost=cost)
+    from ilqg_mujoco_b200 import sharding
+    bufs = [h.peer_alloc(60 * m.nd * 8)[0] for _ in range(3)]
+    first = 5   # the range's blocks land at knot offset 5 of every destination
+    h.fd_batch_dev_scatter(dq, dv, du, dw, [b + first * m.nd * 8 for b in bufs], cost=cost)
+    torch.cuda.synchronize()
+    for b in bufs:
+        full = torch.as_tensor(sharding._DevArray(b, (60, m.nd)), device="cuda:0")
+        assert torch.equal(full[first:first + 53], ref)
+        assert float(full[:first].abs().sum()) == 0.0 and float(full[first + 53:].abs().sum()) == 0.0
+    for b in bufs:
+        h.peer_free(b)
+    h.close()
+
+
+def _rank(rank, world, port, T, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import __graft_entry__ as entry
+    pkg = entry.load_package()
+    o = entry.load_oracle()
+    from ilqg_mujoco_b200 import sharding
+    om = o.Model(os.path.join(pkg.MODELS_DIR, "hopper.ilqgm"))
+    q, v, u, w = scenario_states("hopper", T, seed=5, oracle=o, om=om, roll=100)
+    dev = f"cuda:{rank}"
+    dq, dv, du, dw = (torch.from_numpy(a).to(dev) for a in (q, v, u, w))
+    h = pkg.Handle(pkg.Model.named("hopper"), rank)
+    peer = sharding.PeerDeriv(h, T, h.model.nd)
+    cost = pkg.make_cost(q1=[1.0])
+    full = sharding.fd_knot_sharded_peer(h, peer, dq, dv, du, dw, cost=cost)
+    for _ in range(5):   # repeated passes exercise the barrier's epochs
+        full = sharding.fd_knot_sharded_peer(h, peer, dq, dv, du, dw, cost=cost)
+    torch.cuda.synchronize()
+    assert not h.peer_barrier_timed_out()
+    np.save(os.path.join(out, f"peer_{rank}.npy"), full.cpu().numpy())
+    if rank == 0:
+        ref = torch.zeros((T, h.model.nd), dtype=torch.float64, device=dev)
+        h.fd_batch_dev(dq, dv, du, dw, ref, cost=cost)
+        np.save(os.path.join(out, "single.npy"), ref.cpu().numpy())
+    peer.close()
+    h.close()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_store_into_each_others_arrays(tmp_path):
+    import torch
+    import torch.multiprocessing as mp
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs on one node")
+    T = 101
+    mp.spawn(_rank, args=(2, 29700 + os.getpid() % 200, T, str(tmp_path)), nprocs=2, join=True)
+    single = np.load(tmp_path / "single.npy")
+    for r in range(2):
+        assert np.array_equal(np.load(tmp_path / f"peer_{r}.npy"), single)

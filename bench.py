@@ -410,9 +410,9 @@ def run_gpu_arm(args):
         one_step()
         ev[i][1].record()
         ev[i][1].synchronize()
-        c_ms, p_ms = C.c_float(0), C.c_float(0)
-        L.ilqg_fd_last_kernel_ms(h._h, C.byref(c_ms), C.byref(p_ms))
-        kern_ms.append((c_ms.value, p_ms.value))
+        c_ms, v_ms, q_ms = C.c_float(0), C.c_float(0), C.c_float(0)
+        L.ilqg_fd_last_stage_ms(h._h, C.byref(c_ms), C.byref(v_ms), C.byref(q_ms))
+        kern_ms.append((c_ms.value, v_ms.value, q_ms.value))
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -471,26 +471,35 @@ def run_gpu_arm(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches, "secondary": secondary}
         # ---- roofline of the dominant kernel (fd_perturb_kernel) + cpu baseline: rank 0 only
-        p_ms = float(np.mean([k[1] for k in kern_ms]))
-        c_ms = float(np.mean([k[0] for k in kern_ms]))
+        c_ms, v_ms, q_ms = (float(np.mean([k[j] for k in kern_ms])) for j in range(3))
+        p_ms = v_ms + q_ms
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except OSError:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        alg_bytes = nk * (8 * (model.nq + 2 * model.nv + model.nu) + 8 * model.nd)
-        ach = alg_bytes / (p_ms * 1e-3) / 1e9
+        nv, nu, nq = model.nv, model.nu, model.nq
+        in_b = 8 * (nq + 2 * nv + nu)                      # knot inputs: qpos, qvel, ctrl, warm start (centre qacc)
+        kern = {"fd_velctrl_kernel<Topo_hopper>": (v_ms, in_b + 8 * (nv * nv + nv * nu + nv + nu)),   # dv | du blocks + their cost-gradient entries
+                "fd_qpos_kernel<Topo_hopper>": (q_ms, in_b + 8 * (nv * nv + nv)),                       # dq block + its cost-gradient entries
+                "fd_center_kernel<Topo_hopper>": (c_ms, in_b + 8 * nv)}
+        split = v_ms > 1e-3   # batches below the size threshold run the single-launch kernel (all perturbed evaluations in q_ms)
+        if not split:
+            kern = {"fd_perturb_kernel<Topo_hopper>": (q_ms, in_b + 8 * model.nd), "fd_center_kernel<Topo_hopper>": (c_ms, in_b + 8 * nv)}
+        dom = max(kern, key=lambda k: kern[k][0])
+        ach = kern[dom][1] * nk / (kern[dom][0] * 1e-3) / 1e9
         traffic = None
-        try:  # dram bytes per knot of the perturb kernel from the committed ncu --set full capture, scaled to this launch
+        try:  # dram bytes per knot of that kernel from the committed ncu --set full capture, scaled to this launch
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            traffic = tj["fd_perturb_dram_bytes_per_knot"] * nk
+            traffic = tj["dram_bytes_per_knot"][dom.split("<")[0]] * nk
         except (OSError, KeyError, ValueError):
             pass
         line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic,
                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650",
-                            "kernel": "fd_perturb_kernel<Topo_hopper>", "kernel_ms": p_ms, "center_kernel_ms": c_ms,
-                            "note": "schema-conformant HBM view; the path is fp64-compute bound (SURVEY 8d): see roofline_fp64"}
+                            "kernel": dom, "kernel_ms": kern[dom][0], "algorithmic_bytes_per_knot": kern[dom][1],
+                            "kernels_ms": {k: v[0] for k, v in kern.items()},
+                            "note": "schema-conformant HBM view of the longest kernel; the path is fp64-compute bound (SURVEY 8d): see roofline_fp64"}
         if world == 1:
             o = entry.load_oracle()
             om = o.Model(os.path.join(pkg.MODELS_DIR, "hopper.ilqgm"))
@@ -509,7 +518,7 @@ def run_gpu_arm(args):
             ach_tf = flops_per_knot * nk / ((p_ms + c_ms) * 1e-3) / 1e12
             line["roofline_fp64"] = {"bound": "fp64", "achieved": ach_tf, "peak": tf.value, "unit": "TFLOP/s",
                                      "frac": ach_tf / tf.value if tf.value else None, "flops_per_knot": flops_per_knot,
-                                     "how": "oracle-counted fp64 flops per knot (FMA=2) on a sample of this workload x knots / (center+perturb kernel time); "
+                                     "how": "oracle-counted fp64 flops per knot (FMA=2, under the reference's stage-skipping schedule) on a sample of this workload x knots / (sum of the three FD kernels' time); "
                                             "peak = DFMA-chain microbenchmark run now on this GPU (MEASURED_PEAKS.json has no fp64 figure)"}
             # parity spot check of the timed outputs against the oracle on the sample
             dg = deriv[:ns].cpu().numpy()

@@ -441,6 +441,8 @@ struct EngineT : Engine {
         if (ev) cudaEventRecord(ev[1], s);
         if (variant >= 3) {  // stage-skipping split: qvel/ctrl columns, then qpos columns
             using P = FdSplit<T>;
+            // (the default L1 / shared-memory split is the best one: forcing a larger shared carve-out shrinks the L1 that holds the
+            //  rollouts' local-memory rows and costs up to 30 % — measured with cudaFuncAttributePreferredSharedMemoryCarveout)
             fd_velctrl_kernel<T, true><<<(nknots + P::KPC_VU - 1) / P::KPC_VU, P::THREADS, 0, s>>>(dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev,
                                                                                                  o.eps, o.niter, dst, status);
             if (ev) cudaEventRecord(ev[3], s);
@@ -957,7 +959,11 @@ int ilqg_fd_batch_host(ilqg_handle h, int nknots, const double* qpos, const doub
         CU(h, cudaMemcpy(h->d_cost, cost, sizeof(ilqg_cost), cudaMemcpyHostToDevice));
         dcost = h->d_cost;
     }
-    const size_t chunk = n <= 4096 ? n : (n + 7) / 8 < 4096 ? 4096 : (n + 7) / 8;
+    // chunks large enough for the stage-skipping kernels (>= 16384 knots), four of them at the benchmark size: measured best
+    // on B200 (86,016 hopper knots: 1 chunk 3.11 ms, 2: 2.33, 4: 2.04, 8: 2.25, 16: 2.85; raw D2H of deriv alone: 1.35 ms)
+    size_t nchunks = n / 20000 < 4 ? (n >= 8192 ? 4 : 1) : n / 20000;
+    if (const char* e = getenv("ILQG_HOST_CHUNKS")) nchunks = (size_t)atoi(e) > 0 ? (size_t)atoi(e) : nchunks;
+    const size_t chunk = (n + nchunks - 1) / nchunks;
     int ci = 0;
     for (size_t lo = 0; lo < n; lo += chunk, ci++) {
         const size_t cn = lo + chunk <= n ? chunk : n - lo;

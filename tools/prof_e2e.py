@@ -1,0 +1,33 @@
+"""Host-pointer FD call (ilqg_fd_batch_host) timing for a few chunkings of its copy/compute pipeline."""
+import ctypes as C, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import __graft_entry__ as e
+pkg = e.load_package()
+from ilqg_mujoco_b200 import workload as wl
+model = pkg.Model.named("hopper")
+h = pkg.Handle(model, 0)
+q, v, u, w, _ = wl.make_knots(h, 4096, 21, seed=0, device="cuda:0", model="hopper")
+nk = q.shape[0]
+hq, hv, hu, hw = (t.cpu().pin_memory() for t in (q, v, u, w))
+hd = torch.zeros((nk, model.nd), dtype=torch.float64).pin_memory()
+ha = torch.zeros((nk, model.nv), dtype=torch.float64).pin_memory()
+hs = torch.zeros(nk, dtype=torch.int32).pin_memory()
+cost = pkg.make_cost(q1=[1.0]); L = pkg.lib()
+def step():
+    L.ilqg_fd_batch_host(h._h, nk, C.c_void_p(hq.data_ptr()), C.c_void_p(hv.data_ptr()), C.c_void_p(hu.data_ptr()), C.c_void_p(hw.data_ptr()),
+                         cost.ctypes.data_as(C.c_void_p), None, C.c_void_p(hd.data_ptr()), C.c_void_p(ha.data_ptr()), C.c_void_p(hs.data_ptr()))
+for ch in sys.argv[1:] or ["0"]:
+    if ch != "0": os.environ["ILQG_HOST_CHUNKS"] = ch
+    for _ in range(3): step()
+    t0 = time.perf_counter()
+    for _ in range(30): step()
+    dt = (time.perf_counter() - t0) / 30
+    print(f"chunks={ch}: {dt*1e3:.3f} ms/step -> {nk/dt/1e6:.2f} M knots/s e2e; D2H {nk*(model.nd+model.nv)*8/dt/1e9:.1f} GB/s")
+# raw PCIe rates for reference
+d = torch.empty(nk * model.nd, dtype=torch.float64, device="cuda:0")
+for name, fn in (("D2H", lambda: hd.view(-1).copy_(d, non_blocking=True)), ("H2D", lambda: d.copy_(hd.view(-1), non_blocking=True))):
+    fn(); torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(10): fn()
+    torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 10
+    print(f"raw {name} of the deriv array: {nk*model.nd*8/dt/1e9:.1f} GB/s")

@@ -390,6 +390,8 @@ struct IlqrLaunch<T, true> {
     }
     static cudaError_t accept(const IlqrBuffers& b, int accept_always, double* Jtrace, int* acc_trace, cudaStream_t s) {
         ilqr_accept_kernel<T><<<(b.ninst + 127) / 128, 128, 0, s>>>(b, accept_always, Jtrace, acc_trace);
+        const size_t T1 = (size_t)(b.N + 1) * b.ninst;
+        ilqr_commit_kernel<T><<<(unsigned)((T1 + 127) / 128), 128, 0, s>>>(b);
         return cudaGetLastError();
     }
     static cudaError_t backward(const IlqrBuffers& b, double dt, cudaStream_t s) {
@@ -1171,7 +1173,7 @@ int ilqg_ilqr_init_dev(ilqg_ilqr w, const double* qpos, const double* qvel, cons
     one.nalpha = 1;  // alphas[0] multiplies k = 0: any value gives the open-loop rollout
     CU(h, h->eng->ilqr_rollout(one, w->host_cost ? nullptr : w->d_cost, s));
     CU(h, h->eng->ilqr_accept(one, 1, nullptr, nullptr, s));
-    h->launches += 2;
+    h->launches += 3;
     w->iters = 0;
     return ILQG_OK;
 }
@@ -1190,7 +1192,7 @@ int ilqg_ilqr_forward(ilqg_ilqr w, int accept_always, void* stream) {   // forwa
     int slot = w->iters % w->trace_cap;
     CU(h, h->eng->ilqr_rollout(b, w->host_cost ? nullptr : w->d_cost, s));
     CU(h, h->eng->ilqr_accept(b, accept_always, w->d_Jtrace + (size_t)slot * b.ninst, w->d_acc_trace + (size_t)slot * b.ninst, s));
-    h->launches += 2;
+    h->launches += 3;
     w->iters++;
     return ILQG_OK;
 }

@@ -51,21 +51,32 @@ __global__ void __launch_bounds__(128) ilqr_rollout_kernel(const __grid_constant
     Work<T> w;
     double J = 0;
     const size_t T1 = (size_t)(b.N + 1) * ninst;
+    // The rollout is one dependent chain per thread; the knot's feedback data (K, k, nominal) does not depend on the state, so
+    // the NEXT knot's record is fetched while the current mj_step runs instead of stalling the chain on an L2 round trip.
+    double Kn[nz(NU) * NX], kn_[nz(NU)], xq[NQ], xv[NV], xu[nz(NU)];
+    auto fetch = [&](int n) {
+        const size_t kn = (size_t)n * ninst + i;
+        sfor<0, NU * NX>([&](auto ee) { Kn[IDX(ee)] = b.K[kn * NU * NX + IDX(ee)]; });
+        sfor<0, NU>([&](auto rr) { kn_[IDX(rr)] = b.k[kn * NU + IDX(rr)]; xu[IDX(rr)] = b.nom_u[kn * NU + IDX(rr)]; });
+        sfor<0, NQ>([&](auto ii) { xq[IDX(ii)] = b.nom_q[kn * NQ + IDX(ii)]; });
+        sfor<0, NV>([&](auto ii) { xv[IDX(ii)] = b.nom_v[kn * NV + IDX(ii)]; });
+    };
+    fetch(b.N);
     for (int n = b.N; n >= 0; n--) {
         const size_t kn = (size_t)n * ninst + i;
         // u = K[n] (x - x*_n) + alpha k[n] + u*_n      (ilqr.h:126; alpha = 1 there)
         double dx[NX];
         sfor<0, NV>([&](auto ii) {
-            dx[IDX(ii)] = q[IDX(ii)] - b.nom_q[kn * NQ + IDX(ii)];
-            dx[NV + IDX(ii)] = v[IDX(ii)] - b.nom_v[kn * NV + IDX(ii)];
+            dx[IDX(ii)] = q[IDX(ii)] - xq[IDX(ii)];
+            dx[NV + IDX(ii)] = v[IDX(ii)] - xv[IDX(ii)];
         });
-        const double* K = b.K + kn * NU * NX;
         sfor<0, NU>([&](auto rr) {
             constexpr int r = IDX(rr);
             double s = 0;
-            sfor<0, NX>([&](auto cc) { s += K[r + IDX(cc) * NU] * dx[IDX(cc)]; });
-            u[r] = s + alpha * b.k[kn * NU + r] + b.nom_u[kn * NU + r];
+            sfor<0, NX>([&](auto cc) { s += Kn[r + IDX(cc) * NU] * dx[IDX(cc)]; });
+            u[r] = s + alpha * kn_[r] + xu[r];
         });
+        if (n > 0) fetch(n - 1);
         // snapshot the knot (cpMjData(dArray[n], d), ilqr.h:127) into this alpha's candidate
         const size_t cn = (size_t)a * T1 + kn;
         sfor<0, NQ>([&](auto ii) { b.cand_q[cn * NQ + IDX(ii)] = q[IDX(ii)]; });
@@ -78,14 +89,14 @@ __global__ void __launch_bounds__(128) ilqr_rollout_kernel(const __grid_constant
 }
 
 // ------------------------------------------------------------------ ladder-order acceptance
-// One block column per instance: thread (knot) copies the accepted candidate over the nominal.  The accepted alpha is
-// the FIRST one in ladder order whose cost beats the nominal's — exactly what sequential backtracking would pick.
+// The accepted alpha is the FIRST one in ladder order whose cost beats the nominal's — exactly what sequential backtracking
+// would pick.  Two small launches: the decision per instance, then one thread per (knot, instance) copies the accepted
+// candidate over the nominal (time-major layout: consecutive threads touch consecutive knots' records).
 template <class T>
 __global__ void ilqr_accept_kernel(IlqrBuffers b, int accept_always, double* __restrict__ Jtrace, int* __restrict__ acc_trace) {
-    constexpr int NQ = T::NQ, NV = T::NV, NU = T::NU;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= b.ninst) return;
-    const int ninst = b.ninst, Tn = b.N + 1;
+    const int ninst = b.ninst;
     int acc = -1;
     const double Jprev = b.nom_J[i];
     double J = Jprev;
@@ -95,23 +106,31 @@ __global__ void ilqr_accept_kernel(IlqrBuffers b, int accept_always, double* __r
             double Ja = b.cand_J[(size_t)a * ninst + i];
             if (Ja < Jprev) { acc = a; J = Ja; break; }
         }
-    if (acc >= 0) {
-        const size_t T1 = (size_t)Tn * ninst;
-        for (int n = 0; n < Tn; n++) {
-            const size_t kn = (size_t)n * ninst + i, cn = (size_t)acc * T1 + kn;
-            for (int c = 0; c < NQ; c++) b.nom_q[kn * NQ + c] = b.cand_q[cn * NQ + c];
-            for (int c = 0; c < NV; c++) { b.nom_v[kn * NV + c] = b.cand_v[cn * NV + c]; b.nom_w[kn * NV + c] = b.cand_w[cn * NV + c]; }
-            for (int c = 0; c < NU; c++) b.nom_u[kn * NU + c] = b.cand_u[cn * NU + c];
-        }
-        b.nom_J[i] = J;
-    }
+    if (acc >= 0) b.nom_J[i] = J;
     b.accepted[i] = acc;
     if (Jtrace) Jtrace[i] = J;
     if (acc_trace) acc_trace[i] = acc;
-    // setDInit(dArray[N]) (ilqr.h:183): the next pass starts from the nominal's first knot
-    const size_t kN = (size_t)b.N * ninst + i;
-    for (int c = 0; c < NQ; c++) b.init_q[(size_t)i * NQ + c] = b.nom_q[kN * NQ + c];
-    for (int c = 0; c < NV; c++) { b.init_v[(size_t)i * NV + c] = b.nom_v[kN * NV + c]; b.init_w[(size_t)i * NV + c] = b.nom_w[kN * NV + c]; }
+}
+
+template <class T>
+__global__ void ilqr_commit_kernel(IlqrBuffers b) {
+    constexpr int NQ = T::NQ, NV = T::NV, NU = T::NU;
+    const int ninst = b.ninst, Tn = b.N + 1;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x, T1 = (size_t)Tn * ninst;
+    if (t >= T1) return;
+    const int n = (int)(t / ninst), i = (int)(t - (size_t)n * ninst);
+    const int acc = b.accepted[i];
+    const size_t kn = t;
+    if (acc >= 0) {
+        const size_t cn = (size_t)acc * T1 + kn;
+        for (int c = 0; c < NQ; c++) b.nom_q[kn * NQ + c] = b.cand_q[cn * NQ + c];
+        for (int c = 0; c < NV; c++) { b.nom_v[kn * NV + c] = b.cand_v[cn * NV + c]; b.nom_w[kn * NV + c] = b.cand_w[cn * NV + c]; }
+        for (int c = 0; c < NU; c++) b.nom_u[kn * NU + c] = b.cand_u[cn * NU + c];
+    }
+    if (n == b.N) {   // setDInit(dArray[N]) (ilqr.h:183): the next pass starts from the nominal's first knot
+        for (int c = 0; c < NQ; c++) b.init_q[(size_t)i * NQ + c] = b.nom_q[kn * NQ + c];
+        for (int c = 0; c < NV; c++) { b.init_v[(size_t)i * NV + c] = b.nom_v[kn * NV + c]; b.init_w[(size_t)i * NV + c] = b.nom_w[kn * NV + c]; }
+    }
 }
 
 // ------------------------------------------------------------------ backward pass

@@ -58,8 +58,8 @@ __global__ void __launch_bounds__(128) fd_center_kernel(const __grid_constant__ 
     sfor<0, T::NV>([&](auto ii) { warm[IDX(ii)] = warmstart ? warmstart[(size_t)k * T::NV + IDX(ii)] : 0.0; });
     Work<T> w;
     build_problem<T>(m, q, v, u, w);
-    solve<T>(m, w, warm, qacc, niter, 0.0);
-    for (int rep = 1; rep < nwarmup; rep++) solve<T>(m, w, warm, qacc, niter, 0.0);
+#pragma unroll 1
+    for (int rep = 0; rep < nwarmup; rep++) solve<T>(m, w, warm, qacc, niter, 0.0);   // one copy of the solver (instruction footprint)
     bool ok = true;
     sfor<0, T::NV>([&](auto ii) { qacc_center[(size_t)k * T::NV + IDX(ii)] = qacc[IDX(ii)]; ok = ok && isfinite(qacc[IDX(ii)]); });
     if (status) status[k] = ok ? 0 : ILQG_ERR_NONFINITE;

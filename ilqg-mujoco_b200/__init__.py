@@ -255,6 +255,9 @@ class Ilqr:
     def set_cost(self, cost):
         self.h._check(lib().ilqg_ilqr_set_cost(self._w, _hp(cost)))
 
+    def set_layout(self, corrected):
+        self.h._check(lib().ilqg_ilqr_set_layout(self._w, 1 if corrected else 0))
+
     def set_mu(self, mu):
         self.h._check(lib().ilqg_ilqr_set_mu(self._w, C.c_double(mu)))
 

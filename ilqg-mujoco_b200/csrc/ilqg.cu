@@ -1104,6 +1104,7 @@ int ilqg_ilqr_create(ilqg_handle h, int ninst, int N, int nalpha, const double* 
     const size_t T = (size_t)N + 1, TI = T * ninst;
     auto& b = w->b;
     b.ninst = ninst; b.N = N; b.nalpha = nalpha; b.mu = 1000.0;  // ilqr.h:65
+    b.corrected = 0;
     ILQR_ALLOC(w, b.nom_q, TI * nq); ILQR_ALLOC(w, b.nom_v, TI * nv); ILQR_ALLOC(w, b.nom_u, TI * nu); ILQR_ALLOC(w, b.nom_w, TI * nv);
     ILQR_ALLOC(w, b.init_q, (size_t)ninst * nq); ILQR_ALLOC(w, b.init_v, (size_t)ninst * nv); ILQR_ALLOC(w, b.init_w, (size_t)ninst * nv);
     ILQR_ALLOC(w, b.cand_q, nalpha * TI * nq); ILQR_ALLOC(w, b.cand_v, nalpha * TI * nv); ILQR_ALLOC(w, b.cand_u, nalpha * TI * nu);
@@ -1128,6 +1129,13 @@ int ilqg_ilqr_set_cost(ilqg_ilqr w, const ilqg_cost* cost) {
     if (cost) CU(h, cudaMemcpy(w->d_cost, cost, sizeof(ilqg_cost), cudaMemcpyHostToDevice));
     w->has_cost = true;
     w->host_cost = cost == nullptr;  // NULL: the caller owns the cost (a host stepCostFn) and supplies the gradient rows itself
+    return ILQG_OK;
+}
+// opt-in: read the deriv blocks as what they are (d qacc_j / d x_i at i + j*stride), i.e. undo quirk Q1/Q2.
+// Default 0 = the reference's A/B, which is what parity is judged on.
+int ilqg_ilqr_set_layout(ilqg_ilqr w, int corrected) {
+    if (!w) return ILQG_ERR_ARG;
+    w->b.corrected = corrected ? 1 : 0;
     return ILQG_OK;
 }
 int ilqg_ilqr_set_mu(ilqg_ilqr w, double mu) {

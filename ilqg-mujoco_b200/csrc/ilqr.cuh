@@ -33,6 +33,7 @@ struct IlqrBuffers {
     double *V, *v;      // [ninst][nx*nx] (column-major), [ninst][nx]
     double* deriv;      // [T][ninst][ND]
     double mu;
+    int corrected;      // 0: A/B through the reference's column-major views of the row-major deriv blocks (quirk Q1); 1: transposed back
 };
 
 // ------------------------------------------------------------------ forward pass, all alphas at once
@@ -210,13 +211,13 @@ __global__ void __launch_bounds__(LANES * GROUPS) ilqr_backward_kernel(IlqrBuffe
                 int r = e % NX, c = e / NX;
                 double a;
                 if (r < NV) a = (c == r ? 1.0 : 0.0) + (c == NV + r ? dt : 0.0);
-                else if (c < NV) a = deriv[(r - NV) + c * NV] * dt;
-                else a = ((r - NV) == (c - NV) ? 1.0 : 0.0) + deriv[NV * NV + (r - NV) + (c - NV) * NV] * dt;
+                else if (c < NV) a = deriv[b.corrected ? c + (r - NV) * NV : (r - NV) + c * NV] * dt;
+                else a = ((r - NV) == (c - NV) ? 1.0 : 0.0) + deriv[NV * NV + (b.corrected ? (c - NV) + (r - NV) * NV : (r - NV) + (c - NV) * NV)] * dt;
                 s.A[e] = a;
             }
             for (int e = lane; e < NX * NU; e += LANES) {
                 int r = e % NX, c = e / NX;
-                s.B[e] = r < NV ? 0.0 : deriv[2 * NV * NV + (r - NV) + c * NV] * dt;
+                s.B[e] = r < NV ? 0.0 : deriv[2 * NV * NV + (b.corrected ? c + (r - NV) * NU : (r - NV) + c * NV)] * dt;
             }
             for (int e = lane; e < NX; e += LANES) {
                 s.q[e] = deriv[2 * NV * NV + NV * NU + e];

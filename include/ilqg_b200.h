@@ -155,6 +155,9 @@ int ilqg_ilqr_create(ilqg_handle h, int ninst, int N, int nalpha, const double* 
 int ilqg_ilqr_destroy(ilqg_ilqr w);
 int ilqg_ilqr_set_cost(ilqg_ilqr w, const ilqg_cost* cost); /* host struct; NULL selects host-cost mode */
 int ilqg_ilqr_set_mu(ilqg_ilqr w, double mu);               /* Levenberg-Marquardt term, default 1000 (ilqr.h:65) */
+/* corrected != 0: assemble A/B from deriv as d qacc_j / d x_i (undoes the column-major-view quirk of
+ * /root/reference/inc/differentiator.h:68-71); default 0 = the reference's matrices (parity mode) */
+int ilqg_ilqr_set_layout(ilqg_ilqr w, int corrected);
 int ilqg_ilqr_init_dev(ilqg_ilqr w, const double* qpos, const double* qvel, const double* ctrl, const double* warm, void* stream);
 int ilqg_ilqr_init_host(ilqg_ilqr w, const double* qpos, const double* qvel, const double* ctrl, const double* warm);
 int ilqg_ilqr_set_state_dev(ilqg_ilqr w, const double* qpos, const double* qvel, const double* warm, void* stream);

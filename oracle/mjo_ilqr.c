@@ -143,6 +143,10 @@ double mjo_ilqr_forward_pass(mjo_ilqr* il, double alpha) {
     return mjo_ilqr_traj_cost(il);
 }
 
+/* process-wide switch for the opt-in corrected A/B layout (tests only; default 0 = the reference's views) */
+int mjo_ilqr_corrected_layout = 0;
+void mjo_ilqr_set_corrected_layout(int on) { mjo_ilqr_corrected_layout = on ? 1 : 0; }
+
 /* Differentiator::updateDerivatives at knot n (differentiator.h:85-93): FD, then A/B through the
    column-major views of the row-major deriv blocks (quirk Q1) */
 static void linearise_knot(mjo_ilqr* il, int n) {
@@ -156,6 +160,16 @@ static void linearise_knot(mjo_ilqr* il, int n) {
     memset(B, 0, sizeof(double) * nx * nu);
     for (int i = 0; i < nv; i++) { CM(A, i, i, nx) = 1; CM(A, i, nv + i, nx) = dt; }
     const double *dq = deriv, *dv = deriv + nv * nv, *du = deriv + 2 * nv * nv;
+    if (mjo_ilqr_corrected_layout) { /* opt-in, not the reference: d qacc_r / d x_c sits at c + r*stride (mjderivative.cpp:107,138,202) */
+        for (int r = 0; r < nv; r++)
+            for (int c = 0; c < nv; c++) {
+                CM(A, nv + r, c, nx) = dq[c + r * nv] * dt;
+                CM(A, nv + r, nv + c, nx) = (r == c ? 1.0 : 0.0) + dv[c + r * nv] * dt;
+            }
+        for (int r = 0; r < nv; r++)
+            for (int c = 0; c < nu; c++) CM(B, nv + r, c, nx) = du[c + r * nu] * dt;
+        return;
+    }
     for (int r = 0; r < nv; r++)
         for (int c = 0; c < nv; c++) {
             CM(A, nv + r, c, nx) = CM(dq, r, c, nv) * dt;

@@ -107,3 +107,41 @@ def test_unsupported_and_bad_arguments(pkg, handles):
     with pytest.raises(pkg.IlqgError):
         il.iterate(1)          # cost not set
     il.close()
+
+
+def test_corrected_layout_mode_matches_oracle_and_differs_from_the_quirk(pkg, handles, oracle, omodels):
+    """Opt-in: A/B assembled from deriv as d qacc_j / d x_i instead of through the reference's
+    column-major views (quirk Q1).  Not the parity mode — but the oracle carries the same switch, so the GPU is still
+    checked against a CPU statement of it; on the hopper (nu = 3 != nv) the two layouts give different gains."""
+    h = handles["hopper"]; om = omodels["hopper"]
+    q, v, u, w = scenario_states("hopper", 6, seed=43, oracle=oracle, om=om, roll=100)
+    cost = oracle.make_cost(q2=[0, 5, 1, 0, 0, 0], q1=[-1.0], v2=[0.1] * 6, u2=[0.01] * 3)
+    ref = oracle.ilqr_run_batch(om, 20, 1, q, v, u, w, cost, alphas=None, corrected=True)
+    quirk = oracle.ilqr_run_batch(om, 20, 1, q, v, u, w, cost, alphas=None)
+    il = pkg.Ilqr(h, 6, 20, (1.0,))
+    il.set_cost(cost)
+    il.set_layout(True)
+    il.init_host(q, v, u, w)
+    il.iterate(1, True)
+    out = il.get()
+    il.close()
+    for key in ("K", "k", "V", "v"):
+        a_, b_ = (out[key][:, 1:], ref[key][:, 1:]) if key in ("K", "k") else (out[key], ref[key])
+        assert rel(a_, b_) < 1e-5, (key, rel(a_, b_))
+    assert rel(quirk["K"][:, 1:], ref["K"][:, 1:]) > 1e-3      # the switch changes the matrices
+    # pendulum, 10 iterations with the ladder: cost trace parity in corrected mode as well
+    hp = handles["inverted_pendulum"]; omp_ = omodels["inverted_pendulum"]
+    q, v, u, w = scenario_states("inverted_pendulum", 16, seed=7)
+    u = u * 0
+    pc = oracle.make_cost(**PEND_COST)
+    al = tuple(0.5 ** a for a in range(6))
+    ref = oracle.ilqr_run_batch(omp_, 20, 10, q, v, u, w, pc, alphas=al, accept_always=False, corrected=True)
+    il = pkg.Ilqr(hp, 16, 20, al)
+    il.set_cost(pc)
+    il.set_layout(True)
+    il.init_host(q, v, u, w)
+    il.iterate(10, False)
+    out = il.get()
+    il.close()
+    assert np.array_equal(out["accepted"], ref["accepted"])
+    assert rel(out["J"], ref["J"]) < 1e-8

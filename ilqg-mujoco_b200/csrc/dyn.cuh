@@ -334,8 +334,10 @@ DEV void make_frame(V3 n, V3 hint, bool has_hint, V3& t1, V3& t2) {
 // warps of a CTA drift apart and each streams its own copy of the instructions through the instruction caches (ncu: the
 // second-largest stall reason was "no instruction").  With them the CTA's warps walk the code together and share fetches.
 // Every thread of the block must call the stage functions when SYNC is set.
-template <class T, bool SYNC = false>
-DEV void build_pos(const DevModel<T>& m, const double (&q)[T::NQ], PosStage<T>& ps, Work<T>& w) {
+// FUSED (qv != nullptr): the velocity is known while the rows are built — aref is finished here from the Jacobian still in
+// registers and the per-row constants (B, k-term) never go to local memory; build_vel then skips its pass over the rows.
+template <class T, bool SYNC = false, bool FUSED = false>
+DEV void build_pos(const DevModel<T>& m, const double (&q)[T::NQ], PosStage<T>& ps, Work<T>& w, const double* qv = nullptr) {
     auto stage_sync = [&]() { if constexpr (SYNC) __syncthreads(); };
     constexpr int NB = T::NBODY, NV = T::NV, NJ = T::NJNT;
     V3 xpos[NB];
@@ -475,8 +477,8 @@ DEV void build_pos(const DevModel<T>& m, const double (&q)[T::NQ], PosStage<T>& 
                     row_params(m.jnt_K[j], m.jnt_imp[j], m.jnt_solimp[j], dist, m.jnt_margin[j], m.dof_invw[da], R, kt);
                     sfor<0, NV>([&](auto ii) { w.J[ne][IDX(ii)] = IDX(ii) == da ? -side : 0.0; });
                     w.D[ne] = 1.0 / R;
-                    w.rB[ne] = B;
-                    w.rkt[ne] = kt;
+                    if constexpr (FUSED) w.aref[ne] = -B * (-side * qv[da]) - kt;
+                    else { w.rB[ne] = B; w.rkt[ne] = kt; }
                     ne++;
                 }
             });
@@ -637,8 +639,11 @@ DEV void build_pos(const DevModel<T>& m, const double (&q)[T::NQ], PosStage<T>& 
                 row_params(K, imp, m.pair_solimp[p], dist, margin, tran, R, kt);
                 sfor<0, NV>([&](auto ii) { w.J[ne][IDX(ii)] = jn[IDX(ii)]; });
                 w.D[ne] = 1.0 / R;
-                w.rB[ne] = B;
-                w.rkt[ne] = kt;
+                if constexpr (FUSED) {
+                    double s = 0;
+                    sfor<0, NV>([&](auto ii) { s += jn[IDX(ii)] * qv[IDX(ii)]; });
+                    w.aref[ne] = -B * s - kt;
+                } else { w.rB[ne] = B; w.rkt[ne] = kt; }
                 ne++;
             } else {
                 double R0, kt;
@@ -650,10 +655,15 @@ DEV void build_pos(const DevModel<T>& m, const double (&q)[T::NQ], PosStage<T>& 
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     const double sg = (k % 2) ? -mu : mu;
-                    sfor<0, NV>([&](auto ii) { w.J[ne][IDX(ii)] = jn[IDX(ii)] + sg * (k < 2 ? ja[IDX(ii)] : jb[IDX(ii)]); });
+                    double s = 0;
+                    sfor<0, NV>([&](auto ii) {
+                        const double Jri = jn[IDX(ii)] + sg * (k < 2 ? ja[IDX(ii)] : jb[IDX(ii)]);
+                        w.J[ne][IDX(ii)] = Jri;
+                        if constexpr (FUSED) s += Jri * qv[IDX(ii)];
+                    });
                     w.D[ne] = Dpy;
-                    w.rB[ne] = B;
-                    w.rkt[ne] = kt;
+                    if constexpr (FUSED) w.aref[ne] = -B * s - kt;
+                    else { w.rB[ne] = B; w.rkt[ne] = kt; }
                     ne++;
                 }
             }
@@ -663,7 +673,7 @@ DEV void build_pos(const DevModel<T>& m, const double (&q)[T::NQ], PosStage<T>& 
     stage_sync();
 }
 
-template <class T, bool SYNC = false>
+template <class T, bool SYNC = false, bool FUSED = false>
 DEV void build_vel(const DevModel<T>& m, const PosStage<T>& ps, const double (&qv)[T::NV], Work<T>& w) {
     auto stage_sync = [&]() { if constexpr (SYNC) __syncthreads(); };
     constexpr int NB = T::NBODY, NV = T::NV;
@@ -706,6 +716,7 @@ DEV void build_vel(const DevModel<T>& m, const PosStage<T>& ps, const double (&q
         w.fb[i] = f;
     });
     // reference accelerations of the rows (mj_referenceConstraint): aref = -B (J qvel) - K imp (pos - margin)
+    if constexpr (!FUSED)
     for (int r = 0; r < w.nefc; r++) {
         double s = 0;
         sfor<0, NV>([&](auto ii) { s += w.J[r][IDX(ii)] * qv[IDX(ii)]; });
@@ -733,8 +744,8 @@ template <class T, bool SYNC = false>
 DEV void build_problem(const DevModel<T>& m, const double (&q)[T::NQ], const double (&qv)[T::NV], const double (&u)[nz(T::NU)],
                        Work<T>& w) {
     PosStage<T> ps;
-    build_pos<T, SYNC>(m, q, ps, w);
-    build_vel<T, SYNC>(m, ps, qv, w);
+    build_pos<T, SYNC, true>(m, q, ps, w, qv);
+    build_vel<T, SYNC, true>(m, ps, qv, w);
     finish_smooth<T>(m, u, w);
 }
 

@@ -258,6 +258,9 @@ class Ilqr:
     def set_layout(self, corrected):
         self.h._check(lib().ilqg_ilqr_set_layout(self._w, 1 if corrected else 0))
 
+    def set_mu_schedule(self, factor, mu_min=1e-6, mu_max=1e10):
+        self.h._check(lib().ilqg_ilqr_set_mu_schedule(self._w, C.c_double(factor), C.c_double(mu_min), C.c_double(mu_max)))
+
     def set_mu(self, mu):
         self.h._check(lib().ilqg_ilqr_set_mu(self._w, C.c_double(mu)))
 

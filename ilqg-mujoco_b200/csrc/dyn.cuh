@@ -750,24 +750,6 @@ DEV void build_problem(const DevModel<T>& m, const double (&q)[T::NQ], const dou
 }
 
 // ------------------------------------------------------------------ constraint solve (mj_fwdConstraint)
-template <class T>
-DEV double problem_cost(const Work<T>& w, const double* a) {
-    constexpr int NV = T::NV;
-    double cost = 0;
-    for (int r = 0; r < w.nefc; r++) {
-        double jar = -w.aref[r];
-        sfor<0, NV>([&](auto ii) { jar += w.J[r][IDX(ii)] * a[IDX(ii)]; });
-        if (jar < 0) cost += 0.5 * w.D[r] * jar * jar;
-    }
-    sfor<0, NV>([&](auto ii) {
-        constexpr int i = IDX(ii);
-        double Ma = 0;
-        sfor<0, NV>([&](auto kk) { Ma += w.M[tri(i, IDX(kk))] * a[IDX(kk)]; });
-        cost += 0.5 * (Ma - w.fs[i]) * (a[i] - w.as[i]);
-    });
-    return cost;
-}
-
 // Newton with exact linesearch on the convex piecewise-quadratic cost.  `warm` in: qacc_warmstart;
 // out: the solution (which is also the next warm start, as in MuJoCo 2.x).  qacc out.
 //

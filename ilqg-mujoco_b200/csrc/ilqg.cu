@@ -1,13 +1,15 @@
 // ilqg.cu — sm_100a kernels and the C ABI (include/ilqg_b200.h) of the iLQG hot path.
 //
-// FD linearisation (replaces /root/reference/src/mjderivative.cpp:43-255):
-//   fd_center_kernel  : one thread per knot — the centre evaluation and its nwarmup-1 extra solves
-//                       (:61-68); its only product is the warm start every perturbed solve begins from (:75).
-//   fd_perturb_kernel : one thread per perturbed evaluation, G = 2(2nv+nu) consecutive lanes per knot
-//                       (+/- pairs adjacent), floor(32/G) knots per warp.  The +/- lanes difference their
-//                       qacc with one shuffle, the knot's deriv block is staged in shared memory in the
-//                       reference layout and written to HBM by the whole warp in consecutive 8-byte words.
-// All T x 2(2nv+nu) perturbations of every trajectory in the batch go out in one launch each.
+// FD linearisation (replaces /root/reference/src/mjderivative.cpp:43-255), all knots of all trajectories per call:
+//   fd_center_kernel  : one thread per knot — the centre evaluation and its warm-up solves (:61-68); its product is the
+//                       warm start every perturbed solve begins from (:75).
+//   large batches     : fd_velctrl_kernel (qvel + ctrl columns on ONE position stage per thread: the reference's
+//                       mjSTAGE_POS / mjSTAGE_VEL skips, :92,124) and fd_qpos_kernel (qpos columns, full pipeline, :178).
+//   small batches     : fd_perturb_kernel, one thread per perturbed evaluation of any column in a single launch.
+//   Blocks of deriv are staged in shared memory and written as contiguous runs in the reference layout, to the caller's
+//   buffer or to several (peer-GPU) destinations at once.
+// Batched iLQR (ilqr.cuh), the warp-per-rollout engine for large trees (coop.cuh), the peer-memory barrier and the C ABI
+// (include/ilqg_b200.h) follow.
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
@@ -85,14 +87,15 @@ struct FdShape {
     static_assert(G <= 32, "thread-per-rollout FD kernel needs 2(2nv+nu) <= 32; larger models use the cooperative kernel");
 };
 
-template <class T, int WARPS, int MINBLOCKS, bool SYNC>
-__global__ void __launch_bounds__(WARPS * 32, MINBLOCKS) fd_perturb_kernel(const __grid_constant__ DevModel<T> m, int nknots,
+template <class T>
+__global__ void __launch_bounds__(256, 1) fd_perturb_kernel(const __grid_constant__ DevModel<T> m, int nknots,
                                                                  const double* __restrict__ qpos, const double* __restrict__ qvel,
                                                                  const double* __restrict__ ctrl, const double* __restrict__ qacc_center,
                                                                  const ilqg_cost* __restrict__ cost, double eps, int niter,
                                                                  const FdDst dst, int* __restrict__ status) {
     using S = FdShape<T>;
-    constexpr int NV = T::NV, NU = T::NU, NQ = T::NQ;
+    constexpr int NV = T::NV, NU = T::NU, NQ = T::NQ, WARPS = 8;
+    constexpr bool SYNC = true;   // stage barriers: the CTA's warps share instruction fetches
     __shared__ double stage[WARPS][S::KPW * S::ND];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int warp = blockIdx.x * WARPS + wib;
@@ -432,11 +435,10 @@ struct EngineT : Engine {
     cudaError_t fd(int nknots, const double* qpos, const double* qvel, const double* ctrl, const double* warm, const ilqg_cost* cost_dev,
                    const ilqg_fd_opts& o, const FdDst& dst, double* qacc_center, int* status, cudaStream_t s, cudaEvent_t* ev) override {
         using S = FdShape<T>;
-        // variant: 3 = stage-skipping split (fewest instructions: best once its qvel/ctrl kernel fills the GPU), 2 = one thread per
-        // perturbed evaluation in a single launch (30x more threads per knot: lower latency for small batches), -1 = by size
+        // variant 3 = stage-skipping split (fewest instructions: best once its qvel/ctrl kernel fills the GPU), 2 = one thread per
+        // perturbed evaluation in a single launch (30x more threads per knot: lower latency for small batches); fd_variant -1 = by size
         const int variant = fd_variant >= 0 ? fd_variant : (nknots >= 16384 ? 3 : 2);
         last_launches = variant >= 3 ? 3 : 2;
-        constexpr int WARPS = 4;
         if (nknots <= 0) return cudaSuccess;
         if (ev) cudaEventRecord(ev[0], s);
         fd_center_kernel<T><<<(nknots + 127) / 128, 128, 0, s>>>(dm, nknots, qpos, qvel, ctrl, warm, o.niter, o.nwarmup, qacc_center, status);
@@ -454,13 +456,8 @@ struct EngineT : Engine {
             return cudaGetLastError();
         }
         if (ev) cudaEventRecord(ev[3], s);
-        int nwarps = (nknots + S::KPW - 1) / S::KPW;
-        dim3 grid((nwarps + WARPS - 1) / WARPS), block(WARPS * 32);
-        switch (variant) {  // experiment switch (ILQG_FD_VARIANT): 0 = 4 warps x 2 CTAs/SM, no stage barriers; 1 = with barriers; 2 = 8 warps x 1 CTA with barriers
-            case 0: fd_perturb_kernel<T, 4, 2, false><<<grid, block, 0, s>>>(dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps, o.niter, dst, status); break;
-            case 2: fd_perturb_kernel<T, 8, 1, true><<<dim3((nwarps + 7) / 8), dim3(256), 0, s>>>(dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps, o.niter, dst, status); break;
-            default: fd_perturb_kernel<T, 4, 2, true><<<grid, block, 0, s>>>(dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps, o.niter, dst, status); break;
-        }
+        const int nwarps = (nknots + S::KPW - 1) / S::KPW;
+        fd_perturb_kernel<T><<<(nwarps + 7) / 8, 256, 0, s>>>(dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps, o.niter, dst, status);
         if (ev) cudaEventRecord(ev[2], s);
         return cudaGetLastError();
     }
@@ -660,6 +657,7 @@ struct ilqg_handle_s {
     // staging for the *_host entry points
     void* d_stage = nullptr; size_t stage_cap = 0;
     long launches = 0;  // kernels launched through this handle (bench.py reports it)
+    int host_chunks = 0;  // > 0: forced chunk count of the host-pointer FD pipeline
     bool profiling = false;
     cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};  // chunk pipeline of the *_host FD entry point
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // before centre, after centre, after the last FD kernel, between the two column kernels
@@ -712,6 +710,7 @@ int ilqg_create(const ilqg_model* m, int device, ilqg_handle* out) {
     h->model = *m;
     h->eng = eng;
     if (const char* e = getenv("ILQG_FD_VARIANT")) eng->fd_variant = atoi(e);
+    if (const char* e = getenv("ILQG_HOST_CHUNKS")) h->host_chunks = atoi(e);
     if (cudaMalloc(&h->d_cost, sizeof(ilqg_cost)) != cudaSuccess) {
         delete eng;
         delete h;
@@ -964,7 +963,7 @@ int ilqg_fd_batch_host(ilqg_handle h, int nknots, const double* qpos, const doub
     // chunks large enough for the stage-skipping kernels (>= 16384 knots), four of them at the benchmark size: measured best
     // on B200 (86,016 hopper knots: 1 chunk 3.11 ms, 2: 2.33, 4: 2.04, 8: 2.25, 16: 2.85; raw D2H of deriv alone: 1.35 ms)
     size_t nchunks = n / 20000 < 4 ? (n >= 8192 ? 4 : 1) : n / 20000;
-    if (const char* e = getenv("ILQG_HOST_CHUNKS")) nchunks = (size_t)atoi(e) > 0 ? (size_t)atoi(e) : nchunks;
+    if (h->host_chunks > 0) nchunks = (size_t)h->host_chunks;   // ILQG_HOST_CHUNKS (experiments)
     const size_t chunk = (n + nchunks - 1) / nchunks;
     int ci = 0;
     for (size_t lo = 0; lo < n; lo += chunk, ci++) {
@@ -1105,6 +1104,7 @@ int ilqg_ilqr_create(ilqg_handle h, int ninst, int N, int nalpha, const double* 
     auto& b = w->b;
     b.ninst = ninst; b.N = N; b.nalpha = nalpha; b.mu = 1000.0;  // ilqr.h:65
     b.corrected = 0;
+    b.mu_i = nullptr; b.mu_factor = 1.0; b.mu_min = 1e-6; b.mu_max = 1e10;
     ILQR_ALLOC(w, b.nom_q, TI * nq); ILQR_ALLOC(w, b.nom_v, TI * nv); ILQR_ALLOC(w, b.nom_u, TI * nu); ILQR_ALLOC(w, b.nom_w, TI * nv);
     ILQR_ALLOC(w, b.init_q, (size_t)ninst * nq); ILQR_ALLOC(w, b.init_v, (size_t)ninst * nv); ILQR_ALLOC(w, b.init_w, (size_t)ninst * nv);
     ILQR_ALLOC(w, b.cand_q, nalpha * TI * nq); ILQR_ALLOC(w, b.cand_v, nalpha * TI * nv); ILQR_ALLOC(w, b.cand_u, nalpha * TI * nu);
@@ -1141,6 +1141,25 @@ int ilqg_ilqr_set_layout(ilqg_ilqr w, int corrected) {
 int ilqg_ilqr_set_mu(ilqg_ilqr w, double mu) {
     if (!w) return ILQG_ERR_ARG;
     w->b.mu = mu;
+    if (w->b.mu_i) {   // (re)start the schedule from this value
+        std::vector<double> v((size_t)w->b.ninst, mu);
+        CU(w->h, cudaSetDevice(w->h->device));
+        CU(w->h, cudaMemcpy(w->b.mu_i, v.data(), sizeof(double) * v.size(), cudaMemcpyHostToDevice));
+    }
+    return ILQG_OK;
+}
+// opt-in: per-instance mu, divided by `factor` after an iteration whose ladder accepted a step and multiplied
+// by it after a rejected one, clamped to [mu_min, mu_max].  factor <= 1 returns to the reference's constant mu.
+int ilqg_ilqr_set_mu_schedule(ilqg_ilqr w, double factor, double mu_min, double mu_max) {
+    if (!w || !(mu_min > 0) || !(mu_max >= mu_min)) return ILQG_ERR_ARG;
+    ilqg_handle h = w->h;
+    CU(h, cudaSetDevice(h->device));
+    if (factor > 1.0 && !w->b.mu_i) {
+        ILQR_ALLOC(w, w->b.mu_i, w->b.ninst);
+        std::vector<double> v((size_t)w->b.ninst, w->b.mu);
+        CU(h, cudaMemcpy(w->b.mu_i, v.data(), sizeof(double) * v.size(), cudaMemcpyHostToDevice));
+    }
+    w->b.mu_factor = factor; w->b.mu_min = mu_min; w->b.mu_max = mu_max;
     return ILQG_OK;
 }
 
@@ -1179,6 +1198,7 @@ int ilqg_ilqr_init_dev(ilqg_ilqr w, const double* qpos, const double* qvel, cons
     }
     ilqg::IlqrBuffers one = b;
     one.nalpha = 1;  // alphas[0] multiplies k = 0: any value gives the open-loop rollout
+    one.mu_i = nullptr;  // the constructor's rollout is not a line-search outcome: the mu schedule does not move
     CU(h, h->eng->ilqr_rollout(one, w->host_cost ? nullptr : w->d_cost, s));
     CU(h, h->eng->ilqr_accept(one, 1, nullptr, nullptr, s));
     h->launches += 3;

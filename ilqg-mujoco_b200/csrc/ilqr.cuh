@@ -32,7 +32,9 @@ struct IlqrBuffers {
     double *K, *k;      // [T][ninst][nu*nx], [T][ninst][nu]
     double *V, *v;      // [ninst][nx*nx] (column-major), [ninst][nx]
     double* deriv;      // [T][ninst][ND]
-    double mu;
+    double mu;          // Levenberg-Marquardt term (ilqr.h:65,166) when mu_i is NULL
+    double* mu_i;       // [ninst] per-instance mu under the opt-in schedule, else NULL
+    double mu_factor, mu_min, mu_max;
     int corrected;      // 0: A/B through the reference's column-major views of the row-major deriv blocks (quirk Q1); 1: transposed back
 };
 
@@ -108,6 +110,12 @@ __global__ void ilqr_accept_kernel(IlqrBuffers b, int accept_always, double* __r
             if (Ja < Jprev) { acc = a; J = Ja; break; }
         }
     if (acc >= 0) b.nom_J[i] = J;
+    if (b.mu_i && b.mu_factor > 1.0) {   // opt-in schedule: relax after an accepted step, stiffen after a rejected ladder
+        double mu = b.mu_i[i];
+        if (acc >= 0) { mu = mu / b.mu_factor; if (mu < b.mu_min) mu = b.mu_min; }
+        else { mu = mu * b.mu_factor; if (mu > b.mu_max) mu = b.mu_max; }
+        b.mu_i[i] = mu;
+    }
     b.accepted[i] = acc;
     if (Jtrace) Jtrace[i] = J;
     if (acc_trace) acc_trace[i] = acc;
@@ -187,6 +195,7 @@ __global__ void __launch_bounds__(LANES * GROUPS) ilqr_backward_kernel(IlqrBuffe
     const bool live = i < b.ninst;
     SM& s = all[g];
     const int ninst = b.ninst;
+    const double mu = (b.mu_i && live) ? b.mu_i[i] : b.mu;
     // groups are whole warps or aligned sub-warps; sync the lanes of this group only
     const unsigned gmask = LANES == 32 ? 0xffffffffu : (((1u << LANES) - 1u) << ((threadIdx.x % 32) / LANES * LANES));
     auto gsync = [&]() { __syncwarp(gmask); };
@@ -227,7 +236,7 @@ __global__ void __launch_bounds__(LANES * GROUPS) ilqr_backward_kernel(IlqrBuffe
         }
         gsync();
         if (live)  // V = sym(V) + mu I   (ilqr.h:166; never removed — quirk Q3)
-            for (int e = lane; e < NX * NX; e += LANES) s.V[e] = s.Vn[e] + ((e % NX) == (e / NX) ? b.mu : 0.0);
+            for (int e = lane; e < NX * NX; e += LANES) s.V[e] = s.Vn[e] + ((e % NX) == (e / NX) ? mu : 0.0);
         gsync();
         if (live) {
             for (int e = lane; e < NX * NU; e += LANES) {  // VB = V B

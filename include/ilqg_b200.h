@@ -158,6 +158,10 @@ int ilqg_ilqr_set_mu(ilqg_ilqr w, double mu);               /* Levenberg-Marquar
 /* corrected != 0: assemble A/B from deriv as d qacc_j / d x_i (undoes the column-major-view quirk of
  * /root/reference/inc/differentiator.h:68-71); default 0 = the reference's matrices (parity mode) */
 int ilqg_ilqr_set_layout(ilqg_ilqr w, int corrected);
+/* opt-in mu schedule (the README of the reference advertises regularisation it does not implement, README.md:9-17):
+ * per instance, mu /= factor after an accepted line-search step, mu *= factor after a rejected ladder, clamped to
+ * [mu_min, mu_max]; factor <= 1 (default) keeps the reference's constant mu */
+int ilqg_ilqr_set_mu_schedule(ilqg_ilqr w, double factor, double mu_min, double mu_max);
 int ilqg_ilqr_init_dev(ilqg_ilqr w, const double* qpos, const double* qvel, const double* ctrl, const double* warm, void* stream);
 int ilqg_ilqr_init_host(ilqg_ilqr w, const double* qpos, const double* qvel, const double* ctrl, const double* warm);
 int ilqg_ilqr_set_state_dev(ilqg_ilqr w, const double* qpos, const double* qvel, const double* warm, void* stream);

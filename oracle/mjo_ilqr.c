@@ -143,6 +143,13 @@ double mjo_ilqr_forward_pass(mjo_ilqr* il, double alpha) {
     return mjo_ilqr_traj_cost(il);
 }
 
+/* process-wide switches of the opt-in extensions (tests only; the defaults are the reference's behaviour):
+   mu schedule: after an iteration whose ladder accepted a step mu <- max(mu_min, mu / factor), after a
+   rejected one mu <- min(mu_max, mu * factor); factor <= 1 keeps the reference's constant mu (ilqr.h:65,166) */
+double mjo_ilqr_mu_factor = 1.0, mjo_ilqr_mu_min = 1e-6, mjo_ilqr_mu_max = 1e10;
+void mjo_ilqr_set_mu_schedule(double factor, double mu_min, double mu_max) {
+    mjo_ilqr_mu_factor = factor; mjo_ilqr_mu_min = mu_min; mjo_ilqr_mu_max = mu_max;
+}
 /* process-wide switch for the opt-in corrected A/B layout (tests only; default 0 = the reference's views) */
 int mjo_ilqr_corrected_layout = 0;
 void mjo_ilqr_set_corrected_layout(int on) { mjo_ilqr_corrected_layout = on ? 1 : 0; }
@@ -338,6 +345,10 @@ int mjo_ilqr_iterate_linesearch(mjo_ilqr* il, const double* alphas, int nalpha, 
         memcpy(il->warm, s_w, sizeof(double) * sv); memcpy(il->qacc, s_a, sizeof(double) * sv);
     }
     free(save);
+    if (mjo_ilqr_mu_factor > 1.0) {
+        if (accepted >= 0) { il->mu = il->mu / mjo_ilqr_mu_factor; if (il->mu < mjo_ilqr_mu_min) il->mu = mjo_ilqr_mu_min; }
+        else { il->mu = il->mu * mjo_ilqr_mu_factor; if (il->mu > mjo_ilqr_mu_max) il->mu = mjo_ilqr_mu_max; }
+    }
     mjo_ilqr_set_dinit(il, il->qpos + (size_t)N * il->nq, il->qvel + (size_t)N * il->nv, il->ctrl + (size_t)N * il->nu,
                        il->warm + (size_t)N * il->nv, il->qacc + (size_t)N * il->nv);
     mjo_ilqr_backward_pass(il);

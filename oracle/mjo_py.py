@@ -77,7 +77,7 @@ def make_cost(q2=(), q1=(), v2=(), v1=(), u2=(), u1=()):
     return c
 
 
-def ilqr_run_batch(m, N, niter, qpos0, qvel0, ctrl0, warm0, cost, alphas=None, accept_always=True, mu=1000.0, corrected=False):
+def ilqr_run_batch(m, N, niter, qpos0, qvel0, ctrl0, warm0, cost, alphas=None, accept_always=True, mu=1000.0, corrected=False, mu_schedule=None):
     """niter x iterate for every instance (reference cadence); alphas=None -> the reference's own iterate()."""
     n = qpos0.shape[0]
     T, nx = N + 1, 2 * m.nv
@@ -87,8 +87,11 @@ def ilqr_run_batch(m, N, niter, qpos0, qvel0, ctrl0, warm0, cost, alphas=None, a
     out = dict(J=np.zeros((n, niter)), accepted=np.zeros((n, niter), np.int32), qpos=np.zeros((n, T, m.nq)), qvel=np.zeros((n, T, m.nv)),
                ctrl=np.zeros((n, T, m.nu)), K=np.zeros((n, T, m.nu * nx)), k=np.zeros((n, T, m.nu)), V=np.zeros((n, nx * nx)), v=np.zeros((n, nx)))
     lib().mjo_ilqr_set_corrected_layout(1 if corrected else 0)
+    f, lo, hi = mu_schedule if mu_schedule else (1.0, 1e-6, 1e10)
+    lib().mjo_ilqr_set_mu_schedule(C.c_double(f), C.c_double(lo), C.c_double(hi))
     lib().mjo_ilqr_run_batch(m.ptr, n, N, niter, _p(q0), _p(v0), _p(u0), _p(w0), _p(cost), _p(al), 0 if al is None else len(al),
                              1 if accept_always else 0, C.c_double(mu), _p(out["J"]), _p(out["accepted"]), _p(out["qpos"]), _p(out["qvel"]),
                              _p(out["ctrl"]), _p(out["K"]), _p(out["k"]), _p(out["V"]), _p(out["v"]), 0)
     lib().mjo_ilqr_set_corrected_layout(0)
+    lib().mjo_ilqr_set_mu_schedule(C.c_double(1.0), C.c_double(1e-6), C.c_double(1e10))
     return out

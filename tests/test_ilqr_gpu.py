@@ -145,3 +145,27 @@ def test_corrected_layout_mode_matches_oracle_and_differs_from_the_quirk(pkg, ha
     il.close()
     assert np.array_equal(out["accepted"], ref["accepted"])
     assert rel(out["J"], ref["J"]) < 1e-8
+
+
+def test_mu_schedule_matches_oracle(pkg, handles, oracle, omodels):
+    """Opt-in: per-instance Levenberg-Marquardt term, relaxed after an accepted line-search step and
+    stiffened after a rejected ladder.  Same switch in the oracle; traces and accepted alphas must agree, and the schedule
+    must change the iterates with respect to the reference's constant mu = 1000."""
+    h = handles["inverted_pendulum"]; om = omodels["inverted_pendulum"]
+    q, v, u, w = scenario_states("inverted_pendulum", 24, seed=21)
+    u = u * 0
+    cost = oracle.make_cost(**PEND_COST)
+    al = tuple(0.5 ** a for a in range(5))
+    sched = (2.0, 1.0, 1e6)
+    ref = oracle.ilqr_run_batch(om, 20, 8, q, v, u, w, cost, alphas=al, accept_always=False, mu_schedule=sched)
+    const = oracle.ilqr_run_batch(om, 20, 8, q, v, u, w, cost, alphas=al, accept_always=False)
+    il = pkg.Ilqr(h, 24, 20, al)
+    il.set_cost(cost)
+    il.set_mu_schedule(*sched)
+    il.init_host(q, v, u, w)
+    il.iterate(8, False)
+    out = il.get()
+    il.close()
+    assert np.array_equal(out["accepted"], ref["accepted"])
+    assert rel(out["J"], ref["J"]) < 1e-8
+    assert rel(ref["J"][:, -1], const["J"][:, -1]) > 1e-6      # the schedule is not a no-op

@@ -8,6 +8,7 @@ from ilqg_mujoco_b200 import workload as wl
 model = pkg.Model.named("hopper")
 h = pkg.Handle(model, 0)
 q, v, u, w, _ = wl.make_knots(h, 4096, 21, seed=0, device="cuda:0", model="hopper")
+h.close()
 nk = q.shape[0]
 hq, hv, hu, hw = (t.cpu().pin_memory() for t in (q, v, u, w))
 hd = torch.zeros((nk, model.nd), dtype=torch.float64).pin_memory()
@@ -18,11 +19,13 @@ def step():
     L.ilqg_fd_batch_host(h._h, nk, C.c_void_p(hq.data_ptr()), C.c_void_p(hv.data_ptr()), C.c_void_p(hu.data_ptr()), C.c_void_p(hw.data_ptr()),
                          cost.ctypes.data_as(C.c_void_p), None, C.c_void_p(hd.data_ptr()), C.c_void_p(ha.data_ptr()), C.c_void_p(hs.data_ptr()))
 for ch in sys.argv[1:] or ["0"]:
-    if ch != "0": os.environ["ILQG_HOST_CHUNKS"] = ch
+    if ch != "0": os.environ["ILQG_HOST_CHUNKS"] = ch   # read when the handle is created
+    h = pkg.Handle(model, 0)
     for _ in range(3): step()
     t0 = time.perf_counter()
     for _ in range(30): step()
     dt = (time.perf_counter() - t0) / 30
+    h.close()
     print(f"chunks={ch}: {dt*1e3:.3f} ms/step -> {nk/dt/1e6:.2f} M knots/s e2e; D2H {nk*(model.nd+model.nv)*8/dt/1e9:.1f} GB/s")
 # raw PCIe rates for reference
 d = torch.empty(nk * model.nd, dtype=torch.float64, device="cuda:0")

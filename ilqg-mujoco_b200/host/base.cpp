@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include "hopper/hopper.h"
 #include "inverted_pendulum/inverted_pendulum.h"
 
 int main(int argc, const char** argv) {
@@ -14,6 +15,17 @@ int main(int argc, const char** argv) {
     if (!m) mju_error(error);
     mjData* d = mj_makeData(m);
     int nsteps = argc > 2 ? atoi(argv[2]) : 50;
+    if (m->nv == Hopper::nv && m->nu == Hopper::nu) {   // res/hopper.xml: the hopper task (no reference equivalent)
+        Hopper hopper(m, d);
+        for (int s = 0; s < nsteps; s++) {
+            hopper.forward();
+            printf("{\"step\": %d, \"x\": %.9g, \"z\": %.9g, \"pitch\": %.9g, \"xdot\": %.9g, \"cost\": %.9g, \"ctrl\": [%.9g, %.9g, %.9g]}\n", s, d->qpos[0],
+                   d->qpos[1], d->qpos[2], d->qvel[0], hopper.J[Hopper::maxIterUtilConvergence - 1], d->ctrl[0], d->ctrl[1], d->ctrl[2]);
+        }
+        mj_deleteData(d);
+        mj_deleteModel(m);
+        return 0;
+    }
     InvertedPendulum invertedPendulum(m, d);
     for (int s = 0; s < nsteps; s++) {
         invertedPendulum.forward();

@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "inverted_pendulum/cost.h"
+#include "hopper/hopper.h"
 #include "inverted_pendulum/inverted_pendulum.h"
 #include "mjderivative.h"
 #include "update.h"
@@ -176,7 +177,71 @@ void InvertedPendulum::forward() {
     mj_step(m, d);                                 // proceed simulation
 }
 
-// ---- C entry points for tests (ctypes): the headless MPC demo and a Differentiator<6,3> probe
+// ---- hopper task (no reference equivalent: SURVEY 8f row 3)
+ilqg_cost Hopper::hopperCost() {
+    ilqg_cost c;
+    memset(&c, 0, sizeof c);
+    c.q2[1] = 5.0; c.q1[1] = -12.5;      // 5 (z - 1.25)^2 up to a constant
+    c.q2[2] = 1.0;                       // torso pitch
+    c.v1[0] = -1.0;                      // forward progress
+    for (int i = 0; i < nv; i++) c.v2[i] = 0.05;
+    for (int i = 0; i < nu; i++) c.u2[i] = 0.01;
+    return c;
+}
+static void hopperCheck(mjModel* m, int rc, const char* what) {
+    if (rc) {
+        char buf[512];
+        snprintf(buf, sizeof buf, "Hopper: %s failed (%d): %s", what, rc, ilqg_last_error(m->gpu));
+        mju_error(buf);
+    }
+}
+Hopper::Hopper(mjModel* m, mjData* d) : m(m), d(d) {
+    cost = hopperCost();
+    for (auto i = 0; i < 10; i++) mj_step(m, d);
+    double alphas[nalpha];
+    for (int a = 0; a < nalpha; a++) alphas[a] = 1.0 / (1 << a);
+    hopperCheck(m, ilqg_ilqr_create(m->gpu, 1, N, nalpha, alphas, &ws), "ilqg_ilqr_create");
+    hopperCheck(m, ilqg_ilqr_set_cost(ws, &cost), "ilqg_ilqr_set_cost");
+    hopperCheck(m, ilqg_ilqr_set_layout(ws, 1), "ilqg_ilqr_set_layout");
+    hopperCheck(m, ilqg_ilqr_set_mu_schedule(ws, 2.0, 1.0, 1e8), "ilqg_ilqr_set_mu_schedule");
+    hopperCheck(m, ilqg_ilqr_init_host(ws, d->qpos, d->qvel, d->ctrl, d->qacc_warmstart), "ilqg_ilqr_init_host");
+    for (int i = 0; i < maxIterUtilConvergence; i++) J[i] = 0;
+}
+Hopper::~Hopper() { ilqg_ilqr_destroy(ws); }
+void Hopper::forward() {
+    hopperCheck(m, ilqg_ilqr_set_state_host(ws, d->qpos, d->qvel, d->qacc_warmstart), "ilqg_ilqr_set_state_host");
+    hopperCheck(m, ilqg_ilqr_iterate(ws, maxIterUtilConvergence, 0, NULL), "ilqg_ilqr_iterate");
+    mjtNum u[(N + 1) * nu];
+    const int done = ilqg_ilqr_iterations_done(ws);
+    std::vector<mjtNum> Jt(done < 256 ? done : 256);
+    hopperCheck(m, ilqg_ilqr_get_host(ws, NULL, NULL, u, NULL, NULL, NULL, NULL, Jt.data(), NULL), "ilqg_ilqr_get_host");
+    for (int i = 0; i < maxIterUtilConvergence; i++) J[i] = Jt[Jt.size() - maxIterUtilConvergence + i];
+    mju_copy(d->ctrl, u + N * nu, nu);   // get first u (knot N is the initial one, ilqr.h:52)
+    mj_step(m, d);                       // proceed simulation
+}
+
+// ---- C entry points for tests (ctypes): the headless MPC demos and a Differentiator<6,3> probe
+extern "C" int ilqg_host_hopper_mpc(const char* model_path, const double* qpos0, const double* qvel0, int nmpc, double* trace /* [nmpc][15] */,
+                                    double* Jtrace /* [nmpc][10] */) {
+    char err[512] = "";
+    mjModel* m = mj_loadXML(model_path, NULL, err, sizeof err);
+    if (!m) { fprintf(stderr, "%s\n", err); return 1; }
+    mjData* d = mj_makeData(m);
+    if (qpos0) mju_copy(d->qpos, qpos0, m->nq);
+    if (qvel0) mju_copy(d->qvel, qvel0, m->nv);
+    {
+        Hopper hp(m, d);
+        for (int s = 0; s < nmpc; s++) {
+            hp.forward();
+            if (trace) { mju_copy(trace + 15 * s, d->qpos, 6); mju_copy(trace + 15 * s + 6, d->qvel, 6); mju_copy(trace + 15 * s + 12, d->ctrl, 3); }
+            if (Jtrace) mju_copy(Jtrace + Hopper::maxIterUtilConvergence * s, hp.J, Hopper::maxIterUtilConvergence);
+        }
+    }
+    mj_deleteData(d);
+    mj_deleteModel(m);
+    return 0;
+}
+
 extern "C" int ilqg_host_pendulum_mpc(const char* model_path, const double* qpos0, const double* qvel0, int nmpc, double* trace,
                                       double* nom_qpos, double* nom_qvel, double* nom_ctrl, double* K, double* k, double* V, double* v) {
     char err[512] = "";

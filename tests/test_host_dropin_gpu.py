@@ -79,3 +79,41 @@ def test_headless_base_demo_runs():
     import json
     rec = json.loads(lines[-1])
     assert rec["step"] == 2 and abs(rec["time"] - 13 * 0.02) < 1e-9 and np.isfinite(rec["ctrl"][0])
+
+
+def test_hopper_task_mpc_matches_oracle(hostlib, oracle, omodels):
+    """the Hopper task class (host/hopper/hopper.h) — MPC through contacts with the opt-in corrected A/B
+    layout, the backtracking ladder and the mu schedule — against the oracle's restated MPC loop with the same switches."""
+    om = omodels["hopper"]
+    nmpc, N, niter = 3, 20, 10
+    tr = np.zeros((nmpc, 15)); Jt = np.zeros((nmpc, niter))
+    path = os.path.join(PKG, "models", "hopper.ilqgm").encode()
+    # start in stance: the hopper dropped from its rest pose and settled on the ground (400 passive steps)
+    z6 = np.zeros((1, 6))
+    q0, v0, _, _ = oracle.step_batch(om, np.array([[0, 1.25, 0, 0, 0, 0.0]]), z6, np.zeros((1, 3)), z6.copy(), 400)
+    q0, v0 = q0[0].copy(), v0[0].copy()
+    assert hostlib.ilqg_host_hopper_mpc(path, oracle._p(q0), oracle._p(v0), nmpc, oracle._p(tr), oracle._p(Jt)) == 0
+    cost = oracle.make_cost(q2=[0, 5, 1], q1=[0, -12.5], v1=[-1.0], v2=[0.05] * 6, u2=[0.01] * 3)
+    al = np.array([0.5 ** a for a in range(6)])
+    tr_o = np.zeros((nmpc, 15)); Jt_o = np.zeros((nmpc, niter)); acc_o = np.zeros((nmpc, niter), np.int32)
+    L = oracle.lib()
+    L.mjo_ilqr_set_corrected_layout(1)
+    L.mjo_ilqr_set_mu_schedule(C.c_double(2.0), C.c_double(1.0), C.c_double(1e8))
+    try:
+        L.mjo_mpc_run(om.ptr, oracle._p(q0), oracle._p(v0), 10, N, niter, nmpc, oracle._p(cost), oracle._p(al), 6, 0, oracle._p(tr_o), oracle._p(Jt_o),
+                      oracle._p(acc_o), None, None, None, None, None, None, None)
+    finally:
+        L.mjo_ilqr_set_corrected_layout(0)
+        L.mjo_ilqr_set_mu_schedule(C.c_double(1.0), C.c_double(1e-6), C.c_double(1e10))
+    assert np.isfinite(tr).all() and np.isfinite(Jt).all()
+    assert (acc_o >= 0).sum() >= nmpc            # the ladder accepts steps: the extensions make iLQR usable on this model
+    for J in (Jt, Jt_o):                         # the cost never increases within an MPC step, on either side
+        assert (np.diff(J, axis=1) <= 1e-9 * np.abs(J[:, :-1])).all()
+    # first MPC step: ten iterations through contacts agree to round-off, and so does the state the plant reaches
+    assert np.allclose(Jt[0], Jt_o[0], rtol=1e-8, atol=1e-9)
+    assert np.allclose(tr[0], tr_o[0], rtol=1e-6, atol=1e-8)
+    # Later MPC steps run through stick/slip transitions where the ladder's discrete decisions flip under 1e-11 perturbations of
+    # the initial state (checked on the oracle alone: the accepted-alpha sequence of step 1 changes), so only the first
+    # iterations of step 1 — before the first marginal decision — are compared, and the overall progress.
+    assert np.allclose(Jt[1, :5], Jt_o[1, :5], rtol=1e-8, atol=1e-9)
+    assert Jt[-1, -1] < Jt[0, 0] - 1.0 and Jt_o[-1, -1] < Jt_o[0, 0] - 1.0

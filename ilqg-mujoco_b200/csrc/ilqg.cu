@@ -399,6 +399,10 @@ struct IlqrLaunch<T, true> {
     }
     static cudaError_t backward(const IlqrBuffers& b, double dt, cudaStream_t s) {
         constexpr int NX = 2 * T::NV;
+        if constexpr (NX <= 4 && T::NU <= 2) {   // tiny models: one thread per instance, matrices in registers
+            ilqr_backward_small_kernel<T::NV, T::NU><<<(b.ninst + 31) / 32, 32, 0, s>>>(b, dt);
+            return cudaGetLastError();
+        }
         constexpr int LANES = NX * NX >= 64 ? 32 : 8, GROUPS = 128 / LANES;
         size_t smem = sizeof(BackwardSmem<T::NV, T::NU, LANES>) * GROUPS;
         ilqr_backward_kernel<T::NV, T::NU, LANES, GROUPS><<<(b.ninst + GROUPS - 1) / GROUPS, LANES * GROUPS, smem, s>>>(b, dt);

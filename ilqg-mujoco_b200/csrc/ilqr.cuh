@@ -184,6 +184,200 @@ DEV void ldlt_solve_small(const double* S, double* x) {  // S: N x N column-majo
     for (int i = 0; i < N; i++) x[perm[i]] = y[i];
 }
 
+// Small state vectors (2 nv <= 4: the inverted pendulum): ONE THREAD per instance, every matrix in registers, all loops unrolled.
+// Same algebra, same order of operations as the lane-group kernel below (which stays the path for larger nx); what goes is the
+// dozen shared-memory phases and group barriers per knot that made a 4 x 4 Riccati step cost ~10 K cycles.  The next knot's
+// deriv block and nominal are fetched while the current knot is processed.
+template <int NV, int NU>
+__global__ void __launch_bounds__(32) ilqr_backward_small_kernel(IlqrBuffers b, double dt) {
+    constexpr int NX = 2 * NV, ND = NV * (2 * NV + NU) + 2 * NV + NU, NQ = NV;
+    static_assert(NX <= 4 && NU <= 2, "register-resident Riccati step is for tiny models");
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b.ninst) return;
+    const int ninst = b.ninst;
+    const double mu = b.mu_i ? b.mu_i[i] : b.mu;
+#define CMX(M, r, c, rows) ((M)[(r) + (c) * (rows)])
+    double V[NX * NX], v[NX];
+    {   // initV (ilqr.h:100-107): v = dgdx at knot 0, V = v' v
+        const double* d0 = b.deriv + ((size_t)0 * ninst + i) * ND + 2 * NV * NV + NV * NU;
+#pragma unroll
+        for (int e = 0; e < NX; e++) v[e] = d0[e];
+#pragma unroll
+        for (int e = 0; e < NX * NX; e++) V[e] = v[e % NX] * v[e / NX];
+    }
+    double dnext[ND], xn[NX], xp[NX];   // deriv block of knot n, nominal state of knots n and n-1
+    auto fetch = [&](int n) {
+        const size_t kn = (size_t)n * ninst + i;
+        const double* d = b.deriv + kn * ND;
+#pragma unroll
+        for (int e = 0; e < ND; e++) dnext[e] = d[e];
+#pragma unroll
+        for (int e = 0; e < NV; e++) { xn[e] = b.nom_q[kn * NQ + e]; xn[NV + e] = b.nom_v[kn * NV + e]; }
+    };
+    {
+        const size_t k0 = (size_t)0 * ninst + i;
+#pragma unroll
+        for (int e = 0; e < NV; e++) { xp[e] = b.nom_q[k0 * NQ + e]; xp[NV + e] = b.nom_v[k0 * NV + e]; }
+    }
+    fetch(1);
+    for (int n = 1; n <= b.N; n++) {
+        const size_t kn = (size_t)n * ninst + i;
+        double deriv[ND], c[NX];
+#pragma unroll
+        for (int e = 0; e < ND; e++) deriv[e] = dnext[e];
+#pragma unroll
+        for (int e = 0; e < NX; e++) { c[e] = xp[e] - xn[e]; xp[e] = xn[e]; }
+        if (n < b.N) fetch(n + 1);
+        double Vn[NX * NX], A[NX * NX], B[NX * NU], q[NX], r[NU];
+#pragma unroll
+        for (int e = 0; e < NX * NX; e++) { const int rr = e % NX, cc = e / NX; Vn[e] = (CMX(V, rr, cc, NX) + CMX(V, cc, rr, NX)) / 2; }
+#pragma unroll
+        for (int e = 0; e < NX * NX; e++) {
+            const int rr = e % NX, cc = e / NX;
+            double a;
+            if (rr < NV) a = (cc == rr ? 1.0 : 0.0) + (cc == NV + rr ? dt : 0.0);
+            else if (cc < NV) a = deriv[b.corrected ? cc + (rr - NV) * NV : (rr - NV) + cc * NV] * dt;
+            else a = ((rr - NV) == (cc - NV) ? 1.0 : 0.0) + deriv[NV * NV + (b.corrected ? (cc - NV) + (rr - NV) * NV : (rr - NV) + (cc - NV) * NV)] * dt;
+            A[e] = a;
+        }
+#pragma unroll
+        for (int e = 0; e < NX * NU; e++) {
+            const int rr = e % NX, cc = e / NX;
+            B[e] = rr < NV ? 0.0 : deriv[2 * NV * NV + (b.corrected ? cc + (rr - NV) * NU : (rr - NV) + cc * NV)] * dt;
+        }
+#pragma unroll
+        for (int e = 0; e < NX; e++) q[e] = deriv[2 * NV * NV + NV * NU + e];
+#pragma unroll
+        for (int e = 0; e < NU; e++) r[e] = deriv[2 * NV * NV + NV * NU + 2 * NV + e];
+#pragma unroll
+        for (int e = 0; e < NX * NX; e++) V[e] = Vn[e] + ((e % NX) == (e / NX) ? mu : 0.0);   // ilqr.h:166; never removed (quirk Q3)
+        double VB[NX * NU], T1[NX * NX], w[NX];
+#pragma unroll
+        for (int e = 0; e < NX * NU; e++) {
+            const int rr = e % NX, cc = e / NX;
+            double t = 0;
+#pragma unroll
+            for (int x = 0; x < NX; x++) t += CMX(V, rr, x, NX) * CMX(B, x, cc, NX);
+            VB[e] = t;
+        }
+#pragma unroll
+        for (int e = 0; e < NX * NX; e++) {
+            const int rr = e % NX, cc = e / NX;
+            double t = 0;
+#pragma unroll
+            for (int x = 0; x < NX; x++) t += CMX(V, rr, x, NX) * CMX(A, x, cc, NX);
+            T1[e] = t;
+        }
+#pragma unroll
+        for (int e = 0; e < NX; e++) {
+            double t = 0;
+#pragma unroll
+            for (int x = 0; x < NX; x++) t += CMX(V, e, x, NX) * c[x];
+            w[e] = v[e] + 2 * t;
+        }
+        double S[NU * NU], K[NU * NX], k[NU];
+#pragma unroll
+        for (int e = 0; e < NU * NU; e++) {
+            const int a = e % NU, cc = e / NU;
+            double t = 0;
+#pragma unroll
+            for (int x = 0; x < NX; x++) t += CMX(B, x, a, NX) * CMX(VB, x, cc, NX);
+            S[e] = -2 * t - 2 * r[a] * r[cc];
+        }
+#pragma unroll
+        for (int e = 0; e < NU * NX; e++) {
+            const int a = e % NU, cc = e / NU;
+            double t = 0;
+#pragma unroll
+            for (int x = 0; x < NX; x++) t += CMX(B, x, a, NX) * CMX(T1, x, cc, NX);
+            K[e] = 2 * t;
+        }
+#pragma unroll
+        for (int e = 0; e < NU; e++) {
+            double t = 0;
+#pragma unroll
+            for (int x = 0; x < NX; x++) t += CMX(B, x, e, NX) * w[x];
+            k[e] = t + r[e];
+        }
+#pragma unroll
+        for (int cc = 0; cc < NX + 1; cc++) {   // K[n] = S^-1 rhsK (column by column), k[n] = S^-1 rhsk
+            double x[NU];
+#pragma unroll
+            for (int a = 0; a < NU; a++) x[a] = cc < NX ? K[a + cc * NU] : k[a];
+            ldlt_solve_small<NU>(S, x);
+#pragma unroll
+            for (int a = 0; a < NU; a++) { if (cc < NX) K[a + cc * NU] = x[a]; else k[a] = x[a]; }
+        }
+#pragma unroll
+        for (int e = 0; e < NU * NX; e++) b.K[kn * NU * NX + e] = K[e];
+#pragma unroll
+        for (int e = 0; e < NU; e++) b.k[kn * NU + e] = k[e];
+        double Acl[NX * NX], rK[NX];
+#pragma unroll
+        for (int e = 0; e < NX * NX; e++) {
+            const int rr = e % NX, cc = e / NX;
+            double t = A[e];
+#pragma unroll
+            for (int a = 0; a < NU; a++) t += CMX(B, rr, a, NX) * K[a + cc * NU];
+            Acl[e] = t;
+        }
+#pragma unroll
+        for (int e = 0; e < NX; e++) {
+            double t = 0;
+#pragma unroll
+            for (int a = 0; a < NU; a++) t += r[a] * K[a + e * NU];
+            rK[e] = t;
+            double u = c[e];
+#pragma unroll
+            for (int a = 0; a < NU; a++) u += CMX(B, e, a, NX) * k[a];
+            w[e] = u;
+        }
+#pragma unroll
+        for (int e = 0; e < NX * NX; e++) {   // T1 = V Acl
+            const int rr = e % NX, cc = e / NX;
+            double t = 0;
+#pragma unroll
+            for (int x = 0; x < NX; x++) t += CMX(V, rr, x, NX) * CMX(Acl, x, cc, NX);
+            T1[e] = t;
+        }
+#pragma unroll
+        for (int e = 0; e < NX * NX; e++) {   // Vn = Acl' V Acl + q'q + (rK)'(rK)   (ilqr.h:173)
+            const int rr = e % NX, cc = e / NX;
+            double t = 0;
+#pragma unroll
+            for (int x = 0; x < NX; x++) t += CMX(Acl, x, rr, NX) * CMX(T1, x, cc, NX);
+            Vn[e] = t + q[rr] * q[cc] + rK[rr] * rK[cc];
+        }
+        double wV[NX], vn[NX];
+#pragma unroll
+        for (int e = 0; e < NX * NX; e++) V[e] = Vn[e];
+#pragma unroll
+        for (int e = 0; e < NX; e++) {        // wV = (k'B' + c') V_new      (quirk Q4)
+            double t = 0;
+#pragma unroll
+            for (int x = 0; x < NX; x++) t += w[x] * CMX(Vn, x, e, NX);
+            wV[e] = t;
+        }
+        double kr = 0;
+#pragma unroll
+        for (int a = 0; a < NU; a++) kr += k[a] * r[a];
+#pragma unroll
+        for (int e = 0; e < NX; e++) {        // v = 2 wV Acl + v Acl + q + 2 (k'r') rK   (ilqr.h:174)
+            double t1 = 0, t2 = 0;
+#pragma unroll
+            for (int x = 0; x < NX; x++) { t1 += wV[x] * CMX(Acl, x, e, NX); t2 += v[x] * CMX(Acl, x, e, NX); }
+            vn[e] = 2 * t1 + t2 + q[e] + 2 * kr * rK[e];
+        }
+#pragma unroll
+        for (int e = 0; e < NX; e++) v[e] = vn[e];
+    }
+#pragma unroll
+    for (int e = 0; e < NX * NX; e++) b.V[(size_t)i * NX * NX + e] = V[e];
+#pragma unroll
+    for (int e = 0; e < NX; e++) b.v[(size_t)i * NX + e] = v[e];
+#undef CMX
+}
+
 template <int NV, int NU, int LANES, int GROUPS>
 __global__ void __launch_bounds__(LANES * GROUPS) ilqr_backward_kernel(IlqrBuffers b, double dt) {
     constexpr int NX = 2 * NV, ND = NV * (2 * NV + NU) + 2 * NV + NU, NQ = NV;

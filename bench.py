@@ -53,7 +53,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thr = threading.Thread(target=self._read, daemon=True)
             self.thr.start()
         except OSError:
@@ -357,6 +357,24 @@ def bench_humanoid(pkg, dev_index, nknots, steps, world, rank, with_cpu):
     return res
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """One process per GPU: run on the CPUs NVML reports as local to that GPU, so that the pinned staging buffers of the host-pointer
+    path are first-touched on the GPU's own NUMA node (8 ranks otherwise contend for one socket's memory controllers)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        hdl = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(hdl, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 # ------------------------------------------------------------------ the GPU arm
 def run_gpu_arm(args):
     import torch
@@ -369,6 +387,7 @@ def run_gpu_arm(args):
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
+    bind_to_gpu_numa_node(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device(dev))
@@ -416,7 +435,6 @@ def run_gpu_arm(args):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    clocks = sampler.stop()
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
     launches = h.launches - launches0
     nonfinite = int((status != 0).sum())
@@ -443,6 +461,7 @@ def run_gpu_arm(args):
     for _ in range(args.steps):
         e2e_step()
     e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()   # sampled across both timed regions (device-resident steps and host-pointer steps)
     h2d = nk * (model.nq + 2 * model.nv + model.nu) * 8
     d2h = nk * (model.nd + model.nv) * 8 + nk * 4
 

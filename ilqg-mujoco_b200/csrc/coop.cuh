@@ -169,24 +169,84 @@ __host__ __device__ constexpr int ptri(int i, int j) { return i * (i + 1) / 2 + 
 
 #define COOP_NMAX 32   // lane i owns dof i / row i of the nv x nv matrices
 
-// in-place Cholesky of the packed lower triangle A (n <= 32), left-looking: at column j lane l owns row j + l.
-// The diagonal is left holding 1 / L_jj.  (Measured alternatives that LOST on B200: rows in registers with every loop unrolled
-// — instruction-cache misses, the SM's warps sit at unrelated points of the pipeline; manual 4-way unrolling with split
-// accumulators; Hessian accumulators in registers streaming the active rows.  See profiles/r01_e_*.)
+// fp64 tensor-core tile product (mma.sync m8n8k4): {d0, d1} += A(8x4) B(4x8).  Fragment layout (PTX ISA, .f64):
+// a: row = lane / 4, k = lane % 4;  b: k = lane % 4, col = lane / 4;  c/d: row = lane / 4, cols = 2 (lane % 4) + {0, 1}.
+DEV void dmma_8x8x4(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// In-place Cholesky of the packed lower triangle A (n <= 32); the diagonal is left holding 1 / L_jj.
+// Blocked left-looking over 8-wide panels: before a panel is factored, the contributions of all earlier panels are taken off
+// its block column by DMMA tile updates (20 tensor-core instructions for n = 27 instead of ~260 of the 351 scalar
+// multiply-adds per row-lane); the panel itself needs no cross-lane step (see below): 4 warp barriers per factorisation
+// instead of 27 shuffle / rsqrt / barrier rounds.
+// (Measured alternatives that LOST on B200: rows in registers with every loop unrolled — instruction-cache misses, the SM's
+// warps sit at unrelated points of the pipeline; manual 4-way unrolling with split accumulators.)
 DEV void coop_chol(double* A, int n, int lane) {
-    for (int j = 0; j < n; j++) {
-        const int i = j + lane;
-        double s = 0;
-        if (i < n) {
-            s = A[ptri(i, j)];
-            const double* ri = A + ptri(i, 0);
-            const double* rj = A + ptri(j, 0);
-            for (int k = 0; k < j; k++) s -= ri[k] * rj[k];
+    const int g = lane >> 2, t = lane & 3;
+    const int nblk = (n + 7) >> 3;
+    for (int p = 0; p < nblk; p++) {
+        const int c0 = 8 * p;
+        if (p > 0) {
+            const int jb = c0 + g;                                  // row of L that feeds B's column g
+            for (int ib = p; ib < nblk; ib++) {
+                const int i = 8 * ib + g, j = c0 + 2 * t;
+                const bool v0 = i < n && j <= i, v1 = i < n && j + 1 <= i;
+                double d0 = v0 ? A[ptri(i, j)] : 0.0, d1 = v1 ? A[ptri(i, j + 1)] : 0.0;
+                for (int k0 = 0; k0 < c0; k0 += 4) {
+                    const double a = i < n ? -A[ptri(i, k0 + t)] : 0.0;     // k < c0 <= i, jb: strictly lower entries (true L values)
+                    const double b = jb < n ? A[ptri(jb, k0 + t)] : 0.0;
+                    dmma_8x8x4(d0, d1, a, b);
+                }
+                if (v0) A[ptri(i, j)] = d0;
+                if (v1) A[ptri(i, j + 1)] = d1;
+            }
+            __syncwarp();
         }
-        double d = __shfl_sync(0xffffffffu, s, 0);
-        if (d < ILQG_MINVAL) d = ILQG_MINVAL;
-        const double rinv = rsqrt(d);
-        if (i < n) A[ptri(i, j)] = (i == j) ? rinv : s * rinv;
+        // The 8 x 8 diagonal tile is factored by EVERY lane in registers (same arithmetic, same result): no shuffles, no
+        // barriers inside the panel.  Each row below the panel is then one lane's private forward substitution against it.
+        double T[8][8], rinv[8];
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+#pragma unroll
+            for (int bb = 0; bb <= a; bb++) T[a][bb] = c0 + a < n ? A[ptri(c0 + a, c0 + bb)] : (a == bb ? 1.0 : 0.0);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            double d = T[j][j];
+#pragma unroll
+            for (int k = 0; k < j; k++) d -= T[j][k] * T[j][k];
+            if (d < ILQG_MINVAL) d = ILQG_MINVAL;
+            rinv[j] = rsqrt(d);
+#pragma unroll
+            for (int a = j + 1; a < 8; a++) {
+                double sa = T[a][j];
+#pragma unroll
+                for (int k = 0; k < j; k++) sa -= T[a][k] * T[j][k];
+                T[a][j] = sa * rinv[j];
+            }
+        }
+        const int i = c0 + 8 + lane;
+        if (i < n) {
+            double* ri = A + ptri(i, c0);
+            double x[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                double sx = ri[j];
+#pragma unroll
+                for (int k = 0; k < j; k++) sx -= x[k] * T[j][k];
+                x[j] = sx * rinv[j];
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) ri[j] = x[j];
+        }
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+            if (lane == a && c0 + a < n) {
+                double* ra = A + ptri(c0 + a, c0);
+#pragma unroll
+                for (int bb = 0; bb < a; bb++) ra[bb] = T[a][bb];
+                ra[a] = rinv[a];
+            }
         __syncwarp();
     }
 }
@@ -628,19 +688,53 @@ DEV void coop_smooth(const GModel* __restrict__ g, CoopMem& w, const double* uu,
 struct Mask128 { unsigned w[4]; };
 DEV bool operator==(const Mask128& a, const Mask128& b) { return a.w[0] == b.w[0] && a.w[1] == b.w[1] && a.w[2] == b.w[2] && a.w[3] == b.w[3]; }
 
-// Newton Hessian M + sum_active D_r J_r J_r' (packed) into `H`, then its Cholesky factor in place
+// Newton Hessian M + sum_active D_r J_r J_r' (packed) into `H`, then its Cholesky factor in place.
+// The rank-na update is the one dense contraction of this path that ncu shows as dense enough for the tensor cores (13 % of
+// the instructions of a full humanoid evaluation when done entry by entry, profiles/r01_humanoid_coop_kernels.md): it runs as
+// fp64 DMMA (mma.sync m8n8k4) over 8 x 8 tiles of the lower triangle.  Per k-step of four active rows the warp loads the rows'
+// D and four 8-wide slices of J once and issues one DMMA per tile: A = D_r J_r[i-slice] (8 x 4), B = J_r[j-slice] (4 x 8).
+// Fragment layout (PTX ISA, m8n8k4 .f64): a: row = lane / 4, k = lane % 4;  b: k = lane % 4, col = lane / 4;
+// c/d: row = lane / 4, cols = 2 (lane % 4) + {0, 1}.
 DEV void coop_hessian_factor(const CoopMem& w, double* H, int nv, int na, int lane) {
-    const int nt = coop_nt(nv);
-    for (int e = lane; e < nt; e += 32) {
-        // e -> (i, j), j <= i
-        int i = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
-        while (ptri(i + 1, 0) <= e) i++;
-        while (ptri(i, 0) > e) i--;
-        const int j = e - ptri(i, 0);
-        double h = w.M[e];
-        for (int a = 0; a < na; a++) { const double* Jr = w.J + w.alist[a] * nv; h += w.D[w.alist[a]] * Jr[i] * Jr[j]; }
-        H[e] = h;
+    constexpr int NB8 = COOP_NMAX / 8;           // 8-wide blocks per side
+    const int nblk = (nv + 7) >> 3;
+    const int g = lane >> 2, t = lane & 3;       // fragment coordinates
+    double acc[NB8 * (NB8 + 1) / 2][2];
+#pragma unroll
+    for (int ib = 0; ib < NB8; ib++)
+#pragma unroll
+        for (int jb = 0; jb <= ib; jb++) {
+            const int tile = ib * (ib + 1) / 2 + jb, i = 8 * ib + g, j = 8 * jb + 2 * t;
+            acc[tile][0] = (ib < nblk && i < nv && j <= i) ? w.M[ptri(i, j)] : 0.0;
+            acc[tile][1] = (ib < nblk && i < nv && j + 1 <= i) ? w.M[ptri(i, j + 1)] : 0.0;
+        }
+    for (int a0 = 0; a0 < na; a0 += 4) {
+        const bool in = a0 + t < na;
+        const int r = in ? w.alist[a0 + t] : 0;
+        const double D = in ? w.D[r] : 0.0;
+        const double* Jr = w.J + r * nv;
+        double Jv[NB8];
+#pragma unroll
+        for (int bb = 0; bb < NB8; bb++) Jv[bb] = (in && 8 * bb + g < nv) ? Jr[8 * bb + g] : 0.0;
+#pragma unroll
+        for (int ib = 0; ib < NB8; ib++) {
+            if (ib < nblk) {   // uniform
+                const double av = D * Jv[ib];
+#pragma unroll
+                for (int jb = 0; jb <= ib; jb++) dmma_8x8x4(acc[ib * (ib + 1) / 2 + jb][0], acc[ib * (ib + 1) / 2 + jb][1], av, Jv[jb]);
+            }
+        }
     }
+#pragma unroll
+    for (int ib = 0; ib < NB8; ib++)
+#pragma unroll
+        for (int jb = 0; jb <= ib; jb++) {
+            const int tile = ib * (ib + 1) / 2 + jb, i = 8 * ib + g, j = 8 * jb + 2 * t;
+            if (ib < nblk && i < nv) {
+                if (j <= i) H[ptri(i, j)] = acc[tile][0];
+                if (j + 1 <= i) H[ptri(i, j + 1)] = acc[tile][1];
+            }
+        }
     __syncwarp();
     coop_chol(H, nv, lane);
 }

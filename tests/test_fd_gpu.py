@@ -202,3 +202,19 @@ def test_both_fd_kernel_variants(pkg, oracle, omodels, variant, name, n, roll):
     nj = m.nv * (2 * m.nv + m.nu)
     assert np.array_equal(d2[:, nj:], pre[:, nj:]) and np.array_equal(d2[:, :nj], d_gpu[:, :nj])
     h.close()
+
+
+def test_empty_and_single_knot_batches(handles, pkg):
+    """nknots = 0 is a no-op that returns OK on every entry point (host and device flavours); nknots = 1 works."""
+    import torch
+    L = pkg.lib()
+    for name in ("inverted_pendulum", "hopper"):
+        h = handles[name]; m = h.model
+        assert L.ilqg_fd_batch_host(h._h, 0, None, None, None, None, None, None, None, None, None) == pkg.OK
+        assert L.ilqg_fd_batch_dev(h._h, 0, None, None, None, None, None, None, None, None, None, None) == pkg.OK
+        assert L.ilqg_step_batch_host(h._h, 0, 5, None, None, None, None, None) == pkg.OK
+        assert L.ilqg_forward_batch_dev(h._h, 0, None, None, None, None, None, None) == pkg.OK
+        assert L.ilqg_fd_batch_host(h._h, -1, None, None, None, None, None, None, None, None, None) == pkg.ERR_ARG
+        q = np.zeros((1, m.nq)); q[0, min(1, m.nq - 1)] = 1.2 if name == "hopper" else 0.1
+        d, a, st = h.fd_batch_host(q, np.zeros((1, m.nv)), np.zeros((1, m.nu)), None, None)
+        assert d.shape == (1, m.nd) and st[0] == 0 and np.isfinite(d[:, :m.nv * (2 * m.nv + m.nu)]).all()

@@ -341,15 +341,17 @@ def bench_humanoid(pkg, dev_index, nknots, steps, world, rank, with_cpu):
         o = entry.load_oracle()
         om = o.Model(os.path.join(pkg.MODELS_DIR, "humanoid.ilqgm"))
         ns = min(nknots, 4 * (os.cpu_count() or 1))
-        sq, sv, su, sw = (x[:ns].cpu().numpy().copy() for x in (q, v, u, w))
+        kidx = np.linspace(0, nknots - 1, ns).astype(np.int64)   # strided: the generator orders the states by pre-roll length
+        kt = torch.from_numpy(kidx).to(dev)
+        sq, sv, su, sw = (x[kt].cpu().numpy().copy() for x in (q, v, u, w))
         t0 = time.perf_counter()
         dref, _, flops = o.fd_batch(om, sq, sv, su, sw, None, nthreads=0)
         dt = time.perf_counter() - t0
-        ok = st[:ns] == 0
-        dg = deriv[:ns].cpu().numpy()[:, :model.nv * (2 * model.nv + model.nu)]
+        ok = st[kidx] == 0
+        dg = deriv[kt].cpu().numpy()[:, :model.nv * (2 * model.nv + model.nu)]
         dr = dref[:, :model.nv * (2 * model.nv + model.nu)]
         res["cpu_baseline"] = {"value": ns / dt, "unit": "knots/s", "cores": os.cpu_count(), "kind": "port",
-                               "sample": f"first {ns} knots, oracle FD, OpenMP over knots"}
+                               "sample": f"{ns} knots spread over the batch, oracle FD, OpenMP over knots"}
         res["flops_per_knot_oracle"] = flops / ns
         if ok.any():
             res["parity_sample_max_rel_err"] = float(np.abs(dg[ok] - dr[ok]).max() / max(1.0, np.abs(dr[ok]).max()))
@@ -522,8 +524,24 @@ def run_gpu_arm(args):
         if world == 1:
             o = entry.load_oracle()
             om = o.Model(os.path.join(pkg.MODELS_DIR, "hopper.ilqgm"))
-            ns = min(nk, args.cpu_sample)
-            sq, sv, su, sw = (t[:ns].cpu().numpy().copy() for t in (q, v, u, w))
+            # a REPRESENTATIVE sample: every stride-th trajectory (the generator orders trajectories by pre-roll length, so a
+            # prefix of the batch would be the knots still in flight and would under-count the work per knot)
+            ntraj_all = nk // args.T
+            ntraj_s = max(1, min(ntraj_all, args.cpu_sample // args.T))
+            pick = (np.arange(ntraj_s) * (ntraj_all / ntraj_s)).astype(np.int64)
+            kidx = (pick[:, None] * args.T + np.arange(args.T)[None, :]).reshape(-1)
+            ns = kidx.size
+            kidx_t = torch.from_numpy(kidx).to(dev)
+            sq, sv, su, sw = (t[kidx_t].cpu().numpy().copy() for t in (q, v, u, w))
+            # share of the sample's knots with at least one active contact at the centre (report stance and flight)
+            ninfo = min(ns, 1024)
+            sel = np.linspace(0, ns - 1, ninfo).astype(np.int64)
+            info = np.zeros(4, np.int32); qa = np.zeros(om.nv); ncontact = 0
+            for i in sel:
+                o.lib().mjo_debug_forward(om.ptr, o._p(sq[i]), o._p(sv[i]), o._p(su[i]), o._p(sw[i]), 30, C.c_double(0.0), o._p(qa),
+                                          info.ctypes.data_as(C.c_void_p), None, None, None)
+                ncontact += int(info[0] > 0)
+            line["config"]["contact_share_of_knots"] = ncontact / ninfo
             # (i) fair port: OpenMP over knots, all cores; also yields the oracle-counted flops per knot
             t0 = time.perf_counter()
             dref, _, flops = o.fd_batch(om, sq, sv, su, sw, cost, nthreads=0)
@@ -540,16 +558,16 @@ def run_gpu_arm(args):
                                      "how": "oracle-counted fp64 flops per knot (FMA=2, under the reference's stage-skipping schedule) on a sample of this workload x knots / (sum of the three FD kernels' time); "
                                             "peak = DFMA-chain microbenchmark run now on this GPU (MEASURED_PEAKS.json has no fp64 figure)"}
             # parity spot check of the timed outputs against the oracle on the sample
-            dg = deriv[:ns].cpu().numpy()
+            dg = deriv[kidx_t].cpu().numpy()
             err = float(np.abs(dg - dref).max() / max(1.0, np.abs(dref).max()))
             line["parity_sample_max_rel_err"] = err
             if r is not None:
                 rdt, rc, _ = r
                 line["cpu_baseline"] = {"value": nr / rdt, "unit": UNIT, "cores": rc, "kind": "reference",
-                                        "sample": f"first {nr} knots of this workload; the reference's calcMJDerivatives (verbatim source, oracle "
+                                        "sample": f"{nr} knots of this workload (every {ntraj_all // ntraj_s}th trajectory); the reference's calcMJDerivatives (verbatim source, oracle "
                                                   "physics) knot by knot, OpenMP over FD columns"}
             line["cpu_baseline_port"] = {"value": ns / port_s, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                                         "sample": f"first {ns} knots of this workload; oracle FD, OpenMP over knots, persistent scratch"}
+                                         "sample": f"{ns} knots of this workload (every {ntraj_all // ntraj_s}th trajectory); oracle FD, OpenMP over knots, persistent scratch"}
             if "cpu_baseline" not in line:
                 line["cpu_baseline"] = line["cpu_baseline_port"]
         print(json.dumps(line), flush=True)

@@ -951,39 +951,39 @@ DEV void step(const DevModel<T>& m, Work<T>& w, double (&q)[T::NQ], double (&v)[
               double (&warm)[T::NV], double (&qacc)[T::NV]) {
     constexpr int NV = T::NV, NQ = T::NQ, NT = NV * (NV + 1) / 2;
     const double h = m.timestep;
-    if (m.integrator == ILQG_INT_RK4) {
-        // One copy of the pipeline in a 4-trip loop (not four inlined copies): a rollout thread runs this chain alone on its
-        // SM sub-partition and a 4x smaller body is what the instruction cache needs.  The stage values are folded into the
-        // RK4 combination as they appear, in the tableau's order: (1/6) k0 + (1/3) k1 + (1/3) k2 + (1/6) k3.
-        double q0[NQ], v0[NV], Xp[NV], Fp[NV], dX[NV], dF[NV];
-        sfor<0, NQ>([&](auto ii) { q0[IDX(ii)] = q[IDX(ii)]; });
-        sfor<0, NV>([&](auto ii) { v0[IDX(ii)] = v[IDX(ii)]; dX[IDX(ii)] = 0; dF[IDX(ii)] = 0; Xp[IDX(ii)] = 0; Fp[IDX(ii)] = 0; });
+    // ONE copy of the pipeline for both integrators (a rollout thread runs this chain alone on its SM sub-partition: the
+    // instruction footprint is what limits it).  RK4: a 4-trip loop, the stage values folded into the combination as they
+    // appear, in the tableau's order (1/6) k0 + (1/3) k1 + (1/3) k2 + (1/6) k3.  Euler: one trip, then the implicit-damping update.
+    const bool rk4 = m.integrator == ILQG_INT_RK4;
+    const int nstage = rk4 ? 4 : 1;
+    double q0[NQ], v0[NV], Xp[NV], Fp[NV], dX[NV], dF[NV];
+    sfor<0, NQ>([&](auto ii) { q0[IDX(ii)] = q[IDX(ii)]; });
+    sfor<0, NV>([&](auto ii) { v0[IDX(ii)] = v[IDX(ii)]; dX[IDX(ii)] = 0; dF[IDX(ii)] = 0; Xp[IDX(ii)] = 0; Fp[IDX(ii)] = 0; });
 #pragma unroll 1
-        for (int s = 0; s < 4; s++) {
-            if (s > 0) {
-                const double a = s == 3 ? 1.0 : 0.5;  // the only non-zero tableau entry of row s-1 sits at column s-1
-                double sx[NV];
-                sfor<0, NV>([&](auto ii) { sx[IDX(ii)] = a * Xp[IDX(ii)]; });
-                sfor<0, NQ>([&](auto ii) { q[IDX(ii)] = q0[IDX(ii)]; });
-                integrate_pos<T>(q, sx, h);
-                sfor<0, NV>([&](auto ii) { v[IDX(ii)] = v0[IDX(ii)] + h * (a * Fp[IDX(ii)]); });
-            }
-            build_problem<T>(m, q, v, u, w);
-            solve<T>(m, w, warm, qacc, m.iterations, m.tolerance);
-            const double wgt = (s == 0 || s == 3) ? 1.0 / 6 : 1.0 / 3;
-            sfor<0, NV>([&](auto ii) {
-                constexpr int i = IDX(ii);
-                Xp[i] = v[i]; Fp[i] = qacc[i];
-                dX[i] = fma(wgt, Xp[i], dX[i]);
-                dF[i] = fma(wgt, Fp[i], dF[i]);
-            });
+    for (int s = 0; s < nstage; s++) {
+        if (s > 0) {
+            const double a = s == 3 ? 1.0 : 0.5;  // the only non-zero tableau entry of row s-1 sits at column s-1
+            double sx[NV];
+            sfor<0, NV>([&](auto ii) { sx[IDX(ii)] = a * Xp[IDX(ii)]; });
+            sfor<0, NQ>([&](auto ii) { q[IDX(ii)] = q0[IDX(ii)]; });
+            integrate_pos<T>(q, sx, h);
+            sfor<0, NV>([&](auto ii) { v[IDX(ii)] = v0[IDX(ii)] + h * (a * Fp[IDX(ii)]); });
         }
+        build_problem<T>(m, q, v, u, w);
+        solve<T>(m, w, warm, qacc, m.iterations, m.tolerance, !rk4);
+        const double wgt = (s == 0 || s == 3) ? 1.0 / 6 : 1.0 / 3;
+        sfor<0, NV>([&](auto ii) {
+            constexpr int i = IDX(ii);
+            Xp[i] = v[i]; Fp[i] = qacc[i];
+            dX[i] = fma(wgt, Xp[i], dX[i]);
+            dF[i] = fma(wgt, Fp[i], dF[i]);
+        });
+    }
+    if (rk4) {
         sfor<0, NQ>([&](auto ii) { q[IDX(ii)] = q0[IDX(ii)]; });
         sfor<0, NV>([&](auto ii) { v[IDX(ii)] = v0[IDX(ii)] + h * dF[IDX(ii)]; });
         integrate_pos<T>(q, dX, h);
     } else {
-        build_problem<T>(m, q, v, u, w);
-        solve<T>(m, w, warm, qacc, m.iterations, m.tolerance, true);
         double a[NV];
         if constexpr (T::ANY_DAMPING) {
             double A[NT], La[NT];

@@ -78,3 +78,25 @@ def test_capacity_overflow_is_flagged(generic_handles, pkg):
     v = np.zeros((1, 27)); u = np.zeros((1, 21)); w = np.zeros((1, 27))
     d, a, status = h.fd_batch_host(q, v, u, w, None)
     assert status[0] in (0, pkg.ERR_CAPACITY, pkg.ERR_NONFINITE)
+
+
+def test_generic_engine_is_idempotent_and_chunk_invariant(generic_handles, handles, pkg):
+    """The warp-cooperative engine linearises in passes of <= 8192 knots (its C-state scratch): a batch that crosses the pass
+    boundary must equal the same knots computed alone, bit for bit, and the thread-per-rollout kernels to the FD tolerance."""
+    import torch
+    from ilqg_mujoco_b200 import workload as wl
+    h = generic_handles["hopper"]; ht = handles["hopper"]
+    q, v, u, w, _ = wl.make_knots(ht, 400, 21, seed=5, device="cuda:0", model="hopper")     # 8400 knots > one pass
+    n = q.shape[0]
+    cost = pkg.make_cost(q1=[1.0])
+    a = torch.zeros((n, h.model.nd), dtype=torch.float64, device="cuda:0"); b = torch.zeros_like(a); c = torch.zeros_like(a)
+    sa = torch.zeros(n, dtype=torch.int32, device="cuda:0")
+    h.fd_batch_dev(q, v, u, w, a, None, sa, cost=cost)
+    h.fd_batch_dev(q, v, u, w, b, cost=cost)
+    assert int((sa != 0).sum()) == 0 and torch.equal(a, b)
+    lo, hi = 8100, 8400                                      # straddles the 8192 boundary when part of the full batch
+    part = torch.zeros((hi - lo, h.model.nd), dtype=torch.float64, device="cuda:0")
+    h.fd_batch_dev(q[lo:hi], v[lo:hi], u[lo:hi], w[lo:hi], part, cost=cost)
+    assert torch.equal(part, a[lo:hi])
+    ht.fd_batch_dev(q, v, u, w, c, cost=cost)
+    assert_deriv_close(a.cpu().numpy(), c.cpu().numpy(), 6, 3)

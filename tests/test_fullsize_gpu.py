@@ -1,0 +1,87 @@
+"""BASELINE.json's full size (configs[1]: 4096 trajectories x 21 hopper knots = 86,016 knots on one GPU) through
+size-independent properties, plus an oracle spot check on a strided sample:
+  * idempotence: the same call twice is bit-identical (no data races, no dependence on scheduling);
+  * batch-split invariance: every knot's block is independent of which other knots share the launch — a slice computed alone
+    (same kernel variant) is bit-identical to the slice of the full batch, the other kernel variant agrees to the FD tolerance;
+  * permutation: permuting the knots permutes the blocks;
+  * the host-pointer entry point (chunked copy/compute pipeline) returns the device-pointer result bit for bit."""
+import os
+
+import numpy as np
+import pytest
+
+from test_fd_gpu import assert_deriv_close
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def full(pkg):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from ilqg_mujoco_b200 import workload as wl
+    os.environ["ILQG_FD_VARIANT"] = "3"
+    try:
+        h = pkg.Handle(pkg.Model.named("hopper"), 0)
+    finally:
+        del os.environ["ILQG_FD_VARIANT"]
+    q, v, u, w, _ = wl.make_knots(h, 4096, 21, seed=0, device="cuda:0", model="hopper")
+    cost = pkg.make_cost(q1=[1.0])
+    n = q.shape[0]
+    deriv = torch.zeros((n, h.model.nd), dtype=torch.float64, device="cuda:0")
+    status = torch.zeros(n, dtype=torch.int32, device="cuda:0")
+    h.fd_batch_dev(q, v, u, w, deriv, None, status, cost=cost)
+    torch.cuda.synchronize()
+    yield dict(h=h, q=q, v=v, u=u, w=w, cost=cost, deriv=deriv, status=status, n=n)
+    h.close()
+
+
+def test_full_batch_is_finite_and_idempotent(full):
+    import torch
+    f = full
+    assert f["n"] == 86016 and int((f["status"] != 0).sum()) == 0
+    assert bool(torch.isfinite(f["deriv"]).all())
+    again = torch.zeros_like(f["deriv"])
+    f["h"].fd_batch_dev(f["q"], f["v"], f["u"], f["w"], again, cost=f["cost"])
+    assert torch.equal(again, f["deriv"])
+
+
+def test_batch_split_and_permutation_invariance(full, pkg):
+    import torch
+    f = full; h = f["h"]
+    lo, hi = 30000, 30000 + 17011            # a ragged slice, still the split kernels (forced variant 3)
+    part = torch.zeros((hi - lo, h.model.nd), dtype=torch.float64, device="cuda:0")
+    h.fd_batch_dev(f["q"][lo:hi], f["v"][lo:hi], f["u"][lo:hi], f["w"][lo:hi], part, cost=f["cost"])
+    assert torch.equal(part, f["deriv"][lo:hi])
+    perm = torch.randperm(f["n"], generator=torch.Generator().manual_seed(3)).to("cuda:0")
+    out = torch.zeros_like(f["deriv"])
+    h.fd_batch_dev(f["q"][perm].contiguous(), f["v"][perm].contiguous(), f["u"][perm].contiguous(), f["w"][perm].contiguous(), out, cost=f["cost"])
+    assert torch.equal(out, f["deriv"][perm])
+    # the single-launch kernel (what small batches use) on a slice: same numbers to the FD tolerance
+    os.environ["ILQG_FD_VARIANT"] = "2"
+    try:
+        h2 = pkg.Handle(pkg.Model.named("hopper"), 0)
+    finally:
+        del os.environ["ILQG_FD_VARIANT"]
+    other = torch.zeros((4000, h.model.nd), dtype=torch.float64, device="cuda:0")
+    h2.fd_batch_dev(f["q"][50000:54000], f["v"][50000:54000], f["u"][50000:54000], f["w"][50000:54000], other, cost=f["cost"])
+    assert_deriv_close(other.cpu().numpy(), f["deriv"][50000:54000].cpu().numpy(), 6, 3)
+    h2.close()
+
+
+def test_host_entry_point_equals_device_path(full):
+    f = full; h = f["h"]
+    d, a, st = h.fd_batch_host(f["q"].cpu().numpy(), f["v"].cpu().numpy(), f["u"].cpu().numpy(), f["w"].cpu().numpy(), f["cost"])
+    assert st.sum() == 0
+    assert np.array_equal(d, f["deriv"].cpu().numpy())
+
+
+def test_strided_sample_matches_oracle(full, oracle, omodels):
+    f = full
+    idx = np.arange(0, f["n"], 97)           # 887 knots spread over flight and stance trajectories
+    import torch
+    it = torch.from_numpy(idx).to("cuda:0")
+    q, v, u, w = (f[k][it].cpu().numpy() for k in ("q", "v", "u", "w"))
+    d_ref, _, _ = oracle.fd_batch(omodels["hopper"], q, v, u, w, f["cost"])
+    assert_deriv_close(f["deriv"][it].cpu().numpy(), d_ref, 6, 3)

@@ -86,6 +86,11 @@ bool dev_model_from_tables(const ilqg_model& s, DevModel<T>& d) {
         if (s.body_parentid[b] != T::body_parent(b) || s.body_rootid[b] != T::body_root(b) || s.body_jntadr[b] != T::body_jntadr(b) ||
             s.body_jntnum[b] != T::body_jntnum(b) || s.body_dofadr[b] != T::body_dofadr(b) || s.body_dofnum[b] != T::body_dofnum(b))
             return false;
+    for (int b = 0; b < T::NBODY; b++)   // constants the kernels fold at compile time
+        if (T::body_quat_identity(b) && !(s.body_quat[b][0] == 1 && s.body_quat[b][1] == 0 && s.body_quat[b][2] == 0 && s.body_quat[b][3] == 0))
+            return false;
+    for (int j = 0; j < T::NJNT; j++)
+        if (T::jnt_pos_zero(j) && !(s.jnt_pos[j][0] == 0 && s.jnt_pos[j][1] == 0 && s.jnt_pos[j][2] == 0)) return false;
     for (int j = 0; j < T::NJNT; j++)
         if (s.jnt_type[j] != T::jnt_type(j) || s.jnt_bodyid[j] != T::jnt_body(j) || s.jnt_qposadr[j] != T::jnt_qposadr(j) ||
             s.jnt_dofadr[j] != T::jnt_dofadr(j) || (s.jnt_limited[j] != 0) != (T::jnt_limited(j) != 0) ||
@@ -348,27 +353,36 @@ DEV void build_pos(const DevModel<T>& m, const double (&q)[T::NQ], PosStage<T>& 
     xquat[0] = {1, 0, 0, 0};
     xmat[0] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
     // ---- mj_kinematics
+    // Exact folds (topology flags, verified against the runtime tables when the model is bound): an identity body quaternion
+    // leaves the parent's frame untouched (q * 1 = q and q2m of the same quaternion is the parent's xmat, bit for bit), a joint
+    // at the body origin has anchor = pos and no off-centre correction (R * 0 = 0).
     sfor<1, NB>([&](auto bb) {
         constexpr int b = IDX(bb), p = T::body_parent(b);
+        constexpr bool qid = T::body_quat_identity(b) != 0;
         V3 pos;
         Q4 quat;
+        M3 R;   // rotation of `quat`, valid while only slide joints have been applied (see slide_only below)
         if constexpr (p == 0) {
             pos = ld3(m.body_pos[b]);
-            quat = {m.body_quat[b][0], m.body_quat[b][1], m.body_quat[b][2], m.body_quat[b][3]};
+            if constexpr (qid) { quat = {1, 0, 0, 0}; R = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}; }
+            else { quat = {m.body_quat[b][0], m.body_quat[b][1], m.body_quat[b][2], m.body_quat[b][3]}; R = q2m(quat); }
         } else {
             pos = xpos[p] + mulv(xmat[p], ld3(m.body_pos[b]));
-            quat = qmul(xquat[p], {m.body_quat[b][0], m.body_quat[b][1], m.body_quat[b][2], m.body_quat[b][3]});
+            if constexpr (qid) { quat = xquat[p]; R = xmat[p]; }
+            else { quat = qmul(xquat[p], {m.body_quat[b][0], m.body_quat[b][1], m.body_quat[b][2], m.body_quat[b][3]}); R = q2m(quat); }
         }
         sfor<0, T::body_jntnum(b)>([&](auto jj) {
             constexpr int j = T::body_jntadr(b) + IDX(jj), qa = T::jnt_qposadr(j), ty = T::jnt_type(j);
             if constexpr (ty == ILQG_JNT_FREE) {
                 pos = {q[qa], q[qa + 1], q[qa + 2]};
                 quat = qnormalized({q[qa + 3], q[qa + 4], q[qa + 5], q[qa + 6]});
+                R = q2m(quat);
                 anchor[j] = pos;
                 axis[j] = {0, 0, 1};
             } else {
-                M3 R = q2m(quat);
-                anchor[j] = pos + mulv(R, ld3(m.jnt_pos[j]));
+                constexpr bool jz = T::jnt_pos_zero(j) != 0;
+                if constexpr (jz) anchor[j] = pos;
+                else anchor[j] = pos + mulv(R, ld3(m.jnt_pos[j]));
                 axis[j] = mulv(R, ld3(m.jnt_axis[j]));
                 double qq = q[qa] - m.qpos0[qa];
                 if constexpr (ty == ILQG_JNT_SLIDE) {
@@ -377,7 +391,10 @@ DEV void build_pos(const DevModel<T>& m, const double (&q)[T::NQ], PosStage<T>& 
                     double s, c;
                     sincos(0.5 * qq, &s, &c);
                     quat = qmul(quat, {c, m.jnt_axis[j][0] * s, m.jnt_axis[j][1] * s, m.jnt_axis[j][2] * s});
-                    pos = anchor[j] - mulv(q2m(quat), ld3(m.jnt_pos[j]));
+                    constexpr bool last = IDX(jj) + 1 == T::body_jntnum(b);
+                    if constexpr (!jz || !last) R = q2m(quat);   // the rotated frame: off-centre correction and / or the next joint
+                    if constexpr (jz) pos = anchor[j];
+                    else pos = anchor[j] - mulv(R, ld3(m.jnt_pos[j]));
                 }
             }
         });

@@ -72,7 +72,10 @@ class PeerDeriv:
             handles = [None] * self.world
             dist.all_gather_object(handles, hd, group=group)
         self.ptrs = [self.own if r == self.rank else handle.peer_open(handles[r]) for r in range(self.world)]
-        self.full = torch.as_tensor(_DevArray(self.own, (self.T, self.nd)), device=f"cuda:{torch.cuda.current_device()}")
+        if hasattr(handle, "peer_view"):   # host-memory stand-in used by the CPU (gloo) tests of this logic
+            self.full = handle.peer_view(self.own, (self.T, self.nd))
+        else:
+            self.full = torch.as_tensor(_DevArray(self.own, (self.T, self.nd)), device=f"cuda:{torch.cuda.current_device()}")
 
     def scatter_ptrs(self, first_knot):
         """Destination addresses of knot `first_knot` in every rank's copy, this rank's first."""

@@ -558,9 +558,15 @@ DEV void build_pos(const DevModel<T>& m, const double (&q)[T::NQ], PosStage<T>& 
             } else if constexpr (t1 == ILQG_GEOM_CAPSULE && t2 == ILQG_GEOM_CAPSULE) {
                 V3 p1 = gpos[g1], a1 = gax[g1], p2 = gpos[g2], a2 = gax[g2];
                 double r1 = m.geom_size[g1][0], h1 = m.geom_size[g1][1], r2 = m.geom_size[g2][0], h2 = m.geom_size[g2][1];
-                // candidate closest-point pairs on the two axis segments (at most two survive the distance test)
+                // exact cull: the capsules lie inside spheres of radius h + r about their centres; if even those are farther apart
+                // than the margin the narrow phase below cannot produce a contact (its distance is at least this one).  Self-collision
+                // pairs are almost always culled here, and the closest-point search is the most expensive piece of the position stage.
                 V3 ca[2], cb[2];
                 int ncand = 0;
+                const double reach = h1 + r1 + h2 + r2 + margin;
+                const V3 cc = p1 - p2;
+                if (!(reach > 0 && dot(cc, cc) > reach * reach)) {
+                // candidate closest-point pairs on the two axis segments (at most two survive the distance test)
                 auto consider = [&](V3 c1, V3 c2) {
                     V3 d = c2 - c1;
                     if (sqrt(dot(d, d)) - r1 - r2 > margin) return false;
@@ -602,6 +608,7 @@ DEV void build_pos(const DevModel<T>& m, const double (&q)[T::NQ], PosStage<T>& 
                             }
                         consider(bq1, bq2);
                     }
+                }
                 }
 #pragma unroll 1
                 for (int c = 0; c < ncand; c++) sphere_sphere(c ? ca[1] : ca[0], r1, c ? cb[1] : cb[0], r2);

@@ -602,7 +602,10 @@ def run_gpu_arm(args):
             flops_per_knot = flops / ns
             # (ii) the reference's own driver (knots serial, OpenMP over columns), smaller sample
             nr = min(ns, args.ref_sample)
-            r = time_reference_driver(o, om, sq[:nr], sv[:nr], su[:nr], sw[:nr], cost)
+            rsel = (np.arange(nr // args.T) * max(1, (ns // args.T) // max(1, nr // args.T)))[:, None] * args.T + np.arange(args.T)[None, :]
+            rsel = rsel.reshape(-1)
+            nr = rsel.size
+            r = time_reference_driver(o, om, sq[rsel].copy(), sv[rsel].copy(), su[rsel].copy(), sw[rsel].copy(), cost)
             tf = C.c_double(0)
             L.ilqg_fp64_peak(local, C.byref(tf))
             ach_tf = flops_per_knot * nk / ((p_ms + c_ms) * 1e-3) / 1e12
@@ -617,10 +620,10 @@ def run_gpu_arm(args):
             if r is not None:
                 rdt, rc, _ = r
                 line["cpu_baseline"] = {"value": nr / rdt, "unit": UNIT, "cores": rc, "kind": "reference",
-                                        "sample": f"{nr} knots of this workload (every {ntraj_all // ntraj_s}th trajectory); the reference's calcMJDerivatives (verbatim source, oracle "
+                                        "sample": f"{nr} knots of this workload (trajectories spread over the batch); the reference's calcMJDerivatives (verbatim source, oracle "
                                                   "physics) knot by knot, OpenMP over FD columns"}
             line["cpu_baseline_port"] = {"value": ns / port_s, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                                         "sample": f"{ns} knots of this workload (every {ntraj_all // ntraj_s}th trajectory); oracle FD, OpenMP over knots, persistent scratch"}
+                                         "sample": f"{ns} knots of this workload (trajectories spread over the batch); oracle FD, OpenMP over knots, persistent scratch"}
             if "cpu_baseline" not in line:
                 line["cpu_baseline"] = line["cpu_baseline_port"]
         print(json.dumps(line), flush=True)
@@ -638,8 +641,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ntraj", type=int, default=4096)
     ap.add_argument("--T", type=int, default=21)
-    ap.add_argument("--cpu-sample", type=int, default=21 * 1024, help="knots of the workload timed on the CPU port (rank 0, N=1)")
-    ap.add_argument("--ref-sample", type=int, default=21 * 48, help="knots timed through the reference's own driver in the GPU arm")
+    ap.add_argument("--cpu-sample", type=int, default=21 * 4096, help="knots of the workload timed on the CPU port (rank 0, N=1)")
+    ap.add_argument("--ref-sample", type=int, default=21 * 1024, help="knots timed through the reference's own driver in the GPU arm")
     ap.add_argument("--ref-traj", type=int, default=24, help="trajectories per step in --impl reference")
     ap.add_argument("--ilqr-instances", type=int, default=4096, help="pendulum iLQR problems per GPU (secondary metric)")
     ap.add_argument("--humanoid-knots", type=int, default=4096, help="humanoid knots per GPU (secondary metric)")

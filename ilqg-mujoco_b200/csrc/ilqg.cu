@@ -965,7 +965,8 @@ int ilqg_fd_batch_host(ilqg_handle h, int nknots, const double* qpos, const doub
         dcost = h->d_cost;
     }
     // chunks large enough for the stage-skipping kernels (>= 16384 knots), four of them at the benchmark size: measured best
-    // on B200 (86,016 hopper knots: 1 chunk 3.11 ms, 2: 2.33, 4: 2.04, 8: 2.25, 16: 2.85; raw D2H of deriv alone: 1.35 ms)
+    // on B200 (86,016 hopper knots: 1 chunk 3.11 ms, 2: 2.33, 4: 2.04, 8: 2.25, 16: 2.85; raw D2H of deriv alone: 1.35 ms).
+    // Also measured and not better: centre evaluations for all knots in one launch first, then the columns chunk by chunk (2.08 ms).
     size_t nchunks = n / 20000 < 4 ? (n >= 8192 ? 4 : 1) : n / 20000;
     if (h->host_chunks > 0) nchunks = (size_t)h->host_chunks;   // ILQG_HOST_CHUNKS (experiments)
     const size_t chunk = (n + nchunks - 1) / nchunks;

@@ -48,23 +48,62 @@ DEV void load_knot(int k, const double* qpos, const double* qvel, const double* 
 }
 
 // ------------------------------------------------------------------ FD: centre
+// Work classes of a batch (large batches only).  The cost of a knot's perturbed evaluations is set by the number of constraint
+// rows its solves walk (0 in flight, 4 per contact point in stance, +1 per joint at its limit), so the centre kernel — which
+// knows that number — ranks every knot inside the bucket of its row count, heaviest bucket first; fd_bin_kernel turns the
+// ranks into a permutation and the column kernels take their knots through it.  Lanes of a warp and warps of a CTA then run
+// the same solver trip counts (no lane waits for a neighbour in contact, no CTA for its one stance warp), and the heavy CTAs
+// start first.  Placement only: every knot's arithmetic is unchanged.
+constexpr int FD_NBUCKET = 64;
+struct FdBins {
+    int* cnt;            // [FD_NBUCKET] knots per bucket (zeroed before the centre kernel)
+    unsigned int* key;   // [nknots] bucket << 24 | rank inside the bucket
+    int* perm;           // [nknots] slot -> knot
+};
+
 template <class T>
 __global__ void __launch_bounds__(128) fd_center_kernel(const __grid_constant__ DevModel<T> m, int nknots, const double* __restrict__ qpos,
                                                         const double* __restrict__ qvel, const double* __restrict__ ctrl,
                                                         const double* __restrict__ warmstart, int niter, int nwarmup,
-                                                        double* __restrict__ qacc_center, int* __restrict__ status) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= nknots) return;
+                                                        double* __restrict__ qacc_center, int* __restrict__ status, const FdBins bins) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = k < nknots;
+    const int kk = valid ? k : nknots - 1;   // the tail's idle lanes evaluate a clamped knot, writes masked (warp-wide ranking below)
     double q[T::NQ], v[T::NV], u[nz(T::NU)], warm[T::NV], qacc[T::NV];
-    load_knot<T>(k, qpos, qvel, ctrl, q, v, u);
-    sfor<0, T::NV>([&](auto ii) { warm[IDX(ii)] = warmstart ? warmstart[(size_t)k * T::NV + IDX(ii)] : 0.0; });
+    load_knot<T>(kk, qpos, qvel, ctrl, q, v, u);
+    sfor<0, T::NV>([&](auto ii) { warm[IDX(ii)] = warmstart ? warmstart[(size_t)kk * T::NV + IDX(ii)] : 0.0; });
     Work<T> w;
     build_problem<T>(m, q, v, u, w);
 #pragma unroll 1
     for (int rep = 0; rep < nwarmup; rep++) solve<T>(m, w, warm, qacc, niter, 0.0);   // one copy of the solver (instruction footprint)
+    if (bins.key) {
+        const int ne = w.nefc < FD_NBUCKET - 1 ? w.nefc : FD_NBUCKET - 1;
+        const int b = valid ? FD_NBUCKET - 1 - ne : FD_NBUCKET;   // heaviest first; idle lanes form a group of their own
+        const unsigned peers = __match_any_sync(0xffffffffu, b);
+        const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+        int base = 0;
+        if (valid && lane == leader) base = atomicAdd(&bins.cnt[b], __popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (valid) bins.key[k] = ((unsigned)b << 24) | (unsigned)(base + __popc(peers & ((1u << lane) - 1)));
+    }
+    if (!valid) return;
     bool ok = true;
     sfor<0, T::NV>([&](auto ii) { qacc_center[(size_t)k * T::NV + IDX(ii)] = qacc[IDX(ii)]; ok = ok && isfinite(qacc[IDX(ii)]); });
     if (status) status[k] = ok ? 0 : ILQG_ERR_NONFINITE;
+}
+
+__global__ void __launch_bounds__(256) fd_bin_kernel(int nknots, const FdBins bins) {
+    __shared__ int off[FD_NBUCKET];
+    if (threadIdx.x < FD_NBUCKET) {
+        int s = 0;
+        for (int b = 0; b < (int)threadIdx.x; b++) s += bins.cnt[b];
+        off[threadIdx.x] = s;
+    }
+    __syncthreads();
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nknots) return;
+    const unsigned key = bins.key[k];
+    bins.perm[off[key >> 24] + (int)(key & 0xffffffu)] = k;
 }
 
 // ------------------------------------------------------------------ FD: perturbed evaluations
@@ -190,33 +229,39 @@ __global__ void __launch_bounds__(256, 1) fd_perturb_kernel(const __grid_constan
 // Per knot that is (GK + 2nv) position stages instead of 2(2nv+nu).  A CTA owns a whole number of knots
 // (floor(256 / lanes-per-knot)); their deriv segments are staged in shared memory and written as contiguous runs
 // (the dv|du blocks are adjacent in the reference layout: 54 doubles per hopper knot; dq: 36).
-template <class T>
+template <class T, int THREADS_ = 256>
 struct FdSplit {
     static constexpr int NV = T::NV, NU = T::NU, NCOL = 2 * NV + NU;
     static constexpr int gcd_(int a, int b) { return b == 0 ? a : gcd_(b, a % b); }
     static constexpr int GK = NU > 0 ? gcd_(NV, NU) : 1;
     static constexpr int CU = NU / GK, CV = NV / GK;      // ctrl / qvel columns per thread
-    static constexpr int THREADS = 256;
+    static constexpr int THREADS = THREADS_;
     static constexpr int KPC_VU = THREADS / GK;           // knots per CTA
     static constexpr int KPC_Q = THREADS / (2 * NV);
     static constexpr int NJAC = NV * NCOL, ND = NJAC + NCOL;
     static constexpr int SEG_VU = NV * NV + NV * NU, STG_VU = SEG_VU + NV + NU;   // dv | du | dg/dqvel | dg/dctrl
     static constexpr int SEG_Q = NV * NV, STG_Q = SEG_Q + NV;                     // dq | dg/dqpos
-    static_assert(2 * NV <= THREADS, "thread-per-rollout FD kernels need 2 nv <= 256");
+    static_assert(2 * NV <= THREADS, "thread-per-rollout FD kernels need 2 nv <= CTA size");
 };
 
-template <class T, bool SYNC>
-__global__ void __launch_bounds__(256, 1) fd_velctrl_kernel(const __grid_constant__ DevModel<T> m, int nknots, const double* __restrict__ qpos,
+// `perm` (slot -> knot, from fd_bin_kernel) or NULL for the identity: which knot a CTA slot works on.  A knot's segment is
+// contiguous in deriv either way; with the identity the CTA's segments also follow each other.
+template <class T, bool SYNC, int THREADS>
+__global__ void __launch_bounds__(THREADS, 256 / THREADS) fd_velctrl_kernel(const __grid_constant__ DevModel<T> m, int nknots, const double* __restrict__ qpos,
                                                             const double* __restrict__ qvel, const double* __restrict__ ctrl,
                                                             const double* __restrict__ qacc_center, const ilqg_cost* __restrict__ cost,
-                                                            double eps, int niter, const FdDst dst, int* __restrict__ status) {
-    using S = FdSplit<T>;
+                                                            double eps, int niter, const FdDst dst, int* __restrict__ status,
+                                                            const int* __restrict__ perm) {
+    using S = FdSplit<T, THREADS>;
     constexpr int NV = T::NV, NU = T::NU, NQ = T::NQ, GK = S::GK;
     __shared__ double stage[S::KPC_VU * S::STG_VU];
+    __shared__ int knot_of[S::KPC_VU];
     const int kl = threadIdx.x / GK, g = threadIdx.x - kl * GK;
-    const int k0 = blockIdx.x * S::KPC_VU, k = k0 + kl;
-    const bool valid = kl < S::KPC_VU && k < nknots;
-    const int kk = k < nknots ? k : nknots - 1;   // idle lanes evaluate a clamped knot with their writes masked (stage barriers)
+    const int k0 = blockIdx.x * S::KPC_VU, slot = k0 + kl;
+    const bool valid = kl < S::KPC_VU && slot < nknots;
+    const int sc = slot < nknots ? slot : nknots - 1;   // idle lanes evaluate a clamped knot with their writes masked (stage barriers)
+    const int kk = perm ? perm[sc] : sc;
+    if (valid && g == 0) knot_of[kl] = kk;
     double q[NQ], v[NV], u[nz(NU)], center[NV];
     load_knot<T>(kk, qpos, qvel, ctrl, q, v, u);
     sfor<0, NV>([&](auto ii) { center[IDX(ii)] = qacc_center[(size_t)kk * NV + IDX(ii)]; });
@@ -254,35 +299,39 @@ __global__ void __launch_bounds__(256, 1) fd_velctrl_kernel(const __grid_constan
             if (valid) st[S::SEG_VU + (is_vel ? col : NV + col)] = dcost;
         }
     }
-    if (valid && !finite && status) atomicExch(&status[k], ILQG_ERR_NONFINITE);
+    if (valid && !finite && status) atomicExch(&status[kk], ILQG_ERR_NONFINITE);
     __syncthreads();
     int nk = nknots - k0;
     if (nk > S::KPC_VU) nk = S::KPC_VU;
     for (int e = threadIdx.x; e < nk * S::SEG_VU; e += blockDim.x) {
         const int kn = e / S::SEG_VU, off = e - kn * S::SEG_VU;
         const double val = stage[kn * S::STG_VU + off];
-        for (int d = 0; d < dst.n; d++) dst.p[d][(size_t)(k0 + kn) * S::ND + NV * NV + off] = val;
+        for (int d = 0; d < dst.n; d++) dst.p[d][(size_t)knot_of[kn] * S::ND + NV * NV + off] = val;
     }
     if (cost)   // without a device cost the gradient entries stay untouched
         for (int e = threadIdx.x; e < nk * (NV + NU); e += blockDim.x) {
             const int kn = e / (NV + NU), off = e - kn * (NV + NU);
             const double val = stage[kn * S::STG_VU + S::SEG_VU + off];
-            for (int d = 0; d < dst.n; d++) dst.p[d][(size_t)(k0 + kn) * S::ND + S::NJAC + NV + off] = val;
+            for (int d = 0; d < dst.n; d++) dst.p[d][(size_t)knot_of[kn] * S::ND + S::NJAC + NV + off] = val;
         }
 }
 
-template <class T, bool SYNC>
-__global__ void __launch_bounds__(256, 1) fd_qpos_kernel(const __grid_constant__ DevModel<T> m, int nknots, const double* __restrict__ qpos,
+template <class T, bool SYNC, int THREADS>
+__global__ void __launch_bounds__(THREADS, 256 / THREADS) fd_qpos_kernel(const __grid_constant__ DevModel<T> m, int nknots, const double* __restrict__ qpos,
                                                          const double* __restrict__ qvel, const double* __restrict__ ctrl,
                                                          const double* __restrict__ qacc_center, const ilqg_cost* __restrict__ cost,
-                                                         double eps, int niter, const FdDst dst, int* __restrict__ status) {
-    using S = FdSplit<T>;
+                                                         double eps, int niter, const FdDst dst, int* __restrict__ status,
+                                                         const int* __restrict__ perm) {
+    using S = FdSplit<T, THREADS>;
     constexpr int NV = T::NV, NU = T::NU, NQ = T::NQ, G = 2 * NV;
     __shared__ double stage[S::KPC_Q * S::STG_Q];
+    __shared__ int knot_of[S::KPC_Q];
     const int kl = threadIdx.x / G, l = threadIdx.x - kl * G;
-    const int k0 = blockIdx.x * S::KPC_Q, k = k0 + kl;
-    const bool valid = kl < S::KPC_Q && k < nknots;
-    const int kk = k < nknots ? k : nknots - 1;
+    const int k0 = blockIdx.x * S::KPC_Q, slot = k0 + kl;
+    const bool valid = kl < S::KPC_Q && slot < nknots;
+    const int sc = slot < nknots ? slot : nknots - 1;
+    const int kk = perm ? perm[sc] : sc;
+    if (valid && l == 0) knot_of[kl] = kk;
     const int col = l >> 1;
     const double se = (l & 1) ? -eps : eps;
     double qacc[NV], dcost = 0;
@@ -320,7 +369,7 @@ __global__ void __launch_bounds__(256, 1) fd_qpos_kernel(const __grid_constant__
     });
     if (valid && !(l & 1)) {
         st[S::SEG_Q + col] = dcost;
-        if (!finite && status) atomicExch(&status[k], ILQG_ERR_NONFINITE);
+        if (!finite && status) atomicExch(&status[kk], ILQG_ERR_NONFINITE);
     }
     __syncthreads();
     int nk = nknots - k0;
@@ -328,13 +377,13 @@ __global__ void __launch_bounds__(256, 1) fd_qpos_kernel(const __grid_constant__
     for (int e = threadIdx.x; e < nk * S::SEG_Q; e += blockDim.x) {
         const int kn = e / S::SEG_Q, off = e - kn * S::SEG_Q;
         const double val = stage[kn * S::STG_Q + off];
-        for (int d = 0; d < dst.n; d++) dst.p[d][(size_t)(k0 + kn) * S::ND + off] = val;
+        for (int d = 0; d < dst.n; d++) dst.p[d][(size_t)knot_of[kn] * S::ND + off] = val;
     }
     if (cost)
         for (int e = threadIdx.x; e < nk * NV; e += blockDim.x) {
             const int kn = e / NV, off = e - kn * NV;
             const double val = stage[kn * S::STG_Q + S::SEG_Q + off];
-            for (int d = 0; d < dst.n; d++) dst.p[d][(size_t)(k0 + kn) * S::ND + S::NJAC + off] = val;
+            for (int d = 0; d < dst.n; d++) dst.p[d][(size_t)knot_of[kn] * S::ND + S::NJAC + off] = val;
         }
 }
 
@@ -413,12 +462,15 @@ struct IlqrLaunch<T, true> {
 // ------------------------------------------------------------------ engines (one per compiled-in topology)
 struct Engine {
     int fd_variant = -1;   // -1: chosen per call by batch size (ILQG_FD_VARIANT overrides)
+    int fd_bins = 1;       // work-class ordering of the knots in the stage-skipping kernels (ILQG_FD_BINS=0 disables)
+    // ints of scratch fd() wants for `nknots` knots (bucket counters, keys, permutation); 0 = none
+    virtual size_t fd_scratch_ints(int nknots) const { (void)nknots; return 0; }
     virtual ~Engine() {}
     virtual int fd_launches() const { return 2; }
     virtual const char* name() const = 0;
     virtual cudaError_t fd(int nknots, const double* qpos, const double* qvel, const double* ctrl, const double* warm,
                            const ilqg_cost* cost_dev, const ilqg_fd_opts& o, const FdDst& dst, double* qacc_center, int* status,
-                           cudaStream_t s, cudaEvent_t* ev) = 0;
+                           int* scratch, cudaStream_t s, cudaEvent_t* ev) = 0;
     virtual cudaError_t forward(int n, const double* qpos, const double* qvel, const double* ctrl, double* warm, double* qacc,
                                 cudaStream_t s) = 0;
     virtual cudaError_t step(int n, int nsteps, double* qpos, double* qvel, const double* ctrl, double* warm, double* qacc,
@@ -436,26 +488,46 @@ struct EngineT : Engine {
     const char* name() const override { return T::NAME; }
     int fd_launches() const override { return last_launches; }
     int last_launches = 3;
+    static constexpr int SPLIT_MIN = 16384;   // knots from which the stage-skipping split is chosen
+    int variant_for(int nknots) const { return fd_variant >= 0 ? fd_variant : (nknots >= SPLIT_MIN ? 3 : 2); }
+    size_t fd_scratch_ints(int nknots) const override {
+        return (variant_for(nknots) >= 3 && fd_bins && nknots < (1 << 24)) ? (size_t)FD_NBUCKET + 2 * (size_t)nknots : 0;
+    }
+    template <int THREADS>
+    void launch_split(int nknots, const double* qpos, const double* qvel, const double* ctrl, const ilqg_cost* cost_dev, const ilqg_fd_opts& o,
+                      const FdDst& dst, const double* qacc_center, int* status, const int* perm, cudaStream_t s, cudaEvent_t* ev) {
+        using P = FdSplit<T, THREADS>;
+        // (the default L1 / shared-memory split is the best one: forcing a larger shared carve-out shrinks the L1 that holds the
+        //  rollouts' local-memory rows and costs up to 30 % — measured with cudaFuncAttributePreferredSharedMemoryCarveout)
+        fd_velctrl_kernel<T, true, THREADS><<<(nknots + P::KPC_VU - 1) / P::KPC_VU, THREADS, 0, s>>>(dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev,
+                                                                                                   o.eps, o.niter, dst, status, perm);
+        if (ev) cudaEventRecord(ev[3], s);
+        fd_qpos_kernel<T, true, THREADS><<<(nknots + P::KPC_Q - 1) / P::KPC_Q, THREADS, 0, s>>>(dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps,
+                                                                                              o.niter, dst, status, perm);
+    }
     cudaError_t fd(int nknots, const double* qpos, const double* qvel, const double* ctrl, const double* warm, const ilqg_cost* cost_dev,
-                   const ilqg_fd_opts& o, const FdDst& dst, double* qacc_center, int* status, cudaStream_t s, cudaEvent_t* ev) override {
+                   const ilqg_fd_opts& o, const FdDst& dst, double* qacc_center, int* status, int* scratch, cudaStream_t s,
+                   cudaEvent_t* ev) override {
         using S = FdShape<T>;
         // variant 3 = stage-skipping split (fewest instructions: best once its qvel/ctrl kernel fills the GPU), 2 = one thread per
         // perturbed evaluation in a single launch (30x more threads per knot: lower latency for small batches); fd_variant -1 = by size
-        const int variant = fd_variant >= 0 ? fd_variant : (nknots >= 16384 ? 3 : 2);
-        last_launches = variant >= 3 ? 3 : 2;
+        const int variant = variant_for(nknots);
         if (nknots <= 0) return cudaSuccess;
+        FdBins bins{nullptr, nullptr, nullptr};
+        if (scratch && fd_scratch_ints(nknots)) {
+            bins.cnt = scratch;
+            bins.key = (unsigned int*)(scratch + FD_NBUCKET);
+            bins.perm = scratch + FD_NBUCKET + nknots;
+            cudaMemsetAsync(bins.cnt, 0, FD_NBUCKET * sizeof(int), s);
+        }
+        last_launches = variant >= 3 ? (bins.key ? 4 : 3) : 2;
         if (ev) cudaEventRecord(ev[0], s);
-        fd_center_kernel<T><<<(nknots + 127) / 128, 128, 0, s>>>(dm, nknots, qpos, qvel, ctrl, warm, o.niter, o.nwarmup, qacc_center, status);
+        fd_center_kernel<T><<<(nknots + 127) / 128, 128, 0, s>>>(dm, nknots, qpos, qvel, ctrl, warm, o.niter, o.nwarmup, qacc_center, status, bins);
+        if (bins.key) fd_bin_kernel<<<(nknots + 255) / 256, 256, 0, s>>>(nknots, bins);
         if (ev) cudaEventRecord(ev[1], s);
         if (variant >= 3) {  // stage-skipping split: qvel/ctrl columns, then qpos columns
-            using P = FdSplit<T>;
-            // (the default L1 / shared-memory split is the best one: forcing a larger shared carve-out shrinks the L1 that holds the
-            //  rollouts' local-memory rows and costs up to 30 % — measured with cudaFuncAttributePreferredSharedMemoryCarveout)
-            fd_velctrl_kernel<T, true><<<(nknots + P::KPC_VU - 1) / P::KPC_VU, P::THREADS, 0, s>>>(dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev,
-                                                                                                 o.eps, o.niter, dst, status);
-            if (ev) cudaEventRecord(ev[3], s);
-            fd_qpos_kernel<T, true><<<(nknots + P::KPC_Q - 1) / P::KPC_Q, P::THREADS, 0, s>>>(dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps,
-                                                                                            o.niter, dst, status);
+            // (256-thread CTAs, one per SM; two 128-thread CTAs per SM were measured 7 % slower: fewer warps share the instruction stream)
+            launch_split<256>(nknots, qpos, qvel, ctrl, cost_dev, o, dst, qacc_center, status, bins.perm, s, ev);
             if (ev) cudaEventRecord(ev[2], s);
             return cudaGetLastError();
         }
@@ -543,7 +615,8 @@ struct CoopEngine : Engine {
         return e;
     }
     cudaError_t fd(int nknots, const double* qpos, const double* qvel, const double* ctrl, const double* warm, const ilqg_cost* cost_dev,
-                   const ilqg_fd_opts& o, const FdDst& dst, double* qacc_center, int* status, cudaStream_t s, cudaEvent_t* ev) override {
+                   const ilqg_fd_opts& o, const FdDst& dst, double* qacc_center, int* status, int* /*scratch*/, cudaStream_t s,
+                   cudaEvent_t* ev) override {
         if (nknots <= 0) return cudaSuccess;
         if (dst.n > 1) return cudaErrorNotSupported;   // peer scatter is wired into the thread-per-rollout kernels only
         double* deriv = dst.p[0];
@@ -656,6 +729,7 @@ struct ilqg_handle_s {
     std::string err;
     // scratch owned by the handle (grown on demand)
     double* d_center = nullptr; size_t center_cap = 0;
+    int* d_bins = nullptr; size_t bins_cap = 0;   // work-class scratch of the FD kernels (ints)
     ilqg_cost* d_cost = nullptr;
     int* d_timeout = nullptr;  // set by a peer barrier that gave up waiting
     // staging for the *_host entry points
@@ -714,6 +788,7 @@ int ilqg_create(const ilqg_model* m, int device, ilqg_handle* out) {
     h->model = *m;
     h->eng = eng;
     if (const char* e = getenv("ILQG_FD_VARIANT")) eng->fd_variant = atoi(e);
+    if (const char* e = getenv("ILQG_FD_BINS")) eng->fd_bins = atoi(e);
     if (const char* e = getenv("ILQG_HOST_CHUNKS")) h->host_chunks = atoi(e);
     if (cudaMalloc(&h->d_cost, sizeof(ilqg_cost)) != cudaSuccess) {
         delete eng;
@@ -728,6 +803,7 @@ int ilqg_destroy(ilqg_handle h) {
     if (!h) return ILQG_OK;
     cudaSetDevice(h->device);
     cudaFree(h->d_center);
+    cudaFree(h->d_bins);
     cudaFree(h->d_cost);
     cudaFree(h->d_timeout);
     cudaFree(h->d_stage);
@@ -805,6 +881,15 @@ static int ensure_center(ilqg_handle h, size_t n) {
     h->center_cap = n;
     return ILQG_OK;
 }
+static int ensure_bins(ilqg_handle h, size_t n) {
+    if (n <= h->bins_cap) return ILQG_OK;
+    cudaFree(h->d_bins);
+    h->d_bins = nullptr;
+    h->bins_cap = 0;
+    CU(h, cudaMalloc(&h->d_bins, n * sizeof(int)));
+    h->bins_cap = n;
+    return ILQG_OK;
+}
 static int ensure_stage(ilqg_handle h, size_t bytes) {
     if (bytes <= h->stage_cap) return ILQG_OK;
     cudaFree(h->d_stage);
@@ -816,8 +901,11 @@ static int ensure_stage(ilqg_handle h, size_t bytes) {
 }
 
 // launch the two FD kernels; `dcost` is a DEVICE pointer (or NULL)
+// `scratch`: the engine's work-class scratch for this call (fd_scratch_ints(nknots) ints), or NULL to use the handle's own
+// (calls that overlap on different streams must bring their own)
 static int fd_launch(ilqg_handle h, int nknots, const double* qpos, const double* qvel, const double* ctrl, const double* warmstart,
-                     const ilqg_cost* dcost, const ilqg_fd_opts* opts, const ilqg::FdDst& dst, double* qacc_out, int* status, cudaStream_t s) {
+                     const ilqg_cost* dcost, const ilqg_fd_opts* opts, const ilqg::FdDst& dst, double* qacc_out, int* status, cudaStream_t s,
+                     int* scratch = nullptr) {
     ilqg_fd_opts o;
     ilqg_fd_opts_default(&o);
     if (opts) o = *opts;
@@ -828,7 +916,15 @@ static int fd_launch(ilqg_handle h, int nknots, const double* qpos, const double
         if (rc) return rc;
         center = h->d_center;
     }
-    CU(h, h->eng->fd(nknots, qpos, qvel, ctrl, warmstart, dcost, o, dst, center, status, s, h->profiling ? h->ev : nullptr));
+    if (!scratch) {
+        const size_t want = h->eng->fd_scratch_ints(nknots);
+        if (want) {
+            int rc = ensure_bins(h, want);
+            if (rc) return rc;
+            scratch = h->d_bins;
+        }
+    }
+    CU(h, h->eng->fd(nknots, qpos, qvel, ctrl, warmstart, dcost, o, dst, center, status, scratch, s, h->profiling ? h->ev : nullptr));
     h->launches += h->eng->fd_launches();
     return ILQG_OK;
 }
@@ -949,11 +1045,19 @@ int ilqg_fd_batch_host(ilqg_handle h, int nknots, const double* qpos, const doub
     // one staging block: qpos | qvel | ctrl | warm | qacc | deriv | status
     size_t off_q = 0, off_v = off_q + n * nq, off_u = off_v + n * nv, off_w = off_u + n * nu, off_a = off_w + n * nv,
            off_d = off_a + n * nv, ndbl = off_d + n * nd;
-    size_t bytes = ndbl * sizeof(double) + n * sizeof(int);
+    // chunks large enough for the stage-skipping kernels (>= 16384 knots), four of them at the benchmark size: measured best
+    // on B200 (86,016 hopper knots: 1 chunk 3.11 ms, 2: 2.33, 4: 2.04, 8: 2.25, 16: 2.85; raw D2H of deriv alone: 1.35 ms).
+    // Also measured and not better: centre evaluations for all knots in one launch first, then the columns chunk by chunk (2.08 ms).
+    size_t nchunks = n / 20000 < 4 ? (n >= 8192 ? 4 : 1) : n / 20000;
+    if (h->host_chunks > 0) nchunks = (size_t)h->host_chunks;   // ILQG_HOST_CHUNKS (experiments)
+    const size_t chunk = (n + nchunks - 1) / nchunks;
+    const size_t scr = h->eng->fd_scratch_ints((int)chunk);   // per chunk: the chunks overlap on the three streams
+    size_t bytes = ndbl * sizeof(double) + (n + nchunks * scr) * sizeof(int);
     int rc = ensure_stage(h, bytes);
     if (rc) return rc;
     double* b = (double*)h->d_stage;
     int* dstat = (int*)(b + ndbl);
+    int* dscr = dstat + n;
     std::unique_ptr<int[]> hs(new int[n]);
     // Pipeline over chunks of knots on three streams: while chunk c computes, chunk c+1 uploads and chunk c-1 downloads
     // (the deriv download is 5x the upload and, at PCIe rates, as long as the kernels).
@@ -964,12 +1068,6 @@ int ilqg_fd_batch_host(ilqg_handle h, int nknots, const double* qpos, const doub
         CU(h, cudaMemcpy(h->d_cost, cost, sizeof(ilqg_cost), cudaMemcpyHostToDevice));
         dcost = h->d_cost;
     }
-    // chunks large enough for the stage-skipping kernels (>= 16384 knots), four of them at the benchmark size: measured best
-    // on B200 (86,016 hopper knots: 1 chunk 3.11 ms, 2: 2.33, 4: 2.04, 8: 2.25, 16: 2.85; raw D2H of deriv alone: 1.35 ms).
-    // Also measured and not better: centre evaluations for all knots in one launch first, then the columns chunk by chunk (2.08 ms).
-    size_t nchunks = n / 20000 < 4 ? (n >= 8192 ? 4 : 1) : n / 20000;
-    if (h->host_chunks > 0) nchunks = (size_t)h->host_chunks;   // ILQG_HOST_CHUNKS (experiments)
-    const size_t chunk = (n + nchunks - 1) / nchunks;
     int ci = 0;
     for (size_t lo = 0; lo < n; lo += chunk, ci++) {
         const size_t cn = lo + chunk <= n ? chunk : n - lo;
@@ -985,7 +1083,7 @@ int ilqg_fd_batch_host(ilqg_handle h, int nknots, const double* qpos, const doub
         dst.p[0] = b + off_d + lo * nd;
         dst.n = 1;
         rc = fd_launch(h, (int)cn, b + off_q + lo * nq, b + off_v + lo * nv, b + off_u + lo * nu, b + off_w + lo * nv, dcost, opts, dst,
-                       b + off_a + lo * nv, dstat + lo, s);
+                       b + off_a + lo * nv, dstat + lo, s, scr ? dscr + (size_t)ci * scr : nullptr);
         if (rc) return rc;
         CU(h, cudaMemcpyAsync(deriv + lo * nd, b + off_d + lo * nd, cn * nd * sizeof(double), cudaMemcpyDeviceToHost, s));
         if (qacc_out) CU(h, cudaMemcpyAsync(qacc_out + lo * nv, b + off_a + lo * nv, cn * nv * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -1241,7 +1339,14 @@ int ilqg_ilqr_linearise(ilqg_ilqr w, void* stream) {                     // FD a
     ilqg::FdDst dst{};
     dst.p[0] = b.deriv;
     dst.n = 1;
-    CU(h, h->eng->fd(nknots, b.nom_q, b.nom_v, b.nom_u, b.nom_w, w->host_cost ? nullptr : w->d_cost, w->fd, dst, h->d_center, nullptr, s, nullptr));
+    int* scratch = nullptr;
+    if (const size_t want = h->eng->fd_scratch_ints(nknots)) {
+        rc = ensure_bins(h, want);
+        if (rc) return rc;
+        scratch = h->d_bins;
+    }
+    CU(h, h->eng->fd(nknots, b.nom_q, b.nom_v, b.nom_u, b.nom_w, w->host_cost ? nullptr : w->d_cost, w->fd, dst, h->d_center, nullptr, scratch, s,
+                     nullptr));
     h->launches += h->eng->fd_launches();
     return ILQG_OK;
 }

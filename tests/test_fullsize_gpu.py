@@ -85,3 +85,22 @@ def test_strided_sample_matches_oracle(full, oracle, omodels):
     q, v, u, w = (f[k][it].cpu().numpy() for k in ("q", "v", "u", "w"))
     d_ref, _, _ = oracle.fd_batch(omodels["hopper"], q, v, u, w, f["cost"])
     assert_deriv_close(f["deriv"][it].cpu().numpy(), d_ref, 6, 3)
+
+
+def test_work_class_ordering_changes_placement_only(full, pkg):
+    """The split kernels take their knots through a permutation that groups them by the centre's constraint-row count
+    (heaviest first).  Switching the ordering off (identity placement) must give the same bits for every knot."""
+    import torch
+    f = full
+    os.environ["ILQG_FD_VARIANT"] = "3"
+    os.environ["ILQG_FD_BINS"] = "0"
+    try:
+        h0 = pkg.Handle(pkg.Model.named("hopper"), 0)
+    finally:
+        del os.environ["ILQG_FD_VARIANT"], os.environ["ILQG_FD_BINS"]
+    plain = torch.zeros_like(f["deriv"])
+    st = torch.full((f["n"],), -1, dtype=torch.int32, device="cuda:0")
+    h0.fd_batch_dev(f["q"], f["v"], f["u"], f["w"], plain, None, st, cost=f["cost"])
+    torch.cuda.synchronize()
+    assert torch.equal(plain, f["deriv"]) and torch.equal(st, f["status"])
+    h0.close()

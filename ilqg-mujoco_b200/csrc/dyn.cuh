@@ -19,6 +19,7 @@
 
 #include "../../include/ilqg_b200.h"
 #include "topo_gen.h"
+#include "planar.h"
 
 namespace ilqg {
 
@@ -107,6 +108,7 @@ bool dev_model_from_tables(const ilqg_model& s, DevModel<T>& d) {
     bool damped = false;
     for (int i = 0; i < T::NV; i++) damped |= s.dof_damping[i] > 0;
     if (damped && !T::ANY_DAMPING) return false;
+    if (T::PLANAR_Y && !model_is_planar_y(s)) return false;   // the kernels' static zero pattern (Alg<true>) must hold exactly
 
     d.timestep = s.timestep;
     for (int k = 0; k < 3; k++) d.gravity[k] = s.gravity[k];
@@ -211,6 +213,126 @@ DEV S6 mul(const Inert& I, S6 s) {
     return {Iw + cross(I.h, s.v), I.m * s.v + cross(s.w, I.h)};
 }
 
+// ------------------------------------------------------------------ statically sparse vectors (planar trees)
+// A tree whose joints are slides in the xz-plane and hinges about y, with every frame, offset and geom axis in that plane
+// (inverted pendulum, hopper — and most locomotion benchmarks), moves in a 3-dimensional subspace of the spatial algebra:
+// angular parts are (0, wy, 0), linear parts and positions (x, 0, z), quaternions (w, 0, y, 0), inertias couple x and z only.
+// MuJoCo computes the full 6-D algebra and multiplies by those zeros at run time.  Here the zero pattern is part of the
+// TYPE: a component of type Z0 is exactly zero, products with it are Z0, sums drop it — the same formulas (one copy of the
+// pipeline below, written once over the type family Alg<PLANAR>) instantiate to roughly a third of the arithmetic and half
+// of the live registers.  Dropping a term that is exactly 0.0 leaves every other term's value unchanged; only the
+// association of the remaining FMAs may differ from the dense instantiation (last-bit differences, far inside the FD
+// tolerance).  The topology flag T::PLANAR_Y is verified against the runtime tables when a model is bound.
+struct Z0 {
+    constexpr Z0() = default;
+    DEV constexpr Z0(int) {}   // from the literal 0 of a brace initialiser (a run-time double cannot narrow into it)
+};
+DEV constexpr Z0 operator+(Z0, Z0) { return {}; }
+DEV constexpr Z0 operator-(Z0, Z0) { return {}; }
+DEV constexpr Z0 operator*(Z0, Z0) { return {}; }
+DEV constexpr Z0 operator-(Z0) { return {}; }
+DEV constexpr double operator+(Z0, double b) { return b; }
+DEV constexpr double operator+(double a, Z0) { return a; }
+DEV constexpr double operator-(double a, Z0) { return a; }
+DEV constexpr double operator-(Z0, double b) { return -b; }
+DEV constexpr Z0 operator*(Z0, double) { return {}; }
+DEV constexpr Z0 operator*(double, Z0) { return {}; }
+DEV constexpr Z0 operator*(int, Z0) { return {}; }
+DEV constexpr double val(double x) { return x; }
+DEV constexpr double val(Z0) { return 0.0; }
+
+template <class X, class Y, class W> struct V3T { X x; Y y; W z; };
+template <class X, class Y, class W> DEV V3T<X, Y, W> mk3(X x, Y y, W z) { return {x, y, z}; }
+#define V3T_A template <class A0, class A1, class A2>
+#define V3T_AB template <class A0, class A1, class A2, class B0, class B1, class B2>
+V3T_AB DEV auto operator+(V3T<A0, A1, A2> a, V3T<B0, B1, B2> b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+V3T_AB DEV auto operator-(V3T<A0, A1, A2> a, V3T<B0, B1, B2> b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+V3T_A DEV auto operator*(double s, V3T<A0, A1, A2> a) { return mk3(s * a.x, s * a.y, s * a.z); }
+V3T_AB DEV auto dot(V3T<A0, A1, A2> a, V3T<B0, B1, B2> b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+V3T_A DEV auto dot(V3 a, V3T<A0, A1, A2> b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+V3T_AB DEV auto cross(V3T<A0, A1, A2> a, V3T<B0, B1, B2> b) {
+    return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+V3T_A DEV V3 full(V3T<A0, A1, A2> a) { return {val(a.x), val(a.y), val(a.z)}; }
+DEV V3 full(V3 a) { return a; }
+
+template <class W, class X, class Y, class Zc> struct Q4T { W w; X x; Y y; Zc z; };
+template <class W, class X, class Y, class Zc> DEV Q4T<W, X, Y, Zc> mk4(W w, X x, Y y, Zc z) { return {w, x, y, z}; }
+template <class A0, class A1, class A2, class A3, class B0, class B1, class B2, class B3>
+DEV auto qmul(Q4T<A0, A1, A2, A3> a, Q4T<B0, B1, B2, B3> b) {
+    return mk4(a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z, a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y,
+               a.w * b.y - a.x * b.z + a.y * b.w + a.z * b.x, a.w * b.z + a.x * b.y - a.y * b.x + a.z * b.w);
+}
+template <class A0, class A1, class A2, class A3>
+DEV Q4T<A0, A1, A2, A3> qnormalized(Q4T<A0, A1, A2, A3> q) {
+    double n = sqrt(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
+    if (n < ILQG_MINVAL) return {1, 0, 0, 0};
+    double r = 1.0 / n;
+    return {q.w * r, q.x * r, q.y * r, q.z * r};
+}
+template <class R0, class R1, class R2> struct M3T { R0 r0; R1 r1; R2 r2; };  // rows
+template <class R0, class R1, class R2> DEV M3T<R0, R1, R2> mkm(R0 a, R1 b, R2 c) { return {a, b, c}; }
+template <class A0, class A1, class A2, class A3>
+DEV auto q2m(Q4T<A0, A1, A2, A3> q) {
+    auto w = q.w; auto x = q.x; auto y = q.y; auto z = q.z;
+    return mkm(mk3(w * w + x * x - y * y - z * z, 2 * (x * y - w * z), 2 * (x * z + w * y)),
+               mk3(2 * (x * y + w * z), w * w - x * x + y * y - z * z, 2 * (y * z - w * x)),
+               mk3(2 * (x * z - w * y), 2 * (y * z + w * x), w * w - x * x - y * y + z * z));
+}
+template <class R0, class R1, class R2, class A0, class A1, class A2>
+DEV auto mulv(const M3T<R0, R1, R2>& R, V3T<A0, A1, A2> v) { return mk3(dot(R.r0, v), dot(R.r1, v), dot(R.r2, v)); }
+
+template <class W, class V> struct S6T { W w; V v; };
+template <class W, class V> DEV S6T<W, V> mk6(W w, V v) { return {w, v}; }
+#define S6T_AB template <class AW, class AV, class BW, class BV>
+S6T_AB DEV auto operator+(S6T<AW, AV> a, S6T<BW, BV> b) { return mk6(a.w + b.w, a.v + b.v); }
+template <class AW, class AV> DEV auto operator*(double s, S6T<AW, AV> a) { return mk6(s * a.w, s * a.v); }
+S6T_AB DEV auto dot(S6T<AW, AV> a, S6T<BW, BV> b) { return dot(a.w, b.w) + dot(a.v, b.v); }
+S6T_AB DEV auto cross_motion(S6T<AW, AV> vel, S6T<BW, BV> x) { return mk6(cross(vel.w, x.w), cross(vel.w, x.v) + cross(vel.v, x.w)); }
+S6T_AB DEV auto cross_force(S6T<AW, AV> vel, S6T<BW, BV> f) { return mk6(cross(vel.w, f.w) + cross(vel.v, f.v), cross(vel.w, f.v)); }
+template <class XX, class YY, class ZZ, class XY, class XZ, class YZ, class H>
+struct InertT { XX xx; YY yy; ZZ zz; XY xy; XZ xz; YZ yz; H h; double m; };
+#define INERTT_A template <class XX, class YY, class ZZ, class XY, class XZ, class YZ, class H>
+INERTT_A DEV InertT<XX, YY, ZZ, XY, XZ, YZ, H> operator+(const InertT<XX, YY, ZZ, XY, XZ, YZ, H>& a, const InertT<XX, YY, ZZ, XY, XZ, YZ, H>& b) {
+    return {a.xx + b.xx, a.yy + b.yy, a.zz + b.zz, a.xy + b.xy, a.xz + b.xz, a.yz + b.yz, a.h + b.h, a.m + b.m};
+}
+template <class XX, class YY, class ZZ, class XY, class XZ, class YZ, class H, class AW, class AV>
+DEV auto mul(const InertT<XX, YY, ZZ, XY, XZ, YZ, H>& I, S6T<AW, AV> s) {
+    auto Iw = mk3(I.xx * s.w.x + I.xy * s.w.y + I.xz * s.w.z, I.xy * s.w.x + I.yy * s.w.y + I.yz * s.w.z,
+                  I.xz * s.w.x + I.yz * s.w.y + I.zz * s.w.z);
+    return mk6(Iw + cross(I.h, s.v), I.m * s.v + cross(s.w, I.h));
+}
+// body-frame inertia tensor as loaded from the model tables
+template <class XY, class YZ> struct IbT { double xx, yy, zz; XY xy; double xz; YZ yz; };
+
+// The type family the pipeline is written over.  Alg<false>: the dense 3-D types above.  Alg<true>: the planar patterns.
+template <bool PLANAR> struct Alg;
+template <> struct Alg<false> {
+    using P3 = V3; using A3 = V3; using QT = Q4; using MT = M3; using ST = S6; using CD = S6; using IT = Inert;
+    using IB = IbT<double, double>;
+    static DEV P3 ldP(const double* p) { return {p[0], p[1], p[2]}; }
+    static DEV A3 ldA(const double* p) { return {p[0], p[1], p[2]}; }
+    static DEV QT ldQ(const double* p) { return {p[0], p[1], p[2], p[3]}; }
+    static DEV QT hinge_quat(double c, double s, const double* ax) { return {c, ax[0] * s, ax[1] * s, ax[2] * s}; }
+    static DEV IB ldI(const double* in) { return {in[0], in[1], in[2], in[3], in[4], in[5]}; }
+};
+template <> struct Alg<true> {
+    using P3 = V3T<double, Z0, double>;   // positions, linear parts, in-plane axes
+    using A3 = V3T<Z0, double, Z0>;       // angular parts, hinge axes
+    using QT = Q4T<double, Z0, double, Z0>;
+    using MT = M3T<P3, A3, P3>;
+    using ST = S6T<A3, P3>;               // motion and force vectors have the same pattern
+    using CD = S6T<V3T<Z0, Z0, Z0>, P3>;  // cdof_dot: the angular part of (planar) x (planar) vanishes
+    using IT = InertT<double, double, double, Z0, double, Z0, P3>;
+    using IB = IbT<Z0, Z0>;
+    static DEV P3 ldP(const double* p) { return {p[0], 0, p[2]}; }
+    static DEV A3 ldA(const double* p) { return {0, p[1], 0}; }
+    static DEV QT ldQ(const double* p) { return {p[0], 0, p[2], 0}; }
+    static DEV QT hinge_quat(double c, double s, const double* ax) { return {c, 0, ax[1] * s, 0}; }
+    static DEV IB ldI(const double* in) { return {in[0], in[1], in[2], 0, in[4], 0}; }
+};
+template <class T> using AlgOf = Alg<(T::PLANAR_Y != 0)>;
+
 // ------------------------------------------------------------------ per-rollout solver inputs
 template <class T>
 struct Work {
@@ -231,8 +353,8 @@ struct Work {
 // what the position stage leaves for the velocity stage (mjSTAGE_POS products that mj_fwdVelocity reads)
 template <class T>
 struct PosStage {
-    S6 cdof[T::NV];
-    Inert cin[T::NBODY];
+    typename AlgOf<T>::ST cdof[T::NV];
+    typename AlgOf<T>::IT cin[T::NBODY];
     double dspr[T::NV];  // q - qpos_spring of sprung dofs
 };
 
@@ -327,6 +449,19 @@ DEV void make_frame(V3 n, V3 hint, bool has_hint, V3& t1, V3& t2) {
     t2 = cross(n, t1);
 }
 
+// Free joints exist in dense (non-planar) trees only.  The explicit template argument makes the call sites dependent on the
+// enclosing generic lambda's parameter, so the planar instantiation of the pipeline never looks inside.
+template <int J, class P3, class Q4, class M3>
+DEV void kin_free_joint(const double* q7, P3& pos, Q4& quat, M3& R) {
+    pos = {q7[0], q7[1], q7[2]};
+    quat = qnormalized(Q4{q7[3], q7[4], q7[5], q7[6]});
+    R = q2m(quat);
+}
+template <int J, class M3, class P3, class S6>
+DEV void cdof_free_rot(const M3& xmat, P3 off, S6* cdof3) {
+    sfor<0, 3>([&](auto kk) { P3 a = col(xmat, IDX(kk)); cdof3[IDX(kk)] = {a, cross(a, off)}; });
+}
+
 // ------------------------------------------------------------------ the pipeline up to the constraint problem
 // Split along MuJoCo's stage boundaries (mjSTAGE_POS / mjSTAGE_VEL, the skip levels the reference passes to
 // mj_forwardSkip, /root/reference/src/mjderivative.cpp:92,124,178):
@@ -345,10 +480,14 @@ template <class T, bool SYNC = false, bool FUSED = false>
 DEV void build_pos(const DevModel<T>& m, const double (&q)[T::NQ], PosStage<T>& ps, Work<T>& w, const double* qv = nullptr) {
     auto stage_sync = [&]() { if constexpr (SYNC) __syncthreads(); };
     constexpr int NB = T::NBODY, NV = T::NV, NJ = T::NJNT;
-    V3 xpos[NB];
+    using A = AlgOf<T>;   // dense 3-D types, or the planar patterns (see Alg)
+    using P3 = typename A::P3; using A3 = typename A::A3; using Q4 = typename A::QT; using M3 = typename A::MT;
+    using S6 = typename A::ST; using Inert = typename A::IT;
+    P3 xpos[NB];
     M3 xmat[NB];
     Q4 xquat[NB];
-    V3 anchor[NJ], axis[NJ];
+    P3 anchor[NJ], axisP[NJ];   // slide axes (in-plane for planar trees)
+    A3 axisA[NJ];               // hinge axes
     xpos[0] = {0, 0, 0};
     xquat[0] = {1, 0, 0, 0};
     xmat[0] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
@@ -359,42 +498,40 @@ DEV void build_pos(const DevModel<T>& m, const double (&q)[T::NQ], PosStage<T>& 
     sfor<1, NB>([&](auto bb) {
         constexpr int b = IDX(bb), p = T::body_parent(b);
         constexpr bool qid = T::body_quat_identity(b) != 0;
-        V3 pos;
+        P3 pos;
         Q4 quat;
         M3 R;   // rotation of `quat`, valid while only slide joints have been applied (see slide_only below)
         if constexpr (p == 0) {
-            pos = ld3(m.body_pos[b]);
+            pos = A::ldP(m.body_pos[b]);
             if constexpr (qid) { quat = {1, 0, 0, 0}; R = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}; }
-            else { quat = {m.body_quat[b][0], m.body_quat[b][1], m.body_quat[b][2], m.body_quat[b][3]}; R = q2m(quat); }
+            else { quat = A::ldQ(m.body_quat[b]); R = q2m(quat); }
         } else {
-            pos = xpos[p] + mulv(xmat[p], ld3(m.body_pos[b]));
+            pos = xpos[p] + mulv(xmat[p], A::ldP(m.body_pos[b]));
             if constexpr (qid) { quat = xquat[p]; R = xmat[p]; }
-            else { quat = qmul(xquat[p], {m.body_quat[b][0], m.body_quat[b][1], m.body_quat[b][2], m.body_quat[b][3]}); R = q2m(quat); }
+            else { quat = qmul(xquat[p], A::ldQ(m.body_quat[b])); R = q2m(quat); }
         }
         sfor<0, T::body_jntnum(b)>([&](auto jj) {
             constexpr int j = T::body_jntadr(b) + IDX(jj), qa = T::jnt_qposadr(j), ty = T::jnt_type(j);
             if constexpr (ty == ILQG_JNT_FREE) {
-                pos = {q[qa], q[qa + 1], q[qa + 2]};
-                quat = qnormalized({q[qa + 3], q[qa + 4], q[qa + 5], q[qa + 6]});
-                R = q2m(quat);
+                kin_free_joint<j>(&q[qa], pos, quat, R);
                 anchor[j] = pos;
-                axis[j] = {0, 0, 1};
             } else {
                 constexpr bool jz = T::jnt_pos_zero(j) != 0;
                 if constexpr (jz) anchor[j] = pos;
-                else anchor[j] = pos + mulv(R, ld3(m.jnt_pos[j]));
-                axis[j] = mulv(R, ld3(m.jnt_axis[j]));
+                else anchor[j] = pos + mulv(R, A::ldP(m.jnt_pos[j]));
                 double qq = q[qa] - m.qpos0[qa];
                 if constexpr (ty == ILQG_JNT_SLIDE) {
-                    pos = pos + qq * axis[j];
+                    axisP[j] = mulv(R, A::ldP(m.jnt_axis[j]));
+                    pos = pos + qq * axisP[j];
                 } else {
+                    axisA[j] = mulv(R, A::ldA(m.jnt_axis[j]));
                     double s, c;
                     sincos(0.5 * qq, &s, &c);
-                    quat = qmul(quat, {c, m.jnt_axis[j][0] * s, m.jnt_axis[j][1] * s, m.jnt_axis[j][2] * s});
+                    quat = qmul(quat, A::hinge_quat(c, s, m.jnt_axis[j]));
                     constexpr bool last = IDX(jj) + 1 == T::body_jntnum(b);
                     if constexpr (!jz || !last) R = q2m(quat);   // the rotated frame: off-centre correction and / or the next joint
                     if constexpr (jz) pos = anchor[j];
-                    else pos = anchor[j] - mulv(R, ld3(m.jnt_pos[j]));
+                    else pos = anchor[j] - mulv(R, A::ldP(m.jnt_pos[j]));
                 }
             }
         });
@@ -405,11 +542,11 @@ DEV void build_pos(const DevModel<T>& m, const double (&q)[T::NQ], PosStage<T>& 
     });
     stage_sync();
     // ---- mj_comPos: tree centres of mass, spatial inertias, motion axes
-    V3 xipos[NB], com[NB];
+    P3 xipos[NB], com[NB];
     double tmass[NB];
     sfor<1, NB>([&](auto bb) {
         constexpr int b = IDX(bb);
-        xipos[b] = xpos[b] + mulv(xmat[b], ld3(m.body_ipos[b]));
+        xipos[b] = xpos[b] + mulv(xmat[b], A::ldP(m.body_ipos[b]));
         if constexpr (T::body_root(b) == b) { com[b] = m.body_mass[b] * xipos[b]; tmass[b] = m.body_mass[b]; }
         else { com[T::body_root(b)] = com[T::body_root(b)] + m.body_mass[b] * xipos[b]; tmass[T::body_root(b)] += m.body_mass[b]; }
     });
@@ -421,18 +558,16 @@ DEV void build_pos(const DevModel<T>& m, const double (&q)[T::NQ], PosStage<T>& 
     sfor<1, NB>([&](auto bb) {
         constexpr int b = IDX(bb);
         const M3& R = xmat[b];
-        const double* in = m.body_inertia[b];
+        const auto in = A::ldI(m.body_inertia[b]);
         // Iw = R Ib R^T
-        V3 c0 = col(R, 0), c1 = col(R, 1), c2 = col(R, 2);  // unused helper columns keep the algebra readable
-        (void)c0; (void)c1; (void)c2;
-        V3 t0 = {R.r0.x * in[0] + R.r0.y * in[3] + R.r0.z * in[4], R.r0.x * in[3] + R.r0.y * in[1] + R.r0.z * in[5],
-                 R.r0.x * in[4] + R.r0.y * in[5] + R.r0.z * in[2]};
-        V3 t1 = {R.r1.x * in[0] + R.r1.y * in[3] + R.r1.z * in[4], R.r1.x * in[3] + R.r1.y * in[1] + R.r1.z * in[5],
-                 R.r1.x * in[4] + R.r1.y * in[5] + R.r1.z * in[2]};
-        V3 t2 = {R.r2.x * in[0] + R.r2.y * in[3] + R.r2.z * in[4], R.r2.x * in[3] + R.r2.y * in[1] + R.r2.z * in[5],
-                 R.r2.x * in[4] + R.r2.y * in[5] + R.r2.z * in[2]};
+        P3 t0 = {R.r0.x * in.xx + R.r0.y * in.xy + R.r0.z * in.xz, R.r0.x * in.xy + R.r0.y * in.yy + R.r0.z * in.yz,
+                 R.r0.x * in.xz + R.r0.y * in.yz + R.r0.z * in.zz};
+        A3 t1 = {R.r1.x * in.xx + R.r1.y * in.xy + R.r1.z * in.xz, R.r1.x * in.xy + R.r1.y * in.yy + R.r1.z * in.yz,
+                 R.r1.x * in.xz + R.r1.y * in.yz + R.r1.z * in.zz};
+        P3 t2 = {R.r2.x * in.xx + R.r2.y * in.xy + R.r2.z * in.xz, R.r2.x * in.xy + R.r2.y * in.yy + R.r2.z * in.yz,
+                 R.r2.x * in.xz + R.r2.y * in.yz + R.r2.z * in.zz};
         double ms = m.body_mass[b];
-        V3 d = xipos[b] - com[T::body_root(b)];
+        P3 d = xipos[b] - com[T::body_root(b)];
         double dd = dot(d, d);
         cin[b] = {dot(t0, R.r0) + ms * (dd - d.x * d.x), dot(t1, R.r1) + ms * (dd - d.y * d.y), dot(t2, R.r2) + ms * (dd - d.z * d.z),
                   dot(t0, R.r1) - ms * d.x * d.y, dot(t0, R.r2) - ms * d.x * d.z, dot(t1, R.r2) - ms * d.y * d.z, ms * d, ms};
@@ -440,16 +575,16 @@ DEV void build_pos(const DevModel<T>& m, const double (&q)[T::NQ], PosStage<T>& 
     S6 (&cdof)[NV] = ps.cdof;
     sfor<0, NJ>([&](auto jj) {
         constexpr int j = IDX(jj), b = T::jnt_body(j), da = T::jnt_dofadr(j), ty = T::jnt_type(j);
-        V3 off = com[T::body_root(b)] - anchor[j];
+        P3 off = com[T::body_root(b)] - anchor[j];
         if constexpr (ty == ILQG_JNT_FREE) {
             cdof[da] = {{0, 0, 0}, {1, 0, 0}};
             cdof[da + 1] = {{0, 0, 0}, {0, 1, 0}};
             cdof[da + 2] = {{0, 0, 0}, {0, 0, 1}};
-            sfor<0, 3>([&](auto kk) { V3 a = col(xmat[b], IDX(kk)); cdof[da + 3 + IDX(kk)] = {a, cross(a, off)}; });
+            cdof_free_rot<j>(xmat[b], off, &cdof[da + 3]);
         } else if constexpr (ty == ILQG_JNT_SLIDE) {
-            cdof[da] = {{0, 0, 0}, axis[j]};
+            cdof[da] = {{0, 0, 0}, axisP[j]};
         } else {
-            cdof[da] = {axis[j], cross(axis[j], off)};
+            cdof[da] = {axisA[j], cross(axisA[j], off)};
         }
     });
     stage_sync();
@@ -467,7 +602,7 @@ DEV void build_pos(const DevModel<T>& m, const double (&q)[T::NQ], PosStage<T>& 
     });
     sfor<0, NV>([&](auto ii) {
         constexpr int i = IDX(ii);
-        S6 buf = mul(crb[T::dof_body(i)], cdof[i]);
+        const S6 buf = mul(crb[T::dof_body(i)], cdof[i]);
         sfor<0, i + 1>([&](auto jj) {
             constexpr int j = IDX(jj);
             if constexpr (dof_is_ancestor<T>(j, i)) w.M[tri(i, j)] = dot(cdof[j], buf);
@@ -504,11 +639,11 @@ DEV void build_pos(const DevModel<T>& m, const double (&q)[T::NQ], PosStage<T>& 
     stage_sync();
     if constexpr (T::NPAIR > 0) {
         // geom frames
-        V3 gpos[T::NGEOM], gax[T::NGEOM];
+        P3 gpos[T::NGEOM], gax[T::NGEOM];
         sfor<0, T::NGEOM>([&](auto gg) {
             constexpr int g = IDX(gg), b = T::geom_body(g);
-            if constexpr (b == 0) { gpos[g] = ld3(m.geom_pos[g]); gax[g] = ld3(m.geom_axis[g]); }
-            else { gpos[g] = xpos[b] + mulv(xmat[b], ld3(m.geom_pos[g])); gax[g] = mulv(xmat[b], ld3(m.geom_axis[g])); }
+            if constexpr (b == 0) { gpos[g] = A::ldP(m.geom_pos[g]); gax[g] = A::ldP(m.geom_axis[g]); }
+            else { gpos[g] = xpos[b] + mulv(xmat[b], A::ldP(m.geom_pos[g])); gax[g] = mulv(xmat[b], A::ldP(m.geom_axis[g])); }
         });
         // Phase A (unrolled over the model's pair list): narrow phase only — every contact found is pushed as a small
         // record.  Phase B (one runtime loop over the records) builds the rows.  The row construction is by far the
@@ -516,29 +651,29 @@ DEV void build_pos(const DevModel<T>& m, const double (&q)[T::NQ], PosStage<T>& 
         // instruction footprint by a third and lets lanes whose contacts come from different pairs share the same code.
         constexpr int MC = nz(T::MAXCON);
         double cdist[MC];
-        V3 cpos[MC], cnrm[MC], chint[MC];
+        P3 cpos[MC], cnrm[MC], chint[MC];
         int cpair[MC];   // pair index, bit 8 set when the tangent hint is valid
         int nc = 0;
-        auto push = [&](int p, double dist, V3 pos, V3 n, V3 hint, bool has_hint) {
+        auto push = [&](int p, double dist, P3 pos, P3 n, P3 hint, bool has_hint) {
             if (nc < MC) { cdist[nc] = dist; cpos[nc] = pos; cnrm[nc] = n; chint[nc] = hint; cpair[nc] = p | (has_hint ? 256 : 0); nc++; }
         };
         sfor<0, T::NPAIR>([&](auto pp) {
             constexpr int p = IDX(pp), g1 = T::pair_g1(p), g2 = T::pair_g2(p), t1 = T::geom_type(g1), t2 = T::geom_type(g2);
             const double margin = m.pair_margin[p];
-            auto sphere_sphere = [&](V3 p1, double r1, V3 p2, double r2) {
-                V3 n = p2 - p1;
+            auto sphere_sphere = [&](P3 p1, double r1, P3 p2, double r2) {
+                P3 n = p2 - p1;
                 double len = sqrt(dot(n, n));
                 double dist = len - r1 - r2;
                 if (dist > margin) return false;
                 if (len < ILQG_MINVAL) n = {1, 0, 0};
                 else n = (1.0 / len) * n;
-                push(p, dist, p1 + (r1 + 0.5 * dist) * n, n, V3{0, 0, 0}, false);
+                push(p, dist, p1 + (r1 + 0.5 * dist) * n, n, P3{0, 0, 0}, false);
                 return true;
             };
             if constexpr (t1 == ILQG_GEOM_PLANE && (t2 == ILQG_GEOM_CAPSULE || t2 == ILQG_GEOM_SPHERE)) {
-                V3 pn = gax[g1];
+                P3 pn = gax[g1];
                 double r = m.geom_size[g2][0];
-                auto plane_sphere = [&](V3 c, bool hint) {
+                auto plane_sphere = [&](P3 c, bool hint) {
                     double dist = dot(c - gpos[g1], pn) - r;
                     if (dist > margin) return;
                     push(p, dist, c - (r + 0.5 * dist) * pn, pn, gax[g2], hint);
@@ -556,25 +691,25 @@ DEV void build_pos(const DevModel<T>& m, const double (&q)[T::NQ], PosStage<T>& 
                 double t = clampd(dot(gpos[g1] - gpos[g2], gax[g2]), -h, h);
                 sphere_sphere(gpos[g1], m.geom_size[g1][0], gpos[g2] + t * gax[g2], m.geom_size[g2][0]);
             } else if constexpr (t1 == ILQG_GEOM_CAPSULE && t2 == ILQG_GEOM_CAPSULE) {
-                V3 p1 = gpos[g1], a1 = gax[g1], p2 = gpos[g2], a2 = gax[g2];
+                P3 p1 = gpos[g1], a1 = gax[g1], p2 = gpos[g2], a2 = gax[g2];
                 double r1 = m.geom_size[g1][0], h1 = m.geom_size[g1][1], r2 = m.geom_size[g2][0], h2 = m.geom_size[g2][1];
                 // exact cull: the capsules lie inside spheres of radius h + r about their centres; if even those are farther apart
                 // than the margin the narrow phase below cannot produce a contact (its distance is at least this one).  Self-collision
                 // pairs are almost always culled here, and the closest-point search is the most expensive piece of the position stage.
-                V3 ca[2], cb[2];
+                P3 ca[2], cb[2];
                 int ncand = 0;
                 const double reach = h1 + r1 + h2 + r2 + margin;
-                const V3 cc = p1 - p2;
+                const P3 cc = p1 - p2;
                 if (!(reach > 0 && dot(cc, cc) > reach * reach)) {
                 // candidate closest-point pairs on the two axis segments (at most two survive the distance test)
-                auto consider = [&](V3 c1, V3 c2) {
-                    V3 d = c2 - c1;
+                auto consider = [&](P3 c1, P3 c2) {
+                    P3 d = c2 - c1;
                     if (sqrt(dot(d, d)) - r1 - r2 > margin) return false;
                     if (ncand == 0) { ca[0] = c1; cb[0] = c2; } else { ca[1] = c1; cb[1] = c2; }
                     ncand++;
                     return true;
                 };
-                V3 dif = p1 - p2;
+                P3 dif = p1 - p2;
                 double mb = -dot(a1, a2), uu = -dot(a1, dif), vv = dot(a2, dif);
                 double det = 1.0 - mb * mb;
                 if (fabs(det) >= 1e-12) {
@@ -586,23 +721,23 @@ DEV void build_pos(const DevModel<T>& m, const double (&q)[T::NQ], PosStage<T>& 
                     consider(p1 + x1 * a1, p2 + x2 * a2);
                 } else {  // parallel axes: end points against the other segment, at most two contacts
                     for (int s = -1; s <= 1 && ncand < 2; s += 2) {
-                        V3 c1 = p1 + (s * h1) * a1;
+                        P3 c1 = p1 + (s * h1) * a1;
                         double t = dot(c1 - p2, a2);
                         if (t < -h2 || t > h2) continue;
                         consider(c1, p2 + t * a2);
                     }
                     for (int s = -1; s <= 1 && ncand < 2; s += 2) {
-                        V3 c2 = p2 + (s * h2) * a2;
+                        P3 c2 = p2 + (s * h2) * a2;
                         double t = dot(c2 - p1, a1);
                         if (t <= -h1 || t >= h1) continue;
                         consider(p1 + t * a1, c2);
                     }
                     if (ncand == 0) {
                         double best = 1e300;
-                        V3 bq1 = p1, bq2 = p2;
+                        P3 bq1 = p1, bq2 = p2;
                         for (int s = -1; s <= 1; s += 2)
                             for (int t = -1; t <= 1; t += 2) {
-                                V3 c1 = p1 + (s * h1) * a1, c2 = p2 + (t * h2) * a2;
+                                P3 c1 = p1 + (s * h1) * a1, c2 = p2 + (t * h2) * a2;
                                 double dd = dot(c1 - c2, c1 - c2);
                                 if (dd < best) { best = dd; bq1 = c1; bq2 = c2; }
                             }
@@ -621,12 +756,12 @@ DEV void build_pos(const DevModel<T>& m, const double (&q)[T::NQ], PosStage<T>& 
             const int p = cpair[c] & 255;
             const bool has_hint = (cpair[c] & 256) != 0;
             const double dist = cdist[c];
-            const V3 pos = cpos[c], n = cnrm[c];
+            const P3 pos = cpos[c], n = cnrm[c];
             // the pair's constants, selected from compile-time-indexed tables
             unsigned mk1 = 0, mk2 = 0;   // dofs that move body 1 / body 2
             int condim = 1;
             double margin = 0, mu = 0, tran = 0, K = 0, B = 0, imp = 0;
-            V3 r1 = {0, 0, 0}, r2 = {0, 0, 0};  // contact point relative to the com of body 1's / body 2's tree
+            P3 r1 = {0, 0, 0}, r2 = {0, 0, 0};  // contact point relative to the com of body 1's / body 2's tree
             sfor<0, T::NPAIR>([&](auto pp) {
                 constexpr int P = IDX(pp), b1 = T::geom_body(T::pair_g1(P)), b2 = T::geom_body(T::pair_g2(P));
                 if (p == P) {
@@ -643,15 +778,15 @@ DEV void build_pos(const DevModel<T>& m, const double (&q)[T::NQ], PosStage<T>& 
                     if constexpr (b2 > 0) r2 = pos - com[T::body_root(b2)];
                 }
             });
-            V3 ta, tb;
-            make_frame(n, chint[c], has_hint, ta, tb);
+            V3 ta, tb;   // the tangents are dense even for a planar tree (one of them is the out-of-plane direction)
+            make_frame(full(n), full(chint[c]), has_hint, ta, tb);
             double jn[NV], ja[NV], jb[NV];
             sfor<0, NV>([&](auto ii) {
                 constexpr int i = IDX(ii);
                 const bool m1 = (mk1 >> i) & 1u, m2 = (mk2 >> i) & 1u;
                 jn[i] = 0; ja[i] = 0; jb[i] = 0;
                 if (m1 != m2) {  // a dof that moves both bodies or neither gives no relative motion
-                    V3 jp = cdof[i].v + cross(cdof[i].w, m2 ? r2 : r1);
+                    P3 jp = cdof[i].v + cross(cdof[i].w, m2 ? r2 : r1);
                     if (!m2) jp = -1.0 * jp;
                     jn[i] = dot(n, jp);
                     if (condim == 3) { ja[i] = dot(ta, jp); jb[i] = dot(tb, jp); }
@@ -701,12 +836,15 @@ template <class T, bool SYNC = false, bool FUSED = false>
 DEV void build_vel(const DevModel<T>& m, const PosStage<T>& ps, const double (&qv)[T::NV], Work<T>& w) {
     auto stage_sync = [&]() { if constexpr (SYNC) __syncthreads(); };
     constexpr int NB = T::NBODY, NV = T::NV;
+    using A = AlgOf<T>;
+    using S6 = typename A::ST; using CD = typename A::CD; using Inert = typename A::IT;
     const S6 (&cdof)[NV] = ps.cdof;
     const Inert (&cin)[NB] = ps.cin;
     // ---- mj_comVel + mj_rne(flg_acc=0): bias forces
-    S6 cvel[NB], cdofdot[NV], cacc[NB], cfrc[NB];
+    S6 cvel[NB], cacc[NB], cfrc[NB];
+    CD cdofdot[NV];
     cvel[0] = {{0, 0, 0}, {0, 0, 0}};
-    cacc[0] = {{0, 0, 0}, {-m.gravity[0], -m.gravity[1], -m.gravity[2]}};
+    cacc[0] = {{0, 0, 0}, -1.0 * A::ldP(m.gravity)};
     sfor<1, NB>([&](auto bb) {
         constexpr int b = IDX(bb), p = T::body_parent(b);
         S6 cv = cvel[p];

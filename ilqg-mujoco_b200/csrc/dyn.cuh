@@ -24,6 +24,25 @@
 namespace ilqg {
 
 #define ILQG_MINVAL 1e-15
+// unrolling of the solver's loops over the constraint rows (local memory): independent loads of the next rows issue early
+#ifndef ILQG_ROW_UNROLL
+#define ILQG_ROW_UNROLL 2
+#endif
+#ifndef ILQG_HESS_UNROLL
+#define ILQG_HESS_UNROLL 0
+#endif
+#define ILQG_PRAGMA_(x) _Pragma(#x)
+#define ILQG_PRAGMA(x) ILQG_PRAGMA_(x)
+#if ILQG_ROW_UNROLL > 0
+#define ILQG_ROW_PRAGMA ILQG_PRAGMA(unroll ILQG_ROW_UNROLL)
+#else
+#define ILQG_ROW_PRAGMA
+#endif
+#if ILQG_HESS_UNROLL > 0
+#define ILQG_HESS_PRAGMA ILQG_PRAGMA(unroll ILQG_HESS_UNROLL)
+#else
+#define ILQG_HESS_PRAGMA
+#endif
 #define DEV __device__ __forceinline__
 
 template <int I, int N, class F>
@@ -879,6 +898,7 @@ DEV void build_vel(const DevModel<T>& m, const PosStage<T>& ps, const double (&q
     });
     // reference accelerations of the rows (mj_referenceConstraint): aref = -B (J qvel) - K imp (pos - margin)
     if constexpr (!FUSED)
+    ILQG_ROW_PRAGMA
     for (int r = 0; r < w.nefc; r++) {
         double s = 0;
         sfor<0, NV>([&](auto ii) { s += w.J[r][IDX(ii)] * qv[IDX(ii)]; });
@@ -939,6 +959,7 @@ DEV void solve(const DevModel<T>& m, Work<T>& w, double (&warm)[T::NV], double (
         // start from the better of the warm start and qacc_smooth; one pass over the rows evaluates both candidates
         // (J lives in local memory: every pass over it is a round of L1/L2 traffic) and leaves jar of the chosen one
         double cw = 0, cs = 0;
+        ILQG_ROW_PRAGMA
         for (int r = 0; r < ne; r++) {
             double jw = -w.aref[r], js = jw;
             sfor<0, NV>([&](auto ii) { const double Jri = w.J[r][IDX(ii)]; jw += Jri * warm[IDX(ii)]; js += Jri * w.as[IDX(ii)]; });
@@ -978,6 +999,7 @@ DEV void solve(const DevModel<T>& m, Work<T>& w, double (&warm)[T::NV], double (
             sfor<0, NT>([&](auto tt) { H[IDX(tt)] = w.M[IDX(tt)]; });
             sfor<0, NV>([&](auto ii) { w.fc[IDX(ii)] = 0; });
             double c = 0;
+            ILQG_HESS_PRAGMA
             for (int r = 0; r < ne; r++) {
                 double jar = w.jar[r];
                 if (jar < 0) {
@@ -1023,6 +1045,7 @@ DEV void solve(const DevModel<T>& m, Work<T>& w, double (&warm)[T::NV], double (
         });
         sfor<0, NV>([&](auto ii) { constexpr int i = IDX(ii); g1 += search[i] * (Ma[i] - w.fs[i]); g2 += search[i] * Mv[i]; });
         double d1 = g1, d2 = g2;
+        ILQG_ROW_PRAGMA
         for (int r = 0; r < ne; r++) {
             double s = 0;
             sfor<0, NV>([&](auto ii) { s += w.J[r][IDX(ii)] * search[IDX(ii)]; });
@@ -1043,6 +1066,7 @@ DEV void solve(const DevModel<T>& m, Work<T>& w, double (&warm)[T::NV], double (
             if (!(an > lo && an < hi)) an = isinf(hi) ? 2 * alpha + 1 : 0.5 * (lo + hi);
             double e1 = g1 + g2 * an, e2 = g2;
             mask_t mk = 0;
+            ILQG_ROW_PRAGMA
             for (int r = 0; r < ne; r++) {
                 double jv = w.jv[r];
                 double x = w.jar[r] + an * jv;
@@ -1063,6 +1087,7 @@ DEV void solve(const DevModel<T>& m, Work<T>& w, double (&warm)[T::NV], double (
         }
         if (alpha == 0) break;
         sfor<0, NV>([&](auto ii) { constexpr int i = IDX(ii); qacc[i] += alpha * search[i]; Ma[i] += alpha * Mv[i]; });
+        ILQG_ROW_PRAGMA
         for (int r = 0; r < ne; r++) w.jar[r] += alpha * w.jv[r];
         old = cost;
         iter++;
@@ -1071,6 +1096,7 @@ DEV void solve(const DevModel<T>& m, Work<T>& w, double (&warm)[T::NV], double (
     }
     if (need_forces && !forces_current) {  // qfrc_constraint at the final point (the integrators need it)
         sfor<0, NV>([&](auto ii) { w.fc[IDX(ii)] = 0; });
+        ILQG_ROW_PRAGMA
         for (int r = 0; r < ne; r++) {
             double jar = w.jar[r];
             if (jar < 0) {

@@ -246,8 +246,8 @@ struct FdSplit {
 
 // `perm` (slot -> knot, from fd_bin_kernel) or NULL for the identity: which knot a CTA slot works on.  A knot's segment is
 // contiguous in deriv either way; with the identity the CTA's segments also follow each other.
-template <class T, bool SYNC, int THREADS>
-__global__ void __launch_bounds__(THREADS, 256 / THREADS) fd_velctrl_kernel(const __grid_constant__ DevModel<T> m, int nknots, const double* __restrict__ qpos,
+template <class T, bool SYNC, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) fd_velctrl_kernel(const __grid_constant__ DevModel<T> m, int nknots, const double* __restrict__ qpos,
                                                             const double* __restrict__ qvel, const double* __restrict__ ctrl,
                                                             const double* __restrict__ qacc_center, const ilqg_cost* __restrict__ cost,
                                                             double eps, int niter, const FdDst dst, int* __restrict__ status,
@@ -316,8 +316,8 @@ __global__ void __launch_bounds__(THREADS, 256 / THREADS) fd_velctrl_kernel(cons
         }
 }
 
-template <class T, bool SYNC, int THREADS>
-__global__ void __launch_bounds__(THREADS, 256 / THREADS) fd_qpos_kernel(const __grid_constant__ DevModel<T> m, int nknots, const double* __restrict__ qpos,
+template <class T, bool SYNC, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) fd_qpos_kernel(const __grid_constant__ DevModel<T> m, int nknots, const double* __restrict__ qpos,
                                                          const double* __restrict__ qvel, const double* __restrict__ ctrl,
                                                          const double* __restrict__ qacc_center, const ilqg_cost* __restrict__ cost,
                                                          double eps, int niter, const FdDst dst, int* __restrict__ status,
@@ -464,13 +464,15 @@ struct Engine {
     int fd_variant = -1;   // -1: chosen per call by batch size (ILQG_FD_VARIANT overrides)
     int fd_bins = 1;       // work-class ordering of the knots in the stage-skipping kernels (ILQG_FD_BINS=0 disables)
     // ints of scratch fd() wants for `nknots` knots (bucket counters, keys, permutation); 0 = none
-    virtual size_t fd_scratch_ints(int nknots) const { (void)nknots; return 0; }
+    // (`batch`: the size of the whole batch a chunk belongs to — the kernel variant is chosen on it, so that a chunked host
+    //  call runs the same kernels, and returns the same bits, as one device call over the batch)
+    virtual size_t fd_scratch_ints(int nknots, int batch) const { (void)nknots; (void)batch; return 0; }
     virtual ~Engine() {}
     virtual int fd_launches() const { return 2; }
     virtual const char* name() const = 0;
     virtual cudaError_t fd(int nknots, const double* qpos, const double* qvel, const double* ctrl, const double* warm,
                            const ilqg_cost* cost_dev, const ilqg_fd_opts& o, const FdDst& dst, double* qacc_center, int* status,
-                           int* scratch, cudaStream_t s, cudaEvent_t* ev) = 0;
+                           int* scratch, int batch, cudaStream_t s, cudaEvent_t* ev) = 0;
     virtual cudaError_t forward(int n, const double* qpos, const double* qvel, const double* ctrl, double* warm, double* qacc,
                                 cudaStream_t s) = 0;
     virtual cudaError_t step(int n, int nsteps, double* qpos, double* qvel, const double* ctrl, double* warm, double* qacc,
@@ -490,31 +492,39 @@ struct EngineT : Engine {
     int last_launches = 3;
     static constexpr int SPLIT_MIN = 16384;   // knots from which the stage-skipping split is chosen
     int variant_for(int nknots) const { return fd_variant >= 0 ? fd_variant : (nknots >= SPLIT_MIN ? 3 : 2); }
-    size_t fd_scratch_ints(int nknots) const override {
-        return (variant_for(nknots) >= 3 && fd_bins && nknots < (1 << 24)) ? (size_t)FD_NBUCKET + 2 * (size_t)nknots : 0;
+    size_t fd_scratch_ints(int nknots, int batch) const override {
+        return (variant_for(batch) >= 3 && fd_bins && nknots < (1 << 24)) ? (size_t)FD_NBUCKET + 2 * (size_t)nknots : 0;
     }
-    template <int THREADS>
+    // CTA shapes of the split kernels (measured on B200 after the planar algebra shrank the per-rollout state):
+    //   qvel/ctrl: 256 threads, one CTA per SM at 255 registers (two CTAs at 128 registers spill the rows' neighbours: +70 % time);
+    //   qpos     : 192 threads = 16 knots with no idle lane, two CTAs per SM at 168 registers (12 warps per SM: -7 % time;
+    //              two 256-thread CTAs at 128 registers: +8 %).
+#ifndef ILQG_VU_THREADS
+#define ILQG_VU_THREADS 256
+#endif
+    static constexpr int VU_THREADS = ILQG_VU_THREADS, VU_MINB = 1, Q_THREADS = 192, Q_MINB = 2;
     void launch_split(int nknots, const double* qpos, const double* qvel, const double* ctrl, const ilqg_cost* cost_dev, const ilqg_fd_opts& o,
                       const FdDst& dst, const double* qacc_center, int* status, const int* perm, cudaStream_t s, cudaEvent_t* ev) {
-        using P = FdSplit<T, THREADS>;
+        using PV = FdSplit<T, VU_THREADS>;
+        using PQ = FdSplit<T, Q_THREADS>;
         // (the default L1 / shared-memory split is the best one: forcing a larger shared carve-out shrinks the L1 that holds the
         //  rollouts' local-memory rows and costs up to 30 % — measured with cudaFuncAttributePreferredSharedMemoryCarveout)
-        fd_velctrl_kernel<T, true, THREADS><<<(nknots + P::KPC_VU - 1) / P::KPC_VU, THREADS, 0, s>>>(dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev,
-                                                                                                   o.eps, o.niter, dst, status, perm);
+        fd_velctrl_kernel<T, true, VU_THREADS, VU_MINB><<<(nknots + PV::KPC_VU - 1) / PV::KPC_VU, VU_THREADS, 0, s>>>(
+            dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps, o.niter, dst, status, perm);
         if (ev) cudaEventRecord(ev[3], s);
-        fd_qpos_kernel<T, true, THREADS><<<(nknots + P::KPC_Q - 1) / P::KPC_Q, THREADS, 0, s>>>(dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps,
-                                                                                              o.niter, dst, status, perm);
+        fd_qpos_kernel<T, true, Q_THREADS, Q_MINB><<<(nknots + PQ::KPC_Q - 1) / PQ::KPC_Q, Q_THREADS, 0, s>>>(
+            dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps, o.niter, dst, status, perm);
     }
     cudaError_t fd(int nknots, const double* qpos, const double* qvel, const double* ctrl, const double* warm, const ilqg_cost* cost_dev,
-                   const ilqg_fd_opts& o, const FdDst& dst, double* qacc_center, int* status, int* scratch, cudaStream_t s,
+                   const ilqg_fd_opts& o, const FdDst& dst, double* qacc_center, int* status, int* scratch, int batch, cudaStream_t s,
                    cudaEvent_t* ev) override {
         using S = FdShape<T>;
         // variant 3 = stage-skipping split (fewest instructions: best once its qvel/ctrl kernel fills the GPU), 2 = one thread per
         // perturbed evaluation in a single launch (30x more threads per knot: lower latency for small batches); fd_variant -1 = by size
-        const int variant = variant_for(nknots);
+        const int variant = variant_for(batch > nknots ? batch : nknots);
         if (nknots <= 0) return cudaSuccess;
         FdBins bins{nullptr, nullptr, nullptr};
-        if (scratch && fd_scratch_ints(nknots)) {
+        if (scratch && fd_scratch_ints(nknots, batch > nknots ? batch : nknots)) {
             bins.cnt = scratch;
             bins.key = (unsigned int*)(scratch + FD_NBUCKET);
             bins.perm = scratch + FD_NBUCKET + nknots;
@@ -526,8 +536,7 @@ struct EngineT : Engine {
         if (bins.key) fd_bin_kernel<<<(nknots + 255) / 256, 256, 0, s>>>(nknots, bins);
         if (ev) cudaEventRecord(ev[1], s);
         if (variant >= 3) {  // stage-skipping split: qvel/ctrl columns, then qpos columns
-            // (256-thread CTAs, one per SM; two 128-thread CTAs per SM were measured 7 % slower: fewer warps share the instruction stream)
-            launch_split<256>(nknots, qpos, qvel, ctrl, cost_dev, o, dst, qacc_center, status, bins.perm, s, ev);
+            launch_split(nknots, qpos, qvel, ctrl, cost_dev, o, dst, qacc_center, status, bins.perm, s, ev);
             if (ev) cudaEventRecord(ev[2], s);
             return cudaGetLastError();
         }
@@ -615,7 +624,7 @@ struct CoopEngine : Engine {
         return e;
     }
     cudaError_t fd(int nknots, const double* qpos, const double* qvel, const double* ctrl, const double* warm, const ilqg_cost* cost_dev,
-                   const ilqg_fd_opts& o, const FdDst& dst, double* qacc_center, int* status, int* /*scratch*/, cudaStream_t s,
+                   const ilqg_fd_opts& o, const FdDst& dst, double* qacc_center, int* status, int* /*scratch*/, int /*batch*/, cudaStream_t s,
                    cudaEvent_t* ev) override {
         if (nknots <= 0) return cudaSuccess;
         if (dst.n > 1) return cudaErrorNotSupported;   // peer scatter is wired into the thread-per-rollout kernels only
@@ -722,6 +731,7 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, 
 }  // namespace ilqg
 
 // ==================================================================== C ABI
+#define ILQG_HOST_MAXCHUNKS 32
 struct ilqg_handle_s {
     int device = 0;
     ilqg_model model;
@@ -736,8 +746,11 @@ struct ilqg_handle_s {
     void* d_stage = nullptr; size_t stage_cap = 0;
     long launches = 0;  // kernels launched through this handle (bench.py reports it)
     int host_chunks = 0;  // > 0: forced chunk count of the host-pointer FD pipeline
+    int host_comp_streams = 2;  // compute streams of that pipeline (ILQG_HOST_COMP)
     bool profiling = false;
-    cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};  // chunk pipeline of the *_host FD entry point
+    cudaStream_t pipe[4] = {nullptr, nullptr, nullptr, nullptr};  // upload / compute A / download / compute B streams of the *_host FD entry point
+    cudaEvent_t pipe_ev[2 * ILQG_HOST_MAXCHUNKS] = {};    // per chunk: uploaded, computed
+    int* h_stat = nullptr; size_t hstat_cap = 0;          // pinned landing buffer of the status words
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // before centre, after centre, after the last FD kernel, between the two column kernels
 };
 
@@ -790,6 +803,7 @@ int ilqg_create(const ilqg_model* m, int device, ilqg_handle* out) {
     if (const char* e = getenv("ILQG_FD_VARIANT")) eng->fd_variant = atoi(e);
     if (const char* e = getenv("ILQG_FD_BINS")) eng->fd_bins = atoi(e);
     if (const char* e = getenv("ILQG_HOST_CHUNKS")) h->host_chunks = atoi(e);
+    if (const char* e = getenv("ILQG_HOST_COMP")) h->host_comp_streams = atoi(e);
     if (cudaMalloc(&h->d_cost, sizeof(ilqg_cost)) != cudaSuccess) {
         delete eng;
         delete h;
@@ -808,7 +822,9 @@ int ilqg_destroy(ilqg_handle h) {
     cudaFree(h->d_timeout);
     cudaFree(h->d_stage);
     for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
-    for (int i = 0; i < 3; i++) if (h->pipe[i]) cudaStreamDestroy(h->pipe[i]);
+    for (int i = 0; i < 4; i++) if (h->pipe[i]) cudaStreamDestroy(h->pipe[i]);
+    for (int i = 0; i < 2 * ILQG_HOST_MAXCHUNKS; i++) if (h->pipe_ev[i]) cudaEventDestroy(h->pipe_ev[i]);
+    if (h->h_stat) cudaFreeHost(h->h_stat);
     delete h->eng;
     delete h;
     return ILQG_OK;
@@ -905,7 +921,7 @@ static int ensure_stage(ilqg_handle h, size_t bytes) {
 // (calls that overlap on different streams must bring their own)
 static int fd_launch(ilqg_handle h, int nknots, const double* qpos, const double* qvel, const double* ctrl, const double* warmstart,
                      const ilqg_cost* dcost, const ilqg_fd_opts* opts, const ilqg::FdDst& dst, double* qacc_out, int* status, cudaStream_t s,
-                     int* scratch = nullptr) {
+                     int* scratch = nullptr, int batch = 0) {
     ilqg_fd_opts o;
     ilqg_fd_opts_default(&o);
     if (opts) o = *opts;
@@ -916,15 +932,16 @@ static int fd_launch(ilqg_handle h, int nknots, const double* qpos, const double
         if (rc) return rc;
         center = h->d_center;
     }
+    if (batch < nknots) batch = nknots;
     if (!scratch) {
-        const size_t want = h->eng->fd_scratch_ints(nknots);
+        const size_t want = h->eng->fd_scratch_ints(nknots, batch);
         if (want) {
             int rc = ensure_bins(h, want);
             if (rc) return rc;
             scratch = h->d_bins;
         }
     }
-    CU(h, h->eng->fd(nknots, qpos, qvel, ctrl, warmstart, dcost, o, dst, center, status, scratch, s, h->profiling ? h->ev : nullptr));
+    CU(h, h->eng->fd(nknots, qpos, qvel, ctrl, warmstart, dcost, o, dst, center, status, scratch, batch, s, h->profiling ? h->ev : nullptr));
     h->launches += h->eng->fd_launches();
     return ILQG_OK;
 }
@@ -1042,58 +1059,83 @@ int ilqg_fd_batch_host(ilqg_handle h, int nknots, const double* qpos, const doub
     CU(h, cudaSetDevice(h->device));
     const int nq = h->model.nq, nv = h->model.nv, nu = h->model.nu, nd = ilqg_deriv_size(&h->model);
     size_t n = (size_t)nknots;
-    // one staging block: qpos | qvel | ctrl | warm | qacc | deriv | status
+    // one staging block: qpos | qvel | ctrl | warm | qacc | deriv | status | work-class scratch
     size_t off_q = 0, off_v = off_q + n * nq, off_u = off_v + n * nv, off_w = off_u + n * nu, off_a = off_w + n * nv,
            off_d = off_a + n * nv, ndbl = off_d + n * nd;
-    // chunks large enough for the stage-skipping kernels (>= 16384 knots), four of them at the benchmark size: measured best
-    // on B200 (86,016 hopper knots: 1 chunk 3.11 ms, 2: 2.33, 4: 2.04, 8: 2.25, 16: 2.85; raw D2H of deriv alone: 1.35 ms).
-    // Also measured and not better: centre evaluations for all knots in one launch first, then the columns chunk by chunk (2.08 ms).
-    size_t nchunks = n / 20000 < 4 ? (n >= 8192 ? 4 : 1) : n / 20000;
+    // Pipeline over chunks of knots on streams BY FUNCTION — upload, compute (two, alternating), download — chained by events.
+    // The chunks' kernels run (nearly) in chunk order, so the first download starts after one chunk's upload + kernels and the
+    // copy engine then streams deriv back to back: the download is 5x the upload and, at PCIe rates, longer than the kernels
+    // (86,016 hopper knots = 72 MB = 1.3 ms at the measured 57 GB/s).  Two compute streams let the next chunk's CTAs fill the
+    // SMs the current chunk's last wave leaves idle.  Every chunk runs the kernel variant of the WHOLE batch, so the result is
+    // bit-identical to one device call.  Measured on B200, 86,016 knots: 1.73 ms with 4-6 chunks (one stream per chunk: 1.97;
+    // one compute stream: 1.87; chunk sizes ramping up from 4096: 1.97 — small chunks of the split kernels are latency-bound;
+    // kernels storing deriv straight into pinned host memory, no copy: 2.05 ms — the 432/288-byte segments of the reference
+    // layout reach 35 GB/s over PCIe as SM stores against the copy engine's 57).
+    size_t csize[ILQG_HOST_MAXCHUNKS];
+    size_t nchunks = n / 14336 < 1 ? 1 : n / 14336, cmax = 0;
     if (h->host_chunks > 0) nchunks = (size_t)h->host_chunks;   // ILQG_HOST_CHUNKS (experiments)
-    const size_t chunk = (n + nchunks - 1) / nchunks;
-    const size_t scr = h->eng->fd_scratch_ints((int)chunk);   // per chunk: the chunks overlap on the three streams
-    size_t bytes = ndbl * sizeof(double) + (n + nchunks * scr) * sizeof(int);
+    if (nchunks > ILQG_HOST_MAXCHUNKS) nchunks = ILQG_HOST_MAXCHUNKS;
+    {
+        const size_t c = (n + nchunks - 1) / nchunks;
+        nchunks = 0;
+        for (size_t lo = 0; lo < n; lo += c) csize[nchunks++] = lo + c <= n ? c : n - lo;
+    }
+    for (size_t i = 0; i < nchunks; i++) cmax = csize[i] > cmax ? csize[i] : cmax;
+    const size_t scr = h->eng->fd_scratch_ints((int)cmax, nknots);
+    size_t bytes = ndbl * sizeof(double) + (n + 2 * scr) * sizeof(int);
     int rc = ensure_stage(h, bytes);
     if (rc) return rc;
     double* b = (double*)h->d_stage;
     int* dstat = (int*)(b + ndbl);
     int* dscr = dstat + n;
-    std::unique_ptr<int[]> hs(new int[n]);
-    // Pipeline over chunks of knots on three streams: while chunk c computes, chunk c+1 uploads and chunk c-1 downloads
-    // (the deriv download is 5x the upload and, at PCIe rates, as long as the kernels).
-    if (!h->pipe[0])
-        for (int i = 0; i < 3; i++) CU(h, cudaStreamCreateWithFlags(&h->pipe[i], cudaStreamNonBlocking));
+    if (n > h->hstat_cap) {   // pinned landing buffer of the status words (the caller's array may be pageable)
+        if (h->h_stat) cudaFreeHost(h->h_stat);
+        h->h_stat = nullptr;
+        h->hstat_cap = 0;
+        CU(h, cudaHostAlloc((void**)&h->h_stat, n * sizeof(int), cudaHostAllocDefault));
+        h->hstat_cap = n;
+    }
+    if (!h->pipe[0]) {
+        for (int i = 0; i < 4; i++) CU(h, cudaStreamCreateWithFlags(&h->pipe[i], cudaStreamNonBlocking));
+        for (int i = 0; i < 2 * ILQG_HOST_MAXCHUNKS; i++) CU(h, cudaEventCreateWithFlags(&h->pipe_ev[i], cudaEventDisableTiming));
+    }
+    cudaStream_t up = h->pipe[0], down = h->pipe[2];
+    const int ncomp = h->host_comp_streams;
     const ilqg_cost* dcost = nullptr;
     if (cost) {
-        CU(h, cudaMemcpy(h->d_cost, cost, sizeof(ilqg_cost), cudaMemcpyHostToDevice));
+        CU(h, cudaMemcpyAsync(h->d_cost, cost, sizeof(ilqg_cost), cudaMemcpyHostToDevice, up));
         dcost = h->d_cost;
     }
-    int ci = 0;
-    for (size_t lo = 0; lo < n; lo += chunk, ci++) {
-        const size_t cn = lo + chunk <= n ? chunk : n - lo;
-        cudaStream_t s = h->pipe[ci % 3];
-        CU(h, cudaMemcpyAsync(b + off_q + lo * nq, qpos + lo * nq, cn * nq * sizeof(double), cudaMemcpyHostToDevice, s));
-        CU(h, cudaMemcpyAsync(b + off_v + lo * nv, qvel + lo * nv, cn * nv * sizeof(double), cudaMemcpyHostToDevice, s));
-        if (nu) CU(h, cudaMemcpyAsync(b + off_u + lo * nu, ctrl + lo * nu, cn * nu * sizeof(double), cudaMemcpyHostToDevice, s));
-        if (warmstart) CU(h, cudaMemcpyAsync(b + off_w + lo * nv, warmstart + lo * nv, cn * nv * sizeof(double), cudaMemcpyHostToDevice, s));
-        else CU(h, cudaMemsetAsync(b + off_w + lo * nv, 0, cn * nv * sizeof(double), s));
+    size_t lo = 0;
+    for (int ci = 0; ci < (int)nchunks; lo += csize[ci], ci++) {
+        const size_t cn = csize[ci];
+        CU(h, cudaMemcpyAsync(b + off_q + lo * nq, qpos + lo * nq, cn * nq * sizeof(double), cudaMemcpyHostToDevice, up));
+        CU(h, cudaMemcpyAsync(b + off_v + lo * nv, qvel + lo * nv, cn * nv * sizeof(double), cudaMemcpyHostToDevice, up));
+        if (nu) CU(h, cudaMemcpyAsync(b + off_u + lo * nu, ctrl + lo * nu, cn * nu * sizeof(double), cudaMemcpyHostToDevice, up));
+        if (warmstart) CU(h, cudaMemcpyAsync(b + off_w + lo * nv, warmstart + lo * nv, cn * nv * sizeof(double), cudaMemcpyHostToDevice, up));
+        else CU(h, cudaMemsetAsync(b + off_w + lo * nv, 0, cn * nv * sizeof(double), up));
         if (!cost)  // keep the caller's cost-gradient entries
-            CU(h, cudaMemcpyAsync(b + off_d + lo * nd, deriv + lo * nd, cn * nd * sizeof(double), cudaMemcpyHostToDevice, s));
+            CU(h, cudaMemcpyAsync(b + off_d + lo * nd, deriv + lo * nd, cn * nd * sizeof(double), cudaMemcpyHostToDevice, up));
+        cudaStream_t comp = h->pipe[(ncomp > 1 && (ci & 1)) ? 3 : 1];
+        CU(h, cudaEventRecord(h->pipe_ev[2 * ci], up));
+        CU(h, cudaStreamWaitEvent(comp, h->pipe_ev[2 * ci], 0));
         ilqg::FdDst dst{};
         dst.p[0] = b + off_d + lo * nd;
         dst.n = 1;
         rc = fd_launch(h, (int)cn, b + off_q + lo * nq, b + off_v + lo * nv, b + off_u + lo * nu, b + off_w + lo * nv, dcost, opts, dst,
-                       b + off_a + lo * nv, dstat + lo, s, scr ? dscr + (size_t)ci * scr : nullptr);
+                       b + off_a + lo * nv, dstat + lo, comp, scr ? dscr + ((ncomp > 1 && (ci & 1)) ? scr : 0) : nullptr, nknots);   // scratch per compute stream
         if (rc) return rc;
-        CU(h, cudaMemcpyAsync(deriv + lo * nd, b + off_d + lo * nd, cn * nd * sizeof(double), cudaMemcpyDeviceToHost, s));
-        if (qacc_out) CU(h, cudaMemcpyAsync(qacc_out + lo * nv, b + off_a + lo * nv, cn * nv * sizeof(double), cudaMemcpyDeviceToHost, s));
+        CU(h, cudaEventRecord(h->pipe_ev[2 * ci + 1], comp));
+        CU(h, cudaStreamWaitEvent(down, h->pipe_ev[2 * ci + 1], 0));
+        CU(h, cudaMemcpyAsync(deriv + lo * nd, b + off_d + lo * nd, cn * nd * sizeof(double), cudaMemcpyDeviceToHost, down));
+        if (qacc_out) CU(h, cudaMemcpyAsync(qacc_out + lo * nv, b + off_a + lo * nv, cn * nv * sizeof(double), cudaMemcpyDeviceToHost, down));
+        CU(h, cudaMemcpyAsync(h->h_stat + lo, dstat + lo, cn * sizeof(int), cudaMemcpyDeviceToHost, down));
     }
-    for (int i = 0; i < 3; i++) CU(h, cudaStreamSynchronize(h->pipe[i]));
-    CU(h, cudaMemcpy(hs.get(), dstat, n * sizeof(int), cudaMemcpyDeviceToHost));  // pageable target: after the pipeline has drained
+    CU(h, cudaStreamSynchronize(down));   // the last download follows every upload and every kernel
     int bad = 0;
     for (size_t i = 0; i < n; i++) {
-        if (status) status[i] = hs[i];
-        if (hs[i]) bad = 1;
+        if (status) status[i] = h->h_stat[i];
+        if (h->h_stat[i]) bad = 1;
     }
     return bad ? fail(h, ILQG_ERR_NONFINITE, "non-finite accelerations or exceeded contact capacity in at least one knot (see status[])") : ILQG_OK;
 }
@@ -1340,12 +1382,12 @@ int ilqg_ilqr_linearise(ilqg_ilqr w, void* stream) {                     // FD a
     dst.p[0] = b.deriv;
     dst.n = 1;
     int* scratch = nullptr;
-    if (const size_t want = h->eng->fd_scratch_ints(nknots)) {
+    if (const size_t want = h->eng->fd_scratch_ints(nknots, nknots)) {
         rc = ensure_bins(h, want);
         if (rc) return rc;
         scratch = h->d_bins;
     }
-    CU(h, h->eng->fd(nknots, b.nom_q, b.nom_v, b.nom_u, b.nom_w, w->host_cost ? nullptr : w->d_cost, w->fd, dst, h->d_center, nullptr, scratch, s,
+    CU(h, h->eng->fd(nknots, b.nom_q, b.nom_v, b.nom_u, b.nom_w, w->host_cost ? nullptr : w->d_cost, w->fd, dst, h->d_center, nullptr, scratch, nknots, s,
                      nullptr));
     h->launches += h->eng->fd_launches();
     return ILQG_OK;

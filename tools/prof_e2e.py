@@ -19,6 +19,7 @@ def step():
     L.ilqg_fd_batch_host(h._h, nk, C.c_void_p(hq.data_ptr()), C.c_void_p(hv.data_ptr()), C.c_void_p(hu.data_ptr()), C.c_void_p(hw.data_ptr()),
                          cost.ctypes.data_as(C.c_void_p), None, C.c_void_p(hd.data_ptr()), C.c_void_p(ha.data_ptr()), C.c_void_p(hs.data_ptr()))
 for ch in sys.argv[1:] or ["0"]:
+    if ":" in ch: ch, os.environ["ILQG_HOST_COMP"] = ch.split(":")
     if ch != "0": os.environ["ILQG_HOST_CHUNKS"] = ch   # read when the handle is created
     h = pkg.Handle(model, 0)
     for _ in range(3): step()

@@ -61,6 +61,7 @@ struct FdBins {
     int* perm;           // [nknots] slot -> knot
 };
 
+// (register caps for 12 / 16 resident warps per SM were measured on this kernel after the planar algebra: +16 % time both)
 template <class T>
 __global__ void __launch_bounds__(128) fd_center_kernel(const __grid_constant__ DevModel<T> m, int nknots, const double* __restrict__ qpos,
                                                         const double* __restrict__ qvel, const double* __restrict__ ctrl,
@@ -490,19 +491,20 @@ struct EngineT : Engine {
     const char* name() const override { return T::NAME; }
     int fd_launches() const override { return last_launches; }
     int last_launches = 3;
-    static constexpr int SPLIT_MIN = 16384;   // knots from which the stage-skipping split is chosen
+    // knots from which the stage-skipping split is chosen.  Measured on B200 (hopper, M knots/s, single launch vs split):
+    // 16K 58.9 / 48.1, 21.5K 60.5 / 55.8, 28.7K 64.9 / 63.4, 43K 69.8 / 82.9, 86K 76.9 / 105 — the split's qvel/ctrl kernel has a
+    // latency floor of 0.18 ms (a stance CTA's 6 sequential solves), the single launch none.
+    static constexpr int SPLIT_MIN = 24576;
     int variant_for(int nknots) const { return fd_variant >= 0 ? fd_variant : (nknots >= SPLIT_MIN ? 3 : 2); }
     size_t fd_scratch_ints(int nknots, int batch) const override {
         return (variant_for(batch) >= 3 && fd_bins && nknots < (1 << 24)) ? (size_t)FD_NBUCKET + 2 * (size_t)nknots : 0;
     }
     // CTA shapes of the split kernels (measured on B200 after the planar algebra shrank the per-rollout state):
-    //   qvel/ctrl: 256 threads, one CTA per SM at 255 registers (two CTAs at 128 registers spill the rows' neighbours: +70 % time);
+    //   qvel/ctrl: 256 threads, one CTA per SM at 255 registers (two CTAs at 128 registers spill the rows' neighbours: +70 % time;
+    //              192 threads, one CTA per SM — a quarter less local-memory footprint in L1, a quarter fewer warps: +19 %);
     //   qpos     : 192 threads = 16 knots with no idle lane, two CTAs per SM at 168 registers (12 warps per SM: -7 % time;
     //              two 256-thread CTAs at 128 registers: +8 %).
-#ifndef ILQG_VU_THREADS
-#define ILQG_VU_THREADS 256
-#endif
-    static constexpr int VU_THREADS = ILQG_VU_THREADS, VU_MINB = 1, Q_THREADS = 192, Q_MINB = 2;
+    static constexpr int VU_THREADS = 256, VU_MINB = 1, Q_THREADS = 192, Q_MINB = 2;
     void launch_split(int nknots, const double* qpos, const double* qvel, const double* ctrl, const ilqg_cost* cost_dev, const ilqg_fd_opts& o,
                       const FdDst& dst, const double* qacc_center, int* status, const int* perm, cudaStream_t s, cudaEvent_t* ev) {
         using PV = FdSplit<T, VU_THREADS>;

@@ -218,3 +218,31 @@ def test_empty_and_single_knot_batches(handles, pkg):
         q = np.zeros((1, m.nq)); q[0, min(1, m.nq - 1)] = 1.2 if name == "hopper" else 0.1
         d, a, st = h.fd_batch_host(q, np.zeros((1, m.nv)), np.zeros((1, m.nu)), None, None)
         assert d.shape == (1, m.nd) and st[0] == 0 and np.isfinite(d[:, :m.nv * (2 * m.nv + m.nu)]).all()
+
+
+def test_out_of_plane_variant_of_a_planar_tree_leaves_the_planar_kernels(pkg, oracle, tmp_path):
+    """The compiled-in hopper topology carries PLANAR_Y (its kernels drop every out-of-plane component at compile time).
+    The same tree with one geom moved out of the xz-plane must NOT bind to those kernels: it runs on the generic engine
+    and still matches the oracle, which computes the dense algebra on the modified tables."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    m = pkg.Model.named("hopper").copy()
+    gp = m.field("geom_pos").reshape(-1, 3)
+    gp[4, 1] = 0.03                       # the foot capsule, 3 cm off the plane
+    path = str(tmp_path / "hopper_offplane.ilqgm")
+    assert pkg.lib().ilqg_model_save(path.encode(), m.ptr) == 0
+    om = oracle.Model(path)
+    h = pkg.Handle(m, 0)
+    assert h.engine == "generic-warp-per-rollout"
+    q, v, u, w = scenario_states("hopper", 48, seed=4242, oracle=oracle, om=om, roll=120)
+    cost = oracle.make_cost(q2=[1, 10], v2=[1, 10], u2=[1])
+    d_ref, _, _ = oracle.fd_batch(om, q, v, u, w, cost)
+    d_gpu, _, status = h.fd_batch_host(q, v, u, w, cost)
+    assert status.sum() == 0
+    assert_deriv_close(d_gpu, d_ref, m.nv, m.nu)
+    h.close()
+    # and the untouched tables do bind to the planar instantiation
+    h2 = pkg.Handle(pkg.Model.named("hopper"), 0)
+    assert h2.engine == "hopper"
+    h2.close()

@@ -534,6 +534,7 @@ struct EngineT : Engine {
         }
         last_launches = variant >= 3 ? (bins.key ? 4 : 3) : 2;
         if (ev) cudaEventRecord(ev[0], s);
+        // (64- and 32-thread CTAs for finer-grained balancing of this kernel's 2.3 waves: no gain, measured)
         fd_center_kernel<T><<<(nknots + 127) / 128, 128, 0, s>>>(dm, nknots, qpos, qvel, ctrl, warm, o.niter, o.nwarmup, qacc_center, status, bins);
         if (bins.key) fd_bin_kernel<<<(nknots + 255) / 256, 256, 0, s>>>(nknots, bins);
         if (ev) cudaEventRecord(ev[1], s);

@@ -90,7 +90,9 @@ struct CoopMem {
     double *J, *D, *rB, *rkt;              // constraint rows: Jacobian, 1/R, damping B, K*imp*(pos - margin)
     double *fb0, *aref0;                   // the centre's velocity-stage products (ctrl columns reuse them)
     double* Hc;                            // factor of the Newton Hessian M + J_A' D_A J_A for the centre solution's active set A
-    int* hdr;                              // hdr[0] = nefc, hdr[1] = capacity ok, hdr[2] = Hc valid, hdr[4..7] = active-set mask of Hc
+    int* hdr;                              // hdr[0] = nefc, hdr[1] = capacity ok, hdr[2] = Hc valid, hdr[3] = row bound of the knot's +-eps
+                                           // neighbourhood (centre only), hdr[4..7] = active-set mask of Hc
+    int maxefc;                            // row capacity of this block
     // ---- private working set
     double *pv, *pu;                       // perturbed qvel / ctrl
     double *cvel, *cacc, *cfrc, *cdofdot;
@@ -103,41 +105,44 @@ struct CoopMem {
 };
 
 __host__ __device__ inline int coop_nt(int nv) { return nv * (nv + 1) / 2; }
-__host__ __device__ inline size_t coop_cstate_doubles(const ilqg_model& m, bool full) {
+// `maxefc`: row capacity of the block (COOP_MAXEFC everywhere except the qpos-column kernel, which is launched once per capacity
+// class with the knots whose row bound fits — the rows are the largest part of a rollout's shared-memory state)
+__host__ __device__ inline size_t coop_cstate_doubles(const ilqg_model& m, bool full, int maxefc = COOP_MAXEFC) {
     const size_t nv = m.nv, nb = m.nbody;
     size_t n = m.nq + nv + m.nu + nv;                       // q v u center
     n += 6 * nv + 10 * nb + 3 * nb + nv;                    // cdof cinert com dspr
     n += 2 * (size_t)coop_nt(m.nv);                         // M L
-    n += (size_t)COOP_MAXEFC * nv + 3 * COOP_MAXEFC;        // J D rB rkt
+    n += (size_t)maxefc * nv + 3 * maxefc;                  // J D rB rkt
     n += 4;                                                 // hdr (8 ints)
     n = (n + 1) & ~(size_t)1;
     if (!full) return n;                                    // what a stand-alone rollout needs
-    n += nv + COOP_MAXEFC;                                  // fb0 aref0   } products of the centre evaluation that
+    n += nv + maxefc;                                       // fb0 aref0   } products of the centre evaluation that
     n += coop_nt(m.nv);                                     // Hc          } the qvel / ctrl columns reuse
     return (n + 1) & ~(size_t)1;
 }
-__host__ __device__ inline size_t coop_priv_doubles(const ilqg_model& m) {
+__host__ __device__ inline size_t coop_priv_doubles(const ilqg_model& m, int maxefc = COOP_MAXEFC) {
     const size_t nv = m.nv, nb = m.nbody, nj = m.njnt, ng = m.ngeom;
     size_t rne = 18 * nb + 6 * nv, hes = coop_nt(m.nv);   // the bias recursion's scratch is dead before the Newton Hessian is built
-    size_t priv = nv + m.nu + (rne > hes ? rne : hes) + 10 * nv + 3 * COOP_MAXEFC + (COOP_MAXEFC + 1) / 2;
+    size_t priv = nv + m.nu + (rne > hes ? rne : hes) + 10 * nv + 3 * (size_t)maxefc + ((size_t)maxefc + 1) / 2;
     size_t tmp = 19 * nb + 6 * nj + 6 * ng + 10 * nb + (size_t)COOP_MAXCON * 13 + (COOP_MAXCON + 1) / 2;
     size_t n = priv > tmp ? priv : tmp;
     return (n + 1) & ~(size_t)1;
 }
 
-DEV void coop_carve_cstate(CoopMem& w, double* base, const ilqg_model& m) {
+DEV void coop_carve_cstate(CoopMem& w, double* base, const ilqg_model& m, int maxefc = COOP_MAXEFC) {
+    w.maxefc = maxefc;
     const int nq = m.nq, nv = m.nv, nu = m.nu, nb = m.nbody, nt = coop_nt(m.nv);
     double* p = base;
     auto take = [&](size_t n) { double* r = p; p += n; return r; };
     w.q = take(nq); w.v = take(nv); w.u = take(nu); w.center = take(nv);
     w.cdof = take(6 * nv); w.cinert = take(10 * nb); w.com = take(3 * nb); w.dspr = take(nv);
     w.M = take(nt); w.L = take(nt);
-    w.J = take((size_t)COOP_MAXEFC * nv); w.D = take(COOP_MAXEFC); w.rB = take(COOP_MAXEFC); w.rkt = take(COOP_MAXEFC);
+    w.J = take((size_t)maxefc * nv); w.D = take(maxefc); w.rB = take(maxefc); w.rkt = take(maxefc);
     w.hdr = reinterpret_cast<int*>(p);
-    p = base + coop_cstate_doubles(m, false);
-    w.fb0 = take(nv); w.aref0 = take(COOP_MAXEFC); w.Hc = take(nt);   // only valid where the full C-state is allocated
+    p = base + coop_cstate_doubles(m, false, maxefc);
+    w.fb0 = take(nv); w.aref0 = take(maxefc); w.Hc = take(nt);   // only valid where the full C-state is allocated
 }
-DEV void coop_carve_priv(CoopMem& w, double* base, const ilqg_model& m) {
+DEV void coop_carve_priv(CoopMem& w, double* base, const ilqg_model& m, int maxefc = COOP_MAXEFC) {
     const int nv = m.nv, nu = m.nu, nb = m.nbody, nj = m.njnt, ng = m.ngeom, nt = coop_nt(m.nv);
     double* p = base;
     auto take = [&](size_t n) { double* r = p; p += n; return r; };
@@ -150,7 +155,7 @@ DEV void coop_carve_priv(CoopMem& w, double* base, const ilqg_model& m) {
     }
     w.fb = take(nv); w.fs = take(nv); w.as = take(nv); w.fc = take(nv); w.qacc = take(nv); w.warm = take(nv);
     w.Ma = take(nv); w.grad = take(nv); w.search = take(nv); w.Mv = take(nv);
-    w.aref = take(COOP_MAXEFC); w.jar = take(COOP_MAXEFC); w.jv = take(COOP_MAXEFC);
+    w.aref = take(maxefc); w.jar = take(maxefc); w.jv = take(maxefc);
     w.alist = reinterpret_cast<int*>(p);
     // temporaries of the position stage share the same bytes
     p = base;
@@ -424,20 +429,25 @@ DEV void coop_pos(const GModel* __restrict__ g, CoopMem& w, int lane, const int*
     __syncwarp();
     coop_chol(w.L, nv, lane);
     // ---- constraint rows: joint limits
-    int ne = 0;
+    // rowbound: the rows an evaluation within +-eps of this one can have at most — limits within margin + slack, and for every
+    // pair within margin + slack of contact the most contacts its narrow phase can return times its rows per contact
+    int ne = 0, rowbound = 0;
     for (int j0 = 0; j0 < nj; j0 += 32) {
         const int j = j0 + lane;
         int side = 0;
+        bool nearlim = false;
         double dist = 0;
         if (j < nj && m.jnt_limited[j] && m.jnt_type[j] != ILQG_JNT_FREE) {
             double value = w.q[m.jnt_qposadr[j]];
             double dlo = value - m.jnt_range[j][0], dhi = m.jnt_range[j][1] - value;
             if (dlo < m.jnt_margin[j]) { side = -1; dist = dlo; }
             else if (dhi < m.jnt_margin[j]) { side = 1; dist = dhi; }
+            nearlim = dlo < m.jnt_margin[j] + slack || dhi < m.jnt_margin[j] + slack;
         }
+        rowbound += __popc(__ballot_sync(0xffffffffu, nearlim));
         unsigned bal = __ballot_sync(0xffffffffu, side != 0);
         int r = ne + __popc(bal & ((1u << lane) - 1u));
-        if (side != 0 && r < COOP_MAXEFC) {
+        if (side != 0 && r < w.maxefc) {
             const int da = m.jnt_dofadr[j];
             double R, kt;
             row_params(g->jnt_K[j], g->jnt_imp[j], m.jnt_solimp[j], dist, m.jnt_margin[j], m.dof_invweight0[da], R, kt);
@@ -532,6 +542,14 @@ DEV void coop_pos(const GModel* __restrict__ g, CoopMem& w, int lane, const int*
         }
         if (cand_out) {   // record the near pairs in pair order
             unsigned nb_ = __ballot_sync(0xffffffffu, near);
+            int prow = 0;
+            if (near) {
+                const int t1 = m.geom_type[m.pair_geom1[p]], t2 = m.geom_type[m.pair_geom2[p]];
+                prow = ((t2 == ILQG_GEOM_CAPSULE && (t1 == ILQG_GEOM_PLANE || t1 == ILQG_GEOM_CAPSULE)) ? 2 : 1) * (m.pair_condim[p] == 3 ? 4 : 1);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) prow += __shfl_xor_sync(0xffffffffu, prow, o);
+            rowbound += prow;
             int slot = nrec + __popc(nb_ & ((1u << lane) - 1u));
             if (near && slot < COOP_MAXCAND) cand_out[1 + slot] = p;
             nrec += __popc(nb_);
@@ -554,16 +572,20 @@ DEV void coop_pos(const GModel* __restrict__ g, CoopMem& w, int lane, const int*
         }
         ncon += __shfl_sync(0xffffffffu, incl, 31);
     }
-    if (cand_out && lane == 0) cand_out[0] = nrec <= COOP_MAXCAND ? nrec : -1;
+    if (cand_out && lane == 0) {
+        cand_out[0] = nrec <= COOP_MAXCAND ? nrec : -1;
+        w.hdr[3] = rowbound;
+    }
     __syncwarp();
-    bool ok = ncon <= COOP_MAXCON;
-    if (!ok) ncon = COOP_MAXCON;
+    bool ok = ncon <= COOP_MAXCON && ne <= w.maxefc;
+    if (ncon > COOP_MAXCON) ncon = COOP_MAXCON;
+    if (ne > w.maxefc) ne = w.maxefc;
     // ---- contact rows: sequential over contacts, lanes over dofs
     for (int c = 0; c < ncon; c++) {
         const int p = w.cpair[c], condim = m.pair_condim[p];
         const int b1 = m.geom_bodyid[m.pair_geom1[p]], b2 = m.geom_bodyid[m.pair_geom2[p]];
         const int nrows = condim == 3 ? 4 : 1;
-        if (ne + nrows > COOP_MAXEFC) { ok = false; break; }
+        if (ne + nrows > w.maxefc) { ok = false; break; }
         V3 pos = gl3(w.cpos + 3 * c), n = gl3(w.cframe + 9 * c), ta = gl3(w.cframe + 9 * c + 3), tb = gl3(w.cframe + 9 * c + 6);
         double jn = 0, ja = 0, jb = 0;
         if (lane < nv) {
@@ -903,7 +925,8 @@ __global__ void __launch_bounds__(32) coop_center_kernel(const GModel* __restric
                                                          const double* __restrict__ qvel, const double* __restrict__ ctrl,
                                                          const double* __restrict__ warmstart, int niter, int nwarmup, double slack,
                                                          int cdbl, int pdbl, double* __restrict__ qacc_center, int* __restrict__ status,
-                                                         double* __restrict__ cstate_out, int* __restrict__ cand_out) {
+                                                         double* __restrict__ cstate_out, int* __restrict__ cand_out,
+                                                         int* __restrict__ rowbound_out) {
     extern __shared__ __align__(16) double coop_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int k = blockIdx.x * (blockDim.x >> 5) + wib;
@@ -945,6 +968,8 @@ __global__ void __launch_bounds__(32) coop_center_kernel(const GModel* __restric
     }
     fin = __all_sync(0xffffffffu, fin);
     if (status && lane == 0) status[k] = !ok ? ILQG_ERR_CAPACITY : (fin ? 0 : ILQG_ERR_NONFINITE);
+    if (rowbound_out && lane == 0)   // a knot whose candidate list overflowed tests every pair when perturbed: full capacity
+        rowbound_out[k] = (cand_out && cand_out[(size_t)k * (COOP_MAXCAND + 1)] < 0) ? COOP_MAXEFC : w.hdr[3];
     __syncwarp();
     if (cstate_out) {
         double* dst = cstate_out + (size_t)k * cdbl;
@@ -1022,7 +1047,10 @@ __global__ void __launch_bounds__(32) coop_qpos_kernel(const GModel* __restrict_
                                                        const double* __restrict__ qvel, const double* __restrict__ ctrl,
                                                        const double* __restrict__ qacc_center, const int* __restrict__ cand,
                                                        const ilqg_cost* __restrict__ cost, double eps, int niter, int cdbl, int pdbl,
+                                                       const int* __restrict__ rowbound, int cap_lo, int cap,
                                                        double* __restrict__ deriv, int* __restrict__ status) {
+    // Launched once per row-capacity class (cap_lo, cap]: a warp whose knot's row bound falls outside leaves at once.  cdbl / pdbl
+    // are the block sizes for capacity `cap` — the smaller class fits 8 rollouts per SM instead of 6.
     extern __shared__ __align__(16) double coop_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const ilqg_model& m = g->m;
@@ -1030,10 +1058,14 @@ __global__ void __launch_bounds__(32) coop_qpos_kernel(const GModel* __restrict_
     const long item = (long)blockIdx.x * (blockDim.x >> 5) + wib;
     if (item >= (long)nknots * nv) return;
     const int k = (int)(item / nv), i = (int)(item - (long)k * nv), col = nu + nv + i;
+    if (rowbound) {
+        const int rb = rowbound[k];
+        if (rb <= cap_lo || (rb > cap && cap < COOP_MAXEFC)) return;   // (bounds above the largest class run there and report capacity)
+    }
     CoopMem w;
     double* base = coop_smem + (size_t)wib * (cdbl + pdbl);
-    coop_carve_cstate(w, base, m);
-    coop_carve_priv(w, base + cdbl, m);
+    coop_carve_cstate(w, base, m, cap);
+    coop_carve_priv(w, base + cdbl, m, cap);
     const int* kc = cand ? cand + (size_t)k * (COOP_MAXCAND + 1) : nullptr;
     const int ncand = kc ? kc[0] : -1;
     double plus = 0, dcost = 0;

@@ -578,11 +578,17 @@ struct CoopEngine : Engine {
     ilqg_model tab;
     double* d_cstate = nullptr;      // [chunk][cdbl]  the centre's position-stage products
     int* d_cand = nullptr;           // [chunk][COOP_MAXCAND + 1]  collision pairs near contact
+    int* d_rowbound = nullptr;       // [chunk]  most rows an evaluation within +-eps of the knot can have
+    // row-capacity classes of the qpos kernel: 8 / 7 / 6 rollouts per SM for the humanoid (measured on B200, 2048 knots, qpos
+    // columns: one class of 72 rows 8.70 ms; classes 40|72 7.72 ms; 56|72 7.80 ms)
+    static constexpr int NCAP = 3;
+    int cap_class[NCAP] = {40, 56, COOP_MAXEFC};
+    int cdbl_c[NCAP] = {0, 0, 0}, pdbl_c[NCAP] = {0, 0, 0};
     int chunk_cap = 0;
     static constexpr int MAX_CHUNK = 8192;   // knots per internal pass (bounds the scratch: 27 KB of C-state per humanoid knot)
     const char* name() const override { return "generic-warp-per-rollout"; }
-    int fd_launches() const override { return 3; }
-    ~CoopEngine() override { cudaFree(d_g); cudaFree(d_cstate); cudaFree(d_cand); }
+    int fd_launches() const override { return 2 + NCAP; }
+    ~CoopEngine() override { cudaFree(d_g); cudaFree(d_cstate); cudaFree(d_cand); cudaFree(d_rowbound); }
     size_t warp_bytes() const { return (size_t)(cdbl + pdbl) * sizeof(double); }
     size_t center_bytes() const { return (size_t)(cfull + pdbl) * sizeof(double); }
     cudaError_t init(const ilqg_model& m) {
@@ -592,6 +598,10 @@ struct CoopEngine : Engine {
         cdbl = (int)coop_cstate_doubles(m, false);
         cfull = (int)coop_cstate_doubles(m, true);
         pdbl = (int)coop_priv_doubles(m);
+        for (int c = 0; c < NCAP; c++) {
+            cdbl_c[c] = (int)coop_cstate_doubles(m, false, cap_class[c]);
+            pdbl_c[c] = (int)coop_priv_doubles(m, cap_class[c]);
+        }
         cudaError_t e = cudaMalloc(&d_g, sizeof(GModel));
         if (e == cudaSuccess) e = cudaMemcpy(d_g, hg, sizeof(GModel), cudaMemcpyHostToDevice);
         delete hg;
@@ -619,10 +629,11 @@ struct CoopEngine : Engine {
     }
     cudaError_t ensure_scratch(int n) {
         if (n <= chunk_cap) return cudaSuccess;
-        cudaFree(d_cstate); cudaFree(d_cand);
-        d_cstate = nullptr; d_cand = nullptr; chunk_cap = 0;
+        cudaFree(d_cstate); cudaFree(d_cand); cudaFree(d_rowbound);
+        d_cstate = nullptr; d_cand = nullptr; d_rowbound = nullptr; chunk_cap = 0;
         cudaError_t e = cudaMalloc(&d_cstate, (size_t)n * cfull * sizeof(double));
         if (e == cudaSuccess) e = cudaMalloc(&d_cand, (size_t)n * (COOP_MAXCAND + 1) * sizeof(int));
+        if (e == cudaSuccess) e = cudaMalloc(&d_rowbound, (size_t)n * sizeof(int));
         if (e == cudaSuccess) chunk_cap = n;
         return e;
     }
@@ -644,11 +655,17 @@ struct CoopEngine : Engine {
             const double *q = qpos + (size_t)lo * nq, *v = qvel + (size_t)lo * nv, *u = ctrl + (size_t)lo * nu, *w = warm ? warm + (size_t)lo * nv : nullptr;
             double *qc = qacc_center + (size_t)lo * nv, *dv = deriv + (size_t)lo * nd;
             int* st = status ? status + lo : nullptr;
-            coop_center_kernel<<<n, 32, center_bytes(), s>>>(d_g, n, q, v, u, w, o.niter, o.nwarmup, slack, cfull, pdbl, qc, st, d_cstate, d_cand);
+            coop_center_kernel<<<n, 32, center_bytes(), s>>>(d_g, n, q, v, u, w, o.niter, o.nwarmup, slack, cfull, pdbl, qc, st, d_cstate, d_cand,
+                                                             d_rowbound);
             if (ev && lo == 0) cudaEventRecord(ev[1], s);
             coop_velctrl_kernel<<<n, vc_warps * 32, vc, s>>>(d_g, n, d_cstate, cost_dev, o.eps, o.niter, cfull, pdbl, dv, st);
             if (ev && lo == 0) cudaEventRecord(ev[3], s);
-            coop_qpos_kernel<<<(unsigned)((long)n * nv), 32, one, s>>>(d_g, n, q, v, u, qc, d_cand, cost_dev, o.eps, o.niter, cdbl, pdbl, dv, st);
+            // qpos columns, one launch per row-capacity class of the knots (a warp whose knot belongs to another class leaves at once)
+            for (int c = 0; c < NCAP; c++) {
+                const size_t bytes = (size_t)(cdbl_c[c] + pdbl_c[c]) * sizeof(double);
+                coop_qpos_kernel<<<(unsigned)((long)n * nv), 32, bytes, s>>>(d_g, n, q, v, u, qc, d_cand, cost_dev, o.eps, o.niter, cdbl_c[c], pdbl_c[c],
+                                                                            d_rowbound, c ? cap_class[c - 1] : -1, cap_class[c], dv, st);
+            }
         }
         if (ev) cudaEventRecord(ev[2], s);
         return cudaGetLastError();

@@ -2,9 +2,10 @@
 //
 // FD linearisation (replaces /root/reference/src/mjderivative.cpp:43-255), all knots of all trajectories per call:
 //   fd_center_kernel  : one thread per knot — the centre evaluation and its warm-up solves (:61-68); its product is the
-//                       warm start every perturbed solve begins from (:75).
-//   large batches     : fd_velctrl_kernel (qvel + ctrl columns on ONE position stage per thread: the reference's
-//                       mjSTAGE_POS / mjSTAGE_VEL skips, :92,124) and fd_qpos_kernel (qpos columns, full pipeline, :178).
+//                       warm start every perturbed solve begins from (:75).  It also ranks the knot in its work class.
+//   large batches     : fd_bin_kernel (work-class ordering of the knots), fd_velctrl_kernel (qvel + ctrl columns on ONE position
+//                       stage per thread: the reference's mjSTAGE_POS / mjSTAGE_VEL skips, :92,124) and fd_qpos_kernel (qpos
+//                       columns, full pipeline, :178).
 //   small batches     : fd_perturb_kernel, one thread per perturbed evaluation of any column in a single launch.
 //   Blocks of deriv are staged in shared memory and written as contiguous runs in the reference layout, to the caller's
 //   buffer or to several (peer-GPU) destinations at once.
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(256, 1) fd_perturb_kernel(const __grid_constan
 //                       (velocity stage + solve), +eps then -eps, all lanes of the CTA in the same iteration kind.
 //   fd_qpos_kernel    : one thread per perturbed evaluation of a qpos column (full pipeline), +/- lanes adjacent.
 // Per knot that is (GK + 2nv) position stages instead of 2(2nv+nu).  A CTA owns a whole number of knots
-// (floor(256 / lanes-per-knot)); their deriv segments are staged in shared memory and written as contiguous runs
+// (floor(CTA size / lanes-per-knot)); their deriv segments are staged in shared memory and written as contiguous runs
 // (the dv|du blocks are adjacent in the reference layout: 54 doubles per hopper knot; dq: 36).
 template <class T, int THREADS_ = 256>
 struct FdSplit {
@@ -534,7 +535,10 @@ struct EngineT : Engine {
         }
         last_launches = variant >= 3 ? (bins.key ? 4 : 3) : 2;
         if (ev) cudaEventRecord(ev[0], s);
-        // (64- and 32-thread CTAs for finer-grained balancing of this kernel's 2.3 waves: no gain, measured)
+        // (64- and 32-thread CTAs for finer-grained balancing of this kernel's 2.3 waves: no gain, measured.  Ordering this kernel's
+        //  knots by the permutation the previous call on the same batch ended with — stance knots first, sharing warps — takes 21 us
+        //  off it (SMs are busy 61 % of this kernel: ncu) but scrambles the ranks inside the buckets, which follow this kernel's
+        //  execution order; the column kernels then lose the locality of neighbouring knots and give 17 us back.  Not kept.)
         fd_center_kernel<T><<<(nknots + 127) / 128, 128, 0, s>>>(dm, nknots, qpos, qvel, ctrl, warm, o.niter, o.nwarmup, qacc_center, status, bins);
         if (bins.key) fd_bin_kernel<<<(nknots + 255) / 256, 256, 0, s>>>(nknots, bins);
         if (ev) cudaEventRecord(ev[1], s);

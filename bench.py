@@ -358,6 +358,61 @@ def bench_t1000(pkg, dev_index, T, steps, world, rank):
                            if world > 1 else "none (1 rank)"), "scaling": "strong"}
 
 
+# ------------------------------------------------------------------ pendulum MPC step (BASELINE configs[0]): a latency case
+_REF_MPC_SCRIPT = r"""
+import sys, os, time, ctypes as C
+sys.path.insert(0, os.path.join(%(root)r, "oracle"))
+import numpy as np, mjo_py as o
+R = C.CDLL(os.path.join(%(root)r, "oracle", "_ref", "libref_fd.so"))
+m = o.Model(os.path.join(%(root)r, "ilqg-mujoco_b200", "models", "inverted_pendulum.ilqgm"))
+q0 = np.array([0.1, 0.2]); v0 = np.zeros(2); nmpc = %(nmpc)d
+tr = np.zeros((nmpc, 5))
+t0 = time.perf_counter()
+rc = R.ref_pendulum_mpc(m.ptr, o._p(q0), o._p(v0), nmpc, o._p(tr), None, None, None, None, None, None, None)
+print(time.perf_counter() - t0 if rc == 0 else -1.0)
+"""
+
+
+def bench_mpc_step(pkg):
+    """One InvertedPendulum::forward() (10 iLQR iterations at N = 20 + one mj_step, inverted_pendulum.cpp:19-30) for ONE problem:
+    the host-language mirror on the GPU against the reference's own classes on the CPU.  A single 2-dof problem is a chain of
+    dependent launches — it cannot fill a GPU; the number is reported because configs[0] names this run."""
+    import subprocess
+    path = os.path.join(ROOT, "ilqg-mujoco_b200", "libilqg_host.so")
+    out = {"metric": "pendulum MPC step latency (configs[0]: one problem, N=20, 10 iterations)", "unit": "ms/step", "higher_is_better": False}
+    if not os.path.exists(path):
+        out["unavailable"] = "libilqg_host.so missing"
+        return out
+    H = C.CDLL(path)
+    model = os.path.join(pkg.MODELS_DIR, "inverted_pendulum.ilqgm").encode()
+    q0 = np.array([0.1, 0.2]); v0 = np.zeros(2)
+
+    def gpu(nmpc):
+        tr = np.zeros((nmpc, 5))
+        t0 = time.perf_counter()
+        rc = H.ilqg_host_pendulum_mpc(model, q0.ctypes.data_as(C.c_void_p), v0.ctypes.data_as(C.c_void_p), nmpc, tr.ctypes.data_as(C.c_void_p),
+                                      None, None, None, None, None, None, None)
+        return (time.perf_counter() - t0) if rc == 0 else float("nan"), tr
+    gpu(2)                              # warm-up (library and kernel load)
+    t_a, _ = gpu(2)
+    t_b, tr_gpu = gpu(22)               # the difference leaves out model load, handle creation and the constructor's rollout
+    out["value"] = 1e3 * (t_b - t_a) / 20
+
+    def ref(nmpc):                      # one reference ILQR instance per process (function-local statics, ilqr.h:137-140)
+        r = subprocess.run([sys.executable, "-c", _REF_MPC_SCRIPT % dict(root=ROOT, nmpc=nmpc)], capture_output=True, text=True, timeout=600)
+        try:
+            return float(r.stdout.strip().splitlines()[-1])
+        except (ValueError, IndexError):
+            return -1.0
+    if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_fd.so")):
+        r_a, r_b = ref(1), ref(4)
+        if r_a > 0 and r_b > 0:
+            out["cpu_baseline"] = {"value": 1e3 * (r_b - r_a) / 3, "unit": "ms/step", "cores": min(16, os.cpu_count() or 1), "kind": "reference",
+                                   "sample": "3 MPC steps of the reference's own InvertedPendulum / ILQR / Differentiator / calcMJDerivatives (verbatim "
+                                             "sources, oracle physics), OpenMP over FD columns"}
+    return out
+
+
 # ------------------------------------------------------------------ humanoid FD (BASELINE configs[2])
 def bench_humanoid(pkg, dev_index, nknots, steps, world, rank, with_cpu):
     import torch
@@ -529,6 +584,8 @@ def run_gpu_arm(args):
         secondary.append(bench_hopper_ilqr(pkg, local, 1024, 10, 2, world, rank))
         secondary.append(bench_t1000(pkg, local, 1000, 20, world, rank))
         secondary.append(bench_humanoid(pkg, local, args.humanoid_knots, 3, world, rank, with_cpu=(world == 1 and rank == 0)))
+        if world == 1 and rank == 0:
+            secondary.append(bench_mpc_step(pkg))
     total_ms, e2e_ms = float(tt[0]), float(tt[1])
     value = world * nk * args.steps / (total_ms * 1e-3)
     e2e_value = world * nk * args.steps / (e2e_ms * 1e-3)

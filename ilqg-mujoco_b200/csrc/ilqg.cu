@@ -1433,10 +1433,10 @@ int ilqg_ilqr_put_cost_rows_host(ilqg_ilqr w, const double* rows) {
     auto& b = w->b;
     const int nv = h->model.nv, nu = h->model.nu, nd = ilqg_deriv_size(&h->model), nr = 2 * nv + nu, T = b.N + 1, n = b.ninst;
     CU(h, cudaDeviceSynchronize());
-    for (int t = 0; t < T; t++)
-        for (int i = 0; i < n; i++)
-            CU(h, cudaMemcpy(b.deriv + ((size_t)t * n + i) * nd + (nd - nr), rows + ((size_t)i * T + t) * nr, sizeof(double) * nr,
-                             cudaMemcpyHostToDevice));
+    // one strided copy per instance: T rows of nr doubles into the tails of its T deriv blocks (time-major: block stride n * nd)
+    for (int i = 0; i < n; i++)
+        CU(h, cudaMemcpy2D(b.deriv + (size_t)i * nd + (nd - nr), sizeof(double) * (size_t)n * nd, rows + (size_t)i * T * nr, sizeof(double) * nr,
+                           sizeof(double) * nr, (size_t)T, cudaMemcpyHostToDevice));
     return ILQG_OK;
 }
 

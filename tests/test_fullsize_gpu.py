@@ -104,3 +104,21 @@ def test_work_class_ordering_changes_placement_only(full, pkg):
     torch.cuda.synchronize()
     assert torch.equal(plain, f["deriv"]) and torch.equal(st, f["status"])
     h0.close()
+
+
+@pytest.mark.parametrize("n", [50011, 28673, 14337])
+def test_host_pipeline_ragged_sizes(full, n):
+    """The host-pointer call splits the batch into uniform chunks over an upload, two compute and a download stream; sizes that
+    do not divide (ragged last chunk), that give an odd chunk count and that fall just above one chunk must return the bits of
+    one device call over the same knots (forced split kernels: the chunks run the variant of the whole batch)."""
+    import torch
+    f = full; h = f["h"]
+    sl = slice(1000, 1000 + n)
+    dev = torch.zeros((n, h.model.nd), dtype=torch.float64, device="cuda:0")
+    st = torch.zeros(n, dtype=torch.int32, device="cuda:0")
+    h.fd_batch_dev(f["q"][sl].contiguous(), f["v"][sl].contiguous(), f["u"][sl].contiguous(), f["w"][sl].contiguous(), dev, None, st, cost=f["cost"])
+    torch.cuda.synchronize()
+    d, a, hs = h.fd_batch_host(f["q"][sl].cpu().numpy(), f["v"][sl].cpu().numpy(), f["u"][sl].cpu().numpy(), f["w"][sl].cpu().numpy(), f["cost"])
+    assert np.array_equal(hs, st.cpu().numpy())
+    assert np.array_equal(d, dev.cpu().numpy())
+    assert np.array_equal(d, f["deriv"][sl].cpu().numpy())     # and of the full batch's slice

@@ -560,6 +560,121 @@ DEV void build_pos(const DevModel<T>& m, const double (&q)[T::NQ], PosStage<T>& 
         xmat[b] = q2m(quat);
     });
     stage_sync();
+    // contact records (narrow phase -> row construction); the narrow phase runs right after the kinematics so that the frames
+    // (xpos, xmat, geom frames) are dead while M is assembled and factorised — fewer live registers where the pressure peaks
+    constexpr int MC = nz(T::MAXCON);
+    double cdist[MC];
+    P3 cpos[MC], cnrm[MC], chint[MC];
+    int cpair[MC];   // pair index, bit 8 set when the tangent hint is valid
+    int nc = 0;
+    if constexpr (T::NPAIR > 0) {
+        // geom frames
+        P3 gpos[T::NGEOM], gax[T::NGEOM];
+        sfor<0, T::NGEOM>([&](auto gg) {
+            constexpr int g = IDX(gg), b = T::geom_body(g);
+            if constexpr (b == 0) { gpos[g] = A::ldP(m.geom_pos[g]); gax[g] = A::ldP(m.geom_axis[g]); }
+            else { gpos[g] = xpos[b] + mulv(xmat[b], A::ldP(m.geom_pos[g])); gax[g] = mulv(xmat[b], A::ldP(m.geom_axis[g])); }
+        });
+        // Phase A (unrolled over the model's pair list): narrow phase only — every contact found is pushed as a small
+        // record.  Phase B (one runtime loop over the records) builds the rows.  The row construction is by far the
+        // largest piece of code of the pipeline; keeping ONE copy of it instead of one per pair shrinks the kernel's
+        // instruction footprint by a third and lets lanes whose contacts come from different pairs share the same code.
+        auto push = [&](int p, double dist, P3 pos, P3 n, P3 hint, bool has_hint) {
+            if (nc < MC) { cdist[nc] = dist; cpos[nc] = pos; cnrm[nc] = n; chint[nc] = hint; cpair[nc] = p | (has_hint ? 256 : 0); nc++; }
+        };
+        sfor<0, T::NPAIR>([&](auto pp) {
+            constexpr int p = IDX(pp), g1 = T::pair_g1(p), g2 = T::pair_g2(p), t1 = T::geom_type(g1), t2 = T::geom_type(g2);
+            const double margin = m.pair_margin[p];
+            auto sphere_sphere = [&](P3 p1, double r1, P3 p2, double r2) {
+                P3 n = p2 - p1;
+                double len = sqrt(dot(n, n));
+                double dist = len - r1 - r2;
+                if (dist > margin) return false;
+                if (len < ILQG_MINVAL) n = {1, 0, 0};
+                else n = (1.0 / len) * n;
+                push(p, dist, p1 + (r1 + 0.5 * dist) * n, n, P3{0, 0, 0}, false);
+                return true;
+            };
+            if constexpr (t1 == ILQG_GEOM_PLANE && (t2 == ILQG_GEOM_CAPSULE || t2 == ILQG_GEOM_SPHERE)) {
+                P3 pn = gax[g1];
+                double r = m.geom_size[g2][0];
+                auto plane_sphere = [&](P3 c, bool hint) {
+                    double dist = dot(c - gpos[g1], pn) - r;
+                    if (dist > margin) return;
+                    push(p, dist, c - (r + 0.5 * dist) * pn, pn, gax[g2], hint);
+                };
+                if constexpr (t2 == ILQG_GEOM_SPHERE) plane_sphere(gpos[g2], false);
+                else {
+                    double h = m.geom_size[g2][1];
+#pragma unroll 1
+                    for (int e = 0; e < 2; e++) plane_sphere(gpos[g2] + (e ? -h : h) * gax[g2], true);
+                }
+            } else if constexpr (t1 == ILQG_GEOM_SPHERE && t2 == ILQG_GEOM_SPHERE) {
+                sphere_sphere(gpos[g1], m.geom_size[g1][0], gpos[g2], m.geom_size[g2][0]);
+            } else if constexpr (t1 == ILQG_GEOM_SPHERE && t2 == ILQG_GEOM_CAPSULE) {
+                double h = m.geom_size[g2][1];
+                double t = clampd(dot(gpos[g1] - gpos[g2], gax[g2]), -h, h);
+                sphere_sphere(gpos[g1], m.geom_size[g1][0], gpos[g2] + t * gax[g2], m.geom_size[g2][0]);
+            } else if constexpr (t1 == ILQG_GEOM_CAPSULE && t2 == ILQG_GEOM_CAPSULE) {
+                P3 p1 = gpos[g1], a1 = gax[g1], p2 = gpos[g2], a2 = gax[g2];
+                double r1 = m.geom_size[g1][0], h1 = m.geom_size[g1][1], r2 = m.geom_size[g2][0], h2 = m.geom_size[g2][1];
+                // exact cull: the capsules lie inside spheres of radius h + r about their centres; if even those are farther apart
+                // than the margin the narrow phase below cannot produce a contact (its distance is at least this one).  Self-collision
+                // pairs are almost always culled here, and the closest-point search is the most expensive piece of the position stage.
+                P3 ca[2], cb[2];
+                int ncand = 0;
+                const double reach = h1 + r1 + h2 + r2 + margin;
+                const P3 cc = p1 - p2;
+                if (!(reach > 0 && dot(cc, cc) > reach * reach)) {
+                // candidate closest-point pairs on the two axis segments (at most two survive the distance test)
+                auto consider = [&](P3 c1, P3 c2) {
+                    P3 d = c2 - c1;
+                    if (sqrt(dot(d, d)) - r1 - r2 > margin) return false;
+                    if (ncand == 0) { ca[0] = c1; cb[0] = c2; } else { ca[1] = c1; cb[1] = c2; }
+                    ncand++;
+                    return true;
+                };
+                P3 dif = p1 - p2;
+                double mb = -dot(a1, a2), uu = -dot(a1, dif), vv = dot(a2, dif);
+                double det = 1.0 - mb * mb;
+                if (fabs(det) >= 1e-12) {
+                    double x1 = (uu - mb * vv) / det, x2 = (vv - mb * uu) / det;
+                    if (x1 > h1) { x1 = h1; x2 = vv - mb * h1; }
+                    else if (x1 < -h1) { x1 = -h1; x2 = vv + mb * h1; }
+                    if (x2 > h2) { x2 = h2; x1 = clampd(uu - mb * h2, -h1, h1); }
+                    else if (x2 < -h2) { x2 = -h2; x1 = clampd(uu + mb * h2, -h1, h1); }
+                    consider(p1 + x1 * a1, p2 + x2 * a2);
+                } else {  // parallel axes: end points against the other segment, at most two contacts
+                    for (int s = -1; s <= 1 && ncand < 2; s += 2) {
+                        P3 c1 = p1 + (s * h1) * a1;
+                        double t = dot(c1 - p2, a2);
+                        if (t < -h2 || t > h2) continue;
+                        consider(c1, p2 + t * a2);
+                    }
+                    for (int s = -1; s <= 1 && ncand < 2; s += 2) {
+                        P3 c2 = p2 + (s * h2) * a2;
+                        double t = dot(c2 - p1, a1);
+                        if (t <= -h1 || t >= h1) continue;
+                        consider(p1 + t * a1, c2);
+                    }
+                    if (ncand == 0) {
+                        double best = 1e300;
+                        P3 bq1 = p1, bq2 = p2;
+                        for (int s = -1; s <= 1; s += 2)
+                            for (int t = -1; t <= 1; t += 2) {
+                                P3 c1 = p1 + (s * h1) * a1, c2 = p2 + (t * h2) * a2;
+                                double dd = dot(c1 - c2, c1 - c2);
+                                if (dd < best) { best = dd; bq1 = c1; bq2 = c2; }
+                            }
+                        consider(bq1, bq2);
+                    }
+                }
+                }
+#pragma unroll 1
+                for (int c = 0; c < ncand; c++) sphere_sphere(c ? ca[1] : ca[0], r1, c ? cb[1] : cb[0], r2);
+            }
+        });
+    }
     // ---- mj_comPos: tree centres of mass, spatial inertias, motion axes
     P3 xipos[NB], com[NB];
     double tmass[NB];
@@ -657,118 +772,6 @@ DEV void build_pos(const DevModel<T>& m, const double (&q)[T::NQ], PosStage<T>& 
     });
     stage_sync();
     if constexpr (T::NPAIR > 0) {
-        // geom frames
-        P3 gpos[T::NGEOM], gax[T::NGEOM];
-        sfor<0, T::NGEOM>([&](auto gg) {
-            constexpr int g = IDX(gg), b = T::geom_body(g);
-            if constexpr (b == 0) { gpos[g] = A::ldP(m.geom_pos[g]); gax[g] = A::ldP(m.geom_axis[g]); }
-            else { gpos[g] = xpos[b] + mulv(xmat[b], A::ldP(m.geom_pos[g])); gax[g] = mulv(xmat[b], A::ldP(m.geom_axis[g])); }
-        });
-        // Phase A (unrolled over the model's pair list): narrow phase only — every contact found is pushed as a small
-        // record.  Phase B (one runtime loop over the records) builds the rows.  The row construction is by far the
-        // largest piece of code of the pipeline; keeping ONE copy of it instead of one per pair shrinks the kernel's
-        // instruction footprint by a third and lets lanes whose contacts come from different pairs share the same code.
-        constexpr int MC = nz(T::MAXCON);
-        double cdist[MC];
-        P3 cpos[MC], cnrm[MC], chint[MC];
-        int cpair[MC];   // pair index, bit 8 set when the tangent hint is valid
-        int nc = 0;
-        auto push = [&](int p, double dist, P3 pos, P3 n, P3 hint, bool has_hint) {
-            if (nc < MC) { cdist[nc] = dist; cpos[nc] = pos; cnrm[nc] = n; chint[nc] = hint; cpair[nc] = p | (has_hint ? 256 : 0); nc++; }
-        };
-        sfor<0, T::NPAIR>([&](auto pp) {
-            constexpr int p = IDX(pp), g1 = T::pair_g1(p), g2 = T::pair_g2(p), t1 = T::geom_type(g1), t2 = T::geom_type(g2);
-            const double margin = m.pair_margin[p];
-            auto sphere_sphere = [&](P3 p1, double r1, P3 p2, double r2) {
-                P3 n = p2 - p1;
-                double len = sqrt(dot(n, n));
-                double dist = len - r1 - r2;
-                if (dist > margin) return false;
-                if (len < ILQG_MINVAL) n = {1, 0, 0};
-                else n = (1.0 / len) * n;
-                push(p, dist, p1 + (r1 + 0.5 * dist) * n, n, P3{0, 0, 0}, false);
-                return true;
-            };
-            if constexpr (t1 == ILQG_GEOM_PLANE && (t2 == ILQG_GEOM_CAPSULE || t2 == ILQG_GEOM_SPHERE)) {
-                P3 pn = gax[g1];
-                double r = m.geom_size[g2][0];
-                auto plane_sphere = [&](P3 c, bool hint) {
-                    double dist = dot(c - gpos[g1], pn) - r;
-                    if (dist > margin) return;
-                    push(p, dist, c - (r + 0.5 * dist) * pn, pn, gax[g2], hint);
-                };
-                if constexpr (t2 == ILQG_GEOM_SPHERE) plane_sphere(gpos[g2], false);
-                else {
-                    double h = m.geom_size[g2][1];
-#pragma unroll 1
-                    for (int e = 0; e < 2; e++) plane_sphere(gpos[g2] + (e ? -h : h) * gax[g2], true);
-                }
-            } else if constexpr (t1 == ILQG_GEOM_SPHERE && t2 == ILQG_GEOM_SPHERE) {
-                sphere_sphere(gpos[g1], m.geom_size[g1][0], gpos[g2], m.geom_size[g2][0]);
-            } else if constexpr (t1 == ILQG_GEOM_SPHERE && t2 == ILQG_GEOM_CAPSULE) {
-                double h = m.geom_size[g2][1];
-                double t = clampd(dot(gpos[g1] - gpos[g2], gax[g2]), -h, h);
-                sphere_sphere(gpos[g1], m.geom_size[g1][0], gpos[g2] + t * gax[g2], m.geom_size[g2][0]);
-            } else if constexpr (t1 == ILQG_GEOM_CAPSULE && t2 == ILQG_GEOM_CAPSULE) {
-                P3 p1 = gpos[g1], a1 = gax[g1], p2 = gpos[g2], a2 = gax[g2];
-                double r1 = m.geom_size[g1][0], h1 = m.geom_size[g1][1], r2 = m.geom_size[g2][0], h2 = m.geom_size[g2][1];
-                // exact cull: the capsules lie inside spheres of radius h + r about their centres; if even those are farther apart
-                // than the margin the narrow phase below cannot produce a contact (its distance is at least this one).  Self-collision
-                // pairs are almost always culled here, and the closest-point search is the most expensive piece of the position stage.
-                P3 ca[2], cb[2];
-                int ncand = 0;
-                const double reach = h1 + r1 + h2 + r2 + margin;
-                const P3 cc = p1 - p2;
-                if (!(reach > 0 && dot(cc, cc) > reach * reach)) {
-                // candidate closest-point pairs on the two axis segments (at most two survive the distance test)
-                auto consider = [&](P3 c1, P3 c2) {
-                    P3 d = c2 - c1;
-                    if (sqrt(dot(d, d)) - r1 - r2 > margin) return false;
-                    if (ncand == 0) { ca[0] = c1; cb[0] = c2; } else { ca[1] = c1; cb[1] = c2; }
-                    ncand++;
-                    return true;
-                };
-                P3 dif = p1 - p2;
-                double mb = -dot(a1, a2), uu = -dot(a1, dif), vv = dot(a2, dif);
-                double det = 1.0 - mb * mb;
-                if (fabs(det) >= 1e-12) {
-                    double x1 = (uu - mb * vv) / det, x2 = (vv - mb * uu) / det;
-                    if (x1 > h1) { x1 = h1; x2 = vv - mb * h1; }
-                    else if (x1 < -h1) { x1 = -h1; x2 = vv + mb * h1; }
-                    if (x2 > h2) { x2 = h2; x1 = clampd(uu - mb * h2, -h1, h1); }
-                    else if (x2 < -h2) { x2 = -h2; x1 = clampd(uu + mb * h2, -h1, h1); }
-                    consider(p1 + x1 * a1, p2 + x2 * a2);
-                } else {  // parallel axes: end points against the other segment, at most two contacts
-                    for (int s = -1; s <= 1 && ncand < 2; s += 2) {
-                        P3 c1 = p1 + (s * h1) * a1;
-                        double t = dot(c1 - p2, a2);
-                        if (t < -h2 || t > h2) continue;
-                        consider(c1, p2 + t * a2);
-                    }
-                    for (int s = -1; s <= 1 && ncand < 2; s += 2) {
-                        P3 c2 = p2 + (s * h2) * a2;
-                        double t = dot(c2 - p1, a1);
-                        if (t <= -h1 || t >= h1) continue;
-                        consider(p1 + t * a1, c2);
-                    }
-                    if (ncand == 0) {
-                        double best = 1e300;
-                        P3 bq1 = p1, bq2 = p2;
-                        for (int s = -1; s <= 1; s += 2)
-                            for (int t = -1; t <= 1; t += 2) {
-                                P3 c1 = p1 + (s * h1) * a1, c2 = p2 + (t * h2) * a2;
-                                double dd = dot(c1 - c2, c1 - c2);
-                                if (dd < best) { best = dd; bq1 = c1; bq2 = c2; }
-                            }
-                        consider(bq1, bq2);
-                    }
-                }
-                }
-#pragma unroll 1
-                for (int c = 0; c < ncand; c++) sphere_sphere(c ? ca[1] : ca[0], r1, c ? cb[1] : cb[0], r2);
-            }
-        });
-        stage_sync();
         // Phase B: rows of every contact found
 #pragma unroll 1
         for (int c = 0; c < nc; c++) {

@@ -496,7 +496,13 @@ DEV void cdof_free_rot(const M3& xmat, P3 off, S6* cdof3) {
 // FUSED (qv != nullptr): the velocity is known while the rows are built — aref is finished here from the Jacobian still in
 // registers and the per-row constants (B, k-term) never go to local memory; build_vel then skips its pass over the rows.
 template <class T, bool SYNC = false, bool FUSED = false>
-DEV void build_pos(const DevModel<T>& m, const double (&q)[T::NQ], PosStage<T>& ps, Work<T>& w, const double* qv = nullptr) {
+DEV void build_vel(const DevModel<T>& m, const PosStage<T>& ps, const double (&qv)[T::NV], Work<T>& w);
+template <class T>
+DEV void finish_smooth(const DevModel<T>& m, const double (&u)[nz(T::NU)], Work<T>& w);
+
+template <class T, bool SYNC = false, bool FUSED = false>
+DEV void build_pos(const DevModel<T>& m, const double (&q)[T::NQ], PosStage<T>& ps, Work<T>& w, const double* qv = nullptr,
+                   const double* uu = nullptr) {
     auto stage_sync = [&]() { if constexpr (SYNC) __syncthreads(); };
     constexpr int NB = T::NBODY, NV = T::NV, NJ = T::NJNT;
     using A = AlgOf<T>;   // dense 3-D types, or the planar patterns (see Alg)
@@ -727,6 +733,9 @@ DEV void build_pos(const DevModel<T>& m, const double (&q)[T::NQ], PosStage<T>& 
         if constexpr (T::jnt_type(j) != ILQG_JNT_FREE && T::jnt_hasspring(j)) ps.dspr[i] = q[T::jnt_qposadr(j)] - m.qpos_spring[T::jnt_qposadr(j)];
         else ps.dspr[i] = 0;
     });
+    // FUSED (velocity and controls known): the bias recursion runs before M is assembled and qacc_smooth right after the
+    // factorisation — neither the recursion's per-body quantities nor the factor are live while the rows are built
+    if constexpr (FUSED) build_vel<T, SYNC, true>(m, ps, *reinterpret_cast<const double (*)[NV]>(qv), w);
     // ---- mj_crb + factor
     Inert crb[NB];
     sfor<1, NB>([&](auto bb) { crb[IDX(bb)] = cin[IDX(bb)]; });
@@ -745,6 +754,7 @@ DEV void build_pos(const DevModel<T>& m, const double (&q)[T::NQ], PosStage<T>& 
         w.M[tri(i, i)] += m.dof_armature[i];
     });
     chol_packed<NV>(w.M, w.L);
+    if constexpr (FUSED) finish_smooth<T>(m, *reinterpret_cast<const double (*)[nz(T::NU)]>(uu), w);
 
     stage_sync();
     // ---- constraint rows: joint limits, then contacts
@@ -854,7 +864,7 @@ DEV void build_pos(const DevModel<T>& m, const double (&q)[T::NQ], PosStage<T>& 
     stage_sync();
 }
 
-template <class T, bool SYNC = false, bool FUSED = false>
+template <class T, bool SYNC, bool FUSED>
 DEV void build_vel(const DevModel<T>& m, const PosStage<T>& ps, const double (&qv)[T::NV], Work<T>& w) {
     auto stage_sync = [&]() { if constexpr (SYNC) __syncthreads(); };
     constexpr int NB = T::NBODY, NV = T::NV;
@@ -929,9 +939,7 @@ template <class T, bool SYNC = false>
 DEV void build_problem(const DevModel<T>& m, const double (&q)[T::NQ], const double (&qv)[T::NV], const double (&u)[nz(T::NU)],
                        Work<T>& w) {
     PosStage<T> ps;
-    build_pos<T, SYNC, true>(m, q, ps, w, qv);
-    build_vel<T, SYNC, true>(m, ps, qv, w);
-    finish_smooth<T>(m, u, w);
+    build_pos<T, SYNC, true>(m, q, ps, w, qv, u);   // FUSED: includes the velocity stage and qacc_smooth
 }
 
 // ------------------------------------------------------------------ constraint solve (mj_fwdConstraint)

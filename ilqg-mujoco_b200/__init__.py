@@ -62,12 +62,21 @@ class Model:
 
     def __init__(self, buf):
         self.buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        if self.buf.size != lib().ilqg_model_sizeof():
+            raise ValueError(f"not an ilqg model table: {self.buf.size} bytes, expected {lib().ilqg_model_sizeof()}")
         ints = self.buf[:40].view(np.int32)
         if ints[0] != 0x494C5147:
             raise ValueError("not an ilqg model table")
         self.nq, self.nv, self.nu, self.nbody, self.njnt, self.ngeom, self.npair = (int(x) for x in ints[2:9])
         self.nd = self.nv * (2 * self.nv + self.nu) + 2 * self.nv + self.nu
         self.timestep = float(self.buf[40:48].view(np.float64)[0])
+
+    def validate(self):
+        """Structural check of the table (ilqg_model_validate): raises IlqgError with the offending field."""
+        err = C.create_string_buffer(256)
+        rc = lib().ilqg_model_validate(self.ptr, err, 256)
+        if rc:
+            raise IlqgError(rc, err.value.decode())
 
     @classmethod
     def load(cls, path):
@@ -217,6 +226,11 @@ class Handle:
     def peer_barrier(self, flag_ptrs, rank, epoch, stream=None):
         arr = (C.c_void_p * len(flag_ptrs))(*[C.c_void_p(int(p)) for p in flag_ptrs])
         self._check(lib().ilqg_peer_barrier(self._h, arr, len(flag_ptrs), int(rank), int(epoch), C.c_void_p(stream) if stream else None))
+
+    def fd_set_diag(self, diag):
+        """Per-knot diagnostics of the centre evaluation of the following fd_batch_dev calls: int32 CUDA tensor [nknots, 8]
+        (columns: nefc, iterations of the first solve, of all warm-up solves, active rows, cycles build, cycles solve) or None."""
+        self._check(lib().ilqg_fd_set_diag(self._h, _dp(diag)))
 
     def peer_barrier_timed_out(self):
         return bool(lib().ilqg_peer_barrier_timed_out(self._h))

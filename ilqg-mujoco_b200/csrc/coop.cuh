@@ -764,14 +764,14 @@ DEV void coop_hessian_factor(const CoopMem& w, double* H, int nv, int na, int la
 // in: private fs, as, aref, warm; out: private qacc (and warm, the next warm start); nv <= 32: lane i owns dof i
 // reuse: take the C-state's cached factor Hc whenever the active set equals the one it was built for (the qvel / ctrl columns
 // of a knot share M, J and D with the centre, so all of their Newton systems with that active set are the same matrix)
-DEV void coop_solve(const GModel* __restrict__ g, CoopMem& w, int maxiter, double tol, int lane, bool need_forces = false, bool reuse = false) {
+DEV int coop_solve(const GModel* __restrict__ g, CoopMem& w, int maxiter, double tol, int lane, bool need_forces = false, bool reuse = false) {
     const ilqg_model& m = g->m;
     const int nv = m.nv, ne = w.hdr[0];
     static_assert(COOP_MAXEFC <= 128, "mask width");
     if (ne == 0) {
         if (lane < nv) { w.qacc[lane] = w.as[lane]; w.warm[lane] = w.as[lane]; w.fc[lane] = 0; }
         __syncwarp();
-        return;
+        return 0;
     }
     const bool dof = lane < nv;
     const double fs_i = dof ? w.fs[lane] : 0.0, as_i = dof ? w.as[lane] : 0.0, warm_i = dof ? w.warm[lane] : 0.0;
@@ -908,6 +908,7 @@ DEV void coop_solve(const GModel* __restrict__ g, CoopMem& w, int maxiter, doubl
     }
     if (dof) { w.qacc[lane] = qacc_i; w.warm[lane] = qacc_i; w.fc[lane] = fc_i; }
     __syncwarp();
+    return iter;
 }
 
 // step cost on the device, lane 0 semantics (same term order as ilqg.cu's cost_eval)
@@ -926,7 +927,7 @@ __global__ void __launch_bounds__(32) coop_center_kernel(const GModel* __restric
                                                          const double* __restrict__ warmstart, int niter, int nwarmup, double slack,
                                                          int cdbl, int pdbl, double* __restrict__ qacc_center, int* __restrict__ status,
                                                          double* __restrict__ cstate_out, int* __restrict__ cand_out,
-                                                         int* __restrict__ rowbound_out) {
+                                                         int* __restrict__ rowbound_out, int* __restrict__ diag) {
     extern __shared__ __align__(16) double coop_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int k = blockIdx.x * (blockDim.x >> 5) + wib;
@@ -940,13 +941,27 @@ __global__ void __launch_bounds__(32) coop_center_kernel(const GModel* __restric
     for (int i = lane; i < m.nv; i += 32) w.v[i] = qvel[(size_t)k * m.nv + i];
     for (int i = lane; i < m.nu; i += 32) w.u[i] = ctrl[(size_t)k * m.nu + i];
     __syncwarp();
+    const long long t0 = clock64();
     coop_pos(g, w, lane, nullptr, -1, cand_out ? cand_out + (size_t)k * (COOP_MAXCAND + 1) : nullptr, slack);
     const bool ok = w.hdr[1] != 0;
     coop_vel(g, w, w.v, lane);
     coop_smooth(g, w, w.u, lane);
     if (lane < m.nv) w.warm[lane] = warmstart ? warmstart[(size_t)k * m.nv + lane] : 0.0;
     __syncwarp();
-    for (int rep = 0; rep < nwarmup; rep++) coop_solve(g, w, niter, 0.0, lane);
+    const long long t1 = clock64();
+    int it_first = 0, it_all = 0;
+    for (int rep = 0; rep < nwarmup; rep++) {
+        const int it = coop_solve(g, w, niter, 0.0, lane);
+        if (rep == 0) it_first = it;
+        it_all += it;
+    }
+    if (diag && lane == 0) {   // ILQG_DIAG_* (include/ilqg_b200.h)
+        const long long t2 = clock64();
+        int na = 0;
+        for (int r = 0; r < w.hdr[0]; r++) na += w.jar[r] < 0;
+        int* d = diag + (size_t)k * ILQG_DIAG_INTS;
+        d[0] = w.hdr[0]; d[1] = it_first; d[2] = it_all; d[3] = na; d[4] = (int)(t1 - t0); d[5] = (int)(t2 - t1); d[6] = 0; d[7] = 0;
+    }
     bool fin = true;
     for (int i = lane; i < m.nv; i += 32) { qacc_center[(size_t)k * m.nv + i] = w.qacc[i]; w.center[i] = w.qacc[i]; w.fb0[i] = w.fb[i]; fin = fin && isfinite(w.qacc[i]); }
     for (int r = lane; r < w.hdr[0]; r += 32) w.aref0[r] = w.aref[r];

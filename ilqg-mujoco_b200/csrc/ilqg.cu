@@ -67,7 +67,8 @@ template <class T>
 __global__ void __launch_bounds__(128) fd_center_kernel(const __grid_constant__ DevModel<T> m, int nknots, const double* __restrict__ qpos,
                                                         const double* __restrict__ qvel, const double* __restrict__ ctrl,
                                                         const double* __restrict__ warmstart, int niter, int nwarmup,
-                                                        double* __restrict__ qacc_center, int* __restrict__ status, const FdBins bins) {
+                                                        double* __restrict__ qacc_center, int* __restrict__ status, const FdBins bins,
+                                                        int* __restrict__ diag) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = k < nknots;
     const int kk = valid ? k : nknots - 1;   // the tail's idle lanes evaluate a clamped knot, writes masked (warp-wide ranking below)
@@ -75,9 +76,24 @@ __global__ void __launch_bounds__(128) fd_center_kernel(const __grid_constant__ 
     load_knot<T>(kk, qpos, qvel, ctrl, q, v, u);
     sfor<0, T::NV>([&](auto ii) { warm[IDX(ii)] = warmstart ? warmstart[(size_t)kk * T::NV + IDX(ii)] : 0.0; });
     Work<T> w;
+    const long long t0 = clock64();
     build_problem<T>(m, q, v, u, w);
+    const long long t1 = clock64();
+    int it_first = 0, it_all = 0;
 #pragma unroll 1
-    for (int rep = 0; rep < nwarmup; rep++) solve<T>(m, w, warm, qacc, niter, 0.0);   // one copy of the solver (instruction footprint)
+    for (int rep = 0; rep < nwarmup; rep++) {   // one copy of the solver (instruction footprint)
+        solve<T>(m, w, warm, qacc, niter, 0.0);
+        if (rep == 0) it_first = w.iters;
+        it_all += w.iters;
+    }
+    if (diag && valid) {   // ILQG_DIAG_* (include/ilqg_b200.h)
+        const long long t2 = clock64();
+        int na = 0;
+        for (int r = 0; r < w.nefc; r++) na += w.jar[r] < 0;
+        int4* d = reinterpret_cast<int4*>(diag + (size_t)k * ILQG_DIAG_INTS);
+        d[0] = make_int4(w.nefc, it_first, it_all, na);
+        d[1] = make_int4((int)(t1 - t0), (int)(t2 - t1), 0, 0);
+    }
     if (bins.key) {
         const int ne = w.nefc < FD_NBUCKET - 1 ? w.nefc : FD_NBUCKET - 1;
         const int b = valid ? FD_NBUCKET - 1 - ne : FD_NBUCKET;   // heaviest first; idle lanes form a group of their own
@@ -454,6 +470,10 @@ struct IlqrLaunch<T, true> {
 struct Engine {
     int fd_variant = -1;   // -1: chosen per call by batch size (ILQG_FD_VARIANT overrides)
     int fd_bins = 1;       // work-class ordering of the knots in the stage-skipping kernels (ILQG_FD_BINS=0 disables)
+    int* fd_diag = nullptr;   // [nknots][ILQG_DIAG_INTS] per-knot diagnostics of the next fd() call (device), or NULL
+    // false: fd() keeps engine-owned scratch indexed by the knot's position in the call, so two fd() calls must not overlap
+    // on different streams (the host-pointer pipeline then uses ONE compute stream)
+    virtual bool fd_calls_may_overlap() const { return true; }
     // ints of scratch fd() wants for `nknots` knots (bucket counters, keys, permutation); 0 = none
     // (`batch`: the size of the whole batch a chunk belongs to — the kernel variant is chosen on it, so that a chunked host
     //  call runs the same kernels, and returns the same bits, as one device call over the batch)
@@ -528,7 +548,7 @@ struct EngineT : Engine {
         //  knots by the permutation the previous call on the same batch ended with — stance knots first, sharing warps — takes 21 us
         //  off it (SMs are busy 61 % of this kernel: ncu) but scrambles the ranks inside the buckets, which follow this kernel's
         //  execution order; the column kernels then lose the locality of neighbouring knots and give 17 us back.  Not kept.)
-        fd_center_kernel<T><<<(nknots + 127) / 128, 128, 0, s>>>(dm, nknots, qpos, qvel, ctrl, warm, o.niter, o.nwarmup, qacc_center, status, bins);
+        fd_center_kernel<T><<<(nknots + 127) / 128, 128, 0, s>>>(dm, nknots, qpos, qvel, ctrl, warm, o.niter, o.nwarmup, qacc_center, status, bins, fd_diag);
         if (bins.key) fd_bin_kernel<<<(nknots + 255) / 256, 256, 0, s>>>(nknots, bins);
         if (ev) cudaEventRecord(ev[1], s);
         if (variant >= 3) {  // stage-skipping split: qvel/ctrl columns, then qpos columns
@@ -580,6 +600,7 @@ struct CoopEngine : Engine {
     int chunk_cap = 0;
     static constexpr int MAX_CHUNK = 8192;   // knots per internal pass (bounds the scratch: 27 KB of C-state per humanoid knot)
     const char* name() const override { return "generic-warp-per-rollout"; }
+    bool fd_calls_may_overlap() const override { return false; }   // d_cstate / d_cand / d_rowbound are indexed by position in the call
     int fd_launches() const override { return 2 + NCAP; }
     ~CoopEngine() override { cudaFree(d_g); cudaFree(d_cstate); cudaFree(d_cand); cudaFree(d_rowbound); }
     size_t warp_bytes() const { return (size_t)(cdbl + pdbl) * sizeof(double); }
@@ -649,7 +670,7 @@ struct CoopEngine : Engine {
             double *qc = qacc_center + (size_t)lo * nv, *dv = deriv + (size_t)lo * nd;
             int* st = status ? status + lo : nullptr;
             coop_center_kernel<<<n, 32, center_bytes(), s>>>(d_g, n, q, v, u, w, o.niter, o.nwarmup, slack, cfull, pdbl, qc, st, d_cstate, d_cand,
-                                                             d_rowbound);
+                                                             d_rowbound, fd_diag ? fd_diag + (size_t)lo * ILQG_DIAG_INTS : nullptr);
             if (ev && lo == 0) cudaEventRecord(ev[1], s);
             coop_velctrl_kernel<<<n, vc_warps * 32, vc, s>>>(d_g, n, d_cstate, cost_dev, o.eps, o.niter, cfull, pdbl, dv, st);
             if (ev && lo == 0) cudaEventRecord(ev[3], s);
@@ -755,6 +776,7 @@ struct ilqg_handle_s {
     int* d_bins = nullptr; size_t bins_cap = 0;   // work-class scratch of the FD kernels (ints)
     ilqg_cost* d_cost = nullptr;
     int* d_timeout = nullptr;  // set by a peer barrier that gave up waiting
+    int* diag = nullptr;       // caller's device array for per-knot diagnostics of the *_dev FD calls (ilqg_fd_set_diag), or NULL
     // staging for the *_host entry points
     void* d_stage = nullptr; size_t stage_cap = 0;
     long launches = 0;  // kernels launched through this handle (bench.py reports it)
@@ -798,7 +820,11 @@ const char* ilqg_last_error(ilqg_handle h) { return h ? h->err.c_str() : g_creat
 int ilqg_create(const ilqg_model* m, int device, ilqg_handle* out) {
     if (!m || !out) return fail(nullptr, ILQG_ERR_ARG, "null argument");
     *out = nullptr;
-    if (m->magic != ILQG_MODEL_MAGIC || m->version != ILQG_MODEL_VERSION) return fail(nullptr, ILQG_ERR_MODEL, "bad model magic/version");
+    {
+        char verr[256] = "";
+        const int vrc = ilqg_model_validate(m, verr, sizeof verr);
+        if (vrc) return fail(nullptr, vrc, verr);
+    }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -934,7 +960,7 @@ static int ensure_stage(ilqg_handle h, size_t bytes) {
 // (calls that overlap on different streams must bring their own)
 static int fd_launch(ilqg_handle h, int nknots, const double* qpos, const double* qvel, const double* ctrl, const double* warmstart,
                      const ilqg_cost* dcost, const ilqg_fd_opts* opts, const ilqg::FdDst& dst, double* qacc_out, int* status, cudaStream_t s,
-                     int* scratch = nullptr, int batch = 0) {
+                     int* scratch = nullptr, int batch = 0, int* diag = nullptr) {
     ilqg_fd_opts o;
     ilqg_fd_opts_default(&o);
     if (opts) o = *opts;
@@ -954,7 +980,10 @@ static int fd_launch(ilqg_handle h, int nknots, const double* qpos, const double
             scratch = h->d_bins;
         }
     }
-    CU(h, h->eng->fd(nknots, qpos, qvel, ctrl, warmstart, dcost, o, dst, center, status, scratch, batch, s, h->profiling ? h->ev : nullptr));
+    h->eng->fd_diag = diag;
+    cudaError_t fe = h->eng->fd(nknots, qpos, qvel, ctrl, warmstart, dcost, o, dst, center, status, scratch, batch, s, h->profiling ? h->ev : nullptr);
+    h->eng->fd_diag = nullptr;
+    CU(h, fe);
     h->launches += h->eng->fd_launches();
     return ILQG_OK;
 }
@@ -974,7 +1003,14 @@ int ilqg_fd_batch_dev(ilqg_handle h, int nknots, const double* qpos, const doubl
     ilqg::FdDst dst{};
     dst.p[0] = deriv;
     dst.n = 1;
-    return fd_launch(h, nknots, qpos, qvel, ctrl, warmstart, dcost, opts, dst, qacc_out, status, s);
+    return fd_launch(h, nknots, qpos, qvel, ctrl, warmstart, dcost, opts, dst, qacc_out, status, s, nullptr, 0, h->diag);
+}
+
+// per-knot diagnostics of the centre evaluation (ILQG_DIAG_* in ilqg_b200.h), written by the following *_dev FD calls on this handle
+int ilqg_fd_set_diag(ilqg_handle h, int* diag_dev) {
+    if (!h) return ILQG_ERR_ARG;
+    h->diag = diag_dev;
+    return ILQG_OK;
 }
 
 // The same linearisation with the deriv blocks stored to `ndst` destinations at once (each dsts[i] points at the slot of knot 0 of
@@ -999,7 +1035,7 @@ int ilqg_fd_batch_dev_scatter(ilqg_handle h, int nknots, const double* qpos, con
         dst.p[i] = dsts[i];
     }
     dst.n = ndst;
-    return fd_launch(h, nknots, qpos, qvel, ctrl, warmstart, dcost, opts, dst, qacc_out, status, s);
+    return fd_launch(h, nknots, qpos, qvel, ctrl, warmstart, dcost, opts, dst, qacc_out, status, s, nullptr, 0, h->diag);
 }
 
 // ---- peer-visible device buffers (CUDA IPC): one per rank, opened by every other rank of the node
@@ -1050,11 +1086,12 @@ int ilqg_peer_barrier(ilqg_handle h, int* const* flags, int nranks, int rank, in
     h->launches += 1;
     return ILQG_OK;
 }
-int ilqg_peer_barrier_timed_out(ilqg_handle h) {   // synchronises the device
+int ilqg_peer_barrier_timed_out(ilqg_handle h) {   // synchronises the device; reading clears the flag
     if (!h || !h->d_timeout) return 0;
     int v = 0;
     cudaSetDevice(h->device);
     if (cudaMemcpy(&v, h->d_timeout, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+    if (v) cudaMemset(h->d_timeout, 0, sizeof(int));
     return v;
 }
 int ilqg_peer_free(ilqg_handle h, void* dev_ptr) {
@@ -1067,7 +1104,7 @@ int ilqg_peer_free(ilqg_handle h, void* dev_ptr) {
 int ilqg_fd_batch_host(ilqg_handle h, int nknots, const double* qpos, const double* qvel, const double* ctrl, const double* warmstart,
                        const ilqg_cost* cost, const ilqg_fd_opts* opts, double* deriv, double* qacc_out, int* status) {
     if (!h) return ILQG_ERR_ARG;
-    if (nknots < 0 || (nknots > 0 && (!qpos || !qvel || !deriv))) return fail(h, ILQG_ERR_ARG, "null buffer");
+    if (nknots < 0 || (nknots > 0 && (!qpos || !qvel || !deriv || (h->model.nu > 0 && !ctrl)))) return fail(h, ILQG_ERR_ARG, "null buffer");
     if (nknots == 0) return ILQG_OK;
     CU(h, cudaSetDevice(h->device));
     const int nq = h->model.nq, nv = h->model.nv, nu = h->model.nu, nd = ilqg_deriv_size(&h->model);
@@ -1113,7 +1150,7 @@ int ilqg_fd_batch_host(ilqg_handle h, int nknots, const double* qpos, const doub
         for (int i = 0; i < 2 * ILQG_HOST_MAXCHUNKS; i++) CU(h, cudaEventCreateWithFlags(&h->pipe_ev[i], cudaEventDisableTiming));
     }
     cudaStream_t up = h->pipe[0], down = h->pipe[2];
-    const int ncomp = h->host_comp_streams;
+    const int ncomp = h->eng->fd_calls_may_overlap() ? h->host_comp_streams : 1;
     const ilqg_cost* dcost = nullptr;
     if (cost) {
         CU(h, cudaMemcpyAsync(h->d_cost, cost, sizeof(ilqg_cost), cudaMemcpyHostToDevice, up));
@@ -1176,7 +1213,7 @@ int ilqg_step_batch_dev(ilqg_handle h, int n, int nsteps, double* qpos, double* 
 static int state_host_call(ilqg_handle h, int n, int nsteps, bool stepping, double* qpos, double* qvel, const double* ctrl, double* warmstart,
                            double* qacc) {
     if (!h) return ILQG_ERR_ARG;
-    if (n < 0 || (n > 0 && (!qpos || !qvel))) return fail(h, ILQG_ERR_ARG, "null buffer");
+    if (n < 0 || (n > 0 && (!qpos || !qvel || (h->model.nu > 0 && !ctrl)))) return fail(h, ILQG_ERR_ARG, "null buffer");
     if (n == 0) return ILQG_OK;
     CU(h, cudaSetDevice(h->device));
     const int nq = h->model.nq, nv = h->model.nv, nu = h->model.nu;
@@ -1312,10 +1349,14 @@ int ilqg_ilqr_set_mu_schedule(ilqg_ilqr w, double factor, double mu_min, double 
     if (!w || !(mu_min > 0) || !(mu_max >= mu_min)) return ILQG_ERR_ARG;
     ilqg_handle h = w->h;
     CU(h, cudaSetDevice(h->device));
-    if (factor > 1.0 && !w->b.mu_i) {
-        ILQR_ALLOC(w, w->b.mu_i, w->b.ninst);
+    if (factor > 1.0 && !w->b.mu_i) {   // (a failed allocation leaves the workspace as it was: the caller still owns it)
+        double* p = nullptr;
+        CU(h, cudaMalloc(&p, sizeof(double) * (size_t)w->b.ninst));
+        w->allocs.push_back(p);
         std::vector<double> v((size_t)w->b.ninst, w->b.mu);
-        CU(h, cudaMemcpy(w->b.mu_i, v.data(), sizeof(double) * v.size(), cudaMemcpyHostToDevice));
+        cudaError_t ce = cudaMemcpy(p, v.data(), sizeof(double) * v.size(), cudaMemcpyHostToDevice);
+        if (ce != cudaSuccess) return cuda_fail(h, ce, "cudaMemcpy");
+        w->b.mu_i = p;
     }
     w->b.mu_factor = factor; w->b.mu_min = mu_min; w->b.mu_max = mu_max;
     return ILQG_OK;

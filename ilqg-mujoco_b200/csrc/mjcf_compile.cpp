@@ -724,14 +724,73 @@ extern "C" int ilqg_model_save(const char* path, const ilqg_model* m) {
     return n == 1 ? ILQG_OK : ILQG_ERR_IO;
 }
 
+// Structural check of a table that did not come out of the compiler in this process (a file, a buffer handed over the ABI):
+// counts within the fixed capacities, every index inside its range, tree order (parents before children), address
+// consistency, and only the joint / geom / integrator kinds the kernels implement.  The kernels index with these values.
+extern "C" int ilqg_model_validate(const ilqg_model* m, char* err, int errlen) {
+    auto bad = [&](int code, const char* what, int idx) {
+        if (err && errlen > 0) snprintf(err, errlen, "invalid model table: %s (index %d)", what, idx);
+        return code;
+    };
+    if (!m) return bad(ILQG_ERR_ARG, "null table", 0);
+    if (m->magic != ILQG_MODEL_MAGIC || m->version != ILQG_MODEL_VERSION) return bad(ILQG_ERR_MODEL, "bad magic / version", 0);
+    if (m->nq < 1 || m->nq > ILQG_MAXQ || m->nv < 1 || m->nv > ILQG_MAXV || m->nu < 0 || m->nu > ILQG_MAXU || m->nbody < 2 ||
+        m->nbody > ILQG_MAXBODY || m->njnt < 1 || m->njnt > ILQG_MAXJNT || m->ngeom < 0 || m->ngeom > ILQG_MAXGEOM || m->npair < 0 ||
+        m->npair > ILQG_MAXPAIR)
+        return bad(ILQG_ERR_MODEL, "a count is outside the table capacities", 0);
+    if (!(m->timestep > 0) || m->iterations < 0 || m->ls_iterations < 0 || !(m->meaninertia > 0)) return bad(ILQG_ERR_MODEL, "option block", 0);
+    if (m->integrator != ILQG_INT_EULER && m->integrator != ILQG_INT_RK4) return bad(ILQG_ERR_UNSUPPORTED, "integrator", m->integrator);
+    int nq = 0, nv = 0;
+    for (int j = 0; j < m->njnt; j++) {
+        const int ty = m->jnt_type[j], b = m->jnt_bodyid[j];
+        if (ty == ILQG_JNT_BALL) return bad(ILQG_ERR_UNSUPPORTED, "ball joint (not implemented by the kernels)", j);
+        if (ty != ILQG_JNT_FREE && ty != ILQG_JNT_SLIDE && ty != ILQG_JNT_HINGE) return bad(ILQG_ERR_MODEL, "joint type", j);
+        if (b < 1 || b >= m->nbody) return bad(ILQG_ERR_MODEL, "jnt_bodyid", j);
+        if (m->jnt_qposadr[j] != nq || m->jnt_dofadr[j] != nv) return bad(ILQG_ERR_MODEL, "jnt_qposadr / jnt_dofadr not cumulative", j);
+        nq += ty == ILQG_JNT_FREE ? 7 : 1;
+        nv += ty == ILQG_JNT_FREE ? 6 : 1;
+    }
+    if (nq != m->nq || nv != m->nv) return bad(ILQG_ERR_MODEL, "nq / nv do not match the joints", 0);
+    if (m->body_parentid[0] != 0) return bad(ILQG_ERR_MODEL, "body 0 must be the world", 0);
+    for (int b = 1; b < m->nbody; b++) {
+        if (m->body_parentid[b] < 0 || m->body_parentid[b] >= b) return bad(ILQG_ERR_MODEL, "body_parentid (parents precede children)", b);
+        if (m->body_rootid[b] < 1 || m->body_rootid[b] > b) return bad(ILQG_ERR_MODEL, "body_rootid", b);
+        if (m->body_jntnum[b] < 0 || m->body_dofnum[b] < 0) return bad(ILQG_ERR_MODEL, "body_jntnum / body_dofnum", b);
+        if (m->body_jntnum[b] > 0 && (m->body_jntadr[b] < 0 || m->body_jntadr[b] + m->body_jntnum[b] > m->njnt)) return bad(ILQG_ERR_MODEL, "body_jntadr", b);
+        if (m->body_dofnum[b] > 0 && (m->body_dofadr[b] < 0 || m->body_dofadr[b] + m->body_dofnum[b] > m->nv)) return bad(ILQG_ERR_MODEL, "body_dofadr", b);
+        if (!(m->body_mass[b] >= 0)) return bad(ILQG_ERR_MODEL, "body_mass", b);
+    }
+    for (int i = 0; i < m->nv; i++) {
+        if (m->dof_bodyid[i] < 1 || m->dof_bodyid[i] >= m->nbody) return bad(ILQG_ERR_MODEL, "dof_bodyid", i);
+        if (m->dof_jntid[i] < 0 || m->dof_jntid[i] >= m->njnt) return bad(ILQG_ERR_MODEL, "dof_jntid", i);
+        if (m->dof_parentid[i] < -1 || m->dof_parentid[i] >= i) return bad(ILQG_ERR_MODEL, "dof_parentid", i);
+    }
+    for (int g = 0; g < m->ngeom; g++) {
+        const int ty = m->geom_type[g];
+        if (ty != ILQG_GEOM_PLANE && ty != ILQG_GEOM_SPHERE && ty != ILQG_GEOM_CAPSULE) return bad(ILQG_ERR_UNSUPPORTED, "geom type", g);
+        if (m->geom_bodyid[g] < 0 || m->geom_bodyid[g] >= m->nbody) return bad(ILQG_ERR_MODEL, "geom_bodyid", g);
+    }
+    for (int p = 0; p < m->npair; p++) {
+        if (m->pair_geom1[p] < 0 || m->pair_geom1[p] >= m->ngeom || m->pair_geom2[p] < 0 || m->pair_geom2[p] >= m->ngeom)
+            return bad(ILQG_ERR_MODEL, "pair_geom", p);
+        if (m->pair_condim[p] != 1 && m->pair_condim[p] != 3) return bad(ILQG_ERR_UNSUPPORTED, "pair_condim (1 and 3 are implemented)", p);
+        if (m->geom_type[m->pair_geom2[p]] == ILQG_GEOM_PLANE) return bad(ILQG_ERR_MODEL, "a plane must be geom1 of its pair", p);
+    }
+    for (int a = 0; a < m->nu; a++)
+        if (m->act_dofid[a] < 0 || m->act_dofid[a] >= m->nv) return bad(ILQG_ERR_MODEL, "act_dofid", a);
+    if (err && errlen > 0) err[0] = 0;
+    return ILQG_OK;
+}
+
 extern "C" int ilqg_model_load(const char* path, ilqg_model* m) {
+    if (!path || !m) return ILQG_ERR_ARG;
     FILE* f = fopen(path, "rb");
     if (!f) return ILQG_ERR_IO;
     size_t n = fread(m, sizeof(*m), 1, f);
+    const bool more = n == 1 && fgetc(f) != EOF;   // a file of another size is not one of our tables
     fclose(f);
-    if (n != 1) return ILQG_ERR_IO;
-    if (m->magic != ILQG_MODEL_MAGIC || m->version != ILQG_MODEL_VERSION) return ILQG_ERR_MODEL;
-    return ILQG_OK;
+    if (n != 1 || more) return ILQG_ERR_IO;
+    return ilqg_model_validate(m, nullptr, 0);
 }
 
 extern "C" int ilqg_model_sizeof(void) { return (int)sizeof(ilqg_model); }

@@ -1,5 +1,6 @@
 // host_api.cpp — host-language side of the drop-in: the MuJoCo-shaped entry points and the reference's free functions
 // (calcMJDerivatives, cpMjData, forwardStep/forwardFrame, InvertedPendulum) implemented on the B200 C ABI.
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -16,9 +17,35 @@ static const double kEps = 1e-6;  // /root/reference/src/mjderivative.cpp:39
 
 extern "C" {
 
+// MuJoCo's error / warning hooks: a user handler (mju_user_error / mju_user_warning) replaces the default print-and-exit /
+// print.  A handler that returns hands control back to the wrapper, which leaves without computing.
+void (*mju_user_error)(const char*) = NULL;
+void (*mju_user_warning)(const char*) = NULL;
 void mju_error(const char* msg) {
+    if (mju_user_error) { mju_user_error(msg); return; }
     fprintf(stderr, "ilqg-b200 ERROR: %s\n", msg);
     exit(1);
+}
+void mju_warning(const char* msg) {
+    if (mju_user_warning) { mju_user_warning(msg); return; }
+    fprintf(stderr, "ilqg-b200 WARNING: %s\n", msg);
+}
+// q <- normalize(q) * quat(axis = vel / |vel|, angle = scale |vel|): MuJoCo's mju_quatIntegrate, the tangent-space perturbation
+// of /root/reference/src/mjderivative.cpp:168,191 (same operation order as the kernels' quat_integrate, csrc/dyn.cuh)
+void mju_quatIntegrate(mjtNum* quat, const mjtNum* vel, mjtNum scale) {
+    mjtNum n = sqrt(vel[0] * vel[0] + vel[1] * vel[1] + vel[2] * vel[2]);
+    mjtNum ax[3] = {1, 0, 0};
+    if (n < 1e-15) n = 0;
+    else { ax[0] = vel[0] / n; ax[1] = vel[1] / n; ax[2] = vel[2] / n; }
+    const mjtNum s = sin(0.5 * scale * n), c = cos(0.5 * scale * n);
+    mjtNum qn = sqrt(quat[0] * quat[0] + quat[1] * quat[1] + quat[2] * quat[2] + quat[3] * quat[3]);
+    mjtNum q[4] = {1, 0, 0, 0};
+    if (qn >= 1e-15) for (int i = 0; i < 4; i++) q[i] = quat[i] / qn;
+    const mjtNum r[4] = {c, ax[0] * s, ax[1] * s, ax[2] * s};
+    quat[0] = q[0] * r[0] - q[1] * r[1] - q[2] * r[2] - q[3] * r[3];
+    quat[1] = q[0] * r[1] + q[1] * r[0] + q[2] * r[3] - q[3] * r[2];
+    quat[2] = q[0] * r[2] - q[1] * r[3] + q[2] * r[0] + q[3] * r[1];
+    quat[3] = q[0] * r[3] + q[1] * r[2] - q[2] * r[1] + q[3] * r[0];
 }
 void mju_copy(mjtNum* res, const mjtNum* data, int n) { memcpy(res, data, sizeof(mjtNum) * n); }
 void* mju_malloc(size_t size) { return malloc(size); }
@@ -79,18 +106,37 @@ void mj_resetData(const mjModel* m, mjData* d) {
     memcpy(d->qpos, m->tab.qpos0, sizeof(mjtNum) * m->nq);
     d->time = 0;
 }
-static void gpu_check(const mjModel* m, int rc, const char* what) {
+static bool gpu_check(const mjModel* m, int rc, const char* what) {
     if (rc) {
         char buf[512];
         snprintf(buf, sizeof buf, "%s failed (%d): %s", what, rc, ilqg_last_error(m->gpu));
         mju_error(buf);
+        return false;
     }
+    return true;
+}
+// A knot is what cpMjData copies (/root/reference/src/util.cpp:4-13), and that includes qfrc_applied / xfrc_applied, which
+// MuJoCo adds to qfrc_smooth.  The GPU pipeline does not take them (the reference never sets them): a state that carries a
+// non-zero applied force is refused here instead of being linearised without it.
+int ilqg_host_check_applied(const mjModel* m, const mjData* d) {
+    for (int i = 0; i < m->nv; i++) if (d->qfrc_applied[i] != 0) return ILQG_ERR_UNSUPPORTED;
+    for (int i = 0; i < 6 * m->nbody; i++) if (d->xfrc_applied[i] != 0) return ILQG_ERR_UNSUPPORTED;
+    return ILQG_OK;
+}
+static bool applied_ok(const mjModel* m, const mjData* d, const char* what) {
+    if (ilqg_host_check_applied(m, d) == ILQG_OK) return true;
+    char buf[256];
+    snprintf(buf, sizeof buf, "%s: non-zero qfrc_applied / xfrc_applied are not supported by the GPU pipeline (%d)", what, ILQG_ERR_UNSUPPORTED);
+    mju_error(buf);
+    return false;
 }
 void mj_step(const mjModel* m, mjData* d) {
-    gpu_check(m, ilqg_step_batch_host(m->gpu, 1, 1, d->qpos, d->qvel, d->ctrl, d->qacc_warmstart, d->qacc), "mj_step");
+    if (!applied_ok(m, d, "mj_step")) return;
+    if (!gpu_check(m, ilqg_step_batch_host(m->gpu, 1, 1, d->qpos, d->qvel, d->ctrl, d->qacc_warmstart, d->qacc), "mj_step")) return;
     d->time += m->opt.timestep;
 }
 void mj_forward(const mjModel* m, mjData* d) {
+    if (!applied_ok(m, d, "mj_forward")) return;
     gpu_check(m, ilqg_forward_batch_host(m->gpu, 1, d->qpos, d->qvel, d->ctrl, d->qacc_warmstart, d->qacc), "mj_forward");
 }
 
@@ -134,11 +180,18 @@ void calcCostGradientRows(const mjModel* m, const mjData* dmain, stepCostFn_t st
     }
     for (int i = 0; i < nv; i++) {
         const int jid = m->dof_jntid[i];
-        if (m->jnt_type[jid] == mjJNT_FREE && i >= m->jnt_dofadr[jid] + 3) { rows[i] = 0; continue; }  // quaternion dofs: GPU-side cost only
-        const int adr = m->jnt_qposadr[jid] + i - m->jnt_dofadr[jid];
-        d->qpos[adr] += kEps;
-        rows[i] = (stepCostFn(d) - costCenter) / kEps;
-        d->qpos[adr] = dmain->qpos[adr];
+        // quaternion address and position of the dof inside it (-1: a scalar joint), /root/reference/src/mjderivative.cpp:150-160
+        int quatadr = -1, dofpos = 0;
+        if (m->jnt_type[jid] == mjJNT_BALL) { quatadr = m->jnt_qposadr[jid]; dofpos = i - m->jnt_dofadr[jid]; }
+        else if (m->jnt_type[jid] == mjJNT_FREE && i >= m->jnt_dofadr[jid] + 3) { quatadr = m->jnt_qposadr[jid] + 3; dofpos = i - m->jnt_dofadr[jid] - 3; }
+        if (quatadr >= 0) {   // tangent-space perturbation (:163-168)
+            mjtNum angvel[3] = {0, 0, 0};
+            angvel[dofpos] = kEps;
+            mju_quatIntegrate(d->qpos + quatadr, angvel, 1);
+        } else
+            d->qpos[m->jnt_qposadr[jid] + i - m->jnt_dofadr[jid]] += kEps;
+        rows[i] = (stepCostFn(d) - costCenter) / kEps;   // (:174)
+        mju_copy(d->qpos, dmain->qpos, m->nq);            // undo (:184)
     }
     mj_deleteData(d);
 }
@@ -152,8 +205,26 @@ void calcMJDerivativesBatch(mjModel* m, mjData* const* dknots, int nknots, mjtNu
         mju_copy(u.data() + (size_t)k * nu, dknots[k]->ctrl, nu);
         mju_copy(w.data() + (size_t)k * nv, dknots[k]->qacc_warmstart, nv);
     }
-    int rc = ilqg_fd_batch_host(m->gpu, nknots, q.data(), v.data(), u.data(), w.data(), NULL, NULL, deriv, NULL, NULL);
-    if (rc && rc != ILQG_ERR_NONFINITE) gpu_check(m, rc, "calcMJDerivatives");
+    for (int k = 0; k < nknots; k++)
+        if (!applied_ok(m, dknots[k], "calcMJDerivatives")) return;
+    std::vector<int> status((size_t)nknots, 0);
+    int rc = ilqg_fd_batch_host(m->gpu, nknots, q.data(), v.data(), u.data(), w.data(), NULL, NULL, deriv, NULL, status.data());
+    if (rc && rc != ILQG_ERR_NONFINITE && !gpu_check(m, rc, "calcMJDerivatives")) return;
+    // per-knot flags: a knot that overflowed the kernels' row / contact capacity has no valid block (an error, as MuJoCo's
+    // "nconmax / njmax too small"); a non-finite one is MuJoCo's "Nan, Inf or huge value in QACC" warning
+    for (int k = 0; k < nknots; k++) {
+        if (status[k] == ILQG_ERR_CAPACITY) {
+            char buf[160];
+            snprintf(buf, sizeof buf, "calcMJDerivatives: knot %d exceeds the constraint-row / contact capacity of the GPU kernels (%d)", k, status[k]);
+            mju_error(buf);
+            return;
+        }
+        if (status[k] == ILQG_ERR_NONFINITE) {
+            char buf[160];
+            snprintf(buf, sizeof buf, "calcMJDerivatives: Nan, Inf or huge value in the derivatives of knot %d", k);
+            mju_warning(buf);
+        }
+    }
     if (stepCostFn)
         for (int k = 0; k < nknots; k++) calcCostGradientRows(m, dknots[k], stepCostFn, deriv + (size_t)k * nd + (nd - nr));
 }
@@ -315,4 +386,56 @@ extern "C" int ilqg_host_hopper_differentiator(const char* model_path, int nstep
     mj_deleteData(dStar);
     mj_deleteModel(m);
     return 0;
+}
+
+// ---- probes for the parity holes of the drop-in (tests/test_host_dropin_gpu.py)
+// a host cost that depends on the root orientation (an uprightness term: 1 - z-axis of the torso dotted with the world z-axis)
+static mjtNum uprightCost(const mjData* d) {
+    const mjtNum* q = d->qpos + 3;
+    return (1.0 - (1.0 - 2.0 * (q[1] * q[1] + q[2] * q[2]))) + 0.5 * d->qpos[2] * d->qpos[2] + 0.1 * d->qvel[4] + 0.01 * d->ctrl[2] * d->ctrl[2];
+}
+// calcMJDerivatives on a free-joint model with that cost: deriv out (ND doubles)
+extern "C" int ilqg_host_freejoint_cost_rows(const char* model_path, const double* qpos, const double* qvel, const double* ctrl, double* deriv) {
+    char err[512] = "";
+    mjModel* m = mj_loadXML(model_path, NULL, err, sizeof err);
+    if (!m) { fprintf(stderr, "%s\n", err); return 1; }
+    mjData* d = mj_makeData(m);
+    mju_copy(d->qpos, qpos, m->nq);
+    mju_copy(d->qvel, qvel, m->nv);
+    mju_copy(d->ctrl, ctrl, m->nu);
+    calcMJDerivatives(m, d, deriv, uprightCost);
+    mj_deleteData(d);
+    mj_deleteModel(m);
+    return 0;
+}
+
+static int g_probe_errors = 0;
+static char g_probe_msg[256];
+static void probeHandler(const char* msg) { g_probe_errors++; snprintf(g_probe_msg, sizeof g_probe_msg, "%s", msg); }
+// a state with applied forces must be refused by every wrapper (and left untouched); returns the number of refusals, -1 on a
+// setup failure; msg receives the last error text
+extern "C" int ilqg_host_applied_force_probe(const char* model_path, int use_xfrc, char* msg, int msglen) {
+    char err[512] = "";
+    mjModel* m = mj_loadXML(model_path, NULL, err, sizeof err);
+    if (!m) { fprintf(stderr, "%s\n", err); return -1; }
+    mjData* d = mj_makeData(m);
+    if (ilqg_host_check_applied(m, d) != ILQG_OK) return -1;
+    if (use_xfrc) d->xfrc_applied[6 * (m->nbody - 1) + 2] = 3.0; else d->qfrc_applied[m->nv - 1] = -0.5;
+    if (ilqg_host_check_applied(m, d) != ILQG_ERR_UNSUPPORTED) return -1;
+    std::vector<mjtNum> deriv(ilqg_deriv_size(&m->tab), 123.0), q0(d->qpos, d->qpos + m->nq);
+    g_probe_errors = 0;
+    void (*old)(const char*) = mju_user_error;
+    mju_user_error = probeHandler;
+    calcMJDerivatives(m, d, deriv.data(), NULL);
+    mj_step(m, d);
+    mj_forward(m, d);
+    mju_user_error = old;
+    int n = g_probe_errors;
+    for (size_t i = 0; i < deriv.size(); i++) if (deriv[i] != 123.0) n = -2;   // nothing may have been computed
+    for (int i = 0; i < m->nq; i++) if (d->qpos[i] != q0[i]) n = -3;
+    if (d->time != 0) n = -4;
+    if (msg && msglen > 0) snprintf(msg, msglen, "%s", g_probe_msg);
+    mj_deleteData(d);
+    mj_deleteModel(m);
+    return n;
 }

@@ -59,7 +59,14 @@ int mj_activate(const char* filename);         // licence call of MuJoCo 2.0 (cm
 void mju_copy(mjtNum* res, const mjtNum* data, int n);
 void* mju_malloc(size_t size);
 void mju_free(void* p);
-void mju_error(const char* msg);               // prints and aborts, as MuJoCo's default handler does
+void mju_error(const char* msg);               // prints and aborts, as MuJoCo's default handler does — unless mju_user_error is set
+void mju_warning(const char* msg);
+extern void (*mju_user_error)(const char*);    // MuJoCo's handler hooks
+extern void (*mju_user_warning)(const char*);
+void mju_quatIntegrate(mjtNum* quat, const mjtNum* vel, mjtNum scale);   // /root/reference/src/mjderivative.cpp:168,191
+// ILQG_OK when the state carries no applied forces, else ILQG_ERR_UNSUPPORTED (qfrc_applied / xfrc_applied are part of the
+// knot, /root/reference/src/util.cpp:10-11, but not of the GPU pipeline: mj_step / mj_forward / calcMJDerivatives refuse them)
+int ilqg_host_check_applied(const struct mjModel_* m, const struct mjData_* d);
 #ifdef __cplusplus
 }
 #endif

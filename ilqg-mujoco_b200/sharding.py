@@ -58,13 +58,20 @@ class _DevArray:
 class PeerDeriv:
     """One deriv[T, nd] array per rank, each mapped into every other rank of the node with CUDA IPC, so that the FD kernels
     of a knot-sharded horizon store their blocks straight into all copies (ilqg_fd_batch_dev_scatter): the all-gather of
-    SURVEY 8(e) rides in the kernels' write-out over NVLink instead of following them as a separate collective."""
+    SURVEY 8(e) rides in the kernels' write-out over NVLink instead of following them as a separate collective.
+
+    The array is DOUBLE-BUFFERED by pass parity: the flag barrier that closes pass k only proves that every rank's stores of
+    pass k have landed; a faster rank may already be storing pass k+1 while a slower one still reads pass k, so pass k+1 goes
+    to the other buffer.  Buffer k & 1 is stored to again in pass k+2, which no rank can start before every rank has reached
+    the barrier of pass k+1 — and a rank issues that barrier after its own readers of pass k PROVIDED THEY RUN ON THE SAME
+    STREAM as the FD calls (or are otherwise ordered before the next `fd_knot_sharded_peer` call).  That is the contract."""
 
     def __init__(self, handle, T, nd, group=None):
         self.h, self.T, self.nd, self.group = handle, int(T), int(nd), group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.flag_off = self.T * self.nd * 8           # the barrier's flag array sits behind the blocks (zero-initialised)
+        self.buf_bytes = self.T * self.nd * 8
+        self.flag_off = 2 * self.buf_bytes             # the barrier's flag array sits behind the two buffers (zero-initialised)
         self.epoch = 0
         self.own, hd = handle.peer_alloc(self.flag_off + 256)
         handles = [hd]
@@ -73,14 +80,21 @@ class PeerDeriv:
             dist.all_gather_object(handles, hd, group=group)
         self.ptrs = [self.own if r == self.rank else handle.peer_open(handles[r]) for r in range(self.world)]
         if hasattr(handle, "peer_view"):   # host-memory stand-in used by the CPU (gloo) tests of this logic
-            self.full = handle.peer_view(self.own, (self.T, self.nd))
+            both = handle.peer_view(self.own, (2, self.T, self.nd))
         else:
-            self.full = torch.as_tensor(_DevArray(self.own, (self.T, self.nd)), device=f"cuda:{torch.cuda.current_device()}")
+            both = torch.as_tensor(_DevArray(self.own, (2, self.T, self.nd)), device=f"cuda:{torch.cuda.current_device()}")
+        self.bufs = [both[0], both[1]]
+        self.full = self.bufs[0]
 
-    def scatter_ptrs(self, first_knot):
-        """Destination addresses of knot `first_knot` in every rank's copy, this rank's first."""
+    def scatter_ptrs(self, first_knot, parity=0):
+        """Destination addresses of knot `first_knot` in buffer `parity` of every rank's copy, this rank's first."""
         order = [self.rank] + [r for r in range(self.world) if r != self.rank]
-        return [self.ptrs[r] + first_knot * self.nd * 8 for r in order]
+        return [self.ptrs[r] + parity * self.buf_bytes + first_knot * self.nd * 8 for r in order]
+
+    def check(self):
+        """Synchronises; raises if a barrier gave up waiting for a peer (the arrays then hold a partial pass)."""
+        if self.h.peer_barrier_timed_out():
+            raise RuntimeError("ilqg peer barrier timed out: a rank of the node did not finish its FD pass; the gathered deriv array is incomplete")
 
     def barrier(self, stream=None):
         """Every rank's preceding kernels (and their peer stores) are complete and visible once this returns on the stream."""
@@ -95,18 +109,25 @@ class PeerDeriv:
             if r != self.rank:
                 self.h.peer_close(p)
         self.full = None
+        self.bufs = None
         self.h.peer_free(self.own)
 
 
 def fd_knot_sharded_peer(handle, peer, qpos, qvel, ctrl, warm, cost=None, stream=None):
     """FD linearisation of one long trajectory, knots sharded over the ranks, blocks stored by the kernels into every
-    rank's `peer.full`.  Returns peer.full (all T blocks, knot order) once every rank's kernels have finished."""
+    rank's copy of the pass's buffer.  Returns that buffer (all T blocks, knot order; also `peer.full`), valid on `stream`
+    once every rank's kernels have finished.  Consecutive passes alternate between two buffers; readers of the returned array
+    must be ordered on `stream` before the next call (see PeerDeriv)."""
     T = qpos.shape[0]
     lo, hi = shard_range(T, peer.world, peer.rank)
+    parity = peer.epoch & 1
     if hi > lo:
-        handle.fd_batch_dev_scatter(qpos[lo:hi], qvel[lo:hi], ctrl[lo:hi], warm[lo:hi], peer.scatter_ptrs(lo), cost=cost, stream=stream)
+        handle.fd_batch_dev_scatter(qpos[lo:hi], qvel[lo:hi], ctrl[lo:hi], warm[lo:hi], peer.scatter_ptrs(lo, parity), cost=cost, stream=stream)
+    peer.full = peer.bufs[parity]
     if peer.world > 1:
         peer.barrier(stream=stream)   # a 1-warp kernel per rank exchanging flags through peer memory: no NCCL call on this path
+    else:
+        peer.epoch += 1
     return peer.full
 
 

@@ -13,6 +13,11 @@
  * There is no CPU implementation behind these calls: without a CUDA device they fail with
  * ILQG_ERR_CUDA.
  *
+ * Concurrency: a handle (and the iLQR workspaces created on it) owns device scratch — the cost block, the centre
+ * accelerations, the work-class permutation, the profiling events — that every call reuses.  Calls on ONE handle must
+ * therefore be issued on one stream at a time (stream-ordered, like the reference's single-threaded caller,
+ * /root/reference/cmd/basic.cpp:158-164); create one handle per stream (or per thread) to overlap calls.
+ *
  * Layouts are the reference's:
  *   deriv (per knot, ND = nv*(2nv+nu) + 2nv + nu doubles, /root/reference/inc/differentiator.h:56-61):
  *     [0, nv^2)                 d qacc_j / d qpos_i   at i + j*nv   (/root/reference/src/mjderivative.cpp:202)
@@ -53,6 +58,9 @@ int ilqg_compile_mjcf_string(const char* xml, ilqg_model* out, char* err, int er
 int ilqg_model_save(const char* path, const ilqg_model* m);
 int ilqg_model_load(const char* path, ilqg_model* m);
 int ilqg_model_sizeof(void);
+/* structural check of a table (counts, index ranges, tree order, supported joint / geom kinds); ilqg_create and
+ * ilqg_model_load run it and refuse the table with ILQG_ERR_MODEL / ILQG_ERR_UNSUPPORTED.  err may be NULL. */
+int ilqg_model_validate(const ilqg_model* m, char* err, int errlen);
 /* byte offset / element count / type of a named ilqg_model field (bindings that hold the table as bytes) */
 int ilqg_model_field(const char* name, int* offset, int* count, int* is_double);
 
@@ -100,6 +108,22 @@ int ilqg_fd_batch_dev(ilqg_handle h, int nknots, const double* qpos, const doubl
 int ilqg_fd_batch_host(ilqg_handle h, int nknots, const double* qpos, const double* qvel, const double* ctrl,
                        const double* warmstart, const ilqg_cost* cost, const ilqg_fd_opts* opts, double* deriv,
                        double* qacc_out, int* status);
+
+/* ---- optional per-knot diagnostics of the centre evaluation (mj_forward + warm-up solves, /root/reference/src/mjderivative.cpp:64-68).
+ * The reference pins the solver to `niter` iterations / tolerance 0 (:241-242); the kernels' solver leaves earlier when it has
+ * reached the exact minimiser of the convex piecewise-quadratic cost ("Solver") — these counters say how many Newton
+ * iterations actually ran.  diag_dev: DEVICE array [nknots][ILQG_DIAG_INTS] written by the following ilqg_fd_batch_dev /
+ * ilqg_fd_batch_dev_scatter calls on the handle (NULL switches it off; the *_host call does not write it). */
+#define ILQG_DIAG_INTS 8
+enum {
+    ILQG_DIAG_NEFC = 0,        /* constraint rows at the centre point */
+    ILQG_DIAG_ITERS_FIRST = 1, /* Newton iterations of the first centre solve (from the caller's warm start) */
+    ILQG_DIAG_ITERS_ALL = 2,   /* Newton iterations of all nwarmup centre solves */
+    ILQG_DIAG_NACTIVE = 3,     /* rows active (force > 0) at the centre solution */
+    ILQG_DIAG_CYC_BUILD = 4,   /* SM cycles the rollout spent in the position / velocity / actuation stages */
+    ILQG_DIAG_CYC_SOLVE = 5    /* SM cycles it spent in the nwarmup solves */
+};
+int ilqg_fd_set_diag(ilqg_handle h, int* diag_dev);
 
 /* ---- multi-GPU: the knots of ONE long horizon sharded over the GPUs of a node (BASELINE configs[4]).
  * The reference computes the knots' derivatives one after the other inside ILQR::backwardPass

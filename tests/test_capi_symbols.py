@@ -55,3 +55,31 @@ def test_null_arguments_are_rejected(pkg):
     assert L.ilqg_deriv_size(pkg.Model.named("hopper").ptr) == 105
     assert L.ilqg_deriv_size(pkg.Model.named("inverted_pendulum").ptr) == 15
     assert L.ilqg_deriv_size(pkg.Model.named("humanoid").ptr) == 2100
+
+
+def test_model_tables_are_validated(pkg, tmp_path):
+    """A table that did not come out of the compiler (a file, a buffer over the ABI) is checked before the kernels index with it."""
+    L = pkg.lib()
+    err = C.create_string_buffer(256)
+    for name in ("inverted_pendulum", "hopper", "humanoid"):
+        assert L.ilqg_model_validate(pkg.Model.named(name).ptr, err, 256) == pkg.OK, err.value
+    # out-of-range indices and counts
+    for field, idx, val, code in (("body_parentid", 2, 9, pkg.ERR_MODEL), ("dof_parentid", 1, 5, pkg.ERR_MODEL), ("pair_geom2", 0, 23, pkg.ERR_MODEL),
+                                  ("act_dofid", 0, 31, pkg.ERR_MODEL), ("jnt_type", 3, 1, pkg.ERR_UNSUPPORTED),   # a ball joint: declared, not implemented
+                                  ("geom_type", 1, 5, pkg.ERR_UNSUPPORTED), ("npair", 0, 4000, pkg.ERR_MODEL)):
+        bad = pkg.Model.named("hopper").copy()
+        bad.field(field)[idx] = val
+        rc = L.ilqg_model_validate(bad.ptr, err, 256)
+        assert rc == code, (field, rc, err.value)
+        assert field.split("_")[0].encode() in err.value or b"count" in err.value or b"joint" in err.value or b"geom" in err.value
+        h = C.c_void_p()
+        assert L.ilqg_create(bad.ptr, 0, C.byref(h)) == code    # refused before any CUDA call
+        with pytest.raises(pkg.IlqgError):
+            bad.validate()
+    # a file of the wrong size is not a table
+    short = tmp_path / "short.ilqgm"
+    short.write_bytes(pkg.Model.named("hopper").buf.tobytes()[:-8])
+    buf = np.zeros(L.ilqg_model_sizeof(), np.uint8)
+    assert L.ilqg_model_load(str(short).encode(), buf.ctypes.data_as(C.c_void_p)) == pkg.ERR_IO
+    with pytest.raises(ValueError):
+        pkg.Model(np.zeros(100, np.uint8))

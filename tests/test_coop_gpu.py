@@ -100,3 +100,27 @@ def test_generic_engine_is_idempotent_and_chunk_invariant(generic_handles, handl
     assert torch.equal(part, a[lo:hi])
     ht.fd_batch_dev(q, v, u, w, c, cost=cost)
     assert_deriv_close(a.cpu().numpy(), c.cpu().numpy(), 6, 3)
+
+
+def test_humanoid_host_pipeline_chunks_do_not_share_scratch(pkg, oracle, omodels):
+    """ilqg_fd_batch_host pipelines chunks of knots over streams.  The warp-cooperative engine keeps the centre's C-state,
+    candidate lists and row bounds in engine-owned scratch indexed by the knot's position in its chunk, so its chunks must not
+    overlap on two compute streams (round-1 advisor finding): with 4 chunks the result must equal one device call bit for bit."""
+    import torch
+    os.environ["ILQG_HOST_CHUNKS"] = "4"
+    try:
+        h = pkg.Handle(pkg.Model.named("humanoid"), 0)
+    finally:
+        del os.environ["ILQG_HOST_CHUNKS"]
+    m = h.model
+    n = 96
+    q, v, u, w = scenario_states("humanoid", n, seed=41, oracle=oracle, om=omodels["humanoid"], roll=60)   # in ground contact
+    cost = pkg.make_cost(q1=[1.0])
+    for _ in range(3):   # a race would not necessarily show in one pass
+        d_host, a_host, status = h.fd_batch_host(q, v, u, w, cost)
+        assert status.sum() == 0
+        dq, dv, du, dw = (torch.from_numpy(x).cuda() for x in (q, v, u, w))
+        d_dev = torch.zeros((n, m.nd), dtype=torch.float64, device="cuda")
+        h.fd_batch_dev(dq, dv, du, dw, d_dev, cost=cost)
+        assert np.array_equal(d_host, d_dev.cpu().numpy())
+    h.close()

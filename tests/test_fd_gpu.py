@@ -246,3 +246,37 @@ def test_out_of_plane_variant_of_a_planar_tree_leaves_the_planar_kernels(pkg, or
     h2 = pkg.Handle(pkg.Model.named("hopper"), 0)
     assert h2.engine == "hopper"
     h2.close()
+
+
+@pytest.mark.parametrize("name", ["hopper", "humanoid"])
+def test_centre_diagnostics_report_solver_iterations(pkg, handles, oracle, omodels, name):
+    """ilqg_fd_set_diag: rows and Newton iterations of the centre evaluation (the reference pins 30 iterations / tolerance 0,
+    mjderivative.cpp:241-242; the kernels' solver leaves at the exact minimiser — the caller can see how many ran)."""
+    import torch
+    h = handles[name] if name in handles else pkg.Handle(pkg.Model.named(name), 0)
+    m = h.model; om = omodels[name]
+    n = 64 if name == "hopper" else 12
+    q, v, u, w = scenario_states(name, n, seed=17, oracle=oracle, om=om, roll=150 if name == "hopper" else 60)
+    dq, dv, du, dw = (torch.from_numpy(x).cuda() for x in (q, v, u, w))
+    deriv = torch.zeros((n, m.nd), dtype=torch.float64, device="cuda")
+    diag = torch.full((n, 8), -1, dtype=torch.int32, device="cuda")
+    h.fd_set_diag(diag)
+    h.fd_batch_dev(dq, dv, du, dw, deriv)
+    h.fd_set_diag(None)
+    d = diag.cpu().numpy()
+    info = np.zeros(4, np.int32); qa = np.zeros(om.nv)
+    for k in range(n):
+        oracle.lib().mjo_debug_forward(om.ptr, oracle._p(q[k]), oracle._p(v[k]), oracle._p(u[k]), oracle._p(w[k]), 30, C.c_double(0.0), oracle._p(qa),
+                                       info.ctypes.data_as(C.c_void_p), None, None, None)
+        assert d[k, 0] == info[0]                      # nefc
+    assert (d[:, 0] > 0).any() and ((d[:, 1] >= 0) & (d[:, 1] <= 30)).all() and (d[:, 2] >= d[:, 1]).all()
+    assert (d[d[:, 0] == 0, 2] == 0).all()             # no rows: no iterations
+    assert (d[d[:, 0] > 0, 2] >= 1).all() and (d[:, 3] <= d[:, 0]).all()
+    assert (d[:, 4] > 0).all() and (d[:, 5] >= 0).all()
+    # switched off: the array is left alone
+    diag.fill_(-7)
+    h.fd_batch_dev(dq, dv, du, dw, deriv)
+    torch.cuda.synchronize()
+    assert int((diag != -7).sum()) == 0
+    if name not in handles:
+        h.close()

@@ -117,3 +117,59 @@ def test_hopper_task_mpc_matches_oracle(hostlib, oracle, omodels):
     # iterations of step 1 — before the first marginal decision — are compared, and the overall progress.
     assert np.allclose(Jt[1, :5], Jt_o[1, :5], rtol=1e-8, atol=1e-9)
     assert Jt[-1, -1] < Jt[0, 0] - 1.0 and Jt_o[-1, -1] < Jt_o[0, 0] - 1.0
+
+
+def test_host_cost_gradient_on_quaternion_dofs(hostlib, oracle, omodels):
+    """/root/reference/src/mjderivative.cpp:161-174: the cost row of a free joint's rotational dofs comes from a tangent-space
+    perturbation (mju_quatIntegrate) followed by the caller's stepCostFn — a host cost that depends on the root orientation
+    (uprightness) must see it.  Checked against the same forward difference done in numpy."""
+    om = omodels["humanoid"]
+    rng = np.random.default_rng(3)
+    q = np.zeros(28); q[2] = 1.3; q[3:7] = [0.9, 0.2, -0.3, 0.1]; q[3:7] /= np.linalg.norm(q[3:7]); q[7:] = rng.uniform(-0.1, 0.1, 21)
+    v = rng.normal(0, 0.2, 27); u = rng.uniform(-0.3, 0.3, 21)
+    deriv = np.zeros(2100)
+    path = os.path.join(PKG, "models", "humanoid.ilqgm").encode()
+    assert hostlib.ilqg_host_freejoint_cost_rows(path, oracle._p(q), oracle._p(v), oracle._p(u), oracle._p(deriv)) == 0
+
+    def cost(q, v, u):
+        return (1.0 - (1.0 - 2.0 * (q[4] ** 2 + q[5] ** 2))) + 0.5 * q[2] ** 2 + 0.1 * v[4] + 0.01 * u[2] ** 2
+
+    def qmul(a, b):
+        return np.array([a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3], a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2],
+                         a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1], a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0]])
+    eps, c0 = 1e-6, cost(q, v, u)
+    rows = np.zeros(27 + 27 + 21)
+    for i in range(27):
+        qp = q.copy()
+        if 3 <= i < 6:
+            ax = np.zeros(3); ax[i - 3] = 1.0
+            qp[3:7] = qmul(q[3:7] / np.linalg.norm(q[3:7]), np.concatenate([[np.cos(eps / 2)], ax * np.sin(eps / 2)]))
+        else:
+            qp[i if i < 3 else i + 1] += eps
+        rows[i] = (cost(qp, v, u) - c0) / eps
+    for i in range(27):
+        vp = v.copy(); vp[i] += eps
+        rows[27 + i] = (cost(q, vp, u) - c0) / eps
+    for i in range(21):
+        up = u.copy(); up[i] += eps
+        rows[54 + i] = (cost(q, v, up) - c0) / eps
+    got = deriv[-75:]
+    assert np.abs(got[3:6]).max() > 1e-2            # the orientation rows are not zero (they were, silently, in round 1)
+    assert np.allclose(got, rows, rtol=0, atol=2e-9)  # two evaluations of the same differences: round-off / eps
+    # and the dynamics blocks of the same call are the oracle's
+    d_ref, _, _ = oracle.fd_batch(om, q[None], v[None], u[None], np.zeros((1, 27)), None)
+    from test_fd_gpu import assert_deriv_close
+    both = np.concatenate([deriv[:-75], d_ref[0, -75:]])[None]
+    assert_deriv_close(both, d_ref, 27, 21, tol=1e-5)
+
+
+@pytest.mark.parametrize("use_xfrc", [0, 1])
+def test_applied_forces_are_refused_not_ignored(hostlib, use_xfrc):
+    """qfrc_applied / xfrc_applied are part of the knot (/root/reference/src/util.cpp:10-11) but not of the GPU pipeline:
+    calcMJDerivatives, mj_step and mj_forward refuse a state that carries them (ILQG_ERR_UNSUPPORTED through mju_error) and
+    compute nothing."""
+    msg = C.create_string_buffer(256)
+    path = os.path.join(PKG, "models", "hopper.ilqgm").encode()
+    n = hostlib.ilqg_host_applied_force_probe(path, use_xfrc, msg, 256)
+    assert n == 3, (n, msg.value)
+    assert b"applied" in msg.value and b"(5)" in msg.value

@@ -58,11 +58,24 @@ def _rank(rank, world, port, T, out):
     h = pkg.Handle(pkg.Model.named("hopper"), rank)
     peer = sharding.PeerDeriv(h, T, h.model.nd)
     cost = pkg.make_cost(q1=[1.0])
-    full = sharding.fd_knot_sharded_peer(h, peer, dq, dv, du, dw, cost=cost)
-    for _ in range(5):   # repeated passes exercise the barrier's epochs
-        full = sharding.fd_knot_sharded_peer(h, peer, dq, dv, du, dw, cost=cost)
+    # repeated passes exercise the barrier's epochs and the two buffers; the inputs differ from pass to pass (the controls are
+    # scaled) and rank 1 reads each pass's array late (a long kernel ahead of the copy), while rank 0 is already storing the
+    # next pass — into the other buffer
+    spin = torch.zeros(1 << 24, dtype=torch.float64, device=dev)
+    snaps = []
+    for p in range(6):
+        full = sharding.fd_knot_sharded_peer(h, peer, dq, dv, du * (1.0 - 0.1 * (5 - p)), dw, cost=cost)
+        assert full.data_ptr() == peer.bufs[p & 1].data_ptr()
+        if rank == 1:
+            for _ in range(20):
+                spin.add_(1.0)
+        snaps.append(full.clone())   # the reader, ordered on the stream before the next pass, as the contract asks
     torch.cuda.synchronize()
-    assert not h.peer_barrier_timed_out()
+    for p in range(6):
+        one = torch.zeros((T, h.model.nd), dtype=torch.float64, device=dev)
+        h.fd_batch_dev(dq, dv, du * (1.0 - 0.1 * (5 - p)), dw, one, cost=cost)
+        assert torch.equal(snaps[p], one), p
+    peer.check()   # synchronises; raises on a barrier timeout
     np.save(os.path.join(out, f"peer_{rank}.npy"), full.cpu().numpy())
     if rank == 0:
         ref = torch.zeros((T, h.model.nd), dtype=torch.float64, device=dev)

@@ -146,13 +146,20 @@ def _peer_worker(rank, world, port, T, tmpdir):
     from ilqg_mujoco_b200 import sharding
     om = o.Model(os.path.join(pkg.MODELS_DIR, "hopper.ilqgm"))
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    q, v, u, w = scenario_states("hopper", T, seed=5)
-    tq, tv, tu, tw = (torch.from_numpy(a) for a in (q, v, u, w))
     h = _HostPeerHandle(o, om)
     peer = sharding.PeerDeriv(h, T, om.nd)
     assert peer.scatter_ptrs(3)[0] == peer.own + 3 * om.nd * 8          # this rank's copy first, knot offset in bytes
-    for _ in range(3):                                                    # several passes: epochs 1, 2, 3
+    assert peer.scatter_ptrs(3, 1)[0] == peer.own + (T + 3) * om.nd * 8  # the second buffer follows the first
+    import time
+    for p in range(3):                                                    # several passes with DIFFERENT inputs: epochs 1, 2, 3
+        q, v, u, w = scenario_states("hopper", T, seed=5 + p)
+        ref, _, _ = o.fd_batch(om, q, v, u, w, None, nthreads=1)
+        tq, tv, tu, tw = (torch.from_numpy(a) for a in (q, v, u, w))
         full = sharding.fd_knot_sharded_peer(h, peer, tq, tv, tu, tw)
+        assert full.data_ptr() == peer.bufs[p & 1].data_ptr()
+        if rank == 1:
+            time.sleep(0.3)   # a slow reader: rank 0 is already storing the next pass — into the OTHER buffer
+        assert np.array_equal(full.numpy(), ref)
     np.save(os.path.join(tmpdir, f"peer_{rank}.npy"), full.numpy().copy())
     assert peer.epoch == 3
     dist.barrier()
@@ -161,6 +168,8 @@ def _peer_worker(rank, world, port, T, tmpdir):
             h.peer_close(p)
     dist.barrier()
     peer.full = None
+    peer.bufs = None
+    full = None
     h.peer_free(peer.own)
     dist.destroy_process_group()
 
@@ -173,7 +182,7 @@ def test_knot_sharded_fd_peer_store_gather_host_logic(tmp_path, oracle, omodels,
     port = 29600 + (os.getpid() % 2000) + T
     mp.spawn(_peer_worker, args=(world, port, T, str(tmp_path)), nprocs=world, join=True)
     om = omodels["hopper"]
-    q, v, u, w = scenario_states("hopper", T, seed=5)
+    q, v, u, w = scenario_states("hopper", T, seed=7)   # the last pass's inputs
     ref, _, _ = oracle.fd_batch(om, q, v, u, w, None, nthreads=1)
     for r in range(world):
         assert np.array_equal(np.load(tmp_path / f"peer_{r}.npy"), ref)

@@ -764,15 +764,19 @@ DEV void coop_hessian_factor(const CoopMem& w, double* H, int nv, int na, int la
 // in: private fs, as, aref, warm; out: private qacc (and warm, the next warm start); nv <= 32: lane i owns dof i
 // reuse: take the C-state's cached factor Hc whenever the active set equals the one it was built for (the qvel / ctrl columns
 // of a knot share M, J and D with the centre, so all of their Newton systems with that active set are the same matrix)
-DEV int coop_solve(const GModel* __restrict__ g, CoopMem& w, int maxiter, double tol, int lane, bool need_forces = false, bool reuse = false) {
+// returns the Newton iterations run; *exact (optional) = the solve left through the exact-optimum test or had no rows
+DEV int coop_solve(const GModel* __restrict__ g, CoopMem& w, int maxiter, double tol, int lane, bool need_forces = false, bool reuse = false,
+                   bool* exact = nullptr) {
     const ilqg_model& m = g->m;
     const int nv = m.nv, ne = w.hdr[0];
     static_assert(COOP_MAXEFC <= 128, "mask width");
     if (ne == 0) {
         if (lane < nv) { w.qacc[lane] = w.as[lane]; w.warm[lane] = w.as[lane]; w.fc[lane] = 0; }
         __syncwarp();
+        if (exact) *exact = true;
         return 0;
     }
+    if (exact) *exact = false;
     const bool dof = lane < nv;
     const double fs_i = dof ? w.fs[lane] : 0.0, as_i = dof ? w.as[lane] : 0.0, warm_i = dof ? w.warm[lane] : 0.0;
     double qacc_i, Ma_i;
@@ -897,7 +901,10 @@ DEV int coop_solve(const GModel* __restrict__ g, CoopMem& w, int maxiter, double
         __syncwarp();
         old = cost;
         iter++;
-        if (cur == act) break;  // exact optimum: full Newton step inside the piece the Hessian was built for
+        if (cur == act) {  // exact optimum: full Newton step inside the piece the Hessian was built for
+            if (exact) *exact = true;
+            break;
+        }
     }
     if (need_forces) {  // qfrc_constraint at the final point (mj_Euler needs it)
         double f = 0;
@@ -950,10 +957,12 @@ __global__ void __launch_bounds__(32) coop_center_kernel(const GModel* __restric
     __syncwarp();
     const long long t1 = clock64();
     int it_first = 0, it_all = 0;
-    for (int rep = 0; rep < nwarmup; rep++) {
-        const int it = coop_solve(g, w, niter, 0.0, lane);
+    for (int rep = 0; rep < nwarmup; rep++) {   // repetitions stop at the first solve that is exact (see fd_center_kernel)
+        bool exact = false;
+        const int it = coop_solve(g, w, niter, 0.0, lane, false, false, &exact);
         if (rep == 0) it_first = it;
         it_all += it;
+        if (exact) break;
     }
     if (diag && lane == 0) {   // ILQG_DIAG_* (include/ilqg_b200.h)
         const long long t2 = clock64();

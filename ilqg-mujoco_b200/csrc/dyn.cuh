@@ -353,7 +353,52 @@ template <> struct Alg<true> {
 template <class T> using AlgOf = Alg<(T::PLANAR_Y != 0)>;
 
 // ------------------------------------------------------------------ per-rollout solver inputs
+// Where a rollout's constraint rows live.  The row count is data dependent (0 in flight, 4 per contact point, 1 per joint at its
+// limit; up to T::MAXEFC), so the rows cannot be registers.  Two placements behind one interface (element accessors):
+//   RowsLocal   per-thread local memory (L1-resident as long as the CTA's rows fit there) — every kernel but one;
+//   RowsShared  shared memory, ONE copy of J / D / B / k-term per KNOT for the threads that linearise the knot's qvel / ctrl
+//               columns on the same position stage (fd_velctrl_kernel), plus per-thread aref / jar / jv — see there.
 template <class T>
+struct RowsLocal {
+    static constexpr int NV = T::NV, ME = nz(T::MAXEFC);
+    double J_[ME][NV];
+    double D_[ME], aref_[ME], jar_[ME], jv_[ME];
+    double rB_[ME], rkt_[ME];  // per-row damping B and stiffness term K*imp*(pos-margin): aref = -B (J qvel) - rkt
+    DEV double& J(int r, int i) { return J_[r][i]; }
+    DEV double& D(int r) { return D_[r]; }
+    DEV double& aref(int r) { return aref_[r]; }
+    DEV double& jar(int r) { return jar_[r]; }
+    DEV double& jv(int r) { return jv_[r]; }
+    DEV double& rB(int r) { return rB_[r]; }
+    DEV double& rkt(int r) { return rkt_[r]; }
+    static constexpr bool private_rows = true;   // every thread owns (and writes) its rows
+    DEV bool row_writer() const { return true; }
+    DEV int capacity() const { return ME; }
+};
+// Shared-memory placement.  `knot`: base of the knot's block, element (field f, row r) at (r * KF + f) * kstride — consecutive
+// knots of the CTA at consecutive addresses, the threads of one knot read the same word (a broadcast): conflict-free.
+// `mine`: base of the thread's private block, element (field f, row r) at (r * 3 + f) * tstride.
+template <class T>
+struct RowsShared {
+    static constexpr int NV = T::NV, KF = NV + 3;   // J[nv], D, B, k-term per row of the knot's block
+    double* knot;
+    double* mine;
+    int kstride, tstride;
+    int cap;       // rows the blocks hold (a knot with more is flagged Work::overflow and redone with RowsLocal)
+    bool writer;   // one thread of the knot's group stores the shared fields (all compute the same values)
+    static constexpr bool private_rows = false;
+    DEV double& J(int r, int i) { return knot[(r * KF + i) * kstride]; }
+    DEV double& D(int r) { return knot[(r * KF + NV) * kstride]; }
+    DEV double& rB(int r) { return knot[(r * KF + NV + 1) * kstride]; }
+    DEV double& rkt(int r) { return knot[(r * KF + NV + 2) * kstride]; }
+    DEV double& aref(int r) { return mine[(r * 3 + 0) * tstride]; }
+    DEV double& jar(int r) { return mine[(r * 3 + 1) * tstride]; }
+    DEV double& jv(int r) { return mine[(r * 3 + 2) * tstride]; }
+    DEV bool row_writer() const { return writer; }
+    DEV int capacity() const { return cap; }
+};
+
+template <class T, class R = RowsLocal<T>>
 struct Work {
     static constexpr int NV = T::NV, NT = T::NV * (T::NV + 1) / 2, ME = nz(T::MAXEFC);
     double M[NT];    // mass matrix (packed lower)
@@ -364,9 +409,10 @@ struct Work {
     double fc[NV];   // qfrc_constraint of the last solve
     int nefc;
     int iters;       // Newton iterations of the last solve
-    double J[ME][NV];
-    double D[ME], aref[ME], jar[ME], jv[ME];
-    double rB[ME], rkt[ME];  // per-row damping B and stiffness term K*imp*(pos-margin): aref = -B (J qvel) - rkt
+    int exact;       // the last solve left through the exact-optimum test (or had no rows): solving again from its result is a no-op
+    int overflow;    // more rows than the placement's capacity (RowsShared): the knot must be redone with RowsLocal
+    using RowsT = R;
+    R rows;
 };
 
 // what the position stage leaves for the velocity stage (mjSTAGE_POS products that mj_fwdVelocity reads)
@@ -495,13 +541,13 @@ DEV void cdof_free_rot(const M3& xmat, P3 off, S6* cdof3) {
 // Every thread of the block must call the stage functions when SYNC is set.
 // FUSED (qv != nullptr): the velocity is known while the rows are built — aref is finished here from the Jacobian still in
 // registers and the per-row constants (B, k-term) never go to local memory; build_vel then skips its pass over the rows.
-template <class T, bool SYNC = false, bool FUSED = false>
-DEV void build_vel(const DevModel<T>& m, const PosStage<T>& ps, const double (&qv)[T::NV], Work<T>& w);
-template <class T>
-DEV void finish_smooth(const DevModel<T>& m, const double (&u)[nz(T::NU)], Work<T>& w);
+template <class T, bool SYNC = false, bool FUSED = false, class W>
+DEV void build_vel(const DevModel<T>& m, const PosStage<T>& ps, const double (&qv)[T::NV], W& w);
+template <class T, class W>
+DEV void finish_smooth(const DevModel<T>& m, const double (&u)[nz(T::NU)], W& w);
 
-template <class T, bool SYNC = false, bool FUSED = false>
-DEV void build_pos(const DevModel<T>& m, const double (&q)[T::NQ], PosStage<T>& ps, Work<T>& w, const double* qv = nullptr,
+template <class T, bool SYNC = false, bool FUSED = false, class W>
+DEV void build_pos(const DevModel<T>& m, const double (&q)[T::NQ], PosStage<T>& ps, W& w, const double* qv = nullptr,
                    const double* uu = nullptr) {
     auto stage_sync = [&]() { if constexpr (SYNC) __syncthreads(); };
     constexpr int NB = T::NBODY, NV = T::NV, NJ = T::NJNT;
@@ -758,6 +804,10 @@ DEV void build_pos(const DevModel<T>& m, const double (&q)[T::NQ], PosStage<T>& 
 
     stage_sync();
     // ---- constraint rows: joint limits, then contacts
+    static_assert(!FUSED || W::RowsT::private_rows, "the fused stages finish aref per rollout: rows must be private");
+    const int cap = w.rows.capacity();
+    const bool wr = w.rows.row_writer();
+    w.overflow = 0;
     int ne = 0;
     sfor<0, NJ>([&](auto jj) {
         constexpr int j = IDX(jj);
@@ -771,11 +821,16 @@ DEV void build_pos(const DevModel<T>& m, const double (&q)[T::NQ], PosStage<T>& 
                     double R, kt;
                     const double B = m.jnt_B[j];
                     row_params(m.jnt_K[j], m.jnt_imp[j], m.jnt_solimp[j], dist, m.jnt_margin[j], m.dof_invw[da], R, kt);
-                    sfor<0, NV>([&](auto ii) { w.J[ne][IDX(ii)] = IDX(ii) == da ? -side : 0.0; });
-                    w.D[ne] = 1.0 / R;
-                    if constexpr (FUSED) w.aref[ne] = -B * (-side * qv[da]) - kt;
-                    else { w.rB[ne] = B; w.rkt[ne] = kt; }
-                    ne++;
+                    if (ne < cap) {
+                        if (wr) {
+                            sfor<0, NV>([&](auto ii) { w.rows.J(ne, IDX(ii)) = IDX(ii) == da ? -side : 0.0; });
+                            w.rows.D(ne) = 1.0 / R;
+                            if constexpr (FUSED) w.rows.aref(ne) = -B * (-side * qv[da]) - kt;
+                            else { w.rows.rB(ne) = B; w.rows.rkt(ne) = kt; }
+                        }
+                        ne++;
+                    } else
+                        w.overflow = 1;
                 }
             });
         }
@@ -828,14 +883,19 @@ DEV void build_pos(const DevModel<T>& m, const double (&q)[T::NQ], PosStage<T>& 
             if (condim == 1) {
                 double R, kt;
                 row_params(K, imp, m.pair_solimp[p], dist, margin, tran, R, kt);
-                sfor<0, NV>([&](auto ii) { w.J[ne][IDX(ii)] = jn[IDX(ii)]; });
-                w.D[ne] = 1.0 / R;
-                if constexpr (FUSED) {
-                    double s = 0;
-                    sfor<0, NV>([&](auto ii) { s += jn[IDX(ii)] * qv[IDX(ii)]; });
-                    w.aref[ne] = -B * s - kt;
-                } else { w.rB[ne] = B; w.rkt[ne] = kt; }
-                ne++;
+                if (ne < cap) {
+                    if (wr) {
+                        sfor<0, NV>([&](auto ii) { w.rows.J(ne, IDX(ii)) = jn[IDX(ii)]; });
+                        w.rows.D(ne) = 1.0 / R;
+                        if constexpr (FUSED) {
+                            double s = 0;
+                            sfor<0, NV>([&](auto ii) { s += jn[IDX(ii)] * qv[IDX(ii)]; });
+                            w.rows.aref(ne) = -B * s - kt;
+                        } else { w.rows.rB(ne) = B; w.rows.rkt(ne) = kt; }
+                    }
+                    ne++;
+                } else
+                    w.overflow = 1;
             } else {
                 double R0, kt;
                 // all four facets share pos/margin; R of the first facet sets the pyramid's regulariser
@@ -843,20 +903,25 @@ DEV void build_pos(const DevModel<T>& m, const double (&q)[T::NQ], PosStage<T>& 
                 double Rpy = 2 * mu * mu * R0;
                 if (Rpy < ILQG_MINVAL) Rpy = ILQG_MINVAL;
                 double Dpy = 1.0 / Rpy;
+                if (ne + 4 <= cap) {
+                    if (wr) {
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const double sg = (k % 2) ? -mu : mu;
-                    double s = 0;
-                    sfor<0, NV>([&](auto ii) {
-                        const double Jri = jn[IDX(ii)] + sg * (k < 2 ? ja[IDX(ii)] : jb[IDX(ii)]);
-                        w.J[ne][IDX(ii)] = Jri;
-                        if constexpr (FUSED) s += Jri * qv[IDX(ii)];
-                    });
-                    w.D[ne] = Dpy;
-                    if constexpr (FUSED) w.aref[ne] = -B * s - kt;
-                    else { w.rB[ne] = B; w.rkt[ne] = kt; }
-                    ne++;
-                }
+                        for (int k = 0; k < 4; k++) {
+                            const double sg = (k % 2) ? -mu : mu;
+                            double s = 0;
+                            sfor<0, NV>([&](auto ii) {
+                                const double Jri = jn[IDX(ii)] + sg * (k < 2 ? ja[IDX(ii)] : jb[IDX(ii)]);
+                                w.rows.J(ne + k, IDX(ii)) = Jri;
+                                if constexpr (FUSED) s += Jri * qv[IDX(ii)];
+                            });
+                            w.rows.D(ne + k) = Dpy;
+                            if constexpr (FUSED) w.rows.aref(ne + k) = -B * s - kt;
+                            else { w.rows.rB(ne + k) = B; w.rows.rkt(ne + k) = kt; }
+                        }
+                    }
+                    ne += 4;
+                } else
+                    w.overflow = 1;
             }
         }
     }
@@ -864,8 +929,8 @@ DEV void build_pos(const DevModel<T>& m, const double (&q)[T::NQ], PosStage<T>& 
     stage_sync();
 }
 
-template <class T, bool SYNC, bool FUSED>
-DEV void build_vel(const DevModel<T>& m, const PosStage<T>& ps, const double (&qv)[T::NV], Work<T>& w) {
+template <class T, bool SYNC, bool FUSED, class W>
+DEV void build_vel(const DevModel<T>& m, const PosStage<T>& ps, const double (&qv)[T::NV], W& w) {
     auto stage_sync = [&]() { if constexpr (SYNC) __syncthreads(); };
     constexpr int NB = T::NBODY, NV = T::NV;
     using A = AlgOf<T>;
@@ -914,14 +979,14 @@ DEV void build_vel(const DevModel<T>& m, const PosStage<T>& ps, const double (&q
     ILQG_ROW_PRAGMA
     for (int r = 0; r < w.nefc; r++) {
         double s = 0;
-        sfor<0, NV>([&](auto ii) { s += w.J[r][IDX(ii)] * qv[IDX(ii)]; });
-        w.aref[r] = -w.rB[r] * s - w.rkt[r];
+        sfor<0, NV>([&](auto ii) { s += w.rows.J(r, IDX(ii)) * qv[IDX(ii)]; });
+        w.rows.aref(r) = -w.rows.rB(r) * s - w.rows.rkt(r);
     }
     stage_sync();
 }
 
-template <class T>
-DEV void finish_smooth(const DevModel<T>& m, const double (&u)[nz(T::NU)], Work<T>& w) {
+template <class T, class W>
+DEV void finish_smooth(const DevModel<T>& m, const double (&u)[nz(T::NU)], W& w) {
     constexpr int NV = T::NV;
     sfor<0, NV>([&](auto ii) { w.fs[IDX(ii)] = w.fb[IDX(ii)]; });
     sfor<0, T::NU>([&](auto uu) {
@@ -935,9 +1000,9 @@ DEV void finish_smooth(const DevModel<T>& m, const double (&u)[nz(T::NU)], Work<
 }
 
 // the whole of mj_fwdPosition + mj_fwdVelocity + mj_fwdActuation + qacc_smooth for one rollout
-template <class T, bool SYNC = false>
+template <class T, bool SYNC = false, class W>
 DEV void build_problem(const DevModel<T>& m, const double (&q)[T::NQ], const double (&qv)[T::NV], const double (&u)[nz(T::NU)],
-                       Work<T>& w) {
+                       W& w) {
     PosStage<T> ps;
     build_pos<T, SYNC, true>(m, q, ps, w, qv, u);   // FUSED: includes the velocity stage and qacc_smooth
 }
@@ -952,18 +1017,27 @@ DEV void build_problem(const DevModel<T>& m, const double (&q)[T::NQ], const dou
 // that piece's minimiser and the piece is the right one — the point is the global minimum up to the
 // round-off of the linear solve, and further iterations (which the reference's tol = 0 setting would
 // spend until the cost stops decreasing in fp64) only add rounding noise.
-template <class T>
-DEV void solve(const DevModel<T>& m, Work<T>& w, double (&warm)[T::NV], double (&qacc)[T::NV], int maxiter, double tol,
-               bool need_forces = false) {
+// fac (optional): a cached Newton factor (chol_packed layout) valid for the active set fac_mask — the factor of M + J_A' D_A J_A
+// only depends on M, J, D and the active set A, so rollouts that share the position stage (the qvel / ctrl columns of a knot and
+// its centre evaluation) share it: an iteration whose active set equals fac_mask skips the Hessian assembly and the factorisation.
+// fac_out / fac_mask_out (optional): where this solve leaves the factor of its last iteration and, if it ended exact, that
+// iteration's active set (else ~0: no set matches).
+template <class T, class W>
+DEV void solve(const DevModel<T>& m, W& w, double (&warm)[T::NV], double (&qacc)[T::NV], int maxiter, double tol,
+               bool need_forces = false, const double* fac = nullptr, unsigned long long fac_mask = ~0ull, int fac_stride = 1,
+               double* fac_out = nullptr, unsigned long long* fac_mask_out = nullptr) {
     constexpr int NV = T::NV, NT = NV * (NV + 1) / 2;
     static_assert(T::MAXEFC <= 64, "active-set masks are 64-bit: larger models use the cooperative kernel");
     typedef unsigned long long mask_t;
     const int ne = w.nefc;
     w.iters = 0;
+    w.exact = 1;
     if (ne == 0) {
         sfor<0, NV>([&](auto ii) { qacc[IDX(ii)] = w.as[IDX(ii)]; warm[IDX(ii)] = w.as[IDX(ii)]; w.fc[IDX(ii)] = 0; });
+        if (fac_mask_out) *fac_mask_out = ~0ull;
         return;
     }
+    w.exact = 0;
     const double scale = 1.0 / (m.meaninertia * (NV > 1 ? NV : 1));
     double Ma[NV], grad[NV], search[NV], Mv[NV];
     {
@@ -972,13 +1046,13 @@ DEV void solve(const DevModel<T>& m, Work<T>& w, double (&warm)[T::NV], double (
         double cw = 0, cs = 0;
         ILQG_ROW_PRAGMA
         for (int r = 0; r < ne; r++) {
-            double jw = -w.aref[r], js = jw;
-            sfor<0, NV>([&](auto ii) { const double Jri = w.J[r][IDX(ii)]; jw += Jri * warm[IDX(ii)]; js += Jri * w.as[IDX(ii)]; });
-            const double D = w.D[r];
+            double jw = -w.rows.aref(r), js = jw;
+            sfor<0, NV>([&](auto ii) { const double Jri = w.rows.J(r, IDX(ii)); jw += Jri * warm[IDX(ii)]; js += Jri * w.as[IDX(ii)]; });
+            const double D = w.rows.D(r);
             if (jw < 0) cw += 0.5 * D * jw * jw;
             if (js < 0) cs += 0.5 * D * js * js;   // the Gauss term of cost(qacc_smooth) is zero
-            w.jar[r] = jw;
-            w.jv[r] = js;
+            w.rows.jar(r) = jw;
+            w.rows.jv(r) = js;
         }
         sfor<0, NV>([&](auto ii) {
             constexpr int i = IDX(ii);
@@ -996,36 +1070,44 @@ DEV void solve(const DevModel<T>& m, Work<T>& w, double (&warm)[T::NV], double (
                 sfor<0, NV>([&](auto kk) { s += w.M[tri(i, IDX(kk))] * qacc[IDX(kk)]; });
                 Ma[i] = s;
             });
-            for (int r = 0; r < ne; r++) w.jar[r] = w.jv[r];
+            for (int r = 0; r < ne; r++) w.rows.jar(r) = w.rows.jv(r);
         }
     }
     double cost = 0, old = 0;
     int iter = 0;
     bool forces_current = false;
+    mask_t act = 0;
     for (;;) {
         // ---- cost, gradient, Hessian factor and Newton direction at the current point
-        mask_t act = 0;
+        act = 0;
         {
             double H[NT], Lh[NT];
-            sfor<0, NT>([&](auto tt) { H[IDX(tt)] = w.M[IDX(tt)]; });
+            bool cached = false;
+            if (fac) {   // the active set first: with the cached factor's set the Hessian is not assembled at all
+                mask_t pre = 0;
+                for (int r = 0; r < ne; r++) pre |= (mask_t)(w.rows.jar(r) < 0) << r;
+                cached = pre == fac_mask;
+            }
+            if (!cached) sfor<0, NT>([&](auto tt) { H[IDX(tt)] = w.M[IDX(tt)]; });
             sfor<0, NV>([&](auto ii) { w.fc[IDX(ii)] = 0; });
             double c = 0;
             ILQG_HESS_PRAGMA
             for (int r = 0; r < ne; r++) {
-                double jar = w.jar[r];
+                double jar = w.rows.jar(r);
                 if (jar < 0) {
                     act |= (mask_t)1 << r;
-                    double D = w.D[r];
+                    double D = w.rows.D(r);
                     double Jr[NV];
-                    sfor<0, NV>([&](auto ii) { Jr[IDX(ii)] = w.J[r][IDX(ii)]; });
+                    sfor<0, NV>([&](auto ii) { Jr[IDX(ii)] = w.rows.J(r, IDX(ii)); });
                     double f = -D * jar;
                     c += 0.5 * D * jar * jar;
-                    sfor<0, NV>([&](auto ii) {
-                        constexpr int i = IDX(ii);
-                        w.fc[i] += Jr[i] * f;
-                        double t = D * Jr[i];
-                        sfor<0, i + 1>([&](auto kk) { H[tri(i, IDX(kk))] += t * Jr[IDX(kk)]; });
-                    });
+                    sfor<0, NV>([&](auto ii) { w.fc[IDX(ii)] += Jr[IDX(ii)] * f; });
+                    if (!cached)
+                        sfor<0, NV>([&](auto ii) {
+                            constexpr int i = IDX(ii);
+                            double t = D * Jr[i];
+                            sfor<0, i + 1>([&](auto kk) { H[tri(i, IDX(kk))] += t * Jr[IDX(kk)]; });
+                        });
                 }
             }
             sfor<0, NV>([&](auto ii) {
@@ -1036,7 +1118,11 @@ DEV void solve(const DevModel<T>& m, Work<T>& w, double (&warm)[T::NV], double (
             });
             cost = c;
             forces_current = true;
-            chol_packed<NV>(H, Lh);
+            if (cached) sfor<0, NT>([&](auto tt) { Lh[IDX(tt)] = fac[IDX(tt) * fac_stride]; });
+            else {
+                chol_packed<NV>(H, Lh);
+                if (fac_out) sfor<0, NT>([&](auto tt) { fac_out[IDX(tt)] = Lh[IDX(tt)]; });
+            }
             chol_solve_packed<NV>(Lh, search);
             sfor<0, NV>([&](auto ii) { search[IDX(ii)] = -search[IDX(ii)]; });
         }
@@ -1059,11 +1145,11 @@ DEV void solve(const DevModel<T>& m, Work<T>& w, double (&warm)[T::NV], double (
         ILQG_ROW_PRAGMA
         for (int r = 0; r < ne; r++) {
             double s = 0;
-            sfor<0, NV>([&](auto ii) { s += w.J[r][IDX(ii)] * search[IDX(ii)]; });
-            w.jv[r] = s;
+            sfor<0, NV>([&](auto ii) { s += w.rows.J(r, IDX(ii)) * search[IDX(ii)]; });
+            w.rows.jv(r) = s;
             if ((act >> r) & 1) {
-                double t = w.D[r] * s;
-                d1 += t * w.jar[r];
+                double t = w.rows.D(r) * s;
+                d1 += t * w.rows.jar(r);
                 d2 += t * s;
             }
         }
@@ -1079,10 +1165,10 @@ DEV void solve(const DevModel<T>& m, Work<T>& w, double (&warm)[T::NV], double (
             mask_t mk = 0;
             ILQG_ROW_PRAGMA
             for (int r = 0; r < ne; r++) {
-                double jv = w.jv[r];
-                double x = w.jar[r] + an * jv;
+                double jv = w.rows.jv(r);
+                double x = w.rows.jar(r) + an * jv;
                 if (x < 0) {
-                    double t = w.D[r] * jv;
+                    double t = w.rows.D(r) * jv;
                     e1 += t * x;
                     e2 += t * jv;
                     mk |= (mask_t)1 << r;
@@ -1098,25 +1184,31 @@ DEV void solve(const DevModel<T>& m, Work<T>& w, double (&warm)[T::NV], double (
         }
         if (alpha == 0) break;
         sfor<0, NV>([&](auto ii) { constexpr int i = IDX(ii); qacc[i] += alpha * search[i]; Ma[i] += alpha * Mv[i]; });
-        ILQG_ROW_PRAGMA
-        for (int r = 0; r < ne; r++) w.jar[r] += alpha * w.jv[r];
+        const bool exact = reached == act;  // exact optimum (see above)
+        // (the rows' residuals at the new point are only read by a further iteration or by the force evaluation below: a solve
+        //  that leaves here without either skips this pass over the rows)
+        if (!exact || need_forces) {
+            ILQG_ROW_PRAGMA
+            for (int r = 0; r < ne; r++) w.rows.jar(r) += alpha * w.rows.jv(r);
+        }
         old = cost;
         iter++;
         forces_current = false;
-        if (reached == act) break;  // exact optimum (see above)
+        if (exact) { w.exact = 1; break; }
     }
     if (need_forces && !forces_current) {  // qfrc_constraint at the final point (the integrators need it)
         sfor<0, NV>([&](auto ii) { w.fc[IDX(ii)] = 0; });
         ILQG_ROW_PRAGMA
         for (int r = 0; r < ne; r++) {
-            double jar = w.jar[r];
+            double jar = w.rows.jar(r);
             if (jar < 0) {
-                double f = -w.D[r] * jar;
-                sfor<0, NV>([&](auto ii) { w.fc[IDX(ii)] += w.J[r][IDX(ii)] * f; });
+                double f = -w.rows.D(r) * jar;
+                sfor<0, NV>([&](auto ii) { w.fc[IDX(ii)] += w.rows.J(r, IDX(ii)) * f; });
             }
         }
     }
     w.iters = iter;
+    if (fac_mask_out) *fac_mask_out = w.exact ? act : ~0ull;   // (an exact exit leaves `act` = the set the last factor was built for)
     sfor<0, NV>([&](auto ii) { warm[IDX(ii)] = qacc[IDX(ii)]; });
 }
 
@@ -1145,8 +1237,8 @@ DEV void integrate_pos(double (&q)[T::NQ], const double (&v)[T::NV], double dt) 
 }
 
 // one mj_step: forward dynamics with the model's solver settings, then the model's integrator
-template <class T>
-DEV void step(const DevModel<T>& m, Work<T>& w, double (&q)[T::NQ], double (&v)[T::NV], const double (&u)[nz(T::NU)],
+template <class T, class W>
+DEV void step(const DevModel<T>& m, W& w, double (&q)[T::NQ], double (&v)[T::NV], const double (&u)[nz(T::NU)],
               double (&warm)[T::NV], double (&qacc)[T::NV]) {
     constexpr int NV = T::NV, NQ = T::NQ, NT = NV * (NV + 1) / 2;
     const double h = m.timestep;

@@ -60,7 +60,12 @@ struct FdBins {
     int* cnt;            // [FD_NBUCKET] knots per bucket (zeroed before the centre kernel)
     unsigned int* key;   // [nknots] bucket << 24 | rank inside the bucket
     int* perm;           // [nknots] slot -> knot
+    double* fac;         // [nknots][NT + 1] the centre solution's Newton factor and (as bits) its active set: the qvel / ctrl columns
+                         // of the knot share M, J and D with the centre, so their Newton systems with that active set are this matrix
 };
+
+// rows of the heaviest knot of the CTA that starts at slot k0 (the centre kernel's work-class key: bucket = FD_NBUCKET - 1 - rows)
+DEV int fd_cta_rows(const FdBins& bins, int k0) { return FD_NBUCKET - 1 - (int)(bins.key[bins.perm[k0]] >> 24); }
 
 // (register caps for 12 / 16 resident warps per SM were measured on this kernel after the planar algebra: +16 % time both)
 template <class T>
@@ -69,6 +74,9 @@ __global__ void __launch_bounds__(128) fd_center_kernel(const __grid_constant__ 
                                                         const double* __restrict__ warmstart, int niter, int nwarmup,
                                                         double* __restrict__ qacc_center, int* __restrict__ status, const FdBins bins,
                                                         int* __restrict__ diag) {
+    // programmatic dependent launch: the single-launch column kernel that follows does not need this kernel's result before
+    // its own position / velocity stages are done — let it start now and wait (griddepcontrol.wait) just before its solves
+    asm volatile("griddepcontrol.launch_dependents;");
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = k < nknots;
     const int kk = valid ? k : nknots - 1;   // the tail's idle lanes evaluate a clamped knot, writes masked (warp-wide ranking below)
@@ -80,16 +88,22 @@ __global__ void __launch_bounds__(128) fd_center_kernel(const __grid_constant__ 
     build_problem<T>(m, q, v, u, w);
     const long long t1 = clock64();
     int it_first = 0, it_all = 0;
+    // The reference repeats the centre solve nwarmup times to polish the warm start (mjderivative.cpp:67-68).  A solve that left
+    // through the exact-optimum test (dyn.cuh) already sits on the minimiser: repeating it from there changes nothing but
+    // round-off, so the repetitions stop at the first such solve.
+    constexpr int NTF = T::NV * (T::NV + 1) / 2;
+    double* fout = bins.fac ? bins.fac + (size_t)kk * (NTF + 1) : nullptr;   // (idle lanes rewrite the clamped knot's block with the same values)
 #pragma unroll 1
     for (int rep = 0; rep < nwarmup; rep++) {   // one copy of the solver (instruction footprint)
-        solve<T>(m, w, warm, qacc, niter, 0.0);
+        solve<T>(m, w, warm, qacc, niter, 0.0, diag != nullptr, nullptr, ~0ull, 1, fout, fout ? reinterpret_cast<unsigned long long*>(fout + NTF) : nullptr);
         if (rep == 0) it_first = w.iters;
         it_all += w.iters;
+        if (w.exact) break;
     }
     if (diag && valid) {   // ILQG_DIAG_* (include/ilqg_b200.h)
         const long long t2 = clock64();
         int na = 0;
-        for (int r = 0; r < w.nefc; r++) na += w.jar[r] < 0;
+        for (int r = 0; r < w.nefc; r++) na += w.rows.jar(r) < 0;
         int4* d = reinterpret_cast<int4*>(diag + (size_t)k * ILQG_DIAG_INTS);
         d[0] = make_int4(w.nefc, it_first, it_all, na);
         d[1] = make_int4((int)(t1 - t0), (int)(t2 - t1), 0, 0);
@@ -169,7 +183,6 @@ __global__ void __launch_bounds__(256, 1) fd_perturb_kernel(const __grid_constan
         const int kk = valid ? k : (k < nknots ? k : nknots - 1);
         double q[NQ], v[NV], u[nz(NU)], warm[NV];
         load_knot<T>(kk, qpos, qvel, ctrl, q, v, u);
-        sfor<0, NV>([&](auto ii) { warm[IDX(ii)] = qacc_center[(size_t)kk * NV + IDX(ii)]; });
         double c0 = 0;
         if (cost) c0 = cost_eval<T>(*cost, q, v, u);
         // perturb this lane's input (ctrl: mjderivative.cpp:85,99; qvel: :117,130; qpos: :164-169,187-192)
@@ -188,6 +201,11 @@ __global__ void __launch_bounds__(256, 1) fd_perturb_kernel(const __grid_constan
         if (cost && !(l & 1)) dcost = __ddiv_rn(__dsub_rn(cost_eval<T>(*cost, q, v, u), c0), eps);
         Work<T> w;
         build_problem<T, SYNC>(m, q, v, u, w);
+        // everything up to here is independent of the centre kernel: launched as its programmatic dependent, this kernel overlaps
+        // it and waits here for its completion (a no-op when launched the ordinary way).  Only the warm start comes from there
+        // (mjderivative.cpp:75,91) — and the status words, written below.
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        sfor<0, NV>([&](auto ii) { warm[IDX(ii)] = __ldcg(&qacc_center[(size_t)kk * NV + IDX(ii)]); });
         solve<T>(m, w, warm, qacc, niter, 0.0);
     }
     // central difference: the '+' lane (even) takes the '-' lane's result
@@ -236,6 +254,157 @@ __global__ void __launch_bounds__(256, 1) fd_perturb_kernel(const __grid_constan
     }
 }
 
+// ------------------------------------------------------------------ FD of a small batch in ONE launch
+// A batch too small to fill the GPU (the T = 1000 horizon of BASELINE configs[4], the 125 knots a rank holds when that horizon is
+// sharded over 8 GPUs, a single trajectory of 21 knots) is bound by the latency of the chain centre -> perturbed evaluation, not by
+// throughput.  Here the knot's centre evaluation rides on a spare lane next to its G perturbed evaluations: all G + 1 problems are
+// built side by side (one pass through the pipeline's instruction stream instead of two kernels' worth), the centre lane runs its
+// solves (mjderivative.cpp:64-68) while the others wait, hands the warm start over by shuffle (:75,91), and the perturbed solves
+// follow — one launch, no round trip through HBM, no second kernel start.  Same arithmetic per rollout as the two-launch path.
+// (Round 1 measured this arrangement and dropped it: with three full centre solves per knot the lone centre lane cost more than the
+// second launch.  With the repetitions stopping at the first exact solve the balance is the other way for small batches.)
+template <class T>
+struct FdFusedShape {
+    static constexpr int NV = T::NV, NU = T::NU;
+    static constexpr int NCOL = 2 * NV + NU;
+    static constexpr int G = 2 * NCOL;          // perturbed evaluations per knot
+    static constexpr int GL = G + 1;            // lanes per knot: + the centre
+    static constexpr int KPW = 32 / GL;         // knots per warp
+    static constexpr int ND = NV * NCOL + NCOL, NJAC = NV * NCOL;
+    static constexpr bool OK = GL <= 32;
+};
+
+template <class T>
+__global__ void __launch_bounds__(256, 1) fd_fused_kernel(const __grid_constant__ DevModel<T> m, int nknots, const double* __restrict__ qpos,
+                                                          const double* __restrict__ qvel, const double* __restrict__ ctrl,
+                                                          const double* __restrict__ warmstart, const ilqg_cost* __restrict__ cost, double eps,
+                                                          int niter, int nwarmup, const FdDst dst, double* __restrict__ qacc_center,
+                                                          int* __restrict__ status, int* __restrict__ diag) {
+    using S = FdFusedShape<T>;
+    constexpr int NV = T::NV, NU = T::NU, NQ = T::NQ, WARPS = 8, KPW = S::KPW > 0 ? S::KPW : 1;
+    __shared__ double stage[WARPS][KPW * S::ND];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int warp = blockIdx.x * WARPS + wib;
+    const int sub = lane / S::GL, l = lane - sub * S::GL;
+    const int k = warp * KPW + sub;
+    const bool valid = sub < KPW && k < nknots;
+    const bool is_center = l == S::G;
+    const int col = l >> 1;                     // the centre lane's "column" (NCOL) matches no input: it evaluates the knot itself
+    const double se = (l & 1) ? -eps : eps;
+    const int base = (sub < KPW ? sub : 0) * S::GL;   // first lane of this knot's group
+    double qacc[NV], warm[NV];
+    double dcost = 0;
+    int it_first = 0, it_all = 0, nefc = 0, nact = 0;
+    long long t0 = 0, t1 = 0, t2 = 0;
+    {
+        // idle lanes (tail of the grid, spare lanes of a warp) evaluate a clamped knot with their writes masked, so that every
+        // thread reaches the stage barriers
+        const int kk = valid ? k : (k < nknots ? k : nknots - 1);
+        double q[NQ], v[NV], u[nz(NU)];
+        load_knot<T>(kk, qpos, qvel, ctrl, q, v, u);
+        sfor<0, NV>([&](auto ii) { warm[IDX(ii)] = (is_center && warmstart) ? warmstart[(size_t)kk * NV + IDX(ii)] : 0.0; });
+        double c0 = 0;
+        if (cost) c0 = cost_eval<T>(*cost, q, v, u);
+        sfor<0, NU>([&](auto ii) { if (col == IDX(ii)) u[IDX(ii)] += se; });
+        sfor<0, NV>([&](auto ii) { if (col == NU + IDX(ii)) v[IDX(ii)] += se; });
+        sfor<0, NV>([&](auto ii) {
+            constexpr int i = IDX(ii), j = T::dof_jnt(i);
+            if (col == NU + NV + i) {
+                if constexpr (T::jnt_type(j) == ILQG_JNT_FREE && i >= T::jnt_dofadr(j) + 3) {
+                    constexpr int a = i - T::jnt_dofadr(j) - 3;
+                    quat_integrate(&q[T::jnt_qposadr(j) + 3], V3{a == 0 ? se : 0.0, a == 1 ? se : 0.0, a == 2 ? se : 0.0}, 1.0);
+                } else
+                    q[T::jnt_qposadr(j) + i - T::jnt_dofadr(j)] += se;
+            }
+        });
+        if (cost && !(l & 1) && !is_center) dcost = __ddiv_rn(__dsub_rn(cost_eval<T>(*cost, q, v, u), c0), eps);
+        Work<T> w;
+        t0 = clock64();
+        build_problem<T, true>(m, q, v, u, w);
+        t1 = clock64();
+        // phase 0: the centre lanes solve (repetitions stop at the first exact solve, see fd_center_kernel); phase 1: the warm start
+        // goes to the knot's other lanes and they solve.  ONE copy of the solver for both (instruction footprint).
+#pragma unroll 1
+        for (int phase = 0; phase < 2; phase++) {
+            if (phase == 1) {
+                t2 = clock64();
+                sfor<0, NV>([&](auto jj) {
+                    const double c = __shfl_sync(0xffffffffu, qacc[IDX(jj)], base + S::G);
+                    if (!is_center) warm[IDX(jj)] = c;
+                });
+            }
+            if ((phase == 0) == is_center) {
+                const int reps = phase == 0 ? nwarmup : 1;
+#pragma unroll 1
+                for (int rep = 0; rep < reps; rep++) {
+                    solve<T>(m, w, warm, qacc, niter, 0.0, phase == 0 && diag != nullptr);
+                    if (phase == 0) { if (rep == 0) it_first = w.iters; it_all += w.iters; }
+                    if (w.exact) break;
+                }
+            }
+            __syncwarp();
+        }
+        if (is_center) {
+            nefc = w.nefc;
+            if (diag) for (int r = 0; r < w.nefc; r++) nact += w.rows.jar(r) < 0;
+        }
+    }
+    if (valid && is_center) {
+        bool ok = true;
+        sfor<0, NV>([&](auto ii) { qacc_center[(size_t)k * NV + IDX(ii)] = qacc[IDX(ii)]; ok = ok && isfinite(qacc[IDX(ii)]); });
+        if (status) status[k] = ok ? 0 : ILQG_ERR_NONFINITE;
+        if (diag) {
+            int4* d = reinterpret_cast<int4*>(diag + (size_t)k * ILQG_DIAG_INTS);
+            d[0] = make_int4(nefc, it_first, it_all, nact);
+            d[1] = make_int4((int)(t1 - t0), (int)(t2 - t1), 0, 0);
+        }
+    }
+    __syncwarp();   // the centre's status word is written before the columns may flag it
+    // central difference: the '+' lane (even l) takes the '-' lane's result
+    bool finite = true;
+    const double inv2eps = 1.0 / (2 * eps);
+    double* st = stage[wib] + (sub < KPW ? sub : 0) * S::ND;
+    const int partner = is_center ? lane : base + (l ^ 1);
+    sfor<0, NV>([&](auto jj) {
+        constexpr int j = IDX(jj);
+        double other = __shfl_sync(0xffffffffu, qacc[j], partner);
+        double d = (qacc[j] - other) * inv2eps;
+        finite = finite && isfinite(d);
+        if (valid && !(l & 1) && !is_center) {
+            int off;   // reference layout: block of kind, element i + j*stride
+            if (col < NU) off = 2 * NV * NV + col + j * NU;
+            else if (col < NU + NV) off = NV * NV + (col - NU) + j * NV;
+            else off = (col - NU - NV) + j * NV;
+            st[off] = d;
+        }
+    });
+    if (valid && !(l & 1) && !is_center) {
+        int off;   // cost gradient entries: dg/dqpos[nv], dg/dqvel[nv], dg/dctrl[nu]
+        if (col < NU) off = S::NJAC + 2 * NV + col;
+        else if (col < NU + NV) off = S::NJAC + NV + (col - NU);
+        else off = S::NJAC + (col - NU - NV);
+        st[off] = dcost;
+        if (!finite && status) atomicExch(&status[k], ILQG_ERR_NONFINITE);
+    }
+    __syncwarp();
+    // coalesced write-out: the warp's knots are contiguous in deriv
+    const int k0 = warp * KPW;
+    int nk = nknots - k0;
+    if (nk > KPW) nk = KPW;
+    if (nk > 0) {
+        const int per = cost ? S::ND : S::NJAC;  // without a device cost the gradient entries stay untouched
+        for (int d = 0; d < dst.n; d++) {
+            double* out = dst.p[d] + (size_t)k0 * S::ND;
+            if (per == S::ND) {
+                for (int e = lane; e < nk * S::ND; e += 32) out[e] = stage[wib][e];
+            } else {
+                for (int kk = 0; kk < nk; kk++)
+                    for (int e = lane; e < per; e += 32) out[kk * S::ND + e] = stage[wib][kk * S::ND + e];
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------ FD with stage skipping: two kernels after the centre
 // The reference re-runs only the stages a perturbation can change: mj_forwardSkip(mjSTAGE_VEL) for ctrl columns,
 // mj_forwardSkip(mjSTAGE_POS) for qvel columns, everything for qpos columns (mjderivative.cpp:92,124,178).  In SIMT the
@@ -268,7 +437,11 @@ __global__ void __launch_bounds__(THREADS, MINB) fd_velctrl_kernel(const __grid_
                                                             const double* __restrict__ qvel, const double* __restrict__ ctrl,
                                                             const double* __restrict__ qacc_center, const ilqg_cost* __restrict__ cost,
                                                             double eps, int niter, const FdDst dst, int* __restrict__ status,
-                                                            const int* __restrict__ perm) {
+                                                            const int* __restrict__ perm, const FdBins bins, int skip_lo, int skip_hi) {
+    if (skip_hi > skip_lo) {   // CTAs whose heaviest knot has skip_lo < rows <= skip_hi belong to fd_velctrl_shared_kernel
+        const int rows = fd_cta_rows(bins, blockIdx.x * FdSplit<T, THREADS>::KPC_VU);
+        if (rows > skip_lo && rows <= skip_hi) return;
+    }
     // No shared-memory staging of the results here (the qpos kernel has it): each thread stores its own entries of the dv | du
     // blocks straight to deriv.  The stores are few (54 doubles per knot) and fire-and-forget, while the 43 KB a staged CTA would
     // take out of the SM's L1 hold the rollouts' constraint rows (local memory) — measured: 0.324 -> 0.305 ms.
@@ -312,6 +485,103 @@ __global__ void __launch_bounds__(THREADS, MINB) fd_velctrl_kernel(const __grid_
                 double d = (qplus[j] - qacc[j]) * inv2eps;
                 finite = finite && isfinite(d);
                 // reference layout: dv block at nv^2 (element i + j nv), du block at 2 nv^2 (element i + j nu)
+                const size_t off = base + NV * NV + (is_vel ? col + j * NV : NV * NV + col + j * NU);
+                if (valid)
+                    for (int dd = 0; dd < dst.n; dd++) dst.p[dd][off] = d;
+            });
+            if (valid && cost)   // without a device cost the gradient entries stay untouched
+                for (int dd = 0; dd < dst.n; dd++) dst.p[dd][base + S::NJAC + NV + (is_vel ? col : NV + col)] = dcost;
+        }
+    }
+    if (valid && !finite && status) atomicExch(&status[kk], ILQG_ERR_NONFINITE);
+}
+
+// The same columns with the knot's constraint rows in SHARED memory, one copy per knot.  The GK threads of a knot run the
+// position stage on the same qpos: their J, D, B and k-term are identical, and in per-thread local memory a CTA of stance knots
+// (85 knots x 3 copies x ~1 KB) overflows the L1 (ncu, round 1: 60 % hit rate, 128 MB of DRAM write-back per launch against
+// 46 MB of results, long-scoreboard the top stall).  Here one thread of the group stores them, all read them (a broadcast),
+// and only aref / jar / jv — which differ per column — are per thread, also in shared memory.  The centre's Newton factor
+// comes along (FdBins::fac): a column's Newton iteration whose active set is the centre solution's skips the Hessian assembly
+// and the 6 x 6 factorisation.  `cap` rows fit the carve-out; the batch is ordered heaviest knot first (work classes), so a
+// CTA whose first knot has <= cap rows takes this kernel and the others the local-memory one above: both are launched over
+// the whole grid and a CTA of the other class leaves at once.
+template <class T, int THREADS>
+struct FdVuShared {
+    using S = FdSplit<T, THREADS>;
+    static constexpr int KF = RowsShared<T>::KF, NT = T::NV * (T::NV + 1) / 2, KPC = S::KPC_VU;
+    static constexpr size_t bytes(int cap) { return sizeof(double) * ((size_t)cap * (KF * KPC + 3 * THREADS) + (size_t)NT * KPC); }
+    static constexpr int max_cap(size_t smem) {
+        const long c = ((long)(smem / sizeof(double)) - (long)NT * KPC) / (KF * KPC + 3 * THREADS);
+        return c < 0 ? 0 : (c > T::MAXEFC ? T::MAXEFC : (int)c);
+    }
+};
+
+template <class T, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) fd_velctrl_shared_kernel(const __grid_constant__ DevModel<T> m, int nknots, const double* __restrict__ qpos,
+                                                                  const double* __restrict__ qvel, const double* __restrict__ ctrl,
+                                                                  const double* __restrict__ qacc_center, const ilqg_cost* __restrict__ cost,
+                                                                  double eps, int niter, const FdDst dst, int* __restrict__ status,
+                                                                  const FdBins bins, int cap_lo, int cap) {
+    using S = FdSplit<T, THREADS>;
+    using P = FdVuShared<T, THREADS>;
+    constexpr int NV = T::NV, NU = T::NU, NQ = T::NQ, GK = S::GK, KPC = P::KPC, NT = P::NT;
+    extern __shared__ __align__(16) double vu_smem[];
+    const int k0 = blockIdx.x * KPC;
+    {
+        const int rows = fd_cta_rows(bins, k0);
+        if (rows <= cap_lo || rows > cap) return;   // another launch's CTA (uniform over the block)
+    }
+    const int kl = threadIdx.x / GK, g = threadIdx.x - kl * GK;
+    const int slot = k0 + kl;
+    const bool valid = kl < KPC && slot < nknots;
+    const int sc = slot < nknots ? slot : nknots - 1;   // idle lanes evaluate a clamped knot with their writes masked (stage barriers)
+    const int kk = bins.perm[sc];
+    const int kq = kl < KPC ? kl : KPC - 1;             // the CTA's spare thread reads the last knot's blocks and writes nothing
+    double* sh_knot = vu_smem;
+    double* sh_mine = sh_knot + (size_t)cap * P::KF * KPC;
+    double* sh_fac = sh_mine + (size_t)cap * 3 * THREADS;
+    double q[NQ], v[NV], u[nz(NU)], center[NV];
+    load_knot<T>(kk, qpos, qvel, ctrl, q, v, u);
+    sfor<0, NV>([&](auto ii) { center[IDX(ii)] = qacc_center[(size_t)kk * NV + IDX(ii)]; });
+    const double* kfac = bins.fac + (size_t)kk * (NT + 1);
+    if (kl < KPC)
+        for (int e = g; e < NT; e += GK) sh_fac[e * KPC + kl] = kfac[e];
+    const unsigned long long fmask = *reinterpret_cast<const unsigned long long*>(kfac + NT);
+    double c0 = 0;
+    if (cost) c0 = cost_eval<T>(*cost, q, v, u);
+    PosStage<T> ps;
+    Work<T, RowsShared<T>> w;
+    w.rows.knot = sh_knot + kq;
+    w.rows.mine = sh_mine + threadIdx.x;
+    w.rows.kstride = KPC;
+    w.rows.tstride = THREADS;
+    w.rows.cap = cap;
+    w.rows.writer = g == 0 && kl < KPC;
+    build_pos<T, true>(m, q, ps, w);   // ends with a block barrier: the knot's rows (and the factors) are visible to its threads
+    const double inv2eps = 1.0 / (2 * eps);
+    const size_t base = (size_t)kk * S::ND;
+    double qplus[NV], dcost = 0;
+    bool finite = true;
+#pragma unroll 1
+    for (int it = 0; it < 2 * (S::CU + S::CV); it++) {
+        const int c = it >> 1;
+        const bool is_vel = c >= S::CU;                       // uniform over the grid
+        const int col = (is_vel ? c - S::CU : c) * GK + g;    // column within its kind
+        const double se = (it & 1) ? -eps : eps;
+        double vp[NV], up[nz(NU)], warm[NV], qacc[NV];
+        sfor<0, NV>([&](auto ii) { vp[IDX(ii)] = v[IDX(ii)] + ((is_vel && col == IDX(ii)) ? se : 0.0); warm[IDX(ii)] = center[IDX(ii)]; });
+        sfor<0, NU>([&](auto ii) { up[IDX(ii)] = u[IDX(ii)] + ((!is_vel && col == IDX(ii)) ? se : 0.0); });
+        if (cost && !(it & 1)) dcost = __ddiv_rn(__dsub_rn(cost_eval<T>(*cost, q, vp, up), c0), eps);
+        if (it == 0 || is_vel) build_vel<T, false>(m, ps, vp, w);   // ctrl columns keep the centre's velocity stage (mjSTAGE_VEL skip)
+        finish_smooth<T>(m, up, w);
+        solve<T>(m, w, warm, qacc, niter, 0.0, false, sh_fac + kq, fmask, KPC);
+        if (!(it & 1)) {
+            sfor<0, NV>([&](auto jj) { qplus[IDX(jj)] = qacc[IDX(jj)]; });
+        } else {
+            sfor<0, NV>([&](auto jj) {
+                constexpr int j = IDX(jj);
+                double d = (qplus[j] - qacc[j]) * inv2eps;
+                finite = finite && isfinite(d);
                 const size_t off = base + NV * NV + (is_vel ? col + j * NV : NV * NV + col + j * NU);
                 if (valid)
                     for (int dd = 0; dd < dst.n; dd++) dst.p[dd][off] = d;
@@ -471,9 +741,12 @@ struct Engine {
     int fd_variant = -1;   // -1: chosen per call by batch size (ILQG_FD_VARIANT overrides)
     int fd_bins = 1;       // work-class ordering of the knots in the stage-skipping kernels (ILQG_FD_BINS=0 disables)
     int* fd_diag = nullptr;   // [nknots][ILQG_DIAG_INTS] per-knot diagnostics of the next fd() call (device), or NULL
+    int fd_pdl = 1;           // single-launch column kernel as the centre kernel's programmatic dependent (ILQG_FD_PDL=0 disables)
     // false: fd() keeps engine-owned scratch indexed by the knot's position in the call, so two fd() calls must not overlap
     // on different streams (the host-pointer pipeline then uses ONE compute stream)
     virtual bool fd_calls_may_overlap() const { return true; }
+    virtual void set_fused_max(int) {}
+    virtual void set_vu_classes(const char*) {}
     // ints of scratch fd() wants for `nknots` knots (bucket counters, keys, permutation); 0 = none
     // (`batch`: the size of the whole batch a chunk belongs to — the kernel variant is chosen on it, so that a chunked host
     //  call runs the same kernels, and returns the same bits, as one device call over the batch)
@@ -505,9 +778,26 @@ struct EngineT : Engine {
     // 16K 58.9 / 48.1, 21.5K 60.5 / 55.8, 28.7K 64.9 / 63.4, 43K 69.8 / 82.9, 86K 76.9 / 105 — the split's qvel/ctrl kernel has a
     // latency floor of 0.18 ms (a stance CTA's 6 sequential solves), the single launch none.
     static constexpr int SPLIT_MIN = 24576;
-    int variant_for(int nknots) const { return fd_variant >= 0 ? fd_variant : (nknots >= SPLIT_MIN ? 3 : 2); }
+    // below this the batch cannot fill the GPU and the one-launch kernel (centre on a spare lane of its knot's warp) has the
+    // shortest chain; above it the lone centre lane costs throughput (ILQG_FD_FUSED_MAX overrides; measured on B200)
+    int fused_max = FdFusedShape<T>::OK ? 64 : 0;
+    void set_fused_max(int n) override { fused_max = FdFusedShape<T>::OK ? n : 0; }
+    void set_vu_classes(const char* e) override {
+        vu_nclass = 0;
+        while (*e && vu_nclass < 4) {
+            const int c = atoi(e);
+            if (c > 0) vu_class[vu_nclass++] = c;
+            while (*e && *e != ',') e++;
+            if (*e == ',') e++;
+        }
+    }
+    int variant_for(int nknots) const {
+        if (fd_variant >= 0) return (fd_variant == 1 && !FdFusedShape<T>::OK) ? 2 : fd_variant;
+        return nknots >= SPLIT_MIN ? 3 : (nknots <= fused_max ? 1 : 2);
+    }
     size_t fd_scratch_ints(int nknots, int batch) const override {
-        return (variant_for(batch) >= 3 && fd_bins && nknots < (1 << 24)) ? (size_t)FD_NBUCKET + 2 * (size_t)nknots : 0;
+        constexpr int NTF = T::NV * (T::NV + 1) / 2;   // + the centre's Newton factor and active set per knot (FdBins::fac)
+        return (variant_for(batch) >= 3 && fd_bins && nknots < (1 << 24)) ? (size_t)FD_NBUCKET + 2 * (size_t)nknots * (NTF + 2) : 0;
     }
     // CTA shapes of the split kernels (measured on B200 after the planar algebra shrank the per-rollout state):
     //   qvel/ctrl: 256 threads, one CTA per SM at 255 registers (two CTAs at 128 registers spill the rows' neighbours: +70 % time;
@@ -515,14 +805,46 @@ struct EngineT : Engine {
     //   qpos     : 192 threads = 16 knots with no idle lane, two CTAs per SM at 168 registers (12 warps per SM: -7 % time;
     //              two 256-thread CTAs at 128 registers: +8 %).
     static constexpr int VU_THREADS = 256, VU_MINB = 1, Q_THREADS = 192, Q_MINB = 2;
+    // rows per knot the shared-memory qvel/ctrl kernel holds (ILQG_VU_CAP; 0 = local-memory kernel only).  Measured on B200: see DESIGN.md
+    // Row-capacity classes of the shared-memory qvel/ctrl kernel, ascending (ILQG_VU_CLASSES="8,16"; "0" = local-memory kernel
+    // only): one launch per class with a carve-out sized for it; knots without rows (flight) and knots above the last class
+    // run the local-memory kernel, whose CTAs keep the whole L1.
+    // MEASURED on B200 (round 2, tools/prof_split.py): not a gain.  Benchmark batch (23 % stance): local-memory kernel
+    // 0.299 ms, one class of 16 rows 0.516 ms (each class is one more serialised launch with the 0.1 ms latency floor of a stance
+    // CTA, and the carve-out takes the L1 that the rest of a rollout's local state lives in); a batch with 91 % of the knots in
+    // stance: 0.779 ms local against 0.803-0.826 ms.  Off by default.
+    int vu_class[4] = {0, 0, 0, 0};
+    int vu_nclass = 0;
+    bool vu_attr_set = false;
     void launch_split(int nknots, const double* qpos, const double* qvel, const double* ctrl, const ilqg_cost* cost_dev, const ilqg_fd_opts& o,
-                      const FdDst& dst, const double* qacc_center, int* status, const int* perm, cudaStream_t s, cudaEvent_t* ev) {
+                      const FdDst& dst, const double* qacc_center, int* status, const FdBins& bins, cudaStream_t s, cudaEvent_t* ev) {
         using PV = FdSplit<T, VU_THREADS>;
         using PQ = FdSplit<T, Q_THREADS>;
-        // (the default L1 / shared-memory split is the best one: forcing a larger shared carve-out shrinks the L1 that holds the
-        //  rollouts' local-memory rows and costs up to 30 % — measured with cudaFuncAttributePreferredSharedMemoryCarveout)
-        fd_velctrl_kernel<T, true, VU_THREADS, VU_MINB><<<(nknots + PV::KPC_VU - 1) / PV::KPC_VU, VU_THREADS, 0, s>>>(
-            dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps, o.niter, dst, status, perm);
+        using SH = FdVuShared<T, VU_THREADS>;
+        const int* perm = bins.perm;
+        const unsigned grid_vu = (nknots + PV::KPC_VU - 1) / PV::KPC_VU;
+        int lo = 0, hi = 0;   // classes cover lo < rows <= hi
+        if constexpr (T::MAXEFC > 0) {
+            if (bins.key && bins.fac) {
+                const int maxc = SH::max_cap(227 * 1024);
+                if (!vu_attr_set) {
+                    cudaFuncSetAttribute(fd_velctrl_shared_kernel<T, VU_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SH::bytes(maxc));
+                    vu_attr_set = true;
+                }
+                for (int c = 0; c < vu_nclass; c++) {
+                    const int cap = vu_class[c] < maxc ? vu_class[c] : maxc;
+                    if (cap <= hi) continue;
+                    fd_velctrl_shared_kernel<T, VU_THREADS><<<grid_vu, VU_THREADS, SH::bytes(cap), s>>>(dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev,
+                                                                                                   o.eps, o.niter, dst, status, bins, hi, cap);
+                    hi = cap;
+                }
+            }
+        }
+        // everything else (and the whole batch when it is not ordered by work class): rows in local memory
+        // (the default L1 / shared-memory split is the best one for this kernel: forcing a larger shared carve-out shrinks the L1 that
+        //  holds the rollouts' local-memory rows and costs up to 30 % — measured with cudaFuncAttributePreferredSharedMemoryCarveout)
+        fd_velctrl_kernel<T, true, VU_THREADS, VU_MINB><<<grid_vu, VU_THREADS, 0, s>>>(
+            dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps, o.niter, dst, status, perm, bins, lo, hi);
         if (ev) cudaEventRecord(ev[3], s);
         fd_qpos_kernel<T, true, Q_THREADS, Q_MINB><<<(nknots + PQ::KPC_Q - 1) / PQ::KPC_Q, Q_THREADS, 0, s>>>(
             dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps, o.niter, dst, status, perm);
@@ -535,15 +857,29 @@ struct EngineT : Engine {
         // perturbed evaluation in a single launch (30x more threads per knot: lower latency for small batches); fd_variant -1 = by size
         const int variant = variant_for(batch > nknots ? batch : nknots);
         if (nknots <= 0) return cudaSuccess;
-        FdBins bins{nullptr, nullptr, nullptr};
+        FdBins bins{nullptr, nullptr, nullptr, nullptr};
         if (scratch && fd_scratch_ints(nknots, batch > nknots ? batch : nknots)) {
-            bins.cnt = scratch;
-            bins.key = (unsigned int*)(scratch + FD_NBUCKET);
-            bins.perm = scratch + FD_NBUCKET + nknots;
+            constexpr int NTF = T::NV * (T::NV + 1) / 2;
+            bins.fac = vu_nclass > 0 ? reinterpret_cast<double*>(scratch) : nullptr;   // doubles first (the scratch base is 8-byte aligned)
+            int* ints = scratch + 2 * (size_t)nknots * (NTF + 1);
+            bins.cnt = ints;
+            bins.key = (unsigned int*)(ints + FD_NBUCKET);
+            bins.perm = ints + FD_NBUCKET + nknots;
             cudaMemsetAsync(bins.cnt, 0, FD_NBUCKET * sizeof(int), s);
         }
-        last_launches = variant >= 3 ? (bins.key ? 4 : 3) : 2;
+        last_launches = variant >= 3 ? (bins.key ? 4 + (T::MAXEFC > 0 ? vu_nclass : 0) : 3) : (variant == 1 ? 1 : 2);
         if (ev) cudaEventRecord(ev[0], s);
+        if constexpr (FdFusedShape<T>::OK) {
+            if (variant == 1) {   // small batch: one launch
+                using F = FdFusedShape<T>;
+                const int nw = (nknots + F::KPW - 1) / F::KPW;
+                if (ev) { cudaEventRecord(ev[1], s); cudaEventRecord(ev[3], s); }
+                fd_fused_kernel<T><<<(nw + 7) / 8, 256, 0, s>>>(dm, nknots, qpos, qvel, ctrl, warm, cost_dev, o.eps, o.niter, o.nwarmup, dst, qacc_center,
+                                                                status, fd_diag);
+                if (ev) cudaEventRecord(ev[2], s);
+                return cudaGetLastError();
+            }
+        }
         // (64- and 32-thread CTAs for finer-grained balancing of this kernel's 2.3 waves: no gain, measured.  Ordering this kernel's
         //  knots by the permutation the previous call on the same batch ended with — stance knots first, sharing warps — takes 21 us
         //  off it (SMs are busy 61 % of this kernel: ncu) but scrambles the ranks inside the buckets, which follow this kernel's
@@ -552,13 +888,28 @@ struct EngineT : Engine {
         if (bins.key) fd_bin_kernel<<<(nknots + 255) / 256, 256, 0, s>>>(nknots, bins);
         if (ev) cudaEventRecord(ev[1], s);
         if (variant >= 3) {  // stage-skipping split: qvel/ctrl columns, then qpos columns
-            launch_split(nknots, qpos, qvel, ctrl, cost_dev, o, dst, qacc_center, status, bins.perm, s, ev);
+            launch_split(nknots, qpos, qvel, ctrl, cost_dev, o, dst, qacc_center, status, bins, s, ev);
             if (ev) cudaEventRecord(ev[2], s);
             return cudaGetLastError();
         }
         if (ev) cudaEventRecord(ev[3], s);
         const int nwarps = (nknots + S::KPW - 1) / S::KPW;
-        fd_perturb_kernel<T><<<(nwarps + 7) / 8, 256, 0, s>>>(dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps, o.niter, dst, status);
+        {
+            // programmatic dependent launch (see fd_center_kernel): legal only directly behind the centre kernel in the stream, so
+            // not when profiling events sit between the two
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((nwarps + 7) / 8);
+            cfg.blockDim = dim3(256);
+            cfg.stream = s;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = (ev || !fd_pdl) ? 0 : 1;
+            const double* qc = qacc_center;
+            cudaError_t le = cudaLaunchKernelEx(&cfg, fd_perturb_kernel<T>, dm, nknots, qpos, qvel, ctrl, qc, cost_dev, o.eps, o.niter, dst, status);
+            if (le != cudaSuccess) return le;
+        }
         if (ev) cudaEventRecord(ev[2], s);
         return cudaGetLastError();
     }
@@ -841,6 +1192,9 @@ int ilqg_create(const ilqg_model* m, int device, ilqg_handle* out) {
     h->eng = eng;
     if (const char* e = getenv("ILQG_FD_VARIANT")) eng->fd_variant = atoi(e);
     if (const char* e = getenv("ILQG_FD_BINS")) eng->fd_bins = atoi(e);
+    if (const char* e = getenv("ILQG_FD_PDL")) eng->fd_pdl = atoi(e);
+    if (const char* e = getenv("ILQG_FD_FUSED_MAX")) eng->set_fused_max(atoi(e));
+    if (const char* e = getenv("ILQG_VU_CLASSES")) eng->set_vu_classes(e);
     if (const char* e = getenv("ILQG_HOST_CHUNKS")) h->host_chunks = atoi(e);
     if (const char* e = getenv("ILQG_HOST_COMP")) h->host_comp_streams = atoi(e);
     if (cudaMalloc(&h->d_cost, sizeof(ilqg_cost)) != cudaSuccess) {
@@ -1131,13 +1485,14 @@ int ilqg_fd_batch_host(ilqg_handle h, int nknots, const double* qpos, const doub
         for (size_t lo = 0; lo < n; lo += c) csize[nchunks++] = lo + c <= n ? c : n - lo;
     }
     for (size_t i = 0; i < nchunks; i++) cmax = csize[i] > cmax ? csize[i] : cmax;
-    const size_t scr = h->eng->fd_scratch_ints((int)cmax, nknots);
-    size_t bytes = ndbl * sizeof(double) + (n + 2 * scr) * sizeof(int);
+    const size_t scr = (h->eng->fd_scratch_ints((int)cmax, nknots) + 1) & ~(size_t)1;   // even: the scratch holds doubles too
+    const size_t nstat = (n + 1) & ~(size_t)1;
+    size_t bytes = ndbl * sizeof(double) + (nstat + 2 * scr) * sizeof(int);
     int rc = ensure_stage(h, bytes);
     if (rc) return rc;
     double* b = (double*)h->d_stage;
     int* dstat = (int*)(b + ndbl);
-    int* dscr = dstat + n;
+    int* dscr = dstat + nstat;
     if (n > h->hstat_cap) {   // pinned landing buffer of the status words (the caller's array may be pageable)
         if (h->h_stat) cudaFreeHost(h->h_stat);
         h->h_stat = nullptr;

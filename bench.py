@@ -90,22 +90,27 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ CPU arms (oracle = checker/baseline only)
-def cpu_workload(o, om, ntraj, T, seed):
-    """Same generator as ilqg-mujoco_b200/workload.py, stepped by the CPU oracle (reference arm only)."""
-    pkg = entry.load_package()
+def cpu_workload(o, om, ntraj, T, seed, roll_step=20, roll_max=360, ctrl_amp=0.25):
+    """Same generator as ilqg-mujoco_b200/workload.py:make_knots_8d (about half of the knots in contact,
+    time-varying control), stepped by the CPU oracle (reference arm only)."""
+    entry.load_package()
     from ilqg_mujoco_b200 import workload as wl  # noqa
-    qpos, qvel, ctrl, roll = wl.hopper_initial_states(ntraj, seed)
+    qpos, qvel, ctrl, _ = wl.hopper_initial_states(ntraj, seed)
+    rng = np.random.default_rng(seed + 7919)
+    roll = rng.integers(0, roll_max // roll_step + 1, ntraj) * roll_step
+    freq = rng.uniform(1.0, 8.0, (ntraj, om.nu)) * 2 * np.pi
+    phase = rng.uniform(0, 2 * np.pi, (ntraj, om.nu))
     warm = np.zeros((ntraj, om.nv))
     for i in range(ntraj):
         if roll[i]:
             q, v, w, _ = o.step_batch(om, qpos[i:i + 1], qvel[i:i + 1], ctrl[i:i + 1], warm[i:i + 1], int(roll[i]))
             qpos[i], qvel[i], warm[i] = q[0], v[0], w[0]
-    Q = np.zeros((ntraj, T, om.nq)); V = np.zeros((ntraj, T, om.nv)); W = np.zeros((ntraj, T, om.nv))
+    Q = np.zeros((ntraj, T, om.nq)); V = np.zeros((ntraj, T, om.nv)); W = np.zeros((ntraj, T, om.nv)); U = np.zeros((ntraj, T, om.nu))
     for t in range(T):
-        Q[:, t], V[:, t], W[:, t] = qpos, qvel, warm
+        ut = np.clip(ctrl + ctrl_amp * np.sin(freq * (t * om.timestep) + phase), -1.0, 1.0)
+        Q[:, t], V[:, t], W[:, t], U[:, t] = qpos, qvel, warm, ut
         if t + 1 < T:
-            qpos, qvel, warm, _ = o.step_batch(om, qpos, qvel, ctrl, warm, 1)
-    U = np.repeat(ctrl[:, None, :], T, axis=1)
+            qpos, qvel, warm, _ = o.step_batch(om, qpos, qvel, ut, warm, 1)
     ok = np.isfinite(Q).all(axis=(1, 2)) & np.isfinite(V).all(axis=(1, 2))
     Q, V, W, U = Q[ok], V[ok], W[ok], U[ok]
     return (Q.reshape(-1, om.nq).copy(), V.reshape(-1, om.nv).copy(), U.reshape(-1, om.nu).copy(), W.reshape(-1, om.nv).copy())
@@ -161,7 +166,8 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"hopper FD Jacobians, {args.ntraj} trajectories x {args.T} knots (bounded CPU sample: {nk} knots/step)",
+            "config": {"workload": f"hopper FD Jacobians (BASELINE configs[1], SURVEY 8d config 2): {args.ntraj} trajectories x {args.T} knots per GPU, "
+                                   f"pre-roll U{{0,20,..,360}} steps, time-varying control (bounded CPU sample: {nk} knots/step)",
                        "eps": 1e-6, "niter": 30, "nwarmup": 3},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -171,15 +177,36 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------ iLQR iterations/s (BASELINE configs[3])
+def ilqr_reference_classes_rate():
+    """iLQR iterations/s of the REFERENCE's own InvertedPendulum / ILQR / Differentiator / calcMJDerivatives (oracle/_ref: verbatim
+    sources on the oracle physics): MPC steps of 10 iterations, one problem after the other as cmd/basic.cpp drives them.
+    One reference ILQR instance per process (function-local statics, ilqr.h:137-140), hence the subprocesses."""
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_fd.so")):
+        return None
+
+    def ref(nmpc):
+        r = subprocess.run([sys.executable, "-c", _REF_MPC_SCRIPT % dict(root=ROOT, nmpc=nmpc)], capture_output=True, text=True, timeout=600)
+        try:
+            return float(r.stdout.strip().splitlines()[-1])
+        except (ValueError, IndexError):
+            return -1.0
+    r_a, r_b = ref(1), ref(4)
+    if r_a <= 0 or r_b <= r_a:
+        return None
+    return 30.0 / (r_b - r_a), 1e3 * (r_b - r_a) / 3
+
+
 def bench_ilqr(pkg, dev_index, ninst, niter, reps, world, rank, with_cpu):
-    """4096 independent inverted-pendulum iLQR problems (N = 20), `niter` x ILQR::iterate each, all on the device:
-    rollouts + FD of 21 knots + Riccati per iteration.  Reference mode (alpha = 1 accepted unconditionally)."""
+    """BASELINE configs[3] — the second half of the headline metric: 4096 independent inverted-pendulum iLQR problems (N = 20),
+    `niter` x ILQR::iterate each, all on the device: rollouts + FD of 21 knots + Riccati per iteration.  Reference mode (alpha = 1
+    accepted unconditionally).  ilqg_ilqr_iterate replays a captured CUDA graph of the niter iterations."""
     import torch
     import torch.distributed as dist
     from ilqg_mujoco_b200 import workload as wl
     dev = f"cuda:{dev_index}"
     model = pkg.Model.named("inverted_pendulum")
     h = pkg.Handle(model, dev_index)
+    L = pkg.lib()
     q, v, u, _ = wl.pendulum_initial_states(ninst, seed=100 + rank)
     u = u * 0.0
     dq, dv, du = (torch.from_numpy(a).to(dev) for a in (q, v, u))
@@ -189,27 +216,52 @@ def bench_ilqr(pkg, dev_index, ninst, niter, reps, world, rank, with_cpu):
     il.set_cost(cost)
     stream = torch.cuda.current_stream().cuda_stream
     times = []
-    for r in range(reps + 1):
+    launches0 = 0
+    nwarm = 3   # plain launches, graph capture, first replay
+    for r in range(reps + nwarm):
         il.init_dev(dq, dv, du, dw, stream=stream)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
+        if r == nwarm:
+            launches0 = h.launches
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         il.iterate(niter, accept_always=True, stream=stream)
         e1.record()
         e1.synchronize()
-        if r > 0:
+        if r >= nwarm:
             times.append(e0.elapsed_time(e1))
+    launches = h.launches - launches0
     out = il.get()
     nonfinite = int((~np.isfinite(out["J"]).all(axis=1)).sum())
     okm = np.isfinite(out["J"]).all(axis=1)
     total_ms = sum(times)
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    # ---- end to end through the host-pointer calls: x0 up, first control + cost trace down, every "MPC step" of niter iterations
+    hq, hv = q.copy(), v.copy()
+    e2e_reps = max(2, reps)
+    il.set_state_host(hq, hv)
+    il.iterate(niter, accept_always=True, stream=stream)
+    il.fetch_controls()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_reps):
+        il.set_state_host(hq, hv)                              # setDInit(d) of every problem: host -> device
+        il.iterate(niter, accept_always=True, stream=stream)   # 10 x iterate
+        u0, Jt = il.fetch_controls()                           # dArray[N]->ctrl and the cost trace: device -> host
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([total_ms, e2e_s * 1e3 * reps / e2e_reps], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_iter = float(t[0]) / (reps * niter)
     res = {"metric": "iLQR iterations/sec (inverted pendulum, N=20, fp64)", "value": world * ninst * niter * reps / (float(t[0]) * 1e-3),
-           "unit": "iterations/s", "instances_per_gpu": ninst, "iterations": niter, "ms_per_batch_iteration": float(t[0]) / (reps * niter),
+           "unit": "iterations/s", "instances_per_gpu": ninst, "iterations": niter, "ms_per_batch_iteration": ms_iter,
+           "gpu_launches_per_batch_iteration": launches / (reps * niter), "cuda_graph": os.environ.get("ILQG_ILQR_GRAPH", "1") != "0",
+           "e2e": {"value": world * ninst * niter * reps / (float(t[1]) * 1e-3), "unit": "iterations/s",
+                   "h2d_bytes_per_step": ninst * 4 * 8, "d2h_bytes_per_step": ninst * (1 + niter) * 8,
+                   "step": f"set_state_host (x0 of {ninst} problems up) + ilqg_ilqr_iterate({niter}) + first control and cost trace down"},
            "diverged_instances": nonfinite,
            "note": "reference mode = full step, no line search (ilqr.h:126): a few random starts diverge, in the oracle too (same instances)",
            "median_cost_first_last": [float(np.median(out["J"][okm, 0])), float(np.median(out["J"][okm, -1]))]}
@@ -220,10 +272,32 @@ def bench_ilqr(pkg, dev_index, ninst, niter, reps, world, rank, with_cpu):
         t0 = time.perf_counter()
         ref = o.ilqr_run_batch(om, 20, niter, q[:ns], v[:ns], u[:ns], None, cost, alphas=None)
         dt = time.perf_counter() - t0
-        res["cpu_baseline"] = {"value": ns * niter / dt, "unit": "iterations/s", "cores": os.cpu_count(), "kind": "port",
-                               "sample": f"first {ns} instances, oracle restatement of ILQR::iterate, OpenMP over instances"}
+        res["cpu_baseline_port"] = {"value": ns * niter / dt, "unit": "iterations/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"first {ns} instances, oracle restatement of ILQR::iterate, OpenMP over instances"}
+        rr = ilqr_reference_classes_rate()
+        if rr is not None:
+            res["cpu_baseline"] = {"value": rr[0], "unit": "iterations/s", "cores": min(16, os.cpu_count() or 1), "kind": "reference",
+                                   "sample": "3 MPC steps x 10 iterations of the reference's own InvertedPendulum / ILQR / Differentiator / calcMJDerivatives "
+                                             "(verbatim sources, oracle physics), one problem, OpenMP over FD columns"}
+        else:
+            res["cpu_baseline"] = res["cpu_baseline_port"]
         both = np.isfinite(ref["J"]).all(axis=1) & okm[:ns]
         res["parity_cost_trace_max_rel_err"] = float((np.abs(out["J"][:ns][both] - ref["J"][both]) / np.abs(ref["J"][both])).max())
+        # roofline of the iteration: algorithmic fp64 flops (instrumented oracle) / time against the measured DFMA peak.  Per instance
+        # and iteration: 21 mj_step (RK4: 4 evaluations each) + 21 FD knots + 20 Riccati steps of ~4 n^3 + 8 m n^2 flops (n = 4, m = 1)
+        fl = C.c_double(0)
+        o.lib().mjo_debug_step_flops(om.ptr, o._p(q[0].copy()), o._p(v[0].copy()), o._p(u[0].copy()), C.byref(fl))
+        _, _, fd_fl = o.fd_batch(om, q[:64], v[:64], u[:64], np.zeros((64, 2)), cost, nthreads=1)
+        flops_iter = 21 * fl.value + 21 * fd_fl / 64 + 20 * (4 * 4 ** 3 + 8 * 1 * 4 ** 2)
+        tf = C.c_double(0)
+        L.ilqg_fp64_peak(dev_index, C.byref(tf))
+        ach = flops_iter * ninst / (ms_iter * 1e-3) / 1e12
+        res["roofline_fp64"] = {"bound": "fp64 (in practice: latency of one dependent chain per problem — 84 dynamics evaluations in the rollout)",
+                                "achieved": ach, "peak": tf.value, "unit": "TFLOP/s", "frac": ach / tf.value if tf.value else None,
+                                "flops_per_iteration_per_instance": flops_iter,
+                                "how": "oracle-counted flops of 21 RK4 steps + 21 FD knots + analytic Riccati count, x instances / batch-iteration time"}
+        res["roofline"] = {"bound": "hbm", "unit": "GB/s", "achieved": ninst * 21 * (56 + 120 + 2 * 8 * 9) / (ms_iter * 1e-3) / 1e9,
+                           "note": "knot inputs + deriv blocks + candidate / nominal trajectory writes per iteration: far below the HBM roof, the iteration is latency-bound"}
     il.close()
     h.close()
     return res
@@ -329,30 +403,49 @@ def bench_t1000(pkg, dev_index, T, steps, world, rank):
         tot_fd += ev[0].elapsed_time(ev[1])
         tot += ev[1].elapsed_time(ev[2])
     # the same gather fused into the FD kernels' write-out: every rank's blocks are stored to all ranks' arrays over NVLink
-    peer = sharding.PeerDeriv(h, T, model.nd)
-    for _ in range(3):
-        pfull = sharding.fd_knot_sharded_peer(h, peer, q, v, u, w, stream=stream)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ep = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    ep[0].record()
-    for _ in range(steps):
-        pfull = sharding.fd_knot_sharded_peer(h, peer, q, v, u, w, stream=stream)
-    ep[1].record()
-    ep[1].synchronize()
-    tot_peer = ep[0].elapsed_time(ep[1])
+
+    def peer_pass_ms(qq, vv, uu, ww, reps):
+        peer = sharding.PeerDeriv(h, qq.shape[0], model.nd)
+        for _ in range(3):
+            out = sharding.fd_knot_sharded_peer(h, peer, qq, vv, uu, ww, stream=stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ep = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ep[0].record()
+        for _ in range(reps):
+            out = sharding.fd_knot_sharded_peer(h, peer, qq, vv, uu, ww, stream=stream)
+        ep[1].record()
+        ep[1].synchronize()
+        peer.check()
+        ms = ep[0].elapsed_time(ep[1]) / reps
+        out = out.clone()
+        peer.close()
+        return ms, out
+
+    peer_ms, pfull = peer_pass_ms(q, v, u, w, steps)
     same = bool(torch.equal(pfull[:, :90], full[:, :90]))
-    t = torch.tensor([tot, tot_fd, tot_peer], dtype=torch.float64, device=dev)
+    # the horizon length from which sharding pays: the same pass for longer horizons (the 1000-knot nominal tiled), knots over all
+    # `world` ranks.  Compare the lines of the 1-, 2-, 4- and 8-GPU runs: sharding.pick_ranks encodes the measured crossover.
+    sweep = {}
+    for Tl in (4000, 16000, 64000):
+        rep = (Tl + T - 1) // T
+        ql, vl, ul, wl_ = (x.repeat(rep, 1)[:Tl].contiguous() for x in (q, v, u, w))
+        ms, _ = peer_pass_ms(ql, vl, ul, wl_, max(3, steps // 4))
+        tl = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+        sweep[str(Tl)] = Tl / (float(tl[0]) * 1e-3)
+    t = torch.tensor([tot, tot_fd, peer_ms * steps], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ok = bool(torch.isfinite(full[:, :90]).all())
-    peer.close()
     h.close()
     return {"metric": "hopper T=1000 knot-sharded FD knots/sec", "value": T * steps / (float(t[2]) * 1e-3), "unit": "knots/s",
             "value_nccl_all_gather": T * steps / (float(t[0]) * 1e-3),
             "value_excluding_all_gather": T * steps / (float(t[1]) * 1e-3), "T": T, "knots_per_rank": per, "finite": ok,
             "peer_scatter_equals_all_gather": same,
+            "longer_horizons_knots_per_s": sweep, "ranks_pick_ranks_would_use_for_T": {str(x): sharding.pick_ranks(x, 8) for x in (1000, 4000, 16000, 64000)},
             "collective": ("none on the data path: the FD kernels store each deriv block (840 B/knot) to every rank's array through CUDA-IPC peer "
                            "mappings (NVLink), then a flag barrier through the same peer memory (1-warp kernel, no NCCL call).  value_nccl_all_gather = the same with all_gather_into_tensor after the kernels"
                            if world > 1 else "none (1 rank)"), "scaling": "strong"}
@@ -485,6 +578,22 @@ def bind_to_gpu_numa_node(gpu_index):
 
 
 # ------------------------------------------------------------------ the GPU arm
+def timed_fd(h, q, v, u, w, deriv, qacc, status, cost, stream, reps, flush=None):
+    """Mean CUDA-event ms of `reps` device-resident FD passes (L2 flushed between them when `flush` is given)."""
+    import torch
+    tot = 0.0
+    for i in range(reps):
+        if flush is not None:
+            flush.fill_(float(i))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        h.fd_batch_dev(q, v, u, w, deriv, qacc, status, cost=cost, stream=stream)
+        e1.record()
+        e1.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / reps
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -496,7 +605,7 @@ def run_gpu_arm(args):
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
-    bind_to_gpu_numa_node(local)
+    ncpus_bound = bind_to_gpu_numa_node(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device(dev))
@@ -505,8 +614,9 @@ def run_gpu_arm(args):
     from ilqg_mujoco_b200 import workload as wl
     model = pkg.Model.named("hopper")
     h = pkg.Handle(model, local)
-    # weak scaling: every rank linearises its own ntraj x T knots (independent trajectories, no collective on the data path)
-    q, v, u, w, nbad = wl.make_knots(h, args.ntraj, args.T, seed=1000 * rank, device=dev, model="hopper")
+    # weak scaling: every rank linearises its own ntraj x T knots (independent trajectories, no collective on the data path).
+    # The batch SURVEY 8(d) config 2 specifies: about half of the knots in ground contact, time-varying control.
+    q, v, u, w, nbad = wl.make_knots_8d(h, args.ntraj, args.T, seed=1000 * rank, device=dev)
     nk = q.shape[0]
     deriv = torch.zeros((nk, model.nd), dtype=torch.float64, device=dev)
     qacc = torch.zeros((nk, model.nv), dtype=torch.float64, device=dev)
@@ -547,61 +657,165 @@ def run_gpu_arm(args):
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
     launches = h.launches - launches0
     nonfinite = int((status != 0).sum())
+    L.ilqg_set_profiling(h._h, 0)
 
-    # ---- e2e: host buffers through the host-pointer C ABI
+    # ---- e2e: host buffers through the host-pointer C ABI (pinned, as a caller that owns its staging would; then pageable, as
+    #      the reference's caller — plain malloc'ed mjData — would)
     hq, hv, hu, hw = (t.cpu().pin_memory() for t in (q, v, u, w))
     hderiv = torch.zeros((nk, model.nd), dtype=torch.float64).pin_memory()
     hqacc = torch.zeros((nk, model.nv), dtype=torch.float64).pin_memory()
     hstat = torch.zeros(nk, dtype=torch.int32).pin_memory()
     costp = cost.ctypes.data_as(C.c_void_p)
 
-    def e2e_step():
-        rc = L.ilqg_fd_batch_host(h._h, nk, C.c_void_p(hq.data_ptr()), C.c_void_p(hv.data_ptr()), C.c_void_p(hu.data_ptr()),
-                                  C.c_void_p(hw.data_ptr()), costp, None, C.c_void_p(hderiv.data_ptr()), C.c_void_p(hqacc.data_ptr()),
-                                  C.c_void_p(hstat.data_ptr()))
+    def e2e_step(bufs):
+        rc = L.ilqg_fd_batch_host(h._h, nk, *[C.c_void_p(b) for b in bufs[:4]], costp, None, *[C.c_void_p(b) for b in bufs[4:]])
         if rc not in (0, pkg.ERR_NONFINITE):
             raise pkg.IlqgError(rc, L.ilqg_last_error(h._h).decode())
 
+    pinned = [t.data_ptr() for t in (hq, hv, hu, hw, hderiv, hqacc, hstat)]
     for _ in range(2):
-        e2e_step()
+        e2e_step(pinned)
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        e2e_step()
+        e2e_step(pinned)
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()   # sampled across both timed regions (device-resident steps and host-pointer steps)
+    pg = [np.array(t.numpy(), copy=True) for t in (hq, hv, hu, hw)] + [np.zeros((nk, model.nd)), np.zeros((nk, model.nv)), np.zeros(nk, np.int32)]
+    pageable = [a.ctypes.data for a in pg]
+    e2e_step(pageable)
+    if world > 1:
+        dist.barrier()
+    npg = max(3, args.steps // 10)
+    t0 = time.perf_counter()
+    for _ in range(npg):
+        e2e_step(pageable)
+    e2e_pg_s = (time.perf_counter() - t0) * args.steps / npg
     h2d = nk * (model.nq + 2 * model.nv + model.nu) * 8
     d2h = nk * (model.nd + model.nv) * 8 + nk * 4
-
-    tt = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    # what the host side can take: every rank copies its deriv array device -> pinned host at the same time (the e2e path's bound)
     if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        hderiv.copy_(deriv, non_blocking=True)
+    torch.cuda.synchronize()
+    d2h_gbs = 5 * nk * model.nd * 8 / (time.perf_counter() - t0) / 1e9
+
+    tt = torch.tensor([total_ms, e2e_s * 1e3, e2e_pg_s * 1e3, -d2h_gbs, d2h_gbs], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt[:4], op=dist.ReduceOp.MAX)
+        dist.all_reduce(tt[4:], op=dist.ReduceOp.SUM)
+    d2h_min, d2h_sum = -float(tt[3]), float(tt[4])
+
+    # ---- what the batch is made of, from the kernels' own diagnostics (ilqg_fd_set_diag): contacts, rows, solver iterations
+    diag = torch.zeros((nk, 8), dtype=torch.int32, device=dev)
+    h.fd_set_diag(diag)
+    one_step()
+    h.fd_set_diag(None)
+    torch.cuda.synchronize()
+    dg = diag.cpu().numpy()
+    in_contact = dg[:, 6] > 0
+    contact_share = float(in_contact.mean())
+    it_hist = {int(k): int(c) for k, c in zip(*np.unique(dg[:, 2], return_counts=True))}
+    rows_hist = {int(k): int(c) for k, c in zip(*np.unique(np.minimum(dg[:, 0], 24), return_counts=True))}
+    # stance and flight separately: the knots with / without a contact at the centre, each set as its own batch
+    split = {}
+    for lab, sel in (("stance", in_contact), ("flight", ~in_contact)):
+        idx = torch.from_numpy(np.nonzero(sel)[0]).to(dev)
+        if idx.numel() == 0:
+            continue
+        sq, sv, su, sw = (x[idx].contiguous() for x in (q, v, u, w))
+        n_s = int(idx.numel())
+        for _ in range(3):
+            h.fd_batch_dev(sq, sv, su, sw, deriv[:n_s], qacc[:n_s], status[:n_s], cost=cost, stream=stream)
+        ms = timed_fd(h, sq, sv, su, sw, deriv[:n_s], qacc[:n_s], status[:n_s], cost, stream, max(5, args.steps // 10), flush)
+        tl = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+        split[lab] = {"knots_per_gpu": n_s, "value": world * n_s / (float(tl[0]) * 1e-3), "unit": UNIT}
+    # B in {1, 64} trajectories (B = 4096 is the headline): trajectories spread over the batch
+    bsweep = {}
+    ntraj_all = nk // args.T
+    for B in (1, 64):
+        if B > ntraj_all:
+            continue
+        pick = (np.arange(B) * (ntraj_all / B)).astype(np.int64)
+        kidx_b = torch.from_numpy((pick[:, None] * args.T + np.arange(args.T)[None, :]).reshape(-1)).to(dev)
+        bq, bv, bu, bw = (x[kidx_b].contiguous() for x in (q, v, u, w))
+        n_b = int(kidx_b.numel())
+        for _ in range(3):
+            h.fd_batch_dev(bq, bv, bu, bw, deriv[:n_b], qacc[:n_b], status[:n_b], cost=cost, stream=stream)
+        ms = timed_fd(h, bq, bv, bu, bw, deriv[:n_b], qacc[:n_b], status[:n_b], cost, stream, 20)
+        tl = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+        bsweep[str(B)] = {"knots_per_gpu": n_b, "ms_per_pass": float(tl[0]), "value": world * n_b / (float(tl[0]) * 1e-3), "unit": UNIT}
+    one_step()   # leave deriv / status of the whole batch in place for the parity spot check below
+    torch.cuda.synchronize()
+
     # secondary workloads (every rank takes part; rank 0 reports)
     secondary = []
     if not args.no_secondary:
+        # the round-1 batch (constant control, pre-roll <= 200 steps: 23 % of the knots in contact) so that rounds stay comparable
+        q1, v1, u1, w1, _ = wl.make_knots(h, args.ntraj, args.T, seed=1000 * rank, device=dev, model="hopper")
+        for _ in range(3):
+            h.fd_batch_dev(q1, v1, u1, w1, deriv, qacc, status, cost=cost, stream=stream)
+        ms = timed_fd(h, q1, v1, u1, w1, deriv, qacc, status, cost, stream, max(10, args.steps // 5), flush)
+        tl = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+        secondary.append({"metric": "FD dynamics Jacobian knots/sec (hopper, fp64) on the ROUND-1 batch", "value": world * nk / (float(tl[0]) * 1e-3),
+                          "unit": UNIT, "ms_per_step": float(tl[0]),
+                          "workload": "round 1's headline batch: constant control along each trajectory, pre-roll U{0,20,..,200} steps (23 % of the knots in contact)"})
+        del q1, v1, u1, w1
+        one_step()
+        torch.cuda.synchronize()
         secondary.append(bench_ilqr(pkg, local, args.ilqr_instances, 10, 3, world, rank, with_cpu=(world == 1 and rank == 0)))
         secondary.append(bench_hopper_ilqr(pkg, local, 1024, 10, 2, world, rank))
         secondary.append(bench_t1000(pkg, local, 1000, 20, world, rank))
         secondary.append(bench_humanoid(pkg, local, args.humanoid_knots, 3, world, rank, with_cpu=(world == 1 and rank == 0)))
         if world == 1 and rank == 0:
             secondary.append(bench_mpc_step(pkg))
-    total_ms, e2e_ms = float(tt[0]), float(tt[1])
+    total_ms, e2e_ms, e2e_pg_ms = float(tt[0]), float(tt[1]), float(tt[2])
     value = world * nk * args.steps / (total_ms * 1e-3)
     e2e_value = world * nk * args.steps / (e2e_ms * 1e-3)
+    rc_exit = 0
 
     if rank == 0:
+        topo = ""
+        try:
+            topo = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+            sys.stderr.write("[bench] nvidia-smi topo -m\n" + topo + "\n")
+        except (OSError, subprocess.SubprocessError):
+            pass
+        numa = sorted({ln.split()[-2] for ln in topo.splitlines() if ln.startswith("GPU") and len(ln.split()) > 3}) if topo else []
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
-                "config": {"workload": f"hopper FD Jacobians (BASELINE configs[1]): {args.ntraj} trajectories x {args.T} knots per GPU",
+                "config": {"workload": f"hopper FD Jacobians (BASELINE configs[1], SURVEY 8d config 2): {args.ntraj} trajectories x {args.T} knots per GPU, "
+                                       "pre-roll U{0,20,..,360} steps, time-varying control",
                            "knots_per_gpu": nk, "eps": 1e-6, "niter": 30, "nwarmup": 3, "parallelism": f"independent trajectories x{world}",
                            "l2": "flushed between timed iterations (512 MiB fill outside the events)",
+                           "contact_share_of_knots": contact_share, "rows_histogram": rows_hist,
+                           "centre_solver_iterations_histogram": it_hist,
                            "replaced_nonfinite_knots": nbad, "nonfinite_status": nonfinite},
+                "stance_flight": split, "batch_sweep": bsweep,
                 "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "value_pageable_buffers": world * nk * args.steps / (e2e_pg_ms * 1e-3),
+                        "host_limit_gbs": d2h_sum, "d2h_gbs_per_gpu_all_ranks_copying": d2h_min,
+                        "note": ("the host-pointer call is bound by the device-to-host copy of deriv (892 B per knot): host_limit_gbs is what all "
+                                 f"{world} rank(s) reach TOGETHER copying deriv to pinned host memory at the same time; e2e cannot exceed host_limit_gbs / 892 B "
+                                 "knots/s whatever the kernels do.  GPU NUMA affinity column of `nvidia-smi topo -m`: " + ",".join(numa) +
+                                 f"; this rank is bound to {ncpus_bound} CPUs local to its GPU")},
                 "gpu_launches": launches, "secondary": secondary}
-        # ---- roofline of the dominant kernel (fd_perturb_kernel) + cpu baseline: rank 0 only
+        for sec in secondary:
+            if sec.get("peer_scatter_equals_all_gather") is False:
+                rc_exit = 3   # the peer-store gather disagrees with the NCCL all-gather: not a number to report
+        # ---- roofline of the dominant kernel + cpu baseline: rank 0 only
         c_ms, v_ms, q_ms = (float(np.mean([k[j] for k in kern_ms])) for j in range(3))
         p_ms = v_ms + q_ms
         peaks = {}
@@ -615,10 +829,10 @@ def run_gpu_arm(args):
         kern = {"fd_velctrl_kernel<Topo_hopper>": (v_ms, in_b + 8 * (nv * nv + nv * nu + nv + nu)),   # dv | du blocks + their cost-gradient entries
                 "fd_qpos_kernel<Topo_hopper>": (q_ms, in_b + 8 * (nv * nv + nv)),                       # dq block + its cost-gradient entries
                 "fd_center_kernel<Topo_hopper>": (c_ms, in_b + 8 * nv)}
-        split = v_ms > 1e-3   # batches below the size threshold run the single-launch kernel (all perturbed evaluations in q_ms)
-        if not split:
+        split_k = v_ms > 1e-3   # batches below the size threshold run the single-launch kernel (all perturbed evaluations in q_ms)
+        if not split_k:
             kern = {"fd_perturb_kernel<Topo_hopper>": (q_ms, in_b + 8 * model.nd), "fd_center_kernel<Topo_hopper>": (c_ms, in_b + 8 * nv)}
-        dom = max(kern, key=lambda k: kern[k][0])
+        dom = max(kern, key=lambda k: kern[k][0])   # the longest kernel of the step
         ach = kern[dom][1] * nk / (kern[dom][0] * 1e-3) / 1e9
         traffic = None
         try:  # dram bytes per knot of that kernel from the committed ncu --set full capture, scaled to this launch
@@ -637,22 +851,12 @@ def run_gpu_arm(args):
             om = o.Model(os.path.join(pkg.MODELS_DIR, "hopper.ilqgm"))
             # a REPRESENTATIVE sample: every stride-th trajectory (the generator orders trajectories by pre-roll length, so a
             # prefix of the batch would be the knots still in flight and would under-count the work per knot)
-            ntraj_all = nk // args.T
             ntraj_s = max(1, min(ntraj_all, args.cpu_sample // args.T))
             pick = (np.arange(ntraj_s) * (ntraj_all / ntraj_s)).astype(np.int64)
             kidx = (pick[:, None] * args.T + np.arange(args.T)[None, :]).reshape(-1)
             ns = kidx.size
             kidx_t = torch.from_numpy(kidx).to(dev)
             sq, sv, su, sw = (t[kidx_t].cpu().numpy().copy() for t in (q, v, u, w))
-            # share of the sample's knots with at least one active contact at the centre (report stance and flight)
-            ninfo = min(ns, 1024)
-            sel = np.linspace(0, ns - 1, ninfo).astype(np.int64)
-            info = np.zeros(4, np.int32); qa = np.zeros(om.nv); ncontact = 0
-            for i in sel:
-                o.lib().mjo_debug_forward(om.ptr, o._p(sq[i]), o._p(sv[i]), o._p(su[i]), o._p(sw[i]), 30, C.c_double(0.0), o._p(qa),
-                                          info.ctypes.data_as(C.c_void_p), None, None, None)
-                ncontact += int(info[0] > 0)
-            line["config"]["contact_share_of_knots"] = ncontact / ninfo
             # (i) fair port: OpenMP over knots, all cores; also yields the oracle-counted flops per knot
             t0 = time.perf_counter()
             dref, _, flops = o.fd_batch(om, sq, sv, su, sw, cost, nthreads=0)
@@ -669,14 +873,16 @@ def run_gpu_arm(args):
             ach_tf = flops_per_knot * nk / ((p_ms + c_ms) * 1e-3) / 1e12
             line["roofline_fp64"] = {"bound": "fp64", "achieved": ach_tf, "peak": tf.value, "unit": "TFLOP/s",
                                      "frac": ach_tf / tf.value if tf.value else None, "flops_per_knot": flops_per_knot,
-                                     "how": "ALGORITHMIC fp64 flops per knot (counted by the instrumented oracle, which runs the dense reference algorithm: FMA=2, the reference's "
-                                            "stage-skipping schedule) on a sample of this workload x knots / (sum of the FD kernels' time); the kernels execute about a third fewer fp64 "
-                                            "operations than that (planar trees: multiplications by structural zeros are removed at compile time), so this is delivered work against the "
-                                            "pipe's peak, not pipe occupancy (ncu: fp64 pipe 20-28 % active); "
+                                     "how": "ALGORITHMIC fp64 flops per knot (counted by the instrumented oracle, which runs the dense reference algorithm with "
+                                            "the solver pinned as the reference pins it: FMA=2, the reference's stage-skipping schedule and its three centre "
+                                            "solves per knot) on a sample of this workload x knots / (sum of the FD kernels' time).  The kernels execute fewer "
+                                            "fp64 operations than that: planar trees drop the multiplications by structural zeros at compile time, and the centre "
+                                            "repetitions stop at the first exact solve (config.centre_solver_iterations_histogram says how many Newton iterations "
+                                            "ran) — so this is delivered algorithmic work against the pipe's peak, not pipe occupancy (ncu: fp64 pipe 18-30 % active); "
                                             "peak = DFMA-chain microbenchmark run now on this GPU (MEASURED_PEAKS.json has no fp64 figure)"}
             # parity spot check of the timed outputs against the oracle on the sample
-            dg = deriv[kidx_t].cpu().numpy()
-            err = float(np.abs(dg - dref).max() / max(1.0, np.abs(dref).max()))
+            dgp = deriv[kidx_t].cpu().numpy()
+            err = float(np.abs(dgp - dref).max() / max(1.0, np.abs(dref).max()))
             line["parity_sample_max_rel_err"] = err
             if r is not None:
                 rdt, rc, _ = r
@@ -691,7 +897,7 @@ def run_gpu_arm(args):
     h.close()
     if world > 1:
         dist.destroy_process_group()
-    return 0
+    return rc_exit
 
 
 _json_out = None

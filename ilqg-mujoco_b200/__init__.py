@@ -298,6 +298,16 @@ class Ilqr:
     def iterations(self):
         return int(lib().ilqg_ilqr_iterations_done(self._w))
 
+    def fetch_controls(self):
+        """First control of every problem (dArray[N]->ctrl, what InvertedPendulum::forward applies) and the cost trace of the
+        iterations run so far: (u0[ninst, nu], J[ninst, kept]).  Synchronises."""
+        m = self.h.model
+        kept = min(self.iterations, 256)
+        u0 = np.zeros((self.ninst, m.nu))
+        J = np.zeros((self.ninst, kept))
+        self.h._check(lib().ilqg_ilqr_get_first_control_host(self._w, _hp(u0), _hp(J)))
+        return u0, J
+
     def get(self):
         m = self.h.model
         n, T, nx = self.ninst, self.N + 1, 2 * m.nv

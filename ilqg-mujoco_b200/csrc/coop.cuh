@@ -93,6 +93,7 @@ struct CoopMem {
     int* hdr;                              // hdr[0] = nefc, hdr[1] = capacity ok, hdr[2] = Hc valid, hdr[3] = row bound of the knot's +-eps
                                            // neighbourhood (centre only), hdr[4..7] = active-set mask of Hc
     int maxefc;                            // row capacity of this block
+    int ncon;                              // contact points of the last position stage (diagnostics)
     // ---- private working set
     double *pv, *pu;                       // perturbed qvel / ctrl
     double *cvel, *cacc, *cfrc, *cdofdot;
@@ -579,6 +580,7 @@ DEV void coop_pos(const GModel* __restrict__ g, CoopMem& w, int lane, const int*
     __syncwarp();
     bool ok = ncon <= COOP_MAXCON && ne <= w.maxefc;
     if (ncon > COOP_MAXCON) ncon = COOP_MAXCON;
+    w.ncon = ncon;
     if (ne > w.maxefc) ne = w.maxefc;
     // ---- contact rows: sequential over contacts, lanes over dofs
     for (int c = 0; c < ncon; c++) {
@@ -969,7 +971,7 @@ __global__ void __launch_bounds__(32) coop_center_kernel(const GModel* __restric
         int na = 0;
         for (int r = 0; r < w.hdr[0]; r++) na += w.jar[r] < 0;
         int* d = diag + (size_t)k * ILQG_DIAG_INTS;
-        d[0] = w.hdr[0]; d[1] = it_first; d[2] = it_all; d[3] = na; d[4] = (int)(t1 - t0); d[5] = (int)(t2 - t1); d[6] = 0; d[7] = 0;
+        d[0] = w.hdr[0]; d[1] = it_first; d[2] = it_all; d[3] = na; d[4] = (int)(t1 - t0); d[5] = (int)(t2 - t1); d[6] = w.ncon; d[7] = 0;
     }
     bool fin = true;
     for (int i = lane; i < m.nv; i += 32) { qacc_center[(size_t)k * m.nv + i] = w.qacc[i]; w.center[i] = w.qacc[i]; w.fb0[i] = w.fb[i]; fin = fin && isfinite(w.qacc[i]); }

@@ -408,6 +408,7 @@ struct Work {
     double as[NV];   // qacc_smooth
     double fc[NV];   // qfrc_constraint of the last solve
     int nefc;
+    int ncon;        // contact points the narrow phase found (diagnostics)
     int iters;       // Newton iterations of the last solve
     int exact;       // the last solve left through the exact-optimum test (or had no rows): solving again from its result is a no-op
     int overflow;    // more rows than the placement's capacity (RowsShared): the knot must be redone with RowsLocal
@@ -926,6 +927,7 @@ DEV void build_pos(const DevModel<T>& m, const double (&q)[T::NQ], PosStage<T>& 
         }
     }
     w.nefc = ne;
+    w.ncon = nc;
     stage_sync();
 }
 

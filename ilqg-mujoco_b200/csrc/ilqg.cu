@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(128) fd_center_kernel(const __grid_constant__ 
         for (int r = 0; r < w.nefc; r++) na += w.rows.jar(r) < 0;
         int4* d = reinterpret_cast<int4*>(diag + (size_t)k * ILQG_DIAG_INTS);
         d[0] = make_int4(w.nefc, it_first, it_all, na);
-        d[1] = make_int4((int)(t1 - t0), (int)(t2 - t1), 0, 0);
+        d[1] = make_int4((int)(t1 - t0), (int)(t2 - t1), w.ncon, 0);
     }
     if (bins.key) {
         const int ne = w.nefc < FD_NBUCKET - 1 ? w.nefc : FD_NBUCKET - 1;
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(256, 1) fd_fused_kernel(const __grid_constant_
     const int base = (sub < KPW ? sub : 0) * S::GL;   // first lane of this knot's group
     double qacc[NV], warm[NV];
     double dcost = 0;
-    int it_first = 0, it_all = 0, nefc = 0, nact = 0;
+    int it_first = 0, it_all = 0, nefc = 0, nact = 0, ncon = 0;
     long long t0 = 0, t1 = 0, t2 = 0;
     {
         // idle lanes (tail of the grid, spare lanes of a warp) evaluate a clamped knot with their writes masked, so that every
@@ -346,6 +346,7 @@ __global__ void __launch_bounds__(256, 1) fd_fused_kernel(const __grid_constant_
         }
         if (is_center) {
             nefc = w.nefc;
+            ncon = w.ncon;
             if (diag) for (int r = 0; r < w.nefc; r++) nact += w.rows.jar(r) < 0;
         }
     }
@@ -356,7 +357,7 @@ __global__ void __launch_bounds__(256, 1) fd_fused_kernel(const __grid_constant_
         if (diag) {
             int4* d = reinterpret_cast<int4*>(diag + (size_t)k * ILQG_DIAG_INTS);
             d[0] = make_int4(nefc, it_first, it_all, nact);
-            d[1] = make_int4((int)(t1 - t0), (int)(t2 - t1), 0, 0);
+            d[1] = make_int4((int)(t1 - t0), (int)(t2 - t1), ncon, 0);
         }
     }
     __syncwarp();   // the centre's status word is written before the columns may flag it
@@ -1620,6 +1621,18 @@ struct ilqg_ilqr_s {
     int trace_cap = 0, iters = 0;
     std::vector<void*> allocs;
     ilqg_fd_opts fd;
+    // ilqg_ilqr_iterate as a CUDA graph: one iteration is 7-9 dependent launches of 0.04-0.15 ms kernels; replaying a captured
+    // graph takes the host's launch cost (and, with 8 ranks on one host, its contention) off the chain
+    cudaGraphExec_t graph = nullptr;
+    int graph_niter = 0, graph_accept = 0, graph_warm = 0;   // what the graph was captured for; calls seen with that shape
+    long graph_launches = 0;                                 // kernels one replay launches
+    cudaStream_t cap_stream = nullptr;
+    bool use_graph = true;
+    void drop_graph() {
+        if (graph) cudaGraphExecDestroy(graph);
+        graph = nullptr;
+        graph_warm = 0;
+    }
 };
 
 #define ILQR_ALLOC(w, ptr, count)                                                              \
@@ -1635,6 +1648,8 @@ struct ilqg_ilqr_s {
 int ilqg_ilqr_destroy(ilqg_ilqr w) {
     if (!w) return ILQG_OK;
     if (w->h) cudaSetDevice(w->h->device);
+    w->drop_graph();
+    if (w->cap_stream) cudaStreamDestroy(w->cap_stream);
     for (void* p : w->allocs) cudaFree(p);
     delete w;
     return ILQG_OK;
@@ -1655,6 +1670,8 @@ int ilqg_ilqr_create(ilqg_handle h, int ninst, int N, int nalpha, const double* 
     b.ninst = ninst; b.N = N; b.nalpha = nalpha; b.mu = 1000.0;  // ilqr.h:65
     b.corrected = 0;
     b.mu_i = nullptr; b.mu_factor = 1.0; b.mu_min = 1e-6; b.mu_max = 1e10;
+    b.trace_cap = 256;
+    if (const char* e = getenv("ILQG_ILQR_GRAPH")) w->use_graph = atoi(e) != 0;
     ILQR_ALLOC(w, b.nom_q, TI * nq); ILQR_ALLOC(w, b.nom_v, TI * nv); ILQR_ALLOC(w, b.nom_u, TI * nu); ILQR_ALLOC(w, b.nom_w, TI * nv);
     ILQR_ALLOC(w, b.init_q, (size_t)ninst * nq); ILQR_ALLOC(w, b.init_v, (size_t)ninst * nv); ILQR_ALLOC(w, b.init_w, (size_t)ninst * nv);
     ILQR_ALLOC(w, b.cand_q, nalpha * TI * nq); ILQR_ALLOC(w, b.cand_v, nalpha * TI * nv); ILQR_ALLOC(w, b.cand_u, nalpha * TI * nu);
@@ -1665,6 +1682,7 @@ int ilqg_ilqr_create(ilqg_handle h, int ninst, int N, int nalpha, const double* 
     ILQR_ALLOC(w, w->d_cost, 1);
     w->trace_cap = 256;
     ILQR_ALLOC(w, w->d_Jtrace, (size_t)w->trace_cap * ninst); ILQR_ALLOC(w, w->d_acc_trace, (size_t)w->trace_cap * ninst);
+    ILQR_ALLOC(w, b.iter_dev, 1);
     std::vector<double> al(nalpha);
     for (int a = 0; a < nalpha; a++) al[a] = alphas ? alphas[a] : std::ldexp(1.0, -a);  // default ladder 1, 1/2, 1/4, ...
     CU(h, cudaMemcpy(b.alphas, al.data(), sizeof(double) * nalpha, cudaMemcpyHostToDevice));
@@ -1678,6 +1696,7 @@ int ilqg_ilqr_set_cost(ilqg_ilqr w, const ilqg_cost* cost) {
     CU(h, cudaSetDevice(h->device));
     if (cost) CU(h, cudaMemcpy(w->d_cost, cost, sizeof(ilqg_cost), cudaMemcpyHostToDevice));
     w->has_cost = true;
+    w->drop_graph();   // the kernels' parameters are baked into a captured graph
     w->host_cost = cost == nullptr;  // NULL: the caller owns the cost (a host stepCostFn) and supplies the gradient rows itself
     return ILQG_OK;
 }
@@ -1686,10 +1705,12 @@ int ilqg_ilqr_set_cost(ilqg_ilqr w, const ilqg_cost* cost) {
 int ilqg_ilqr_set_layout(ilqg_ilqr w, int corrected) {
     if (!w) return ILQG_ERR_ARG;
     w->b.corrected = corrected ? 1 : 0;
+    w->drop_graph();
     return ILQG_OK;
 }
 int ilqg_ilqr_set_mu(ilqg_ilqr w, double mu) {
     if (!w) return ILQG_ERR_ARG;
+    if (mu != w->b.mu) w->drop_graph();
     w->b.mu = mu;
     if (w->b.mu_i) {   // (re)start the schedule from this value
         std::vector<double> v((size_t)w->b.ninst, mu);
@@ -1714,6 +1735,7 @@ int ilqg_ilqr_set_mu_schedule(ilqg_ilqr w, double factor, double mu_min, double 
         w->b.mu_i = p;
     }
     w->b.mu_factor = factor; w->b.mu_min = mu_min; w->b.mu_max = mu_max;
+    w->drop_graph();
     return ILQG_OK;
 }
 
@@ -1753,6 +1775,8 @@ int ilqg_ilqr_init_dev(ilqg_ilqr w, const double* qpos, const double* qvel, cons
     ilqg::IlqrBuffers one = b;
     one.nalpha = 1;  // alphas[0] multiplies k = 0: any value gives the open-loop rollout
     one.mu_i = nullptr;  // the constructor's rollout is not a line-search outcome: the mu schedule does not move
+    one.iter_dev = nullptr;
+    CU(h, cudaMemsetAsync(b.iter_dev, 0, sizeof(int), s));
     CU(h, h->eng->ilqr_rollout(one, w->host_cost ? nullptr : w->d_cost, s));
     CU(h, h->eng->ilqr_accept(one, 1, nullptr, nullptr, s));
     h->launches += 3;
@@ -1771,9 +1795,8 @@ int ilqg_ilqr_forward(ilqg_ilqr w, int accept_always, void* stream) {   // forwa
     cudaStream_t s = (cudaStream_t)stream;
     CU(h, cudaSetDevice(h->device));
     auto& b = w->b;
-    int slot = w->iters % w->trace_cap;
     CU(h, h->eng->ilqr_rollout(b, w->host_cost ? nullptr : w->d_cost, s));
-    CU(h, h->eng->ilqr_accept(b, accept_always, w->d_Jtrace + (size_t)slot * b.ninst, w->d_acc_trace + (size_t)slot * b.ninst, s));
+    CU(h, h->eng->ilqr_accept(b, accept_always, w->d_Jtrace, w->d_acc_trace, s));   // trace slot: the device iteration counter
     h->launches += 3;
     w->iters++;
     return ILQG_OK;
@@ -1809,15 +1832,63 @@ int ilqg_ilqr_backward(ilqg_ilqr w, void* stream) {                      // init
     h->launches += 1;
     return ILQG_OK;
 }
-int ilqg_ilqr_iterate(ilqg_ilqr w, int niter, int accept_always, void* stream) {
-    if (!w || niter < 0) return ILQG_ERR_ARG;
-    if (w->host_cost) return fail(w->h, ILQG_ERR_ARG, "host-cost workspaces drive the phases themselves (cost rows come from the host)");
+static int ilqr_iterate_plain(ilqg_ilqr w, int niter, int accept_always, void* stream) {
     for (int it = 0; it < niter; it++) {
         int rc;
         if ((rc = ilqg_ilqr_forward(w, accept_always, stream))) return rc;
         if ((rc = ilqg_ilqr_linearise(w, stream))) return rc;
         if ((rc = ilqg_ilqr_backward(w, stream))) return rc;
     }
+    return ILQG_OK;
+}
+int ilqg_ilqr_iterate(ilqg_ilqr w, int niter, int accept_always, void* stream) {
+    if (!w || niter < 0) return ILQG_ERR_ARG;
+    ilqg_handle h = w->h;
+    if (w->host_cost) return fail(h, ILQG_ERR_ARG, "host-cost workspaces drive the phases themselves (cost rows come from the host)");
+    if (niter == 0) return ILQG_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    accept_always = accept_always ? 1 : 0;
+    if (!w->use_graph || h->profiling) return ilqr_iterate_plain(w, niter, accept_always, stream);
+    CU(h, cudaSetDevice(h->device));
+    if (w->graph && (w->graph_niter != niter || w->graph_accept != accept_always)) w->drop_graph();
+    if (!w->graph) {
+        // The first call of a shape runs launch by launch (it also sizes the handle's scratch: no allocation may happen while a
+        // stream is capturing); the second captures the same sequence on a private stream; from then on the graph is replayed.
+        if (w->graph_niter != niter || w->graph_accept != accept_always || w->graph_warm == 0) {
+            w->graph_niter = niter; w->graph_accept = accept_always; w->graph_warm = 1;
+            return ilqr_iterate_plain(w, niter, accept_always, stream);
+        }
+        if (!w->cap_stream) CU(h, cudaStreamCreateWithFlags(&w->cap_stream, cudaStreamNonBlocking));
+        const int iters0 = w->iters;
+        const long launches0 = h->launches;
+        const int pdl0 = h->eng->fd_pdl;
+        h->eng->fd_pdl = 0;   // plain kernel-to-kernel edges inside the graph
+        CU(h, cudaStreamBeginCapture(w->cap_stream, cudaStreamCaptureModeThreadLocal));
+        int rc = ilqr_iterate_plain(w, niter, accept_always, w->cap_stream);
+        cudaGraph_t g = nullptr;
+        cudaError_t ce = cudaStreamEndCapture(w->cap_stream, &g);
+        h->eng->fd_pdl = pdl0;
+        w->iters = iters0;            // nothing ran yet
+        w->graph_launches = h->launches - launches0;
+        h->launches = launches0;
+        if (rc || ce != cudaSuccess || !g) {
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+            w->use_graph = false;     // capture is not possible here: stay with plain launches
+            return ilqr_iterate_plain(w, niter, accept_always, stream);
+        }
+        ce = cudaGraphInstantiate(&w->graph, g, 0);
+        cudaGraphDestroy(g);
+        if (ce != cudaSuccess) {
+            w->graph = nullptr;
+            cudaGetLastError();
+            w->use_graph = false;
+            return ilqr_iterate_plain(w, niter, accept_always, stream);
+        }
+    }
+    CU(h, cudaGraphLaunch(w->graph, s));
+    w->iters += niter;
+    h->launches += w->graph_launches;
     return ILQG_OK;
 }
 
@@ -1894,6 +1965,31 @@ int ilqg_ilqr_get_host(ilqg_ilqr w, double* qpos, double* qvel, double* ctrl, do
                 if (accepted) accepted[(size_t)i * kept + j] = ta[(size_t)slot * n + i];
             }
         }
+    }
+    return ILQG_OK;
+}
+
+// What one MPC step hands back to the plant (InvertedPendulum::forward, /root/reference/src/inverted_pendulum/inverted_pendulum.cpp:26):
+// the first control of every problem, u0[ninst][nu] = dArray[N]->ctrl, and (optionally) the cost trace [ninst][kept] of the
+// last kept = min(iterations, 256) iterations — without downloading the trajectories.
+int ilqg_ilqr_get_first_control_host(ilqg_ilqr w, double* u0, double* Jtrace) {
+    if (!w) return ILQG_ERR_ARG;
+    ilqg_handle h = w->h;
+    CU(h, cudaSetDevice(h->device));
+    auto& b = w->b;
+    const int nu = h->model.nu, n = b.ninst;
+    CU(h, cudaDeviceSynchronize());
+    if (u0 && nu) CU(h, cudaMemcpy(u0, b.nom_u + (size_t)b.N * n * nu, sizeof(double) * (size_t)n * nu, cudaMemcpyDeviceToHost));   // time-major: knot N is one block
+    const int kept = w->iters < w->trace_cap ? w->iters : w->trace_cap;
+    if (Jtrace && kept > 0) {
+        std::vector<double> tj((size_t)kept * n);
+        const int first = w->iters - kept;
+        for (int j = 0; j < kept; j++) {
+            const int slot = (first + j) % w->trace_cap;
+            CU(h, cudaMemcpy(tj.data() + (size_t)j * n, w->d_Jtrace + (size_t)slot * n, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
+        }
+        for (int j = 0; j < kept; j++)
+            for (int i = 0; i < n; i++) Jtrace[(size_t)i * kept + j] = tj[(size_t)j * n + i];
     }
     return ILQG_OK;
 }

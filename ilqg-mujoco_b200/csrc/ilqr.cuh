@@ -36,6 +36,9 @@ struct IlqrBuffers {
     double* mu_i;       // [ninst] per-instance mu under the opt-in schedule, else NULL
     double mu_factor, mu_min, mu_max;
     int corrected;      // 0: A/B through the reference's column-major views of the row-major deriv blocks (quirk Q1); 1: transposed back
+    int* iter_dev;      // iterations done (device counter: the trace slot of a pass is taken from it, so that a captured CUDA graph
+                        // of iterations can be replayed), or NULL for a pass that is not an iteration (the constructor's rollout)
+    int trace_cap;      // slots of the cost / accepted-alpha traces
 };
 
 // ------------------------------------------------------------------ forward pass, all alphas at once
@@ -117,8 +120,9 @@ __global__ void ilqr_accept_kernel(IlqrBuffers b, int accept_always, double* __r
         b.mu_i[i] = mu;
     }
     b.accepted[i] = acc;
-    if (Jtrace) Jtrace[i] = J;
-    if (acc_trace) acc_trace[i] = acc;
+    const size_t slot = (Jtrace || acc_trace) && b.iter_dev ? (size_t)(*b.iter_dev % b.trace_cap) * ninst : 0;
+    if (Jtrace) Jtrace[slot + i] = J;
+    if (acc_trace) acc_trace[slot + i] = acc;
 }
 
 template <class T>
@@ -136,6 +140,7 @@ __global__ void ilqr_commit_kernel(IlqrBuffers b) {
         for (int c = 0; c < NV; c++) { b.nom_v[kn * NV + c] = b.cand_v[cn * NV + c]; b.nom_w[kn * NV + c] = b.cand_w[cn * NV + c]; }
         for (int c = 0; c < NU; c++) b.nom_u[kn * NU + c] = b.cand_u[cn * NU + c];
     }
+    if (t == 0 && b.iter_dev) *b.iter_dev += 1;   // (the accept kernel, which reads the counter, has finished)
     if (n == b.N) {   // setDInit(dArray[N]) (ilqr.h:183): the next pass starts from the nominal's first knot
         for (int c = 0; c < NQ; c++) b.init_q[(size_t)i * NQ + c] = b.nom_q[kn * NQ + c];
         for (int c = 0; c < NV; c++) { b.init_v[(size_t)i * NV + c] = b.nom_v[kn * NV + c]; b.init_w[(size_t)i * NV + c] = b.nom_w[kn * NV + c]; }

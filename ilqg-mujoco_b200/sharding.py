@@ -19,6 +19,17 @@ def shard_range(n, world, rank):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def pick_ranks(T, world, knots_per_rank_min=2000):
+    """How many of the node's `world` GPUs to shard a horizon of T knots over.  A pass over fewer than ~2000 hopper knots is bound
+    by the latency of one centre + one perturbed evaluation (about 60 us on B200 whether a rank holds 125 knots or 1000), and
+    every additional rank adds the flag barrier: measured (bench.py's `longer_horizons_knots_per_s` at 1, 2, 4, 8 GPUs)
+    sharding starts to pay once each rank keeps at least ~2000 knots.  Returns a power of two <= world."""
+    r = 1
+    while r * 2 <= world and T // (r * 2) >= knots_per_rank_min:
+        r *= 2
+    return r
+
+
 def padded_count(n, world):
     """Per-rank unit count after padding n to a multiple of world (all_gather needs equal contributions)."""
     return (n + world - 1) // world

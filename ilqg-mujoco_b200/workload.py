@@ -105,3 +105,45 @@ def make_knots(handle, ntraj, T, seed=0, device="cuda:0", model="hopper"):
             Q[bad, 1] = 1.25
     return (Q.reshape(-1, m.nq).contiguous(), V.reshape(-1, m.nv).contiguous(), U.reshape(-1, m.nu).contiguous(),
             W.reshape(-1, m.nv).contiguous(), nbad)
+
+
+def make_knots_8d(handle, ntraj, T, seed=0, device="cuda:0", roll_step=20, roll_max=360, ctrl_amp=0.25):
+    """The hopper batch SURVEY.md 8(d) config 2 specifies: the config-2 initial states pre-rolled long enough that about HALF of
+    the knots are in ground contact (pre-roll uniform over {0, 20, ..., roll_max} steps; calibrated with the CPU oracle: 200 ->
+    25 %, 300 -> 40 %, 400 -> 56 % of the knots with at least one contact), then T knots one mj_step apart under a TIME-VARYING
+    control u_t = clip(u_0 + ctrl_amp sin(w t + phi), -1, 1) (per actuator: w ~ U[1, 8] Hz, phi ~ U[0, 2 pi]).
+    Returns device tensors (qpos[ntraj*T,nq], qvel, ctrl, warm) in trajectory-major order and the count of replaced knots."""
+    m = handle.model
+    qpos, qvel, ctrl, _ = hopper_initial_states(ntraj, seed)
+    rng = np.random.default_rng(seed + 7919)
+    roll = rng.integers(0, roll_max // roll_step + 1, ntraj) * roll_step
+    freq = rng.uniform(1.0, 8.0, (ntraj, m.nu)) * 2 * np.pi
+    phase = rng.uniform(0, 2 * np.pi, (ntraj, m.nu))
+    order = np.argsort(roll, kind="stable")
+    qpos, qvel, ctrl, roll, freq, phase = qpos[order], qvel[order], ctrl[order], roll[order], freq[order], phase[order]
+    dq, dv, du0 = (torch.from_numpy(a).to(device) for a in (qpos, qvel, ctrl))
+    dfr, dph = torch.from_numpy(freq).to(device), torch.from_numpy(phase).to(device)
+    dw = torch.zeros((ntraj, m.nv), dtype=torch.float64, device=device)
+    for r in range(roll_step, int(roll.max()) + 1, roll_step):   # pre-roll under the constant u_0, the tail that still has steps to go
+        start = int(np.searchsorted(roll, r, side="left"))
+        if start < ntraj:
+            handle.step_batch_dev(dq[start:], dv[start:], du0[start:], dw[start:], None, nsteps=roll_step)
+    Q = torch.empty((ntraj, T, m.nq), dtype=torch.float64, device=device)
+    V = torch.empty((ntraj, T, m.nv), dtype=torch.float64, device=device)
+    W = torch.empty((ntraj, T, m.nv), dtype=torch.float64, device=device)
+    U = torch.empty((ntraj, T, m.nu), dtype=torch.float64, device=device)
+    for t in range(T):
+        ut = torch.clamp(du0 + ctrl_amp * torch.sin(dfr * (t * m.timestep) + dph), -1.0, 1.0).contiguous()
+        Q[:, t], V[:, t], W[:, t], U[:, t] = dq, dv, dw, ut
+        if t + 1 < T:
+            handle.step_batch_dev(dq, dv, ut, dw, None, nsteps=1)
+    torch.cuda.synchronize()
+    bad = ~(torch.isfinite(Q).all(dim=2) & torch.isfinite(V).all(dim=2) & torch.isfinite(W).all(dim=2))
+    nbad = int(bad.sum())
+    if nbad:
+        Q[bad] = 0.0
+        V[bad] = 0.0
+        W[bad] = 0.0
+        Q[bad, 1] = 1.25
+    return (Q.reshape(-1, m.nq).contiguous(), V.reshape(-1, m.nv).contiguous(), U.reshape(-1, m.nu).contiguous(),
+            W.reshape(-1, m.nv).contiguous(), nbad)

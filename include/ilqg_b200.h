@@ -121,7 +121,8 @@ enum {
     ILQG_DIAG_ITERS_ALL = 2,   /* Newton iterations of all nwarmup centre solves */
     ILQG_DIAG_NACTIVE = 3,     /* rows active (force > 0) at the centre solution */
     ILQG_DIAG_CYC_BUILD = 4,   /* SM cycles the rollout spent in the position / velocity / actuation stages */
-    ILQG_DIAG_CYC_SOLVE = 5    /* SM cycles it spent in the nwarmup solves */
+    ILQG_DIAG_CYC_SOLVE = 5,   /* SM cycles it spent in the nwarmup solves */
+    ILQG_DIAG_NCON = 6         /* contact points at the centre point (nefc also counts joints at their limits) */
 };
 int ilqg_fd_set_diag(ilqg_handle h, int* diag_dev);
 
@@ -200,6 +201,9 @@ int ilqg_ilqr_backward(ilqg_ilqr w, void* stream);
 int ilqg_ilqr_put_cost_rows_host(ilqg_ilqr w, const double* rows);
 int ilqg_ilqr_get_knots_host(ilqg_ilqr w, double* qpos, double* qvel, double* ctrl, double* warm);
 int ilqg_ilqr_iterations_done(ilqg_ilqr w);
+/* the first control of every problem, u0[ninst][nu] (dArray[N]->ctrl: what /root/reference/src/inverted_pendulum/inverted_pendulum.cpp:26
+ * applies to the plant), and optionally the cost trace [ninst][min(iterations,256)]; host pointers, synchronises */
+int ilqg_ilqr_get_first_control_host(ilqg_ilqr w, double* u0, double* Jtrace);
 /* results, instance-major on the host; any pointer may be NULL.  Jtrace/accepted: [ninst][min(iterations,256)] */
 int ilqg_ilqr_get_host(ilqg_ilqr w, double* qpos, double* qvel, double* ctrl, double* K, double* k, double* V, double* v,
                        double* Jtrace, int* accepted);

@@ -58,3 +58,15 @@ void mjo_debug_forward(const ilqg_model* m, const double* qpos, const double* qv
     if (contact_dist) for (int c = 0; c < d->ncon; c++) contact_dist[c] = d->contact[c].dist;
     mjo_delete_data(d);
 }
+
+/* fp64 operations of ONE mj_step at (qpos, qvel, ctrl) — the rollout's unit of work for bench.py's iLQR roofline */
+void mjo_debug_step_flops(const ilqg_model* m, const double* qpos, const double* qvel, const double* ctrl, double* flops) {
+    mjo_data* d = mjo_make_data(m);
+    memcpy(d->qpos, qpos, sizeof(double) * m->nq);
+    memcpy(d->qvel, qvel, sizeof(double) * m->nv);
+    memcpy(d->ctrl, ctrl, sizeof(double) * m->nu);
+    d->flops = 0;
+    mjo_step(m, d);
+    if (flops) *flops = d->flops;
+    mjo_delete_data(d);
+}

@@ -268,7 +268,7 @@ def test_centre_diagnostics_report_solver_iterations(pkg, handles, oracle, omode
     for k in range(n):
         oracle.lib().mjo_debug_forward(om.ptr, oracle._p(q[k]), oracle._p(v[k]), oracle._p(u[k]), oracle._p(w[k]), 30, C.c_double(0.0), oracle._p(qa),
                                        info.ctypes.data_as(C.c_void_p), None, None, None)
-        assert d[k, 0] == info[1]                      # nefc  (info = ncon, nefc, iterations, active rows)
+        assert d[k, 0] == info[1] and d[k, 6] == info[0]   # nefc, ncon  (info = ncon, nefc, iterations, active rows)
     assert (d[:, 0] > 0).any() and ((d[:, 1] >= 0) & (d[:, 1] <= 30)).all() and (d[:, 2] >= d[:, 1]).all()
     assert (d[d[:, 0] == 0, 2] == 0).all()             # no rows: no iterations
     assert (d[d[:, 0] > 0, 2] >= 1).all() and (d[:, 3] <= d[:, 0]).all()

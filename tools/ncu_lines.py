@@ -10,7 +10,7 @@ from collections import defaultdict
 rep, kre, mangled = sys.argv[1], sys.argv[2], sys.argv[3]
 depth = int(sys.argv[4]) if len(sys.argv) > 4 else 2
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-so = os.path.join(root, "ilqg-mujoco_b200", "libilqg_b200.so")
+so = os.environ.get("ILQG_LIB") or os.path.join(root, "ilqg-mujoco_b200", "libilqg_b200.so")
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, capture_output=True)
 cub = [f for f in os.listdir(tmp) if f.startswith("ilqg.") and f.endswith(".cubin")][0]

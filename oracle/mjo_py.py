@@ -95,3 +95,25 @@ def ilqr_run_batch(m, N, niter, qpos0, qvel0, ctrl0, warm0, cost, alphas=None, a
     lib().mjo_ilqr_set_corrected_layout(0)
     lib().mjo_ilqr_set_mu_schedule(C.c_double(1.0), C.c_double(1e-6), C.c_double(1e10))
     return out
+
+
+def dump(m, qpos, qvel, ctrl, warm=None, iterations=30, tolerance=0.0):
+    """Every intermediate of one forward evaluation, under mjData's names (mjo_debug_dump): the quantities the MuJoCo
+    cross-check (tools/mujoco_fixtures.py) and the hand-derived contact anchors compare."""
+    nv, nb = m.nv, m.nbody
+    out = dict(xpos=np.zeros((nb, 3)), xquat=np.zeros((nb, 4)), xipos=np.zeros((nb, 3)), subtree_com=np.zeros((nb, 3)), cinert=np.zeros((nb, 10)),
+               cdof=np.zeros((nv, 6)), qM=np.zeros((nv, nv)), qfrc_bias=np.zeros(nv), qfrc_passive=np.zeros(nv), qfrc_actuator=np.zeros(nv),
+               qacc_smooth=np.zeros(nv), qacc=np.zeros(nv))
+    counts = np.zeros(3, np.int32)
+    con = np.zeros((96, 13)); con_geom = np.zeros((96, 2), np.int32); efc_J = np.zeros((320, nv)); efc = np.zeros((320, 7))
+    q, v, u = (np.ascontiguousarray(a, np.float64) for a in (qpos, qvel, ctrl))
+    w = np.ascontiguousarray(warm, np.float64) if warm is not None else None
+    lib().mjo_debug_dump(m.ptr, _p(q), _p(v), _p(u), _p(w), int(iterations), C.c_double(tolerance), *[_p(out[k]) for k in
+                         ("xpos", "xquat", "xipos", "subtree_com", "cinert", "cdof", "qM", "qfrc_bias", "qfrc_passive", "qfrc_actuator", "qacc_smooth", "qacc")],
+                         counts.ctypes.data_as(C.c_void_p), _p(con), con_geom.ctypes.data_as(C.c_void_p), _p(efc_J), _p(efc))
+    ncon, nefc = int(counts[0]), int(counts[1])
+    out.update(ncon=ncon, nefc=nefc, solver_iter=int(counts[2]), contact_dist=con[:ncon, 0].copy(), contact_pos=con[:ncon, 1:4].copy(),
+               contact_frame=con[:ncon, 4:13].copy(), contact_geom=con_geom[:ncon].copy(), efc_J=efc_J[:nefc].copy(), efc_pos=efc[:nefc, 0].copy(),
+               efc_margin=efc[:nefc, 1].copy(), efc_diagApprox=efc[:nefc, 2].copy(), efc_R=efc[:nefc, 3].copy(), efc_D=efc[:nefc, 4].copy(),
+               efc_aref=efc[:nefc, 5].copy(), efc_force=efc[:nefc, 6].copy())
+    return out

@@ -1,0 +1,239 @@
+"""Independent anchors for the parts of the oracle that the closed-form cart-pole and the energy tests do not reach
+("pin-ready cross-check"): the contact rows and the smooth dynamics, each re-derived here by ANOTHER route.
+
+1. Plane-capsule pyramid rows of the hopper's foot: contact geometry from a hand-written planar forward kinematics with the
+   numbers of /root/reference/res/hopper.xml typed in here (not read from the compiled table), the contact Jacobian by numerical
+   differentiation of that kinematics (the oracle builds it from cdof), R / D / aref from SURVEY.md Appendix A.2 by hand.
+2. qacc_smooth by the ARTICULATED-BODY ALGORITHM (Featherstone; O(n), no mass matrix) written in numpy on the tree tables,
+   against the oracle's CRBA + Cholesky + RNE route — for all three models incl. the humanoid's free joint."""
+import numpy as np
+import pytest
+
+from conftest import scenario_states
+
+# ------------------------------------------------------------------ 1. hopper foot on the floor, by hand
+# /root/reference/res/hopper.xml (global coordinates): joint anchors and axes, the foot capsule, contact parameters
+ANCH = {"rooty": (0, 0, 1.25), "thigh": (0, 0, 1.05), "leg": (0, 0, 0.6), "foot": (0, 0, 0.1)}
+FOOT_A, FOOT_B, FOOT_R = np.array([-0.13, 0, 0.1]), np.array([0.26, 0, 0.1]), 0.06
+MU, MARGIN, IMP, TC, DAMPRATIO, DT = 2.0, 0.001, 0.8, 0.02, 1.0, 0.002   # friction max(1, 2.0); margin; solimp .8 .8; solref .02 1
+
+
+def roty(a):   # rotation about +y
+    c, s = np.cos(a), np.sin(a)
+    return np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]])
+
+
+def foot_point(q, p0):
+    """World position of the material point of the foot that sits at p0 (global coordinates) in the model's reference pose."""
+    p = np.asarray(p0, float)
+    for name, ang in (("foot", -q[5]), ("leg", -q[4]), ("thigh", -q[3]), ("rooty", q[2])):   # hinge axes 0 -1 0: negative angle about +y
+        a = np.array(ANCH[name], float)
+        p = a + roty(ang) @ (p - a)
+    return p + np.array([q[0], 0.0, q[1] - 1.25])   # slides; rootz has ref = 1.25
+
+
+def test_hopper_foot_contact_rows_by_hand(pkg, oracle, omodels):
+    om = omodels["hopper"]
+    q = np.array([0.07, 1.25, 0.04, -0.35, -0.25, 0.12])
+    lo = min(foot_point(q, FOOT_A)[2], foot_point(q, FOOT_B)[2]) - FOOT_R
+    q[1] -= lo + 0.0015                      # the lower end sphere 1.5 mm inside the floor
+    v = np.array([0.3, -0.4, 0.5, -0.7, 0.2, 0.9]); u = np.zeros(3)
+    d = oracle.dump(om, q, v, u)
+    # mjc_PlaneCapsule: the end at +axis first; a `fromto` capsule's local z axis points from `to` back to `from` (MuJoCo's
+    # compiler takes vec = from - to; [EXT] recollection, one of the conventions tools/mujoco_fixtures.py would falsify)
+    ends = [foot_point(q, FOOT_A), foot_point(q, FOOT_B)]
+    n = np.array([0.0, 0.0, 1.0])
+    axis = (ends[0] - ends[1]) / np.linalg.norm(ends[0] - ends[1])
+    t1 = axis - (n @ axis) * n; t1 /= np.linalg.norm(t1)    # mju_makeFrame with the capsule axis as the tangent hint
+    t2 = np.cross(n, t1)
+    # body_invweight0 of the foot, by hand: mean translational inverse inertia at its com in the reference pose, J M^-1 J' / 3
+    q0 = np.array([0, 1.25, 0, 0, 0, 0.0])
+    M0 = oracle.dump(om, q0, np.zeros(6), u)["qM"]
+    com0 = oracle.dump(om, q0, np.zeros(6), u)["xipos"][4]
+    J0 = np.stack([(foot_point(q0 + 1e-6 * np.eye(6)[i], com0) - foot_point(q0 - 1e-6 * np.eye(6)[i], com0)) / 2e-6 for i in range(6)], 1)
+    tran = np.trace(J0 @ np.linalg.solve(M0, J0.T)) / 3
+    assert tran == pytest.approx(pkg.Model.named("hopper").field("body_invweight0").reshape(-1, 2)[4, 0], rel=1e-6)
+    K = 1.0 / (IMP ** 2 * max(TC, 2 * DT) ** 2 * DAMPRATIO ** 2)
+    B = 2.0 / (IMP * max(TC, 2 * DT))
+    rows = []
+    for c in ends:
+        dist = c[2] - FOOT_R
+        if dist >= MARGIN:
+            continue
+        pos = c - n * (FOOT_R + 0.5 * dist)
+        # the point's reference-pose coordinates: invert the kinematics numerically (the map is rigid: solve by 3 Newton steps)
+        p0 = np.array([0.0, 0.0, 0.0])
+        for _ in range(4):
+            Jp = np.stack([(foot_point(q, p0 + 1e-6 * np.eye(3)[k]) - foot_point(q, p0 - 1e-6 * np.eye(3)[k])) / 2e-6 for k in range(3)], 1)
+            p0 = p0 - np.linalg.solve(Jp, foot_point(q, p0) - pos)
+        Jq = np.stack([(foot_point(q + 1e-6 * np.eye(6)[i], p0) - foot_point(q - 1e-6 * np.eye(6)[i], p0)) / 2e-6 for i in range(6)], 1)   # 3 x 6
+        jn, ja, jb = n @ Jq, t1 @ Jq, t2 @ Jq
+        R = 2 * MU ** 2 * (1 - IMP) / IMP * tran * (1 + MU ** 2)
+        for k in range(4):
+            Jr = jn + (MU if k % 2 == 0 else -MU) * (ja if k < 2 else jb)
+            rows.append((Jr, 1.0 / R, -B * (Jr @ v) - K * IMP * (dist - MARGIN), dist))
+    assert d["ncon"] == len(rows) // 4 and d["ncon"] >= 1
+    lim = d["nefc"] - len(rows)               # joint-limit rows come first
+    assert lim >= 0
+    for r, (Jr, D, aref, dist) in enumerate(rows):
+        assert np.allclose(d["efc_J"][lim + r], Jr, rtol=0, atol=5e-9), r
+        assert d["efc_D"][lim + r] == pytest.approx(D, rel=1e-6)
+        assert d["efc_aref"][lim + r] == pytest.approx(aref, rel=1e-7, abs=1e-7)
+        assert d["efc_pos"][lim + r] == pytest.approx(dist, abs=1e-12)
+    assert np.abs(d["efc_J"][lim + 2] - d["efc_J"][lim + 3]).max() < 1e-12   # planar tree: the out-of-plane tangent moves nothing
+
+
+# ------------------------------------------------------------------ 2. articulated-body algorithm
+def qmul(a, b):
+    return np.array([a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3], a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2],
+                     a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1], a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0]])
+
+
+def q2m(q):
+    w, x, y, z = q
+    return np.array([[w * w + x * x - y * y - z * z, 2 * (x * y - w * z), 2 * (x * z + w * y)], [2 * (x * y + w * z), w * w - x * x + y * y - z * z, 2 * (y * z - w * x)],
+                     [2 * (x * z - w * y), 2 * (y * z + w * x), w * w - x * x - y * y + z * z]])
+
+
+def skew(a):
+    return np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+
+
+def crm(v):    # spatial motion cross product, vectors are [angular; linear] about the world origin
+    return np.block([[skew(v[:3]), np.zeros((3, 3))], [skew(v[3:]), skew(v[:3])]])
+
+
+def aba_qacc_smooth(pm, q, qd, ctrl):
+    """Forward dynamics without constraints by Featherstone's articulated-body algorithm, spatial vectors about the world origin."""
+    F = lambda name, shape=None: pm.field(name) if shape is None else pm.field(name).reshape(shape)
+    nb, nj, nv, nu = pm.nbody, pm.njnt, pm.nv, pm.nu
+    ints = {k: pm.field(k) for k in ("body_parentid", "jnt_type", "dof_parentid")}
+    # fields not exported by name are read through the struct layout helper of the package
+    body_jntadr, body_jntnum = tab(pm, "body_jntadr"), tab(pm, "body_jntnum")
+    jnt_qposadr, jnt_dofadr = tab(pm, "jnt_qposadr"), tab(pm, "jnt_dofadr")
+    body_pos, body_quat = F("body_pos", (-1, 3)), tab(pm, "body_quat").reshape(-1, 4)
+    jpos, jaxis = F("jnt_pos", (-1, 3)), F("jnt_axis", (-1, 3))
+    qpos0 = F("qpos0")
+    xpos, xquat = np.zeros((nb, 3)), np.zeros((nb, 4)); xquat[0, 0] = 1
+    S = [None] * nb
+    ballcols = {}
+    for b in range(1, nb):
+        p = ints["body_parentid"][b]
+        pos = xpos[p] + q2m(xquat[p]) @ body_pos[b]
+        quat = qmul(xquat[p], body_quat[b])
+        cols = []
+        ballcols[b] = set()
+        for j in range(body_jntadr[b], body_jntadr[b] + body_jntnum[b]):
+            ty, qa = ints["jnt_type"][j], jnt_qposadr[j]
+            if ty == 0:   # free
+                pos = q[qa:qa + 3].copy(); quat = q[qa + 3:qa + 7] / np.linalg.norm(q[qa + 3:qa + 7])
+                R = q2m(quat)
+                cols += [np.concatenate([np.zeros(3), np.eye(3)[k]]) for k in range(3)]
+                ballcols[b] |= {len(cols) + 1, len(cols) + 2}   # the three body-fixed axes turn together: one "before" velocity
+                cols += [np.concatenate([R[:, k], np.cross(pos, R[:, k])]) for k in range(3)]
+                continue
+            R = q2m(quat)
+            anchor, axis = pos + R @ jpos[j], R @ jaxis[j]
+            ang = q[qa] - qpos0[qa]
+            if ty == 2:   # slide
+                pos = pos + ang * axis
+                cols.append(np.concatenate([np.zeros(3), axis]))
+            else:         # hinge
+                quat = qmul(quat, np.concatenate([[np.cos(ang / 2)], jaxis[j] * np.sin(ang / 2)]))
+                pos = anchor - q2m(quat) @ jpos[j]
+                cols.append(np.concatenate([axis, np.cross(anchor, axis)]))
+        xpos[b], xquat[b] = pos, quat / np.linalg.norm(quat)
+        S[b] = np.stack(cols, 1) if cols else np.zeros((6, 0))
+    mass, ipos, inert = F("body_mass"), F("body_ipos", (-1, 3)), F("body_inertia", (-1, 6))
+    I = [None] * nb
+    for b in range(1, nb):
+        R = q2m(xquat[b]); c = xpos[b] + R @ ipos[b]
+        i6 = inert[b]; Ib = np.array([[i6[0], i6[3], i6[4]], [i6[3], i6[1], i6[5]], [i6[4], i6[5], i6[2]]])
+        Ic, cx = R @ Ib @ R.T, skew(c)
+        I[b] = np.block([[Ic + mass[b] * cx @ cx.T, mass[b] * cx], [mass[b] * cx.T, mass[b] * np.eye(3)]])
+    # joint-space forces: passive (damping, springs) + actuation
+    tau = -F("dof_damping")[:nv] * qd
+    jstiff, qspring, dof_jnt = F("jnt_stiffness"), tab(pm, "qpos_spring"), tab(pm, "dof_jntid")
+    for i in range(nv):
+        j = dof_jnt[i]
+        if ints["jnt_type"][j] != 0 and jstiff[j] != 0:
+            tau[i] -= jstiff[j] * (q[jnt_qposadr[j]] - qspring[jnt_qposadr[j]])
+    gear, rng, lim, adof = F("act_gear"), F("act_ctrlrange", (-1, 2)), F("act_ctrllimited"), F("act_dofid")
+    for a in range(nu):
+        c = np.clip(ctrl[a], rng[a, 0], rng[a, 1]) if lim[a] else ctrl[a]
+        tau[adof[a]] += gear[a] * c
+    dofadr = tab(pm, "body_dofadr")
+    # pass 1: velocities and bias terms
+    vel = [np.zeros(6)] * nb; cb = [np.zeros(6)] * nb; pA = [None] * nb; IA = [None] * nb
+    for b in range(1, nb):
+        vb = vel[ints["body_parentid"][b]].copy(); c = np.zeros(6)
+        vbefore = vb
+        for k in range(S[b].shape[1]):
+            # S_k moves with the velocity of the frame it is fixed in: the frame before joint k for a hinge / slide axis, and for
+            # the three body axes of a free joint's rotation the SAME frame (their own rotation cancels: w x w = 0)
+            if k not in ballcols[b]:
+                vbefore = vb
+            c += crm(vbefore) @ S[b][:, k] * qd[dofadr[b] + k]
+            vb = vb + S[b][:, k] * qd[dofadr[b] + k]
+        vel[b], cb[b] = vb, c
+        IA[b] = I[b].copy()
+        pA[b] = -crm(vb).T @ (I[b] @ vb)
+    # pass 2: articulated inertias, leaves to root
+    U, Dinv, uu = [None] * nb, [None] * nb, [None] * nb
+    arm = F("dof_armature")
+    for b in range(nb - 1, 0, -1):
+        nd = S[b].shape[1]
+        if nd:
+            U[b] = IA[b] @ S[b]
+            Dinv[b] = np.linalg.inv(S[b].T @ U[b] + np.diag(arm[dofadr[b]:dofadr[b] + nd]))
+            uu[b] = tau[dofadr[b]:dofadr[b] + nd] - S[b].T @ pA[b]
+            Ia = IA[b] - U[b] @ Dinv[b] @ U[b].T
+            pa = pA[b] + Ia @ cb[b] + U[b] @ Dinv[b] @ uu[b]
+        else:
+            Ia, pa = IA[b], pA[b] + IA[b] @ cb[b]
+        p = ints["body_parentid"][b]
+        if p > 0:
+            IA[p] = IA[p] + Ia; pA[p] = pA[p] + pa
+    # pass 3: accelerations, root to leaves (gravity as the base's upward acceleration)
+    acc = [np.zeros(6)] * nb
+    acc[0] = np.concatenate([np.zeros(3), -F("gravity")])
+    qdd = np.zeros(nv)
+    for b in range(1, nb):
+        a = acc[ints["body_parentid"][b]] + cb[b]
+        nd = S[b].shape[1]
+        if nd:
+            dd = Dinv[b] @ (uu[b] - U[b].T @ a)
+            qdd[dofadr[b]:dofadr[b] + nd] = dd
+            a = a + S[b] @ dd
+        acc[b] = a
+    return qdd
+
+
+def tab(pm, name):
+    """Fields of ilqg_model that Model.field does not name: located through the struct's known neighbours (include/ilqg_model.h)."""
+    import ctypes as C
+    off, cnt, dbl = C.c_int(), C.c_int(), C.c_int()
+    L = __import__("__graft_entry__").load_package().lib()
+    def at(n):
+        assert L.ilqg_model_field(n.encode(), C.byref(off), C.byref(cnt), C.byref(dbl)) == 0, n
+        return off.value
+    B, J, Q, V = 16, 24, 32, 32   # ILQG_MAXBODY, ILQG_MAXJNT, ILQG_MAXQ, ILQG_MAXV
+    base = {"body_jntadr": (at("body_parentid") + 2 * 4 * B, B, np.int32), "body_jntnum": (at("body_parentid") + 3 * 4 * B, B, np.int32),
+            "body_dofadr": (at("body_parentid") + 4 * 4 * B, B, np.int32), "body_quat": (at("body_pos") + 8 * 3 * B, 4 * B, np.float64),
+            "jnt_qposadr": (at("jnt_type") + 4 * J, J, np.int32), "jnt_dofadr": (at("jnt_type") + 2 * 4 * J, J, np.int32),
+            "qpos_spring": (at("qpos0") + 8 * Q, Q, np.float64), "dof_jntid": (at("dof_parentid") - 4 * V, V, np.int32)}[name]
+    o, n, dt = base
+    return pm.buf[o:o + n * np.dtype(dt).itemsize].view(dt)
+
+
+@pytest.mark.parametrize("name", ["inverted_pendulum", "hopper", "humanoid"])
+def test_qacc_smooth_matches_articulated_body_algorithm(pkg, oracle, omodels, name):
+    om = omodels[name]; pm = pkg.Model.named(name)
+    n = 6
+    q, v, u, _ = scenario_states(name, n, seed=31)
+    if name == "hopper":
+        q[:, 1] += 2.0     # airborne: smooth dynamics only (qacc_smooth is defined either way; keep the states generic)
+    for k in range(n):
+        ref = oracle.dump(om, q[k], v[k], u[k])["qacc_smooth"]
+        got = aba_qacc_smooth(pm, q[k], v[k], u[k])
+        assert np.allclose(got, ref, rtol=1e-8, atol=1e-8 * max(1.0, np.abs(ref).max())), (k, np.abs(got - ref).max())

@@ -1018,7 +1018,7 @@ DEV size_t coop_grad_off(int col, int nv, int nu) {
 // qvel / ctrl columns: one CTA per knot; the warps share the centre's C-state and take columns in turn
 __global__ void __launch_bounds__(256, 2) coop_velctrl_kernel(const GModel* __restrict__ g, int nknots, const double* __restrict__ cstate,
                                                               const ilqg_cost* __restrict__ cost, double eps, int niter, int cdbl, int pdbl,
-                                                              double* __restrict__ deriv, int* __restrict__ status) {
+                                                              const FdDst dst, int* __restrict__ status) {
     extern __shared__ __align__(16) double coop_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const int k = blockIdx.x;
@@ -1058,11 +1058,12 @@ __global__ void __launch_bounds__(256, 2) coop_velctrl_kernel(const GModel* __re
             else if (lane < nv) {
                 const double d = (plus - a) / (2 * eps);
                 fin = fin && isfinite(d);
-                deriv[(size_t)k * nd + coop_deriv_off(col, lane, nv, nu)] = d;
+                for (int t = 0; t < dst.n; t++) dst.p[t][(size_t)k * nd + coop_deriv_off(col, lane, nv, nu)] = d;
             }
             __syncwarp();
         }
-        if (cost && lane == 0) deriv[(size_t)k * nd + coop_grad_off(col, nv, nu)] = dcost;
+        if (cost && lane == 0)
+            for (int t = 0; t < dst.n; t++) dst.p[t][(size_t)k * nd + coop_grad_off(col, nv, nu)] = dcost;
     }
     fin = __all_sync(0xffffffffu, fin);
     if (status && lane == 0 && !fin) atomicCAS(&status[k], 0, ILQG_ERR_NONFINITE);
@@ -1074,7 +1075,7 @@ __global__ void __launch_bounds__(32) coop_qpos_kernel(const GModel* __restrict_
                                                        const double* __restrict__ qacc_center, const int* __restrict__ cand,
                                                        const ilqg_cost* __restrict__ cost, double eps, int niter, int cdbl, int pdbl,
                                                        const int* __restrict__ rowbound, int cap_lo, int cap,
-                                                       double* __restrict__ deriv, int* __restrict__ status) {
+                                                       const FdDst dst, int* __restrict__ status) {
     // Launched once per row-capacity class (cap_lo, cap]: a warp whose knot's row bound falls outside leaves at once.  cdbl / pdbl
     // are the block sizes for capacity `cap` — the smaller class fits 8 rollouts per SM instead of 6.
     extern __shared__ __align__(16) double coop_smem[];
@@ -1126,11 +1127,12 @@ __global__ void __launch_bounds__(32) coop_qpos_kernel(const GModel* __restrict_
         else if (lane < nv) {
             const double d = (plus - a) / (2 * eps);
             fin = isfinite(d);
-            deriv[(size_t)k * nd + coop_deriv_off(col, lane, nv, nu)] = d;
+            for (int t = 0; t < dst.n; t++) dst.p[t][(size_t)k * nd + coop_deriv_off(col, lane, nv, nu)] = d;
         }
         __syncwarp();
     }
-    if (cost && lane == 0) deriv[(size_t)k * nd + coop_grad_off(col, nv, nu)] = dcost;
+    if (cost && lane == 0)
+        for (int t = 0; t < dst.n; t++) dst.p[t][(size_t)k * nd + coop_grad_off(col, nv, nu)] = dcost;
     fin = __all_sync(0xffffffffu, fin);
     if (status && lane == 0) {
         if (!ok) atomicExch(&status[k], ILQG_ERR_CAPACITY);

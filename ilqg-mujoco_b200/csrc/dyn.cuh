@@ -45,6 +45,14 @@ namespace ilqg {
 #endif
 #define DEV __device__ __forceinline__
 
+// Destinations of the deriv blocks.  n = 1: the caller's buffer.  n > 1: the same block is stored to every destination —
+// the copies of a knot-sharded horizon's deriv array on the peer GPUs (mapped over NVLink with CUDA IPC), so that the
+// all-gather of SURVEY 8(e) happens in the FD kernels' write-out instead of a separate collective.
+struct FdDst {
+    double* p[ILQG_MAX_PEERS];
+    int n;
+};
+
 template <int I, int N, class F>
 DEV void sfor(F&& f) {
     if constexpr (I < N) {

@@ -139,13 +139,7 @@ __global__ void __launch_bounds__(256) fd_bin_kernel(int nknots, const FdBins bi
 }
 
 // ------------------------------------------------------------------ FD: perturbed evaluations
-// Destinations of the deriv blocks.  n = 1: the caller's buffer.  n > 1: the same block is stored to every destination —
-// the copies of a knot-sharded horizon's deriv array on the peer GPUs (mapped over NVLink with CUDA IPC), so that the
-// all-gather of SURVEY 8(e) happens in the FD kernels' write-out instead of a separate collective.
-struct FdDst {
-    double* p[ILQG_MAX_PEERS];
-    int n;
-};
+// (FdDst — the destinations of the deriv blocks, one or several — is declared in dyn.cuh)
 
 template <class T>
 struct FdShape {
@@ -1007,8 +1001,6 @@ struct CoopEngine : Engine {
                    const ilqg_fd_opts& o, const FdDst& dst, double* qacc_center, int* status, int* /*scratch*/, int /*batch*/, cudaStream_t s,
                    cudaEvent_t* ev) override {
         if (nknots <= 0) return cudaSuccess;
-        if (dst.n > 1) return cudaErrorNotSupported;   // peer scatter is wired into the thread-per-rollout kernels only
-        double* deriv = dst.p[0];
         const int nq = tab.nq, nv = tab.nv, nu = tab.nu, nd = nv * (2 * nv + nu) + 2 * nv + nu;
         const size_t one = warp_bytes(), vc = (size_t)cfull * sizeof(double) + (size_t)vc_warps * pdbl * sizeof(double);
         // a perturbation of eps moves a geom by eps x (lever arm): pairs farther than margin + slack from contact cannot become active
@@ -1019,7 +1011,9 @@ struct CoopEngine : Engine {
         for (int lo = 0; lo < nknots; lo += MAX_CHUNK) {
             const int n = nknots - lo < MAX_CHUNK ? nknots - lo : MAX_CHUNK;
             const double *q = qpos + (size_t)lo * nq, *v = qvel + (size_t)lo * nv, *u = ctrl + (size_t)lo * nu, *w = warm ? warm + (size_t)lo * nv : nullptr;
-            double *qc = qacc_center + (size_t)lo * nv, *dv = deriv + (size_t)lo * nd;
+            double* qc = qacc_center + (size_t)lo * nv;
+            FdDst dv = dst;   // this pass's knots in every destination
+            for (int d = 0; d < dst.n; d++) dv.p[d] = dst.p[d] + (size_t)lo * nd;
             int* st = status ? status + lo : nullptr;
             coop_center_kernel<<<n, 32, center_bytes(), s>>>(d_g, n, q, v, u, w, o.niter, o.nwarmup, slack, cfull, pdbl, qc, st, d_cstate, d_cand,
                                                              d_rowbound, fd_diag ? fd_diag + (size_t)lo * ILQG_DIAG_INTS : nullptr);

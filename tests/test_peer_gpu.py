@@ -96,3 +96,29 @@ def test_two_ranks_store_into_each_others_arrays(tmp_path):
     single = np.load(tmp_path / "single.npy")
     for r in range(2):
         assert np.array_equal(np.load(tmp_path / f"peer_{r}.npy"), single)
+
+
+def test_generic_engine_scatters_too(pkg, oracle, omodels):
+    """The warp-cooperative engine (humanoid) stores its blocks to several destinations as well (round 1 refused dst.n > 1)."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from ilqg_mujoco_b200 import sharding
+    h = pkg.Handle(pkg.Model.named("humanoid"), 0)
+    m = h.model
+    n = 7
+    q, v, u, w = scenario_states("humanoid", n, seed=19, oracle=oracle, om=omodels["humanoid"], roll=40)
+    dq, dv, du, dw = (torch.from_numpy(a).cuda() for a in (q, v, u, w))
+    cost = pkg.make_cost(q1=[1.0])
+    ref = torch.zeros((n, m.nd), dtype=torch.float64, device="cuda")
+    h.fd_batch_dev(dq, dv, du, dw, ref, cost=cost)
+    bufs = [h.peer_alloc(10 * m.nd * 8)[0] for _ in range(2)]
+    h.fd_batch_dev_scatter(dq, dv, du, dw, [b + 2 * m.nd * 8 for b in bufs], cost=cost)
+    torch.cuda.synchronize()
+    for b in bufs:
+        full = torch.as_tensor(sharding._DevArray(b, (10, m.nd)), device="cuda:0")
+        assert torch.equal(full[2:2 + n], ref)
+        assert float(full[:2].abs().sum()) == 0.0 and float(full[2 + n:].abs().sum()) == 0.0
+    for b in bufs:
+        h.peer_free(b)
+    h.close()

@@ -177,6 +177,21 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------ iLQR iterations/s (BASELINE configs[3])
+def per_rank(value, world, dev):
+    """[min, median, max] of a per-rank figure over the ranks (the reported throughputs use the max time; latency-bound kernels run
+    at noticeably different speeds on the GPUs of one box, and this is where that shows)."""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(value)], dtype=torch.float64, device=dev)
+    if world > 1:
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        v = sorted(float(x[0]) for x in out)
+    else:
+        v = [float(value)]
+    return [v[0], v[len(v) // 2], v[-1]]
+
+
 def ilqr_reference_classes_rate():
     """iLQR iterations/s of the REFERENCE's own InvertedPendulum / ILQR / Differentiator / calcMJDerivatives (oracle/_ref: verbatim
     sources on the oracle physics): MPC steps of 10 iterations, one problem after the other as cmd/basic.cpp drives them.
@@ -256,8 +271,10 @@ def bench_ilqr(pkg, dev_index, ninst, niter, reps, world, rank, with_cpu):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_iter = float(t[0]) / (reps * niter)
+    by_rank = per_rank(total_ms / (reps * niter), world, dev)
     res = {"metric": "iLQR iterations/sec (inverted pendulum, N=20, fp64)", "value": world * ninst * niter * reps / (float(t[0]) * 1e-3),
            "unit": "iterations/s", "instances_per_gpu": ninst, "iterations": niter, "ms_per_batch_iteration": ms_iter,
+           "ms_per_batch_iteration_min_median_max_over_ranks": by_rank,
            "gpu_launches_per_batch_iteration": launches / (reps * niter), "cuda_graph": os.environ.get("ILQG_ILQR_GRAPH", "1") != "0",
            "e2e": {"value": world * ninst * niter * reps / (float(t[1]) * 1e-3), "unit": "iterations/s",
                    "h2d_bytes_per_step": ninst * 4 * 8, "d2h_bytes_per_step": ninst * (1 + niter) * 8,
@@ -531,10 +548,12 @@ def bench_humanoid(pkg, dev_index, nknots, steps, world, rank, with_cpu):
     e1.record()
     e1.synchronize()
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    by_rank = per_rank(nknots * steps / (float(t[0]) * 1e-3), world, dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     st = status.cpu().numpy()
     res = {"metric": "FD dynamics Jacobian knots/sec (humanoid, fp64)", "value": world * nknots * steps / (float(t[0]) * 1e-3), "unit": "knots/s",
+           "knots_per_s_per_gpu_min_median_max_over_ranks": by_rank,
            "knots_per_gpu": nknots, "engine": h.engine, "status_ok": int((st == 0).sum()), "status_capacity": int((st == 7).sum()),
            "status_nonfinite": int((st == 6).sum()), "replaced_nonfinite_states": nbad}
     if with_cpu:

@@ -742,6 +742,7 @@ struct Engine {
     virtual bool fd_calls_may_overlap() const { return true; }
     virtual void set_fused_max(int) {}
     virtual void set_vu_classes(const char*) {}
+    virtual void set_q_minb(int) {}
     // ints of scratch fd() wants for `nknots` knots (bucket counters, keys, permutation); 0 = none
     // (`batch`: the size of the whole batch a chunk belongs to — the kernel variant is chosen on it, so that a chunked host
     //  call runs the same kernels, and returns the same bits, as one device call over the batch)
@@ -777,6 +778,7 @@ struct EngineT : Engine {
     // shortest chain; above it the lone centre lane costs throughput (ILQG_FD_FUSED_MAX overrides; measured on B200)
     int fused_max = FdFusedShape<T>::OK ? 64 : 0;
     void set_fused_max(int n) override { fused_max = FdFusedShape<T>::OK ? n : 0; }
+    void set_q_minb(int n) override { q_minb = n; }
     void set_vu_classes(const char* e) override {
         vu_nclass = 0;
         while (*e && vu_nclass < 4) {
@@ -811,6 +813,7 @@ struct EngineT : Engine {
     int vu_class[4] = {0, 0, 0, 0};
     int vu_nclass = 0;
     bool vu_attr_set = false;
+    int q_minb = Q_MINB;
     void launch_split(int nknots, const double* qpos, const double* qvel, const double* ctrl, const ilqg_cost* cost_dev, const ilqg_fd_opts& o,
                       const FdDst& dst, const double* qacc_center, int* status, const FdBins& bins, cudaStream_t s, cudaEvent_t* ev) {
         using PV = FdSplit<T, VU_THREADS>;
@@ -841,6 +844,10 @@ struct EngineT : Engine {
         fd_velctrl_kernel<T, true, VU_THREADS, VU_MINB><<<grid_vu, VU_THREADS, 0, s>>>(
             dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps, o.niter, dst, status, perm, bins, lo, hi);
         if (ev) cudaEventRecord(ev[3], s);
+        if (q_minb == 1)   // experiment (ILQG_Q_MINB=1): one CTA per SM, no register cap — half the local-memory footprint per SM
+            fd_qpos_kernel<T, true, Q_THREADS, 1><<<(nknots + PQ::KPC_Q - 1) / PQ::KPC_Q, Q_THREADS, 0, s>>>(
+                dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps, o.niter, dst, status, perm);
+        else
         fd_qpos_kernel<T, true, Q_THREADS, Q_MINB><<<(nknots + PQ::KPC_Q - 1) / PQ::KPC_Q, Q_THREADS, 0, s>>>(
             dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps, o.niter, dst, status, perm);
     }
@@ -1190,6 +1197,7 @@ int ilqg_create(const ilqg_model* m, int device, ilqg_handle* out) {
     if (const char* e = getenv("ILQG_FD_PDL")) eng->fd_pdl = atoi(e);
     if (const char* e = getenv("ILQG_FD_FUSED_MAX")) eng->set_fused_max(atoi(e));
     if (const char* e = getenv("ILQG_VU_CLASSES")) eng->set_vu_classes(e);
+    if (const char* e = getenv("ILQG_Q_MINB")) eng->set_q_minb(atoi(e));
     if (const char* e = getenv("ILQG_HOST_CHUNKS")) h->host_chunks = atoi(e);
     if (const char* e = getenv("ILQG_HOST_COMP")) h->host_comp_streams = atoi(e);
     if (cudaMalloc(&h->d_cost, sizeof(ilqg_cost)) != cudaSuccess) {

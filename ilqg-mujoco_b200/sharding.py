@@ -19,11 +19,13 @@ def shard_range(n, world, rank):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def pick_ranks(T, world, knots_per_rank_min=2000):
-    """How many of the node's `world` GPUs to shard a horizon of T knots over.  A pass over fewer than ~2000 hopper knots is bound
-    by the latency of one centre + one perturbed evaluation (about 60 us on B200 whether a rank holds 125 knots or 1000), and
-    every additional rank adds the flag barrier: measured (bench.py's `longer_horizons_knots_per_s` at 1, 2, 4, 8 GPUs)
-    sharding starts to pay once each rank keeps at least ~2000 knots.  Returns a power of two <= world."""
+def pick_ranks(T, world, knots_per_rank_min=1000):
+    """How many of the node's `world` GPUs to shard a horizon of T knots over.  A pass over up to ~1000 hopper knots is bound by the
+    latency of one centre + one perturbed evaluation (60-80 us on B200 whether a rank holds 125 knots or 1000) and sharding adds
+    the flag barrier (~10 us).  Measured on one 8 x B200 node (tools/prof_t_sweep.py, round 2; us per pass at 1 / 2 / 4 / 8 ranks):
+    T = 1000: 78 / 87 / 88 / 87;  2000: 107 / 89 / 88 / 90;  4000: 152 / 115 / 91 / 89;  8000: 244 / 162 / 120 / 96;
+    16000: 435 / 256 / 167 / 126;  64000: 1171 / 717 / 472 / 290;  128000: 2238 / 1225 / 796 / 506.
+    So doubling the ranks pays as long as every rank keeps at least ~1000 knots.  Returns a power of two <= world."""
     r = 1
     while r * 2 <= world and T // (r * 2) >= knots_per_rank_min:
         r *= 2

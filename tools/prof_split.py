@@ -24,9 +24,13 @@ n = q.shape[0]
 cost = pkg.make_cost(q1=[1.0])
 ref = None
 for cap in caps:
-    os.environ["ILQG_VU_CLASSES"] = cap
+    envs = dict(kv.split("=") for kv in cap.split(";") if "=" in kv)   # "ILQG_Q_MINB=1;ILQG_VU_CLASSES=8" or a bare class list
+    if not envs:
+        envs = {"ILQG_VU_CLASSES": cap}
+    os.environ.update(envs)
     h = pkg.Handle(model, 0)
-    del os.environ["ILQG_VU_CLASSES"]
+    for k in envs:
+        del os.environ[k]
     deriv = torch.zeros((n, model.nd), dtype=torch.float64, device="cuda:0"); qacc = torch.zeros((n, model.nv), dtype=torch.float64, device="cuda:0")
     status = torch.zeros(n, dtype=torch.int32, device="cuda:0")
     L.ilqg_set_profiling(h._h, 1)
@@ -43,6 +47,6 @@ for cap in caps:
     if ref is None:
         ref = deriv.clone()
     err = float((deriv - ref).abs().max() / ref.abs().max())
-    print(f"vu_classes={cap:>8s}: {n} knots: centre {acc[0]:.4f} ms, velctrl {acc[1]:.4f} ms, qpos {acc[2]:.4f} ms -> {n / acc.sum() / 1e3:.2f} M knots/s; "
+    print(f"{cap:>28s}: {n} knots: centre {acc[0]:.4f} ms, velctrl {acc[1]:.4f} ms, qpos {acc[2]:.4f} ms -> {n / acc.sum() / 1e3:.2f} M knots/s; "
           f"status ok {int((status == 0).sum())}; max rel diff to first {err:.2e}")
     h.close()

@@ -1139,6 +1139,12 @@ struct ilqg_handle_s {
     cudaStream_t pipe[4] = {nullptr, nullptr, nullptr, nullptr};  // upload / compute A / download / compute B streams of the *_host FD entry point
     cudaEvent_t pipe_ev[2 * ILQG_HOST_MAXCHUNKS] = {};    // per chunk: uploaded, computed
     int* h_stat = nullptr; size_t hstat_cap = 0;          // pinned landing buffer of the status words
+    // opt-in (ilqg_set_host_pinning): large caller buffers of the *_host FD call are page-locked (cudaHostRegister) the first time
+    // they are seen and stay so until the handle is destroyed — a calcMJDerivatives caller hands the same malloc'ed deriv array
+    // every call, and a pageable destination is copied at a fifth of the pinned rate
+    bool pin_host = false;
+    struct Reg { const void* p; size_t bytes; };
+    std::vector<Reg> regs;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // before centre, after centre, after the last FD kernel, between the two column kernels
 };
 
@@ -1200,6 +1206,7 @@ int ilqg_create(const ilqg_model* m, int device, ilqg_handle* out) {
     if (const char* e = getenv("ILQG_Q_MINB")) eng->set_q_minb(atoi(e));
     if (const char* e = getenv("ILQG_HOST_CHUNKS")) h->host_chunks = atoi(e);
     if (const char* e = getenv("ILQG_HOST_COMP")) h->host_comp_streams = atoi(e);
+    if (const char* e = getenv("ILQG_PIN_HOST")) h->pin_host = atoi(e) != 0;
     if (cudaMalloc(&h->d_cost, sizeof(ilqg_cost)) != cudaSuccess) {
         delete eng;
         delete h;
@@ -1221,6 +1228,7 @@ int ilqg_destroy(ilqg_handle h) {
     for (int i = 0; i < 4; i++) if (h->pipe[i]) cudaStreamDestroy(h->pipe[i]);
     for (int i = 0; i < 2 * ILQG_HOST_MAXCHUNKS; i++) if (h->pipe_ev[i]) cudaEventDestroy(h->pipe_ev[i]);
     if (h->h_stat) cudaFreeHost(h->h_stat);
+    for (auto& r : h->regs) cudaHostUnregister(const_cast<void*>(r.p));
     delete h->eng;
     delete h;
     return ILQG_OK;
@@ -1458,6 +1466,41 @@ int ilqg_peer_free(ilqg_handle h, void* dev_ptr) {
     return ILQG_OK;
 }
 
+// page-lock [p, p + bytes) once (no-op when it already is, or is too small to matter); failures leave the buffer pageable
+static void pin_once(ilqg_handle h, const void* p, size_t bytes) {
+    if (!h->pin_host || !p || bytes < (1u << 20)) return;
+    for (size_t i = 0; i < h->regs.size(); i++) {
+        auto& r = h->regs[i];
+        if (r.p == p && r.bytes >= bytes) return;
+        const char *a = (const char*)r.p, *b = (const char*)p;
+        if (a < b + bytes && b < a + r.bytes) {   // overlaps an older registration (the caller re-allocated): drop that one
+            cudaHostUnregister(const_cast<void*>(r.p));
+            h->regs.erase(h->regs.begin() + i);
+            i--;
+        }
+    }
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type != cudaMemoryTypeUnregistered) return;   // pinned or device memory already
+    cudaGetLastError();
+    if (h->regs.size() >= 16) {
+        cudaHostUnregister(const_cast<void*>(h->regs.front().p));
+        h->regs.erase(h->regs.begin());
+    }
+    if (cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault) == cudaSuccess) h->regs.push_back({p, bytes});
+    else cudaGetLastError();
+}
+
+int ilqg_set_host_pinning(ilqg_handle h, int on) {
+    if (!h) return ILQG_ERR_ARG;
+    h->pin_host = on != 0;
+    if (!on) {
+        cudaSetDevice(h->device);
+        for (auto& r : h->regs) cudaHostUnregister(const_cast<void*>(r.p));
+        h->regs.clear();
+    }
+    return ILQG_OK;
+}
+
 int ilqg_fd_batch_host(ilqg_handle h, int nknots, const double* qpos, const double* qvel, const double* ctrl, const double* warmstart,
                        const ilqg_cost* cost, const ilqg_fd_opts* opts, double* deriv, double* qacc_out, int* status) {
     if (!h) return ILQG_ERR_ARG;
@@ -1466,6 +1509,12 @@ int ilqg_fd_batch_host(ilqg_handle h, int nknots, const double* qpos, const doub
     CU(h, cudaSetDevice(h->device));
     const int nq = h->model.nq, nv = h->model.nv, nu = h->model.nu, nd = ilqg_deriv_size(&h->model);
     size_t n = (size_t)nknots;
+    pin_once(h, deriv, n * nd * sizeof(double));
+    pin_once(h, qpos, n * nq * sizeof(double));
+    pin_once(h, qvel, n * nv * sizeof(double));
+    pin_once(h, ctrl, n * nu * sizeof(double));
+    pin_once(h, warmstart, n * nv * sizeof(double));
+    pin_once(h, qacc_out, n * nv * sizeof(double));
     // one staging block: qpos | qvel | ctrl | warm | qacc | deriv | status | work-class scratch
     size_t off_q = 0, off_v = off_q + n * nq, off_u = off_v + n * nv, off_w = off_u + n * nu, off_a = off_w + n * nv,
            off_d = off_a + n * nv, ndbl = off_d + n * nd;

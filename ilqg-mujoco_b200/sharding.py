@@ -99,9 +99,10 @@ class PeerDeriv:
         self.bufs = [both[0], both[1]]
         self.full = self.bufs[0]
 
-    def scatter_ptrs(self, first_knot, parity=0):
-        """Destination addresses of knot `first_knot` in buffer `parity` of every rank's copy, this rank's first."""
-        order = [self.rank] + [r for r in range(self.world) if r != self.rank]
+    def scatter_ptrs(self, first_knot, parity=0, root=None):
+        """Destination addresses of knot `first_knot` in buffer `parity`: every rank's copy, this rank's first — or, with `root`,
+        only the copy of the rank that runs the backward pass (the all-gather becomes a gather: 1/world of the NVLink traffic)."""
+        order = [self.rank] + [r for r in range(self.world) if r != self.rank] if root is None else [int(root)]
         return [self.ptrs[r] + parity * self.buf_bytes + first_knot * self.nd * 8 for r in order]
 
     def check(self):
@@ -126,16 +127,17 @@ class PeerDeriv:
         self.h.peer_free(self.own)
 
 
-def fd_knot_sharded_peer(handle, peer, qpos, qvel, ctrl, warm, cost=None, stream=None):
+def fd_knot_sharded_peer(handle, peer, qpos, qvel, ctrl, warm, cost=None, stream=None, root=None):
     """FD linearisation of one long trajectory, knots sharded over the ranks, blocks stored by the kernels into every
     rank's copy of the pass's buffer.  Returns that buffer (all T blocks, knot order; also `peer.full`), valid on `stream`
     once every rank's kernels have finished.  Consecutive passes alternate between two buffers; readers of the returned array
-    must be ordered on `stream` before the next call (see PeerDeriv)."""
+    must be ordered on `stream` before the next call (see PeerDeriv).  root = r: the blocks go to rank r's copy only (the rank
+    that runs the Riccati sweep, /root/reference/inc/ilqr.h:144-175); the array returned on the other ranks is then not filled."""
     T = qpos.shape[0]
     lo, hi = shard_range(T, peer.world, peer.rank)
     parity = peer.epoch & 1
     if hi > lo:
-        handle.fd_batch_dev_scatter(qpos[lo:hi], qvel[lo:hi], ctrl[lo:hi], warm[lo:hi], peer.scatter_ptrs(lo, parity), cost=cost, stream=stream)
+        handle.fd_batch_dev_scatter(qpos[lo:hi], qvel[lo:hi], ctrl[lo:hi], warm[lo:hi], peer.scatter_ptrs(lo, parity, root), cost=cost, stream=stream)
     peer.full = peer.bufs[parity]
     if peer.world > 1:
         peer.barrier(stream=stream)   # a 1-warp kernel per rank exchanging flags through peer memory: no NCCL call on this path

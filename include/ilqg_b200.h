@@ -109,6 +109,12 @@ int ilqg_fd_batch_host(ilqg_handle h, int nknots, const double* qpos, const doub
                        const double* warmstart, const ilqg_cost* cost, const ilqg_fd_opts* opts, double* deriv,
                        double* qacc_out, int* status);
 
+/* opt-in: page-lock the caller's large host buffers of ilqg_fd_batch_host (cudaHostRegister) the first time they are seen; they
+ * stay registered until ilqg_set_host_pinning(h, 0) or ilqg_destroy.  The reference's caller owns one malloc'ed deriv array for the
+ * life of a Differentiator (/root/reference/inc/differentiator.h:56): pageable memory is copied device-to-host at about a fifth of
+ * the pinned rate.  The caller must not free a registered buffer while the handle lives (or must switch pinning off first). */
+int ilqg_set_host_pinning(ilqg_handle h, int on);
+
 /* ---- optional per-knot diagnostics of the centre evaluation (mj_forward + warm-up solves, /root/reference/src/mjderivative.cpp:64-68).
  * The reference pins the solver to `niter` iterations / tolerance 0 (:241-242); the kernels' solver leaves earlier when it has
  * reached the exact minimiser of the convex piecewise-quadratic cost ("Solver") — these counters say how many Newton

@@ -280,3 +280,25 @@ def test_centre_diagnostics_report_solver_iterations(pkg, handles, oracle, omode
     assert int((diag != -7).sum()) == 0
     if name not in handles:
         h.close()
+
+
+def test_host_pinning_of_caller_buffers_is_transparent(pkg, oracle, omodels):
+    """ilqg_set_host_pinning: the host-pointer call page-locks the caller's (pageable) arrays on first use — same bits out, the
+    registration is reused by the next call, released when switched off or when the handle is destroyed."""
+    h = pkg.Handle(pkg.Model.named("hopper"), 0)
+    n = 2100   # deriv = 1.76 MB: above the 1 MB threshold of the registration
+    q, v, u, w = scenario_states("hopper", n, seed=23)
+    cost = pkg.make_cost(q1=[1.0])
+    d0, a0, s0 = h.fd_batch_host(q, v, u, w, cost)
+    assert pkg.lib().ilqg_set_host_pinning(h._h, 1) == 0
+    buf = np.zeros((n, h.model.nd))
+    for _ in range(3):
+        d1, a1, s1 = h.fd_batch_host(q, v, u, w, cost, deriv=buf)
+        assert d1 is buf and np.array_equal(d1, d0) and np.array_equal(a1, a0)
+    assert pkg.lib().ilqg_set_host_pinning(h._h, 0) == 0
+    d2, _, _ = h.fd_batch_host(q, v, u, w, cost, deriv=buf)
+    assert np.array_equal(d2, d0)
+    pkg.lib().ilqg_set_host_pinning(h._h, 1)
+    h.fd_batch_host(q, v, u, w, cost, deriv=buf)
+    h.close()   # unregisters
+    buf[:] = 1.0  # the array is ordinary memory again

@@ -162,6 +162,14 @@ def _peer_worker(rank, world, port, T, tmpdir):
         assert np.array_equal(full.numpy(), ref)
     np.save(os.path.join(tmpdir, f"peer_{rank}.npy"), full.numpy().copy())
     assert peer.epoch == 3
+    # gather to the backward-pass rank only: one destination per store
+    assert peer.scatter_ptrs(2, 1, root=1) == [peer.ptrs[1] + (T + 2) * om.nd * 8]
+    q, v, u, w = scenario_states("hopper", T, seed=9)
+    full = sharding.fd_knot_sharded_peer(h, peer, *(torch.from_numpy(a) for a in (q, v, u, w)), root=0)
+    if rank == 0:
+        ref, _, _ = o.fd_batch(om, q, v, u, w, None, nthreads=1)
+        assert np.array_equal(full.numpy(), ref)
+    assert peer.epoch == 4
     dist.barrier()
     for r, p in enumerate(peer.ptrs):
         if r != rank:

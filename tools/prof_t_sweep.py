@@ -21,12 +21,13 @@ h = pkg.Handle(model, local)
 q, v, u, w, _ = wl.make_knots(h, 1, 1000, seed=0, device=dev, model="hopper")
 stream = torch.cuda.current_stream().cuda_stream
 rows = []
+root = int(os.environ["ILQG_ROOT"]) if os.environ.get("ILQG_ROOT") else None   # gather to one rank instead of all
 for T in (1000, 2000, 4000, 8000, 16000, 32000, 64000, 128000):
     rep = (T + 999) // 1000
     ql, vl, ul, wl_ = (x.repeat(rep, 1)[:T].contiguous() for x in (q, v, u, w))
     peer = sharding.PeerDeriv(h, T, model.nd)
     for _ in range(3):
-        sharding.fd_knot_sharded_peer(h, peer, ql, vl, ul, wl_, stream=stream)
+        sharding.fd_knot_sharded_peer(h, peer, ql, vl, ul, wl_, stream=stream, root=root)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -34,7 +35,7 @@ for T in (1000, 2000, 4000, 8000, 16000, 32000, 64000, 128000):
     reps = 20 if T <= 16000 else 6
     e0.record()
     for _ in range(reps):
-        sharding.fd_knot_sharded_peer(h, peer, ql, vl, ul, wl_, stream=stream)
+        sharding.fd_knot_sharded_peer(h, peer, ql, vl, ul, wl_, stream=stream, root=root)
     e1.record(); e1.synchronize()
     peer.check()
     t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
@@ -43,7 +44,7 @@ for T in (1000, 2000, 4000, 8000, 16000, 32000, 64000, 128000):
     rows.append((T, float(t[0])))
     peer.close()
 if rank == 0:
-    print(f"ranks={world}: " + "  ".join(f"T={T}: {ms * 1e3:.0f} us {T / ms / 1e3:.1f} M/s" for T, ms in rows))
+    print(f"ranks={world} root={root}: " + "  ".join(f"T={T}: {ms * 1e3:.0f} us {T / ms / 1e3:.1f} M/s" for T, ms in rows))
 h.close()
 if world > 1:
     dist.destroy_process_group()

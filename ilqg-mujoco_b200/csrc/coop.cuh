@@ -27,6 +27,7 @@
 
 #include "../../include/ilqg_b200.h"
 #include "dyn.cuh"
+#include "ilqr.cuh"
 
 namespace ilqg {
 
@@ -1169,7 +1170,43 @@ __global__ void __launch_bounds__(32) coop_forward_kernel(const GModel* __restri
     }
 }
 
-// nsteps x mj_step for n states (Euler with implicit joint damping; RK4 models use the thread-per-rollout path)
+// one mj_step (Euler with implicit joint damping; RK4 models use the thread-per-rollout path) of the state in w.q / w.v under w.u;
+// warm_i: this lane's component of qacc_warmstart (kept in a register: the position stage's temporaries alias w.warm)
+DEV void coop_step_once(const GModel* __restrict__ g, CoopMem& w, int lane, double& warm_i) {
+    const ilqg_model& m = g->m;
+    const int nv = m.nv, nt = coop_nt(m.nv);
+    const double h = m.timestep;
+    coop_pos(g, w, lane, nullptr, -1, nullptr, 0.0);
+    coop_vel(g, w, w.v, lane);
+    coop_smooth(g, w, w.u, lane);
+    if (lane < nv) w.warm[lane] = warm_i;
+    __syncwarp();
+    coop_solve(g, w, m.iterations, m.tolerance, lane, true);
+    if (lane < nv) warm_i = w.warm[lane];
+    // mj_Euler: (M + h diag(b)) a = qfrc_smooth + qfrc_constraint when any dof is damped
+    double a_i = lane < nv ? w.qacc[lane] : 0.0;
+    if (g->any_damping) {
+        for (int e = lane; e < nt; e += 32) w.H[e] = w.M[e];
+        __syncwarp();
+        if (lane < nv) w.H[ptri(lane, lane)] += h * m.dof_damping[lane];
+        __syncwarp();
+        coop_chol(w.H, nv, lane);
+        a_i = coop_chol_solve(w.H, lane < nv ? w.fs[lane] + w.fc[lane] : 0.0, nv, lane);
+    }
+    if (lane < nv) w.v[lane] += h * a_i;
+    __syncwarp();
+    for (int j = lane; j < m.njnt; j += 32) {
+        const int qa = m.jnt_qposadr[j], da = m.jnt_dofadr[j];
+        if (m.jnt_type[j] == ILQG_JNT_FREE) {
+            for (int c = 0; c < 3; c++) w.q[qa + c] += h * w.v[da + c];
+            quat_integrate(&w.q[qa + 3], V3{w.v[da + 3], w.v[da + 4], w.v[da + 5]}, h);
+        } else
+            w.q[qa] += h * w.v[da];
+    }
+    __syncwarp();
+}
+
+// nsteps x mj_step for n states
 __global__ void __launch_bounds__(32) coop_step_kernel(const GModel* __restrict__ g, int n, int nsteps, double* __restrict__ qpos,
                                                        double* __restrict__ qvel, const double* __restrict__ ctrl, double* __restrict__ warmstart,
                                                        double* __restrict__ qacc_out, int cdbl, int pdbl) {
@@ -1178,8 +1215,7 @@ __global__ void __launch_bounds__(32) coop_step_kernel(const GModel* __restrict_
     const int k = blockIdx.x * (blockDim.x >> 5) + wib;
     if (k >= n) return;
     const ilqg_model& m = g->m;
-    const int nv = m.nv, nt = coop_nt(m.nv);
-    const double h = m.timestep;
+    const int nv = m.nv;
     CoopMem w;
     double* base = coop_smem + (size_t)wib * (cdbl + pdbl);
     coop_carve_cstate(w, base, m);
@@ -1187,44 +1223,97 @@ __global__ void __launch_bounds__(32) coop_step_kernel(const GModel* __restrict_
     for (int i = lane; i < m.nq; i += 32) w.q[i] = qpos[(size_t)k * m.nq + i];
     for (int i = lane; i < nv; i += 32) w.v[i] = qvel[(size_t)k * nv + i];
     for (int i = lane; i < m.nu; i += 32) w.u[i] = ctrl[(size_t)k * m.nu + i];
-    double warm_i = (warmstart && lane < nv) ? warmstart[(size_t)k * nv + lane] : 0.0;   // the position stage's temporaries alias w.warm
+    double warm_i = (warmstart && lane < nv) ? warmstart[(size_t)k * nv + lane] : 0.0;
     __syncwarp();
-    for (int s = 0; s < nsteps; s++) {
-        coop_pos(g, w, lane, nullptr, -1, nullptr, 0.0);
-        coop_vel(g, w, w.v, lane);
-        coop_smooth(g, w, w.u, lane);
-        if (lane < nv) w.warm[lane] = warm_i;
-        __syncwarp();
-        coop_solve(g, w, m.iterations, m.tolerance, lane, true);
-        if (lane < nv) warm_i = w.warm[lane];
-        // mj_Euler: (M + h diag(b)) a = qfrc_smooth + qfrc_constraint when any dof is damped
-        double a_i = lane < nv ? w.qacc[lane] : 0.0;
-        if (g->any_damping) {
-            for (int e = lane; e < nt; e += 32) w.H[e] = w.M[e];
-            __syncwarp();
-            if (lane < nv) w.H[ptri(lane, lane)] += h * m.dof_damping[lane];
-            __syncwarp();
-            coop_chol(w.H, nv, lane);
-            a_i = coop_chol_solve(w.H, lane < nv ? w.fs[lane] + w.fc[lane] : 0.0, nv, lane);
-        }
-        if (lane < nv) w.v[lane] += h * a_i;
-        __syncwarp();
-        for (int j = lane; j < m.njnt; j += 32) {
-            const int qa = m.jnt_qposadr[j], da = m.jnt_dofadr[j];
-            if (m.jnt_type[j] == ILQG_JNT_FREE) {
-                for (int c = 0; c < 3; c++) w.q[qa + c] += h * w.v[da + c];
-                quat_integrate(&w.q[qa + 3], V3{w.v[da + 3], w.v[da + 4], w.v[da + 5]}, h);
-            } else
-                w.q[qa] += h * w.v[da];
-        }
-        __syncwarp();
-    }
+    for (int s = 0; s < nsteps; s++) coop_step_once(g, w, lane, warm_i);
     for (int i = lane; i < m.nq; i += 32) qpos[(size_t)k * m.nq + i] = w.q[i];
     for (int i = lane; i < nv; i += 32) {
         qvel[(size_t)k * nv + i] = w.v[i];
         if (warmstart) warmstart[(size_t)k * nv + i] = warm_i;
         if (qacc_out) qacc_out[(size_t)k * nv + i] = w.qacc[i];
     }
+}
+
+// ------------------------------------------------------------------ iLQR on the warp-cooperative engine (nq != nv allowed)
+// x_a (-) x_b in the tangent space, the state vector of the opt-in extension beyond quirk Q9 (the reference's "2 nv doubles at
+// qpos" is undefined with a quaternion in qpos): slide / hinge dofs by plain difference, a free joint's orientation as the
+// body-frame rotation vector w with q_b * quat(w) = q_a (mju_subQuat) — the coordinates the FD blocks already use
+// (mjderivative.cpp:152-169).  Lanes stride over joints; out[0..nv) position part, out[nv..2nv) velocity part.
+DEV void coop_state_diff(const ilqg_model& m, const double* qa, const double* va, const double* qb, const double* vb, double* out, int lane) {
+    const int nv = m.nv;
+    for (int j = lane; j < m.njnt; j += 32) {
+        const int qadr = m.jnt_qposadr[j], dadr = m.jnt_dofadr[j];
+        if (m.jnt_type[j] == ILQG_JNT_FREE) {
+            for (int k = 0; k < 3; k++) out[dadr + k] = qa[qadr + k] - qb[qadr + k];
+            const Q4 A = qnormalized({qa[qadr + 3], qa[qadr + 4], qa[qadr + 5], qa[qadr + 6]});
+            const Q4 Bq = qnormalized({qb[qadr + 3], qb[qadr + 4], qb[qadr + 5], qb[qadr + 6]});
+            const Q4 d = qmul({Bq.w, -Bq.x, -Bq.y, -Bq.z}, A);
+            const double sn = sqrt(d.x * d.x + d.y * d.y + d.z * d.z);
+            double ang = 2 * atan2(sn, d.w);
+            if (ang > 3.14159265358979323846) ang -= 2 * 3.14159265358979323846;
+            const double sc = sn < 1e-15 ? 0.0 : ang / sn;
+            out[dadr + 3] = d.x * sc; out[dadr + 4] = d.y * sc; out[dadr + 5] = d.z * sc;
+        } else
+            out[dadr] = qa[qadr] - qb[qadr];
+    }
+    for (int i = lane; i < nv; i += 32) out[nv + i] = va[i] - vb[i];
+}
+
+// ILQR::forwardPass (ilqr.h:116-130) for every (instance, line-search step size): one warp each, same bookkeeping as
+// ilqr_rollout_kernel (knot snapshots into the alpha's candidate, cost of the stored knots, u = K (x (-) x*) + alpha k + u*)
+__global__ void __launch_bounds__(32) coop_rollout_kernel(const GModel* __restrict__ g, IlqrBuffers b, const ilqg_cost* __restrict__ cost, int cdbl,
+                                                          int pdbl) {
+    extern __shared__ __align__(16) double coop_smem[];
+    const int lane = threadIdx.x & 31;
+    const int item = blockIdx.x;
+    const int ninst = b.ninst;
+    if (item >= ninst * b.nalpha) return;
+    const int a = item / ninst, i = item - a * ninst;
+    const ilqg_model& m = g->m;
+    const int nq = m.nq, nv = m.nv, nu = m.nu, nx = 2 * nv;
+    CoopMem w;
+    coop_carve_cstate(w, coop_smem, m);
+    coop_carve_priv(w, coop_smem + cdbl, m);
+    const double alpha = b.alphas[a];
+    for (int e = lane; e < nq; e += 32) w.q[e] = b.init_q[(size_t)i * nq + e];
+    for (int e = lane; e < nv; e += 32) w.v[e] = b.init_v[(size_t)i * nv + e];
+    double warm_i = lane < nv ? b.init_w[(size_t)i * nv + lane] : 0.0;
+    double J = 0;
+    const size_t T1 = (size_t)(b.N + 1) * ninst;
+    double* dx = w.grad;   // 2 nv doubles (grad | search are adjacent); consumed before the position stage reuses the private block
+    __syncwarp();
+    for (int n = b.N; n >= 0; n--) {
+        const size_t kn = (size_t)n * ninst + i;
+        coop_state_diff(m, w.q, w.v, b.nom_q + kn * nq, b.nom_v + kn * nv, dx, lane);
+        __syncwarp();
+        if (lane < nu) {
+            const double* K = b.K + kn * nu * nx;
+            double s = 0;
+            for (int c = 0; c < nx; c++) s += K[lane + c * nu] * dx[c];
+            w.u[lane] = s + alpha * b.k[kn * nu + lane] + b.nom_u[kn * nu + lane];
+        }
+        __syncwarp();
+        const size_t cn = (size_t)a * T1 + kn;
+        for (int e = lane; e < nq; e += 32) b.cand_q[cn * nq + e] = w.q[e];
+        for (int e = lane; e < nv; e += 32) { b.cand_v[cn * nv + e] = w.v[e]; }
+        if (lane < nv) b.cand_w[cn * nv + lane] = warm_i;
+        for (int e = lane; e < nu; e += 32) b.cand_u[cn * nu + e] = w.u[e];
+        if (cost && lane == 0) J = __dadd_rn(J, coop_cost_eval(cost, w.q, w.v, w.u, nq, nv, nu));
+        coop_step_once(g, w, lane, warm_i);
+    }
+    if (lane == 0) b.cand_J[(size_t)a * ninst + i] = J;
+}
+
+// c_n = x*_{n-1} (-) x*_n for every knot n >= 1 of every instance (the affine term of ilqr.h:161-163 in tangent coordinates)
+__global__ void coop_cdiff_kernel(const GModel* __restrict__ g, IlqrBuffers b) {
+    const int lane = threadIdx.x & 31;
+    const size_t item = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int ninst = b.ninst;
+    if (item >= (size_t)b.N * ninst) return;
+    const int n = 1 + (int)(item / ninst), i = (int)(item % ninst);
+    const ilqg_model& m = g->m;
+    const size_t kn = (size_t)n * ninst + i, kp = (size_t)(n - 1) * ninst + i;
+    coop_state_diff(m, b.nom_q + kp * m.nq, b.nom_v + kp * m.nv, b.nom_q + kn * m.nq, b.nom_v + kn * m.nv, b.cdiff + kn * 2 * m.nv, lane);
 }
 
 }  // namespace ilqg

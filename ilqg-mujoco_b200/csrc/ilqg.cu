@@ -773,7 +773,9 @@ struct EngineT : Engine {
     // knots from which the stage-skipping split is chosen.  Measured on B200 (hopper, M knots/s, single launch vs split):
     // 16K 58.9 / 48.1, 21.5K 60.5 / 55.8, 28.7K 64.9 / 63.4, 43K 69.8 / 82.9, 86K 76.9 / 105 — the split's qvel/ctrl kernel has a
     // latency floor of 0.18 ms (a stance CTA's 6 sequential solves), the single launch none.
-    static constexpr int SPLIT_MIN = 24576;
+    // (a tree without collision pairs — the inverted pendulum — has no position stage worth sharing: at 86,016 knots the single-launch
+    //  column kernel behind the centre's programmatic launch takes 0.054 ms against the split's 0.062)
+    static constexpr int SPLIT_MIN = T::NPAIR > 0 ? 24576 : (1 << 22);
     // below this the batch cannot fill the GPU and the one-launch kernel (centre on a spare lane of its knot's warp) has the
     // shortest chain; above it the lone centre lane costs throughput (ILQG_FD_FUSED_MAX overrides; measured on B200)
     int fused_max = FdFusedShape<T>::OK ? 64 : 0;
@@ -1048,10 +1050,35 @@ struct CoopEngine : Engine {
         coop_step_kernel<<<n, 32, warp_bytes(), s>>>(d_g, n, nsteps, qpos, qvel, ctrl, warm, qacc, cdbl, pdbl);
         return cudaGetLastError();
     }
-    bool ilqr_supported() const override { return false; }
-    cudaError_t ilqr_rollout(const IlqrBuffers&, const ilqg_cost*, cudaStream_t) override { return cudaErrorNotSupported; }
-    cudaError_t ilqr_accept(const IlqrBuffers&, int, double*, int*, cudaStream_t) override { return cudaErrorNotSupported; }
-    cudaError_t ilqr_backward(const IlqrBuffers&, cudaStream_t) override { return cudaErrorNotSupported; }
+    // Batched iLQR for trees that only this engine runs (the humanoid: nq = 28 != nv = 27).  The reference's ILQR is undefined there
+    // (quirk Q9); this is the opt-in tangent-space extension (state x = (q (-) q*, v - v*), corrected A/B layout): rollouts one warp
+    // per (instance, alpha), the Riccati sweep one CTA per instance with every matrix in shared memory.  The backward kernel is
+    // instantiated per (nv, nu): 27 x 21 here.
+    using HumanoidSmem = BackwardSmem<27, 21, 256>;
+    bool ilqr_attr_set = false;
+    bool ilqr_supported() const override { return tab.nv == 27 && tab.nu == 21 && tab.integrator == ILQG_INT_EULER; }
+    cudaError_t ilqr_rollout(const IlqrBuffers& b, const ilqg_cost* cost_dev, cudaStream_t s) override {
+        coop_rollout_kernel<<<(unsigned)(b.ninst * b.nalpha), 32, warp_bytes(), s>>>(d_g, b, cost_dev, cdbl, pdbl);
+        return cudaGetLastError();
+    }
+    cudaError_t ilqr_accept(const IlqrBuffers& b, int accept_always, double* Jtrace, int* acc_trace, cudaStream_t s) override {
+        ilqr_accept_kernel<Topo_inverted_pendulum><<<(b.ninst + 127) / 128, 128, 0, s>>>(b, accept_always, Jtrace, acc_trace);   // (no model sizes in it)
+        const size_t T1 = (size_t)(b.N + 1) * b.ninst;
+        ilqr_commit_rt_kernel<<<(unsigned)((T1 + 127) / 128), 128, 0, s>>>(b, tab.nq, tab.nv, tab.nu);
+        return cudaGetLastError();
+    }
+    cudaError_t ilqr_backward(const IlqrBuffers& b, cudaStream_t s) override {
+        if (!ilqr_supported() || !b.cdiff) return cudaErrorNotSupported;
+        if (!ilqr_attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(ilqr_backward_kernel<27, 21, 256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HumanoidSmem));
+            if (e != cudaSuccess) return e;
+            ilqr_attr_set = true;
+        }
+        const size_t items = (size_t)b.N * b.ninst;
+        coop_cdiff_kernel<<<(unsigned)((items + 3) / 4), 128, 0, s>>>(d_g, b);
+        ilqr_backward_kernel<27, 21, 256, 1><<<b.ninst, 256, sizeof(HumanoidSmem), s>>>(b, tab.timestep);
+        return cudaGetLastError();
+    }
 };
 
 static Engine* make_engine(const ilqg_model& m) {
@@ -1710,7 +1737,9 @@ int ilqg_ilqr_create(ilqg_handle h, int ninst, int N, int nalpha, const double* 
     if (!h || !out) return ILQG_ERR_ARG;
     *out = nullptr;
     if (ninst <= 0 || N < 1 || nalpha < 1 || nalpha > 64) return fail(h, ILQG_ERR_ARG, "bad iLQR sizes");
-    if (!h->eng->ilqr_supported()) return fail(h, ILQG_ERR_UNSUPPORTED, "iLQR needs nq == nv (the reference's state vector, SURVEY quirk Q9)");
+    if (!h->eng->ilqr_supported())
+        return fail(h, ILQG_ERR_UNSUPPORTED, "no batched iLQR for this model: the thread-per-rollout engine needs nq == nv (the reference's state vector, "
+                                             "SURVEY quirk Q9); the generic engine runs the humanoid (27 dofs, 21 actuators, Euler) in tangent coordinates");
     CU(h, cudaSetDevice(h->device));
     auto* w = new ilqg_ilqr_s();
     w->h = h;
@@ -1730,6 +1759,10 @@ int ilqg_ilqr_create(ilqg_handle h, int ninst, int N, int nalpha, const double* 
     ILQR_ALLOC(w, b.alphas, nalpha); ILQR_ALLOC(w, b.nom_J, ninst); ILQR_ALLOC(w, b.accepted, ninst);
     ILQR_ALLOC(w, b.K, TI * nu * nx); ILQR_ALLOC(w, b.k, TI * nu); ILQR_ALLOC(w, b.V, (size_t)ninst * nx * nx); ILQR_ALLOC(w, b.v, (size_t)ninst * nx);
     ILQR_ALLOC(w, b.deriv, TI * nd);
+    b.cdiff = nullptr;
+    if (nq != nv) {   // quaternions in qpos: the tangent-space extension (set_layout(1) is then mandatory, see ilqr_check_layout)
+        ILQR_ALLOC(w, b.cdiff, TI * nx);
+    }
     ILQR_ALLOC(w, w->d_cost, 1);
     w->trace_cap = 256;
     ILQR_ALLOC(w, w->d_Jtrace, (size_t)w->trace_cap * ninst); ILQR_ALLOC(w, w->d_acc_trace, (size_t)w->trace_cap * ninst);
@@ -1839,10 +1872,18 @@ int ilqg_ilqr_get_host(ilqg_ilqr w, double* qpos, double* qvel, double* ctrl, do
                        int* accepted);
 
 // The three phases of ILQR::iterate (ilqr.h:179-186), each for the whole batch and asynchronous on `stream`.
+// The reference assembles A/B through column-major views of the row-major deriv blocks and takes its state as 2 nv doubles at qpos
+// (quirks Q1, Q9): with a quaternion in qpos neither is defined — only the corrected layout in tangent coordinates is.
+static int ilqr_check_layout(ilqg_ilqr w) {
+    if (w->b.cdiff && !w->b.corrected)
+        return fail(w->h, ILQG_ERR_UNSUPPORTED, "this model has nq != nv: the reference's state vector and A/B views are undefined (quirk Q9); call ilqg_ilqr_set_layout(w, 1)");
+    return ILQG_OK;
+}
 int ilqg_ilqr_forward(ilqg_ilqr w, int accept_always, void* stream) {   // forwardPass (+ A10 acceptance) + setDInit(dArray[N])
     if (!w) return ILQG_ERR_ARG;
     ilqg_handle h = w->h;
     if (!w->has_cost) return fail(h, ILQG_ERR_ARG, "ilqg_ilqr_set_cost must be called first");
+    if (int lrc = ilqr_check_layout(w)) return lrc;
     cudaStream_t s = (cudaStream_t)stream;
     CU(h, cudaSetDevice(h->device));
     auto& b = w->b;
@@ -1878,6 +1919,7 @@ int ilqg_ilqr_linearise(ilqg_ilqr w, void* stream) {                     // FD a
 int ilqg_ilqr_backward(ilqg_ilqr w, void* stream) {                      // initV + backwardPass
     if (!w) return ILQG_ERR_ARG;
     ilqg_handle h = w->h;
+    if (int lrc = ilqr_check_layout(w)) return lrc;
     CU(h, cudaSetDevice(h->device));
     CU(h, h->eng->ilqr_backward(w->b, (cudaStream_t)stream));
     h->launches += 1;

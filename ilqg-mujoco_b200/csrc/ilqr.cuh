@@ -36,6 +36,8 @@ struct IlqrBuffers {
     double* mu_i;       // [ninst] per-instance mu under the opt-in schedule, else NULL
     double mu_factor, mu_min, mu_max;
     int corrected;      // 0: A/B through the reference's column-major views of the row-major deriv blocks (quirk Q1); 1: transposed back
+    double* cdiff;      // [T][ninst][nx] x*_{n-1} (-) x*_n in the tangent space, filled before the backward pass for models with
+                        // quaternions (nq != nv: the opt-in extension beyond quirk Q9), else NULL: plain differences of qpos | qvel
     int* iter_dev;      // iterations done (device counter: the trace slot of a pass is taken from it, so that a captured CUDA graph
                         // of iterations can be replayed), or NULL for a pass that is not an iteration (the constructor's rollout)
     int trace_cap;      // slots of the cost / accepted-alpha traces
@@ -142,6 +144,27 @@ __global__ void ilqr_commit_kernel(IlqrBuffers b) {
     }
     if (t == 0 && b.iter_dev) *b.iter_dev += 1;   // (the accept kernel, which reads the counter, has finished)
     if (n == b.N) {   // setDInit(dArray[N]) (ilqr.h:183): the next pass starts from the nominal's first knot
+        for (int c = 0; c < NQ; c++) b.init_q[(size_t)i * NQ + c] = b.nom_q[kn * NQ + c];
+        for (int c = 0; c < NV; c++) { b.init_v[(size_t)i * NV + c] = b.nom_v[kn * NV + c]; b.init_w[(size_t)i * NV + c] = b.nom_w[kn * NV + c]; }
+    }
+}
+
+// the same copy for a model whose sizes are only known at run time (the warp-cooperative engine)
+__global__ void ilqr_commit_rt_kernel(IlqrBuffers b, int NQ, int NV, int NU) {
+    const int ninst = b.ninst, Tn = b.N + 1;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x, T1 = (size_t)Tn * ninst;
+    if (t >= T1) return;
+    const int n = (int)(t / ninst), i = (int)(t - (size_t)n * ninst);
+    const int acc = b.accepted[i];
+    const size_t kn = t;
+    if (acc >= 0) {
+        const size_t cn = (size_t)acc * T1 + kn;
+        for (int c = 0; c < NQ; c++) b.nom_q[kn * NQ + c] = b.cand_q[cn * NQ + c];
+        for (int c = 0; c < NV; c++) { b.nom_v[kn * NV + c] = b.cand_v[cn * NV + c]; b.nom_w[kn * NV + c] = b.cand_w[cn * NV + c]; }
+        for (int c = 0; c < NU; c++) b.nom_u[kn * NU + c] = b.cand_u[cn * NU + c];
+    }
+    if (t == 0 && b.iter_dev) *b.iter_dev += 1;
+    if (n == b.N) {
         for (int c = 0; c < NQ; c++) b.init_q[(size_t)i * NQ + c] = b.nom_q[kn * NQ + c];
         for (int c = 0; c < NV; c++) { b.init_v[(size_t)i * NV + c] = b.nom_v[kn * NV + c]; b.init_w[(size_t)i * NV + c] = b.nom_w[kn * NV + c]; }
     }
@@ -395,9 +418,11 @@ __global__ void __launch_bounds__(LANES * GROUPS) ilqr_backward_kernel(IlqrBuffe
     SM& s = all[g];
     const int ninst = b.ninst;
     const double mu = (b.mu_i && live) ? b.mu_i[i] : b.mu;
-    // groups are whole warps or aligned sub-warps; sync the lanes of this group only
-    const unsigned gmask = LANES == 32 ? 0xffffffffu : (((1u << LANES) - 1u) << ((threadIdx.x % 32) / LANES * LANES));
-    auto gsync = [&]() { __syncwarp(gmask); };
+    // groups are whole warps or aligned sub-warps (sync the lanes of this group only) — or, for large state vectors, the whole
+    // CTA works on one instance (LANES > 32, GROUPS = 1: block barrier)
+    static_assert(LANES <= 32 || GROUPS == 1, "a group wider than a warp is the whole CTA");
+    const unsigned gmask = LANES >= 32 ? 0xffffffffu : (((1u << LANES) - 1u) << ((threadIdx.x % 32) / LANES * LANES));
+    auto gsync = [&]() { if constexpr (LANES > 32) __syncthreads(); else __syncwarp(gmask); };
 #define CMX(M, r, c, rows) ((M)[(r) + (c) * (rows)])
     if (live) {
         // initV (ilqr.h:100-107): v = dgdx at knot 0, V = v' v
@@ -429,7 +454,8 @@ __global__ void __launch_bounds__(LANES * GROUPS) ilqr_backward_kernel(IlqrBuffe
             }
             for (int e = lane; e < NX; e += LANES) {
                 s.q[e] = deriv[2 * NV * NV + NV * NU + e];
-                s.c[e] = e < NV ? b.nom_q[kp * NQ + e] - b.nom_q[kn * NQ + e] : b.nom_v[kp * NV + (e - NV)] - b.nom_v[kn * NV + (e - NV)];
+                if (b.cdiff) s.c[e] = b.cdiff[kn * NX + e];   // tangent-space difference (models with quaternions)
+                else s.c[e] = e < NV ? b.nom_q[kp * NQ + e] - b.nom_q[kn * NQ + e] : b.nom_v[kp * NV + (e - NV)] - b.nom_v[kn * NV + (e - NV)];
             }
             for (int e = lane; e < NU; e += LANES) s.r[e] = deriv[2 * NV * NV + NV * NU + 2 * NV + e];
         }

@@ -20,6 +20,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+extern int mjo_ilqr_corrected_layout;
+
 typedef struct mjo_ilqr {
     const ilqg_model* m;
     int N, nq, nv, nu, nx, nd;
@@ -38,6 +40,34 @@ typedef struct mjo_ilqr {
 
 #define CM(M, r, c, rows) ((M)[(r) + (size_t)(c) * (rows)])
 
+/* x_a (-) x_b in the TANGENT space of the configuration manifold: out[0..nv) = position part, out[nv..2nv) = velocity part.
+   For slide / hinge dofs this is the plain difference the reference takes on raw qpos memory (ilqr.h:126,161-163); for a free
+   joint's orientation it is MuJoCo's mju_subQuat: the body-frame rotation vector w with q_b * quat(w) = q_a.  The reference's
+   own state vector is "2 nv doubles starting at qpos" and is undefined when nq != nv (quirk Q9): this is the opt-in extension
+   that makes Differentiator / ILQR meaningful for the humanoid, in the same coordinates the FD blocks of
+   calcMJDerivatives already use (mjderivative.cpp:152-169). */
+void mjo_state_diff(const ilqg_model* m, const double* qa, const double* va, const double* qb, const double* vb, double* out) {
+    int nv = m->nv;
+    for (int j = 0; j < m->njnt; j++) {
+        int qadr = m->jnt_qposadr[j], dadr = m->jnt_dofadr[j];
+        if (m->jnt_type[j] == ILQG_JNT_FREE) {
+            for (int k = 0; k < 3; k++) out[dadr + k] = qa[qadr + k] - qb[qadr + k];
+            const double *a = qa + qadr + 3, *b = qb + qadr + 3;
+            double na = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2] + a[3] * a[3]), nb = sqrt(b[0] * b[0] + b[1] * b[1] + b[2] * b[2] + b[3] * b[3]);
+            double A[4] = {a[0] / na, a[1] / na, a[2] / na, a[3] / na}, B[4] = {b[0] / nb, -b[1] / nb, -b[2] / nb, -b[3] / nb}; /* conj(q_b) */
+            double d[4] = {B[0] * A[0] - B[1] * A[1] - B[2] * A[2] - B[3] * A[3], B[0] * A[1] + B[1] * A[0] + B[2] * A[3] - B[3] * A[2],
+                           B[0] * A[2] - B[1] * A[3] + B[2] * A[0] + B[3] * A[1], B[0] * A[3] + B[1] * A[2] - B[2] * A[1] + B[3] * A[0]};
+            double sn = sqrt(d[1] * d[1] + d[2] * d[2] + d[3] * d[3]);
+            double ang = 2 * atan2(sn, d[0]);
+            if (ang > 3.14159265358979323846) ang -= 2 * 3.14159265358979323846;
+            double sc = sn < 1e-15 ? 0.0 : ang / sn;
+            for (int k = 0; k < 3; k++) out[dadr + 3 + k] = d[1 + k] * sc;
+        } else
+            out[dadr] = qa[qadr] - qb[qadr];
+    }
+    for (int i = 0; i < nv; i++) out[nv + i] = va[i] - vb[i];
+}
+
 static void knot_store(mjo_ilqr* il, int n, const mjo_data* d) {
     memcpy(il->qpos + (size_t)n * il->nq, d->qpos, sizeof(double) * il->nq);
     memcpy(il->qvel + (size_t)n * il->nv, d->qvel, sizeof(double) * il->nv);
@@ -54,7 +84,9 @@ __attribute__((unused)) static void knot_load(const mjo_ilqr* il, int n, mjo_dat
 }
 
 mjo_ilqr* mjo_ilqr_create(const ilqg_model* m, int N, mjo_cost_fn cost, void* user) {
-    if (m->nq != m->nv) return NULL; /* the reference's state vector assumes nq == nv (quirk Q9) */
+    /* the reference's state vector assumes nq == nv (quirk Q9); with quaternions only the tangent-space extension (corrected
+       A/B layout, mjo_state_diff) is defined */
+    if (m->nq != m->nv && !mjo_ilqr_corrected_layout) return NULL;
     mjo_ilqr* il = (mjo_ilqr*)calloc(1, sizeof(mjo_ilqr));
     il->m = m; il->N = N; il->nq = m->nq; il->nv = m->nv; il->nu = m->nu; il->nx = 2 * m->nv;
     il->nd = m->nv * (2 * m->nv + m->nu) + 2 * m->nv + m->nu;
@@ -129,7 +161,7 @@ double mjo_ilqr_forward_pass(mjo_ilqr* il, double alpha) {
         const double* us = il->ctrl + (size_t)n * nu;
         const double* K = il->K + (size_t)n * nu * nx;
         const double* k = il->k + (size_t)n * nu;
-        for (int i = 0; i < nv; i++) { x[i] = d->qpos[i] - xs_q[i]; x[nv + i] = d->qvel[i] - xs_v[i]; }
+        mjo_state_diff(il->m, d->qpos, d->qvel, xs_q, xs_v, x);
         double unew[ILQG_MAXU];
         for (int r = 0; r < nu; r++) {
             double s = 0;
@@ -239,10 +271,8 @@ void mjo_ilqr_backward_pass(mjo_ilqr* il) {
         const double* q = il->deriv + (size_t)n * il->nd + 2 * nv * nv + nv * nu;
         const double* r_ = q + 2 * nv;
         double c[2 * ILQG_MAXV];
-        for (int i = 0; i < nv; i++) {
-            c[i] = il->qpos[(size_t)(n - 1) * il->nq + i] - il->qpos[(size_t)n * il->nq + i];
-            c[nv + i] = il->qvel[(size_t)(n - 1) * nv + i] - il->qvel[(size_t)n * nv + i];
-        }
+        mjo_state_diff(il->m, il->qpos + (size_t)(n - 1) * il->nq, il->qvel + (size_t)(n - 1) * nv, il->qpos + (size_t)n * il->nq,
+                       il->qvel + (size_t)n * nv, c);
         for (int i = 0; i < nx; i++) CM(V, i, i, nx) += il->mu; /* Q3 */
         /* VB = V B (nx x nu), VA = V A */
         double VB[2 * ILQG_MAXV * ILQG_MAXU], S[ILQG_MAXU * ILQG_MAXU], rhsK[ILQG_MAXU * 2 * ILQG_MAXV], rhsk[ILQG_MAXU];

@@ -169,3 +169,50 @@ def test_mu_schedule_matches_oracle(pkg, handles, oracle, omodels):
     assert np.array_equal(out["accepted"], ref["accepted"])
     assert rel(out["J"], ref["J"]) < 1e-8
     assert rel(ref["J"][:, -1], const["J"][:, -1]) > 1e-6      # the schedule is not a no-op
+
+
+def test_humanoid_ilqr_in_tangent_coordinates_matches_oracle(pkg, oracle, omodels):
+    """the reference's ILQR takes "2 nv doubles at qpos" as its state, which is undefined with the
+    humanoid's quaternion (nq = 28, nv = 27).  The opt-in extension keeps the reference's algorithm (ilqr.h:116-186) in TANGENT
+    coordinates — x (-) x* through mju_subQuat for the free joint, A/B from the FD blocks, which calcMJDerivatives already takes
+    in those coordinates — on the warp-cooperative engine; the oracle carries the same extension (mjo_state_diff)."""
+    h = pkg.Handle(pkg.Model.named("humanoid"), 0)
+    om = omodels["humanoid"]
+    n, N = 3, 6
+    q, v, u, w = scenario_states("humanoid", n, seed=5)     # airborne: smooth dynamics, the parity is not at the mercy of contact flips
+    u = u * 0
+    cost = oracle.make_cost(q2=[0, 0, 2.0, 0, 1, 1, 0], q1=[0, 0, -5.2], v2=[0.05] * 27, u2=[0.02] * 21)   # height, uprightness, effort
+    with pytest.raises(pkg.IlqgError):      # the reference's layout is refused for this model
+        il = pkg.Ilqr(h, n, N, (1.0,))
+        il.set_cost(cost)
+        il.init_host(q, v, u, w)
+        il.iterate(1, True)
+    il.close()
+    al = (1.0, 0.5, 0.25, 0.125)
+    sched = (2.0, 1.0, 1e8)
+    # one iteration: open-loop pass, then gains and value model of the 54-dimensional Riccati sweep
+    ref1 = oracle.ilqr_run_batch(om, N, 1, q, v, u, w, cost, alphas=al, accept_always=False, corrected=True, mu_schedule=sched)
+    il = pkg.Ilqr(h, n, N, al)
+    il.set_cost(cost)
+    il.set_layout(True)
+    il.set_mu_schedule(*sched)
+    il.init_host(q, v, u, w)
+    il.iterate(1, False)
+    out1 = il.get()
+    assert rel(out1["J"], ref1["J"]) < 1e-9
+    assert np.allclose(out1["qpos"], ref1["qpos"], rtol=1e-8, atol=1e-9)
+    for key in ("K", "k", "V", "v"):
+        a_, b_ = (out1[key][:, 1:], ref1[key][:, 1:]) if key in ("K", "k") else (out1[key], ref1[key])
+        assert rel(a_, b_) < 1e-5, (key, rel(a_, b_))
+    # several iterations with the ladder: cost trace and accepted alphas
+    ref = oracle.ilqr_run_batch(om, N, 4, q, v, u, w, cost, alphas=al, accept_always=False, corrected=True, mu_schedule=sched)
+    il.init_host(q, v, u, w)
+    il.set_mu(1000.0)
+    il.iterate(4, False)
+    out = il.get()
+    il.close()
+    h.close()
+    assert np.array_equal(out["accepted"][:, -4:], ref["accepted"])
+    assert rel(out["J"][:, -4:], ref["J"]) < 1e-6
+    assert (ref["accepted"] >= 0).any() and (np.diff(ref["J"], axis=1) <= 1e-12).all()   # the ladder accepts steps and the cost falls
+    assert np.allclose(np.linalg.norm(out["qpos"][:, :, 3:7], axis=2), 1.0, atol=1e-9)

@@ -372,6 +372,53 @@ def bench_hopper_ilqr(pkg, dev_index, ninst, niter, reps, world, rank):
     return res
 
 
+def bench_humanoid_ilqr(pkg, dev_index, ninst, niter, reps, world, rank):
+    """humanoid iLQR (nq = 28 != nv = 27) in tangent coordinates on the warp-cooperative engine, N = 10, `ninst`
+    problems per GPU (one CTA per instance in the 54 x 54 Riccati sweep), 4 concurrent line-search rollouts, mu schedule."""
+    import torch
+    import torch.distributed as dist
+    from ilqg_mujoco_b200 import workload as wl
+    dev = f"cuda:{dev_index}"
+    model = pkg.Model.named("humanoid")
+    h = pkg.Handle(model, dev_index)
+    dq, dv, du, dw, _ = wl.humanoid_states(h, ninst, seed=50 + rank, device=dev)
+    du = du * 0.0
+    cost = pkg.make_cost(q2=[0, 0, 2.0, 0, 1, 1, 0], q1=[0, 0, -5.2], v2=[0.05] * 27, u2=[0.02] * 21)   # Humanoid::humanoidCost()
+    il = pkg.Ilqr(h, ninst, 10, tuple(0.5 ** a for a in range(4)))
+    il.set_cost(cost)
+    il.set_layout(True)
+    il.set_mu_schedule(2.0, 1.0, 1e8)
+    stream = torch.cuda.current_stream().cuda_stream
+    times = []
+    nwarm = 3
+    for r in range(reps + nwarm):
+        il.set_mu(1000.0)
+        il.init_dev(dq, dv, du, dw, stream=stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        il.iterate(niter, accept_always=False, stream=stream)
+        e1.record()
+        e1.synchronize()
+        if r >= nwarm:
+            times.append(e0.elapsed_time(e1))
+    out = il.get()
+    J = out["J"][:, -niter:]
+    t = torch.tensor([sum(times)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    res = {"metric": "iLQR iterations/sec (humanoid, tangent-space extension, N=10, 4 concurrent line-search rollouts, fp64)",
+           "value": world * ninst * niter * reps / (float(t[0]) * 1e-3), "unit": "iterations/s", "instances_per_gpu": ninst, "iterations": niter,
+           "ms_per_batch_iteration": float(t[0]) / (reps * niter), "mode": "opt-in: tangent-space state, corrected A/B layout, backtracking ladder, mu schedule",
+           "finite_instances": int(np.isfinite(J).all(axis=1).sum()), "monotone_instances": int((np.diff(J, axis=1) <= 1e-9 * np.abs(J[:, :-1])).all(axis=1).sum()),
+           "accepted_steps_share": float((out["accepted"][:, -niter:] >= 0).mean())}
+    il.close()
+    h.close()
+    return res
+
+
 # ------------------------------------------------------------------ hopper T=1000, knots sharded + all-gather (BASELINE configs[4])
 def bench_t1000(pkg, dev_index, T, steps, world, rank):
     import torch
@@ -804,6 +851,7 @@ def run_gpu_arm(args):
         torch.cuda.synchronize()
         secondary.append(bench_ilqr(pkg, local, args.ilqr_instances, 10, 3, world, rank, with_cpu=(world == 1 and rank == 0)))
         secondary.append(bench_hopper_ilqr(pkg, local, 1024, 10, 2, world, rank))
+        secondary.append(bench_humanoid_ilqr(pkg, local, 296, 6, 2, world, rank))
         secondary.append(bench_t1000(pkg, local, 1000, 20, world, rank))
         secondary.append(bench_humanoid(pkg, local, args.humanoid_knots, 3, world, rank, with_cpu=(world == 1 and rank == 0)))
         if world == 1 and rank == 0:

@@ -5,6 +5,7 @@
 #include <cstdlib>
 
 #include "hopper/hopper.h"
+#include "humanoid/humanoid.h"
 #include "inverted_pendulum/inverted_pendulum.h"
 
 int main(int argc, const char** argv) {
@@ -21,6 +22,17 @@ int main(int argc, const char** argv) {
             hopper.forward();
             printf("{\"step\": %d, \"x\": %.9g, \"z\": %.9g, \"pitch\": %.9g, \"xdot\": %.9g, \"cost\": %.9g, \"ctrl\": [%.9g, %.9g, %.9g]}\n", s, d->qpos[0],
                    d->qpos[1], d->qpos[2], d->qvel[0], hopper.J[Hopper::maxIterUtilConvergence - 1], d->ctrl[0], d->ctrl[1], d->ctrl[2]);
+        }
+        mj_deleteData(d);
+        mj_deleteModel(m);
+        return 0;
+    }
+    if (m->nv == Humanoid::nv && m->nu == Humanoid::nu) {   // res/humanoid.xml: the humanoid task (no reference equivalent)
+        Humanoid humanoid(m, d);
+        for (int s = 0; s < nsteps; s++) {
+            humanoid.forward();
+            printf("{\"step\": %d, \"x\": %.9g, \"z\": %.9g, \"quat\": [%.9g, %.9g, %.9g, %.9g], \"cost\": %.9g}\n", s, d->qpos[0], d->qpos[2], d->qpos[3],
+                   d->qpos[4], d->qpos[5], d->qpos[6], humanoid.J[Humanoid::maxIterUtilConvergence - 1]);
         }
         mj_deleteData(d);
         mj_deleteModel(m);

@@ -8,6 +8,7 @@
 
 #include "inverted_pendulum/cost.h"
 #include "hopper/hopper.h"
+#include "humanoid/humanoid.h"
 #include "inverted_pendulum/inverted_pendulum.h"
 #include "mjderivative.h"
 #include "update.h"
@@ -291,7 +292,70 @@ void Hopper::forward() {
     mj_step(m, d);                       // proceed simulation
 }
 
+// ---- humanoid task (no reference equivalent: SURVEY 8f row 3; tangent-space iLQR beyond quirk Q9)
+ilqg_cost Humanoid::humanoidCost() {
+    ilqg_cost c;
+    memset(&c, 0, sizeof c);
+    c.q2[2] = 2.0; c.q1[2] = -5.2;       // 2 (z - 1.3)^2 up to a constant
+    c.q2[4] = 1.0; c.q2[5] = 1.0;        // root quaternion x, y: upright torso
+    for (int i = 0; i < nv; i++) c.v2[i] = 0.05;
+    for (int i = 0; i < nu; i++) c.u2[i] = 0.02;
+    return c;
+}
+static void humanoidCheck(mjModel* m, int rc, const char* what) {
+    if (rc) {
+        char buf[512];
+        snprintf(buf, sizeof buf, "Humanoid: %s failed (%d): %s", what, rc, ilqg_last_error(m->gpu));
+        mju_error(buf);
+    }
+}
+Humanoid::Humanoid(mjModel* m, mjData* d) : m(m), d(d) {
+    cost = humanoidCost();
+    for (auto i = 0; i < 10; i++) mj_step(m, d);
+    double alphas[nalpha];
+    for (int a = 0; a < nalpha; a++) alphas[a] = 1.0 / (1 << a);
+    humanoidCheck(m, ilqg_ilqr_create(m->gpu, 1, N, nalpha, alphas, &ws), "ilqg_ilqr_create");
+    humanoidCheck(m, ilqg_ilqr_set_cost(ws, &cost), "ilqg_ilqr_set_cost");
+    humanoidCheck(m, ilqg_ilqr_set_layout(ws, 1), "ilqg_ilqr_set_layout");
+    humanoidCheck(m, ilqg_ilqr_set_mu_schedule(ws, 2.0, 1.0, 1e8), "ilqg_ilqr_set_mu_schedule");
+    humanoidCheck(m, ilqg_ilqr_init_host(ws, d->qpos, d->qvel, d->ctrl, d->qacc_warmstart), "ilqg_ilqr_init_host");
+    for (int i = 0; i < maxIterUtilConvergence; i++) J[i] = 0;
+}
+Humanoid::~Humanoid() { ilqg_ilqr_destroy(ws); }
+void Humanoid::forward() {
+    humanoidCheck(m, ilqg_ilqr_set_state_host(ws, d->qpos, d->qvel, d->qacc_warmstart), "ilqg_ilqr_set_state_host");
+    humanoidCheck(m, ilqg_ilqr_iterate(ws, maxIterUtilConvergence, 0, NULL), "ilqg_ilqr_iterate");
+    mjtNum u0[nu];
+    const int done = ilqg_ilqr_iterations_done(ws);
+    std::vector<mjtNum> Jt(done < 256 ? done : 256);
+    humanoidCheck(m, ilqg_ilqr_get_first_control_host(ws, u0, Jt.data()), "ilqg_ilqr_get_first_control_host");
+    for (int i = 0; i < maxIterUtilConvergence; i++) J[i] = Jt[Jt.size() - maxIterUtilConvergence + i];
+    mju_copy(d->ctrl, u0, nu);           // get first u (knot N is the initial one, ilqr.h:52)
+    mj_step(m, d);                       // proceed simulation
+}
+
 // ---- C entry points for tests (ctypes): the headless MPC demos and a Differentiator<6,3> probe
+extern "C" int ilqg_host_humanoid_mpc(const char* model_path, const double* qpos0, const double* qvel0, int nmpc, double* trace /* [nmpc][76] */,
+                                      double* Jtrace /* [nmpc][4] */) {
+    char err[512] = "";
+    mjModel* m = mj_loadXML(model_path, NULL, err, sizeof err);
+    if (!m) { fprintf(stderr, "%s\n", err); return 1; }
+    mjData* d = mj_makeData(m);
+    if (qpos0) mju_copy(d->qpos, qpos0, m->nq);
+    if (qvel0) mju_copy(d->qvel, qvel0, m->nv);
+    {
+        Humanoid hm(m, d);
+        for (int s = 0; s < nmpc; s++) {
+            hm.forward();
+            if (trace) { mju_copy(trace + 76 * s, d->qpos, 28); mju_copy(trace + 76 * s + 28, d->qvel, 27); mju_copy(trace + 76 * s + 55, d->ctrl, 21); }
+            if (Jtrace) mju_copy(Jtrace + Humanoid::maxIterUtilConvergence * s, hm.J, Humanoid::maxIterUtilConvergence);
+        }
+    }
+    mj_deleteData(d);
+    mj_deleteModel(m);
+    return 0;
+}
+
 extern "C" int ilqg_host_hopper_mpc(const char* model_path, const double* qpos0, const double* qvel0, int nmpc, double* trace /* [nmpc][15] */,
                                     double* Jtrace /* [nmpc][10] */) {
     char err[512] = "";

@@ -173,3 +173,35 @@ def test_applied_forces_are_refused_not_ignored(hostlib, use_xfrc):
     n = hostlib.ilqg_host_applied_force_probe(path, use_xfrc, msg, 256)
     assert n == 3, (n, msg.value)
     assert b"applied" in msg.value and b"(5)" in msg.value
+
+
+def test_humanoid_task_mpc_matches_oracle(hostlib, oracle, omodels):
+    """the Humanoid task class (host/humanoid/humanoid.h) — tangent-space iLQR on the warp-cooperative engine
+    (nq = 28 != nv = 27: the reference's own ILQR is undefined here, quirk Q9) — against the oracle's restated MPC loop with
+    the same extension: the first MPC step's cost trace and the state the plant reaches."""
+    om = omodels["humanoid"]
+    nmpc, N, niter = 2, 10, 4
+    tr = np.zeros((nmpc, 76)); Jt = np.zeros((nmpc, niter))
+    path = os.path.join(PKG, "models", "humanoid.ilqgm").encode()
+    q0 = np.zeros(28); q0[2] = 1.45; q0[3] = 1.0; q0[3:7] += [0.0, 0.03, -0.02, 0.01]; q0[3:7] /= np.linalg.norm(q0[3:7])
+    q0[7:] = np.linspace(-0.1, 0.1, 21)
+    v0 = np.linspace(-0.2, 0.2, 27)
+    assert hostlib.ilqg_host_humanoid_mpc(path, oracle._p(q0), oracle._p(v0), nmpc, oracle._p(tr), oracle._p(Jt)) == 0
+    cost = oracle.make_cost(q2=[0, 0, 2.0, 0, 1, 1, 0], q1=[0, 0, -5.2], v2=[0.05] * 27, u2=[0.02] * 21)
+    al = np.array([0.5 ** a for a in range(4)])
+    tr_o = np.zeros((nmpc, 76)); Jt_o = np.zeros((nmpc, niter)); acc_o = np.zeros((nmpc, niter), np.int32)
+    L = oracle.lib()
+    L.mjo_ilqr_set_corrected_layout(1)
+    L.mjo_ilqr_set_mu_schedule(C.c_double(2.0), C.c_double(1.0), C.c_double(1e8))
+    try:
+        L.mjo_mpc_run(om.ptr, oracle._p(q0), oracle._p(v0), 10, N, niter, nmpc, oracle._p(cost), oracle._p(al), 4, 0, oracle._p(tr_o), oracle._p(Jt_o),
+                      oracle._p(acc_o), None, None, None, None, None, None, None)
+    finally:
+        L.mjo_ilqr_set_corrected_layout(0)
+        L.mjo_ilqr_set_mu_schedule(C.c_double(1.0), C.c_double(1e-6), C.c_double(1e10))
+    assert np.isfinite(tr).all() and np.isfinite(Jt).all()
+    for J in (Jt, Jt_o):
+        assert (np.diff(J, axis=1) <= 1e-9 * np.abs(J[:, :-1])).all()      # the ladder never accepts a worse trajectory
+    assert np.allclose(Jt[0], Jt_o[0], rtol=1e-7, atol=1e-8)
+    assert np.allclose(tr[0], tr_o[0], rtol=1e-6, atol=1e-7)
+    assert np.allclose(np.linalg.norm(tr[:, 3:7], axis=1), 1.0, atol=1e-9)

@@ -331,6 +331,11 @@ DEV void coop_pos(const GModel* __restrict__ g, CoopMem& w, int lane, const int*
                 V3 ax = mulv(R, gl3(m.jnt_axis[j]));
                 gs3(w.anchor + 3 * j, an);
                 gs3(w.axis + 3 * j, ax);
+                if (ty == ILQG_JNT_BALL) {   // rotate about the anchor by the joint's own (normalised) quaternion
+                    quat = qmul(quat, qnormalized({w.q[qa], w.q[qa + 1], w.q[qa + 2], w.q[qa + 3]}));
+                    pos = an - mulv(q2m(quat), gl3(m.jnt_pos[j]));
+                    continue;
+                }
                 double qq = w.q[qa] - m.qpos0[qa];
                 if (ty == ILQG_JNT_SLIDE) pos = pos + qq * ax;
                 else {
@@ -394,6 +399,13 @@ DEV void coop_pos(const GModel* __restrict__ g, CoopMem& w, int lane, const int*
                 gs3(w.cdof + 6 * (da + 3 + i) + 3, cross(ax, off));
             }
             for (int i = 0; i < 6; i++) w.dspr[da + i] = 0;
+        } else if (ty == ILQG_JNT_BALL) {   // the body's three axes about the anchor (mj_comPos)
+            for (int i = 0; i < 3; i++) {
+                V3 ax = {w.xmat[9 * b + i], w.xmat[9 * b + 3 + i], w.xmat[9 * b + 6 + i]};
+                gs3(w.cdof + 6 * (da + i), ax);
+                gs3(w.cdof + 6 * (da + i) + 3, cross(ax, off));
+                w.dspr[da + i] = 0;
+            }
         } else {
             if (ty == ILQG_JNT_SLIDE) {
                 gs3(w.cdof + 6 * da, {0, 0, 0});
@@ -439,7 +451,7 @@ DEV void coop_pos(const GModel* __restrict__ g, CoopMem& w, int lane, const int*
         int side = 0;
         bool nearlim = false;
         double dist = 0;
-        if (j < nj && m.jnt_limited[j] && m.jnt_type[j] != ILQG_JNT_FREE) {
+        if (j < nj && m.jnt_limited[j] && m.jnt_type[j] != ILQG_JNT_FREE && m.jnt_type[j] != ILQG_JNT_BALL) {
             double value = w.q[m.jnt_qposadr[j]];
             double dlo = value - m.jnt_range[j][0], dhi = m.jnt_range[j][1] - value;
             if (dlo < m.jnt_margin[j]) { side = -1; dist = dlo; }
@@ -648,6 +660,9 @@ DEV void coop_vel(const GModel* __restrict__ g, CoopMem& w, const double* vv, in
                     for (int i = 0; i < 3; i++) { putdot(da + i, {{0, 0, 0}, {0, 0, 0}}); cv = cv + vv[da + i] * cd(da + i); }
                     for (int i = 3; i < 6; i++) putdot(da + i, cross_motion(cv, cd(da + i)));
                     for (int i = 3; i < 6; i++) cv = cv + vv[da + i] * cd(da + i);
+                } else if (m.jnt_type[j] == ILQG_JNT_BALL) {   // all three axes turn with the velocity before the joint (mj_comVel)
+                    for (int i = 0; i < 3; i++) putdot(da + i, cross_motion(cv, cd(da + i)));
+                    for (int i = 0; i < 3; i++) cv = cv + vv[da + i] * cd(da + i);
                 } else {
                     putdot(da, cross_motion(cv, cd(da)));
                     cv = cv + vv[da] * cd(da);
@@ -675,7 +690,7 @@ DEV void coop_vel(const GModel* __restrict__ g, CoopMem& w, const double* vv, in
         double f = 0;
         for (int k = 0; k < 6; k++) f -= w.cdof[6 * i + k] * w.cfrc[6 * b + k];
         f -= m.dof_damping[i] * vv[i];
-        if (m.jnt_type[j] != ILQG_JNT_FREE && m.jnt_stiffness[j] != 0) f -= m.jnt_stiffness[j] * w.dspr[i];
+        if (m.jnt_type[j] != ILQG_JNT_FREE && m.jnt_type[j] != ILQG_JNT_BALL && m.jnt_stiffness[j] != 0) f -= m.jnt_stiffness[j] * w.dspr[i];
         w.fb[i] = f;
     }
     for (int r = lane; r < ne; r += 32) {
@@ -1108,7 +1123,10 @@ __global__ void __launch_bounds__(32) coop_qpos_kernel(const GModel* __restrict_
             double c0 = 0;
             if (cost && sgn > 0) c0 = coop_cost_eval(cost, w.q, w.v, w.u, nq, nv, nu);
             const int j = m.dof_jntid[i];
-            if (m.jnt_type[j] == ILQG_JNT_FREE && i >= m.jnt_dofadr[j] + 3) {
+            if (m.jnt_type[j] == ILQG_JNT_BALL) {   // mjderivative.cpp:152-156
+                const int a = i - m.jnt_dofadr[j];
+                quat_integrate(&w.q[m.jnt_qposadr[j]], V3{a == 0 ? se : 0.0, a == 1 ? se : 0.0, a == 2 ? se : 0.0}, 1.0);
+            } else if (m.jnt_type[j] == ILQG_JNT_FREE && i >= m.jnt_dofadr[j] + 3) {
                 const int a = i - m.jnt_dofadr[j] - 3;
                 quat_integrate(&w.q[m.jnt_qposadr[j] + 3], V3{a == 0 ? se : 0.0, a == 1 ? se : 0.0, a == 2 ? se : 0.0}, 1.0);
             } else
@@ -1200,7 +1218,9 @@ DEV void coop_step_once(const GModel* __restrict__ g, CoopMem& w, int lane, doub
         if (m.jnt_type[j] == ILQG_JNT_FREE) {
             for (int c = 0; c < 3; c++) w.q[qa + c] += h * w.v[da + c];
             quat_integrate(&w.q[qa + 3], V3{w.v[da + 3], w.v[da + 4], w.v[da + 5]}, h);
-        } else
+        } else if (m.jnt_type[j] == ILQG_JNT_BALL)
+            quat_integrate(&w.q[qa], V3{w.v[da], w.v[da + 1], w.v[da + 2]}, h);
+        else
             w.q[qa] += h * w.v[da];
     }
     __syncwarp();
@@ -1242,17 +1262,19 @@ __global__ void __launch_bounds__(32) coop_step_kernel(const GModel* __restrict_
 DEV void coop_state_diff(const ilqg_model& m, const double* qa, const double* va, const double* qb, const double* vb, double* out, int lane) {
     const int nv = m.nv;
     for (int j = lane; j < m.njnt; j += 32) {
-        const int qadr = m.jnt_qposadr[j], dadr = m.jnt_dofadr[j];
-        if (m.jnt_type[j] == ILQG_JNT_FREE) {
-            for (int k = 0; k < 3; k++) out[dadr + k] = qa[qadr + k] - qb[qadr + k];
-            const Q4 A = qnormalized({qa[qadr + 3], qa[qadr + 4], qa[qadr + 5], qa[qadr + 6]});
-            const Q4 Bq = qnormalized({qb[qadr + 3], qb[qadr + 4], qb[qadr + 5], qb[qadr + 6]});
+        int qadr = m.jnt_qposadr[j], dadr = m.jnt_dofadr[j];
+        if (m.jnt_type[j] == ILQG_JNT_FREE || m.jnt_type[j] == ILQG_JNT_BALL) {
+            const int fr = m.jnt_type[j] == ILQG_JNT_FREE ? 3 : 0;   // a free joint carries a position in front of its quaternion
+            for (int k = 0; k < fr; k++) out[dadr + k] = qa[qadr + k] - qb[qadr + k];
+            qadr += fr; dadr += fr;
+            const Q4 A = qnormalized({qa[qadr], qa[qadr + 1], qa[qadr + 2], qa[qadr + 3]});
+            const Q4 Bq = qnormalized({qb[qadr], qb[qadr + 1], qb[qadr + 2], qb[qadr + 3]});
             const Q4 d = qmul({Bq.w, -Bq.x, -Bq.y, -Bq.z}, A);
             const double sn = sqrt(d.x * d.x + d.y * d.y + d.z * d.z);
             double ang = 2 * atan2(sn, d.w);
             if (ang > 3.14159265358979323846) ang -= 2 * 3.14159265358979323846;
             const double sc = sn < 1e-15 ? 0.0 : ang / sn;
-            out[dadr + 3] = d.x * sc; out[dadr + 4] = d.y * sc; out[dadr + 5] = d.z * sc;
+            out[dadr] = d.x * sc; out[dadr + 1] = d.y * sc; out[dadr + 2] = d.z * sc;
         } else
             out[dadr] = qa[qadr] - qb[qadr];
     }

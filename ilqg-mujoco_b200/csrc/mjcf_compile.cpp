@@ -307,6 +307,7 @@ struct Compiler {
             if (*ty == "hinge") type = ILQG_JNT_HINGE;
             else if (*ty == "slide") type = ILQG_JNT_SLIDE;
             else if (*ty == "free") type = ILQG_JNT_FREE;
+            else if (*ty == "ball") type = ILQG_JNT_BALL;
             else return cx.fail("unsupported joint type '" + *ty + "'");
         }
         if (const std::string* nm = e->get("name")) jntByName[*nm] = j;
@@ -314,7 +315,7 @@ struct Compiler {
         m->jnt_bodyid[j] = body;
         m->jnt_qposadr[j] = m->nq;
         m->jnt_dofadr[j] = m->nv;
-        int nq = type == ILQG_JNT_FREE ? 7 : 1, nd = type == ILQG_JNT_FREE ? 6 : 1;
+        int nq = type == ILQG_JNT_FREE ? 7 : (type == ILQG_JNT_BALL ? 4 : 1), nd = type == ILQG_JNT_FREE ? 6 : (type == ILQG_JNT_BALL ? 3 : 1);
         if (m->nq + nq > ILQG_MAXQ || m->nv + nd > ILQG_MAXV) return cx.fail("too many dofs");
         double t[5];
         V3 pos = {0, 0, 0}, axis = {0, 0, 1};
@@ -336,6 +337,7 @@ struct Compiler {
         m->jnt_range[j][0] = rg[0] * ang; m->jnt_range[j][1] = rg[1] * ang;
         m->jnt_limited[j] = truthy(attr(e, D, "limited"), false) ? 1 : 0;
         if (type == ILQG_JNT_FREE) m->jnt_limited[j] = 0;
+        if (type == ILQG_JNT_BALL && m->jnt_limited[j]) return cx.fail("limited ball joints are not supported");
         m->jnt_stiffness[j] = nums(attr(e, D, "stiffness"), t, 1) ? t[0] : 0.0;
         m->jnt_margin[j] = nums(attr(e, D, "margin"), t, 1) ? t[0] : 0.0;
         double sr[2] = {0.02, 1};
@@ -354,6 +356,10 @@ struct Compiler {
             double q0[7] = {b.gpos.x, b.gpos.y, b.gpos.z, b.gquat.w, b.gquat.x, b.gquat.y, b.gquat.z};
             for (int i = 0; i < 7; i++) m->qpos0[m->nq + i] = m->qpos_spring[m->nq + i] = q0[i];
             arm = 0; damp = 0;  // freejoint carries no defaults
+        } else if (type == ILQG_JNT_BALL) {   // the joint's own rotation: identity at qpos0
+            if (m->jnt_stiffness[j] != 0) return cx.fail("springs on ball joints are not supported");
+            const double q0[4] = {1, 0, 0, 0};
+            for (int i = 0; i < 4; i++) m->qpos0[m->nq + i] = m->qpos_spring[m->nq + i] = q0[i];
         } else {
             m->qpos0[m->nq] = ref;
             m->qpos_spring[m->nq] = sref;
@@ -403,6 +409,8 @@ struct Compiler {
         }
         m->body_jntnum[b] = m->njnt - m->body_jntadr[b];
         m->body_dofnum[b] = m->nv - m->body_dofadr[b];
+        for (int j = m->body_jntadr[b]; j < m->njnt; j++)   // (its motion axes are the body's own: MuJoCo takes them from the body frame)
+            if (m->jnt_type[j] == ILQG_JNT_BALL && m->body_jntnum[b] != 1) return cx.fail("a ball joint must be the only joint of its body");
         for (auto& k : e->kids)
             if (k->name == "geom") { if (!addGeom(k.get(), b)) return false; }
         if (e->child("inertial")) return cx.fail("<inertial> not supported (inertiafromgeom only)");
@@ -502,6 +510,11 @@ struct Compiler {
                     int k = d - m->jnt_dofadr[j];
                     if (k < 3) { double e[3] = {0, 0, 0}; e[k] = 1; jp = {e[0], e[1], e[2]}; }
                     else { V3 ax = {Rj.m[0][k - 3], Rj.m[1][k - 3], Rj.m[2][k - 3]}; jr = ax; jp = cross(ax, p - bt[db].gpos); }
+                } else if (m->jnt_type[j] == ILQG_JNT_BALL) {   // the body's k-th axis about the joint anchor
+                    int k = d - m->jnt_dofadr[j];
+                    V3 ax = {Rj.m[0][k], Rj.m[1][k], Rj.m[2][k]};
+                    V3 anchor = bt[db].gpos + mulv(Rj, {m->jnt_pos[j][0], m->jnt_pos[j][1], m->jnt_pos[j][2]});
+                    jr = ax; jp = cross(ax, p - anchor);
                 } else {
                     V3 ax = mulv(Rj, {m->jnt_axis[j][0], m->jnt_axis[j][1], m->jnt_axis[j][2]});
                     V3 anchor = bt[db].gpos + mulv(Rj, {m->jnt_pos[j][0], m->jnt_pos[j][1], m->jnt_pos[j][2]});
@@ -555,6 +568,9 @@ struct Compiler {
                 double t = (Minv[a * nv + a] + Minv[(a + 1) * nv + a + 1] + Minv[(a + 2) * nv + a + 2]) / 3;
                 double r = (Minv[(a + 3) * nv + a + 3] + Minv[(a + 4) * nv + a + 4] + Minv[(a + 5) * nv + a + 5]) / 3;
                 for (int k = 0; k < 3; k++) { m->dof_invweight0[a + k] = t; m->dof_invweight0[a + 3 + k] = r; }
+            } else if (m->jnt_type[j] == ILQG_JNT_BALL) {   // one value for the joint's three dofs, as MuJoCo averages them
+                double r = (Minv[a * nv + a] + Minv[(a + 1) * nv + a + 1] + Minv[(a + 2) * nv + a + 2]) / 3;
+                for (int k = 0; k < 3; k++) m->dof_invweight0[a + k] = r;
             } else
                 m->dof_invweight0[a] = Minv[a * nv + a];
         }
@@ -667,6 +683,7 @@ struct Compiler {
                 if (!jn || !jntByName.count(*jn)) return cx.fail("motor without a known joint");
                 int j = jntByName[*jn];
                 if (m->jnt_type[j] == ILQG_JNT_FREE) return cx.fail("motor on a free joint");
+                if (m->jnt_type[j] == ILQG_JNT_BALL) return cx.fail("motor on a ball joint is not supported");
                 m->act_dofid[u] = m->jnt_dofadr[j];
                 double t[6];
                 m->act_gear[u] = nums(attr(k.get(), cx.defMotor, "gear"), t, 6) ? t[0] : 1.0;
@@ -743,12 +760,13 @@ extern "C" int ilqg_model_validate(const ilqg_model* m, char* err, int errlen) {
     int nq = 0, nv = 0;
     for (int j = 0; j < m->njnt; j++) {
         const int ty = m->jnt_type[j], b = m->jnt_bodyid[j];
-        if (ty == ILQG_JNT_BALL) return bad(ILQG_ERR_UNSUPPORTED, "ball joint (not implemented by the kernels)", j);
-        if (ty != ILQG_JNT_FREE && ty != ILQG_JNT_SLIDE && ty != ILQG_JNT_HINGE) return bad(ILQG_ERR_MODEL, "joint type", j);
+        if (ty != ILQG_JNT_FREE && ty != ILQG_JNT_BALL && ty != ILQG_JNT_SLIDE && ty != ILQG_JNT_HINGE) return bad(ILQG_ERR_MODEL, "joint type", j);
+        if (ty == ILQG_JNT_BALL && (m->jnt_limited[j] || m->jnt_stiffness[j] != 0 || m->body_jntnum[b] != 1))
+            return bad(ILQG_ERR_UNSUPPORTED, "ball joint with a limit, a spring or sibling joints on its body", j);
         if (b < 1 || b >= m->nbody) return bad(ILQG_ERR_MODEL, "jnt_bodyid", j);
         if (m->jnt_qposadr[j] != nq || m->jnt_dofadr[j] != nv) return bad(ILQG_ERR_MODEL, "jnt_qposadr / jnt_dofadr not cumulative", j);
-        nq += ty == ILQG_JNT_FREE ? 7 : 1;
-        nv += ty == ILQG_JNT_FREE ? 6 : 1;
+        nq += ty == ILQG_JNT_FREE ? 7 : (ty == ILQG_JNT_BALL ? 4 : 1);
+        nv += ty == ILQG_JNT_FREE ? 6 : (ty == ILQG_JNT_BALL ? 3 : 1);
     }
     if (nq != m->nq || nv != m->nv) return bad(ILQG_ERR_MODEL, "nq / nv do not match the joints", 0);
     if (m->body_parentid[0] != 0) return bad(ILQG_ERR_MODEL, "body 0 must be the world", 0);

@@ -72,7 +72,9 @@ void mjo_integrate_pos(const ilqg_model* m, double* qpos, const double* qvel, do
         if (m->jnt_type[j] == ILQG_JNT_FREE) {
             for (int k = 0; k < 3; k++) qpos[qa + k] += dt * qvel[da + k];
             mjo_quat_integrate(qpos + qa + 3, qvel + da + 3, dt);
-        } else
+        } else if (m->jnt_type[j] == ILQG_JNT_BALL)
+            mjo_quat_integrate(qpos + qa, qvel + da, dt);
+        else
             qpos[qa] += dt * qvel[da];
     }
 }
@@ -125,8 +127,10 @@ void mjo_copy_state(const ilqg_model* m, mjo_data* dst, const mjo_data* src) {
 /* ------------------------------------------------------------------ position stage */
 static void kinematics(const ilqg_model* m, mjo_data* d) {
     /* mj_kinematics: normalise quaternions in qpos, then walk the tree */
-    for (int j = 0; j < m->njnt; j++)
+    for (int j = 0; j < m->njnt; j++) {
         if (m->jnt_type[j] == ILQG_JNT_FREE) quat_normalize(d->qpos + m->jnt_qposadr[j] + 3);
+        if (m->jnt_type[j] == ILQG_JNT_BALL) quat_normalize(d->qpos + m->jnt_qposadr[j]);
+    }
     d->xpos[0][0] = d->xpos[0][1] = d->xpos[0][2] = 0;
     d->xquat[0][0] = 1; d->xquat[0][1] = d->xquat[0][2] = d->xquat[0][3] = 0;
     quat2mat(d->xmat[0], d->xquat[0]);
@@ -151,6 +155,15 @@ static void kinematics(const ilqg_model* m, mjo_data* d) {
             mat_vec(t, mat, m->jnt_pos[j]);
             for (int k = 0; k < 3; k++) d->xanchor[j][k] = xpos[k] + t[k];
             mat_vec(d->xaxis[j], mat, m->jnt_axis[j]);
+            if (m->jnt_type[j] == ILQG_JNT_BALL) { /* rotate about the anchor by the joint's quaternion (mj_kinematics, mjJNT_BALL) */
+                double nq[4];
+                quat_mul(nq, xquat, d->qpos + qa);
+                memcpy(xquat, nq, sizeof nq);
+                quat2mat(mat, xquat);
+                mat_vec(t, mat, m->jnt_pos[j]);
+                for (int k = 0; k < 3; k++) xpos[k] = d->xanchor[j][k] - t[k];
+                continue;
+            }
             double q = d->qpos[qa] - m->qpos0[qa];
             if (m->jnt_type[j] == ILQG_JNT_SLIDE) {
                 for (int k = 0; k < 3; k++) xpos[k] += d->xaxis[j][k] * q;
@@ -241,6 +254,13 @@ static void com_pos(const ilqg_model* m, mjo_data* d) {
                 double ax[3] = {d->xmat[b][i], d->xmat[b][3 + i], d->xmat[b][6 + i]};
                 for (int k = 0; k < 3; k++) d->cdof[da + 3 + i][k] = ax[k];
                 v3_cross(d->cdof[da + 3 + i] + 3, ax, off);
+            }
+            FL(d, 27);
+        } else if (m->jnt_type[j] == ILQG_JNT_BALL) { /* the body's three axes about the anchor (mj_comPos, mjJNT_BALL) */
+            for (int i = 0; i < 3; i++) {
+                double ax[3] = {d->xmat[b][i], d->xmat[b][3 + i], d->xmat[b][6 + i]};
+                for (int k = 0; k < 3; k++) d->cdof[da + i][k] = ax[k];
+                v3_cross(d->cdof[da + i] + 3, ax, off);
             }
             FL(d, 27);
         } else if (m->jnt_type[j] == ILQG_JNT_SLIDE) {
@@ -523,7 +543,7 @@ static void make_constraint(const ilqg_model* m, mjo_data* d) {
     d->nefc = 0;
     /* joint limits (mj_instantiateLimit): slide and hinge */
     for (int j = 0; j < m->njnt; j++) {
-        if (!m->jnt_limited[j] || m->jnt_type[j] == ILQG_JNT_FREE) continue;
+        if (!m->jnt_limited[j] || m->jnt_type[j] == ILQG_JNT_FREE || m->jnt_type[j] == ILQG_JNT_BALL) continue;
         double value = d->qpos[m->jnt_qposadr[j]];
         for (int side = -1; side <= 1; side += 2) {
             double dist = side * (m->jnt_range[j][(side + 1) / 2] - value);
@@ -622,6 +642,11 @@ static void com_vel(const ilqg_model* m, mjo_data* d) {
                 for (int i = 3; i < 6; i++)
                     for (int k = 0; k < 6; k++) cvel[k] += d->cdof[da + i][k] * d->qvel[da + i];
                 FL(d, 72 + 3 * 36);
+            } else if (m->jnt_type[j] == ILQG_JNT_BALL) { /* all three axes turn with the velocity before the joint (mj_comVel) */
+                for (int i = 0; i < 3; i++) cross_motion(d->cdof_dot[da + i], cvel, d->cdof[da + i]);
+                for (int i = 0; i < 3; i++)
+                    for (int k = 0; k < 6; k++) cvel[k] += d->cdof[da + i][k] * d->qvel[da + i];
+                FL(d, 36 + 3 * 36);
             } else {
                 cross_motion(d->cdof_dot[da], cvel, d->cdof[da]);
                 for (int k = 0; k < 6; k++) cvel[k] += d->cdof[da][k] * d->qvel[da];
@@ -635,7 +660,7 @@ static void com_vel(const ilqg_model* m, mjo_data* d) {
 static void passive(const ilqg_model* m, mjo_data* d) {
     for (int i = 0; i < m->nv; i++) d->qfrc_passive[i] = -m->dof_damping[i] * d->qvel[i];
     for (int j = 0; j < m->njnt; j++) {
-        if (m->jnt_type[j] == ILQG_JNT_FREE || m->jnt_stiffness[j] == 0) continue;
+        if (m->jnt_type[j] == ILQG_JNT_FREE || m->jnt_type[j] == ILQG_JNT_BALL || m->jnt_stiffness[j] == 0) continue;
         int qa = m->jnt_qposadr[j];
         d->qfrc_passive[m->jnt_dofadr[j]] -= m->jnt_stiffness[j] * (d->qpos[qa] - m->qpos_spring[qa]);
     }

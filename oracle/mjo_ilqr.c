@@ -50,9 +50,10 @@ void mjo_state_diff(const ilqg_model* m, const double* qa, const double* va, con
     int nv = m->nv;
     for (int j = 0; j < m->njnt; j++) {
         int qadr = m->jnt_qposadr[j], dadr = m->jnt_dofadr[j];
-        if (m->jnt_type[j] == ILQG_JNT_FREE) {
-            for (int k = 0; k < 3; k++) out[dadr + k] = qa[qadr + k] - qb[qadr + k];
-            const double *a = qa + qadr + 3, *b = qb + qadr + 3;
+        if (m->jnt_type[j] == ILQG_JNT_FREE || m->jnt_type[j] == ILQG_JNT_BALL) {
+            const int fr = m->jnt_type[j] == ILQG_JNT_FREE ? 3 : 0;   /* a free joint carries a position in front of its quaternion */
+            for (int k = 0; k < fr; k++) out[dadr + k] = qa[qadr + k] - qb[qadr + k];
+            const double *a = qa + qadr + fr, *b = qb + qadr + fr;
             double na = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2] + a[3] * a[3]), nb = sqrt(b[0] * b[0] + b[1] * b[1] + b[2] * b[2] + b[3] * b[3]);
             double A[4] = {a[0] / na, a[1] / na, a[2] / na, a[3] / na}, B[4] = {b[0] / nb, -b[1] / nb, -b[2] / nb, -b[3] / nb}; /* conj(q_b) */
             double d[4] = {B[0] * A[0] - B[1] * A[1] - B[2] * A[2] - B[3] * A[3], B[0] * A[1] + B[1] * A[0] + B[2] * A[3] - B[3] * A[2],
@@ -61,7 +62,7 @@ void mjo_state_diff(const ilqg_model* m, const double* qa, const double* va, con
             double ang = 2 * atan2(sn, d[0]);
             if (ang > 3.14159265358979323846) ang -= 2 * 3.14159265358979323846;
             double sc = sn < 1e-15 ? 0.0 : ang / sn;
-            for (int k = 0; k < 3; k++) out[dadr + 3 + k] = d[1 + k] * sc;
+            for (int k = 0; k < 3; k++) out[dadr + fr + k] = d[1 + k] * sc;
         } else
             out[dadr] = qa[qadr] - qb[qadr];
     }

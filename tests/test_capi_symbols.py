@@ -65,7 +65,7 @@ def test_model_tables_are_validated(pkg, tmp_path):
         assert L.ilqg_model_validate(pkg.Model.named(name).ptr, err, 256) == pkg.OK, err.value
     # out-of-range indices and counts
     for field, idx, val, code in (("body_parentid", 2, 9, pkg.ERR_MODEL), ("dof_parentid", 1, 5, pkg.ERR_MODEL), ("pair_geom2", 0, 23, pkg.ERR_MODEL),
-                                  ("act_dofid", 0, 31, pkg.ERR_MODEL), ("jnt_type", 3, 1, pkg.ERR_UNSUPPORTED),   # a ball joint: declared, not implemented
+                                  ("act_dofid", 0, 31, pkg.ERR_MODEL), ("jnt_type", 3, 1, pkg.ERR_UNSUPPORTED),   # a LIMITED ball joint (and the dof counts no longer add up)
                                   ("geom_type", 1, 5, pkg.ERR_UNSUPPORTED), ("npair", 0, 4000, pkg.ERR_MODEL)):
         bad = pkg.Model.named("hopper").copy()
         bad.field(field)[idx] = val

@@ -124,3 +124,37 @@ def test_humanoid_host_pipeline_chunks_do_not_share_scratch(pkg, oracle, omodels
         h.fd_batch_dev(dq, dv, du, dw, d_dev, cost=cost)
         assert np.array_equal(d_host, d_dev.cpu().numpy())
     h.close()
+
+
+def test_ball_joint_model_on_the_generic_engine(pkg, oracle, tmp_path):
+    """A tree with a ball joint (/root/reference/src/mjderivative.cpp:152-156 perturbs such joints in the tangent space; none of
+    the reference's three models has one) runs on the warp-cooperative engine: forward, step and FD against the oracle, in flight
+    and with the hand on the floor."""
+    from test_oracle_contact_anchors import ball_model, ball_states
+    pm, path = ball_model(pkg, tmp_path)
+    om = oracle.Model(path)
+    h = pkg.Handle(pm, 0)
+    assert h.engine == "generic-warp-per-rollout"
+    n = 24
+    q, v, u, w = ball_states(n, 11)
+    q[n // 2:, :4] = [0.9239, 0, 0.3827, 0]           # pitched down by 45 degrees: the forearm and hand reach the floor
+    q[n // 2:, :4] += np.random.default_rng(2).normal(0, 0.05, (n - n // 2, 4))
+    q[:, :4] /= np.linalg.norm(q[:, :4], axis=1, keepdims=True)
+    q, v, w, _ = oracle.step_batch(om, q, v, u, w, 40)
+    info = [oracle.dump(om, q[k], v[k], u[k], w[k])["ncon"] for k in range(n)]
+    assert max(info) >= 1 and min(info) == 0          # both regimes are in the sample
+    a_ref, _ = oracle.forward_batch(om, q, v, u, w)
+    a_gpu, _ = h.forward_batch_host(q, v, u, w)
+    assert np.allclose(a_gpu, a_ref, rtol=1e-7, atol=1e-7)
+    q1, v1, _, _ = oracle.step_batch(om, q, v, u, w, 10)
+    q2, v2, _, _ = h.step_batch_host(q, v, u, w, nsteps=10)
+    assert np.allclose(q2, q1, rtol=1e-8, atol=1e-8) and np.allclose(v2, v1, rtol=1e-6, atol=1e-6)
+    assert np.allclose(np.linalg.norm(q2[:, :4], axis=1), 1.0, atol=1e-12)
+    cost = pkg.make_cost(q2=[0, 1, 1, 0, 0.5], v2=[0.1] * 4, u2=[0.3])
+    d_ref, qa_ref, _ = oracle.fd_batch(om, q, v, u, w, cost)
+    d_gpu, qa_gpu, status = h.fd_batch_host(q, v, u, w, cost)
+    assert status.sum() == 0
+    assert np.allclose(qa_gpu, qa_ref, rtol=1e-8, atol=1e-8)
+    assert_deriv_close(d_gpu, d_ref, pm.nv, pm.nu, tol=1e-6)
+    assert np.abs(d_ref[:, :3 * 4]).max() > 1e-2      # the ball joint's tangent columns carry real derivatives
+    h.close()

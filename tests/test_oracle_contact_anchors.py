@@ -134,6 +134,13 @@ def aba_qacc_smooth(pm, q, qd, ctrl):
                 continue
             R = q2m(quat)
             anchor, axis = pos + R @ jpos[j], R @ jaxis[j]
+            if ty == 1:   # ball: the joint's own quaternion, about the anchor; axes = the rotated body axes (turning together)
+                quat = qmul(quat, q[qa:qa + 4] / np.linalg.norm(q[qa:qa + 4]))
+                R = q2m(quat)
+                pos = anchor - R @ jpos[j]
+                ballcols[b] |= {len(cols) + 1, len(cols) + 2}
+                cols += [np.concatenate([R[:, k], np.cross(anchor, R[:, k])]) for k in range(3)]
+                continue
             ang = q[qa] - qpos0[qa]
             if ty == 2:   # slide
                 pos = pos + ang * axis
@@ -156,7 +163,7 @@ def aba_qacc_smooth(pm, q, qd, ctrl):
     jstiff, qspring, dof_jnt = F("jnt_stiffness"), tab(pm, "qpos_spring"), tab(pm, "dof_jntid")
     for i in range(nv):
         j = dof_jnt[i]
-        if ints["jnt_type"][j] != 0 and jstiff[j] != 0:
+        if ints["jnt_type"][j] not in (0, 1) and jstiff[j] != 0:
             tau[i] -= jstiff[j] * (q[jnt_qposadr[j]] - qspring[jnt_qposadr[j]])
     gear, rng, lim, adof = F("act_gear"), F("act_ctrlrange", (-1, 2)), F("act_ctrllimited"), F("act_dofid")
     for a in range(nu):
@@ -237,3 +244,93 @@ def test_qacc_smooth_matches_articulated_body_algorithm(pkg, oracle, omodels, na
         ref = oracle.dump(om, q[k], v[k], u[k])["qacc_smooth"]
         got = aba_qacc_smooth(pm, q[k], v[k], u[k])
         assert np.allclose(got, ref, rtol=1e-8, atol=1e-8 * max(1.0, np.abs(ref).max())), (k, np.abs(got - ref).max())
+
+
+BALL_XML = """
+<mujoco model="ball_arm">
+  <compiler angle="radian"/>
+  <option timestep="0.002" integrator="Euler" gravity="0 0 -9.81"/>
+  <default><geom density="1000" condim="3" friction="0.8" margin="0.001" solref="0.02 1" solimp="0.9 0.9 0.01"/></default>
+  <worldbody>
+    <geom name="floor" type="plane" pos="0 0 0" size="5 5 0.1"/>
+    <body name="upper" pos="0 0 0.6">
+      <joint name="shoulder" type="ball" pos="0 0 0" damping="0.2" armature="0.01"/>
+      <geom name="upper_geom" type="capsule" fromto="0 0 0 0.25 0.05 -0.1" size="0.04"/>
+      <body name="lower" pos="0.25 0.05 -0.1">
+        <joint name="elbow" type="hinge" pos="0 0 0" axis="0 1 0" damping="0.1" armature="0.01" limited="true" range="-2 2"/>
+        <geom name="lower_geom" type="capsule" fromto="0 0 0 0.2 0 -0.25" size="0.03"/>
+        <geom name="hand" type="sphere" pos="0.2 0 -0.25" size="0.05"/>
+      </body>
+    </body>
+  </worldbody>
+  <actuator><motor joint="elbow" gear="5" ctrllimited="true" ctrlrange="-1 1"/></actuator>
+</mujoco>
+"""
+
+
+def ball_model(pkg, tmp_path):
+    import ctypes as C
+    L = pkg.lib()
+    buf = np.zeros(L.ilqg_model_sizeof(), np.uint8)
+    err = C.create_string_buffer(512)
+    rc = L.ilqg_compile_mjcf_string(BALL_XML.encode(), buf.ctypes.data_as(C.c_void_p), err, 512)
+    assert rc == 0, err.value
+    pm = pkg.Model(buf)
+    pm.validate()
+    path = str(tmp_path / "ball_arm.ilqgm")
+    pm.buf.tofile(path)
+    return pm, path
+
+
+def ball_states(n, seed):
+    rng = np.random.default_rng(seed)
+    q = np.zeros((n, 5)); q[:, :4] = rng.normal(0, 1, (n, 4)); q[:, :4] /= np.linalg.norm(q[:, :4], axis=1, keepdims=True)
+    q[:, 4] = rng.uniform(-1.5, 1.5, n)
+    return q, rng.normal(0, 1.0, (n, 4)), rng.uniform(-1, 1, (n, 1)), np.zeros((n, 4))
+
+
+def test_ball_joint_model_compiles_and_oracle_is_anchored(pkg, oracle, tmp_path):
+    """Ball joints (the reference's FD perturbs them in the tangent space, /root/reference/src/mjderivative.cpp:152-156; none of its
+    three models has one): the MJCF subset compiles them (nq 4, nv 3), and the oracle's treatment is anchored by the articulated-body
+    algorithm and by energy conservation."""
+    pm, path = ball_model(pkg, tmp_path)
+    assert (pm.nq, pm.nv, pm.nu, pm.njnt) == (5, 4, 1, 2) and list(pm.field("jnt_type")[:2]) == [1, 3]
+    assert np.allclose(pm.field("qpos0")[:5], [1, 0, 0, 0, 0])
+    iw = pm.field("dof_invweight0")[:4]
+    assert iw[0] == iw[1] == iw[2] > 0                       # one value for the joint's three dofs
+    om = oracle.Model(path)
+    q, v, u, w = ball_states(8, 3)
+    q[:, :4] *= 1.7                                           # un-normalised quaternions in qpos are normalised by the kinematics
+    for k in range(8):
+        ref = oracle.dump(om, q[k], v[k], u[k])["qacc_smooth"]
+        got = aba_qacc_smooth(pm, q[k], v[k], u[k])
+        assert np.allclose(got, ref, rtol=1e-9, atol=1e-9 * max(1.0, np.abs(ref).max())), (k, np.abs(got - ref).max())
+    # energy: no damping, no limits, no contacts, RK4.  MuJoCo's RK4 updates a quaternion with ONE exponential of the combined
+    # angular velocity (SURVEY A.2, "RK4 step"), which is second-order in h for rotations: the drift must be small and must fall
+    # by ~4x when h is halved (a wrong Coriolis term or motion-axis derivative would not converge at all).
+    import ctypes as C
+    drift = []
+    for dt, steps in ((5e-4, 600), (2.5e-4, 1200)):
+        cm = pm.copy()
+        cm.field("dof_damping")[:] = 0; cm.field("jnt_limited")[:] = 0; cm.field("npair")[0] = 0; cm.field("integrator")[0] = 1; cm.field("timestep")[0] = dt
+        p2 = str(tmp_path / "ball_free.ilqgm"); cm.buf.tofile(p2)
+        om2 = oracle.Model(p2)
+
+        def energy(qq, vv):
+            e = C.c_double()
+            oracle.lib().mjo_debug_mass_bias(om2.ptr, oracle._p(np.ascontiguousarray(qq)), oracle._p(np.ascontiguousarray(vv)), None, None, C.byref(e))
+            return e.value
+        q, v, u, w = ball_states(4, 5)
+        u[:] = 0
+        v *= 0.4
+        e0 = np.array([energy(q[i], v[i]) for i in range(4)])
+        q1, v1, _, _ = oracle.step_batch(om2, q, v, u, w, steps)
+        e1 = np.array([energy(q1[i], v1[i]) for i in range(4)])
+        assert np.abs(q1 - q).max() > 0.1
+        assert np.allclose(np.linalg.norm(q1[:, :4], axis=1), 1.0, atol=1e-12)
+        drift.append(np.abs(e1 - e0))
+    assert (drift[0] < 1e-5).all() and (drift[1] < 0.3 * drift[0] + 1e-12).all(), drift
+    # rejected: what the kernels do not implement
+    bad = BALL_XML.replace('type="ball" pos="0 0 0"', 'type="ball" pos="0 0 0" limited="true" range="0 1"')
+    buf = np.zeros(pkg.lib().ilqg_model_sizeof(), np.uint8); err = C.create_string_buffer(512)
+    assert pkg.lib().ilqg_compile_mjcf_string(bad.encode(), buf.ctypes.data_as(C.c_void_p), err, 512) == pkg.ERR_MODEL and b"ball" in err.value

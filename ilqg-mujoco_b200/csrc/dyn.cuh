@@ -432,6 +432,44 @@ struct PosStage {
     double dspr[T::NV];  // q - qpos_spring of sprung dofs
 };
 
+// ---- flat (de)serialisation of the statically sparse types: only the components that exist are stored
+template <bool LOAD> DEV void xfer(double*& p, double& x) { if constexpr (LOAD) x = *p; else *p = x; p++; }
+template <bool LOAD> DEV void xfer(double*&, Z0&) {}
+template <bool LOAD> DEV void xfer(double*& p, V3& a) { xfer<LOAD>(p, a.x); xfer<LOAD>(p, a.y); xfer<LOAD>(p, a.z); }
+template <bool LOAD, class X, class Y, class W> DEV void xfer(double*& p, V3T<X, Y, W>& a) { xfer<LOAD>(p, a.x); xfer<LOAD>(p, a.y); xfer<LOAD>(p, a.z); }
+template <bool LOAD> DEV void xfer(double*& p, S6& a) { xfer<LOAD>(p, a.w); xfer<LOAD>(p, a.v); }
+template <bool LOAD, class W, class V> DEV void xfer(double*& p, S6T<W, V>& a) { xfer<LOAD>(p, a.w); xfer<LOAD>(p, a.v); }
+template <bool LOAD> DEV void xfer(double*& p, Inert& a) {
+    xfer<LOAD>(p, a.xx); xfer<LOAD>(p, a.yy); xfer<LOAD>(p, a.zz); xfer<LOAD>(p, a.xy); xfer<LOAD>(p, a.xz); xfer<LOAD>(p, a.yz); xfer<LOAD>(p, a.h); xfer<LOAD>(p, a.m);
+}
+template <bool LOAD, class XX, class YY, class ZZ, class XY, class XZ, class YZ, class H> DEV void xfer(double*& p, InertT<XX, YY, ZZ, XY, XZ, YZ, H>& a) {
+    xfer<LOAD>(p, a.xx); xfer<LOAD>(p, a.yy); xfer<LOAD>(p, a.zz); xfer<LOAD>(p, a.xy); xfer<LOAD>(p, a.xz); xfer<LOAD>(p, a.yz); xfer<LOAD>(p, a.h); xfer<LOAD>(p, a.m);
+}
+// The position stage's products of one rollout — what mj_forwardSkip(mjSTAGE_POS) keeps (/root/reference/src/mjderivative.cpp:124):
+// motion axes, spatial inertias, spring offsets, M and its factor, the constraint rows (J, D, damping B, k-term) — to or from
+// a flat record: [nefc | PosStage | M | L | rows].  POS_RECORD_DOUBLES bounds it.
+template <class T>
+__host__ __device__ constexpr int pos_record_doubles() { return 2 + 6 * T::NV + 10 * T::NBODY + T::NV + T::NV * (T::NV + 1) + nz(T::MAXEFC) * (T::NV + 3); }
+template <bool LOAD, class T, class W>
+DEV void xfer_pos_stage(double* rec, PosStage<T>& ps, W& w) {
+    double* p = rec;
+    double ne = (double)w.nefc;
+    xfer<LOAD>(p, ne);
+    if constexpr (LOAD) w.nefc = (int)ne;
+    p++;   // (keeps what follows 16-byte aligned)
+    sfor<0, T::NV>([&](auto ii) { xfer<LOAD>(p, ps.cdof[IDX(ii)]); });
+    sfor<1, T::NBODY>([&](auto bb) { xfer<LOAD>(p, ps.cin[IDX(bb)]); });
+    sfor<0, T::NV>([&](auto ii) { xfer<LOAD>(p, ps.dspr[IDX(ii)]); });
+    sfor<0, T::NV*(T::NV + 1) / 2>([&](auto tt) { xfer<LOAD>(p, w.M[IDX(tt)]); });
+    sfor<0, T::NV*(T::NV + 1) / 2>([&](auto tt) { xfer<LOAD>(p, w.L[IDX(tt)]); });
+    for (int r = 0; r < w.nefc; r++) {
+        sfor<0, T::NV>([&](auto ii) { xfer<LOAD>(p, w.rows.J(r, IDX(ii))); });
+        xfer<LOAD>(p, w.rows.D(r));
+        xfer<LOAD>(p, w.rows.rB(r));
+        xfer<LOAD>(p, w.rows.rkt(r));
+    }
+}
+
 // packed Cholesky A = L L^T with reciprocal diagonal
 template <int N>
 DEV void chol_packed(const double* A, double* L) {

@@ -60,6 +60,8 @@ struct FdBins {
     int* cnt;            // [FD_NBUCKET] knots per bucket (zeroed before the centre kernel)
     unsigned int* key;   // [nknots] bucket << 24 | rank inside the bucket
     int* perm;           // [nknots] slot -> knot
+    double* pos;         // [nknots][pos_record_doubles<T>()] the centre's position-stage products (xfer_pos_stage): with them the
+                         // qvel / ctrl column kernel does not run a position stage of its own (mjSTAGE_POS skip across kernels), or NULL
     double* fac;         // [nknots][NT + 1] the centre solution's Newton factor and (as bits) its active set: the qvel / ctrl columns
                          // of the knot share M, J and D with the centre, so their Newton systems with that active set are this matrix
 };
@@ -68,7 +70,7 @@ struct FdBins {
 DEV int fd_cta_rows(const FdBins& bins, int k0) { return FD_NBUCKET - 1 - (int)(bins.key[bins.perm[k0]] >> 24); }
 
 // (register caps for 12 / 16 resident warps per SM were measured on this kernel after the planar algebra: +16 % time both)
-template <class T>
+template <class T, bool EXPORT = false>
 __global__ void __launch_bounds__(128) fd_center_kernel(const __grid_constant__ DevModel<T> m, int nknots, const double* __restrict__ qpos,
                                                         const double* __restrict__ qvel, const double* __restrict__ ctrl,
                                                         const double* __restrict__ warmstart, int niter, int nwarmup,
@@ -85,7 +87,14 @@ __global__ void __launch_bounds__(128) fd_center_kernel(const __grid_constant__ 
     sfor<0, T::NV>([&](auto ii) { warm[IDX(ii)] = warmstart ? warmstart[(size_t)kk * T::NV + IDX(ii)] : 0.0; });
     Work<T> w;
     const long long t0 = clock64();
-    build_problem<T>(m, q, v, u, w);
+    if constexpr (EXPORT) {   // stage by stage, and the position stage's products go to the knot's record for the qvel / ctrl columns
+        PosStage<T> ps;
+        build_pos<T, false, false>(m, q, ps, w);
+        build_vel<T, false, false>(m, ps, v, w);
+        finish_smooth<T>(m, u, w);
+        xfer_pos_stage<false, T>(bins.pos + (size_t)kk * pos_record_doubles<T>(), ps, w);
+    } else
+        build_problem<T>(m, q, v, u, w);
     const long long t1 = clock64();
     int it_first = 0, it_all = 0;
     // The reference repeats the centre solve nwarmup times to polish the warm start (mjderivative.cpp:67-68).  A solve that left
@@ -472,6 +481,8 @@ __global__ void __launch_bounds__(THREADS, MINB) fd_velctrl_kernel(const __grid_
         if (it == 0 || is_vel) build_vel<T, false>(m, ps, vp, w);   // ctrl columns keep the centre's velocity stage (mjSTAGE_VEL skip)
         finish_smooth<T>(m, up, w);
         solve<T>(m, w, warm, qacc, niter, 0.0);
+        // (measured and rejected, round 2: reusing the centre's Newton factor here — FdBins::fac, as fd_velctrl_shared_kernel does —
+        //  0.538 -> 0.552 ms, and the second inlined copy of the solver alone costs 0.465 -> 0.538 ms: instruction footprint)
         if (!(it & 1)) {
             sfor<0, NV>([&](auto jj) { qplus[IDX(jj)] = qacc[IDX(jj)]; });
         } else {
@@ -586,6 +597,64 @@ __global__ void __launch_bounds__(THREADS, 1) fd_velctrl_shared_kernel(const __g
         }
     }
     if (valid && !finite && status) atomicExch(&status[kk], ILQG_ERR_NONFINITE);
+}
+
+// The same columns WITHOUT a position stage of their own: the centre kernel has already run it on this qpos (the reference's
+// mjSTAGE_POS skip, mjderivative.cpp:124, carried across kernels) and left its products in the knot's record (FdBins::pos).
+// Per knot that is 13 position stages instead of 16, and the kernel loses the stage whose register pressure sets its occupancy.
+template <class T, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) fd_velctrl_loaded_kernel(const __grid_constant__ DevModel<T> m, int nknots, const double* __restrict__ qpos,
+                                                                     const double* __restrict__ qvel, const double* __restrict__ ctrl,
+                                                                     const double* __restrict__ qacc_center, const ilqg_cost* __restrict__ cost,
+                                                                     double eps, int niter, const FdDst dst, int* __restrict__ status,
+                                                                     const FdBins bins) {
+    using S = FdSplit<T, THREADS>;
+    constexpr int NV = T::NV, NU = T::NU, NQ = T::NQ, GK = S::GK;
+    const int kl = threadIdx.x / GK, g = threadIdx.x - kl * GK;
+    const int slot = blockIdx.x * S::KPC_VU + kl;
+    if (kl >= S::KPC_VU || slot >= nknots) return;   // no barriers in this kernel
+    const int kk = bins.perm ? bins.perm[slot] : slot;
+    double q[NQ], v[NV], u[nz(NU)], center[NV];
+    load_knot<T>(kk, qpos, qvel, ctrl, q, v, u);
+    sfor<0, NV>([&](auto ii) { center[IDX(ii)] = qacc_center[(size_t)kk * NV + IDX(ii)]; });
+    double c0 = 0;
+    if (cost) c0 = cost_eval<T>(*cost, q, v, u);
+    PosStage<T> ps;
+    Work<T> w;
+    w.nefc = 0;
+    xfer_pos_stage<true, T>(bins.pos + (size_t)kk * pos_record_doubles<T>(), ps, w);
+    const double inv2eps = 1.0 / (2 * eps);
+    const size_t base = (size_t)kk * S::ND;
+    double qplus[NV], dcost = 0;
+    bool finite = true;
+#pragma unroll 1
+    for (int it = 0; it < 2 * (S::CU + S::CV); it++) {
+        const int c = it >> 1;
+        const bool is_vel = c >= S::CU;                       // uniform over the grid
+        const int col = (is_vel ? c - S::CU : c) * GK + g;    // column within its kind
+        const double se = (it & 1) ? -eps : eps;
+        double vp[NV], up[nz(NU)], warm[NV], qacc[NV];
+        sfor<0, NV>([&](auto ii) { vp[IDX(ii)] = v[IDX(ii)] + ((is_vel && col == IDX(ii)) ? se : 0.0); warm[IDX(ii)] = center[IDX(ii)]; });
+        sfor<0, NU>([&](auto ii) { up[IDX(ii)] = u[IDX(ii)] + ((!is_vel && col == IDX(ii)) ? se : 0.0); });
+        if (cost && !(it & 1)) dcost = __ddiv_rn(__dsub_rn(cost_eval<T>(*cost, q, vp, up), c0), eps);
+        if (it == 0 || is_vel) build_vel<T, false>(m, ps, vp, w);   // ctrl columns keep the centre's velocity stage (mjSTAGE_VEL skip)
+        finish_smooth<T>(m, up, w);
+        solve<T>(m, w, warm, qacc, niter, 0.0);
+        if (!(it & 1)) {
+            sfor<0, NV>([&](auto jj) { qplus[IDX(jj)] = qacc[IDX(jj)]; });
+        } else {
+            sfor<0, NV>([&](auto jj) {
+                constexpr int j = IDX(jj);
+                double d = (qplus[j] - qacc[j]) * inv2eps;
+                finite = finite && isfinite(d);
+                const size_t off = base + NV * NV + (is_vel ? col + j * NV : NV * NV + col + j * NU);
+                for (int dd = 0; dd < dst.n; dd++) dst.p[dd][off] = d;
+            });
+            if (cost)   // without a device cost the gradient entries stay untouched
+                for (int dd = 0; dd < dst.n; dd++) dst.p[dd][base + S::NJAC + NV + (is_vel ? col : NV + col)] = dcost;
+        }
+    }
+    if (!finite && status) atomicExch(&status[kk], ILQG_ERR_NONFINITE);
 }
 
 template <class T, bool SYNC, int THREADS, int MINB>
@@ -743,6 +812,7 @@ struct Engine {
     virtual void set_fused_max(int) {}
     virtual void set_vu_classes(const char*) {}
     virtual void set_q_minb(int) {}
+    virtual void set_vu_pos(int) {}
     // ints of scratch fd() wants for `nknots` knots (bucket counters, keys, permutation); 0 = none
     // (`batch`: the size of the whole batch a chunk belongs to — the kernel variant is chosen on it, so that a chunked host
     //  call runs the same kernels, and returns the same bits, as one device call over the batch)
@@ -781,6 +851,7 @@ struct EngineT : Engine {
     int fused_max = FdFusedShape<T>::OK ? 64 : 0;
     void set_fused_max(int n) override { fused_max = FdFusedShape<T>::OK ? n : 0; }
     void set_q_minb(int n) override { q_minb = n; }
+    void set_vu_pos(int n) override { vu_pos = n; }
     void set_vu_classes(const char* e) override {
         vu_nclass = 0;
         while (*e && vu_nclass < 4) {
@@ -796,7 +867,8 @@ struct EngineT : Engine {
     }
     size_t fd_scratch_ints(int nknots, int batch) const override {
         constexpr int NTF = T::NV * (T::NV + 1) / 2;   // + the centre's Newton factor and active set per knot (FdBins::fac)
-        return (variant_for(batch) >= 3 && fd_bins && nknots < (1 << 24)) ? (size_t)FD_NBUCKET + 2 * (size_t)nknots * (NTF + 2) : 0;
+        if (!(variant_for(batch) >= 3 && fd_bins && nknots < (1 << 24))) return 0;
+        return (size_t)FD_NBUCKET + 2 * (size_t)nknots * (NTF + 2) + (vu_pos ? 2 * (size_t)nknots * pos_record_doubles<T>() : 0);
     }
     // CTA shapes of the split kernels (measured on B200 after the planar algebra shrank the per-rollout state):
     //   qvel/ctrl: 256 threads, one CTA per SM at 255 registers (two CTAs at 128 registers spill the rows' neighbours: +70 % time;
@@ -816,6 +888,9 @@ struct EngineT : Engine {
     int vu_nclass = 0;
     bool vu_attr_set = false;
     int q_minb = Q_MINB;
+    // qvel / ctrl columns on the centre's position-stage products (ILQG_VU_POS: 0 = own position stage per thread, 1 = loaded, one
+    // CTA per SM, 2 = loaded, two CTAs per SM at 128 registers)
+    int vu_pos = 0;
     void launch_split(int nknots, const double* qpos, const double* qvel, const double* ctrl, const ilqg_cost* cost_dev, const ilqg_fd_opts& o,
                       const FdDst& dst, const double* qacc_center, int* status, const FdBins& bins, cudaStream_t s, cudaEvent_t* ev) {
         using PV = FdSplit<T, VU_THREADS>;
@@ -823,6 +898,17 @@ struct EngineT : Engine {
         using SH = FdVuShared<T, VU_THREADS>;
         const int* perm = bins.perm;
         const unsigned grid_vu = (nknots + PV::KPC_VU - 1) / PV::KPC_VU;
+        if (bins.pos) {
+            if (vu_pos == 2)
+                fd_velctrl_loaded_kernel<T, VU_THREADS, 2><<<grid_vu, VU_THREADS, 0, s>>>(dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps, o.niter,
+                                                                                        dst, status, bins);
+            else
+                fd_velctrl_loaded_kernel<T, VU_THREADS, 1><<<grid_vu, VU_THREADS, 0, s>>>(dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps, o.niter,
+                                                                                        dst, status, bins);
+            if (ev) cudaEventRecord(ev[3], s);
+            launch_qpos(nknots, qpos, qvel, ctrl, cost_dev, o, dst, qacc_center, status, perm, s);
+            return;
+        }
         int lo = 0, hi = 0;   // classes cover lo < rows <= hi
         if constexpr (T::MAXEFC > 0) {
             if (bins.key && bins.fac) {
@@ -846,6 +932,11 @@ struct EngineT : Engine {
         fd_velctrl_kernel<T, true, VU_THREADS, VU_MINB><<<grid_vu, VU_THREADS, 0, s>>>(
             dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps, o.niter, dst, status, perm, bins, lo, hi);
         if (ev) cudaEventRecord(ev[3], s);
+        launch_qpos(nknots, qpos, qvel, ctrl, cost_dev, o, dst, qacc_center, status, perm, s);
+    }
+    void launch_qpos(int nknots, const double* qpos, const double* qvel, const double* ctrl, const ilqg_cost* cost_dev, const ilqg_fd_opts& o,
+                     const FdDst& dst, const double* qacc_center, int* status, const int* perm, cudaStream_t s) {
+        using PQ = FdSplit<T, Q_THREADS>;
         if (q_minb == 1)   // experiment (ILQG_Q_MINB=1): one CTA per SM, no register cap — half the local-memory footprint per SM
             fd_qpos_kernel<T, true, Q_THREADS, 1><<<(nknots + PQ::KPC_Q - 1) / PQ::KPC_Q, Q_THREADS, 0, s>>>(
                 dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps, o.niter, dst, status, perm);
@@ -861,11 +952,15 @@ struct EngineT : Engine {
         // perturbed evaluation in a single launch (30x more threads per knot: lower latency for small batches); fd_variant -1 = by size
         const int variant = variant_for(batch > nknots ? batch : nknots);
         if (nknots <= 0) return cudaSuccess;
-        FdBins bins{nullptr, nullptr, nullptr, nullptr};
+        FdBins bins{nullptr, nullptr, nullptr, nullptr, nullptr};
         if (scratch && fd_scratch_ints(nknots, batch > nknots ? batch : nknots)) {
             constexpr int NTF = T::NV * (T::NV + 1) / 2;
             bins.fac = vu_nclass > 0 ? reinterpret_cast<double*>(scratch) : nullptr;   // doubles first (the scratch base is 8-byte aligned)
             int* ints = scratch + 2 * (size_t)nknots * (NTF + 1);
+            if (vu_pos) {
+                bins.pos = reinterpret_cast<double*>(ints);
+                ints += 2 * (size_t)nknots * pos_record_doubles<T>();
+            }
             bins.cnt = ints;
             bins.key = (unsigned int*)(ints + FD_NBUCKET);
             bins.perm = ints + FD_NBUCKET + nknots;
@@ -888,6 +983,9 @@ struct EngineT : Engine {
         //  knots by the permutation the previous call on the same batch ended with — stance knots first, sharing warps — takes 21 us
         //  off it (SMs are busy 61 % of this kernel: ncu) but scrambles the ranks inside the buckets, which follow this kernel's
         //  execution order; the column kernels then lose the locality of neighbouring knots and give 17 us back.  Not kept.)
+        if (bins.pos)
+            fd_center_kernel<T, true><<<(nknots + 127) / 128, 128, 0, s>>>(dm, nknots, qpos, qvel, ctrl, warm, o.niter, o.nwarmup, qacc_center, status, bins, fd_diag);
+        else
         fd_center_kernel<T><<<(nknots + 127) / 128, 128, 0, s>>>(dm, nknots, qpos, qvel, ctrl, warm, o.niter, o.nwarmup, qacc_center, status, bins, fd_diag);
         if (bins.key) fd_bin_kernel<<<(nknots + 255) / 256, 256, 0, s>>>(nknots, bins);
         if (ev) cudaEventRecord(ev[1], s);
@@ -1231,6 +1329,7 @@ int ilqg_create(const ilqg_model* m, int device, ilqg_handle* out) {
     if (const char* e = getenv("ILQG_FD_FUSED_MAX")) eng->set_fused_max(atoi(e));
     if (const char* e = getenv("ILQG_VU_CLASSES")) eng->set_vu_classes(e);
     if (const char* e = getenv("ILQG_Q_MINB")) eng->set_q_minb(atoi(e));
+    if (const char* e = getenv("ILQG_VU_POS")) eng->set_vu_pos(atoi(e));
     if (const char* e = getenv("ILQG_HOST_CHUNKS")) h->host_chunks = atoi(e);
     if (const char* e = getenv("ILQG_HOST_COMP")) h->host_comp_streams = atoi(e);
     if (const char* e = getenv("ILQG_PIN_HOST")) h->pin_host = atoi(e) != 0;

@@ -18,8 +18,10 @@ h0 = pkg.Handle(model, 0)
 if os.environ.get("ILQG_WORKLOAD") == "stance":   # a hopper standing / bouncing on the ground: > 90 % of the knots in contact
     q, v, u, w, _ = wl.make_knots(h0, 1, 1000, seed=0, device="cuda:0", model="hopper")
     q, v, u, w = (x.repeat((ntraj * 21 + 999) // 1000, 1)[:ntraj * 21].contiguous() for x in (q, v, u, w))
-else:
+elif os.environ.get("ILQG_WORKLOAD") == "r1":     # round 1's batch: 23 % of the knots in contact, constant control
     q, v, u, w, nbad = wl.make_knots(h0, ntraj, 21, seed=0, device="cuda:0", model="hopper")
+else:                                              # the SURVEY 8d batch: half of the knots in contact, time-varying control
+    q, v, u, w, nbad = wl.make_knots_8d(h0, ntraj, 21, seed=0, device="cuda:0")
 n = q.shape[0]
 cost = pkg.make_cost(q1=[1.0])
 ref = None

@@ -881,6 +881,8 @@ struct EngineT : Engine {
     // only): one launch per class with a carve-out sized for it; knots without rows (flight) and knots above the last class
     // run the local-memory kernel, whose CTAs keep the whole L1.
     // MEASURED on B200 (round 2, tools/prof_split.py): not a gain.  Benchmark batch (23 % stance): local-memory kernel
+    // (With classes the last bits of a knot at a class boundary are not repeatable from run to run: the CTA that straddles two classes
+    //  goes to the kernel of its heaviest knot, and the ranks inside a class follow the centre kernel's execution order.)
     // 0.299 ms, one class of 16 rows 0.516 ms (each class is one more serialised launch with the 0.1 ms latency floor of a stance
     // CTA, and the carve-out takes the L1 that the rest of a rollout's local state lives in); a batch with 91 % of the knots in
     // stance: 0.779 ms local against 0.803-0.826 ms.  Off by default.

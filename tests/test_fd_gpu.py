@@ -302,3 +302,21 @@ def test_host_pinning_of_caller_buffers_is_transparent(pkg, oracle, omodels):
     h.fd_batch_host(q, v, u, w, cost, deriv=buf)
     h.close()   # unregisters
     buf[:] = 1.0  # the array is ordinary memory again
+
+
+@pytest.mark.parametrize("n", [0, 1, 21, 31, 33, 64, 65])
+def test_tiny_and_empty_batches(pkg, handles, oracle, omodels, n):
+    """Edge sizes of the small-batch kernels (one launch up to 64 knots, two overlapped launches above): empty, a single knot, one
+    trajectory, warp-boundary counts — against the oracle, with the centre accelerations and status words."""
+    h = handles["hopper"]; om = omodels["hopper"]
+    q, v, u, w = scenario_states("hopper", max(n, 1), seed=77, oracle=oracle, om=om, roll=130)
+    q, v, u, w = q[:n], v[:n], u[:n], w[:n]
+    cost = oracle.make_cost(q2=[1, 10], v2=[1, 10], u2=[1], q1=[0.5])
+    d_gpu, a_gpu, status = h.fd_batch_host(q, v, u, w, cost)
+    assert d_gpu.shape == (n, 105) and status.shape == (n,)
+    if n == 0:
+        return
+    d_ref, a_ref, _ = oracle.fd_batch(om, q, v, u, w, cost)
+    assert status.sum() == 0
+    assert_deriv_close(d_gpu, d_ref, 6, 3)
+    assert np.allclose(a_gpu, a_ref, rtol=1e-9, atol=1e-9)

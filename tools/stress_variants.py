@@ -1,0 +1,49 @@
+"""Idempotence / uninitialised-memory stress of every FD kernel variant: device memory is poisoned with NaN bit patterns and handed
+back to the driver before each handle is created, so that scratch the library allocates starts as garbage; every variant must then
+give finite, repeatable Jacobians equal (to the FD tolerance) to the default path's.   python tools/stress_variants.py [rounds]"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import __graft_entry__ as e
+pkg = e.load_package()
+from ilqg_mujoco_b200 import workload as wl
+rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+h0 = pkg.Handle(pkg.Model.named("hopper"), 0)
+q, v, u, w, _ = wl.make_knots_8d(h0, 2048, 21, seed=3, device="cuda:0")
+n = q.shape[0]
+cost = pkg.make_cost(q1=[1.0])
+ref = torch.zeros((n, 105), dtype=torch.float64, device="cuda:0")
+h0.fd_batch_dev(q, v, u, w, ref, cost=cost)
+torch.cuda.synchronize()
+envs = [{}, dict(ILQG_FD_VARIANT="1"), dict(ILQG_FD_VARIANT="2"), dict(ILQG_FD_VARIANT="2", ILQG_FD_PDL="0"), dict(ILQG_FD_VARIANT="3"),
+        dict(ILQG_FD_VARIANT="3", ILQG_FD_BINS="0"), dict(ILQG_FD_VARIANT="3", ILQG_VU_CLASSES="8,16"), dict(ILQG_FD_VARIANT="3", ILQG_VU_CLASSES="4"),
+        dict(ILQG_FD_VARIANT="3", ILQG_VU_POS="1"), dict(ILQG_FD_VARIANT="3", ILQG_VU_POS="2"), dict(ILQG_FD_VARIANT="3", ILQG_Q_MINB="1")]
+bad = 0
+for r in range(rounds):
+    for env in envs:
+        x = torch.full((300_000_000 // 8,), float("nan"), dtype=torch.float64, device="cuda:0")   # poison, then give it back to the driver
+        del x
+        torch.cuda.empty_cache()
+        os.environ.update(env)
+        h = pkg.Handle(pkg.Model.named("hopper"), 0)
+        for k in env:
+            del os.environ[k]
+        outs = []
+        st = torch.zeros(n, dtype=torch.int32, device="cuda:0")
+        for rep in range(3):
+            a = torch.full((n, 105), float("nan"), dtype=torch.float64, device="cuda:0")
+            h.fd_batch_dev(q, v, u, w, a, None, st if rep == 0 else None, cost=cost)
+            torch.cuda.synchronize()
+            outs.append(a)
+        if "ILQG_VU_CLASSES" in env:   # a knot at a class boundary may be served by either kernel from run to run (same value, other last bits)
+            same = all(float((outs[0] - o).abs().max()) <= 1e-12 * float(ref.abs().max()) for o in outs[1:])
+        else:
+            same = all(torch.equal(outs[0], o) for o in outs[1:])
+        fin = bool(torch.isfinite(outs[0]).all())
+        err = float((outs[0] - ref).abs().max() / ref.abs().max())
+        ok = same and fin and err < 1e-7 and int((st != 0).sum()) == 0
+        bad += not ok
+        print(f"round {r} {env}: repeatable={same} finite={fin} max rel diff to default={err:.2e} {'ok' if ok else 'FAIL'}")
+        h.close()
+print("FAILURES:", bad)
+sys.exit(1 if bad else 0)

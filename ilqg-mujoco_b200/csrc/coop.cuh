@@ -109,11 +109,13 @@ struct CoopMem {
 __host__ __device__ inline int coop_nt(int nv) { return nv * (nv + 1) / 2; }
 // `maxefc`: row capacity of the block (COOP_MAXEFC everywhere except the qpos-column kernel, which is launched once per capacity
 // class with the knots whose row bound fits — the rows are the largest part of a rollout's shared-memory state)
-__host__ __device__ inline size_t coop_cstate_doubles(const ilqg_model& m, bool full, int maxefc = COOP_MAXEFC) {
+// with_L = false: a block without the Cholesky factor of M (the qpos-column kernel: its evaluations start from the centre's
+// solution and never need qacc_smooth, see coop_solve's warm_only)
+__host__ __device__ inline size_t coop_cstate_doubles(const ilqg_model& m, bool full, int maxefc = COOP_MAXEFC, bool with_L = true) {
     const size_t nv = m.nv, nb = m.nbody;
     size_t n = m.nq + nv + m.nu + nv;                       // q v u center
     n += 6 * nv + 10 * nb + 3 * nb + nv;                    // cdof cinert com dspr
-    n += 2 * (size_t)coop_nt(m.nv);                         // M L
+    n += (with_L ? 2 : 1) * (size_t)coop_nt(m.nv);          // M L
     n += (size_t)maxefc * nv + 3 * maxefc;                  // J D rB rkt
     n += 4;                                                 // hdr (8 ints)
     n = (n + 1) & ~(size_t)1;
@@ -131,17 +133,17 @@ __host__ __device__ inline size_t coop_priv_doubles(const ilqg_model& m, int max
     return (n + 1) & ~(size_t)1;
 }
 
-DEV void coop_carve_cstate(CoopMem& w, double* base, const ilqg_model& m, int maxefc = COOP_MAXEFC) {
+DEV void coop_carve_cstate(CoopMem& w, double* base, const ilqg_model& m, int maxefc = COOP_MAXEFC, bool with_L = true) {
     w.maxefc = maxefc;
     const int nq = m.nq, nv = m.nv, nu = m.nu, nb = m.nbody, nt = coop_nt(m.nv);
     double* p = base;
     auto take = [&](size_t n) { double* r = p; p += n; return r; };
     w.q = take(nq); w.v = take(nv); w.u = take(nu); w.center = take(nv);
     w.cdof = take(6 * nv); w.cinert = take(10 * nb); w.com = take(3 * nb); w.dspr = take(nv);
-    w.M = take(nt); w.L = take(nt);
+    w.M = take(nt); w.L = with_L ? take(nt) : nullptr;
     w.J = take((size_t)maxefc * nv); w.D = take(maxefc); w.rB = take(maxefc); w.rkt = take(maxefc);
     w.hdr = reinterpret_cast<int*>(p);
-    p = base + coop_cstate_doubles(m, false, maxefc);
+    p = base + coop_cstate_doubles(m, false, maxefc, with_L);
     w.fb0 = take(nv); w.aref0 = take(maxefc); w.Hc = take(nt);   // only valid where the full C-state is allocated
 }
 DEV void coop_carve_priv(CoopMem& w, double* base, const ilqg_model& m, int maxefc = COOP_MAXEFC) {
@@ -299,7 +301,7 @@ DEV void gs3(double* p, V3 a) { p[0] = a.x; p[1] = a.y; p[2] = a.z; }
 // ncand >= 0, else over every pair; with cand_out != NULL (centre evaluation) it also records, in pair order, the pairs
 // within margin + slack of contact: cand_out[0] = count (or -1 when more than COOP_MAXCAND), cand_out[1..] = pair indices.
 DEV void coop_pos(const GModel* __restrict__ g, CoopMem& w, int lane, const int* __restrict__ cand, int ncand, int* __restrict__ cand_out,
-                  double slack) {
+                  double slack, bool factor_M = true) {
     const ilqg_model& m = g->m;
     const int nv = m.nv, nb = m.nbody, nj = m.njnt, ng = m.ngeom, nt = coop_nt(m.nv);
     // ---- kinematics, level by level (a level's bodies are independent)
@@ -439,9 +441,11 @@ DEV void coop_pos(const GModel* __restrict__ g, CoopMem& w, int lane, const int*
         }
     }
     __syncwarp();
-    for (int e = lane; e < nt; e += 32) w.L[e] = w.M[e];
-    __syncwarp();
-    coop_chol(w.L, nv, lane);
+    if (factor_M) {
+        for (int e = lane; e < nt; e += 32) w.L[e] = w.M[e];
+        __syncwarp();
+        coop_chol(w.L, nv, lane);
+    }
     // ---- constraint rows: joint limits
     // rowbound: the rows an evaluation within +-eps of this one can have at most — limits within margin + slack, and for every
     // pair within margin + slack of contact the most contacts its narrow phase can return times its rows per contact
@@ -703,7 +707,7 @@ DEV void coop_vel(const GModel* __restrict__ g, CoopMem& w, const double* vv, in
 }
 
 // actuation, qfrc_smooth, qacc_smooth (in: private fb; uu: ctrl vector in shared memory)
-DEV void coop_smooth(const GModel* __restrict__ g, CoopMem& w, const double* uu, int lane) {
+DEV void coop_smooth(const GModel* __restrict__ g, CoopMem& w, const double* uu, int lane, bool solve_as = true) {
     const ilqg_model& m = g->m;
     const int nv = m.nv;
     double f = 0;
@@ -719,8 +723,10 @@ DEV void coop_smooth(const GModel* __restrict__ g, CoopMem& w, const double* uu,
                 }
         w.fs[lane] = f;
     }
-    const double a = coop_chol_solve(w.L, f, nv, lane);
-    if (lane < nv) w.as[lane] = a;
+    if (solve_as) {
+        const double a = coop_chol_solve(w.L, f, nv, lane);
+        if (lane < nv) w.as[lane] = a;
+    }
     __syncwarp();
 }
 
@@ -783,22 +789,39 @@ DEV void coop_hessian_factor(const CoopMem& w, double* H, int nv, int na, int la
 // reuse: take the C-state's cached factor Hc whenever the active set equals the one it was built for (the qvel / ctrl columns
 // of a knot share M, J and D with the centre, so all of their Newton systems with that active set are the same matrix)
 // returns the Newton iterations run; *exact (optional) = the solve left through the exact-optimum test or had no rows
+// warm_only: the solve of a PERTURBED evaluation that starts from the centre's solution (mjderivative.cpp:75,91).  MuJoCo starts from
+// the better of the warm start and qacc_smooth; within +-eps of the centre that is the warm start whenever a row is active, and when none
+// is the first Newton step (Hessian = M) lands on qacc_smooth exactly — so neither qacc_smooth nor the Cholesky factor of M is needed:
+// one 27 x 27 factorisation per evaluation instead of two.  The Gauss term of the cost is taken as a'Ma/2 - a'fs (same differences).
 DEV int coop_solve(const GModel* __restrict__ g, CoopMem& w, int maxiter, double tol, int lane, bool need_forces = false, bool reuse = false,
-                   bool* exact = nullptr) {
+                   bool* exact = nullptr, bool warm_only = false) {
     const ilqg_model& m = g->m;
     const int nv = m.nv, ne = w.hdr[0];
     static_assert(COOP_MAXEFC <= 128, "mask width");
     if (ne == 0) {
-        if (lane < nv) { w.qacc[lane] = w.as[lane]; w.warm[lane] = w.as[lane]; w.fc[lane] = 0; }
+        if (warm_only) {   // qacc = M^-1 qfrc_smooth through the (one) factorisation of this evaluation
+            coop_hessian_factor(w, w.H, nv, 0, lane);
+            const double a = coop_chol_solve(w.H, lane < nv ? w.fs[lane] : 0.0, nv, lane);
+            if (lane < nv) { w.qacc[lane] = a; w.warm[lane] = a; w.fc[lane] = 0; }
+        } else if (lane < nv) { w.qacc[lane] = w.as[lane]; w.warm[lane] = w.as[lane]; w.fc[lane] = 0; }
         __syncwarp();
         if (exact) *exact = true;
         return 0;
     }
     if (exact) *exact = false;
     const bool dof = lane < nv;
-    const double fs_i = dof ? w.fs[lane] : 0.0, as_i = dof ? w.as[lane] : 0.0, warm_i = dof ? w.warm[lane] : 0.0;
+    const double fs_i = dof ? w.fs[lane] : 0.0, as_i = (dof && !warm_only) ? w.as[lane] : 0.0, warm_i = dof ? w.warm[lane] : 0.0;
     double qacc_i, Ma_i;
-    {
+    if (warm_only) {
+        for (int r = lane; r < ne; r += 32) {
+            double jw = -w.aref[r];
+            const double* Jr = w.J + r * nv;
+            for (int i = 0; i < nv; i++) jw += Jr[i] * w.warm[i];
+            w.jar[r] = jw;
+        }
+        qacc_i = warm_i;
+        Ma_i = coop_symv(w.M, w.warm, nv, lane);
+    } else {
         // the better of the warm start and qacc_smooth; one pass over the rows evaluates both
         double cw = 0, cs = 0;
         for (int r = lane; r < ne; r += 32) {
@@ -849,7 +872,7 @@ DEV int coop_solve(const GModel* __restrict__ g, CoopMem& w, int maxiter, double
             for (int a = 0; a < na; a++) { const int r = w.alist[a]; f += w.J[r * nv + lane] * (-w.D[r] * w.jar[r]); }
         fc_i = f;
         const double grad_i = Ma_i - fs_i - f;
-        if (dof) c += 0.5 * (Ma_i - fs_i) * (qacc_i - as_i);
+        if (dof) c += warm_only ? (0.5 * Ma_i - fs_i) * qacc_i : 0.5 * (Ma_i - fs_i) * (qacc_i - as_i);
         cost = warp_sum(c);
         const double* Hf = w.H;
         if (reuse && w.hdr[2] && act.w[0] == (unsigned)w.hdr[4] && act.w[1] == (unsigned)w.hdr[5] && act.w[2] == (unsigned)w.hdr[6] &&
@@ -1107,7 +1130,7 @@ __global__ void __launch_bounds__(32) coop_qpos_kernel(const GModel* __restrict_
     }
     CoopMem w;
     double* base = coop_smem + (size_t)wib * (cdbl + pdbl);
-    coop_carve_cstate(w, base, m, cap);
+    coop_carve_cstate(w, base, m, cap, false);   // no factor of M in this kernel (coop_solve's warm_only)
     coop_carve_priv(w, base + cdbl, m, cap);
     const int* kc = cand ? cand + (size_t)k * (COOP_MAXCAND + 1) : nullptr;
     const int ncand = kc ? kc[0] : -1;
@@ -1134,13 +1157,13 @@ __global__ void __launch_bounds__(32) coop_qpos_kernel(const GModel* __restrict_
             if (cost && sgn > 0) dcost = __ddiv_rn(__dsub_rn(coop_cost_eval(cost, w.q, w.v, w.u, nq, nv, nu), c0), eps);
         }
         __syncwarp();
-        coop_pos(g, w, lane, kc ? kc + 1 : nullptr, ncand, nullptr, 0.0);
+        coop_pos(g, w, lane, kc ? kc + 1 : nullptr, ncand, nullptr, 0.0, false);
         ok = ok && w.hdr[1] != 0;
         coop_vel(g, w, w.v, lane);
-        coop_smooth(g, w, w.u, lane);
+        coop_smooth(g, w, w.u, lane, false);
         if (lane < nv) w.warm[lane] = qacc_center[(size_t)k * nv + lane];
         __syncwarp();
-        coop_solve(g, w, niter, 0.0, lane);
+        coop_solve(g, w, niter, 0.0, lane, false, false, nullptr, true);
         const double a = lane < nv ? w.qacc[lane] : 0.0;
         if (sgn > 0) plus = a;
         else if (lane < nv) {

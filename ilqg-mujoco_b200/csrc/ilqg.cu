@@ -1068,7 +1068,7 @@ struct CoopEngine : Engine {
         cfull = (int)coop_cstate_doubles(m, true);
         pdbl = (int)coop_priv_doubles(m);
         for (int c = 0; c < NCAP; c++) {
-            cdbl_c[c] = (int)coop_cstate_doubles(m, false, cap_class[c]);
+            cdbl_c[c] = (int)coop_cstate_doubles(m, false, cap_class[c], false);   // the qpos kernel's blocks carry no factor of M
             pdbl_c[c] = (int)coop_priv_doubles(m, cap_class[c]);
         }
         cudaError_t e = cudaMalloc(&d_g, sizeof(GModel));

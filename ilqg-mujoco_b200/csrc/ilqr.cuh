@@ -19,6 +19,13 @@ namespace ilqg {
 template <class T>
 DEV double cost_eval(const ilqg_cost& c, const double (&q)[T::NQ], const double (&v)[T::NV], const double (&u)[nz(T::NU)]);
 
+// bring [p, p + bytes) towards the SM (every 128-byte line the range touches)
+DEV void prefetch_l1(const void* p, int bytes) {
+    const char* c = static_cast<const char*>(p);
+    for (int off = 0; off < bytes; off += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(c + off));
+    if (bytes > 8 && (bytes & 127) != 8) asm volatile("prefetch.global.L1 [%0];" ::"l"(c + bytes - 8));
+}
+
 struct IlqrBuffers {
     int ninst, N, nalpha;
     // nominal trajectory and the state every forward pass starts from (ILQR::d)
@@ -60,8 +67,18 @@ __global__ void __launch_bounds__(128) ilqr_rollout_kernel(const __grid_constant
     double J = 0;
     const size_t T1 = (size_t)(b.N + 1) * ninst;
     // The rollout is one dependent chain per thread; the knot's feedback data (K, k, nominal) does not depend on the state, so
-    // the NEXT knot's record is fetched while the current mj_step runs instead of stalling the chain on an L2 round trip.
+    // the NEXT knot's record is brought into L1 while the current mj_step runs instead of stalling the chain on an L2 round trip.
+    // (A prefetch instruction, not loads into registers: ncu showed the compiler spilling the early-loaded record to local memory
+    //  right behind the loads — the spill stores waited for the L2 round trip the loads were meant to hide, 14 % of the kernel.)
     double Kn[nz(NU) * NX], kn_[nz(NU)], xq[NQ], xv[NV], xu[nz(NU)];
+    auto prefetch = [&](int n) {
+        const size_t kn = (size_t)n * ninst + i;
+        prefetch_l1(b.K + kn * NU * NX, NU * NX * 8);
+        prefetch_l1(b.k + kn * NU, NU * 8);
+        prefetch_l1(b.nom_u + kn * NU, NU * 8);
+        prefetch_l1(b.nom_q + kn * NQ, NQ * 8);
+        prefetch_l1(b.nom_v + kn * NV, NV * 8);
+    };
     auto fetch = [&](int n) {
         const size_t kn = (size_t)n * ninst + i;
         sfor<0, NU * NX>([&](auto ee) { Kn[IDX(ee)] = b.K[kn * NU * NX + IDX(ee)]; });
@@ -69,9 +86,9 @@ __global__ void __launch_bounds__(128) ilqr_rollout_kernel(const __grid_constant
         sfor<0, NQ>([&](auto ii) { xq[IDX(ii)] = b.nom_q[kn * NQ + IDX(ii)]; });
         sfor<0, NV>([&](auto ii) { xv[IDX(ii)] = b.nom_v[kn * NV + IDX(ii)]; });
     };
-    fetch(b.N);
     for (int n = b.N; n >= 0; n--) {
         const size_t kn = (size_t)n * ninst + i;
+        fetch(n);
         // u = K[n] (x - x*_n) + alpha k[n] + u*_n      (ilqr.h:126; alpha = 1 there)
         double dx[NX];
         sfor<0, NV>([&](auto ii) {
@@ -84,7 +101,7 @@ __global__ void __launch_bounds__(128) ilqr_rollout_kernel(const __grid_constant
             sfor<0, NX>([&](auto cc) { s += Kn[r + IDX(cc) * NU] * dx[IDX(cc)]; });
             u[r] = s + alpha * kn_[r] + xu[r];
         });
-        if (n > 0) fetch(n - 1);
+        if (n > 0) prefetch(n - 1);
         // snapshot the knot (cpMjData(dArray[n], d), ilqr.h:127) into this alpha's candidate
         const size_t cn = (size_t)a * T1 + kn;
         sfor<0, NQ>([&](auto ii) { b.cand_q[cn * NQ + IDX(ii)] = q[IDX(ii)]; });
@@ -180,6 +197,9 @@ struct BackwardSmem {
     double V[NX * NX], A[NX * NX], Acl[NX * NX], T1[NX * NX], Vn[NX * NX];
     double B[NX * NU], VB[NX * NU], K[NU * NX], S[NU * NU];
     double v[NX], q[NX], c[NX], w[NX], wV[NX], rK[NX], vn[NX], r[NU], k[NU];
+    // a CTA-wide group (LANES > 32) factorises S once per knot (ldlt_factor_warp); lane groups solve on private copies
+    double Lf[LANES > 32 ? NU * NU : 1], Df[LANES > 32 ? NU : 1];
+    int perm[LANES > 32 ? NU : 1];
 };
 
 template <int N>
@@ -210,6 +230,65 @@ DEV void ldlt_solve_small(const double* S, double* x) {  // S: N x N column-majo
     for (int i = 0; i < N; i++) y[i] /= D[i];
     for (int i = N - 1; i >= 0; i--) for (int c = i + 1; c < N; c++) y[i] -= L[c + i * N] * y[c];
     for (int i = 0; i < N; i++) x[perm[i]] = y[i];
+}
+
+// The same pivoted L D L^T for a large nu (the humanoid's 21 x 21), done ONCE per knot by one warp in shared memory — same pivot
+// rule (largest |diagonal|, first among equals), same order of operations per element as ldlt_solve_small — and applied to the
+// nx + 1 right-hand sides by one lane each.  W: N x N work copy of S (destroyed), L: unit lower factor, D, perm: outputs.
+template <int N>
+DEV void ldlt_factor_warp(double* W, double* L, double* D, int* perm, int lane) {
+    for (int e = lane; e < N * N; e += 32) L[e] = 0;
+    for (int e = lane; e < N; e += 32) perm[e] = e;
+    __syncwarp();
+    for (int j = 0; j < N; j++) {
+        double best = -1;
+        int p = N;
+        for (int i = j + lane; i < N; i += 32) { const double a = fabs(W[i + i * N]); if (a > best) { best = a; p = i; } }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int op = __shfl_xor_sync(0xffffffffu, p, o);
+            if (ob > best || (ob == best && op < p)) { best = ob; p = op; }
+        }
+        if (p >= N) p = j;   // (no comparable diagonal left: NaNs propagate, indices stay in range)
+        if (p != j) {   // (uniform over the warp)
+            for (int c = lane; c < N; c += 32) { const double t = W[j + c * N]; W[j + c * N] = W[p + c * N]; W[p + c * N] = t; }
+            __syncwarp();
+            for (int r = lane; r < N; r += 32) { const double t = W[r + j * N]; W[r + j * N] = W[r + p * N]; W[r + p * N] = t; }
+            for (int c = lane; c < j; c += 32) { const double t = L[j + c * N]; L[j + c * N] = L[p + c * N]; L[p + c * N] = t; }
+            if (lane == 0) { const int t = perm[j]; perm[j] = perm[p]; perm[p] = t; }
+            __syncwarp();
+        }
+        const double d = W[j + j * N];
+        if (lane == 0) { D[j] = d; L[j + j * N] = 1; }
+        for (int i = j + 1 + lane; i < N; i += 32) L[i + j * N] = W[i + j * N] / d;
+        __syncwarp();
+        const int m = N - j - 1;
+        for (int e = lane; e < m * m; e += 32) {
+            const int r = j + 1 + e % m, c = j + 1 + e / m;
+            W[r + c * N] -= L[r + j * N] * d * L[c + j * N];
+        }
+        __syncwarp();
+    }
+}
+
+template <int N>
+DEV void ldlt_apply(const double* L, const double* D, const int* perm, double* x, int stride) {  // x[a * stride], in/out
+    double y[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) y[i] = x[perm[i] * stride];
+#pragma unroll
+    for (int i = 0; i < N; i++)
+#pragma unroll
+        for (int c = 0; c < i; c++) y[i] -= L[i + c * N] * y[c];
+#pragma unroll
+    for (int i = 0; i < N; i++) y[i] /= D[i];
+#pragma unroll
+    for (int i = N - 1; i >= 0; i--)
+#pragma unroll
+        for (int c = i + 1; c < N; c++) y[i] -= L[c + i * N] * y[c];
+#pragma unroll
+    for (int i = 0; i < N; i++) x[perm[i] * stride] = y[i];
 }
 
 // Small state vectors (2 nv <= 4: the inverted pendulum): ONE THREAD per instance, every matrix in registers, all loops unrolled.
@@ -503,7 +582,12 @@ __global__ void __launch_bounds__(LANES * GROUPS) ilqr_backward_kernel(IlqrBuffe
             }
         }
         gsync();
-        if (live) {  // K[n] = S^-1 rhsK (column by column), k[n] = S^-1 rhsk
+        if constexpr (LANES > 32) {
+            if (live && lane < 32) ldlt_factor_warp<NU>(s.S, s.Lf, s.Df, s.perm, lane);
+            gsync();
+            if (live)
+                for (int c = lane; c < NX + 1; c += LANES) ldlt_apply<NU>(s.Lf, s.Df, s.perm, c < NX ? s.K + c * NU : s.k, 1);
+        } else if (live) {  // K[n] = S^-1 rhsK (column by column), k[n] = S^-1 rhsk
             for (int c = lane; c < NX + 1; c += LANES) {
                 double x[NU];
                 if (c < NX) { for (int a = 0; a < NU; a++) x[a] = s.K[a + c * NU]; }
@@ -539,13 +623,17 @@ __global__ void __launch_bounds__(LANES * GROUPS) ilqr_backward_kernel(IlqrBuffe
                 double t = 0;
                 for (int x = 0; x < NX; x++) t += CMX(s.V, r, x, NX) * CMX(s.Acl, x, c, NX);
                 s.T1[e] = t;
+                // wide groups: Acl' into A (free from here on) so that the next product reads consecutive words per lane instead
+                // of a stride of NX doubles (NX = 54: 4-way bank conflicts on every load)
+                if constexpr (LANES > 32) CMX(s.A, c, r, NX) = s.Acl[e];
             }
         gsync();
         if (live)
             for (int e = lane; e < NX * NX; e += LANES) {  // Vn = Acl' V Acl + q'q + (rK)'(rK)   (ilqr.h:173)
                 int r = e % NX, c = e / NX;
                 double t = 0;
-                for (int x = 0; x < NX; x++) t += CMX(s.Acl, x, r, NX) * CMX(s.T1, x, c, NX);
+                if constexpr (LANES > 32) { for (int x = 0; x < NX; x++) t += CMX(s.A, r, x, NX) * CMX(s.T1, x, c, NX); }
+                else for (int x = 0; x < NX; x++) t += CMX(s.Acl, x, r, NX) * CMX(s.T1, x, c, NX);
                 s.Vn[e] = t + s.q[r] * s.q[c] + s.rK[r] * s.rK[c];
             }
         gsync();

@@ -13,17 +13,27 @@ dev = "cuda:0"
 model = pkg.Model.named(name)
 h = pkg.Handle(model, 0)
 L = pkg.lib()
-if name == "inverted_pendulum":
-    q, v, u, _ = wl.pendulum_initial_states(ninst, seed=100)
-    cost = pkg.make_cost(q2=[1, 10], v2=[1, 10], u2=[1])
+N = 20
+if name == "humanoid":   # bench.py's bench_humanoid_ilqr: tangent-space extension, N = 10
+    N = 10
+    dq, dv, du, dw, _ = wl.humanoid_states(h, ninst, seed=50, device=dev)
+    du = du * 0.0
+    cost = pkg.make_cost(q2=[0, 0, 2.0, 0, 1, 1, 0], q1=[0, 0, -5.2], v2=[0.05] * 27, u2=[0.02] * 21)
 else:
-    q, v, u, _ = wl.hopper_initial_states(ninst, seed=100)
-    cost = pkg.make_cost(q2=[0, 1, 1, 0, 0, 0], v2=[1] * 6, u2=[0.1] * 3)
-u = u * 0.0
-dq, dv, du = (torch.from_numpy(a).to(dev) for a in (q, v, u))
-dw = torch.zeros((ninst, model.nv), dtype=torch.float64, device=dev)
-il = pkg.Ilqr(h, ninst, 20, tuple(0.5 ** a for a in range(nalpha)))
+    if name == "inverted_pendulum":
+        q, v, u, _ = wl.pendulum_initial_states(ninst, seed=100)
+        cost = pkg.make_cost(q2=[1, 10], v2=[1, 10], u2=[1])
+    else:
+        q, v, u, _ = wl.hopper_initial_states(ninst, seed=100)
+        cost = pkg.make_cost(q2=[0, 1, 1, 0, 0, 0], v2=[1] * 6, u2=[0.1] * 3)
+    u = u * 0.0
+    dq, dv, du = (torch.from_numpy(a).to(dev) for a in (q, v, u))
+    dw = torch.zeros((ninst, model.nv), dtype=torch.float64, device=dev)
+il = pkg.Ilqr(h, ninst, N, tuple(0.5 ** a for a in range(nalpha)))
 il.set_cost(cost)
+if name == "humanoid":
+    il.set_layout(True)
+    il.set_mu(1000.0)
 s = torch.cuda.current_stream().cuda_stream
 sp = C.c_void_p(s)
 for rep in range(3):

@@ -69,7 +69,9 @@ __global__ void __launch_bounds__(128) ilqr_rollout_kernel(const __grid_constant
     // The rollout is one dependent chain per thread; the knot's feedback data (K, k, nominal) does not depend on the state, so
     // the NEXT knot's record is brought into L1 while the current mj_step runs instead of stalling the chain on an L2 round trip.
     // (A prefetch instruction, not loads into registers: ncu showed the compiler spilling the early-loaded record to local memory
-    //  right behind the loads — the spill stores waited for the L2 round trip the loads were meant to hide, 14 % of the kernel.)
+    //  right behind the loads — the spill stores waited for the L2 round trip the loads were meant to hide, 14 % of the kernel's
+    //  stall samples; with the prefetch 10 % sit on the first use instead.  Staging the record in shared memory with cp.async was
+    //  also measured: pendulum forward pass 0.138 -> 0.137 ms, hopper 0.328 -> 0.348 ms — not kept.)
     double Kn[nz(NU) * NX], kn_[nz(NU)], xq[NQ], xv[NV], xu[nz(NU)];
     auto prefetch = [&](int n) {
         const size_t kn = (size_t)n * ninst + i;

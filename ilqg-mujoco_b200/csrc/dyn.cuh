@@ -1260,6 +1260,214 @@ DEV void solve(const DevModel<T>& m, W& w, double (&warm)[T::NV], double (&qacc)
     sfor<0, NV>([&](auto ii) { warm[IDX(ii)] = qacc[IDX(ii)]; });
 }
 
+// ------------------------------------------------------------------ the same solve by a whole warp (small batches)
+// A pass over a small batch (one horizon, a single trajectory) is the latency of its longest dependent chain, and the longest link is
+// the centre evaluation's COLD solve of a stance knot (mjderivative.cpp:64-68): several Newton iterations, each a string of passes of
+// one thread over its rows in local memory.  In the one-launch kernel the other lanes of the knot's warp have nothing to do meanwhile.
+// Here they take the rows: the centre lane (`src`) stages its problem in shared memory (rows J | D | aref, then M, qfrc_smooth,
+// qacc_smooth, warm start), lane r keeps rows r and r + 32 in registers, and every pass over the rows of solve() becomes one or two
+// rows per lane and a butterfly sum: gradient, cost and the 21 entries of the Hessian's row term in one round of reductions, the line
+// search two sums and a ballot per trial point.  The dense nv x nv algebra (products with M, Cholesky, triangular solves) is done by
+// every lane on identical operands — SIMT executes it once either way, and the xor butterfly leaves bit-identical sums on all lanes, so
+// the warp stays converged and every lane ends with the solution: the warm start of the knot's perturbed evaluations
+// (mjderivative.cpp:75,91) needs no hand-over.  Same algorithm, same decisions (active sets as ballot masks, exact-optimum exit,
+// MuJoCo's termination rule) as solve(); the sums associate differently, so results agree to round-off, not bit for bit.
+template <class T>
+struct CoopSolveShape {
+    static constexpr int NV = T::NV, NT = NV * (NV + 1) / 2, ME = nz(T::MAXEFC), RS = NV + 2;
+    static constexpr int NS = (ME + 31) / 32;              // row slots per lane
+    static constexpr int DOUBLES = ME * RS + NT + 3 * NV;  // shared memory per warp
+};
+DEV double warp_allsum(double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+// Called by all 32 lanes, converged.  `w`, `warm`: only the src lane's are read.  Out, on every lane: qacc = warm = the solution;
+// iters / exact as Work::iters / Work::exact of solve(); nact = active rows at the solution.
+template <class T, class W>
+DEV void solve_coop(const DevModel<T>& m, W& w, bool is_src, int src, double* __restrict__ sh, double (&warm)[T::NV], double (&qacc)[T::NV],
+                    int maxiter, double tol, int& iters, int& exact, int& nact) {
+    using S = CoopSolveShape<T>;
+    constexpr int NV = S::NV, NT = S::NT, NS = S::NS, RS = S::RS;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int ne = __shfl_sync(FULL, w.nefc, src);
+    double* shv = sh + S::ME * RS;   // M | fs | as | warm
+    __syncwarp();                    // (readers of the previous call's block are done)
+    if (is_src) {
+        for (int r = 0; r < ne; r++) {
+            sfor<0, NV>([&](auto ii) { sh[r * RS + IDX(ii)] = w.rows.J(r, IDX(ii)); });
+            sh[r * RS + NV] = w.rows.D(r);
+            sh[r * RS + NV + 1] = w.rows.aref(r);
+        }
+        sfor<0, NT>([&](auto tt) { shv[IDX(tt)] = w.M[IDX(tt)]; });
+        sfor<0, NV>([&](auto ii) { shv[NT + IDX(ii)] = w.fs[IDX(ii)]; shv[NT + NV + IDX(ii)] = w.as[IDX(ii)]; shv[NT + 2 * NV + IDX(ii)] = warm[IDX(ii)]; });
+    }
+    __syncwarp();
+    double fs[NV], as[NV];
+    sfor<0, NV>([&](auto ii) { fs[IDX(ii)] = shv[NT + IDX(ii)]; as[IDX(ii)] = shv[NT + NV + IDX(ii)]; warm[IDX(ii)] = shv[NT + 2 * NV + IDX(ii)]; });
+    iters = 0;
+    exact = 1;
+    nact = 0;
+    if (ne == 0) {
+        sfor<0, NV>([&](auto ii) { qacc[IDX(ii)] = as[IDX(ii)]; warm[IDX(ii)] = as[IDX(ii)]; });
+        return;
+    }
+    exact = 0;
+    const double scale = 1.0 / (m.meaninertia * (NV > 1 ? NV : 1));
+    // this lane's rows; a lane without one holds a row that is never active (J = 0, D = 0, residual +1)
+    double Jr[NS][NV], Dr[NS], jar[NS], jv[NS];
+    double Ma[NV], grad[NV], search[NV], Mv[NV];
+    {
+        double cw = 0, cs = 0, jw[NS], js[NS];
+        sfor<0, NS>([&](auto ss) {
+            constexpr int s = IDX(ss);
+            const int r = lane + 32 * s;
+            const bool has = r < ne;
+            const double* row = sh + (has ? r : 0) * RS;
+            sfor<0, NV>([&](auto ii) { Jr[s][IDX(ii)] = has ? row[IDX(ii)] : 0.0; });
+            Dr[s] = has ? row[NV] : 0.0;
+            double a = has ? -row[NV + 1] : 1.0, b = a;
+            sfor<0, NV>([&](auto ii) { a += Jr[s][IDX(ii)] * warm[IDX(ii)]; b += Jr[s][IDX(ii)] * as[IDX(ii)]; });
+            jw[s] = a;
+            js[s] = b;
+            if (a < 0) cw += 0.5 * Dr[s] * a * a;
+            if (b < 0) cs += 0.5 * Dr[s] * b * b;
+        });
+        cw = warp_allsum(cw);
+        cs = warp_allsum(cs);
+        sfor<0, NV>([&](auto ii) {
+            constexpr int i = IDX(ii);
+            double s = 0;
+            sfor<0, NV>([&](auto kk) { s += shv[tri(i, IDX(kk))] * warm[IDX(kk)]; });
+            Ma[i] = s;
+            cw += 0.5 * (s - fs[i]) * (warm[i] - as[i]);
+        });
+        if (cw < cs) {
+            sfor<0, NV>([&](auto ii) { qacc[IDX(ii)] = warm[IDX(ii)]; });
+            sfor<0, NS>([&](auto ss) { jar[IDX(ss)] = jw[IDX(ss)]; });
+        } else {
+            sfor<0, NV>([&](auto ii) { qacc[IDX(ii)] = as[IDX(ii)]; });
+            sfor<0, NV>([&](auto ii) {
+                constexpr int i = IDX(ii);
+                double s = 0;
+                sfor<0, NV>([&](auto kk) { s += shv[tri(i, IDX(kk))] * qacc[IDX(kk)]; });
+                Ma[i] = s;
+            });
+            sfor<0, NS>([&](auto ss) { jar[IDX(ss)] = js[IDX(ss)]; });
+        }
+    }
+    double cost = 0, old = 0;
+    int iter = 0;
+    unsigned act[NS];
+    for (;;) {
+        // ---- cost, gradient, Hessian factor and Newton direction: one round of reductions over [fc | cost | row term of H]
+        double red[NV + 1 + NT];
+        sfor<0, NV + 1 + NT>([&](auto xx) { red[IDX(xx)] = 0; });
+        sfor<0, NS>([&](auto ss) {
+            constexpr int s = IDX(ss);
+            const bool on = jar[s] < 0;
+            act[s] = __ballot_sync(FULL, on);
+            if (on) {
+                const double D = Dr[s], f = -D * jar[s];
+                red[NV] += 0.5 * D * jar[s] * jar[s];
+                sfor<0, NV>([&](auto ii) {
+                    constexpr int i = IDX(ii);
+                    red[i] += Jr[s][i] * f;
+                    const double t = D * Jr[s][i];
+                    sfor<0, i + 1>([&](auto kk) { red[NV + 1 + tri(i, IDX(kk))] += t * Jr[s][IDX(kk)]; });
+                });
+            }
+        });
+        bool any = false;
+        sfor<0, NS>([&](auto ss) { any = any || act[IDX(ss)] != 0; });
+        if (any) sfor<0, NV + 1 + NT>([&](auto xx) { red[IDX(xx)] = warp_allsum(red[IDX(xx)]); });
+        {
+            double H[NT], Lh[NT];
+            sfor<0, NT>([&](auto tt) { H[IDX(tt)] = shv[IDX(tt)] + red[NV + 1 + IDX(tt)]; });
+            double c = red[NV];
+            sfor<0, NV>([&](auto ii) {
+                constexpr int i = IDX(ii);
+                c += 0.5 * (Ma[i] - fs[i]) * (qacc[i] - as[i]);
+                grad[i] = Ma[i] - fs[i] - red[i];
+                search[i] = grad[i];
+            });
+            cost = c;
+            chol_packed<NV>(H, Lh);
+            chol_solve_packed<NV>(Lh, search);
+            sfor<0, NV>([&](auto ii) { search[IDX(ii)] = -search[IDX(ii)]; });
+        }
+        if (iter > 0) {
+            double gn = 0;
+            sfor<0, NV>([&](auto ii) { gn += grad[IDX(ii)] * grad[IDX(ii)]; });
+            if (scale * (old - cost) < tol || scale * sqrt(gn) < tol) break;
+        }
+        if (iter >= maxiter) break;
+        // ---- exact linesearch: root of the piecewise-linear derivative along `search`
+        double g1 = 0, g2 = 0;
+        sfor<0, NV>([&](auto ii) {
+            constexpr int i = IDX(ii);
+            double s = 0;
+            sfor<0, NV>([&](auto kk) { s += shv[tri(i, IDX(kk))] * search[IDX(kk)]; });
+            Mv[i] = s;
+        });
+        sfor<0, NV>([&](auto ii) { constexpr int i = IDX(ii); g1 += search[i] * (Ma[i] - fs[i]); g2 += search[i] * Mv[i]; });
+        double p1 = 0, p2 = 0;
+        sfor<0, NS>([&](auto ss) {
+            constexpr int s = IDX(ss);
+            double x = 0;
+            sfor<0, NV>([&](auto ii) { x += Jr[s][IDX(ii)] * search[IDX(ii)]; });
+            jv[s] = x;
+            if (jar[s] < 0) {
+                const double t = Dr[s] * x;
+                p1 += t * jar[s];
+                p2 += t * x;
+            }
+        });
+        double d1 = g1 + warp_allsum(p1), d2 = g2 + warp_allsum(p2);
+        if (d1 >= 0 || d2 < ILQG_MINVAL) break;  // not a descent direction: converged to round-off
+        double alpha = 0, lo = 0, hi = CUDART_INF;
+        unsigned cur[NS], reached[NS];
+        sfor<0, NS>([&](auto ss) { cur[IDX(ss)] = act[IDX(ss)]; reached[IDX(ss)] = act[IDX(ss)]; });
+        for (int it = 0; it < m.ls_iterations; it++) {
+            if (d1 < 0) lo = alpha; else hi = alpha;
+            double an = alpha - d1 / d2;
+            if (!(an > lo && an < hi)) an = isinf(hi) ? 2 * alpha + 1 : 0.5 * (lo + hi);
+            double q1 = 0, q2 = 0;
+            bool same = true;
+            sfor<0, NS>([&](auto ss) {
+                constexpr int s = IDX(ss);
+                const double x = jar[s] + an * jv[s];
+                const bool on = x < 0;
+                if (on) {
+                    const double t = Dr[s] * jv[s];
+                    q1 += t * x;
+                    q2 += t * jv[s];
+                }
+                const unsigned mk = __ballot_sync(FULL, on);
+                same = same && mk == cur[s];
+                cur[s] = mk;
+                reached[s] = mk;
+            });
+            alpha = an;
+            d1 = g1 + g2 * an + warp_allsum(q1);
+            d2 = g2 + warp_allsum(q2);
+            if (same || d1 == 0 || d2 < ILQG_MINVAL) break;  // `same`: the step stayed inside one linear piece, `an` is its root
+        }
+        if (alpha == 0) break;
+        sfor<0, NV>([&](auto ii) { constexpr int i = IDX(ii); qacc[i] += alpha * search[i]; Ma[i] += alpha * Mv[i]; });
+        bool ex = true;   // exact optimum: the line minimiser lies in the piece the Hessian was built for (see solve())
+        sfor<0, NS>([&](auto ss) { ex = ex && reached[IDX(ss)] == act[IDX(ss)]; jar[IDX(ss)] += alpha * jv[IDX(ss)]; });
+        old = cost;
+        iter++;
+        if (ex) { exact = 1; break; }
+    }
+    iters = iter;
+    sfor<0, NS>([&](auto ss) { nact += __popc(__ballot_sync(FULL, jar[IDX(ss)] < 0)); });
+    sfor<0, NV>([&](auto ii) { warm[IDX(ii)] = qacc[IDX(ii)]; });
+}
+
 // ------------------------------------------------------------------ integration (mj_Euler / mj_RungeKutta)
 DEV void quat_integrate(double* quat, V3 vel, double scale) {
     double n = sqrt(dot(vel, vel));

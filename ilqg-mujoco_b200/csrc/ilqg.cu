@@ -48,6 +48,10 @@ DEV void load_knot(int k, const double* qpos, const double* qvel, const double* 
     sfor<0, T::NU>([&](auto ii) { u[IDX(ii)] = ctrl[(size_t)k * T::NU + IDX(ii)]; });
 }
 
+}  // namespace ilqg
+#include "gsolve.cuh"   // (uses cost_eval / load_knot above)
+namespace ilqg {
+
 // ------------------------------------------------------------------ FD: centre
 // Work classes of a batch (large batches only).  The cost of a knot's perturbed evaluations is set by the number of constraint
 // rows its solves walk (0 in flight, 4 per contact point in stance, +1 per joint at its limit), so the centre kernel — which
@@ -277,7 +281,9 @@ struct FdFusedShape {
     static constexpr bool OK = GL <= 32;
 };
 
-template <class T>
+// COOP (a knot per warp, i.e. G + 1 > 16 lanes per knot — the hopper): the centre's solves are done by the whole warp (solve_coop,
+// dyn.cuh) and leave the warm start on every lane.
+template <class T, bool COOP>
 __global__ void __launch_bounds__(256, 1) fd_fused_kernel(const __grid_constant__ DevModel<T> m, int nknots, const double* __restrict__ qpos,
                                                           const double* __restrict__ qvel, const double* __restrict__ ctrl,
                                                           const double* __restrict__ warmstart, const ilqg_cost* __restrict__ cost, double eps,
@@ -285,7 +291,9 @@ __global__ void __launch_bounds__(256, 1) fd_fused_kernel(const __grid_constant_
                                                           int* __restrict__ status, int* __restrict__ diag) {
     using S = FdFusedShape<T>;
     constexpr int NV = T::NV, NU = T::NU, NQ = T::NQ, WARPS = 8, KPW = S::KPW > 0 ? S::KPW : 1;
+    constexpr bool COOPC = COOP && S::KPW == 1 && T::MAXEFC > 0;
     __shared__ double stage[WARPS][KPW * S::ND];
+    __shared__ double csh[COOPC ? WARPS : 1][COOPC ? CoopSolveShape<T>::DOUBLES : 1];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int warp = blockIdx.x * WARPS + wib;
     const int sub = lane / S::GL, l = lane - sub * S::GL;
@@ -298,7 +306,7 @@ __global__ void __launch_bounds__(256, 1) fd_fused_kernel(const __grid_constant_
     double qacc[NV], warm[NV];
     double dcost = 0;
     int it_first = 0, it_all = 0, nefc = 0, nact = 0, ncon = 0;
-    long long t0 = 0, t1 = 0, t2 = 0;
+    long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
     {
         // idle lanes (tail of the grid, spare lanes of a warp) evaluate a clamped knot with their writes masked, so that every
         // thread reaches the stage barriers
@@ -327,9 +335,22 @@ __global__ void __launch_bounds__(256, 1) fd_fused_kernel(const __grid_constant_
         t1 = clock64();
         // phase 0: the centre lanes solve (repetitions stop at the first exact solve, see fd_center_kernel); phase 1: the warm start
         // goes to the knot's other lanes and they solve.  ONE copy of the solver for both (instruction footprint).
+        double cq[NV];   // COOP: the centre's solution (every lane has it; the centre lane's result)
 #pragma unroll 1
-        for (int phase = 0; phase < 2; phase++) {
-            if (phase == 1) {
+        for (int phase = COOPC ? 1 : 0; phase < 2; phase++) {
+            if constexpr (COOPC) {
+                // the warp solves the centre's problem together; afterwards warm = the centre's solution on every lane
+                int ex = 0;
+#pragma unroll 1
+                for (int rep = 0; rep < nwarmup; rep++) {
+                    int it = 0;
+                    solve_coop<T>(m, w, is_center, S::G, csh[wib], warm, cq, niter, 0.0, it, ex, nact);
+                    if (rep == 0) it_first = it;
+                    it_all += it;
+                    if (ex) break;
+                }
+                t2 = clock64();
+            } else if (phase == 1) {
                 t2 = clock64();
                 sfor<0, NV>([&](auto jj) {
                     const double c = __shfl_sync(0xffffffffu, qacc[IDX(jj)], base + S::G);
@@ -347,10 +368,12 @@ __global__ void __launch_bounds__(256, 1) fd_fused_kernel(const __grid_constant_
             }
             __syncwarp();
         }
+        t3 = clock64();
+        if constexpr (COOPC) { if (is_center) sfor<0, NV>([&](auto ii) { qacc[IDX(ii)] = cq[IDX(ii)]; }); }
         if (is_center) {
             nefc = w.nefc;
             ncon = w.ncon;
-            if (diag) for (int r = 0; r < w.nefc; r++) nact += w.rows.jar(r) < 0;
+            if constexpr (!COOPC) { if (diag) for (int r = 0; r < w.nefc; r++) nact += w.rows.jar(r) < 0; }
         }
     }
     if (valid && is_center) {
@@ -360,7 +383,7 @@ __global__ void __launch_bounds__(256, 1) fd_fused_kernel(const __grid_constant_
         if (diag) {
             int4* d = reinterpret_cast<int4*>(diag + (size_t)k * ILQG_DIAG_INTS);
             d[0] = make_int4(nefc, it_first, it_all, nact);
-            d[1] = make_int4((int)(t1 - t0), (int)(t2 - t1), ncon, 0);
+            d[1] = make_int4((int)(t1 - t0), (int)(t2 - t1), ncon, (int)(t3 - t2));
         }
     }
     __syncwarp();   // the centre's status word is written before the columns may flag it
@@ -806,10 +829,16 @@ struct Engine {
     int fd_bins = 1;       // work-class ordering of the knots in the stage-skipping kernels (ILQG_FD_BINS=0 disables)
     int* fd_diag = nullptr;   // [nknots][ILQG_DIAG_INTS] per-knot diagnostics of the next fd() call (device), or NULL
     int fd_pdl = 1;           // single-launch column kernel as the centre kernel's programmatic dependent (ILQG_FD_PDL=0 disables)
+    // one-launch kernel: the centre's solves by the whole warp (solve_coop; ILQG_FD_COOP=1).  Measured on B200 (T = 1000 hopper horizon,
+    // tools/prof_fused_diag.py): the centre's solve tail drops from 91 K to 43 K cycles, the one-launch pass from 84.8 to 72.5 us — and the
+    // centre kernel + programmatic dependent column kernel stays ahead at 64 us; on a single trajectory (few rows) the staging costs
+    // more than the rows' passes (27.0 against 20.9 us).  Off by default.
+    int fd_coop = 0;
     // false: fd() keeps engine-owned scratch indexed by the knot's position in the call, so two fd() calls must not overlap
     // on different streams (the host-pointer pipeline then uses ONE compute stream)
     virtual bool fd_calls_may_overlap() const { return true; }
     virtual void set_fused_max(int) {}
+    virtual void set_group(int /*max knots*/, int /*lanes per perturbed solve*/) {}
     virtual void set_vu_classes(const char*) {}
     virtual void set_q_minb(int) {}
     virtual void set_vu_pos(int) {}
@@ -861,9 +890,26 @@ struct EngineT : Engine {
             if (*e == ',') e++;
         }
     }
+    // build kernel + group-solve kernel (gsolve.cuh): several lanes per solve, for batches <= group_max knots (ILQG_FD_GROUP_MAX, or
+    // ILQG_FD_VARIANT=4; ILQG_FD_GW = lanes per perturbed solve + 100 x resident CTAs per SM the registers are capped for).
+    // Measured on B200 and NOT a gain: off by default (group_max = 0).
+    int group_max = 0, group_gw = 4, group_minb = 2;
+    static constexpr int GROUP_CAP = 8192;   // knots the record buffer is ever sized for (96 KB per hopper knot)
+    double* d_rec = nullptr;
+    size_t rec_knots = 0;
+    void set_group(int n, int gw) override {
+        if (n >= 0) group_max = FdRecord<T>::OK ? (n < GROUP_CAP ? n : GROUP_CAP) : 0;
+        if (gw % 100 == 2 || gw % 100 == 4) group_gw = gw % 100;   // ILQG_FD_GW = lanes + 100 * (resident CTAs per SM the registers are capped for)
+        if (gw >= 100) group_minb = gw / 100;
+    }
+    ~EngineT() override { if (d_rec) cudaFree(d_rec); }
     int variant_for(int nknots) const {
-        if (fd_variant >= 0) return (fd_variant == 1 && !FdFusedShape<T>::OK) ? 2 : fd_variant;
-        return nknots >= SPLIT_MIN ? 3 : (nknots <= fused_max ? 1 : 2);
+        if (fd_variant >= 0) {
+            if (fd_variant == 1 && !FdFusedShape<T>::OK) return 2;
+            if (fd_variant == 4 && (!FdRecord<T>::OK || nknots > GROUP_CAP)) return 2;
+            return fd_variant;
+        }
+        return nknots >= SPLIT_MIN ? 3 : (nknots <= fused_max ? 1 : (nknots <= group_max ? 4 : 2));
     }
     size_t fd_scratch_ints(int nknots, int batch) const override {
         constexpr int NTF = T::NV * (T::NV + 1) / 2;   // + the centre's Newton factor and active set per knot (FdBins::fac)
@@ -975,8 +1021,52 @@ struct EngineT : Engine {
                 using F = FdFusedShape<T>;
                 const int nw = (nknots + F::KPW - 1) / F::KPW;
                 if (ev) { cudaEventRecord(ev[1], s); cudaEventRecord(ev[3], s); }
-                fd_fused_kernel<T><<<(nw + 7) / 8, 256, 0, s>>>(dm, nknots, qpos, qvel, ctrl, warm, cost_dev, o.eps, o.niter, o.nwarmup, dst, qacc_center,
-                                                                status, fd_diag);
+                if (fd_coop)
+                    fd_fused_kernel<T, true><<<(nw + 7) / 8, 256, 0, s>>>(dm, nknots, qpos, qvel, ctrl, warm, cost_dev, o.eps, o.niter, o.nwarmup, dst,
+                                                                          qacc_center, status, fd_diag);
+                else
+                    fd_fused_kernel<T, false><<<(nw + 7) / 8, 256, 0, s>>>(dm, nknots, qpos, qvel, ctrl, warm, cost_dev, o.eps, o.niter, o.nwarmup, dst,
+                                                                           qacc_center, status, fd_diag);
+                if (ev) cudaEventRecord(ev[2], s);
+                return cudaGetLastError();
+            }
+        }
+        if constexpr (FdRecord<T>::OK) {
+            if (variant == 4) {   // latency-bound batch: build + group solve
+                using R = FdRecord<T>;
+                if (rec_knots < (size_t)nknots) {
+                    if (d_rec) { cudaDeviceSynchronize(); cudaFree(d_rec); d_rec = nullptr; rec_knots = 0; }
+                    size_t want = 1024;
+                    while (want < (size_t)nknots) want *= 2;
+                    cudaError_t ae = cudaMalloc(&d_rec, want * R::DOUBLES * sizeof(double));
+                    if (ae != cudaSuccess) return ae;
+                    rec_knots = want;
+                }
+                last_launches = 2;
+                fd_build_kernel<T><<<(nknots + 7) / 8, 256, 0, s>>>(dm, nknots, qpos, qvel, ctrl, cost_dev, o.eps, d_rec);
+                if (ev) { cudaEventRecord(ev[1], s); cudaEventRecord(ev[3], s); }
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(nknots);
+                cfg.stream = s;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                at[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = at;
+                cfg.numAttrs = (ev || !fd_pdl) ? 0 : 1;
+                const double* rc = d_rec;
+                const int has_cost = cost_dev != nullptr;
+                cudaError_t le = cudaErrorInvalidValue;
+                auto go = [&](auto gw, auto mb) {
+                    constexpr int GWc = decltype(gw)::value, MB = decltype(mb)::value;
+                    cfg.blockDim = dim3(32 * FdSolveShape<T, GWc>::NW);
+                    le = cudaLaunchKernelEx(&cfg, fd_solve_kernel<T, GWc, MB>, dm, nknots, rc, warm, has_cost, o.eps, o.niter, o.nwarmup, dst, qacc_center,
+                                            status, fd_diag);
+                };
+                using I2 = std::integral_constant<int, 2>; using I4 = std::integral_constant<int, 4>; using I6 = std::integral_constant<int, 6>;
+                using I8 = std::integral_constant<int, 8>; using I12 = std::integral_constant<int, 12>;
+                if (group_gw == 2) { if (group_minb <= 4) go(I2{}, I4{}); else if (group_minb <= 8) go(I2{}, I8{}); else go(I2{}, I12{}); }
+                else { if (group_minb <= 2) go(I4{}, I2{}); else if (group_minb <= 4) go(I4{}, I4{}); else go(I4{}, I6{}); }
+                if (le != cudaSuccess) return le;
                 if (ev) cudaEventRecord(ev[2], s);
                 return cudaGetLastError();
             }
@@ -1328,6 +1418,11 @@ int ilqg_create(const ilqg_model* m, int device, ilqg_handle* out) {
     if (const char* e = getenv("ILQG_FD_VARIANT")) eng->fd_variant = atoi(e);
     if (const char* e = getenv("ILQG_FD_BINS")) eng->fd_bins = atoi(e);
     if (const char* e = getenv("ILQG_FD_PDL")) eng->fd_pdl = atoi(e);
+    if (const char* e = getenv("ILQG_FD_COOP")) eng->fd_coop = atoi(e);
+    {
+        const char *gm = getenv("ILQG_FD_GROUP_MAX"), *gw = getenv("ILQG_FD_GW");
+        if (gm || gw) eng->set_group(gm ? atoi(gm) : -1, gw ? atoi(gw) : 0);
+    }
     if (const char* e = getenv("ILQG_FD_FUSED_MAX")) eng->set_fused_max(atoi(e));
     if (const char* e = getenv("ILQG_VU_CLASSES")) eng->set_vu_classes(e);
     if (const char* e = getenv("ILQG_Q_MINB")) eng->set_q_minb(atoi(e));

@@ -128,7 +128,8 @@ enum {
     ILQG_DIAG_NACTIVE = 3,     /* rows active (force > 0) at the centre solution */
     ILQG_DIAG_CYC_BUILD = 4,   /* SM cycles the rollout spent in the position / velocity / actuation stages */
     ILQG_DIAG_CYC_SOLVE = 5,   /* SM cycles it spent in the nwarmup solves */
-    ILQG_DIAG_NCON = 6         /* contact points at the centre point (nefc also counts joints at their limits) */
+    ILQG_DIAG_NCON = 6,        /* contact points at the centre point (nefc also counts joints at their limits) */
+    ILQG_DIAG_CYC_COLUMNS = 7  /* one-launch kernel only: SM cycles until the knot's slowest perturbed solve was done (else 0) */
 };
 int ilqg_fd_set_diag(ilqg_handle h, int* diag_dev);
 

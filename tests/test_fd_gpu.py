@@ -175,20 +175,28 @@ def test_full_size_properties(handles, pkg):
     assert float(err.median()) < 1e-6 and float((err < 1e-4).double().mean()) > 0.9
 
 
-@pytest.mark.parametrize("variant", ["2", "3"])
+@pytest.mark.parametrize("variant", ["1", "1:warp solves the centre", "2", "3", "4:4 lanes per solve", "4:2 lanes per solve"])
 @pytest.mark.parametrize("name,n,roll", [("inverted_pendulum", 300, 10), ("hopper", 271, 150), ("hopper", 85, 0), ("hopper", 1, 200)])
 def test_both_fd_kernel_variants(pkg, oracle, omodels, variant, name, n, roll):
-    """The per-call choice between the single-launch kernel (variant 2: one thread per perturbed evaluation) and the
-    stage-skipping split (variant 3: fd_velctrl_kernel + fd_qpos_kernel) depends on the batch size; both must meet the
-    same tolerance on the same inputs, including ragged tails (n not a multiple of the knots a CTA owns: 85 / 21 hopper)."""
+    """The per-call choice between the one-launch kernel (variant 1: centre evaluation on a spare lane of its knot's warp, its solves
+    done by that lane alone or, ILQG_FD_COOP=1, by the whole warp — solve_coop), the column kernel behind the centre kernel (variant
+    2: one thread per perturbed evaluation) and the stage-skipping split (variant 3: fd_velctrl_kernel + fd_qpos_kernel) depends on
+    the batch size; the round-2 experiment with several lanes per solve (variant 4: fd_build_kernel + fd_solve_kernel, gsolve.cuh) is
+    off by default.  All must meet the same tolerance on the same inputs, including ragged tails (n not a multiple of the knots a
+    CTA owns: 85 / 21 hopper); the pendulum has no variant 4 and falls back to 2."""
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
-    os.environ["ILQG_FD_VARIANT"] = variant
+    os.environ["ILQG_FD_VARIANT"] = variant[0]
+    if variant.startswith("1:"):
+        os.environ["ILQG_FD_COOP"] = "1"
+    if variant.startswith("4:"):
+        os.environ["ILQG_FD_GW"] = "204" if "4 lanes" in variant else "802"
     try:
         h = pkg.Handle(pkg.Model.named(name), 0)
     finally:
-        del os.environ["ILQG_FD_VARIANT"]
+        for k in ("ILQG_FD_VARIANT", "ILQG_FD_COOP", "ILQG_FD_GW"):
+            os.environ.pop(k, None)
     m = h.model; om = omodels[name]
     q, v, u, w = scenario_states(name, n, seed=900 + roll, oracle=oracle, om=om, roll=roll)
     cost = oracle.make_cost(q2=[1, 10], v2=[1, 10], u2=[1], q1=[0.5])

@@ -124,7 +124,7 @@ def test_host_pipeline_ragged_sizes(full, n):
     assert np.array_equal(d, f["deriv"][sl].cpu().numpy())     # and of the full batch's slice
 
 
-@pytest.mark.parametrize("env", [dict(ILQG_FD_VARIANT="1"), dict(ILQG_FD_VARIANT="2", ILQG_FD_PDL="0"), dict(ILQG_FD_VARIANT="2"),
+@pytest.mark.parametrize("env", [dict(ILQG_FD_VARIANT="1"), dict(ILQG_FD_VARIANT="1", ILQG_FD_COOP="1"), dict(ILQG_FD_VARIANT="2", ILQG_FD_PDL="0"), dict(ILQG_FD_VARIANT="2"),
                                  dict(ILQG_FD_VARIANT="3", ILQG_VU_CLASSES="8,16"), dict(ILQG_FD_VARIANT="3", ILQG_VU_POS="1"),
                                  dict(ILQG_FD_VARIANT="3", ILQG_VU_POS="2"), dict(ILQG_FD_VARIANT="3", ILQG_Q_MINB="1")])
 def test_every_kernel_variant_gives_the_same_jacobians(full, pkg, env):

@@ -99,10 +99,18 @@ for lab, sel in (("flight", d[:, 0] == 0), ("stance", d[:, 0] > 0)):
 print("  (cycles at ~1.9 GHz: 1000 cycles = 0.52 us)")
 
 print("-- knot-count sweep (prefix of the horizon, tiled when longer): call us / M knots/s per kernel variant")
-variants = (("auto", {}), ("fused 1-launch", dict(ILQG_FD_VARIANT=1)), ("centre+columns PDL", dict(ILQG_FD_VARIANT=2)),
+variants = (("centre+columns PDL", dict(ILQG_FD_VARIANT=2)), ("auto", {}),
+            ("build+group solve 4 lanes/128r", dict(ILQG_FD_VARIANT=4, ILQG_FD_GW=404)), ("4 lanes/255r", dict(ILQG_FD_VARIANT=4, ILQG_FD_GW=204)),
+            ("4 lanes/80r", dict(ILQG_FD_VARIANT=4, ILQG_FD_GW=604)), ("2 lanes/255r", dict(ILQG_FD_VARIANT=4, ILQG_FD_GW=402)),
+            ("2 lanes/128r", dict(ILQG_FD_VARIANT=4, ILQG_FD_GW=802)), ("2 lanes/80r", dict(ILQG_FD_VARIANT=4, ILQG_FD_GW=1202)),
+            ("1-launch, warp solves centre", dict(ILQG_FD_VARIANT=1, ILQG_FD_COOP=1)), ("1-launch, centre lane alone", dict(ILQG_FD_VARIANT=1)),
             ("centre+columns no PDL", dict(ILQG_FD_VARIANT=2, ILQG_FD_PDL=0)), ("split", dict(ILQG_FD_VARIANT=3)))
+if os.environ.get("PROF_VARIANTS"):
+    keep = [int(x) for x in os.environ["PROF_VARIANTS"].split(",")]
+    variants = tuple(variants[i] for i in keep)
 hs = [(lab, handle(**env)) for lab, env in variants]
-print("  n      " + "".join(f"{lab:>28s}" for lab, _ in hs))
+print("  (third figure: max |difference| to the first variant's deriv blocks / max |block|)")
+print("  n      " + "".join(f"{lab:>30s}" for lab, _ in hs))
 for n in (21, 32, 125, 250, 500, 1000, 2000, 3000, 4000, 6000, 8000, 16000, 24000):
     reps = (n + T - 1) // T
     qq, vv, uu, ww = (x.repeat(reps, 1)[:n].contiguous() for x in (q, v, u, w))
@@ -113,7 +121,7 @@ for n in (21, 32, 125, 250, 500, 1000, 2000, 3000, 4000, 6000, 8000, 16000, 2400
         if ref is None:
             ref = dd
         err = float((dd[:, :90] - ref[:, :90]).abs().max() / ref[:, :90].abs().max())
-        row += f"{wall_us:9.1f} us {n / wall_us:6.2f} M {err:7.0e}"
+        row += f"{wall_us:11.1f} us {n / wall_us:6.2f} M {err:7.0e}"
     print(row)
 for _, hh in hs:
     hh.close()

@@ -9,13 +9,14 @@ pkg = e.load_package()
 from ilqg_mujoco_b200 import workload as wl
 rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 h0 = pkg.Handle(pkg.Model.named("hopper"), 0)
-q, v, u, w, _ = wl.make_knots_8d(h0, 2048, 21, seed=3, device="cuda:0")
+q, v, u, w, _ = wl.make_knots_8d(h0, 384, 21, seed=3, device="cuda:0")   # 8064 knots: inside the cap of the group-solve experiment
 n = q.shape[0]
 cost = pkg.make_cost(q1=[1.0])
 ref = torch.zeros((n, 105), dtype=torch.float64, device="cuda:0")
 h0.fd_batch_dev(q, v, u, w, ref, cost=cost)
 torch.cuda.synchronize()
-envs = [{}, dict(ILQG_FD_VARIANT="1"), dict(ILQG_FD_VARIANT="2"), dict(ILQG_FD_VARIANT="2", ILQG_FD_PDL="0"), dict(ILQG_FD_VARIANT="3"),
+envs = [{}, dict(ILQG_FD_VARIANT="1"), dict(ILQG_FD_VARIANT="1", ILQG_FD_COOP="1"), dict(ILQG_FD_VARIANT="4", ILQG_FD_GW="204"),
+        dict(ILQG_FD_VARIANT="4", ILQG_FD_GW="802"), dict(ILQG_FD_VARIANT="2"), dict(ILQG_FD_VARIANT="2", ILQG_FD_PDL="0"), dict(ILQG_FD_VARIANT="3"),
         dict(ILQG_FD_VARIANT="3", ILQG_FD_BINS="0"), dict(ILQG_FD_VARIANT="3", ILQG_VU_CLASSES="8,16"), dict(ILQG_FD_VARIANT="3", ILQG_VU_CLASSES="4"),
         dict(ILQG_FD_VARIANT="3", ILQG_VU_POS="1"), dict(ILQG_FD_VARIANT="3", ILQG_VU_POS="2"), dict(ILQG_FD_VARIANT="3", ILQG_Q_MINB="1")]
 bad = 0

@@ -298,14 +298,14 @@ class Ilqr:
     def iterations(self):
         return int(lib().ilqg_ilqr_iterations_done(self._w))
 
-    def fetch_controls(self):
+    def fetch_controls(self, last=None):
         """First control of every problem (dArray[N]->ctrl, what InvertedPendulum::forward applies) and the cost trace of the
-        iterations run so far: (u0[ninst, nu], J[ninst, kept]).  Synchronises."""
+        iterations run so far (`last`: only of the last that many): (u0[ninst, nu], J[ninst, kept]).  Synchronises."""
         m = self.h.model
-        kept = min(self.iterations, 256)
+        kept = min(self.iterations, 256) if last is None else min(self.iterations, 256, int(last))
         u0 = np.zeros((self.ninst, m.nu))
         J = np.zeros((self.ninst, kept))
-        self.h._check(lib().ilqg_ilqr_get_first_control_host(self._w, _hp(u0), _hp(J)))
+        self.h._check(lib().ilqg_ilqr_get_first_control_last_host(self._w, kept if last is not None else 256, _hp(u0), _hp(J)))
         return u0, J
 
     def get(self):

@@ -487,6 +487,10 @@ __global__ void __launch_bounds__(32) ilqr_backward_small_kernel(IlqrBuffers b, 
 #undef CMX
 }
 
+// (Round 2 also measured FOUR LANES per instance on this sweep — lane c owning column c of V / K, row c of the products with V, register
+//  transposes and all-gathers by shuffle, every output element still one lane's sum in the same order: bit-identical results, a
+//  quarter of the multiply-adds per lane, and SLOWER: 4096 pendulum problems 0.215 -> 0.248 ms per batch iteration.  The 32 shuffles
+//  and the select chains per knot lengthen the dependent chain by more than the shorter sums save.  Not kept.)
 template <int NV, int NU, int LANES, int GROUPS>
 __global__ void __launch_bounds__(LANES * GROUPS) ilqr_backward_kernel(IlqrBuffers b, double dt) {
     constexpr int NX = 2 * NV, ND = NV * (2 * NV + NU) + 2 * NV + NU, NQ = NV;

@@ -211,6 +211,9 @@ int ilqg_ilqr_iterations_done(ilqg_ilqr w);
 /* the first control of every problem, u0[ninst][nu] (dArray[N]->ctrl: what /root/reference/src/inverted_pendulum/inverted_pendulum.cpp:26
  * applies to the plant), and optionally the cost trace [ninst][min(iterations,256)]; host pointers, synchronises */
 int ilqg_ilqr_get_first_control_host(ilqg_ilqr w, double* u0, double* Jtrace);
+/* the same with the cost trace cut to the last min(nlast, iterations, 256) iterations, Jtrace[ninst][that many] — what one MPC step of
+ * `nlast` iterations on a long-lived workspace reads back (the reference's InvertedPendulum::forward keeps no trace at all) */
+int ilqg_ilqr_get_first_control_last_host(ilqg_ilqr w, int nlast, double* u0, double* Jtrace);
 /* results, instance-major on the host; any pointer may be NULL.  Jtrace/accepted: [ninst][min(iterations,256)] */
 int ilqg_ilqr_get_host(ilqg_ilqr w, double* qpos, double* qvel, double* ctrl, double* K, double* k, double* V, double* v,
                        double* Jtrace, int* accepted);

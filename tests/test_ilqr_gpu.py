@@ -216,3 +216,46 @@ def test_humanoid_ilqr_in_tangent_coordinates_matches_oracle(pkg, oracle, omodel
     assert rel(out["J"][:, -4:], ref["J"]) < 1e-6
     assert (ref["accepted"] >= 0).any() and (np.diff(ref["J"], axis=1) <= 1e-12).all()   # the ladder accepts steps and the cost falls
     assert np.allclose(np.linalg.norm(out["qpos"][:, :, 3:7], axis=2), 1.0, atol=1e-9)
+
+
+@pytest.mark.parametrize("name,n,nsub", [("inverted_pendulum", 100, 3), ("inverted_pendulum", 33, 2), ("hopper", 70, 2)])
+def test_sub_batched_workspace_gives_the_same_bits(pkg, handles, oracle, omodels, name, n, nsub, monkeypatch):
+    """ilqg_ilqr_iterate runs the iteration chains of blocks of instances on separate streams (ilqg_ilqr_s: sub-batches; by default
+    four blocks from 1024 instances on).  Blocks change where an instance's data lives and when its kernels run, not its arithmetic:
+    every result — trajectories, gains, value model, cost trace, accepted alphas, first controls, the knots' warm starts — equals the
+    single-block workspace bit for bit, through the captured graph as well as launch by launch, with ragged blocks (boundaries at
+    multiples of 32 instances), the line-search ladder and the per-instance mu schedule."""
+    h = handles[name]
+    q, v, u, w = scenario_states(name, n, seed=77, oracle=oracle, om=omodels[name], roll=140 if name == "hopper" else 0)
+    u = u * 0.2
+    m = h.model
+    cost = oracle.make_cost(**PEND_COST) if name == "inverted_pendulum" else oracle.make_cost(q2=[0, 5, 1, 0.1, 0.1, 0.1], v2=[0.1] * 6, u2=[0.01] * 3)
+    alphas = [1.0, 0.5, 0.25, 0.125]
+    res = []
+    for sub in (1, nsub):
+        monkeypatch.setenv("ILQG_ILQR_SUB", str(sub))
+        il = pkg.Ilqr(h, n, 12, alphas)
+        monkeypatch.delenv("ILQG_ILQR_SUB")
+        il.set_cost(cost)
+        if name == "hopper":
+            il.set_layout(1)
+        il.set_mu(10.0)
+        il.set_mu_schedule(2.0)
+        il.init_host(q, v, u, w)
+        for _ in range(4):                 # plain launches, graph capture, two replays
+            il.iterate(2, accept_always=False)
+        out = il.get()
+        out["u0"], out["Jt"] = il.fetch_controls()
+        kq = np.zeros((n, 13, m.nq)); kv = np.zeros((n, 13, m.nv)); ku = np.zeros((n, 13, m.nu)); kw = np.zeros((n, 13, m.nv))
+        from ctypes import c_void_p
+        h._check(pkg.lib().ilqg_ilqr_get_knots_host(il._w, kq.ctypes.data_as(c_void_p), kv.ctypes.data_as(c_void_p), ku.ctypes.data_as(c_void_p),
+                                                   kw.ctypes.data_as(c_void_p)))
+        out.update(kq=kq, kv=kv, ku=ku, kw=kw)
+        il.set_state_host(q * 0.9, v)       # a later MPC step on the same workspace
+        il.iterate(2, accept_always=False)
+        out["u0b"], out["Jtb"] = il.fetch_controls()
+        il.close()
+        res.append(out)
+    for key in res[0]:
+        assert np.array_equal(res[0][key], res[1][key]), key
+    assert np.array_equal(res[0]["kq"], res[0]["qpos"]) and len(np.unique(res[0]["accepted"])) > 1

@@ -571,9 +571,20 @@ def bench_mpc_step(pkg):
                                       None, None, None, None, None, None, None)
         return (time.perf_counter() - t0) if rc == 0 else float("nan"), tr
     gpu(2)                              # warm-up (library and kernel load)
-    t_a, _ = gpu(2)
-    t_b, tr_gpu = gpu(22)               # the difference leaves out model load, handle creation and the constructor's rollout
+    t_a, _ = gpu(3)                     # (3 steps: plain launches, graph capture, first replay of ILQR::iterate(int))
+    t_b, tr_gpu = gpu(23)               # the difference leaves out model load, handle creation, the constructor's rollout and the capture
     out["value"] = 1e3 * (t_b - t_a) / 20
+    out["how"] = ("InvertedPendulum::forward through the host-language mirror: the ten iterations as ONE device call (ILQR::iterate(int), the class's "
+                  "quadratic step cost evaluated on the device, CUDA graph), public members synchronised once per step")
+    os.environ["ILQG_MIRROR_HOST_COST"] = "1"
+    try:
+        gpu(2)
+        t_c, _ = gpu(2)
+        t_d, tr_host = gpu(12)
+    finally:
+        del os.environ["ILQG_MIRROR_HOST_COST"]
+    out["value_reference_cadence"] = 1e3 * (t_d - t_c) / 10   # iterate() one at a time, cost rows from the host function (4 round trips per iteration)
+    out["cadences_agree_bitwise"] = bool(np.array_equal(tr_host, tr_gpu[:12]))
 
     def ref(nmpc):                      # one reference ILQR instance per process (function-local statics, ilqr.h:137-140)
         r = subprocess.run([sys.executable, "-c", _REF_MPC_SCRIPT % dict(root=ROOT, nmpc=nmpc)], capture_output=True, text=True, timeout=600)

@@ -241,10 +241,19 @@ InvertedPendulum::InvertedPendulum(mjModel* m, mjData* d) : m(m), d(d) {
     stepCostFn = stepCost;
     for (auto i = 0; i < 10; i++) mj_step(m, d);
     iLQR = new ILQR<nv, nu, N>(m, d, stepCostFn);
+    // the class's own step cost (cost.h) is a quadratic form: the ten iterations of forward() run as one device call
+    // (ILQR::iterate(int)); ILQG_MIRROR_HOST_COST=1 keeps the reference's cadence, one iterate() with the host function at a time
+    if (!getenv("ILQG_MIRROR_HOST_COST")) {
+        ilqg_cost c;
+        memset(&c, 0, sizeof c);
+        c.q2[0] = 1.0; c.q2[1] = 10.0; c.v2[0] = 1.0; c.v2[1] = 10.0; c.u2[0] = 1.0;   // cost.h:7-17
+        iLQR->setDeviceCost(c);
+    }
 }
 void InvertedPendulum::forward() {
     iLQR->setDInit(d);
-    for (int i = 0; i < maxIterUtilConvergence; i++) iLQR->iterate();
+    if (iLQR->hasDeviceCost() && stepCostFn == stepCost) iLQR->iterate(maxIterUtilConvergence);   // (a caller that swapped stepCostFn gets its function)
+    else for (int i = 0; i < maxIterUtilConvergence; i++) iLQR->iterate();
     mju_copy(d->ctrl, iLQR->dArray[N]->ctrl, nu);  // get first u
     mj_step(m, d);                                 // proceed simulation
 }

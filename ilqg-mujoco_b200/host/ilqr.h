@@ -65,12 +65,7 @@ public:
         for (int n = 0; n <= N; n++) calcCostGradientRows(m, dArray[n], differentiator->stepCostFn, rows.data() + (size_t)n * NR);
         check(ilqg_ilqr_put_cost_rows_host(ws, rows.data()), "ilqg_ilqr_put_cost_rows_host");
         check(ilqg_ilqr_backward(ws, NULL), "ilqg_ilqr_backward");
-        std::vector<mjtNum> Kb((size_t)(N + 1) * nu * 2 * nv), kb((size_t)(N + 1) * nu);
-        check(ilqg_ilqr_get_host(ws, NULL, NULL, NULL, Kb.data(), kb.data(), V->data(), v->data(), NULL, NULL), "ilqg_ilqr_get_host");
-        for (int n = 0; n <= N; n++) {
-            for (int e = 0; e < nu * 2 * nv; e++) K[n].data()[e] = Kb[(size_t)n * nu * 2 * nv + e];
-            for (int e = 0; e < nu; e++) k[n].data()[e] = kb[(size_t)n * nu + e];
-        }
+        fetchGains();
     }
 
     void iterate() {
@@ -79,8 +74,41 @@ public:
         backwardPass();
     }
 
+    // Not in the reference: `niter` iterations in ONE device call.  iterate() above keeps every public member current after every
+    // phase, as the reference's class does — four synchronous host round trips per iteration, because the caller's stepCostFn is a
+    // host function.  A caller whose step cost is a quadratic form can hand it over as an ilqg_cost (setDeviceCost): the forward
+    // differences of the cost are then taken on the device with the same arithmetic (bit-exact rows, tests/test_fd_gpu.py), the
+    // niter x (forwardPass; setDInit(dArray[N]); backwardPass) chain replays as one CUDA graph, and the public members (dArray, d,
+    // K, k, V, v) are brought up to date once, at the end — the state iterate() x niter would leave.
+    void setDeviceCost(const ilqg_cost& c) {
+        check(ilqg_ilqr_set_cost(ws, &c), "ilqg_ilqr_set_cost");
+        deviceCost = true;
+    }
+    bool hasDeviceCost() const { return deviceCost; }
+    void iterate(int niter) {
+        if (!deviceCost) {
+            for (int i = 0; i < niter; i++) iterate();
+            return;
+        }
+        check(ilqg_ilqr_set_state_host(ws, d->qpos, d->qvel, d->qacc_warmstart), "ilqg_ilqr_set_state_host");
+        ilqg_ilqr_set_mu(ws, mu);
+        check(ilqg_ilqr_iterate(ws, niter, 1, NULL), "ilqg_ilqr_iterate");
+        fetchKnots();
+        setDInit(dArray[N]);
+        fetchGains();
+    }
+
 private:
     ilqg_ilqr ws = NULL;
+    bool deviceCost = false;
+    void fetchGains() {
+        std::vector<mjtNum> Kb((size_t)(N + 1) * nu * 2 * nv), kb((size_t)(N + 1) * nu);
+        check(ilqg_ilqr_get_host(ws, NULL, NULL, NULL, Kb.data(), kb.data(), V->data(), v->data(), NULL, NULL), "ilqg_ilqr_get_host");
+        for (int n = 0; n <= N; n++) {
+            for (int e = 0; e < nu * 2 * nv; e++) K[n].data()[e] = Kb[(size_t)n * nu * 2 * nv + e];
+            for (int e = 0; e < nu; e++) k[n].data()[e] = kb[(size_t)n * nu + e];
+        }
+    }
     void check(int rc, const char* what) {
         if (rc) {
             char buf[512];

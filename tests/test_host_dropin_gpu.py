@@ -50,6 +50,28 @@ def test_pendulum_mpc_matches_oracle(hostlib, oracle, omodels, q0, v0, nmpc):
         assert np.abs(x - y).max() <= 1e-5 * np.abs(y).max(), key
 
 
+def test_pendulum_mpc_one_device_call_per_step_equals_the_reference_cadence(hostlib, oracle, monkeypatch):
+    """InvertedPendulum::forward runs its ten iterations as ONE device call (ILQR::iterate(int): the class's own quadratic step cost
+    handed over as an ilqg_cost, the chain replayed as a CUDA graph, public members synchronised once); ILQG_MIRROR_HOST_COST=1 keeps the
+    reference's cadence — one iterate() at a time, cost rows from the host function, every member current after every phase.  Same
+    arithmetic either way: closed-loop trace, nominal, gains and value model agree bit for bit."""
+    N, nmpc = 20, 4
+    q0 = np.array([0.1, 0.2]); v0 = np.array([0.0, 0.1])
+    path = os.path.join(PKG, "models", "inverted_pendulum.ilqgm").encode()
+    res = []
+    for host_cost in (False, True):
+        if host_cost:
+            monkeypatch.setenv("ILQG_MIRROR_HOST_COST", "1")
+        a = dict(tr=np.zeros((nmpc, 5)), q=np.zeros((N + 1, 2)), v=np.zeros((N + 1, 2)), u=np.zeros((N + 1, 1)), K=np.zeros((N + 1, 4)),
+                 k=np.zeros((N + 1, 1)), V=np.zeros(16), vv=np.zeros(4))
+        assert hostlib.ilqg_host_pendulum_mpc(path, oracle._p(q0), oracle._p(v0), nmpc, *[oracle._p(a[x]) for x in ("tr", "q", "v", "u", "K", "k", "V", "vv")]) == 0
+        res.append(a)
+    monkeypatch.delenv("ILQG_MIRROR_HOST_COST")
+    for key in res[0]:
+        assert np.array_equal(res[0][key], res[1][key]), key
+    assert np.isfinite(res[0]["tr"]).all() and np.abs(res[0]["K"]).max() > 0
+
+
 def test_hopper_differentiator_scenario(hostlib, oracle, omodels):
     om = omodels["hopper"]
     A = np.zeros((12, 12), order="F"); B = np.zeros((12, 3), order="F"); deriv = np.zeros(105); res = np.zeros(12)

@@ -791,19 +791,26 @@ __global__ void __launch_bounds__(128) step_kernel(const __grid_constant__ DevMo
 
 template <class T, bool OK = (T::NQ == T::NV)>
 struct IlqrLaunch {
-    static cudaError_t rollout(const DevModel<T>&, const IlqrBuffers&, const ilqg_cost*, cudaStream_t) { return cudaErrorNotSupported; }
+    static cudaError_t rollout(const DevModel<T>&, const IlqrBuffers&, const ilqg_cost*, cudaStream_t, bool = false, double* = nullptr, int* = nullptr) {
+        return cudaErrorNotSupported;
+    }
     static cudaError_t accept(const IlqrBuffers&, int, double*, int*, cudaStream_t) { return cudaErrorNotSupported; }
     static cudaError_t backward(const IlqrBuffers&, double, cudaStream_t) { return cudaErrorNotSupported; }
 };
 template <class T>
 struct IlqrLaunch<T, true> {
-    static cudaError_t rollout(const DevModel<T>& dm, const IlqrBuffers& b, const ilqg_cost* cost, cudaStream_t s) {
+    static bool Jtrace_direct_ok(const IlqrBuffers& b, bool direct) { return direct && b.nalpha == 1; }
+    static cudaError_t rollout(const DevModel<T>& dm, const IlqrBuffers& b, const ilqg_cost* cost, cudaStream_t s, bool direct = false,
+                               double* Jtrace = nullptr, int* acc_trace = nullptr) {
         int n = b.ninst * b.nalpha;
         // A rollout is one long dependent chain per thread (T steps x integrator stages), latency-bound.  One warp per CTA, so that the
         // warps of a small batch spread over the SMs instead of sharing one SM's L1 four at a time: 1024 hopper problems x 6 alphas
         // (192 warps, rows in local memory) 0.953 -> 0.899 ms per batch iteration; the pendulum (no rows worth mentioning) is indifferent,
         // 0.2160 / 0.2166 ms.  Fewer rollouts per warp (16 / 8 lanes) were measured too: pendulum +1 %, hopper -1 % / -9 %.
-        ilqr_rollout_kernel<T><<<(n + 31) / 32, 32, 0, s>>>(dm, b, cost);
+        if (Jtrace_direct_ok(b, direct))
+            ilqr_rollout_kernel<T, true><<<(n + 31) / 32, 32, 0, s>>>(dm, b, cost, Jtrace, acc_trace);
+        else
+            ilqr_rollout_kernel<T><<<(n + 31) / 32, 32, 0, s>>>(dm, b, cost);
         return cudaGetLastError();
     }
     static cudaError_t accept(const IlqrBuffers& b, int accept_always, double* Jtrace, int* acc_trace, cudaStream_t s) {
@@ -831,6 +838,7 @@ struct Engine {
     int fd_bins = 1;       // work-class ordering of the knots in the stage-skipping kernels (ILQG_FD_BINS=0 disables)
     int* fd_diag = nullptr;   // [nknots][ILQG_DIAG_INTS] per-knot diagnostics of the next fd() call (device), or NULL
     int fd_pdl = 1;           // single-launch column kernel as the centre kernel's programmatic dependent (ILQG_FD_PDL=0 disables)
+    int ilqr_direct = 1;      // one-launch forward pass in the reference's mode (ILQG_ILQR_DIRECT=0: rollout + accept + commit kernels)
     // one-launch kernel: the centre's solves by the whole warp (solve_coop; ILQG_FD_COOP=1).  Measured on B200 (T = 1000 hopper horizon,
     // tools/prof_fused_diag.py): the centre's solve tail drops from 91 K to 43 K cycles, the one-launch pass from 84.8 to 72.5 us — and the
     // centre kernel + programmatic dependent column kernel stays ahead at 64 us; on a single trajectory (few rows) the staging costs
@@ -864,6 +872,9 @@ struct Engine {
     // batched iLQR (ilqr.cuh); false when the model's state is not (qpos, qvel) with nq == nv (quirk Q9)
     virtual bool ilqr_supported() const = 0;
     virtual cudaError_t ilqr_rollout(const IlqrBuffers& b, const ilqg_cost* cost_dev, cudaStream_t s) = 0;
+    // forward pass of the reference's own mode (one alpha, accepted unconditionally) in ONE launch: rollout straight over the nominal
+    // plus the acceptance bookkeeping (ilqr_rollout_kernel<T, true>).  false: not available, use ilqr_rollout + ilqr_accept
+    virtual bool ilqr_rollout_direct(const IlqrBuffers&, const ilqg_cost*, double*, int*, cudaStream_t, cudaError_t*) { return false; }
     virtual cudaError_t ilqr_accept(const IlqrBuffers& b, int accept_always, double* Jtrace, int* acc_trace, cudaStream_t s) = 0;
     virtual cudaError_t ilqr_backward(const IlqrBuffers& b, cudaStream_t s) = 0;
 };
@@ -1140,6 +1151,11 @@ struct EngineT : Engine {
     bool ilqr_supported() const override { return T::NQ == T::NV; }
     cudaError_t ilqr_rollout(const IlqrBuffers& b, const ilqg_cost* cost_dev, cudaStream_t s) override {
         return IlqrLaunch<T>::rollout(dm, b, cost_dev, s);
+    }
+    bool ilqr_rollout_direct(const IlqrBuffers& b, const ilqg_cost* cost_dev, double* Jtrace, int* acc_trace, cudaStream_t s, cudaError_t* e) override {
+        if (T::NQ != T::NV || b.nalpha != 1 || !ilqr_direct) return false;
+        *e = IlqrLaunch<T>::rollout(dm, b, cost_dev, s, true, Jtrace, acc_trace);
+        return true;
     }
     cudaError_t ilqr_accept(const IlqrBuffers& b, int accept_always, double* Jtrace, int* acc_trace, cudaStream_t s) override {
         return IlqrLaunch<T>::accept(b, accept_always, Jtrace, acc_trace, s);
@@ -1456,6 +1472,7 @@ int ilqg_create(const ilqg_model* m, int device, ilqg_handle* out) {
     if (const char* e = getenv("ILQG_FD_BINS")) eng->fd_bins = atoi(e);
     if (const char* e = getenv("ILQG_FD_PDL")) eng->fd_pdl = atoi(e);
     if (const char* e = getenv("ILQG_FD_COOP")) eng->fd_coop = atoi(e);
+    if (const char* e = getenv("ILQG_ILQR_DIRECT")) eng->ilqr_direct = atoi(e);
     {
         const char *gm = getenv("ILQG_FD_GROUP_MAX"), *gw = getenv("ILQG_FD_GW");
         if (gm || gw) eng->set_group(gm ? atoi(gm) : -1, gw ? atoi(gw) : 0);
@@ -1975,6 +1992,7 @@ static ilqg::IlqrBuffers ilqr_sub_view(const ilqg_ilqr_s* w, int s) {
     if (b.mu_i) b.mu_i += i0;
     if (b.cdiff) b.cdiff += T * i0 * nx;
     b.iter_dev += s;
+    b.ticket += s;
     return b;
 }
 // run `f(s)` with the workspace narrowed to sub-batch s (w->b, the trace arrays), for every s
@@ -2095,7 +2113,8 @@ int ilqg_ilqr_create(ilqg_handle h, int ninst, int N, int nalpha, const double* 
             }
         }
     }
-    ILQR_ALLOC(w, b.iter_dev, ilqg_ilqr_s::MAXSUB);
+    ILQR_ALLOC(w, b.iter_dev, 2 * ilqg_ilqr_s::MAXSUB);
+    b.ticket = b.iter_dev + ilqg_ilqr_s::MAXSUB;
     std::vector<double> al(nalpha);
     for (int a = 0; a < nalpha; a++) al[a] = alphas ? alphas[a] : std::ldexp(1.0, -a);  // default ladder 1, 1/2, 1/4, ...
     CU(h, cudaMemcpy(b.alphas, al.data(), sizeof(double) * nalpha, cudaMemcpyHostToDevice));
@@ -2181,7 +2200,7 @@ int ilqg_ilqr_init_dev(ilqg_ilqr w, const double* qpos, const double* qvel, cons
     CU(h, cudaMemsetAsync(b.k, 0, sizeof(double) * TI * nu, s));
     CU(h, cudaMemsetAsync(b.nom_q, 0, sizeof(double) * TI * nq, s));
     CU(h, cudaMemsetAsync(b.nom_v, 0, sizeof(double) * TI * nv, s));
-    CU(h, cudaMemsetAsync(b.iter_dev, 0, sizeof(int) * ilqg_ilqr_s::MAXSUB, s));
+    CU(h, cudaMemsetAsync(b.iter_dev, 0, sizeof(int) * 2 * ilqg_ilqr_s::MAXSUB, s));   // iteration counters and tickets
     CU(h, ilqr_fork(w, s));
     for (int sb = 0; sb < w->nsub; sb++) {
         ilqg::IlqrBuffers one = ilqr_sub_view(w, sb);
@@ -2218,6 +2237,14 @@ static int ilqr_check_layout(ilqg_ilqr w) {
 static int ilqr_forward_one(ilqg_ilqr w, const ilqg::IlqrBuffers& b, int sb, int accept_always, cudaStream_t s) {
     ilqg_handle h = w->h;
     const size_t toff = (size_t)w->trace_cap * w->sub_i0[sb];
+    if (accept_always && b.nalpha == 1) {   // the reference's own mode: one launch (rollout over the nominal + the acceptance bookkeeping)
+        cudaError_t de = cudaSuccess;
+        if (h->eng->ilqr_rollout_direct(b, w->host_cost ? nullptr : w->d_cost, w->d_Jtrace + toff, w->d_acc_trace + toff, s, &de)) {
+            CU(h, de);
+            h->launches += 1;
+            return ILQG_OK;
+        }
+    }
     CU(h, h->eng->ilqr_rollout(b, w->host_cost ? nullptr : w->d_cost, s));
     CU(h, h->eng->ilqr_accept(b, accept_always, w->d_Jtrace + toff, w->d_acc_trace + toff, s));   // trace slot: the device iteration counter
     h->launches += 3;

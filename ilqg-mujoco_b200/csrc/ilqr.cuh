@@ -48,16 +48,25 @@ struct IlqrBuffers {
     int* iter_dev;      // iterations done (device counter: the trace slot of a pass is taken from it, so that a captured CUDA graph
                         // of iterations can be replayed), or NULL for a pass that is not an iteration (the constructor's rollout)
     int trace_cap;      // slots of the cost / accepted-alpha traces
+    int* ticket;        // CTAs of a direct-mode rollout that have finished (the last one advances iter_dev and clears it)
 };
 
 // ------------------------------------------------------------------ forward pass, all alphas at once
-template <class T>
-__global__ void __launch_bounds__(128) ilqr_rollout_kernel(const __grid_constant__ DevModel<T> m, IlqrBuffers b, const ilqg_cost* __restrict__ cost) {
+// DIRECT (the reference's own mode: one alpha, accepted unconditionally — ilqr.h:116-130 has no line search): the rollout IS the new
+// nominal, so the snapshots go straight over the nominal's knots (a thread reads knot n's record before it writes knot n, and touches
+// no other instance's data) and the bookkeeping of ilqr_accept_kernel / ilqr_commit_kernel — cost, trace slot, mu schedule, iteration
+// counter — is done here: one launch instead of three per iteration.  The trace slot is read from the device counter at the start;
+// the counter is advanced by the last CTA to finish (ticket), i.e. after every thread has read it.
+template <class T, bool DIRECT = false>
+__global__ void __launch_bounds__(128) ilqr_rollout_kernel(const __grid_constant__ DevModel<T> m, IlqrBuffers b, const ilqg_cost* __restrict__ cost,
+                                                           double* __restrict__ Jtrace = nullptr, int* __restrict__ acc_trace = nullptr) {
     constexpr int NQ = T::NQ, NV = T::NV, NU = T::NU, NX = 2 * NV;
     static_assert(NQ == NV, "the reference's state vector is 2*nv doubles starting at qpos (quirk Q9)");
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int ninst = b.ninst;
-    if (tid >= ninst * b.nalpha) return;
+    size_t slot = 0;
+    if constexpr (DIRECT) slot = b.iter_dev ? (size_t)(*b.iter_dev % b.trace_cap) * ninst : 0;
+    if (tid >= ninst * b.nalpha) return;   // (a CTA's first thread always has an instance: it does the ticket below)
     const int a = tid / ninst, i = tid - a * ninst;   // consecutive threads = consecutive instances
     const double alpha = b.alphas[a];
     double q[NQ], v[NV], u[nz(NU)], warm[NV], qacc[NV];
@@ -104,15 +113,39 @@ __global__ void __launch_bounds__(128) ilqr_rollout_kernel(const __grid_constant
             u[r] = s + alpha * kn_[r] + xu[r];
         });
         if (n > 0) prefetch(n - 1);
-        // snapshot the knot (cpMjData(dArray[n], d), ilqr.h:127) into this alpha's candidate
-        const size_t cn = (size_t)a * T1 + kn;
-        sfor<0, NQ>([&](auto ii) { b.cand_q[cn * NQ + IDX(ii)] = q[IDX(ii)]; });
-        sfor<0, NV>([&](auto ii) { b.cand_v[cn * NV + IDX(ii)] = v[IDX(ii)]; b.cand_w[cn * NV + IDX(ii)] = warm[IDX(ii)]; });
-        sfor<0, NU>([&](auto ii) { b.cand_u[cn * NU + IDX(ii)] = u[IDX(ii)]; });
+        // snapshot the knot (cpMjData(dArray[n], d), ilqr.h:127) into this alpha's candidate (DIRECT: into the nominal itself)
+        if constexpr (DIRECT) {
+            sfor<0, NQ>([&](auto ii) { b.nom_q[kn * NQ + IDX(ii)] = q[IDX(ii)]; });
+            sfor<0, NV>([&](auto ii) { b.nom_v[kn * NV + IDX(ii)] = v[IDX(ii)]; b.nom_w[kn * NV + IDX(ii)] = warm[IDX(ii)]; });
+            sfor<0, NU>([&](auto ii) { b.nom_u[kn * NU + IDX(ii)] = u[IDX(ii)]; });
+        } else {
+            const size_t cn = (size_t)a * T1 + kn;
+            sfor<0, NQ>([&](auto ii) { b.cand_q[cn * NQ + IDX(ii)] = q[IDX(ii)]; });
+            sfor<0, NV>([&](auto ii) { b.cand_v[cn * NV + IDX(ii)] = v[IDX(ii)]; b.cand_w[cn * NV + IDX(ii)] = warm[IDX(ii)]; });
+            sfor<0, NU>([&](auto ii) { b.cand_u[cn * NU + IDX(ii)] = u[IDX(ii)]; });
+        }
         if (cost) J = __dadd_rn(J, cost_eval<T>(*cost, q, v, u));
         step<T>(m, w, q, v, u, warm, qacc);   // mj_step (ilqr.h:128)
     }
-    b.cand_J[(size_t)a * ninst + i] = J;
+    if constexpr (DIRECT) {
+        // what ilqr_accept_kernel does for accept_always (acc = 0) and ilqr_commit_kernel's counter; setDInit(dArray[N]) is a no-op here:
+        // knot N of the new nominal is the state this pass started from
+        b.nom_J[i] = J;
+        if (b.mu_i && b.mu_factor > 1.0) {
+            double mu = b.mu_i[i] / b.mu_factor;
+            if (mu < b.mu_min) mu = b.mu_min;
+            b.mu_i[i] = mu;
+        }
+        b.accepted[i] = 0;
+        if (Jtrace) Jtrace[slot + i] = J;
+        if (acc_trace) acc_trace[slot + i] = 0;
+        __syncthreads();
+        if (threadIdx.x == 0 && b.iter_dev) {
+            __threadfence();
+            if (atomicAdd(b.ticket, 1) == (int)gridDim.x - 1) { *b.ticket = 0; *b.iter_dev += 1; }
+        }
+    } else
+        b.cand_J[(size_t)a * ninst + i] = J;
 }
 
 // ------------------------------------------------------------------ ladder-order acceptance

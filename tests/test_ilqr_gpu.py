@@ -259,3 +259,41 @@ def test_sub_batched_workspace_gives_the_same_bits(pkg, handles, oracle, omodels
     for key in res[0]:
         assert np.array_equal(res[0][key], res[1][key]), key
     assert np.array_equal(res[0]["kq"], res[0]["qpos"]) and len(np.unique(res[0]["accepted"])) > 1
+
+
+@pytest.mark.parametrize("nsub", [1, 3])
+def test_one_launch_forward_pass_equals_rollout_accept_commit(pkg, oracle, omodels, nsub, monkeypatch):
+    """In the reference's own mode (one alpha, accepted unconditionally) the forward pass is ONE launch: the rollout writes straight over
+    the nominal and does the acceptance bookkeeping itself (ilqr_rollout_kernel<T, true>: cost, trace slot from the device counter, mu
+    schedule, the counter advanced by the last CTA to finish).  ILQG_ILQR_DIRECT=0 restores the three launches (rollout into the
+    candidate buffers, accept, commit).  Same bits in every output, through plain launches and graph replays, for one block and for
+    ragged blocks."""
+    q, v, u, w = scenario_states("inverted_pendulum", 100, seed=91)
+    u = u * 0.2
+    cost = oracle.make_cost(**PEND_COST)
+    res = []
+    for direct in ("1", "0"):
+        monkeypatch.setenv("ILQG_ILQR_DIRECT", direct)
+        monkeypatch.setenv("ILQG_ILQR_SUB", str(nsub))
+        h = pkg.Handle(pkg.Model.named("inverted_pendulum"), 0)
+        il = pkg.Ilqr(h, 100, 20, (1.0,))
+        monkeypatch.delenv("ILQG_ILQR_DIRECT"); monkeypatch.delenv("ILQG_ILQR_SUB")
+        il.set_cost(cost)
+        il.set_mu(50.0)
+        il.set_mu_schedule(1.5)
+        il.init_host(q, v, u, w)
+        n_launch = []
+        for _ in range(4):
+            l0 = h.launches
+            il.iterate(3, accept_always=True)
+            n_launch.append(h.launches - l0)
+        out = il.get()
+        out["u0"], out["Jt"] = il.fetch_controls(last=5)
+        out["launches"] = np.array(n_launch)
+        il.close(); h.close()
+        res.append(out)
+    for key in res[0]:
+        if key != "launches":     # (full steps without a line search: a few random starts diverge, identically on both sides)
+            assert np.array_equal(res[0][key], res[1][key], equal_nan=res[0][key].dtype.kind == "f"), key
+    assert (res[0]["launches"] < res[1]["launches"]).all()      # two launches fewer per block and iteration
+    assert (res[0]["accepted"] == 0).all() and np.isfinite(res[0]["J"]).all(axis=1).mean() > 0.9

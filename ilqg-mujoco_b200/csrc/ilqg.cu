@@ -2106,11 +2106,12 @@ int ilqg_ilqr_create(ilqg_handle h, int ninst, int N, int nalpha, const double* 
         }
         w->nsub = nsub;
         if (nsub > 1) {
-            CU(h, cudaEventCreateWithFlags(&w->ev_fork, cudaEventDisableTiming));
-            for (int k = 0; k < nsub; k++) {
-                CU(h, cudaStreamCreateWithFlags(&w->sub_stream[k], cudaStreamNonBlocking));
-                CU(h, cudaEventCreateWithFlags(&w->ev_join[k], cudaEventDisableTiming));
+            cudaError_t ce = cudaEventCreateWithFlags(&w->ev_fork, cudaEventDisableTiming);
+            for (int k = 0; k < nsub && ce == cudaSuccess; k++) {
+                ce = cudaStreamCreateWithFlags(&w->sub_stream[k], cudaStreamNonBlocking);
+                if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&w->ev_join[k], cudaEventDisableTiming);
             }
+            if (ce != cudaSuccess) { ilqg_ilqr_destroy(w); return cuda_fail(h, ce, "cudaStreamCreate / cudaEventCreate"); }
         }
     }
     ILQR_ALLOC(w, b.iter_dev, 2 * ilqg_ilqr_s::MAXSUB);

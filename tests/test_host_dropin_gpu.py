@@ -50,6 +50,29 @@ def test_pendulum_mpc_matches_oracle(hostlib, oracle, omodels, q0, v0, nmpc):
         assert np.abs(x - y).max() <= 1e-5 * np.abs(y).max(), key
 
 
+@pytest.mark.parametrize("case", [0, 1, 2])
+def test_pendulum_mpc_matches_the_reference_classes_golden(hostlib, oracle, case):
+    """The same MPC run against tests/golden/mpc_inverted_pendulum_reference_classes.npz: what the REFERENCE'S OWN InvertedPendulum / ILQR /
+    Differentiator / calcMJDerivatives (verbatim sources compiled against the shims, tools/make_golden.py) leave behind — closed-loop trace,
+    final nominal, gains, value model.  GPU drop-in vs the reference's code in one hop (the physics under both is the restated MuJoCo
+    subset); tolerances as in test_pendulum_mpc_matches_oracle."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "mpc_inverted_pendulum_reference_classes.npz"))
+    N = 20
+    q0, v0, nmpc = g[f"c{case}_q0"].copy(), g[f"c{case}_v0"].copy(), int(g[f"c{case}_nmpc"])
+    a = dict(tr=np.zeros((nmpc, 5)), q=np.zeros((N + 1, 2)), v=np.zeros((N + 1, 2)), u=np.zeros((N + 1, 1)), K=np.zeros((N + 1, 4)),
+             k=np.zeros((N + 1, 1)), V=np.zeros(16), vv=np.zeros(4))
+    path = os.path.join(PKG, "models", "inverted_pendulum.ilqgm").encode()
+    assert hostlib.ilqg_host_pendulum_mpc(path, oracle._p(q0), oracle._p(v0), nmpc, *[oracle._p(a[x]) for x in ("tr", "q", "v", "u", "K", "k", "V", "vv")]) == 0
+    b = {k: g[f"c{case}_{k}"] for k in a}
+    assert np.allclose(a["tr"], b["tr"], rtol=1e-6, atol=1e-7)
+    assert np.allclose(a["q"], b["q"], rtol=1e-6, atol=1e-7) and np.allclose(a["u"], b["u"].reshape(a["u"].shape), rtol=1e-5, atol=1e-6)
+    for key in ("K", "k", "V", "vv"):
+        x, y = a[key], b[key].reshape(a[key].shape)
+        if key in ("K", "k"):
+            x, y = x[1:], y[1:]
+        assert np.abs(x - y).max() <= 1e-5 * np.abs(y).max(), key
+
+
 def test_pendulum_mpc_one_device_call_per_step_equals_the_reference_cadence(hostlib, oracle, monkeypatch):
     """InvertedPendulum::forward runs its ten iterations as ONE device call (ILQR::iterate(int): the class's own quadratic step cost
     handed over as an ilqg_cost, the chain replayed as a CUDA graph, public members synchronised once); ILQG_MIRROR_HOST_COST=1 keeps the

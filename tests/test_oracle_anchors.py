@@ -156,6 +156,23 @@ def test_restated_fd_equals_reference_driver(oracle, omodels, name):
 
 
 @pytest.mark.parametrize("name", ["inverted_pendulum", "hopper", "humanoid"])
+def test_golden_deriv_is_what_the_reference_driver_outputs(oracle, omodels, name):
+    """The committed golden `deriv` blocks (tests/golden/fd_<model>.npz — what the GPU tests are compared with on a box that has neither
+    /root/reference nor oracle/_ref) are bit for bit what the reference's own calcMJDerivatives writes for those knots."""
+    ref = os.path.join(ROOT, "oracle", "_ref", "libref_fd.so")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref not built")
+    R = C.CDLL(ref)
+    g = np.load(os.path.join(GOLD, f"fd_{name}.npz"))
+    om = omodels[name]
+    q, v, u, w, cost = (np.ascontiguousarray(g[k]) for k in ("qpos", "qvel", "ctrl", "warm", "cost"))
+    d = np.zeros_like(g["deriv"])
+    ncpu = R.ref_calc_derivatives_batch(om.ptr, q.shape[0], oracle._p(q), oracle._p(v), oracle._p(u), oracle._p(w), oracle._p(cost), oracle._p(d), 16)
+    assert 1 <= ncpu <= 16
+    assert np.array_equal(d, g["deriv"])
+
+
+@pytest.mark.parametrize("name", ["inverted_pendulum", "hopper", "humanoid"])
 def test_oracle_reproduces_golden_vectors(oracle, omodels, name):
     g = np.load(os.path.join(GOLD, f"fd_{name}.npz"))
     om = omodels[name]

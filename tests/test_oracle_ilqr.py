@@ -54,6 +54,27 @@ def test_restated_mpc_equals_reference_classes(q0, v0, nmpc):
     assert res["J0"][-1] < res["J0"][0]          # ten iterations do reduce the cost from a perturbed start
 
 
+@pytest.mark.parametrize("case", [0, 1, 2])
+def test_restated_mpc_reproduces_the_reference_classes_golden(oracle, omodels, case):
+    """The committed outputs of the reference's own classes (tests/golden/mpc_inverted_pendulum_reference_classes.npz, written by
+    tools/make_golden.py where /root/reference exists) against the oracle's restated MPC loop — the same comparison as
+    test_restated_mpc_equals_reference_classes, but one that also runs where oracle/_ref cannot be built."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "mpc_inverted_pendulum_reference_classes.npz"))
+    om = omodels["inverted_pendulum"]
+    N = 20
+    q0, v0, nmpc = g[f"c{case}_q0"].copy(), g[f"c{case}_v0"].copy(), int(g[f"c{case}_nmpc"])
+    b = dict(tr=np.zeros((nmpc, 5)), q=np.zeros((N + 1, 2)), v=np.zeros((N + 1, 2)), u=np.zeros((N + 1, 1)), K=np.zeros((N + 1, 4)),
+             k=np.zeros((N + 1, 1)), V=np.zeros(16), vv=np.zeros(4))
+    cost = oracle.make_cost(q2=[1, 10], v2=[1, 10], u2=[1])
+    oracle.lib().mjo_mpc_run(om.ptr, oracle._p(q0), oracle._p(v0), 10, N, 10, nmpc, oracle._p(cost), None, 0, 1, oracle._p(b["tr"]), None, None,
+                             *[oracle._p(b[x]) for x in ("q", "v", "u", "K", "k", "V", "vv")])
+    for key in b:
+        x, y = b[key], g[f"c{case}_{key}"].reshape(b[key].shape)
+        if key in ("K", "k"):
+            x, y = x[1:], y[1:]
+        assert np.abs(x - y).max() <= (1e-5 if key in ("K", "k", "V", "vv", "u") else 1e-6) * max(1e-300, np.abs(y).max()), key
+
+
 def test_linesearch_spec_reduces_to_reference_iterate(oracle, omodels):
     """A10: alphas = {1}, accept_always -> identical numbers to ILQR::iterate()."""
     om = omodels["inverted_pendulum"]

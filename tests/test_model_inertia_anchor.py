@@ -119,3 +119,106 @@ def test_body_mass_com_and_inertia_by_quadrature(pkg, name):
         assert ipos[k] == pytest.approx(com, abs=1e-11), body.get("name")
         want = np.array([I[0, 0], I[1, 1], I[2, 2], I[0, 1], I[0, 2], I[1, 2]])
         assert np.abs(inertia[k] - want).max() <= 1e-10 * np.abs(want).max(), (body.get("name"), inertia[k], want)
+
+
+# ------------------------------------------------------------------ kinematics, from the MJCF text again
+def quat_mul(a, b):
+    return np.array([a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3], a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2],
+                     a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1], a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0]])
+
+
+def quat_mat(q):
+    w, x, y, z = q / np.linalg.norm(q)
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                     [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                     [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+
+def rodrigues(axis, ang):
+    a = axis / np.linalg.norm(axis)
+    K = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+    return np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K
+
+
+def fk_world_coms(root, qpos, degrees):
+    """World position, rotation and centre of mass of every body at qpos, by composing the XML's own body / joint records
+    (MuJoCo's kinematics: a body starts at parent o (pos, quat); its joints act in order — a free joint sets the frame, a slide
+    translates along its axis, a hinge turns the frame about its anchor)."""
+    global_coords = root.find("compiler").get("coordinate", "local") == "global"
+    out = []
+    qi = [0]
+
+    def visit(body, Pp, Rp, Pp0):
+        # frame at the reference configuration
+        pos = vec(body.get("pos", "0 0 0"))
+        quat = vec(body.get("quat", "1 0 0 0"))
+        if global_coords:
+            P0, R0 = pos.copy(), np.eye(3)                   # given in world coordinates at qpos0 (no rotated frames in hopper.xml)
+            P, R = Pp + Rp @ (P0 - Pp0), Rp.copy()           # the same offset, carried by the parent's current frame
+        else:
+            P0 = None
+            P, R = Pp + Rp @ pos, Rp @ quat_mat(quat)
+        joints = [j for j in body if j.tag in ("joint", "freejoint")]
+        for j in joints:
+            ty = "free" if j.tag == "freejoint" else j.get("type", "hinge")
+            if ty == "free":
+                P, R = qpos[qi[0]:qi[0] + 3].copy(), quat_mat(qpos[qi[0] + 3:qi[0] + 7])
+                qi[0] += 7
+                continue
+            axis = vec(j.get("axis", "0 0 1"))
+            jp = vec(j.get("pos", "0 0 0"))
+            if global_coords:
+                jp = jp - P0                                  # anchor in the body frame
+            ref = num(j.get("ref", "0"))
+            if ty == "hinge" and degrees:
+                ref = np.deg2rad(ref)
+            q = qpos[qi[0]] - ref
+            qi[0] += 1
+            if ty == "slide":
+                P = P + R @ (axis / np.linalg.norm(axis)) * q
+            else:
+                anchor = P + R @ jp
+                R = R @ rodrigues(axis, q)
+                P = anchor - R @ jp
+        M, F, _ = body_moments(body)
+        com_local = F / M - (P0 if global_coords else 0.0)
+        out.append((P, R, P + R @ com_local, M))
+        for ch in body.findall("body"):
+            visit(ch, P, R, P0 if global_coords else None)
+
+    for b in root.find("worldbody").findall("body"):
+        visit(b, np.zeros(3), np.eye(3), np.zeros(3))
+    return out
+
+
+@pytest.mark.parametrize("name", ["hopper", "humanoid"])
+def test_oracle_kinematics_against_the_mjcf_text(oracle, omodels, pkg, name):
+    """The oracle's mj_kinematics / mj_comPos products (xpos, xipos, subtree_com of the whole tree) at random configurations against
+    a forward kinematics composed here from the XML's body and joint records and the quadrature centres of mass above: pins
+    body_pos / body_quat / jnt_pos / jnt_axis / qpos0 / body_ipos of the compiled tables and the kinematics that reads them."""
+    path = os.path.join(RES, name + ".xml")
+    if not os.path.exists(path):
+        pytest.skip("reference MJCF files not present on this machine")
+    root = ET.parse(path).getroot()
+    degrees = root.find("compiler").get("angle", "degree") == "degree"
+    om = omodels[name]
+    m = pkg.Model.named(name)
+    rng = np.random.default_rng(12)
+    for trial in range(4):
+        q = m.field("qpos0")[:m.nq].copy()
+        if name == "humanoid":
+            q[:3] += rng.uniform(-0.5, 0.5, 3)
+            w = rng.normal(0, 0.6, 3); ang = np.linalg.norm(w)
+            q[3:7] = np.concatenate([[np.cos(ang / 2)], np.sin(ang / 2) * w / ang])
+            q[7:] += rng.uniform(-0.7, 0.7, m.nq - 7)
+        else:
+            q += rng.uniform(-0.6, 0.6, m.nq)
+        d = oracle.dump(om, q, np.zeros(m.nv), np.zeros(m.nu))
+        fk = fk_world_coms(root, q, degrees)
+        tot_m, tot_f = 0.0, np.zeros(3)
+        for k, (P, R, com, M) in enumerate(fk, start=1):
+            assert d["xpos"][k] == pytest.approx(P, abs=1e-12), (trial, k)
+            assert quat_mat(d["xquat"][k]) == pytest.approx(R, abs=1e-12), (trial, k)
+            assert d["xipos"][k] == pytest.approx(com, abs=1e-11), (trial, k)
+            tot_m += M; tot_f += M * com
+        assert d["subtree_com"][1] == pytest.approx(tot_f / tot_m, abs=1e-11)     # (body 1 roots the whole mechanism in both models)

@@ -427,3 +427,108 @@ def test_actuator_forces_against_the_mjcf_text(oracle, omodels, pkg, name):
         want[dof_of[mot.get("joint")]] += num(mot.get("gear", "1")) * c
     d = oracle.dump(om, m.field("qpos0")[:m.nq].copy(), np.zeros(m.nv), u)
     assert d["qfrc_actuator"] == pytest.approx(want, abs=1e-12)
+
+
+# ------------------------------------------------------------------ narrow phase: distances by brute force
+def world_geoms(root, q, degrees):
+    """every geom in world coordinates at q: ('plane',) | ('sphere', centre, r) | ('capsule', end a, end b, r), in the model's geom order
+    (the worldbody's own geoms first, then body by body)"""
+    global_coords = root.find("compiler").get("coordinate", "local") == "global"
+    fk = fk_world_coms(root, q, degrees)
+    bodies = []
+    for b in root.find("worldbody").findall("body"):
+        walk(b, bodies)
+    out = [("plane",) for g in root.find("worldbody").findall("geom") if g.get("type") == "plane"]
+    for body, (P, R, _, _) in zip(bodies, fk):
+        P0 = vec(body.get("pos", "0 0 0")) if global_coords else np.zeros(3)
+        for g in body.findall("geom"):
+            size = vec(g.get("size"))
+            if g.get("type", "sphere") == "capsule":
+                ft = vec(g.get("fromto"))
+                out.append(("capsule", P + R @ (ft[:3] - P0), P + R @ (ft[3:] - P0), size[0]))
+            else:
+                out.append(("sphere", P + R @ (vec(g.get("pos", "0 0 0")) - P0), size[0]))
+    return out
+
+
+def segment_points(g):
+    return (g[1], g[1]) if g[0] == "sphere" else (g[1], g[2])
+
+
+def brute_force_distance(g1, g2):
+    """signed distance between two spheres / capsules: minimum over a dense grid of the two axis parameters, refined on a finer grid
+    around the best cell (the squared distance is a convex quadratic in (s, t): no local minima to miss)"""
+    (a1, b1), (a2, b2) = segment_points(g1), segment_points(g2)
+    lo = np.zeros(2); hi = np.ones(2)
+    best = None
+    for _ in range(6):
+        s = np.linspace(lo[0], hi[0], 41); t = np.linspace(lo[1], hi[1], 41)
+        p1 = a1[None, :] + s[:, None] * (b1 - a1)[None, :]
+        p2 = a2[None, :] + t[:, None] * (b2 - a2)[None, :]
+        d = np.linalg.norm(p1[:, None, :] - p2[None, :, :], axis=2)
+        i, j = np.unravel_index(d.argmin(), d.shape)
+        best = (d[i, j], p1[i], p2[j])
+        ws, wt = (hi[0] - lo[0]) / 40, (hi[1] - lo[1]) / 40
+        lo = np.array([max(0.0, s[i] - ws), max(0.0, t[j] - wt)]); hi = np.array([min(1.0, s[i] + ws), min(1.0, t[j] + wt)])
+    d, p1, p2 = best
+    return d - g1[-1] - g2[-1], p1, p2
+
+
+@pytest.mark.parametrize("name", ["hopper", "humanoid"])
+def test_contact_distances_against_brute_force_geometry(oracle, omodels, pkg, name):
+    """Every contact the oracle's narrow phase reports (plane-sphere, plane-capsule, sphere / capsule pairs) at random folded poses near
+    the ground: its distance against geometry done the slow way on the geoms placed by the XML forward kinematics above — the end
+    spheres' heights for a plane, a dense-grid minimum over both axis parameters for a pair — and its position / normal against the
+    witness points.  Pins geom placement, the pair distances and MuJoCo's 'midpoint, normal from geom 1 to geom 2' convention as the
+    oracle restates it."""
+    path = os.path.join(RES, name + ".xml")
+    if not os.path.exists(path):
+        pytest.skip("reference MJCF files not present on this machine")
+    root = ET.parse(path).getroot()
+    degrees = root.find("compiler").get("angle", "degree") == "degree"
+    om = omodels[name]
+    m = pkg.Model.named(name)
+    rng = np.random.default_rng(21)
+    rngs = m.field("jnt_range").reshape(-1, 2)[:m.njnt]
+    seen = {"plane": 0, "pair": 0}
+    for trial in range(40):
+        q = m.field("qpos0")[:m.nq].copy()
+        if name == "humanoid":
+            q[2] = rng.uniform(0.25, 0.9)
+            w = rng.normal(0, 1.0, 3); ang = np.linalg.norm(w)
+            q[3:7] = np.concatenate([[np.cos(ang / 2)], np.sin(ang / 2) * w / ang])
+            q[7:] = rng.uniform(rngs[1:, 0], rngs[1:, 1])          # anywhere inside the joint ranges: folded limbs touch
+        else:
+            q[1] = rng.uniform(0.3, 1.2); q[2] = rng.uniform(-1.5, 1.5)
+            q[3:] = rng.uniform(rngs[3:, 0], rngs[3:, 1])
+        d = oracle.dump(om, q, np.zeros(m.nv), np.zeros(m.nu))
+        geoms = world_geoms(root, q, degrees)
+        assert len(geoms) == m.ngeom
+        for c in range(d["ncon"]):
+            g1, g2 = d["contact_geom"][c]
+            dist, pos, nrm = d["contact_dist"][c], d["contact_pos"][c], d["contact_frame"][c][:3]
+            A, B = geoms[g1], geoms[g2]
+            if A[0] == "plane":
+                ends = [B[1]] if B[0] == "sphere" else [B[1], B[2]]
+                e = min(ends, key=lambda p: np.linalg.norm(p[:2] - pos[:2]))      # the end this contact belongs to
+                assert dist == pytest.approx(e[2] - B[-1], abs=1e-10), (trial, c)
+                assert nrm == pytest.approx([0, 0, 1], abs=1e-12)
+                assert pos == pytest.approx([e[0], e[1], e[2] - B[-1] - 0.5 * dist], abs=1e-10)    # midway between the surfaces
+                seen["plane"] += 1
+            else:
+                want, p1, p2 = brute_force_distance(A, B)
+                ax1 = A[2] - A[1] if A[0] == "capsule" else None
+                ax2 = B[2] - B[1] if B[0] == "capsule" else None
+                if ax1 is not None and ax2 is not None and abs(ax1 @ ax2) > 0.999 * np.linalg.norm(ax1) * np.linalg.norm(ax2):
+                    continue                                                       # (near-parallel axes: several contacts, other convention)
+                assert dist == pytest.approx(want, abs=2e-7), (trial, c, g1, g2)
+                if np.linalg.norm(p2 - p1) < 1e-3:
+                    continue                                                       # (crossing axes: the direction between the witness points is noise)
+                n = (p2 - p1) / np.linalg.norm(p2 - p1)
+                assert nrm == pytest.approx(n, abs=2e-5), (trial, c)
+                s1 = p1 + n * A[-1]; s2 = p2 - n * B[-1]
+                assert pos == pytest.approx(0.5 * (s1 + s2), abs=2e-6), (trial, c)
+                seen["pair"] += 1
+    assert seen["plane"] > 10
+    if name == "humanoid":
+        assert seen["pair"] > 5

@@ -680,18 +680,28 @@ __global__ void __launch_bounds__(THREADS, MINB) fd_velctrl_loaded_kernel(const 
     if (!finite && status) atomicExch(&status[kk], ILQG_ERR_NONFINITE);
 }
 
+// Experiment (ILQG_Q_MIX = W): the batch is ordered heaviest knot first, so the CTAs resident on an SM at the same time are all of one
+// work class and the stance phase of the launch overflows every L1 at once.  With W > 0 the launch order alternates waves of W CTAs
+// from the heavy end and from the light end of that order (a relabelling of blockIdx: heavy-designated launch indices take
+// 0, 1, 2, ... and light-designated ones G - 1, G - 2, ...), so that a stance CTA shares its SM's L1 with a flight CTA.
+DEV int fd_mix_block(int i, int G, int W) {
+    const int pair = i / (2 * W), r = i - pair * 2 * W;
+    return r < W ? pair * W + r : G - 1 - (pair * W + (r - W));
+}
+
 template <class T, bool SYNC, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) fd_qpos_kernel(const __grid_constant__ DevModel<T> m, int nknots, const double* __restrict__ qpos,
                                                          const double* __restrict__ qvel, const double* __restrict__ ctrl,
                                                          const double* __restrict__ qacc_center, const ilqg_cost* __restrict__ cost,
                                                          double eps, int niter, const FdDst dst, int* __restrict__ status,
-                                                         const int* __restrict__ perm) {
+                                                         const int* __restrict__ perm, int mix) {
     using S = FdSplit<T, THREADS>;
     constexpr int NV = T::NV, NU = T::NU, NQ = T::NQ, G = 2 * NV;
     __shared__ double stage[S::KPC_Q * S::STG_Q];
     __shared__ int knot_of[S::KPC_Q];
     const int kl = threadIdx.x / G, l = threadIdx.x - kl * G;
-    const int k0 = blockIdx.x * S::KPC_Q, slot = k0 + kl;
+    const int bx = mix > 0 ? fd_mix_block(blockIdx.x, gridDim.x, mix) : blockIdx.x;
+    const int k0 = bx * S::KPC_Q, slot = k0 + kl;
     const bool valid = kl < S::KPC_Q && slot < nknots;
     const int sc = slot < nknots ? slot : nknots - 1;
     const int kk = perm ? perm[sc] : sc;
@@ -854,6 +864,7 @@ struct Engine {
     virtual void set_group(int /*max knots*/, int /*lanes per perturbed solve*/) {}
     virtual void set_vu_classes(const char*) {}
     virtual void set_q_minb(int) {}
+    virtual void set_q_mix(int) {}
     virtual void set_vu_pos(int) {}
     // ints of scratch fd() wants for `nknots` knots (bucket counters, keys, permutation); 0 = none
     // (`batch`: the size of the whole batch a chunk belongs to — the kernel variant is chosen on it, so that a chunked host
@@ -896,6 +907,7 @@ struct EngineT : Engine {
     int fused_max = FdFusedShape<T>::OK ? 64 : 0;
     void set_fused_max(int n) override { fused_max = FdFusedShape<T>::OK ? n : 0; }
     void set_q_minb(int n) override { q_minb = n; }
+    void set_q_mix(int n) override { q_mix = n; }
     void set_vu_pos(int n) override { vu_pos = n; }
     void set_vu_classes(const char* e) override {
         vu_nclass = 0;
@@ -951,7 +963,19 @@ struct EngineT : Engine {
     //              192 threads, one CTA per SM — a quarter less local-memory footprint in L1, a quarter fewer warps: +19 %);
     //   qpos     : 192 threads = 16 knots with no idle lane, two CTAs per SM at 168 registers (12 warps per SM: -7 % time;
     //              two 256-thread CTAs at 128 registers: +8 %).
-    static constexpr int VU_THREADS = 256, VU_MINB = 1, Q_THREADS = 192, Q_MINB = 2;
+#ifndef ILQG_VU_THREADS   // (compile-time A/B of the CTA shapes: -DILQG_VU_THREADS=... into a second library, loaded through ILQG_LIB)
+#define ILQG_VU_THREADS 256
+#endif
+#ifndef ILQG_VU_MINB
+#define ILQG_VU_MINB 1
+#endif
+#ifndef ILQG_Q_THREADS
+#define ILQG_Q_THREADS 192
+#endif
+#ifndef ILQG_Q_MINBLOCKS
+#define ILQG_Q_MINBLOCKS 2
+#endif
+    static constexpr int VU_THREADS = ILQG_VU_THREADS, VU_MINB = ILQG_VU_MINB, Q_THREADS = ILQG_Q_THREADS, Q_MINB = ILQG_Q_MINBLOCKS;
     // rows per knot the shared-memory qvel/ctrl kernel holds (ILQG_VU_CAP; 0 = local-memory kernel only).  Measured on B200: see DESIGN.md
     // Row-capacity classes of the shared-memory qvel/ctrl kernel, ascending (ILQG_VU_CLASSES="8,16"; "0" = local-memory kernel
     // only): one launch per class with a carve-out sized for it; knots without rows (flight) and knots above the last class
@@ -966,6 +990,7 @@ struct EngineT : Engine {
     int vu_nclass = 0;
     bool vu_attr_set = false;
     int q_minb = Q_MINB;
+    int q_mix = 0;   // ILQG_Q_MIX (fd_mix_block)
     // qvel / ctrl columns on the centre's position-stage products (ILQG_VU_POS: 0 = own position stage per thread, 1 = loaded, one
     // CTA per SM, 2 = loaded, two CTAs per SM at 128 registers)
     int vu_pos = 0;
@@ -1017,10 +1042,10 @@ struct EngineT : Engine {
         using PQ = FdSplit<T, Q_THREADS>;
         if (q_minb == 1)   // experiment (ILQG_Q_MINB=1): one CTA per SM, no register cap — half the local-memory footprint per SM
             fd_qpos_kernel<T, true, Q_THREADS, 1><<<(nknots + PQ::KPC_Q - 1) / PQ::KPC_Q, Q_THREADS, 0, s>>>(
-                dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps, o.niter, dst, status, perm);
+                dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps, o.niter, dst, status, perm, perm ? q_mix : 0);
         else
         fd_qpos_kernel<T, true, Q_THREADS, Q_MINB><<<(nknots + PQ::KPC_Q - 1) / PQ::KPC_Q, Q_THREADS, 0, s>>>(
-            dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps, o.niter, dst, status, perm);
+            dm, nknots, qpos, qvel, ctrl, qacc_center, cost_dev, o.eps, o.niter, dst, status, perm, perm ? q_mix : 0);
     }
     cudaError_t fd(int nknots, const double* qpos, const double* qvel, const double* ctrl, const double* warm, const ilqg_cost* cost_dev,
                    const ilqg_fd_opts& o, const FdDst& dst, double* qacc_center, int* status, int* scratch, int batch, cudaStream_t s,
@@ -1387,6 +1412,7 @@ __global__ void ilqr_pack_first_control_kernel(ilqg::IlqrBuffers b, IlqrSubTable
 
 // ==================================================================== C ABI
 #define ILQG_HOST_MAXCHUNKS 32
+#define ILQG_HOST_MAXCOMP 8
 struct ilqg_handle_s {
     void* stage_host = nullptr;      // pinned landing buffer of small packed results (ilqg_ilqr_get_first_control_*_host)
     size_t stage_host_bytes = 0;
@@ -1404,9 +1430,11 @@ struct ilqg_handle_s {
     void* d_stage = nullptr; size_t stage_cap = 0;
     long launches = 0;  // kernels launched through this handle (bench.py reports it)
     int host_chunks = 0;  // > 0: forced chunk count of the host-pointer FD pipeline
-    int host_comp_streams = 2;  // compute streams of that pipeline (ILQG_HOST_COMP)
+    int host_comp_streams = 4;  // compute streams of that pipeline (ILQG_HOST_COMP)
     bool profiling = false;
     cudaStream_t pipe[4] = {nullptr, nullptr, nullptr, nullptr};  // upload / compute A / download / compute B streams of the *_host FD entry point
+    int host_prio = 1;          // ILQG_HOST_PRIO (0: two plain streams, alternating): compute streams of that pipeline form a priority ladder (comp[])
+    cudaStream_t comp[ILQG_HOST_MAXCOMP] = {};   // compute stream j has priority (greatest + j): chunk ci runs on comp[ci % ncomp]
     cudaEvent_t pipe_ev[2 * ILQG_HOST_MAXCHUNKS] = {};    // per chunk: uploaded, computed
     int* h_stat = nullptr; size_t hstat_cap = 0;          // pinned landing buffer of the status words
     // opt-in (ilqg_set_host_pinning): large caller buffers of the *_host FD call are page-locked (cudaHostRegister) the first time
@@ -1480,9 +1508,11 @@ int ilqg_create(const ilqg_model* m, int device, ilqg_handle* out) {
     if (const char* e = getenv("ILQG_FD_FUSED_MAX")) eng->set_fused_max(atoi(e));
     if (const char* e = getenv("ILQG_VU_CLASSES")) eng->set_vu_classes(e);
     if (const char* e = getenv("ILQG_Q_MINB")) eng->set_q_minb(atoi(e));
+    if (const char* e = getenv("ILQG_Q_MIX")) eng->set_q_mix(atoi(e));
     if (const char* e = getenv("ILQG_VU_POS")) eng->set_vu_pos(atoi(e));
     if (const char* e = getenv("ILQG_HOST_CHUNKS")) h->host_chunks = atoi(e);
     if (const char* e = getenv("ILQG_HOST_COMP")) h->host_comp_streams = atoi(e);
+    if (const char* e = getenv("ILQG_HOST_PRIO")) h->host_prio = atoi(e);
     if (const char* e = getenv("ILQG_PIN_HOST")) h->pin_host = atoi(e) != 0;
     if (cudaMalloc(&h->d_cost, sizeof(ilqg_cost)) != cudaSuccess) {
         delete eng;
@@ -1503,6 +1533,7 @@ int ilqg_destroy(ilqg_handle h) {
     cudaFree(h->d_stage);
     for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i < 4; i++) if (h->pipe[i]) cudaStreamDestroy(h->pipe[i]);
+    for (int i = 0; i < ILQG_HOST_MAXCOMP; i++) if (h->comp[i]) cudaStreamDestroy(h->comp[i]);
     for (int i = 0; i < 2 * ILQG_HOST_MAXCHUNKS; i++) if (h->pipe_ev[i]) cudaEventDestroy(h->pipe_ev[i]);
     if (h->h_stat) cudaFreeHost(h->h_stat);
     if (h->stage_host) cudaFreeHost(h->stage_host);
@@ -1801,12 +1832,16 @@ int ilqg_fd_batch_host(ilqg_handle h, int nknots, const double* qpos, const doub
     // copy engine then streams deriv back to back: the download is 5x the upload and, at PCIe rates, longer than the kernels
     // (86,016 hopper knots = 72 MB = 1.3 ms at the measured 57 GB/s).  Two compute streams let the next chunk's CTAs fill the
     // SMs the current chunk's last wave leaves idle.  Every chunk runs the kernel variant of the WHOLE batch, so the result is
-    // bit-identical to one device call.  Measured on B200, 86,016 knots: 1.73 ms with 4-6 chunks (one stream per chunk: 1.97;
+    // bit-identical to one device call.  The compute streams form a PRIORITY LADDER (below): SURVEY-8d batch 1.85 -> 1.78 ms with
+    // 8 chunks on 4 streams against two plain alternating streams.  Measured on B200 in round 1 (its lighter batch), 86,016 knots:
+    // 1.73 ms with 4-6 chunks on two plain streams (one stream per chunk: 1.97;
     // one compute stream: 1.87; chunk sizes ramping up from 4096: 1.97 — small chunks of the split kernels are latency-bound;
     // kernels storing deriv straight into pinned host memory, no copy: 2.05 ms — the 432/288-byte segments of the reference
     // layout reach 35 GB/s over PCIe as SM stores against the copy engine's 57).
     size_t csize[ILQG_HOST_MAXCHUNKS];
-    size_t nchunks = n / 14336 < 1 ? 1 : n / 14336, cmax = 0;
+    const bool overlap = h->eng->fd_calls_may_overlap();
+    const size_t per_chunk = overlap && h->host_prio ? 10752 : 14336;
+    size_t nchunks = n / per_chunk < 1 ? 1 : n / per_chunk, cmax = 0;
     if (h->host_chunks > 0) nchunks = (size_t)h->host_chunks;   // ILQG_HOST_CHUNKS (experiments)
     if (nchunks > ILQG_HOST_MAXCHUNKS) nchunks = ILQG_HOST_MAXCHUNKS;
     {
@@ -1817,7 +1852,7 @@ int ilqg_fd_batch_host(ilqg_handle h, int nknots, const double* qpos, const doub
     for (size_t i = 0; i < nchunks; i++) cmax = csize[i] > cmax ? csize[i] : cmax;
     const size_t scr = (h->eng->fd_scratch_ints((int)cmax, nknots) + 1) & ~(size_t)1;   // even: the scratch holds doubles too
     const size_t nstat = (n + 1) & ~(size_t)1;
-    size_t bytes = ndbl * sizeof(double) + (nstat + 2 * scr) * sizeof(int);
+    size_t bytes = ndbl * sizeof(double) + (nstat + ILQG_HOST_MAXCOMP * scr) * sizeof(int);
     int rc = ensure_stage(h, bytes);
     if (rc) return rc;
     double* b = (double*)h->d_stage;
@@ -1835,7 +1870,18 @@ int ilqg_fd_batch_host(ilqg_handle h, int nknots, const double* qpos, const doub
         for (int i = 0; i < 2 * ILQG_HOST_MAXCHUNKS; i++) CU(h, cudaEventCreateWithFlags(&h->pipe_ev[i], cudaEventDisableTiming));
     }
     cudaStream_t up = h->pipe[0], down = h->pipe[2];
-    const int ncomp = h->eng->fd_calls_may_overlap() ? h->host_comp_streams : 1;
+    int ncomp = overlap ? h->host_comp_streams : 1;
+    if (ncomp < 1) ncomp = 1;
+    if (ncomp > ILQG_HOST_MAXCOMP) ncomp = ILQG_HOST_MAXCOMP;
+    const bool ladder = h->host_prio != 0 && ncomp > 1;
+    if (ladder && !h->comp[0]) {
+        int least = 0, greatest = 0;
+        CU(h, cudaDeviceGetStreamPriorityRange(&least, &greatest));   // numerically lower = higher priority
+        for (int j = 0; j < ILQG_HOST_MAXCOMP; j++) {
+            const int pr = greatest + j < least ? greatest + j : least;
+            CU(h, cudaStreamCreateWithPriority(&h->comp[j], cudaStreamNonBlocking, pr));
+        }
+    }
     const ilqg_cost* dcost = nullptr;
     if (cost) {
         CU(h, cudaMemcpyAsync(h->d_cost, cost, sizeof(ilqg_cost), cudaMemcpyHostToDevice, up));
@@ -1851,14 +1897,19 @@ int ilqg_fd_batch_host(ilqg_handle h, int nknots, const double* qpos, const doub
         else CU(h, cudaMemsetAsync(b + off_w + lo * nv, 0, cn * nv * sizeof(double), up));
         if (!cost)  // keep the caller's cost-gradient entries
             CU(h, cudaMemcpyAsync(b + off_d + lo * nd, deriv + lo * nd, cn * nd * sizeof(double), cudaMemcpyHostToDevice, up));
-        cudaStream_t comp = h->pipe[(ncomp > 1 && (ci & 1)) ? 3 : 1];
+        // compute stream of the chunk.  Two plain streams, alternating (default); or a priority ladder (ILQG_HOST_PRIO=1,
+        // ILQG_HOST_COMP = streams): chunk ci on stream ci % ncomp, stream j at priority greatest + j — with as many streams as chunks the
+        // CTA scheduler always prefers the EARLIEST chunk's pending CTAs (the chunk the download is waiting for) and later chunks
+        // only fill the SMs it leaves idle.
+        const int cslot = ncomp > 1 ? ci % ncomp : 0;
+        cudaStream_t comp = ladder ? h->comp[cslot] : h->pipe[(cslot & 1) ? 3 : 1];
         CU(h, cudaEventRecord(h->pipe_ev[2 * ci], up));
         CU(h, cudaStreamWaitEvent(comp, h->pipe_ev[2 * ci], 0));
         ilqg::FdDst dst{};
         dst.p[0] = b + off_d + lo * nd;
         dst.n = 1;
         rc = fd_launch(h, (int)cn, b + off_q + lo * nq, b + off_v + lo * nv, b + off_u + lo * nu, b + off_w + lo * nv, dcost, opts, dst,
-                       b + off_a + lo * nv, dstat + lo, comp, scr ? dscr + ((ncomp > 1 && (ci & 1)) ? scr : 0) : nullptr, nknots);   // scratch per compute stream
+                       b + off_a + lo * nv, dstat + lo, comp, scr ? dscr + (ladder ? cslot : (cslot & 1)) * scr : nullptr, nknots);   // scratch per compute stream
         if (rc) return rc;
         CU(h, cudaEventRecord(h->pipe_ev[2 * ci + 1], comp));
         CU(h, cudaStreamWaitEvent(down, h->pipe_ev[2 * ci + 1], 0));

@@ -1,4 +1,7 @@
-"""Host-pointer FD call (ilqg_fd_batch_host) timing for a few chunkings of its copy/compute pipeline."""
+"""Host-pointer FD call (ilqg_fd_batch_host) timing for a few chunkings of its copy/compute pipeline.
+
+    python tools/prof_e2e.py [chunks[:compute_streams[:priority_ladder]] ...]      (- = the default of that setting)
+ILQG_WORKLOAD=r1: round 1's batch instead of the SURVEY-8d one."""
 import ctypes as C, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -7,7 +10,10 @@ pkg = e.load_package()
 from ilqg_mujoco_b200 import workload as wl
 model = pkg.Model.named("hopper")
 h = pkg.Handle(model, 0)
-q, v, u, w, _ = wl.make_knots(h, 4096, 21, seed=0, device="cuda:0", model="hopper")
+if os.environ.get("ILQG_WORKLOAD") == "r1":
+    q, v, u, w, _ = wl.make_knots(h, 4096, 21, seed=0, device="cuda:0", model="hopper")
+else:
+    q, v, u, w, _ = wl.make_knots_8d(h, 4096, 21, seed=0, device="cuda:0")
 h.close()
 nk = q.shape[0]
 hq, hv, hu, hw = (t.cpu().pin_memory() for t in (q, v, u, w))
@@ -18,16 +24,19 @@ cost = pkg.make_cost(q1=[1.0]); L = pkg.lib()
 def step():
     L.ilqg_fd_batch_host(h._h, nk, C.c_void_p(hq.data_ptr()), C.c_void_p(hv.data_ptr()), C.c_void_p(hu.data_ptr()), C.c_void_p(hw.data_ptr()),
                          cost.ctypes.data_as(C.c_void_p), None, C.c_void_p(hd.data_ptr()), C.c_void_p(ha.data_ptr()), C.c_void_p(hs.data_ptr()))
-for ch in sys.argv[1:] or ["0"]:
-    if ":" in ch: ch, os.environ["ILQG_HOST_COMP"] = ch.split(":")
-    if ch != "0": os.environ["ILQG_HOST_CHUNKS"] = ch   # read when the handle is created
+for spec in sys.argv[1:] or ["-"]:
+    f = spec.split(":") + ["-", "-"]
+    ch = f[0]
+    for key, val in (("ILQG_HOST_CHUNKS", f[0]), ("ILQG_HOST_COMP", f[1]), ("ILQG_HOST_PRIO", f[2])):   # read when the handle is created
+        os.environ.pop(key, None)
+        if val != "-": os.environ[key] = val
     h = pkg.Handle(model, 0)
     for _ in range(3): step()
     t0 = time.perf_counter()
     for _ in range(30): step()
     dt = (time.perf_counter() - t0) / 30
     h.close()
-    print(f"chunks={ch}: {dt*1e3:.3f} ms/step -> {nk/dt/1e6:.2f} M knots/s e2e; D2H {nk*(model.nd+model.nv)*8/dt/1e9:.1f} GB/s")
+    print(f"chunks:streams:ladder={spec}: {dt*1e3:.3f} ms/step -> {nk/dt/1e6:.2f} M knots/s e2e; D2H {nk*(model.nd+model.nv)*8/dt/1e9:.1f} GB/s")
 # raw PCIe rates for reference
 d = torch.empty(nk * model.nd, dtype=torch.float64, device="cuda:0")
 for name, fn in (("D2H", lambda: hd.view(-1).copy_(d, non_blocking=True)), ("H2D", lambda: d.copy_(hd.view(-1), non_blocking=True))):

@@ -447,7 +447,11 @@ template <class T, int THREADS_ = 256>
 struct FdSplit {
     static constexpr int NV = T::NV, NU = T::NU, NCOL = 2 * NV + NU;
     static constexpr int gcd_(int a, int b) { return b == 0 ? a : gcd_(b, a % b); }
+#ifdef ILQG_VU_GK   // (compile-time A/B: threads per knot of the qvel/ctrl kernel; must divide nv and nu)
+    static constexpr int GK = (NU > 0 && NV % ILQG_VU_GK == 0 && NU % ILQG_VU_GK == 0) ? ILQG_VU_GK : (NU > 0 ? gcd_(NV, NU) : 1);
+#else
     static constexpr int GK = NU > 0 ? gcd_(NV, NU) : 1;
+#endif
     static constexpr int CU = NU / GK, CV = NV / GK;      // ctrl / qvel columns per thread
     static constexpr int THREADS = THREADS_;
     static constexpr int KPC_VU = THREADS / GK;           // knots per CTA

@@ -108,7 +108,7 @@ def test_work_class_ordering_changes_placement_only(full, pkg):
 
 @pytest.mark.parametrize("n", [50011, 28673, 14337])
 def test_host_pipeline_ragged_sizes(full, n):
-    """The host-pointer call splits the batch into uniform chunks over an upload, two compute and a download stream; sizes that
+    """The host-pointer call splits the batch into uniform chunks over an upload, several compute and a download stream; sizes that
     do not divide (ragged last chunk), that give an odd chunk count and that fall just above one chunk must return the bits of
     one device call over the same knots (forced split kernels: the chunks run the variant of the whole batch)."""
     import torch
@@ -122,6 +122,31 @@ def test_host_pipeline_ragged_sizes(full, n):
     assert np.array_equal(hs, st.cpu().numpy())
     assert np.array_equal(d, dev.cpu().numpy())
     assert np.array_equal(d, f["deriv"][sl].cpu().numpy())     # and of the full batch's slice
+
+
+@pytest.mark.parametrize("env", [dict(ILQG_HOST_PRIO="0"), dict(ILQG_HOST_PRIO="0", ILQG_HOST_COMP="1"), dict(ILQG_HOST_CHUNKS="7", ILQG_HOST_COMP="3"),
+                                 dict(ILQG_HOST_CHUNKS="12", ILQG_HOST_COMP="8"), dict(ILQG_HOST_CHUNKS="5", ILQG_HOST_COMP="2", ILQG_Q_MIX="37")])
+def test_host_pipeline_stream_layouts(full, pkg, env):
+    """The compute streams of the host-pointer call are a priority ladder by default (chunk c on stream c mod 4, stream j at priority
+    greatest + j); ILQG_HOST_PRIO=0 is round 1's pair of plain alternating streams.  Every layout — more chunks than streams (two
+    chunks share a stream and its work-class scratch), one stream, eight — must return the bits of one device call, pass after pass
+    (a scratch slot shared by two chunks in flight would not necessarily show in one).  The last case also relabels the qpos
+    kernel's CTAs (ILQG_Q_MIX): placement only."""
+    f = full
+    os.environ.update(dict(env, ILQG_FD_VARIANT="3"))
+    try:
+        h = pkg.Handle(pkg.Model.named("hopper"), 0)
+    finally:
+        for k in list(env) + ["ILQG_FD_VARIANT"]:
+            del os.environ[k]
+    n = 40000
+    q, v, u, w = (f[k][:n].cpu().numpy() for k in ("q", "v", "u", "w"))
+    ref = f["deriv"][:n].cpu().numpy()
+    for _ in range(3):
+        d, a, st = h.fd_batch_host(q, v, u, w, f["cost"])
+        assert st.sum() == 0
+        assert np.array_equal(d, ref)
+    h.close()
 
 
 @pytest.mark.parametrize("env", [dict(ILQG_FD_VARIANT="1"), dict(ILQG_FD_VARIANT="1", ILQG_FD_COOP="1"), dict(ILQG_FD_VARIANT="2", ILQG_FD_PDL="0"), dict(ILQG_FD_VARIANT="2"),

@@ -789,6 +789,22 @@ def run_gpu_arm(args):
     for _ in range(npg):
         e2e_step(pageable)
     e2e_pg_s = (time.perf_counter() - t0) * args.steps / npg
+    # the same pageable call with the staging left to the driver (ILQG_HOST_THREADS=0: no pinned mirror, no copy threads)
+    os.environ["ILQG_HOST_THREADS"] = "0"
+    try:
+        h_drv = pkg.Handle(model, local)
+    finally:
+        del os.environ["ILQG_HOST_THREADS"]
+    h_main, h = h, h_drv
+    e2e_step(pageable)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        e2e_step(pageable)
+    e2e_drv_s = (time.perf_counter() - t0) * args.steps / 3
+    h = h_main
+    h_drv.close()
     L.ilqg_set_host_pinning(h._h, 1)   # opt-in: the call page-locks the caller's arrays the first time it sees them
     e2e_step(pageable)
     e2e_step(pageable)
@@ -811,11 +827,11 @@ def run_gpu_arm(args):
     torch.cuda.synchronize()
     d2h_gbs = 5 * nk * model.nd * 8 / (time.perf_counter() - t0) / 1e9
 
-    tt = torch.tensor([total_ms, e2e_s * 1e3, e2e_pg_s * 1e3, -d2h_gbs, e2e_reg_s * 1e3, d2h_gbs], dtype=torch.float64, device=dev)
+    tt = torch.tensor([total_ms, e2e_s * 1e3, e2e_pg_s * 1e3, -d2h_gbs, e2e_reg_s * 1e3, e2e_drv_s * 1e3, d2h_gbs], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(tt[:5], op=dist.ReduceOp.MAX)
-        dist.all_reduce(tt[5:], op=dist.ReduceOp.SUM)
-    d2h_min, d2h_sum, e2e_reg_ms = -float(tt[3]), float(tt[5]), float(tt[4])
+        dist.all_reduce(tt[:6], op=dist.ReduceOp.MAX)
+        dist.all_reduce(tt[6:], op=dist.ReduceOp.SUM)
+    d2h_min, d2h_sum, e2e_reg_ms, e2e_drv_ms = -float(tt[3]), float(tt[6]), float(tt[4]), float(tt[5])
 
     # ---- what the batch is made of, from the kernels' own diagnostics (ilqg_fd_set_diag): contacts, rows, solver iterations
     diag = torch.zeros((nk, 8), dtype=torch.int32, device=dev)
@@ -914,6 +930,7 @@ def run_gpu_arm(args):
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "value_pageable_buffers": world * nk * args.steps / (e2e_pg_ms * 1e-3),
+                        "value_pageable_buffers_driver_staging": world * nk * args.steps / (e2e_drv_ms * 1e-3),
                         "value_pageable_buffers_registered_on_first_use": world * nk * args.steps / (e2e_reg_ms * 1e-3),
                         "host_limit_gbs": d2h_sum, "d2h_gbs_per_gpu_all_ranks_copying": d2h_min,
                         "note": ("the host-pointer call is bound by the device-to-host copy of deriv (892 B per knot): host_limit_gbs is what all "

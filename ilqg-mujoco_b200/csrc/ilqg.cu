@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -21,6 +22,13 @@
 #include <string>
 #include <vector>
 #include <cmath>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 
 #include "dyn.cuh"
 #include "ilqr.cuh"
@@ -1417,6 +1425,113 @@ __global__ void ilqr_pack_first_control_kernel(ilqg::IlqrBuffers b, IlqrSubTable
 // ==================================================================== C ABI
 #define ILQG_HOST_MAXCHUNKS 32
 #define ILQG_HOST_MAXCOMP 8
+// Pageable caller buffers in the host-pointer FD call.  A cudaMemcpyAsync from / to pageable memory is staged by the driver through
+// its own bounce buffers by ONE thread at ~10 GB/s and blocks the calling thread: 86,016 hopper knots take 8 ms instead of 1.8.
+// What a calcMJDerivatives-shaped caller hands over is malloc'ed memory, so the call does that staging itself: a handle-owned pinned
+// mirror of the staging block, and a crew of K host threads that copy slice t of K of every chunk — the inputs of chunk c into the
+// mirror before its upload is issued, its deriv / qacc blocks out of the mirror as soon as its download has landed — while the copy
+// engines and the kernels work on the other chunks.  (ilqg_set_host_pinning page-locks the caller's buffers instead: faster still when
+// the same buffers come back call after call, but it changes the caller's pages; this path changes nothing the caller can see.)
+struct BounceCrew {
+    struct Job { char* dst; const char* src; size_t bytes; };
+    int K = 0, nchunks = 0;
+    std::vector<Job> in_jobs[ILQG_HOST_MAXCHUNKS], out_jobs[ILQG_HOST_MAXCHUNKS];
+    std::atomic<int> in_done[ILQG_HOST_MAXCHUNKS], out_ready[ILQG_HOST_MAXCHUNKS], left{0}, abort{0};
+    bool started = false;
+    BounceCrew() { for (int i = 0; i < ILQG_HOST_MAXCHUNKS; i++) { in_done[i].store(0); out_ready[i].store(0); } }
+    static void wait(const std::atomic<int>& a, int want, const std::atomic<int>& abort) {
+        for (int spin = 0; a.load(std::memory_order_acquire) < want && !abort.load(std::memory_order_relaxed); spin++)
+            if (spin > 2000) std::this_thread::yield();
+    }
+    // a copy that does not pull the destination through the cache (each byte is written once and read by somebody else later):
+    // streaming stores where the pointers allow, memcpy for the rest
+    static void copy_stream(char* dst, const char* src, size_t bytes) {
+#if defined(__x86_64__)
+        if ((((uintptr_t)dst | (uintptr_t)src) & 15) == 0) {
+            const size_t body = bytes & ~(size_t)63;
+            for (size_t o = 0; o < body; o += 64) {
+                const __m128i a = _mm_load_si128((const __m128i*)(src + o)), b = _mm_load_si128((const __m128i*)(src + o + 16)),
+                              c = _mm_load_si128((const __m128i*)(src + o + 32)), d = _mm_load_si128((const __m128i*)(src + o + 48));
+                _mm_stream_si128((__m128i*)(dst + o), a);
+                _mm_stream_si128((__m128i*)(dst + o + 16), b);
+                _mm_stream_si128((__m128i*)(dst + o + 32), c);
+                _mm_stream_si128((__m128i*)(dst + o + 48), d);
+            }
+            _mm_sfence();
+            dst += body; src += body; bytes -= body;
+        }
+#endif
+        if (bytes) memcpy(dst, src, bytes);
+    }
+    static void slice(const Job& j, int t, int K) {   // thread t's part of a job, cut at 4 KB boundaries of the byte range
+        const size_t per = ((j.bytes + K - 1) / K + 4095) & ~(size_t)4095, lo = per * t;
+        if (lo >= j.bytes) return;
+        copy_stream(j.dst + lo, j.src + lo, lo + per <= j.bytes ? per : j.bytes - lo);
+    }
+    void run(int t) {
+        for (int c = 0; c < nchunks && !abort.load(std::memory_order_relaxed); c++) {
+            for (const Job& j : in_jobs[c]) slice(j, t, K);
+            in_done[c].fetch_add(1, std::memory_order_release);
+        }
+        for (int c = 0; c < nchunks; c++) {
+            wait(out_ready[c], 1, abort);
+            if (abort.load(std::memory_order_relaxed)) break;
+            for (const Job& j : out_jobs[c]) slice(j, t, K);
+        }
+        left.fetch_add(1, std::memory_order_release);
+    }
+    void inputs_of(int c) { if (K) wait(in_done[c], K, abort); }
+    void landed(int c) { if (K) out_ready[c].store(1, std::memory_order_release); }
+    void finish() {   // every worker has left run(): nothing points into this object any more
+        if (!started) return;
+        const std::atomic<int> never{0};
+        wait(left, K, never);
+        started = false;
+    }
+    ~BounceCrew() { abort.store(1); finish(); }   // (an early error return: the workers leave at their next wait)
+};
+
+// The crew's threads belong to the handle and sleep between calls (creating eight threads costs ~0.2 ms, a tenth of a call).
+struct CopyPool {
+    std::vector<std::thread> th;
+    std::mutex mu;
+    std::condition_variable cv;
+    BounceCrew* job = nullptr;
+    unsigned gen = 0;
+    bool stop = false;
+    void worker(int t) {
+        unsigned seen = 0;
+        for (;;) {
+            BounceCrew* j;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return stop || gen != seen; });
+                if (stop) return;
+                seen = gen;
+                j = job;
+            }
+            j->run(t);
+        }
+    }
+    void shutdown() {
+        { std::lock_guard<std::mutex> lk(mu); stop = true; }
+        cv.notify_all();
+        for (auto& x : th) if (x.joinable()) x.join();
+        th.clear();
+        stop = false;
+    }
+    void launch(BounceCrew* c) {
+        if ((int)th.size() != c->K) {
+            shutdown();
+            for (int t = 0; t < c->K; t++) th.emplace_back([this, t] { worker(t); });
+        }
+        c->started = true;
+        { std::lock_guard<std::mutex> lk(mu); job = c; gen++; }
+        cv.notify_all();
+    }
+    ~CopyPool() { shutdown(); }
+};
+
 struct ilqg_handle_s {
     void* stage_host = nullptr;      // pinned landing buffer of small packed results (ilqg_ilqr_get_first_control_*_host)
     size_t stage_host_bytes = 0;
@@ -1439,8 +1554,11 @@ struct ilqg_handle_s {
     cudaStream_t pipe[4] = {nullptr, nullptr, nullptr, nullptr};  // upload / compute A / download / compute B streams of the *_host FD entry point
     int host_prio = 1;          // ILQG_HOST_PRIO (0: two plain streams, alternating): compute streams of that pipeline form a priority ladder (comp[])
     cudaStream_t comp[ILQG_HOST_MAXCOMP] = {};   // compute stream j has priority (greatest + j): chunk ci runs on comp[ci % ncomp]
-    cudaEvent_t pipe_ev[2 * ILQG_HOST_MAXCHUNKS] = {};    // per chunk: uploaded, computed
+    cudaEvent_t pipe_ev[3 * ILQG_HOST_MAXCHUNKS] = {};    // per chunk: uploaded, computed (2c, 2c + 1); downloaded (2 MAXCHUNKS + c)
     int* h_stat = nullptr; size_t hstat_cap = 0;          // pinned landing buffer of the status words
+    double* h_bounce = nullptr; size_t bounce_cap = 0;    // pinned mirror of the staging block for PAGEABLE caller buffers (BounceCrew)
+    CopyPool* copy_pool = nullptr;                        // its threads (created on first use)
+    int host_threads = -1;                                // ILQG_HOST_THREADS: copy threads of that path (-1: by core count, 0: off)
     // opt-in (ilqg_set_host_pinning): large caller buffers of the *_host FD call are page-locked (cudaHostRegister) the first time
     // they are seen and stay so until the handle is destroyed — a calcMJDerivatives caller hands the same malloc'ed deriv array
     // every call, and a pageable destination is copied at a fifth of the pinned rate
@@ -1517,6 +1635,7 @@ int ilqg_create(const ilqg_model* m, int device, ilqg_handle* out) {
     if (const char* e = getenv("ILQG_HOST_CHUNKS")) h->host_chunks = atoi(e);
     if (const char* e = getenv("ILQG_HOST_COMP")) h->host_comp_streams = atoi(e);
     if (const char* e = getenv("ILQG_HOST_PRIO")) h->host_prio = atoi(e);
+    if (const char* e = getenv("ILQG_HOST_THREADS")) h->host_threads = atoi(e);
     if (const char* e = getenv("ILQG_PIN_HOST")) h->pin_host = atoi(e) != 0;
     if (cudaMalloc(&h->d_cost, sizeof(ilqg_cost)) != cudaSuccess) {
         delete eng;
@@ -1538,8 +1657,10 @@ int ilqg_destroy(ilqg_handle h) {
     for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i < 4; i++) if (h->pipe[i]) cudaStreamDestroy(h->pipe[i]);
     for (int i = 0; i < ILQG_HOST_MAXCOMP; i++) if (h->comp[i]) cudaStreamDestroy(h->comp[i]);
-    for (int i = 0; i < 2 * ILQG_HOST_MAXCHUNKS; i++) if (h->pipe_ev[i]) cudaEventDestroy(h->pipe_ev[i]);
+    for (int i = 0; i < 3 * ILQG_HOST_MAXCHUNKS; i++) if (h->pipe_ev[i]) cudaEventDestroy(h->pipe_ev[i]);
     if (h->h_stat) cudaFreeHost(h->h_stat);
+    delete h->copy_pool;
+    if (h->h_bounce) cudaFreeHost(h->h_bounce);
     if (h->stage_host) cudaFreeHost(h->stage_host);
     for (auto& r : h->regs) cudaHostUnregister(const_cast<void*>(r.p));
     delete h->eng;
@@ -1871,7 +1992,60 @@ int ilqg_fd_batch_host(ilqg_handle h, int nknots, const double* qpos, const doub
     }
     if (!h->pipe[0]) {
         for (int i = 0; i < 4; i++) CU(h, cudaStreamCreateWithFlags(&h->pipe[i], cudaStreamNonBlocking));
-        for (int i = 0; i < 2 * ILQG_HOST_MAXCHUNKS; i++) CU(h, cudaEventCreateWithFlags(&h->pipe_ev[i], cudaEventDisableTiming));
+        for (int i = 0; i < 3 * ILQG_HOST_MAXCHUNKS; i++) CU(h, cudaEventCreateWithFlags(&h->pipe_ev[i], cudaEventDisableTiming));
+    }
+    // pageable caller buffers go through the pinned mirror (BounceCrew); h* = where the copy engines read / write
+    BounceCrew crew;
+    const double *hq = qpos, *hv = qvel, *hu = ctrl, *hw = warmstart;
+    double *hd = deriv, *ha = qacc_out;
+    {
+        int K = h->host_threads;
+        if (K < 0) {
+            const unsigned hc = std::thread::hardware_concurrency();
+            K = hc >= 16 ? 8 : (hc >= 8 ? 4 : (hc >= 4 ? 2 : 0));
+        }
+        if (K > 16) K = 16;
+        auto pageable = [](const void* p) {
+            if (!p) return false;
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return true; }
+            return at.type == cudaMemoryTypeUnregistered;
+        };
+        if (K > 0 && n * nd * sizeof(double) >= ((size_t)4 << 20)) {
+            const bool pq = pageable(qpos), pv = pageable(qvel), pu = nu && pageable(ctrl), pw = pageable(warmstart), pd = pageable(deriv),
+                       pa = pageable(qacc_out);
+            if (pq || pv || pu || pw || pd || pa) {
+                if (ndbl > h->bounce_cap) {
+                    if (h->h_bounce) cudaFreeHost(h->h_bounce);
+                    h->h_bounce = nullptr;
+                    h->bounce_cap = 0;
+                    CU(h, cudaHostAlloc((void**)&h->h_bounce, ndbl * sizeof(double), cudaHostAllocDefault));
+                    h->bounce_cap = ndbl;
+                }
+                double* m = h->h_bounce;
+                if (pq) hq = m + off_q;
+                if (pv) hv = m + off_v;
+                if (pu) hu = m + off_u;
+                if (pw) hw = m + off_w;
+                if (pd) hd = m + off_d;
+                if (pa) ha = m + off_a;
+                size_t lo = 0;
+                for (size_t ci = 0; ci < nchunks; lo += csize[ci], ci++) {
+                    const size_t cn = csize[ci];
+                    auto in = [&](bool on, size_t off, const double* src, size_t w) {
+                        if (on) crew.in_jobs[ci].push_back({(char*)(m + off + lo * w), (const char*)(src + lo * w), cn * w * sizeof(double)});
+                    };
+                    in(pq, off_q, qpos, nq); in(pv, off_v, qvel, nv); in(pu, off_u, ctrl, nu); in(pw, off_w, warmstart, nv);
+                    if (!cost) in(pd, off_d, deriv, nd);   // the caller's cost-gradient entries ride up with the block
+                    if (pd) crew.out_jobs[ci].push_back({(char*)(deriv + lo * nd), (const char*)(m + off_d + lo * nd), cn * nd * sizeof(double)});
+                    if (pa) crew.out_jobs[ci].push_back({(char*)(qacc_out + lo * nv), (const char*)(m + off_a + lo * nv), cn * nv * sizeof(double)});
+                }
+                crew.K = K;
+                crew.nchunks = (int)nchunks;
+                if (!h->copy_pool) h->copy_pool = new CopyPool;
+                h->copy_pool->launch(&crew);
+            }
+        }
     }
     cudaStream_t up = h->pipe[0], down = h->pipe[2];
     int ncomp = overlap ? h->host_comp_streams : 1;
@@ -1894,13 +2068,14 @@ int ilqg_fd_batch_host(ilqg_handle h, int nknots, const double* qpos, const doub
     size_t lo = 0;
     for (int ci = 0; ci < (int)nchunks; lo += csize[ci], ci++) {
         const size_t cn = csize[ci];
-        CU(h, cudaMemcpyAsync(b + off_q + lo * nq, qpos + lo * nq, cn * nq * sizeof(double), cudaMemcpyHostToDevice, up));
-        CU(h, cudaMemcpyAsync(b + off_v + lo * nv, qvel + lo * nv, cn * nv * sizeof(double), cudaMemcpyHostToDevice, up));
-        if (nu) CU(h, cudaMemcpyAsync(b + off_u + lo * nu, ctrl + lo * nu, cn * nu * sizeof(double), cudaMemcpyHostToDevice, up));
-        if (warmstart) CU(h, cudaMemcpyAsync(b + off_w + lo * nv, warmstart + lo * nv, cn * nv * sizeof(double), cudaMemcpyHostToDevice, up));
+        crew.inputs_of(ci);   // (pageable inputs: the chunk's slices are in the pinned mirror)
+        CU(h, cudaMemcpyAsync(b + off_q + lo * nq, hq + lo * nq, cn * nq * sizeof(double), cudaMemcpyHostToDevice, up));
+        CU(h, cudaMemcpyAsync(b + off_v + lo * nv, hv + lo * nv, cn * nv * sizeof(double), cudaMemcpyHostToDevice, up));
+        if (nu) CU(h, cudaMemcpyAsync(b + off_u + lo * nu, hu + lo * nu, cn * nu * sizeof(double), cudaMemcpyHostToDevice, up));
+        if (warmstart) CU(h, cudaMemcpyAsync(b + off_w + lo * nv, hw + lo * nv, cn * nv * sizeof(double), cudaMemcpyHostToDevice, up));
         else CU(h, cudaMemsetAsync(b + off_w + lo * nv, 0, cn * nv * sizeof(double), up));
         if (!cost)  // keep the caller's cost-gradient entries
-            CU(h, cudaMemcpyAsync(b + off_d + lo * nd, deriv + lo * nd, cn * nd * sizeof(double), cudaMemcpyHostToDevice, up));
+            CU(h, cudaMemcpyAsync(b + off_d + lo * nd, hd + lo * nd, cn * nd * sizeof(double), cudaMemcpyHostToDevice, up));
         // compute stream of the chunk.  Two plain streams, alternating (default); or a priority ladder (ILQG_HOST_PRIO=1,
         // ILQG_HOST_COMP = streams): chunk ci on stream ci % ncomp, stream j at priority greatest + j — with as many streams as chunks the
         // CTA scheduler always prefers the EARLIEST chunk's pending CTAs (the chunk the download is waiting for) and later chunks
@@ -1917,9 +2092,17 @@ int ilqg_fd_batch_host(ilqg_handle h, int nknots, const double* qpos, const doub
         if (rc) return rc;
         CU(h, cudaEventRecord(h->pipe_ev[2 * ci + 1], comp));
         CU(h, cudaStreamWaitEvent(down, h->pipe_ev[2 * ci + 1], 0));
-        CU(h, cudaMemcpyAsync(deriv + lo * nd, b + off_d + lo * nd, cn * nd * sizeof(double), cudaMemcpyDeviceToHost, down));
-        if (qacc_out) CU(h, cudaMemcpyAsync(qacc_out + lo * nv, b + off_a + lo * nv, cn * nv * sizeof(double), cudaMemcpyDeviceToHost, down));
+        CU(h, cudaMemcpyAsync(hd + lo * nd, b + off_d + lo * nd, cn * nd * sizeof(double), cudaMemcpyDeviceToHost, down));
+        if (qacc_out) CU(h, cudaMemcpyAsync(ha + lo * nv, b + off_a + lo * nv, cn * nv * sizeof(double), cudaMemcpyDeviceToHost, down));
         CU(h, cudaMemcpyAsync(h->h_stat + lo, dstat + lo, cn * sizeof(int), cudaMemcpyDeviceToHost, down));
+        if (crew.K) CU(h, cudaEventRecord(h->pipe_ev[2 * ILQG_HOST_MAXCHUNKS + ci], down));
+    }
+    if (crew.K) {   // hand every chunk to the crew as its download lands; the crew's last slice ends the call
+        for (int ci = 0; ci < (int)nchunks; ci++) {
+            CU(h, cudaEventSynchronize(h->pipe_ev[2 * ILQG_HOST_MAXCHUNKS + ci]));
+            crew.landed(ci);
+        }
+        crew.finish();
     }
     CU(h, cudaStreamSynchronize(down));   // the last download follows every upload and every kernel
     int bad = 0;

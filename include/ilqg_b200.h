@@ -109,7 +109,10 @@ int ilqg_fd_batch_host(ilqg_handle h, int nknots, const double* qpos, const doub
                        const double* warmstart, const ilqg_cost* cost, const ilqg_fd_opts* opts, double* deriv,
                        double* qacc_out, int* status);
 
-/* opt-in: page-lock the caller's large host buffers of ilqg_fd_batch_host (cudaHostRegister) the first time they are seen; they
+/* Pageable caller buffers of ilqg_fd_batch_host (what a calcMJDerivatives caller's malloc'ed arrays are): batches of 4 MB and more are
+ * staged by the call itself through a pinned mirror owned by the handle, by ILQG_HOST_THREADS copy threads (default by core count,
+ * 0 = the driver's single-threaded staging) working chunk by chunk beside the copy engines; nothing changes for the caller.
+ * opt-in: page-lock the caller's large host buffers of ilqg_fd_batch_host (cudaHostRegister) the first time they are seen; they
  * stay registered until ilqg_set_host_pinning(h, 0) or ilqg_destroy.  The reference's caller owns one malloc'ed deriv array for the
  * life of a Differentiator (/root/reference/inc/differentiator.h:56): pageable memory is copied device-to-host at about a fifth of
  * the pinned rate.  The caller must not free a registered buffer while the handle lives (or must switch pinning off first). */

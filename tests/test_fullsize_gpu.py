@@ -125,7 +125,8 @@ def test_host_pipeline_ragged_sizes(full, n):
 
 
 @pytest.mark.parametrize("env", [dict(ILQG_HOST_PRIO="0"), dict(ILQG_HOST_PRIO="0", ILQG_HOST_COMP="1"), dict(ILQG_HOST_CHUNKS="7", ILQG_HOST_COMP="3"),
-                                 dict(ILQG_HOST_CHUNKS="12", ILQG_HOST_COMP="8"), dict(ILQG_HOST_CHUNKS="5", ILQG_HOST_COMP="2", ILQG_Q_MIX="37")])
+                                 dict(ILQG_HOST_CHUNKS="12", ILQG_HOST_COMP="8"), dict(ILQG_HOST_CHUNKS="5", ILQG_HOST_COMP="2", ILQG_Q_MIX="37"),
+                                 dict(ILQG_HOST_THREADS="0"), dict(ILQG_HOST_THREADS="3", ILQG_HOST_CHUNKS="6")])
 def test_host_pipeline_stream_layouts(full, pkg, env):
     """The compute streams of the host-pointer call are a priority ladder by default (chunk c on stream c mod 4, stream j at priority
     greatest + j); ILQG_HOST_PRIO=0 is round 1's pair of plain alternating streams.  Every layout — more chunks than streams (two
@@ -147,6 +148,30 @@ def test_host_pipeline_stream_layouts(full, pkg, env):
         assert st.sum() == 0
         assert np.array_equal(d, ref)
     h.close()
+
+
+def test_host_pipeline_pageable_and_pinned_buffers(full, pkg):
+    """The arrays above are numpy arrays: PAGEABLE memory, which the call stages itself through a pinned mirror with a crew of copy
+    threads (ILQG_HOST_THREADS=0: the driver's staging).  Same bits with page-locked caller buffers, with a mix of both, and without
+    a device cost — then the caller's cost-gradient entries ride up with the deriv block and must come back untouched, and the
+    Jacobian entries equal the ones computed with a cost."""
+    import torch
+    f = full; h = f["h"]; m = h.model
+    n = 30011
+    q, v, u, w = (f[k][:n].cpu() for k in ("q", "v", "u", "w"))
+    ref = f["deriv"][:n].cpu().numpy()
+    d_page, a_page, st = h.fd_batch_host(q.numpy(), v.numpy(), u.numpy(), w.numpy(), f["cost"])
+    assert st.sum() == 0 and np.array_equal(d_page, ref)
+    pin = [t.pin_memory() for t in (q, v, u, w)]
+    d_pin = torch.zeros((n, m.nd), dtype=torch.float64).pin_memory()
+    out, a_pin, st = h.fd_batch_host(*(t.numpy() for t in pin), f["cost"], deriv=d_pin.numpy())
+    assert st.sum() == 0 and np.array_equal(d_pin.numpy(), ref) and np.array_equal(a_pin, a_page)
+    d_mix, a_mix, st = h.fd_batch_host(pin[0].numpy(), v.numpy(), pin[2].numpy(), w.numpy(), f["cost"])   # pinned qpos / ctrl, pageable rest
+    assert st.sum() == 0 and np.array_equal(d_mix, ref)
+    njac = m.nv * (2 * m.nv + m.nu)
+    mine = np.full((n, m.nd), 7.25)
+    d_nc, _, st = h.fd_batch_host(q.numpy(), v.numpy(), u.numpy(), w.numpy(), None, deriv=mine)
+    assert st.sum() == 0 and np.array_equal(d_nc[:, :njac], ref[:, :njac]) and (d_nc[:, njac:] == 7.25).all()
 
 
 @pytest.mark.parametrize("env", [dict(ILQG_FD_VARIANT="1"), dict(ILQG_FD_VARIANT="1", ILQG_FD_COOP="1"), dict(ILQG_FD_VARIANT="2", ILQG_FD_PDL="0"), dict(ILQG_FD_VARIANT="2"),

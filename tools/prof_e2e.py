@@ -37,6 +37,26 @@ for spec in sys.argv[1:] or ["-"]:
     dt = (time.perf_counter() - t0) / 30
     h.close()
     print(f"chunks:streams:ladder={spec}: {dt*1e3:.3f} ms/step -> {nk/dt/1e6:.2f} M knots/s e2e; D2H {nk*(model.nd+model.nv)*8/dt/1e9:.1f} GB/s")
+# the same call with PAGEABLE caller buffers (numpy / malloc'ed memory, what a calcMJDerivatives-shaped caller has): the call's own
+# pinned mirror + copy threads (ILQG_HOST_THREADS; 0 = leave the staging to the driver)
+pq, pv, pu, pw = (t.cpu().numpy().copy() for t in (q, v, u, w))
+pd = np.zeros((nk, model.nd)); pa = np.zeros((nk, model.nv)); ps = np.zeros(nk, dtype=np.int32)
+def pstep():
+    L.ilqg_fd_batch_host(h._h, nk, pq.ctypes.data_as(C.c_void_p), pv.ctypes.data_as(C.c_void_p), pu.ctypes.data_as(C.c_void_p), pw.ctypes.data_as(C.c_void_p),
+                         cost.ctypes.data_as(C.c_void_p), None, pd.ctypes.data_as(C.c_void_p), pa.ctypes.data_as(C.c_void_p), ps.ctypes.data_as(C.c_void_p))
+for key in ("ILQG_HOST_CHUNKS", "ILQG_HOST_COMP", "ILQG_HOST_PRIO"):
+    os.environ.pop(key, None)
+for th in os.environ.get("ILQG_E2E_THREADS", "-1,0,2,4,8,16").split(","):
+    os.environ["ILQG_HOST_THREADS"] = th
+    h = pkg.Handle(model, 0)
+    for _ in range(3): pstep()
+    t0 = time.perf_counter()
+    for _ in range(20): pstep()
+    dt = (time.perf_counter() - t0) / 20
+    h.close()
+    same = bool(np.array_equal(pd, hd.numpy()))
+    print(f"pageable buffers, copy threads={th}: {dt*1e3:.3f} ms/step -> {nk/dt/1e6:.2f} M knots/s e2e; equals the pinned call's deriv: {same}")
+os.environ.pop("ILQG_HOST_THREADS", None)
 # raw PCIe rates for reference
 d = torch.empty(nk * model.nd, dtype=torch.float64, device="cuda:0")
 for name, fn in (("D2H", lambda: hd.view(-1).copy_(d, non_blocking=True)), ("H2D", lambda: d.copy_(hd.view(-1), non_blocking=True))):

@@ -211,7 +211,7 @@ def ilqr_reference_classes_rate():
     return 30.0 / (r_b - r_a), 1e3 * (r_b - r_a) / 3
 
 
-def bench_ilqr(pkg, dev_index, ninst, niter, reps, world, rank, with_cpu):
+def bench_ilqr(pkg, dev_index, ninst, niter, reps, world, rank, with_cpu, seed_rank=None):
     """BASELINE configs[3] — the second half of the headline metric: 4096 independent inverted-pendulum iLQR problems (N = 20),
     `niter` x ILQR::iterate each, all on the device: rollouts + FD of 21 knots + Riccati per iteration.  Reference mode (alpha = 1
     accepted unconditionally).  ilqg_ilqr_iterate replays a captured CUDA graph of the niter iterations."""
@@ -222,7 +222,7 @@ def bench_ilqr(pkg, dev_index, ninst, niter, reps, world, rank, with_cpu):
     model = pkg.Model.named("inverted_pendulum")
     h = pkg.Handle(model, dev_index)
     L = pkg.lib()
-    q, v, u, _ = wl.pendulum_initial_states(ninst, seed=100 + rank)
+    q, v, u, _ = wl.pendulum_initial_states(ninst, seed=100 + (rank if seed_rank is None else seed_rank))
     u = u * 0.0
     dq, dv, du = (torch.from_numpy(a).to(dev) for a in (q, v, u))
     dw = torch.zeros((ninst, 2), dtype=torch.float64, device=dev)
@@ -317,6 +317,14 @@ def bench_ilqr(pkg, dev_index, ninst, niter, reps, world, rank, with_cpu):
                            "note": "knot inputs + deriv blocks + candidate / nominal trajectory writes per iteration: far below the HBM roof, the iteration is latency-bound"}
     il.close()
     h.close()
+    if world > 1 and seed_rank is None:
+        # A batch iteration lasts as long as its slowest problem (a latency chain per problem), and that depends on the starts drawn:
+        # 0.213 - 0.280 ms for the seeds 100..107 run one after the other on ONE GPU (tools/prof_ilqr_seeds.py).  `value` above takes the
+        # max over ranks that each drew their own starts; this is the same measurement with every rank solving rank 0's problems —
+        # equal work per GPU, the figure that says how the path scales.
+        same = bench_ilqr(pkg, dev_index, ninst, niter, reps, world, rank, with_cpu=False, seed_rank=0)
+        res["value_same_starts_on_every_rank"] = same["value"]
+        res["ms_per_batch_iteration_same_starts_min_median_max_over_ranks"] = same["ms_per_batch_iteration_min_median_max_over_ranks"]
     return res
 
 

@@ -1409,6 +1409,14 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, 
 // ------------------------------------------------------------------ iLQR results of a blocked workspace, packed for one copy
 struct IlqrSubTable { int nsub; int i0[17]; };
 // thread per instance: its first control (knot N of its block, time-major inside the block) and the last `kept` slots of its cost trace
+// u*_n = the same control at every knot of a block's nominal ([T][ni][nu]): the state ILQR::ILQR starts from (ilqr.h:69-97)
+__global__ void ilqr_broadcast_ctrl_kernel(double* __restrict__ nom_u, const double* __restrict__ ctrl, int T, int per) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= per) return;
+    const double c = ctrl ? ctrl[e] : 0.0;
+    for (int t = 0; t < T; t++) nom_u[(size_t)t * per + e] = c;
+}
+
 __global__ void ilqr_pack_first_control_kernel(ilqg::IlqrBuffers b, IlqrSubTable tab, const double* __restrict__ Jtrace, int nu, int kept, int first_slot,
                                                double* __restrict__ u0, double* __restrict__ Jt) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -2445,9 +2453,9 @@ int ilqg_ilqr_init_dev(ilqg_ilqr w, const double* qpos, const double* qvel, cons
         ilqg::IlqrBuffers one = ilqr_sub_view(w, sb);
         cudaStream_t ss = ilqr_stream_of(w, sb, s);
         const size_t i0 = w->sub_i0[sb], ni = one.ninst;
-        for (size_t t = 0; t < T && nu > 0; t++) {  // u*_n = the initial control at every knot
-            if (ctrl) CU(h, cudaMemcpyAsync(one.nom_u + t * ni * nu, ctrl + i0 * nu, sizeof(double) * ni * nu, cudaMemcpyDeviceToDevice, ss));
-            else CU(h, cudaMemsetAsync(one.nom_u + t * ni * nu, 0, sizeof(double) * ni * nu, ss));
+        if (nu > 0) {   // u*_n = the initial control at every knot (one launch per block: T copies per block were 1 ms of API calls at 12 blocks)
+            const int per = (int)(ni * nu);
+            ilqr_broadcast_ctrl_kernel<<<(per + 255) / 256, 256, 0, ss>>>(one.nom_u, ctrl ? ctrl + i0 * nu : nullptr, (int)T, per);
         }
         one.nalpha = 1;  // alphas[0] multiplies k = 0: any value gives the open-loop rollout
         one.mu_i = nullptr;  // the constructor's rollout is not a line-search outcome: the mu schedule does not move

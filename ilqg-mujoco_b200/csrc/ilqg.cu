@@ -913,7 +913,11 @@ struct EngineT : Engine {
     // latency floor of 0.18 ms (a stance CTA's 6 sequential solves), the single launch none.
     // (a tree without collision pairs — the inverted pendulum — has no position stage worth sharing: at 86,016 knots the single-launch
     //  column kernel behind the centre's programmatic launch takes 0.054 ms against the split's 0.062)
-    static constexpr int SPLIT_MIN = T::NPAIR > 0 ? 24576 : (1 << 22);
+    // Round 2, back-to-back passes (tools/prof_split_threshold.py; us, centre + single column kernel / split): SURVEY-8d mix (51 % contact)
+    // 20,480 knots 347 / 364, 21,504 370 / 378, 24,576 440 / 401; stance-heavy batch 16,384 466 / 464, 21,504 600 / 524, 24,576 671 / 552.  The
+    // crossover moves with the share of stance knots; from 21,504 knots (1024 problems x 21: the hopper iLQR workspace of the bench) the split
+    // loses 2 % on the mixed batch and wins 13 % on the stance one.
+    static constexpr int SPLIT_MIN = T::NPAIR > 0 ? 21504 : (1 << 22);
     // below this the batch cannot fill the GPU and the one-launch kernel (centre on a spare lane of its knot's warp) has the
     // shortest chain; above it the lone centre lane costs throughput (ILQG_FD_FUSED_MAX overrides; measured on B200)
     int fused_max = FdFusedShape<T>::OK ? 64 : 0;

@@ -23,6 +23,7 @@
 #include <vector>
 #include <cmath>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <thread>
@@ -1452,8 +1453,11 @@ struct BounceCrew {
     bool started = false;
     BounceCrew() { for (int i = 0; i < ILQG_HOST_MAXCHUNKS; i++) { in_done[i].store(0); out_ready[i].store(0); } }
     static void wait(const std::atomic<int>& a, int want, const std::atomic<int>& abort) {
-        for (int spin = 0; a.load(std::memory_order_acquire) < want && !abort.load(std::memory_order_relaxed); spin++)
-            if (spin > 2000) std::this_thread::yield();
+        for (int spin = 0; a.load(std::memory_order_acquire) < want && !abort.load(std::memory_order_relaxed);) {
+            if (spin < 100000) spin++;
+            if (spin >= 100000) std::this_thread::sleep_for(std::chrono::microseconds(50));   // (a pass of seconds: stop burning the core)
+            else if (spin > 2000) std::this_thread::yield();
+        }
     }
     // a copy that does not pull the destination through the cache (each byte is written once and read by somebody else later):
     // streaming stores where the pointers allow, memcpy for the rest
@@ -2027,35 +2031,50 @@ int ilqg_fd_batch_host(ilqg_handle h, int nknots, const double* qpos, const doub
             const bool pq = pageable(qpos), pv = pageable(qvel), pu = nu && pageable(ctrl), pw = pageable(warmstart), pd = pageable(deriv),
                        pa = pageable(qacc_out);
             if (pq || pv || pu || pw || pd || pa) {
+                // (no pinned mirror or no threads to be had: the call still works, with the staging left to the driver)
+                bool ok = true;
                 if (ndbl > h->bounce_cap) {
                     if (h->h_bounce) cudaFreeHost(h->h_bounce);
                     h->h_bounce = nullptr;
                     h->bounce_cap = 0;
-                    CU(h, cudaHostAlloc((void**)&h->h_bounce, ndbl * sizeof(double), cudaHostAllocDefault));
-                    h->bounce_cap = ndbl;
+                    if (cudaHostAlloc((void**)&h->h_bounce, ndbl * sizeof(double), cudaHostAllocDefault) == cudaSuccess) h->bounce_cap = ndbl;
+                    else { cudaGetLastError(); h->h_bounce = nullptr; ok = false; }
                 }
-                double* m = h->h_bounce;
-                if (pq) hq = m + off_q;
-                if (pv) hv = m + off_v;
-                if (pu) hu = m + off_u;
-                if (pw) hw = m + off_w;
-                if (pd) hd = m + off_d;
-                if (pa) ha = m + off_a;
-                size_t lo = 0;
-                for (size_t ci = 0; ci < nchunks; lo += csize[ci], ci++) {
-                    const size_t cn = csize[ci];
-                    auto in = [&](bool on, size_t off, const double* src, size_t w) {
-                        if (on) crew.in_jobs[ci].push_back({(char*)(m + off + lo * w), (const char*)(src + lo * w), cn * w * sizeof(double)});
-                    };
-                    in(pq, off_q, qpos, nq); in(pv, off_v, qvel, nv); in(pu, off_u, ctrl, nu); in(pw, off_w, warmstart, nv);
-                    if (!cost) in(pd, off_d, deriv, nd);   // the caller's cost-gradient entries ride up with the block
-                    if (pd) crew.out_jobs[ci].push_back({(char*)(deriv + lo * nd), (const char*)(m + off_d + lo * nd), cn * nd * sizeof(double)});
-                    if (pa) crew.out_jobs[ci].push_back({(char*)(qacc_out + lo * nv), (const char*)(m + off_a + lo * nv), cn * nv * sizeof(double)});
+                if (ok) {
+                    double* m = h->h_bounce;
+                    size_t lo = 0;
+                    for (size_t ci = 0; ci < nchunks; lo += csize[ci], ci++) {
+                        const size_t cn = csize[ci];
+                        auto in = [&](bool on, size_t off, const double* src, size_t w) {
+                            if (on) crew.in_jobs[ci].push_back({(char*)(m + off + lo * w), (const char*)(src + lo * w), cn * w * sizeof(double)});
+                        };
+                        in(pq, off_q, qpos, nq); in(pv, off_v, qvel, nv); in(pu, off_u, ctrl, nu); in(pw, off_w, warmstart, nv);
+                        if (!cost) in(pd, off_d, deriv, nd);   // the caller's cost-gradient entries ride up with the block
+                        if (pd) crew.out_jobs[ci].push_back({(char*)(deriv + lo * nd), (const char*)(m + off_d + lo * nd), cn * nd * sizeof(double)});
+                        if (pa) crew.out_jobs[ci].push_back({(char*)(qacc_out + lo * nv), (const char*)(m + off_a + lo * nv), cn * nv * sizeof(double)});
+                    }
+                    crew.K = K;
+                    crew.nchunks = (int)nchunks;
+                    try {
+                        if (!h->copy_pool) h->copy_pool = new CopyPool;
+                        h->copy_pool->launch(&crew);
+                    } catch (...) {   // thread creation failed: drop the pool (its destructor joins what did start) and the crew's work
+                        delete h->copy_pool;
+                        h->copy_pool = nullptr;
+                        crew.K = 0;
+                        crew.started = false;
+                        ok = false;
+                    }
                 }
-                crew.K = K;
-                crew.nchunks = (int)nchunks;
-                if (!h->copy_pool) h->copy_pool = new CopyPool;
-                h->copy_pool->launch(&crew);
+                if (ok) {
+                    double* m = h->h_bounce;
+                    if (pq) hq = m + off_q;
+                    if (pv) hv = m + off_v;
+                    if (pu) hu = m + off_u;
+                    if (pw) hw = m + off_w;
+                    if (pd) hd = m + off_d;
+                    if (pa) ha = m + off_a;
+                }
             }
         }
     }

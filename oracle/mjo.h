@@ -11,8 +11,14 @@
  * against 2.0.0) is absent from /root/reference and from this image, and the reference has no
  * golden vectors: PARITY WITH UPSTREAM MUJOCO IS UNPINNED.  What pins this oracle instead:
  * closed-form cart-pole dynamics, energy conservation, compiler-vs-CRBA mass matrix cross-checks
- * and KKT residuals of the contact solve (tests/test_oracle_*.py), and the reference's own FD
- * driver compiled verbatim against the shim in oracle/shim/ (oracle/_ref, built by oracle/Makefile).
+ * and KKT residuals of the contact solve; everything re-derived from the TEXT of the MJCF files and
+ * textbook mechanics — body mass / centre of mass / inertia by quadrature, forward kinematics, the
+ * mass matrix as the Hessian of the kinetic energy, bias forces from Lagrange's equations, qacc_smooth
+ * by the articulated-body algorithm, every contact of the narrow phase, the rows of every contact and
+ * the solver parameters of every row, the constraint solve as the unique minimiser of its convex
+ * problem, the RK4 and semi-implicit Euler steps (tests/test_oracle_*.py); and the reference's own FD
+ * driver and iLQR classes compiled verbatim against the shim in oracle/shim/ (oracle/_ref, built by
+ * oracle/Makefile).  tools/mujoco_fixtures.py writes the fixtures that would pin it to MuJoCo itself.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * use anything under oracle/.

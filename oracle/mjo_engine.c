@@ -1,5 +1,5 @@
 /* mjo_engine.c — CPU ORACLE (test infrastructure): fp64 restatement of MuJoCo 2.x forward
- * dynamics for the MJCF subset of /root/reference/res/*.xml.  See mjo.h for what pins it.
+ * dynamics for the MJCF subset of /root/reference/res/ (the three .xml models).  See mjo.h for what pins it.
  *
  * Follows the stage structure of mj_forwardSkip as the reference uses it
  * (/root/reference/src/mjderivative.cpp:64,68,92,124,178): position stage (kinematics, com,

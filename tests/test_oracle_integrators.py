@@ -100,3 +100,77 @@ def test_hopper_euler_trajectory_is_that_update_repeated(oracle, omodels):
         v = v + h * np.linalg.solve(d["qM"] + h * np.diag(damp), d["qM"] @ d["qacc"])
         q = q + h * v
     assert np.allclose(qo[0], q, rtol=0, atol=1e-12) and np.allclose(vo[0], v, rtol=0, atol=1e-11)
+
+
+# ------------------------------------------------------------------ quaternions: mju_quatIntegrate and the free joint's position update
+def qmul(a, b):
+    return np.array([a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3], a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2],
+                     a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1], a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0]])
+
+
+def q2m(q):
+    w, x, y, z = q
+    return np.array([[w * w + x * x - y * y - z * z, 2 * (x * y - w * z), 2 * (x * z + w * y)], [2 * (x * y + w * z), w * w - x * x + y * y - z * z, 2 * (y * z - w * x)],
+                     [2 * (x * z - w * y), 2 * (y * z + w * x), w * w - x * x - y * y + z * z]])
+
+
+def quat_integrate(oracle, q, w, s):
+    import ctypes as C
+    out = np.array(q, np.float64)
+    oracle.lib().mjo_quat_integrate(oracle._p(out), oracle._p(np.ascontiguousarray(w, np.float64)), C.c_double(s))
+    return out
+
+
+def test_quat_integrate_is_a_rotation_about_a_body_axis(oracle):
+    """mju_quatIntegrate(q, w, s) (the FD perturbation of ball / free rotations, /root/reference/src/mjderivative.cpp:152-169, and
+    mj_integratePos): q (x) [cos(|w| s / 2), sin(|w| s / 2) w / |w|] — in matrices R(q') = R(q) expm([w s]x), the angular velocity
+    expressed in the BODY frame; unit norm kept; zero velocity is the identity."""
+    from scipy.linalg import expm
+    rng = np.random.default_rng(8)
+    for _ in range(50):
+        q = rng.normal(size=4); q /= np.linalg.norm(q)
+        w = rng.normal(size=3) * 10.0 ** rng.uniform(-6, 1); s = 10.0 ** rng.uniform(-6, 0)
+        got = quat_integrate(oracle, q, w, s)
+        ang = np.linalg.norm(w) * s
+        want = qmul(q, np.concatenate([[np.cos(ang / 2)], np.sin(ang / 2) * w / np.linalg.norm(w)]))
+        assert np.allclose(got, want, rtol=0, atol=1e-14)
+        assert abs(np.linalg.norm(got) - 1) < 1e-14
+        W = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]]) * s
+        assert np.allclose(q2m(got), q2m(q) @ expm(W), rtol=0, atol=1e-12)
+    q = np.array([0.5, -0.5, 0.5, 0.5])
+    assert np.array_equal(quat_integrate(oracle, q, np.zeros(3), 1.0), q)
+
+
+def test_humanoid_euler_step_with_its_free_joint(oracle, omodels, pkg):
+    """One step of the humanoid (integrator Euler, timestep 0.005) from random moving states, contacts and joint limits included:
+    (M + h diag(damping)) a' = M a with the damping attributes of the XML text, v' = v + h a', and mj_integratePos — the root's position
+    by the world-frame linear velocity, its quaternion by mju_quatIntegrate with the body-frame angular velocity, scalar joints added."""
+    path = os.path.join(RES, "humanoid.xml")
+    if not os.path.exists(path):
+        pytest.skip("reference MJCF files not present on this machine")
+    root = ET.parse(path).getroot()
+    dflt = float(root.find("default").find("joint").get("damping", "0"))
+    damp = np.concatenate([np.zeros(6), [float(j.get("damping", dflt)) for j in root.iter("joint") if j.get("name")]])
+    m = omodels["humanoid"]
+    pm = pkg.Model.named("humanoid")
+    assert damp.shape == (27,)
+    h = 0.005
+    rng = np.random.default_rng(9)
+    rngs = pm.field("jnt_range").reshape(-1, 2)[:pm.njnt]
+    for trial in range(6):
+        q = pm.field("qpos0")[:28].copy()
+        q[2] = rng.uniform(0.3, 1.6)
+        w = rng.normal(0, 1.0, 3); ang = np.linalg.norm(w)
+        q[3:7] = np.concatenate([[np.cos(ang / 2)], np.sin(ang / 2) * w / ang])
+        q[7:] = rng.uniform(rngs[1:, 0], rngs[1:, 1])
+        v = rng.normal(0, 1.0, 27); u = rng.uniform(-0.4, 0.4, 21)
+        d = oracle.dump(m, q, v, u, iterations=50, tolerance=1e-10)      # the XML's own solver settings, as mj_step uses them
+        a2 = np.linalg.solve(d["qM"] + h * np.diag(damp), d["qM"] @ d["qacc"])
+        v2 = v + h * a2
+        q2 = q.copy()
+        q2[:3] += h * v2[:3]
+        q2[3:7] = quat_integrate(oracle, q[3:7], v2[3:6], h)
+        q2[7:] += h * v2[6:]
+        qo, vo, _, _ = oracle.step_batch(m, q[None], v[None], u[None], np.zeros((1, 27)), 1)
+        assert np.allclose(vo[0], v2, rtol=0, atol=1e-9 * max(1.0, np.abs(v2).max())), trial
+        assert np.allclose(qo[0], q2, rtol=0, atol=1e-11 * max(1.0, np.abs(v2).max())), trial
